@@ -1,0 +1,200 @@
+/*
+ * jaxoplanet_b200 -- C ABI of the B200 (sm_100a) kernels for jaxoplanet's hot path.
+ *
+ * The reference (exoplanet-dev/jaxoplanet) is pure Python/JAX and has no native
+ * interface; the boundary a drop-in has to honour is its Python API.  Each entry
+ * point below names the reference callable it stands behind (paths relative to the
+ * reference checkout).  The Python facade in jaxoplanet_b200/ keeps the reference
+ * signatures and reaches these symbols through ctypes; an XLA FFI handler is a thin
+ * argument-marshalling wrapper over the same symbols.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer is DEVICE memory owned by the caller
+ *    unless the argument comment says "host".  The library never allocates or frees
+ *    caller-visible memory and never synchronises the stream.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *    Launches go to the calling thread's current CUDA device.  All entry points are
+ *    re-entrant and CUDA-graph capturable.
+ *  - return value: 0 (JXP_OK) or a negative JxpStatus; the message for the calling
+ *    thread's last failure is available from jxp_last_error().
+ *  - strides are in ELEMENTS and must be 0 (broadcast one value) or 1 (dense).
+ *  - `_f64` computes in IEEE double; `_f32` computes the solve and the flux in float
+ *    (times and the phase reduction stay double, see DESIGN.md "fp32 mode").
+ */
+#ifndef JAXOPLANET_B200_H_
+#define JAXOPLANET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JXP_ABI_VERSION 1
+
+typedef enum JxpStatus {
+  JXP_OK = 0,
+  JXP_ERR_NULL_POINTER = -1,
+  JXP_ERR_BAD_SHAPE = -2,
+  JXP_ERR_UNSUPPORTED = -3,
+  JXP_ERR_CUDA = -4,
+  JXP_ERR_WORKSPACE = -5
+} JxpStatus;
+
+int jxp_version(void);
+/* Thread-local, NUL-terminated, valid until the next failing call on this thread. */
+const char* jxp_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  jaxoplanet.core.kepler.kepler(M, ecc) -> (sin f, cos f)
+ *     src/jaxoplanet/core/kepler.py:14-56 (primal), :59-79 (custom JVP)
+ * M, ecc broadcast against each other (stride 0 or 1) to n elements.
+ * Optional outputs (NULL to skip):
+ *   E      the eccentric anomaly in [0, 2pi) the reference keeps internal (kepler.py:39-43)
+ *   dfdM   (1 + e cos f)^2 / (1 - e^2)^{3/2}          } the two factors of the reference's
+ *   dfde   (2 + e cos f) sin f / (1 - e^2)             } JVP rule: f_dot = M_dot dfdM + e_dot dfde,
+ *                                                        d sin f = cos f f_dot, d cos f = -sin f f_dot
+ * ---------------------------------------------------------------------------------- */
+int jxp_kepler_f64(const double* M, int64_t M_stride, const double* ecc, int64_t ecc_stride,
+                   int64_t n, double* sinf, double* cosf, double* E, double* dfdM,
+                   double* dfde, void* stream);
+int jxp_kepler_f32(const float* M, int64_t M_stride, const float* ecc, int64_t ecc_stride,
+                   int64_t n, float* sinf, float* cosf, float* E, float* dfdM, float* dfde,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  jaxoplanet.core.limb_dark.light_curve(u, b, r, order=10) -> flux - 1
+ *     src/jaxoplanet/core/limb_dark.py:19-47 (+ :50-196)
+ * u: n_u coefficients (0 <= n_u <= JXP_MAX_LD_COEFFS), one shared set as in the
+ * reference (u.ndim == 1, limb_dark.py:40).  b, r broadcast (stride 0 or 1) to n.
+ * order: Gauss-Legendre nodes of the line integral (1..JXP_MAX_GL_ORDER).
+ * Optional outputs (NULL to skip):
+ *   dflux_db, dflux_dr   derivatives of the *discretised* formula, as JAX autodiff of the
+ *                        reference gives them (incl. the zero_safe_sqrt rule utils.py:16-24)
+ *   svec                 [n_u + 1][n] solution vector s (limb_dark.py:73-82), so that the
+ *                        caller forms d flux/d u = s . dg/du
+ * ---------------------------------------------------------------------------------- */
+#define JXP_MAX_LD_COEFFS 8
+#define JXP_MAX_GL_ORDER 64
+int jxp_limb_dark_f64(const double* u, int32_t n_u, const double* b, int64_t b_stride,
+                      const double* r, int64_t r_stride, int64_t n, int32_t order,
+                      double* flux_m1, double* dflux_db, double* dflux_dr, double* svec,
+                      void* stream);
+int jxp_limb_dark_f32(const float* u, int32_t n_u, const float* b, int64_t b_stride,
+                      const float* r, int64_t r_stride, int64_t n, int32_t order,
+                      float* flux_m1, float* dflux_db, float* dflux_dr, float* svec,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3/K4  jaxoplanet.light_curves.limb_dark.light_curve(System, u)(t), optionally wrapped in
+ *        light_curves.transforms.integrate(..., exposure_time, order, num_samples), for a
+ *        BATCH of parameter sets (what the reference user writes as jax.vmap over
+ *        parameters), optionally fused with the Gaussian log-likelihood of observed flux.
+ *     src/jaxoplanet/light_curves/limb_dark.py:15-62
+ *     src/jaxoplanet/orbits/keplerian.py:402-419, 537-637   (relative_position)
+ *     src/jaxoplanet/light_curves/transforms.py:21-116      (integrate)
+ *
+ * bodies: [n_sets][n_bodies][JXP_BODY_NFIELDS] derived per-body constants, i.e. the
+ *         fields OrbitalBody.__init__ computes (keplerian.py:262-340); ALWAYS double (a float
+ *         period or epoch cannot place a transit to 1 ppm of flux).
+ * u:      [n_sets or 1][n_u] limb-darkening coefficients (u_set_stride = n_u or 0), n_u <= 2,
+ *         ALWAYS double.
+ * t:      [n_times] time stamps, ALWAYS double, shared by all sets.
+ * exposure_time <= 0 or num_samples <= 0: no exposure integration.  exp_order in {0,1,2}.
+ * Outputs (any may be NULL):
+ *   flux      [n_sets][n_times][n_bodies]  per-body flux - 1, masked to 0 where z <= 0
+ *             (the reference's return value, with a leading set axis)
+ *   flux_sum  [n_sets][n_times]            sum over bodies of the above
+ *   loglike   [n_sets]   sum_t Normal(1 + flux_sum, sigma).log_prob(y); needs y, sigma and a
+ *             workspace of jxp_system_workspace_bytes(...) bytes
+ * flags: JXP_FLAG_* below.
+ * ---------------------------------------------------------------------------------- */
+enum {
+  JXP_BODY_PERIOD = 0,
+  JXP_BODY_TIME_TRANSIT = 1,
+  JXP_BODY_TIME_REF = 2,
+  JXP_BODY_ECC = 3, /* < 0: circular body (eccentricity is None, keplerian.py:299-303) */
+  JXP_BODY_COS_OMEGA = 4,
+  JXP_BODY_SIN_OMEGA = 5,
+  JXP_BODY_COS_INCL = 6,
+  JXP_BODY_SIN_INCL = 7,
+  JXP_BODY_SEMIMAJOR = 8,
+  JXP_BODY_CENTRAL_RADIUS = 9,
+  JXP_BODY_RADIUS = 10,
+  JXP_BODY_RESERVED = 11,
+  JXP_BODY_NFIELDS = 12
+};
+
+/* Evaluate every point in full (no transit-window pre-test).  Results are identical
+ * either way; this exists for measurement (DESIGN.md "window test"). */
+#define JXP_FLAG_NO_WINDOW 1
+
+size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times);
+
+int jxp_system_light_curve_f64(const double* bodies, int32_t n_sets, int32_t n_bodies,
+                               const double* u, int32_t n_u, int64_t u_set_stride,
+                               const double* t, int64_t n_times, double exposure_time,
+                               int32_t exp_order, int32_t num_samples, int32_t gl_order,
+                               int32_t flags, double* flux, double* flux_sum,
+                               const double* y, const double* sigma, int64_t sigma_stride,
+                               double* loglike, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_bodies,
+                               const double* u, int32_t n_u, int64_t u_set_stride,
+                               const double* t, int64_t n_times, double exposure_time,
+                               int32_t exp_order, int32_t num_samples, int32_t gl_order,
+                               int32_t flags, float* flux, float* flux_sum, const float* y,
+                               const float* sigma, int64_t sigma_stride, float* loglike,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5  flux and its forward-mode partials w.r.t. the 8 sampled parameters of a single
+ *     transiting planet, theta = (period, time_transit, eccentricity, omega_peri,
+ *     impact_param, radius, u1, u2): what jax.jvp / jax.grad of
+ *         lambda theta: limb_dark_light_curve(System(Central(mass, radius)).add_body(
+ *             period=, time_transit=, eccentricity=, omega_peri=, impact_param=, radius=),
+ *             [u1, u2])(t)[..., 0]
+ *     evaluates through keplerian.py:262-340 (constants), kepler.py:59-79 (Kepler JVP),
+ *     limb_dark.py (autodiff of the discretised flux) -- SURVEY.md 3.5.
+ * theta:   [n_sets][8];  star: [n_sets or 1][2] = (central mass, central radius),
+ *          star_set_stride = 2 or 0.
+ * Outputs (any may be NULL):
+ *   flux      [n_sets][n_times]      flux - 1
+ *   partials  [n_sets][8][n_times]   d(flux)/d(theta_k)
+ *   loglike   [n_sets], dloglike [n_sets][8]   Gaussian log-likelihood of (y, sigma) and its
+ *             gradient, reduced in-kernel (workspace: jxp_transit_workspace_bytes)
+ * ---------------------------------------------------------------------------------- */
+#define JXP_NTHETA 8
+size_t jxp_transit_workspace_bytes(int32_t n_sets, int64_t n_times);
+
+int jxp_transit_partials_f64(const double* theta, int32_t n_sets, const double* star,
+                             int64_t star_set_stride, const double* t, int64_t n_times,
+                             double exposure_time, int32_t exp_order, int32_t num_samples,
+                             int32_t gl_order, int32_t flags, double* flux, double* partials,
+                             const double* y, const double* sigma, int64_t sigma_stride,
+                             double* loglike, double* dloglike, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int jxp_transit_partials_f32(const double* theta, int32_t n_sets, const double* star,
+                             int64_t star_set_stride, const double* t, int64_t n_times,
+                             double exposure_time, int32_t exp_order, int32_t num_samples,
+                             int32_t gl_order, int32_t flags, float* flux, float* partials,
+                             const float* y, const float* sigma, int64_t sigma_stride,
+                             float* loglike, float* dloglike, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement helper (not part of the reference surface): a dependent-free DFMA (or FFMA)
+ * loop that saturates the FP64 (FP32) pipe; bench.py times it with CUDA events to obtain the
+ * FP64/FP32 roofline denominator MEASURED_PEAKS.json lacks.  Executes
+ * 2 * n_threads * iters * 16 flops and writes one value per thread to `sink`.
+ * ---------------------------------------------------------------------------------- */
+int jxp_peak_fma_f64(double* sink, int32_t n_blocks, int32_t n_threads, int64_t iters,
+                     void* stream);
+int jxp_peak_fma_f32(float* sink, int32_t n_blocks, int32_t n_threads, int64_t iters,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXOPLANET_B200_H_ */

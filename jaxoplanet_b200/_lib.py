@@ -1,0 +1,99 @@
+"""ctypes binding of include/jaxoplanet_b200.h.
+
+There is no CPU fallback: if the shared library is missing the import of any compute
+entry point raises, and every non-zero status from the C ABI becomes a ``JxpError``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libjxp_b200.so")
+
+JXP_BODY_NFIELDS = 12
+JXP_NTHETA = 8
+JXP_FLAG_NO_WINDOW = 1
+JXP_FLAG_COUNT = 2
+
+(BODY_PERIOD, BODY_TIME_TRANSIT, BODY_TIME_REF, BODY_ECC, BODY_COS_OMEGA, BODY_SIN_OMEGA,
+ BODY_COS_INCL, BODY_SIN_INCL, BODY_SEMIMAJOR, BODY_CENTRAL_RADIUS, BODY_RADIUS,
+ BODY_RESERVED) = range(12)
+
+
+class JxpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"jaxoplanet_b200 C ABI error {code}: {msg}")
+        self.code = code
+
+
+_p = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f64 = C.c_double
+_sz = C.c_size_t
+
+SIGNATURES = {
+    "jxp_version": (C.c_int, []),
+    "jxp_last_error": (C.c_char_p, []),
+    "jxp_kepler_f64": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "jxp_kepler_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "jxp_limb_dark_f64": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "jxp_limb_dark_f32": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "jxp_system_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+    "jxp_system_light_curve_f64": (
+        C.c_int,
+        [_p, _i32, _i32, _p, _i32, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+         _i64, _p, _p, _sz, _p],
+    ),
+    "jxp_system_light_curve_f32": (
+        C.c_int,
+        [_p, _i32, _i32, _p, _i32, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+         _i64, _p, _p, _sz, _p],
+    ),
+    "jxp_transit_workspace_bytes": (_sz, [_i32, _i64]),
+    "jxp_transit_partials_f64": (
+        C.c_int,
+        [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,
+         _p, _sz, _p],
+    ),
+    "jxp_transit_partials_f32": (
+        C.c_int,
+        [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,
+         _p, _sz, _p],
+    ),
+    "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),
+    "jxp_peak_fma_f32": (C.c_int, [_p, _i32, _i32, _i64, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m jaxoplanet_b200.build` "
+            "(nvcc, sm_100a). jaxoplanet_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int):
+    if code != 0:
+        msg = load().jxp_last_error()
+        raise JxpError(code, msg.decode() if msg else "")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,784 @@
+// Kernels and C-ABI launchers of jaxoplanet_b200 (sm_100a).  See include/jaxoplanet_b200.h
+// for the contract of every entry point and DESIGN.md for the kernel designs.
+#include "../../include/jaxoplanet_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "jxp_orbit.cuh"
+
+using namespace jxp;
+
+// ======================================================================================
+// error plumbing
+// ======================================================================================
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(JXP_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return JXP_OK;
+}
+
+bool stride_ok(int64_t s) { return s == 0 || s == 1; }
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// Gauss-Legendre nodes/weights on the host for orders other than the built-in 10
+// (the reference calls scipy.special.roots_legendre(order), limb_dark.py:155).
+void gl_table_host(int order, GLTable& tab) {
+  tab.order = order;
+  const double pi = 3.141592653589793238462643383279502884;
+  for (int i = 0; i < (order + 1) / 2; ++i) {
+    double x = std::cos(pi * (i + 0.75) / (order + 0.5));
+    double dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = x;
+      for (int k = 2; k <= order; ++k) {
+        double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1;
+        p1 = pk;
+      }
+      if (order == 1) {
+        p0 = 1.0;
+        p1 = x;
+      }
+      dp = order * (x * p1 - p0) / (x * x - 1.0);
+      double dx = p1 / dp;
+      x -= dx;
+      if (std::fabs(dx) < 1e-16) break;
+    }
+    // recompute derivative at the converged node
+    {
+      double p0 = 1.0, p1 = x;
+      for (int k = 2; k <= order; ++k) {
+        double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1;
+        p1 = pk;
+      }
+      dp = order * (x * p1 - p0) / (x * x - 1.0);
+    }
+    double w = 2.0 / ((1.0 - x * x) * dp * dp);
+    if (2 * i + 1 == order) x = 0.0;
+    tab.x[i] = -x;
+    tab.x[order - 1 - i] = x;
+    tab.w[i] = w;
+    tab.w[order - 1 - i] = w;
+  }
+}
+}  // namespace
+
+extern "C" int jxp_version(void) { return JXP_ABI_VERSION; }
+extern "C" const char* jxp_last_error(void) { return g_err; }
+
+// ======================================================================================
+// K1  Kepler
+// ======================================================================================
+template <typename T, bool EXTRA>
+__global__ void __launch_bounds__(256)
+k_kepler(const T* __restrict__ M, int64_t Ms, const T* __restrict__ ecc, int64_t es, int64_t n,
+         T* __restrict__ sinf_o, T* __restrict__ cosf_o, T* __restrict__ E_o,
+         T* __restrict__ dfdM_o, T* __restrict__ dfde_o) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T m = M[i * Ms];
+    const T e = ecc[i * es];
+    const T ome = T(1) - e, ope = T(1) + e;
+    const T ome2 = ome * ope;
+    const T s1me2 = jsqrt(ome2);
+    const T inv_ope = T(1) / ope;
+    const T Mr = mod_two_pi(m);
+    T sf, cf, E;
+    kepler_reduced<T, EXTRA>(Mr, e, ome, ope, s1me2, inv_ope, sf, cf, E);
+    sinf_o[i] = sf;
+    cosf_o[i] = cf;
+    if (EXTRA) {
+      if (E_o) E_o[i] = E;
+      if (dfdM_o || dfde_o) {
+        // kepler.py:64-77
+        const T ecosf = e * cf;
+        const T inv = T(1) / ome2;
+        const T opc = T(1) + ecosf;
+        if (dfdM_o) dfdM_o[i] = opc * opc * inv / s1me2;
+        if (dfde_o) dfde_o[i] = (T(2) + ecosf) * sf * inv;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_kepler(const T* M, int64_t Ms, const T* ecc, int64_t es, int64_t n, T* sinf,
+                         T* cosf, T* E, T* dfdM, T* dfde, void* stream) {
+  if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_kepler: n = %lld < 0", (long long)n);
+  if (n == 0) return JXP_OK;
+  if (!M || !ecc || !sinf || !cosf) return fail(JXP_ERR_NULL_POINTER, "jxp_kepler: null M/ecc/sinf/cosf");
+  if (!stride_ok(Ms) || !stride_ok(es))
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_kepler: strides must be 0 or 1");
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E || dfdM || dfde)
+    k_kepler<T, true><<<(unsigned)blocks, threads, 0, st>>>(M, Ms, ecc, es, n, sinf, cosf, E, dfdM, dfde);
+  else
+    k_kepler<T, false><<<(unsigned)blocks, threads, 0, st>>>(M, Ms, ecc, es, n, sinf, cosf, E, dfdM, dfde);
+  return check_launch("jxp_kepler");
+}
+
+extern "C" int jxp_kepler_f64(const double* M, int64_t Ms, const double* ecc, int64_t es,
+                              int64_t n, double* sinf, double* cosf, double* E, double* dfdM,
+                              double* dfde, void* stream) {
+  return launch_kepler<double>(M, Ms, ecc, es, n, sinf, cosf, E, dfdM, dfde, stream);
+}
+extern "C" int jxp_kepler_f32(const float* M, int64_t Ms, const float* ecc, int64_t es, int64_t n,
+                              float* sinf, float* cosf, float* E, float* dfdM, float* dfde,
+                              void* stream) {
+  return launch_kepler<float>(M, Ms, ecc, es, n, sinf, cosf, E, dfdM, dfde, stream);
+}
+
+// ======================================================================================
+// K2  limb-darkened flux (core)
+// ======================================================================================
+template <typename T>
+struct LdArgs {
+  const T* u;
+  int n_u;
+  const T* b;
+  int64_t bs;
+  const T* r;
+  int64_t rs;
+  int64_t n;
+  T* flux;
+  T* db;
+  T* dr;
+  T* svec;
+  GLTable tab;
+};
+
+template <typename T, int ORDER, bool GRAD>
+__global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArgs<T> a) {
+  T u1 = a.n_u >= 1 ? a.u[0] : T(0);
+  T u2 = a.n_u >= 2 ? a.u[1] : T(0);
+  T g0, g1, g2;
+  ld_greens<T>(a.n_u, u1, u2, g0, g1, g2);
+  const int lmax = a.n_u;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const T b = a.b[i * a.bs];
+    const T r = a.r[i * a.rs];
+    if (GRAD) {
+      typedef Dual<T, 2> D;
+      D s0, s1, s2;
+      ld_solution<D, ORDER>(D::seed(b, 0), D::seed(r, 1), lmax, &a.tab, s0, s1, s2);
+      D f = ld_combine(lmax, s0, s1, s2, D(g0), D(g1), D(g2));
+      a.flux[i] = f.v;
+      if (a.db) a.db[i] = f.d[0];
+      if (a.dr) a.dr[i] = f.d[1];
+      if (a.svec) {
+        a.svec[i] = s0.v;
+        if (lmax >= 1) a.svec[a.n + i] = s1.v;
+        if (lmax >= 2) a.svec[2 * a.n + i] = s2.v;
+      }
+    } else {
+      T s0, s1, s2;
+      ld_solution<T, ORDER>(b, r, lmax, &a.tab, s0, s1, s2);
+      a.flux[i] = ld_combine(lmax, s0, s1, s2, g0, g1, g2);
+    }
+  }
+}
+
+template <typename T>
+static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, const T* r,
+                            int64_t rs, int64_t n, int32_t order, T* flux, T* db, T* dr, T* svec,
+                            void* stream) {
+  if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_limb_dark: n = %lld < 0", (long long)n);
+  if (n_u < 0 || n_u > JXP_MAX_LD_COEFFS)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_limb_dark: n_u = %d out of range", n_u);
+  if (n_u > 2)
+    return fail(JXP_ERR_UNSUPPORTED,
+                "jxp_limb_dark: %d limb-darkening coefficients; only l_max <= 2 (uniform, linear, "
+                "quadratic) is implemented",
+                n_u);
+  if (order < 1 || order > JXP_MAX_GL_ORDER)
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_limb_dark: order = %d outside 1..%d", order,
+                JXP_MAX_GL_ORDER);
+  if (n == 0) return JXP_OK;
+  if (!b || !r || !flux || (n_u > 0 && !u))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_limb_dark: null u/b/r/flux");
+  if (!stride_ok(bs) || !stride_ok(rs))
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_limb_dark: strides must be 0 or 1");
+  LdArgs<T> a;
+  a.u = u;
+  a.n_u = n_u;
+  a.b = b;
+  a.bs = bs;
+  a.r = r;
+  a.rs = rs;
+  a.n = n;
+  a.flux = flux;
+  a.db = db;
+  a.dr = dr;
+  a.svec = svec;
+  a.tab.order = order;
+  if (order != 10) gl_table_host(order, a.tab);
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool grad = db || dr || svec;
+  if (order == 10) {
+    if (grad)
+      k_limb_dark<T, 10, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+    else
+      k_limb_dark<T, 10, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  } else {
+    if (grad)
+      k_limb_dark<T, 0, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+    else
+      k_limb_dark<T, 0, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  }
+  return check_launch("jxp_limb_dark");
+}
+
+extern "C" int jxp_limb_dark_f64(const double* u, int32_t n_u, const double* b, int64_t bs,
+                                 const double* r, int64_t rs, int64_t n, int32_t order,
+                                 double* flux, double* db, double* dr, double* svec, void* stream) {
+  return launch_limb_dark<double>(u, n_u, b, bs, r, rs, n, order, flux, db, dr, svec, stream);
+}
+extern "C" int jxp_limb_dark_f32(const float* u, int32_t n_u, const float* b, int64_t bs,
+                                 const float* r, int64_t rs, int64_t n, int32_t order, float* flux,
+                                 float* db, float* dr, float* svec, void* stream) {
+  return launch_limb_dark<float>(u, n_u, b, bs, r, rs, n, order, flux, db, dr, svec, stream);
+}
+
+// ======================================================================================
+// K3/K4  fused system light curve (+ exposure integration, + Gaussian log-likelihood)
+// ======================================================================================
+namespace {
+constexpr int SYS_K = 4;          // time samples held in registers per thread
+constexpr int SYS_MAX_SETS = 32;  // parameter sets per CTA (upper bound)
+constexpr int MAX_SUB = 64;
+
+struct Stencil {
+  int n;
+  double dt[MAX_SUB];
+  double w[MAX_SUB];
+};
+
+// transforms.py:67-89
+int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) {
+  if (!(exposure_time > 0.0) || num_samples <= 0) {
+    st.n = 1;
+    st.dt[0] = 0.0;
+    st.w[0] = 1.0;
+    return JXP_OK;
+  }
+  int ns = num_samples;
+  ns += 1 - ns % 2;
+  if (ns > MAX_SUB - 1)
+    return fail(JXP_ERR_UNSUPPORTED, "exposure integration: num_samples = %d > %d", ns, MAX_SUB - 1);
+  st.n = ns;
+  double sum = 0.0;
+  if (order == 0) {
+    // linspace(-0.5, 0.5, 2 ns + 1)[1:-1:2]
+    const int m = 2 * ns + 1;
+    const double step = 1.0 / (m - 1);
+    for (int j = 0; j < ns; ++j) {
+      const int idx = 2 * j + 1;
+      st.dt[j] = (idx == m - 1) ? 0.5 : -0.5 + idx * step;
+      st.w[j] = 1.0;
+    }
+  } else if (order == 1 || order == 2) {
+    const double step = ns > 1 ? 1.0 / (ns - 1) : 0.0;
+    for (int j = 0; j < ns; ++j) {
+      st.dt[j] = (j == ns - 1 && ns > 1) ? 0.5 : -0.5 + j * step;
+      if (order == 1)
+        st.w[j] = (j == 0 || j == ns - 1) ? 1.0 : 2.0;
+      else
+        st.w[j] = (j == 0 || j == ns - 1) ? 1.0 : ((j % 2 == 1) ? 4.0 : 2.0);
+    }
+  } else {
+    return fail(JXP_ERR_UNSUPPORTED,
+                "The parameter 'order' in 'integrate_exposure_time' must be 0, 1, or 2");
+  }
+  for (int j = 0; j < ns; ++j) sum += st.w[j];
+  for (int j = 0; j < ns; ++j) {
+    st.dt[j] *= exposure_time;
+    st.w[j] /= sum;
+  }
+  return JXP_OK;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// workspace carving shared by the size query and the launchers
+struct SysLayout {
+  size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, total;
+  int tile, n_tiles;
+};
+
+SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, size_t set_sz,
+                     size_t elem_sz) {
+  SysLayout L;
+  L.tile = 128 * SYS_K;  // smallest tile any launch configuration uses
+  L.n_tiles = (int)((n_times + L.tile - 1) / L.tile);
+  size_t off = 0;
+  L.off_bodies = off;
+  off = align_up(off + body_sz * (size_t)n_sets * n_bodies, 256);
+  L.off_sets = off;
+  off = align_up(off + set_sz * (size_t)n_sets, 256);
+  L.off_winv = off;
+  off = align_up(off + elem_sz * (size_t)n_times, 256);
+  L.off_scalars = off;
+  off = align_up(off + 8 * sizeof(double), 256);
+  L.off_partial = off;
+  off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles, 256);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+// one thread per (set, body): derived constants -> BodyC (+ transit window), u -> SetC
+template <typename T>
+__global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
+                           const double* __restrict__ u, int n_u, int64_t u_stride,
+                           BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
+                           double widen, double margin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sets * n_bodies) return;
+  const double* p = bodies + (size_t)i * JXP_BODY_NFIELDS;
+  BodyC<T> c;
+  c.t0 = p[JXP_BODY_TIME_TRANSIT];
+  c.tref = p[JXP_BODY_TIME_REF];
+  c.period = p[JXP_BODY_PERIOD];
+  c.t0ref = c.t0 + c.tref;
+  c.inv_period = 1.0 / c.period;
+  double e = p[JXP_BODY_ECC];
+  c.flags = 0;
+  c.pad = 0;
+  if (e < 0.0) {
+    c.flags |= BODY_CIRCULAR;
+    e = 0.0;
+  }
+  const double a = p[JXP_BODY_SEMIMAJOR];
+  const double rstar = p[JXP_BODY_CENTRAL_RADIUS];
+  c.e = T(e);
+  c.ome = T(1.0 - e);
+  c.ope = T(1.0 + e);
+  c.s1me2 = T(sqrt((1.0 - e) * (1.0 + e)));
+  c.inv_ope = T(1.0 / (1.0 + e));
+  c.cw = T(p[JXP_BODY_COS_OMEGA]);
+  c.sw = T(p[JXP_BODY_SIN_OMEGA]);
+  c.ci = T(p[JXP_BODY_COS_INCL]);
+  c.si = T(p[JXP_BODY_SIN_INCL]);
+  c.na_ome2 = T(-a * (1.0 - e * e));
+  c.inv_rstar = T(1.0 / rstar);
+  const double rr = p[JXP_BODY_RADIUS] / rstar;
+  c.rr = T(rr);
+  c.onepr = T(1.0 + fabs(rr));
+  transit_window(c, a, rstar, e, widen, margin);
+  out_b[i] = c;
+  if (i % n_bodies == 0) {
+    const int s = i / n_bodies;
+    const double* us = u + (size_t)s * u_stride;
+    double g0, g1, g2;
+    ld_greens<double>(n_u, n_u >= 1 ? us[0] : 0.0, n_u >= 2 ? us[1] : 0.0, g0, g1, g2);
+    SetC<T> sc;
+    sc.g0 = T(g0);
+    sc.g1 = T(g1);
+    sc.g2 = T(g2);
+    sc.lmax = n_u;
+    out_s[s] = sc;
+  }
+}
+
+// winv[t] = 1 / sigma[t];  scalars[0] = sum_t ((y - 1) winv)^2,
+// scalars[1] = sum_t (-log sigma - log(2 pi) / 2).   One CTA, fixed summation order.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
+               T* __restrict__ winv, double* __restrict__ scalars) {
+  __shared__ double sh0[32], sh1[32];
+  double a0 = 0.0, a1 = 0.0;
+  const double half_log_2pi = 0.918938533204672741780329736405617639;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const T sg = sigma[i * ss];
+    const T w = T(1) / sg;
+    winv[i] = w;
+    const double r0 = (double)((y[i] - T(1)) * w);
+    a0 += r0 * r0;
+    a1 -= log((double)sg) + half_log_2pi;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_down_sync(0xffffffffu, a0, o);
+    a1 += __shfl_down_sync(0xffffffffu, a1, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sh0[w] = a0;
+    sh1[w] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      t0 += sh0[k];
+      t1 += sh1[k];
+    }
+    scalars[0] = t0;
+    scalars[1] = t1;
+  }
+}
+
+template <typename T>
+__global__ void k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
+                                const double* __restrict__ scalars, T* __restrict__ loglike) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sets) return;
+  double acc = 0.0;
+  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)s * n_tiles + k];
+  loglike[s] = T(-0.5 * (scalars[0] + acc) + scalars[1]);
+}
+
+template <typename T>
+struct SysArgs {
+  const BodyC<T>* bodies;
+  const SetC<T>* sets;
+  const double* t;
+  int64_t n_times;
+  int n_sets, n_bodies, sets_per_cta, n_tiles, use_window;
+  T* flux;
+  T* flux_sum;
+  const T* y;
+  const T* winv;
+  double* partial;  // [n_sets][n_tiles]
+  Stencil st;
+  GLTable tab;
+};
+
+// CTA = (tile of blockDim.x * SYS_K time samples) x (group of sets_per_cta parameter sets).
+// Each thread keeps its SYS_K time stamps (and, for the likelihood, the zero-model
+// residuals) in registers and walks over the sets of the group, whose records were staged
+// in shared memory once per CTA; the per-set record is read as a warp-wide broadcast.
+template <typename T, int ORDER, bool LOGLIKE>
+__global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nthreads = blockDim.x;
+  const int nwarps = nthreads >> 5;
+  const int tile = blockIdx.x % a.n_tiles;
+  const int group = blockIdx.x / a.n_tiles;
+  const int set_base = group * a.sets_per_cta;
+  const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
+
+  BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
+  SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * a.n_bodies);
+  double* spart = reinterpret_cast<double*>(sset + a.sets_per_cta);  // [nwarps][sets_per_cta]
+
+  {
+    // stage the group's records (plain 8-byte copies; sizeof(BodyC), sizeof(SetC) % 8 == 0)
+    const unsigned long long* src =
+        reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base * a.n_bodies);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
+    const int nw = nsl * a.n_bodies * (int)(sizeof(BodyC<T>) / 8);
+    for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
+    const unsigned long long* src2 = reinterpret_cast<const unsigned long long*>(a.sets + set_base);
+    unsigned long long* dst2 = reinterpret_cast<unsigned long long*>(sset);
+    const int nw2 = nsl * (int)(sizeof(SetC<T>) / 8);
+    for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
+  }
+
+  const int64_t tile_base = (int64_t)tile * nthreads * SYS_K;
+  double tk[SYS_K];
+  T r0k[SYS_K], wk[SYS_K];
+#pragma unroll
+  for (int k = 0; k < SYS_K; ++k) {
+    const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
+    const bool ok = idx < a.n_times;
+    tk[k] = ok ? a.t[idx] : 0.0;
+    if (LOGLIKE) {
+      wk[k] = ok ? a.winv[idx] : T(0);
+      r0k[k] = ok ? (a.y[idx] - T(1)) * wk[k] : T(0);
+    }
+  }
+  __syncthreads();
+
+  const int nsub = a.st.n;
+  const bool use_window = a.use_window != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int sl = 0; sl < nsl; ++sl) {
+    const int set = set_base + sl;
+    const SetC<T> sc = sset[sl];
+    double dchi = 0.0;
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < SYS_K; ++k) {
+      const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
+      if (idx >= a.n_times) continue;
+      T total = T(0);
+      for (int body = 0; body < a.n_bodies; ++body) {
+        const BodyC<T>& c = sbody[sl * a.n_bodies + body];
+        T acc;
+        if (nsub == 1) {
+          acc = eval_sample<T, ORDER>(c, sc, &a.tab, tk[k], use_window);
+        } else {
+          acc = T(0);
+          for (int j = 0; j < nsub; ++j) {
+            const T v = eval_sample<T, ORDER>(c, sc, &a.tab, tk[k] + a.st.dt[j], use_window);
+            acc = jfma(T(a.st.w[j]), v, acc);
+          }
+        }
+        if (a.flux) a.flux[((size_t)set * a.n_times + idx) * a.n_bodies + body] = acc;
+        total += acc;
+      }
+      if (a.flux_sum) a.flux_sum[(size_t)set * a.n_times + idx] = total;
+      if (LOGLIKE) {
+        if (total != T(0)) {
+          // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: the change of chi^2 w.r.t. the zero model
+          const T mw = total * wk[k];
+          dchi += (double)(-mw) * (double)(T(2) * r0k[k] - mw);
+          hit = true;
+        }
+      }
+    }
+    if (LOGLIKE) {
+      if (__any_sync(0xffffffffu, hit)) {
+        for (int o = 16; o > 0; o >>= 1) dchi += __shfl_down_sync(0xffffffffu, dchi, o);
+      }
+      if (lane == 0) spart[warp * a.sets_per_cta + sl] = dchi;
+    }
+  }
+  if (LOGLIKE) {
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < nsl; sl += nthreads) {
+      double acc = 0.0;
+      for (int w = 0; w < nwarps; ++w) acc += spart[w * a.sets_per_cta + sl];
+      a.partial[(size_t)(set_base + sl) * a.n_tiles + tile] = acc;
+    }
+  }
+}
+
+extern "C" size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times) {
+  if (n_sets <= 0 || n_bodies <= 0 || n_times < 0) return 0;
+  // sized for the wider (double) records so one query serves both precisions
+  return sys_layout(n_sets, n_bodies, n_times, sizeof(BodyC<double>), sizeof(SetC<double>),
+                    sizeof(double))
+      .total;
+}
+
+template <typename T>
+static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies, const double* u,
+                         int32_t n_u, int64_t u_stride, const double* t, int64_t n_times,
+                         double exposure_time, int32_t exp_order, int32_t num_samples,
+                         int32_t gl_order, int32_t flags, T* flux, T* flux_sum, const T* y,
+                         const T* sigma, int64_t sigma_stride, T* loglike, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  static_assert(sizeof(BodyC<T>) % 8 == 0 && sizeof(SetC<T>) % 8 == 0, "record sizes");
+  if (n_sets < 0 || n_bodies < 0 || n_times < 0)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: negative size");
+  if (n_u < 0 || n_u > 2)
+    return fail(JXP_ERR_UNSUPPORTED,
+                "jxp_system_light_curve: n_u = %d; only l_max <= 2 is implemented", n_u);
+  if (gl_order < 1 || gl_order > JXP_MAX_GL_ORDER)
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: order = %d outside 1..%d", gl_order,
+                JXP_MAX_GL_ORDER);
+  if (n_bodies > 64) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: n_bodies > 64");
+  if (u_stride != 0 && u_stride != n_u)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: u_set_stride must be 0 or n_u");
+  if (!stride_ok(sigma_stride))
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: sigma_stride must be 0 or 1");
+  SysArgs<T> a;
+  int rc = make_stencil(exposure_time, exp_order, num_samples, a.st);
+  if (rc != JXP_OK) return rc;
+  if (n_sets == 0 || n_bodies == 0 || n_times == 0) return JXP_OK;
+  if (!bodies || !t || (n_u > 0 && !u))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_system_light_curve: null bodies/u/t");
+  if (loglike && (!y || !sigma))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_system_light_curve: loglike needs y and sigma");
+  if (!flux && !flux_sum && !loglike)
+    return fail(JXP_ERR_NULL_POINTER, "jxp_system_light_curve: no output requested");
+  const size_t need = jxp_system_workspace_bytes(n_sets, n_bodies, n_times);
+  if (!workspace || workspace_bytes < need)
+    return fail(JXP_ERR_WORKSPACE, "jxp_system_light_curve: workspace of %zu bytes needed, %zu given",
+                need, workspace_bytes);
+  if (((uintptr_t)workspace & 255) != 0)
+    return fail(JXP_ERR_WORKSPACE, "jxp_system_light_curve: workspace must be 256-byte aligned");
+
+  const SysLayout L = sys_layout(n_sets, n_bodies, n_times, sizeof(BodyC<double>),
+                                 sizeof(SetC<double>), sizeof(double));
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  BodyC<T>* d_bodies = reinterpret_cast<BodyC<T>*>(ws + L.off_bodies);
+  SetC<T>* d_sets = reinterpret_cast<SetC<T>*>(ws + L.off_sets);
+  T* d_winv = reinterpret_cast<T*>(ws + L.off_winv);
+  double* d_scalars = reinterpret_cast<double*>(ws + L.off_scalars);
+  double* d_partial = reinterpret_cast<double*>(ws + L.off_partial);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const bool f32 = sizeof(T) == 4;
+  {
+    const int n = n_sets * n_bodies;
+    k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride,
+                                                  d_bodies, d_sets, f32 ? 1.0 + 2e-4 : 1.0 + 1e-9,
+                                                  1e-7);
+    rc = check_launch("jxp_system_light_curve(prep)");
+    if (rc != JXP_OK) return rc;
+  }
+  if (loglike) {
+    k_loglike_prep<T><<<1, 1024, 0, st>>>(y, sigma, sigma_stride, n_times, d_winv, d_scalars);
+    rc = check_launch("jxp_system_light_curve(loglike prep)");
+    if (rc != JXP_OK) return rc;
+  }
+
+  // launch geometry: enough CTAs to fill the machine several times over, as many sets per
+  // CTA as that allows (amortises the time-stamp loads and the record staging)
+  const int sms = sm_count();
+  int threads = 256;
+  int64_t n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
+  if (n_tiles * n_sets < 2 * sms) {
+    threads = 128;
+    n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
+  }
+  int spc = (int)((n_tiles * (int64_t)n_sets) / ((int64_t)sms * 32));
+  if (spc < 1) spc = 1;
+  if (spc > SYS_MAX_SETS) spc = SYS_MAX_SETS;
+  if (spc > n_sets) spc = n_sets;
+  const int64_t n_groups = (n_sets + spc - 1) / spc;
+  const int64_t n_ctas = n_tiles * n_groups;
+  if (n_ctas > 2147483647LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: grid too large");
+
+  a.bodies = d_bodies;
+  a.sets = d_sets;
+  a.t = t;
+  a.n_times = n_times;
+  a.n_sets = n_sets;
+  a.n_bodies = n_bodies;
+  a.sets_per_cta = spc;
+  a.n_tiles = (int)n_tiles;
+  a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
+  a.flux = flux;
+  a.flux_sum = flux_sum;
+  a.y = y;
+  a.winv = d_winv;
+  a.partial = d_partial;
+  a.tab.order = gl_order;
+  if (gl_order != 10) gl_table_host(gl_order, a.tab);
+
+  const size_t smem = sizeof(BodyC<T>) * (size_t)spc * n_bodies + sizeof(SetC<T>) * (size_t)spc +
+                      sizeof(double) * (size_t)spc * (threads / 32);
+  if (smem > 200 * 1024) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: shared memory");
+  auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)n_ctas, threads, smem, st>>>(a);
+    return check_launch("jxp_system_light_curve");
+  };
+  if (gl_order == 10)
+    rc = loglike ? launch(k_system<T, 10, true>) : launch(k_system<T, 10, false>);
+  else
+    rc = loglike ? launch(k_system<T, 0, true>) : launch(k_system<T, 0, false>);
+  if (rc != JXP_OK) return rc;
+
+  if (loglike) {
+    k_loglike_final<T><<<(n_sets + 127) / 128, 128, 0, st>>>(d_partial, (int)n_tiles, n_sets,
+                                                            d_scalars, loglike);
+    rc = check_launch("jxp_system_light_curve(loglike final)");
+  }
+  return rc;
+}
+
+extern "C" int jxp_system_light_curve_f64(const double* bodies, int32_t n_sets, int32_t n_bodies,
+                                          const double* u, int32_t n_u, int64_t u_set_stride,
+                                          const double* t, int64_t n_times, double exposure_time,
+                                          int32_t exp_order, int32_t num_samples, int32_t gl_order,
+                                          int32_t flags, double* flux, double* flux_sum,
+                                          const double* y, const double* sigma,
+                                          int64_t sigma_stride, double* loglike, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  return launch_system<double>(bodies, n_sets, n_bodies, u, n_u, u_set_stride, t, n_times,
+                               exposure_time, exp_order, num_samples, gl_order, flags, flux,
+                               flux_sum, y, sigma, sigma_stride, loglike, workspace,
+                               workspace_bytes, stream);
+}
+extern "C" int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_bodies,
+                                          const double* u, int32_t n_u, int64_t u_set_stride,
+                                          const double* t, int64_t n_times, double exposure_time,
+                                          int32_t exp_order, int32_t num_samples, int32_t gl_order,
+                                          int32_t flags, float* flux, float* flux_sum,
+                                          const float* y, const float* sigma, int64_t sigma_stride,
+                                          float* loglike, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  return launch_system<float>(bodies, n_sets, n_bodies, u, n_u, u_set_stride, t, n_times,
+                              exposure_time, exp_order, num_samples, gl_order, flags, flux,
+                              flux_sum, y, sigma, sigma_stride, loglike, workspace, workspace_bytes,
+                              stream);
+}
+
+// ======================================================================================
+// FP64 / FP32 pipe peak (measurement helper)
+// ======================================================================================
+template <typename T>
+__global__ void __launch_bounds__(1024) k_peak_fma(T* sink, int64_t iters) {
+  T x = T(1.0) + T(1e-9) * T(threadIdx.x);
+  const T y = T(1e-7);
+  T a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3, a4 = x + 4, a5 = x + 5, a6 = x + 6, a7 = x + 7;
+  T b0 = x + 8, b1 = x + 9, b2 = x + 10, b3 = x + 11, b4 = x + 12, b5 = x + 13, b6 = x + 14,
+    b7 = x + 15;
+  const T m = T(0.999999);
+  for (int64_t i = 0; i < iters; ++i) {
+    a0 = jfma(a0, m, y); a1 = jfma(a1, m, y); a2 = jfma(a2, m, y); a3 = jfma(a3, m, y);
+    a4 = jfma(a4, m, y); a5 = jfma(a5, m, y); a6 = jfma(a6, m, y); a7 = jfma(a7, m, y);
+    b0 = jfma(b0, m, y); b1 = jfma(b1, m, y); b2 = jfma(b2, m, y); b3 = jfma(b3, m, y);
+    b4 = jfma(b4, m, y); b5 = jfma(b5, m, y); b6 = jfma(b6, m, y); b7 = jfma(b7, m, y);
+  }
+  sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] =
+      ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + ((b0 + b1) + (b2 + b3)) +
+      ((b4 + b5) + (b6 + b7));
+}
+
+template <typename T>
+static int launch_peak(T* sink, int32_t n_blocks, int32_t n_threads, int64_t iters, void* stream) {
+  if (!sink) return fail(JXP_ERR_NULL_POINTER, "jxp_peak_fma: null sink");
+  if (n_blocks <= 0 || n_threads <= 0 || n_threads > 1024 || iters < 0)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_peak_fma: bad launch shape");
+  k_peak_fma<T><<<n_blocks, n_threads, 0, (cudaStream_t)stream>>>(sink, iters);
+  return check_launch("jxp_peak_fma");
+}
+extern "C" int jxp_peak_fma_f64(double* sink, int32_t n_blocks, int32_t n_threads, int64_t iters,
+                                void* stream) {
+  return launch_peak<double>(sink, n_blocks, n_threads, iters, stream);
+}
+extern "C" int jxp_peak_fma_f32(float* sink, int32_t n_blocks, int32_t n_threads, int64_t iters,
+                                void* stream) {
+  return launch_peak<float>(sink, n_blocks, n_threads, iters, stream);
+}

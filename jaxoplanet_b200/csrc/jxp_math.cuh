@@ -1,0 +1,314 @@
+// Device math of the hot path: Kepler solve and polynomial(quadratic)-limb-darkened flux.
+// Written from the published algorithms (Markley 1995 starter + one high-order
+// correction; Agol, Luger & Foreman-Mackey 2020 solution vector with the reference's
+// Gauss-Legendre line integral), re-arranged for the GPU FP64 pipe.  Where an expression
+// is re-arranged relative to the reference the comment says why it stays inside the
+// parity tolerance (DESIGN.md "numerics").
+#pragma once
+
+#include "jxp_scalar.cuh"
+
+namespace jxp {
+
+// ------------------------------------------------------------------------------------
+// M mod 2*pi into [0, 2pi), exact like the reference's `M % (2 * jnp.pi)`
+// (src/jaxoplanet/core/kepler.py:31): k = floor(M / 2pi) from a multiply, then ONE fma
+// M - k * fl(2pi).  The fma result is exact because the true remainder is a multiple of
+// ulp(fl(2pi))/2 below 8 and therefore representable; a wrong k (M within an ulp of a
+// multiple) is fixed by one exact +-2pi step.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T mod_two_pi(T M) {
+  T k = jfloor(M * Num<T>::inv_two_pi);
+  T r = jfma(-k, Num<T>::two_pi, M);
+  if (r < T(0)) r += Num<T>::two_pi;
+  if (r >= Num<T>::two_pi) r -= Num<T>::two_pi;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------
+// Kepler solve for one (M, e):  src/jaxoplanet/core/kepler.py:28-56, 82-108.
+//   in : Mr in [0, 2pi) (already reduced), e, ome = 1 - e, ope = 1 + e,
+//        s1me2 = sqrt((1 - e)(1 + e)), inv_ope = 1 / (1 + e)
+//   out: sin f, cos f and (optionally) E in [0, 2pi)
+// Same starter and the same single correction as the reference.  Re-arrangements:
+//  * the starter's two divisions are merged into one (starter accuracy is irrelevant to
+//    the result: the correction is 5th order, starter error <= 4.4e-4);
+//  * sin E0, 1 - cos E0 come from sincos(E0/2): 2 s c and 2 s^2 (no cancellation);
+//  * d3 uses one division: -f0 f1 / (f1^2 - f0 f2 / 2);
+//  * instead of tan(E/2) sqrt((1+e)/(1-e)) -> (sin f, cos f) the half angle is advanced by
+//    dE/2 with a 3-term Taylor rotation (|dE/2| <= 2.2e-4, truncation < 1e-24) and
+//        sin f = 2 sqrt(1-e^2) s c / D,  cos f = ((1-e) c^2 - (1+e) s^2) / D,
+//        D = (1-e) c^2 + (1+e) s^2        (s, c = sin, cos of E/2)
+//    which is the same function (multiply tan-half-angle formulas through by (1-e) c^2),
+//    has no cancellation in D and is finite at E = pi where tan(E/2) overflows.
+// ------------------------------------------------------------------------------------
+template <typename T, bool WANT_E>
+__device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2, T inv_ope,
+                                               T& sinf, T& cosf, T& E) {
+  const T pi = Num<T>::pi;
+  const bool high = Mr > pi;
+  const T M = high ? Num<T>::two_pi - Mr : Mr;
+
+  // starter, kepler.py:82-92
+  const T k_a = T(3.0 * 3.141592653589793238462643383279502884 /
+                  (3.141592653589793238462643383279502884 -
+                   6.0 / 3.141592653589793238462643383279502884));
+  const T k_b = T(1.6 / (3.141592653589793238462643383279502884 -
+                         6.0 / 3.141592653589793238462643383279502884));
+  const T M2 = M * M;
+  const T alpha = jfma(k_b * (pi - M), inv_ope, k_a);
+  const T d = jfma(alpha, e, T(3) * ome);
+  const T alphad = alpha * d;
+  const T r = jfma(T(3) * alphad, d - ome, M2) * M;
+  const T q = jfma(T(2) * alphad, ome, -M2);
+  const T q2 = q * q;
+  T w = jcbrt(jabs(r) + jsqrt(jfma(q2, q, r * r)));
+  w = w * w;
+  const T W = jfma(w, w + q, q2);
+  const T E0 = jfma(T(2) * r, w, M * W) / (W * d);
+
+  // refine, kepler.py:95-108
+  T hs, hc;
+  jsincos(T(0.5) * E0, &hs, &hc);
+  const T sinE = T(2) * hs * hc;
+  const T cE = T(2) * hs * hs;  // 1 - cos E0
+  const T sE = E0 - sinE;
+  const T f0 = jfma(e, sE, jfma(E0, ome, -M));
+  const T f1 = jfma(e, cE, ome);
+  const T f2 = e * sinE;
+  const T f3 = T(1) - f1;
+  const T d3 = -f0 * f1 / jfma(T(-0.5) * f0, f2, f1 * f1);
+  const T d4 = -f0 / jfma(d3 * d3, f3 * T(1.0 / 6.0), jfma(T(0.5) * d3, f2, f1));
+  const T d42 = d4 * d4;
+  const T dE = -f0 / jfma(-d42 * d4, f2 * T(1.0 / 24.0),
+                          jfma(d42, f3 * T(1.0 / 6.0), jfma(T(0.5) * d4, f2, f1)));
+
+  // advance the half angle by dE/2
+  const T h = T(0.5) * dE;
+  const T h2 = h * h;
+  const T sh = jfma(-h * h2, T(1.0 / 6.0), h);
+  const T ch = jfma(h2, jfma(h2, T(1.0 / 24.0), T(-0.5)), T(1));
+  const T s = jfma(hs, ch, hc * sh);
+  const T c = jfma(hc, ch, -hs * sh);
+
+  const T ss = s * s, cc = c * c;
+  const T a = ome * cc, b = ope * ss;
+  const T invD = T(1) / (a + b);
+  const T sf = T(2) * s1me2 * s * c * invD;
+  sinf = high ? -sf : sf;
+  cosf = (a - b) * invD;
+  if (WANT_E) {
+    const T E1 = E0 + dE;
+    E = high ? Num<T>::two_pi - E1 : E1;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Limb darkening, src/jaxoplanet/core/limb_dark.py.  S is T or Dual<T, N>.
+// ------------------------------------------------------------------------------------
+
+// Gauss-Legendre nodes.  ORDER == 10 (the reference default, limb_dark.py:20) is compiled
+// in: scipy.special.roots_legendre(10) (limb_dark.py:155) as exact float64 literals, plus
+// cos(fl(fl(pi/2 * x_i) + pi/2)) for the kappa0 == pi case (planet inside the disk), where the
+// node angles do not depend on (b, r) -- the values the reference's own argument rounding gives.
+// ORDER == 0 selects a runtime table (any order up to 64) passed by the host.
+struct GLTable {
+  int order;
+  double x[64];
+  double w[64];
+};
+
+template <int ORDER>
+struct GL;
+
+template <>
+struct GL<10> {
+  static constexpr bool has_cpi = true;
+  __device__ __forceinline__ static int n(const GLTable*) { return 10; }
+  __device__ __forceinline__ static double x(int i, const GLTable*) {
+    constexpr double X[10] = {-0.9739065285171717,  -0.8650633666889844, -0.6794095682990244,
+                              -0.4333953941292472,  -0.14887433898163116, 0.14887433898163116,
+                              0.4333953941292472,   0.6794095682990244,  0.8650633666889844,
+                              0.9739065285171717};
+    return X[i];
+  }
+  __device__ __forceinline__ static double w(int i, const GLTable*) {
+    constexpr double W[10] = {0.06667134430868714, 0.14945134915058053, 0.21908636251598224,
+                              0.26926671930999674, 0.2955242247147533,  0.2955242247147533,
+                              0.26926671930999674, 0.21908636251598224, 0.14945134915058053,
+                              0.06667134430868714};
+    return W[i];
+  }
+  __device__ __forceinline__ static double cpi(int i) {
+    constexpr double C[10] = {0.9991601288170098,  0.9776208824732407,  0.8758595017700398,
+                              0.6293961480326326,  0.23172567069845093, -0.23172567069845082,
+                              -0.6293961480326326, -0.8758595017700398, -0.9776208824732407,
+                              -0.9991601288170098};
+    return C[i];
+  }
+};
+
+template <>
+struct GL<0> {
+  static constexpr bool has_cpi = false;
+  __device__ __forceinline__ static int n(const GLTable* t) { return t->order; }
+  __device__ __forceinline__ static double x(int i, const GLTable* t) { return t->x[i]; }
+  __device__ __forceinline__ static double w(int i, const GLTable* t) { return t->w[i]; }
+  __device__ __forceinline__ static double cpi(int) { return 0.0; }
+};
+
+// kite_area, limb_dark.py:187-196
+template <typename S>
+__device__ __forceinline__ S kite_area(S a, S b, S c) {
+  using B = typename BaseOf<S>::type;
+  S t0 = jmin(a, b), t1 = jmax(a, b);
+  a = t0;
+  b = t1;
+  t0 = jmin(b, c);
+  t1 = jmax(b, c);
+  b = t0;
+  c = t1;
+  t0 = jmin(a, b);
+  t1 = jmax(a, b);
+  a = t0;
+  b = t1;
+  S sq = (a + (b + c)) * (c - (a - b)) * (c + (a - b)) * (a + (b - c));
+  return jzsqrt(jmax(S(B(0)), sq));
+}
+
+// Solution vector (s0, s1, s2) for l_max <= 2, limb_dark.py:50-84 with kappas :102-108,
+// s0s2 :111-137 and the l = 1 term of p_integral :140-173.
+//   lmax 0: only s0 is meaningful; lmax 1: s0, s1; lmax 2: all.
+template <typename S, int ORDER>
+__device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* __restrict__ tab,
+                                            S& s0, S& s1, S& s2) {
+  using B = typename BaseOf<S>::type;
+  const B pi = Num<B>::pi;
+  const B eps10 = B(10) * Num<B>::eps;
+  b = jabs(b);
+  r = jabs(r);
+
+  // kappas(b, r) is evaluated on the ORIGINAL b (limb_dark.py:58)
+  const S b2o = b * b;
+  const S factor = (r - B(1)) * (r + B(1));
+  const bool cond_k = (val(b) > fabs(double(B(1) - val(r)))) && (val(b) < B(1) + val(r));
+  S area = S(B(0));
+  S kappa0, kappa1;
+  if (cond_k) {
+    area = kite_area(r, b, S(B(1)));
+    kappa0 = jatan2(area, b2o + factor);
+    kappa1 = jatan2(area, b2o - factor);
+  } else {
+    // area == 0 (constant): atan2(+0, x) is 0 for x >= +0 and pi for x < 0, derivative 0
+    kappa0 = S((val(b2o) + val(factor) < B(0)) ? pi : B(0));
+    kappa1 = S((val(b2o) - val(factor) < B(0)) ? pi : B(0));
+  }
+
+  const bool no_occ = val(b) >= B(1) + val(r);
+  const bool full_occ = B(1) + val(b) <= val(r);
+  const bool cond = no_occ || full_occ;
+  if (cond) {
+    // limb_dark.py:63-82 with b_ = 1: s0 = pi | 0, s2 = 0, P = 0
+    s0 = S(no_occ ? pi : B(0));
+    if (full_occ) s0 = S(B(0));
+    s2 = S(B(0));
+    s1 = -(kappa1 - pi) * B(2) / B(3);
+    return;
+  }
+
+  const S b2 = b2o;
+  const S r2 = r * r;
+
+  // s0s2, limb_dark.py:111-137
+  {
+    const S bpr = b + r;
+    const S onembpr2 = (B(1) + bpr) * (B(1) - bpr);
+    const S eta2 = r2 * (r2 + b2 * B(2)) * B(0.5);
+    const S delta = b * r * B(4);
+    const bool large = val(onembpr2) + val(delta) > val(delta);
+    if (large) {
+      s0 = (B(1) - r2) * pi;
+      s2 = s0 * B(2) + (eta2 - B(0.5)) * (B(4) * pi);
+    } else {
+      const S Alens = kappa1 + r2 * kappa0 - area * B(0.5);
+      s0 = pi - Alens;
+      s2 = s0 * B(2) +
+           (-(pi - kappa1) + eta2 * kappa0 * B(2) - area * (B(1) + r2 * B(5) + b2) * B(0.25)) *
+               B(2);
+    }
+  }
+  if (lmax < 1) {
+    s1 = S(B(0));
+    return;
+  }
+
+  // l = 1 term of p_integral, limb_dark.py:140-173, 184
+  const S rng = kappa0 * B(0.5);
+  const S two_br = b * r * B(2);
+  const S r2pb2 = r2 + b2;
+  const S two_r = r * B(2);
+  S acc = S(B(0));
+  const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
+  const int order = GL<ORDER>::n(tab);
+#pragma unroll
+  for (int i = 0; i < (ORDER > 0 ? ORDER : order); ++i) {
+    const B xi = B(GL<ORDER>::x(i, tab));
+    const B wi = B(GL<ORDER>::w(i, tab));
+    S c;
+    if (const_nodes)
+      c = S(B(GL<ORDER>::cpi(i)));
+    else
+      c = jcos(rng * xi + kappa0 * B(0.5));
+    S omz2 = jmax(S(B(0)), r2pb2 - two_br * c);
+    S z2 = B(1) - omz2;
+    const bool m = val(z2) < eps10;
+    z2 = jsel(m, S(B(1)), z2);
+    const S z3 = z2 * jzsqrt(z2);
+    const bool cnd = val(omz2) < eps10;
+    omz2 = jsel(cnd, S(B(1)), omz2);
+    S res = two_r * (r - b * c) * (B(1) - z3) / (omz2 * B(3));
+    res = jsel(cnd, S(B(0)), res);
+    acc = acc + res * wi;
+  }
+  const S P0 = rng * acc;
+  s1 = -P0 - (kappa1 - pi) * B(2) / B(3);
+}
+
+// Normalised Green's-basis coefficients for n_u <= 2, limb_dark.py:42-45, 87-99.
+template <typename S>
+__device__ __forceinline__ void ld_greens(int n_u, S u1, S u2, S& g0, S& g1, S& g2) {
+  using B = typename BaseOf<S>::type;
+  const B pi = Num<B>::pi;
+  if (n_u == 0) {
+    g0 = S(B(1) / pi);
+    g1 = S(B(0));
+    g2 = S(B(0));
+    return;
+  }
+  if (n_u == 1) {
+    g0 = B(1) - u1;
+    g1 = u1;
+    g2 = S(B(0));
+  } else {
+    g2 = u2 * B(-0.25);
+    g1 = u1 + u2 * B(2);
+    g0 = (B(1) - u1 - u2) + g2 * B(2);
+  }
+  const S norm = (g0 + g1 / B(1.5)) * pi;
+  g0 = g0 / norm;
+  g1 = g1 / norm;
+  g2 = g2 / norm;
+}
+
+template <typename S>
+__device__ __forceinline__ S ld_combine(int lmax, const S& s0, const S& s1, const S& s2,
+                                        const S& g0, const S& g1, const S& g2) {
+  using B = typename BaseOf<S>::type;
+  S f = s0 * g0;
+  if (lmax >= 1) f = f + s1 * g1;
+  if (lmax >= 2) f = f + s2 * g2;
+  return f - B(1);
+}
+
+}  // namespace jxp

@@ -1,0 +1,220 @@
+"""``light_curve(orbit, *u, order=10)(t)``: drop-in for
+src/jaxoplanet/light_curves/limb_dark.py:15-62.
+
+For a Keplerian ``System`` the whole chain time -> mean anomaly -> Kepler -> sky position
+-> b -> limb-darkened flux (and optionally exposure integration and a Gaussian
+log-likelihood) runs in ONE fused CUDA kernel (jxp_system_light_curve_*).  Any other
+object satisfying the ``LightCurveOrbit`` protocol (src/jaxoplanet/proto.py:8-20) goes
+through its own ``relative_position`` and the K2 kernel.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+
+import numpy as np
+import torch
+
+from jaxoplanet_b200 import _array as A
+from jaxoplanet_b200 import _lib, constants
+from jaxoplanet_b200.core.limb_dark import light_curve as _limb_dark_light_curve
+from jaxoplanet_b200.orbits.keplerian import System
+
+__all__ = ["light_curve", "log_likelihood"]
+
+
+def _field(x, n_sets, default=None):
+    if x is None:
+        x = default
+    x = torch.as_tensor(x, dtype=torch.float64) if not isinstance(x, torch.Tensor) else x.detach().to(torch.float64)
+    if x.ndim == 0:
+        return x.expand(n_sets)
+    return x
+
+
+def pack_bodies(system: System):
+    """-> (bodies [n_sets, n_bodies, 12] float64 tensor, n_sets, batched flag); the record
+    layout of include/jaxoplanet_b200.h (JXP_BODY_*)."""
+    n_sets = 1
+    batched = False
+    for body in system.bodies:
+        if body.period.ndim == 1:
+            batched = True
+            n_sets = max(n_sets, body.period.shape[0])
+    recs = []
+    for body in system.bodies:
+        dev = body.period.device
+        a = body.semimajor
+        if body.parallax is not None:  # keplerian.py:620-625 (positions in arcsec)
+            a = a * body.parallax / constants.au
+        circular = body.eccentricity is None
+        f = [None] * _lib.JXP_BODY_NFIELDS
+        f[_lib.BODY_PERIOD] = body.period
+        f[_lib.BODY_TIME_TRANSIT] = body.time_transit
+        f[_lib.BODY_TIME_REF] = body.time_ref
+        f[_lib.BODY_ECC] = -1.0 if circular else body.eccentricity
+        f[_lib.BODY_COS_OMEGA] = 1.0 if circular else body.cos_omega_peri
+        f[_lib.BODY_SIN_OMEGA] = 0.0 if circular else body.sin_omega_peri
+        f[_lib.BODY_COS_INCL] = body.cos_inclination
+        f[_lib.BODY_SIN_INCL] = body.sin_inclination
+        f[_lib.BODY_SEMIMAJOR] = a
+        f[_lib.BODY_CENTRAL_RADIUS] = body.central_radius
+        f[_lib.BODY_RADIUS] = 0.0 if body.radius is None else body.radius
+        f[_lib.BODY_RESERVED] = 0.0
+        recs.append(torch.stack([_field(x, n_sets).to(dev) for x in f], dim=-1))
+    bodies = torch.stack(recs, dim=1)  # [n_sets, n_bodies, 12]
+    return bodies, n_sets, batched
+
+
+@dataclass(frozen=True)
+class FusedSpec:
+    """Everything the fused kernel needs besides the time stamps."""
+
+    orbit: System
+    ld_u: object
+    order: int = 10
+    exposure_time: float | None = None
+    exp_order: int = 0
+    num_samples: int = 7
+    flags: int = 0
+
+
+def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=None):
+    orbit = spec.orbit
+    dt = dtype or A.result_dtype(time, spec.ld_u, *[b.period for b in orbit.bodies])
+    dev = A.device()
+    bodies, n_sets, batched = pack_bodies(orbit)
+    n_bodies = bodies.shape[1]
+    bodies = bodies.to(dev).contiguous()
+    u = spec.ld_u
+    u = u.detach().to(torch.float64) if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u, dtype=np.float64))
+    if u.ndim == 2:
+        if u.shape[0] != n_sets:
+            raise ValueError("batched limb-darkening coefficients must have shape (n_sets, n_u)")
+        u_stride = u.shape[1]
+        n_u = u.shape[1]
+    else:
+        u_stride = 0
+        n_u = u.shape[0]
+    u = u.to(dev).contiguous()
+    t = A.to_dev(time, torch.float64)
+    t_shape = tuple(t.shape)
+    t = t.reshape(-1)
+    n_times = t.numel()
+    ws_bytes = _lib.load().jxp_system_workspace_bytes(n_sets, n_bodies, n_times)
+    ws = torch.empty(max(int(ws_bytes), 256), dtype=torch.uint8, device=dev)
+    flux = flux_sum = loglike = None
+    yd = sd = None
+    s_stride = 0
+    if want == "flux":
+        flux = torch.empty((n_sets, n_times, n_bodies), dtype=dt, device=dev)
+    elif want == "flux_sum":
+        flux_sum = torch.empty((n_sets, n_times), dtype=dt, device=dev)
+    elif want == "loglike":
+        loglike = torch.empty((n_sets,), dtype=dt, device=dev)
+        yd = A.to_dev(y, dt).reshape(-1)
+        sd = A.to_dev(sigma, dt).reshape(-1)
+        if yd.numel() != n_times:
+            raise ValueError("y must have the shape of the time array")
+        if sd.numel() == 1:
+            s_stride = 0
+        elif sd.numel() == n_times:
+            s_stride = 1
+        else:
+            raise ValueError("sigma must be a scalar or have the shape of the time array")
+    else:
+        raise ValueError(want)
+    name = "jxp_system_light_curve_f64" if dt == torch.float64 else "jxp_system_light_curve_f32"
+    expo = 0.0 if spec.exposure_time is None else float(spec.exposure_time)
+    _lib.call(name, A.ptr(bodies), n_sets, n_bodies, A.ptr(u), n_u, u_stride, A.ptr(t), n_times,
+              expo, int(spec.exp_order), int(spec.num_samples), int(spec.order), int(spec.flags),
+              A.ptr(flux), A.ptr(flux_sum), A.ptr(yd), A.ptr(sd), s_stride, A.ptr(loglike),
+              A.ptr(ws), ws.numel(), A.stream_ptr())
+    if want == "flux":
+        out = flux.reshape((n_sets,) + t_shape + (n_bodies,))
+    elif want == "flux_sum":
+        out = flux_sum.reshape((n_sets,) + t_shape)
+    else:
+        out = loglike
+    if not batched:
+        out = out[0]
+    return out
+
+
+def _concat_u(u):
+    if not u:
+        return np.array([], dtype=np.float64)
+    if any(isinstance(u_, torch.Tensor) for u_ in u):
+        return torch.cat([torch.atleast_1d(torch.as_tensor(u_)) for u_ in u], dim=-1)
+    return np.concatenate([np.atleast_1d(np.asarray(u_, dtype=np.float64)) for u_ in u], axis=-1)
+
+
+def light_curve(orbit, *u, order: int = 10):
+    """Compute the light curve for (quadratic) polynomial limb darkening.
+
+    Args:
+        orbit: a Keplerian ``System`` (fused kernel) or any object with ``shape``,
+            ``radius``, ``central_radius`` and ``relative_position(t)``.
+        u: The coefficients of the polynomial limb darkening
+        order: The order of the numerical integration used by the backend
+
+    Returns:
+        A function which takes the time in days and returns the light curve flux
+        (``flux - 1`` per body, shape ``t.shape + orbit.shape``).
+    """
+    ld_u = _concat_u(u)
+
+    if isinstance(orbit, System):
+        spec = FusedSpec(orbit=orbit, ld_u=ld_u, order=order)
+
+        def light_curve_impl(time):
+            return A.like_input(_run_fused(spec, time), time)
+
+        light_curve_impl._jxp_spec = spec
+        return light_curve_impl
+
+    def light_curve_generic(time):
+        # light_curves/limb_dark.py:49-60 for a foreign orbit object
+        r_star = orbit.central_radius
+        x, y, z = orbit.relative_position(time)
+        dt = A.result_dtype(time)
+        x, y, z = (A.to_dev(v, dt) for v in (x, y, z))
+        r_star = A.to_dev(r_star, dt)
+        radius = A.to_dev(orbit.radius, dt)
+        n_b = x.shape[0] if x.ndim > np.ndim(time) else None
+        if n_b is not None:  # (n_bodies, *t.shape) -> t.shape + (n_bodies,)
+            x, y, z = (torch.movedim(v, 0, -1) for v in (x, y, z))
+        b = torch.sqrt(x**2 + y**2) / r_star
+        r = (radius / r_star).expand(b.shape).contiguous()
+        lc = _limb_dark_light_curve(A.to_dev(ld_u, dt), b.contiguous(), r, order=order)
+        lc = torch.where(z > 0, lc, torch.zeros_like(lc))
+        return A.like_input(lc, time)
+
+    return light_curve_generic
+
+
+def log_likelihood(orbit: System, *u, order: int = 10, exposure_time=None, exp_order: int = 0,
+                   num_samples: int = 7):
+    """Fused ``sum_t Normal(1 + sum_bodies light_curve, sigma).log_prob(y)`` per parameter
+    set (the NumPyro pattern of docs/tutorials/transit.ipynb cell 7) -- kernel K4.
+
+    Returns a function ``(t, y, sigma) -> loglike`` (scalar, or ``(n_sets,)`` when batched).
+    """
+    spec = FusedSpec(orbit=orbit, ld_u=_concat_u(u), order=order, exposure_time=exposure_time,
+                     exp_order=exp_order, num_samples=num_samples)
+
+    def impl(time, y, sigma):
+        return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma), time, y)
+
+    impl._jxp_spec = spec
+    return impl
+
+
+def with_spec(func, **changes):
+    spec = replace(func._jxp_spec, **changes)
+
+    def light_curve_impl(time):
+        return A.like_input(_run_fused(spec, time), time)
+
+    light_curve_impl._jxp_spec = spec
+    return light_curve_impl

@@ -1,0 +1,82 @@
+"""``integrate``: exposure-time integration, drop-in for
+src/jaxoplanet/light_curves/transforms.py:21-116.
+
+When ``func`` is a fused Keplerian light curve the sub-samples are folded into the same
+kernel tile (no extra launches, no intermediate arrays); any other callable is evaluated
+at ``t + dt_j`` and combined with the stencil, as the reference does.
+"""
+
+from __future__ import annotations
+
+from functools import wraps
+
+import numpy as np
+import torch
+
+from jaxoplanet_b200 import _array as A
+
+__all__ = ["integrate"]
+
+
+def _stencil(exposure_time, order, num_samples):
+    # transforms.py:67-89
+    num_samples = int(num_samples)
+    num_samples += 1 - num_samples % 2
+    stencil = np.ones(num_samples)
+    if order == 0:
+        dt = np.linspace(-0.5, 0.5, 2 * num_samples + 1)[1:-1:2]
+    elif order == 1:
+        dt = np.linspace(-0.5, 0.5, num_samples)
+        stencil = 2 * stencil
+        stencil[0] = 1
+        stencil[-1] = 1
+    elif order == 2:
+        dt = np.linspace(-0.5, 0.5, num_samples)
+        stencil[1:-1:2] = 4
+        stencil[2:-1:2] = 2
+    else:
+        raise ValueError("The parameter 'order' in 'integrate_exposure_time' must be 0, 1, or 2")
+    return dt * exposure_time, stencil / np.sum(stencil)
+
+
+def integrate(func, exposure_time=None, order: int = 0, num_samples: int = 7):
+    """Transform a light curve function to apply exposure time integration.
+
+    Args:
+        func: A light curve function which takes a time as the first argument
+        exposure_time: The exposure time (in days)
+        order: 0 (resampling, Kipping 2010), 1 (trapezoid) or 2 (Simpson)
+        num_samples: function evaluations per integral (made odd)
+    """
+    if exposure_time is None:
+        return func
+
+    if np.ndim(exposure_time) != 0:
+        raise ValueError(
+            "The exposure time passed to 'integrate_exposure_time' has shape "
+            f"{np.shape(exposure_time)}, but a scalar was expected; "
+            "To use exposure time integration with different exposures at different "
+            "times, manually 'vmap' or 'vectorize' the function"
+        )
+    if order not in (0, 1, 2):
+        raise ValueError("The parameter 'order' in 'integrate_exposure_time' must be 0, 1, or 2")
+
+    spec = getattr(func, "_jxp_spec", None)
+    if spec is not None and spec.exposure_time is None:
+        from jaxoplanet_b200.light_curves.limb_dark import with_spec
+
+        return with_spec(func, exposure_time=float(exposure_time), exp_order=int(order),
+                         num_samples=int(num_samples))
+
+    dt, stencil = _stencil(float(exposure_time), order, num_samples)
+
+    @wraps(func)
+    def wrapped(time, *args, **kwargs):
+        res = None
+        for d, w in zip(dt, stencil):
+            term = func(time + float(d), *args, **kwargs)
+            term = term * float(w)
+            res = term if res is None else res + term
+        return res
+
+    return wrapped

@@ -1,0 +1,125 @@
+"""CPU-only checks of the C-ABI boundary: the library loads without a GPU and exports every
+symbol include/jaxoplanet_b200.h declares; argument validation fails loudly with a message;
+the product package has no oracle import and no CPU fallback."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "jaxoplanet_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from jaxoplanet_b200 import build
+
+    build.build_library()
+    from jaxoplanet_b200 import _lib
+
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jxp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from jaxoplanet_b200 import _lib
+
+    names = declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.jxp_version() == 1
+
+
+def test_argument_validation_messages(lib):
+    # no compute: every call below must be rejected before any launch
+    rc = lib.jxp_kepler_f64(None, 1, None, 1, 10, None, None, None, None, None, None)
+    assert rc == -1 and b"null" in lib.jxp_last_error()
+    rc = lib.jxp_kepler_f64(None, 1, None, 1, -5, None, None, None, None, None, None)
+    assert rc == -2
+    assert lib.jxp_kepler_f64(None, 1, None, 1, 0, None, None, None, None, None, None) == 0
+    rc = lib.jxp_limb_dark_f64(None, 5, None, 1, None, 1, 10, 10, None, None, None, None, None)
+    assert rc == -3 and b"l_max" in lib.jxp_last_error()
+    rc = lib.jxp_limb_dark_f64(None, 2, None, 1, None, 1, 10, 0, None, None, None, None, None)
+    assert rc == -3
+    rc = lib.jxp_system_light_curve_f64(None, 4, 1, None, 2, 0, None, 100, 0.02, 3, 7, 10, 0,
+                                        None, None, None, None, 0, None, None, 0, None)
+    assert rc == -3 and b"must be 0, 1, or 2" in lib.jxp_last_error()
+    assert lib.jxp_system_workspace_bytes(4096, 1, 100000) > 4096 * 100
+    assert lib.jxp_system_workspace_bytes(0, 1, 10) == 0
+
+
+def test_facade_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+
+    from jaxoplanet_b200.core import kepler
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kepler(np.linspace(0, 1, 5), 0.1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "jaxoplanet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+    code = "import sys, jaxoplanet_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_body_validation_errors():
+    # keplerian.py:176-238 error behaviour
+    from jaxoplanet_b200.orbits.keplerian import Body, Central
+
+    with pytest.raises(ValueError, match="Exactly one of period or semimajor"):
+        Body(period=1.0, semimajor=2.0)
+    with pytest.raises(ValueError, match="must be scalars"):
+        Body(period=[1.0, 2.0])
+    with pytest.raises(ValueError, match="Both or neither of eccentricity and omega_peri"):
+        Body(period=1.0, eccentricity=0.1)
+    with pytest.raises(ValueError, match="Only one of impact_param and inclination"):
+        Body(period=1.0, impact_param=0.1, inclination=1.0)
+    with pytest.raises(ValueError, match="Only one of time_transit or time_peri"):
+        Body(period=1.0, time_transit=0.1, time_peri=1.0)
+    with pytest.raises(ValueError, match="exactly two of mass, radius, and density"):
+        Central(mass=1.0, radius=1.0, density=1.0)
+    with pytest.raises(ValueError, match="must be scalars"):
+        Central(mass=[1.0, 2.0], radius=1.0)
+
+
+def test_orbital_constants_match_oracle():
+    # host-side mirror of OrbitalBody.__init__ (keplerian.py:262-340) vs the oracle
+    import numpy as np
+
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+    from oracle import ref_numpy as ref
+
+    kw = dict(period=3.456, time_transit=0.3, impact_param=0.3, radius=0.1, eccentricity=0.1,
+              omega_peri=0.5)
+    body = System(Central(mass=1.3, radius=1.1)).add_body(**kw).bodies[0]
+    want = ref.orbital_body(central_mass=1.3, central_radius=1.1, **kw)
+    for name in ("period", "semimajor", "time_transit", "time_ref", "sin_omega_peri",
+                 "cos_omega_peri", "sin_inclination", "cos_inclination", "impact_param"):
+        np.testing.assert_allclose(float(getattr(body, name)), want[name], rtol=2e-16, atol=1e-300,
+                                   err_msg=name)
+    # circular body, inclination given
+    body = System().add_body(period=12.5, inclination=0.3, mass=0.1).bodies[0]
+    want = ref.orbital_body(period=12.5, inclination=0.3, mass=0.1)
+    for name in ("semimajor", "time_ref", "sin_inclination", "cos_inclination", "impact_param"):
+        np.testing.assert_allclose(float(getattr(body, name)), want[name], rtol=4e-16, err_msg=name)
