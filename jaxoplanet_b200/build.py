@@ -19,6 +19,8 @@ LIB_PATH = os.path.join(LIB_DIR, "libjxp_b200.so")
 SOURCES = ["jxp_kernels.cu", "jxp_partials.cu"]
 HEADERS = [
     os.path.join(CSRC, "jxp_scalar.cuh"),
+    os.path.join(CSRC, "jxp_fastmath.cuh"),
+    os.path.join(CSRC, "jxp_host.h"),
     os.path.join(CSRC, "jxp_math.cuh"),
     os.path.join(CSRC, "jxp_orbit.cuh"),
     os.path.join(ROOT, "include", "jaxoplanet_b200.h"),

@@ -1,0 +1,105 @@
+// Branch-free FP64 primitives for the hot loops: reciprocal, division, square root and
+// sine/cosine on a bounded range.  The CUDA library versions carry slow-path calls
+// (denormals, huge arguments) that are never taken here but cost instruction-cache
+// footprint and registers; the fused kernels are instruction-fetch bound when those are
+// inlined ten times per sample (profiles/r1_c3_first.md).  Each routine is a hardware seed
+// (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20) refined with FMAs to <= 1 ulp.
+//
+// Domain: finite, normal-range inputs (what the hot path produces); zeros are handled where
+// the formulas can produce them (sqrt(0) = 0).  NaN in -> NaN out.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace jxp {
+
+__device__ __forceinline__ double rcp_seed(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+// 1 / x, ~1 ulp
+__device__ __forceinline__ double frcp(double x) {
+  double y = rcp_seed(x);
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);  // third-order step: y (1 + e + e^2)
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// a / b, <= 1 ulp (residual-corrected)
+__device__ __forceinline__ double fdiv(double a, double b) {
+  double y = rcp_seed(b);
+  double e = fma(-b, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  double q = a * y;
+  double r = fma(-b, q, a);
+  return fma(r, y, q);
+}
+
+// sqrt(x) for x >= 0 (0 -> 0, tiny/denormal -> 0), <= 1 ulp
+__device__ __forceinline__ double fsqrt(double x) {
+  double y = rsqrt_seed(x);
+  double g = x * y;
+  double h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  double p = fma(r, 1.5, 1.0) * r;  // r + 1.5 r^2
+  g = fma(g, p, g);
+  h = fma(h, p, h);
+  double d = fma(-g, g, x);
+  g = fma(d, h, g);
+  return (x > 2.3e-308) ? g : ((x >= 0.0) ? 0.0 : nan(""));
+}
+
+// sin and cos for |x| <~ 1e4: two-term Cody-Waite reduction by pi/2 and the classic
+// minimax kernels on [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin.c / k_cos.c, public domain).
+__device__ __forceinline__ void fsincos(double x, double* sp, double* cp) {
+  const double two_over_pi = 6.36619772367581382433e-01;
+  const double pio2_hi = 1.57079632679489655800e+00;
+  const double pio2_lo = 6.12323399573676603587e-17;
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, two_over_pi, magic);
+  const int q = __double2loint(t);
+  const double qd = t - magic;
+  double r = fma(-qd, pio2_hi, x);
+  r = fma(-qd, pio2_lo, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const bool swap = q & 1;
+  double so = swap ? c : s;
+  double co = swap ? s : c;
+  if (q & 2) so = -so;
+  if ((q + 1) & 2) co = -co;
+  *sp = so;
+  *cp = co;
+}
+
+__device__ __forceinline__ double fcos(double x) {
+  double s, c;
+  fsincos(x, &s, &c);
+  return c;
+}
+
+}  // namespace jxp

@@ -1,0 +1,22 @@
+// Host-side helpers shared by the translation units of libjxp_b200 (not part of the ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "jxp_math.cuh"
+
+namespace jxph {
+constexpr int MAX_SUB = 64;
+struct Stencil {
+  int n;
+  double dt[MAX_SUB];
+  double w[MAX_SUB];
+};
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+bool stride_ok(int64_t s);
+int sm_count();
+void gl_table_host(int order, jxp::GLTable& tab);
+int make_stencil(double exposure_time, int order, int num_samples, Stencil& st);
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace jxph

@@ -10,16 +10,20 @@
 #include <cstring>
 #include <mutex>
 
+#include "jxp_host.h"
 #include "jxp_orbit.cuh"
 
 using namespace jxp;
+using namespace jxph;
 
 // ======================================================================================
 // error plumbing
 // ======================================================================================
 namespace {
 thread_local char g_err[512] = "";
+}
 
+namespace jxph {
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -93,7 +97,7 @@ void gl_table_host(int order, GLTable& tab) {
     tab.w[order - 1 - i] = w;
   }
 }
-}  // namespace
+}  // namespace jxph
 
 extern "C" int jxp_version(void) { return JXP_ABI_VERSION; }
 extern "C" const char* jxp_last_error(void) { return g_err; }
@@ -113,7 +117,7 @@ k_kepler(const T* __restrict__ M, int64_t Ms, const T* __restrict__ ecc, int64_t
     const T ome = T(1) - e, ope = T(1) + e;
     const T ome2 = ome * ope;
     const T s1me2 = jsqrt(ome2);
-    const T inv_ope = T(1) / ope;
+    const T inv_ope = jrcp(ope);
     const T Mr = mod_two_pi(m);
     T sf, cf, E;
     kepler_reduced<T, EXTRA>(Mr, e, ome, ope, s1me2, inv_ope, sf, cf, E);
@@ -124,9 +128,9 @@ k_kepler(const T* __restrict__ M, int64_t Ms, const T* __restrict__ ecc, int64_t
       if (dfdM_o || dfde_o) {
         // kepler.py:64-77
         const T ecosf = e * cf;
-        const T inv = T(1) / ome2;
+        const T inv = jrcp(ome2);
         const T opc = T(1) + ecosf;
-        if (dfdM_o) dfdM_o[i] = opc * opc * inv / s1me2;
+        if (dfdM_o) dfdM_o[i] = jdiv(opc * opc * inv, s1me2);
         if (dfde_o) dfde_o[i] = (T(2) + ecosf) * sf * inv;
       }
     }
@@ -285,15 +289,10 @@ extern "C" int jxp_limb_dark_f32(const float* u, int32_t n_u, const float* b, in
 // ======================================================================================
 namespace {
 constexpr int SYS_K = 4;          // time samples held in registers per thread
-constexpr int SYS_MAX_SETS = 32;  // parameter sets per CTA (upper bound)
-constexpr int MAX_SUB = 64;
+constexpr int SYS_MAX_SETS = 64;  // parameter sets per CTA (upper bound)
+}  // namespace
 
-struct Stencil {
-  int n;
-  double dt[MAX_SUB];
-  double w[MAX_SUB];
-};
-
+namespace jxph {
 // transforms.py:67-89
 int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) {
   if (!(exposure_time > 0.0) || num_samples <= 0) {
@@ -337,8 +336,9 @@ int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) 
   }
   return JXP_OK;
 }
+}  // namespace jxph
 
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+namespace {
 
 // workspace carving shared by the size query and the launchers
 struct SysLayout {
@@ -459,6 +459,19 @@ k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss,
   }
 }
 
+namespace jxph {
+int launch_loglike_prep_f64(const double* y, const double* sigma, int64_t ss, int64_t n, double* winv,
+                            double* scalars, cudaStream_t st) {
+  k_loglike_prep<double><<<1, 1024, 0, st>>>(y, sigma, ss, n, winv, scalars);
+  return check_launch("loglike prep");
+}
+int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int64_t n, float* winv,
+                            double* scalars, cudaStream_t st) {
+  k_loglike_prep<float><<<1, 1024, 0, st>>>(y, sigma, ss, n, winv, scalars);
+  return check_launch("loglike prep");
+}
+}  // namespace jxph
+
 template <typename T>
 __global__ void k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
                                 const double* __restrict__ scalars, T* __restrict__ loglike) {
@@ -540,22 +553,21 @@ __global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<
     const SetC<T> sc = sset[sl];
     double dchi = 0.0;
     bool hit = false;
-#pragma unroll
+    // not unrolled: ONE instance of the in-transit code per kernel (instruction-cache footprint)
+#pragma unroll 1
     for (int k = 0; k < SYS_K; ++k) {
       const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
       if (idx >= a.n_times) continue;
+      const double tkk = pick(tk, k);
       T total = T(0);
+#pragma unroll 1
       for (int body = 0; body < a.n_bodies; ++body) {
         const BodyC<T>& c = sbody[sl * a.n_bodies + body];
-        T acc;
-        if (nsub == 1) {
-          acc = eval_sample<T, ORDER>(c, sc, &a.tab, tk[k], use_window);
-        } else {
-          acc = T(0);
-          for (int j = 0; j < nsub; ++j) {
-            const T v = eval_sample<T, ORDER>(c, sc, &a.tab, tk[k] + a.st.dt[j], use_window);
-            acc = jfma(T(a.st.w[j]), v, acc);
-          }
+        T acc = T(0);
+#pragma unroll 1
+        for (int j = 0; j < nsub; ++j) {
+          const T v = eval_sample<T, ORDER>(c, sc, &a.tab, tkk + a.st.dt[j], use_window);
+          acc = (nsub == 1) ? v : jfma(T(a.st.w[j]), v, acc);
         }
         if (a.flux) a.flux[((size_t)set * a.n_times + idx) * a.n_bodies + body] = acc;
         total += acc;
@@ -564,8 +576,9 @@ __global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<
       if (LOGLIKE) {
         if (total != T(0)) {
           // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: the change of chi^2 w.r.t. the zero model
-          const T mw = total * wk[k];
-          dchi += (double)(-mw) * (double)(T(2) * r0k[k] - mw);
+          const T wkk = pick(wk, k);
+          const T mw = total * wkk;
+          dchi += (double)(-mw) * (double)(T(2) * pick(r0k, k) - mw);
           hit = true;
         }
       }

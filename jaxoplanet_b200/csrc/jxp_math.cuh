@@ -66,7 +66,7 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
   T w = jcbrt(jabs(r) + jsqrt(jfma(q2, q, r * r)));
   w = w * w;
   const T W = jfma(w, w + q, q2);
-  const T E0 = jfma(T(2) * r, w, M * W) / (W * d);
+  const T E0 = jdiv(jfma(T(2) * r, w, M * W), W * d);
 
   // refine, kepler.py:95-108
   T hs, hc;
@@ -78,11 +78,11 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
   const T f1 = jfma(e, cE, ome);
   const T f2 = e * sinE;
   const T f3 = T(1) - f1;
-  const T d3 = -f0 * f1 / jfma(T(-0.5) * f0, f2, f1 * f1);
-  const T d4 = -f0 / jfma(d3 * d3, f3 * T(1.0 / 6.0), jfma(T(0.5) * d3, f2, f1));
+  const T d3 = jdiv(-f0 * f1, jfma(T(-0.5) * f0, f2, f1 * f1));
+  const T d4 = jdiv(-f0, jfma(d3 * d3, f3 * T(1.0 / 6.0), jfma(T(0.5) * d3, f2, f1)));
   const T d42 = d4 * d4;
-  const T dE = -f0 / jfma(-d42 * d4, f2 * T(1.0 / 24.0),
-                          jfma(d42, f3 * T(1.0 / 6.0), jfma(T(0.5) * d4, f2, f1)));
+  const T dE = jdiv(-f0, jfma(-d42 * d4, f2 * T(1.0 / 24.0),
+                               jfma(d42, f3 * T(1.0 / 6.0), jfma(T(0.5) * d4, f2, f1))));
 
   // advance the half angle by dE/2
   const T h = T(0.5) * dE;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
 
   const T ss = s * s, cc = c * c;
   const T a = ome * cc, b = ope * ss;
-  const T invD = T(1) / (a + b);
+  const T invD = jrcp(a + b);
   const T sf = T(2) * s1me2 * s * c * invD;
   sinf = high ? -sf : sf;
   cosf = (a - b) * invD;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     s0 = S(no_occ ? pi : B(0));
     if (full_occ) s0 = S(B(0));
     s2 = S(B(0));
-    s1 = -(kappa1 - pi) * B(2) / B(3);
+    s1 = -(kappa1 - pi) * B(2.0 / 3.0);
     return;
   }
 
@@ -247,7 +247,7 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
   const S rng = kappa0 * B(0.5);
   const S two_br = b * r * B(2);
   const S r2pb2 = r2 + b2;
-  const S two_r = r * B(2);
+  const S two_r_3 = r * B(2.0 / 3.0);
   S acc = S(B(0));
   const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
   const int order = GL<ORDER>::n(tab);
@@ -260,19 +260,20 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
       c = S(B(GL<ORDER>::cpi(i)));
     else
       c = jcos(rng * xi + kappa0 * B(0.5));
-    S omz2 = jmax(S(B(0)), r2pb2 - two_br * c);
-    S z2 = B(1) - omz2;
-    const bool m = val(z2) < eps10;
-    z2 = jsel(m, S(B(1)), z2);
-    const S z3 = z2 * jzsqrt(z2);
-    const bool cnd = val(omz2) < eps10;
-    omz2 = jsel(cnd, S(B(1)), omz2);
-    S res = two_r * (r - b * c) * (B(1) - z3) / (omz2 * B(3));
-    res = jsel(cnd, S(B(0)), res);
+    const S omz2 = jmax(S(B(0)), r2pb2 - two_br * c);
+    const S z2 = B(1) - omz2;
+    // limb_dark.py:164-172: the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0
+    // where z^2 < 10 eps (z2 := 1 there) or 1 - z^2 < 10 eps.  (1 - z^3) / (1 - z^2) is evaluated
+    // as 1 + z^2 / (1 + z): the same function without the cancellation in 1 - z^3.
+    const bool dead = (val(z2) < eps10) || (val(omz2) < eps10);
+    const S z2s = jsel(dead, S(B(1)), z2);
+    const S z = jzsqrt(z2s);
+    S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
+    res = jsel(dead, S(B(0)), res);
     acc = acc + res * wi;
   }
   const S P0 = rng * acc;
-  s1 = -P0 - (kappa1 - pi) * B(2) / B(3);
+  s1 = -P0 - (kappa1 - pi) * B(2.0 / 3.0);
 }
 
 // Normalised Green's-basis coefficients for n_u <= 2, limb_dark.py:42-45, 87-99.

@@ -96,16 +96,38 @@ __device__ __forceinline__ double mean_anomaly_reduced(const BodyC<T>& c, double
   return mod_two_pi(M);
 }
 
-// Sky-projected separation (in R*) and the z > 0 test for one sample.
+// Sky-projected separation (in R*) and the z > 0 test for one sample.  S is T or Dual<T, N>.
+template <typename S, typename B>
+__device__ __forceinline__ void sky_position_g(const S& e, const S& cw, const S& sw, const S& ci,
+                                               const S& si, const S& na_ome2, B inv_rstar,
+                                               const S& sf, const S& cf, S& b, S& Z) {
+  const S r0 = jdiv(na_ome2, e * cf + B(1));  // keplerian.py:630
+  const S x0 = r0 * cf, y0 = r0 * sf;
+  const S x1 = cw * x0 - sw * y0;  // :568-569
+  const S y1 = sw * x0 + cw * y0;
+  const S Y = ci * y1;  // :575-576
+  Z = -(si * y1);
+  b = jsqrt(x1 * x1 + Y * Y) * inv_rstar;  // light_curves/limb_dark.py:53
+}
+
 template <typename T>
 __device__ __forceinline__ void sky_position(const BodyC<T>& c, T sf, T cf, T& b, T& Z) {
-  const T r0 = c.na_ome2 / jfma(c.e, cf, T(1));  // keplerian.py:630
+  const T r0 = jdiv(c.na_ome2, jfma(c.e, cf, T(1)));  // keplerian.py:630
   const T x0 = r0 * cf, y0 = r0 * sf;
   const T x1 = jfma(c.cw, x0, -c.sw * y0);       // :568-569
   const T y1 = jfma(c.sw, x0, c.cw * y0);
   const T Y = c.ci * y1;                         // :575-576
   Z = -c.si * y1;
   b = jsqrt(jfma(x1, x1, Y * Y)) * c.inv_rstar;  // light_curves/limb_dark.py:53
+}
+
+// Register-array element by a runtime index (select chain; keeps the array in registers).
+template <typename V, int K>
+__device__ __forceinline__ V pick(const V (&a)[K], int k) {
+  V r = a[0];
+#pragma unroll
+  for (int i = 1; i < K; ++i) r = (k == i) ? a[i] : r;
+  return r;
 }
 
 // flux - 1 of one body at one time (0 when not in transit).

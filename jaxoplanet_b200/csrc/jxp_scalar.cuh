@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "jxp_fastmath.cuh"
+
 namespace jxp {
 
 template <typename T>
@@ -36,9 +38,9 @@ struct Num<float> {
 // ---- primitive wrappers on plain types -------------------------------------------
 __device__ __forceinline__ double jfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float jfma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ double jsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double jsqrt(double x) { return fsqrt(x); }
 __device__ __forceinline__ float jsqrt(float x) { return sqrtf(x); }
-__device__ __forceinline__ double jzsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double jzsqrt(double x) { return fsqrt(x); }
 __device__ __forceinline__ float jzsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double jcbrt(double x) { return cbrt(x); }
 __device__ __forceinline__ float jcbrt(float x) { return cbrtf(x); }
@@ -50,12 +52,20 @@ __device__ __forceinline__ double jmin(double a, double b) { return fmin(a, b); 
 __device__ __forceinline__ float jmin(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double jatan2(double y, double x) { return atan2(y, x); }
 __device__ __forceinline__ float jatan2(float y, float x) { return atan2f(y, x); }
-__device__ __forceinline__ double jcos(double x) { return cos(x); }
+__device__ __forceinline__ double jcos(double x) { return fcos(x); }
 __device__ __forceinline__ float jcos(float x) { return cosf(x); }
-__device__ __forceinline__ double jsin(double x) { return sin(x); }
+__device__ __forceinline__ double jsin(double x) {
+  double s_, c_;
+  fsincos(x, &s_, &c_);
+  return s_;
+}
 __device__ __forceinline__ float jsin(float x) { return sinf(x); }
-__device__ __forceinline__ void jsincos(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ void jsincos(double x, double* s, double* c) { fsincos(x, s, c); }
 __device__ __forceinline__ void jsincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ double jdiv(double a, double b) { return fdiv(a, b); }
+__device__ __forceinline__ float jdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ double jrcp(double x) { return frcp(x); }
+__device__ __forceinline__ float jrcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ double jfloor(double x) { return floor(x); }
 __device__ __forceinline__ float jfloor(float x) { return floorf(x); }
 __device__ __forceinline__ double jsel(bool c, double a, double b) { return c ? a : b; }
@@ -121,8 +131,8 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator*(const JXP_D& a, const JX
 }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator/(const JXP_D& a, const JXP_D& b) {
   JXP_D r;
-  T inv = T(1) / b.v;
-  r.v = a.v * inv;
+  T inv = jrcp(b.v);
+  r.v = jdiv(a.v, b.v);
   JXP_FOR r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
   return r;
 }
@@ -152,12 +162,14 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator*(const JXP_D& a, T b) {
 }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator*(T a, const JXP_D& b) { return b * a; }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator/(const JXP_D& a, T b) {
-  T inv = T(1) / b;
+  T inv = jrcp(b);
   return a * inv;
 }
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jdiv(const JXP_D& a, const JXP_D& b) { return a / b; }
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jdiv(const JXP_D& a, T b) { return a / b; }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D operator/(T a, const JXP_D& b) {
   JXP_D r;
-  T inv = T(1) / b.v;
+  T inv = jrcp(b.v);
   r.v = a * inv;
   T f = -r.v * inv;
   JXP_FOR r.d[i] = f * b.d[i];
@@ -171,7 +183,7 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jfma(const JXP_D& a, const JXP_D& 
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jsqrt(const JXP_D& x) {
   JXP_D r;
   r.v = jsqrt(x.v);
-  T f = T(0.5) / r.v;
+  T f = T(0.5) * jrcp(r.v);
   JXP_FOR r.d[i] = x.d[i] * f;
   return r;
 }
@@ -180,7 +192,7 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jzsqrt(const JXP_D& x) {
   JXP_D r;
   r.v = jsqrt(x.v);
   T denom = (x.v < T(10) * Num<T>::eps) ? T(1) : x.v;
-  T f = T(0.5) * r.v / denom;
+  T f = T(0.5) * r.v * jrcp(denom);
   JXP_FOR r.d[i] = x.d[i] * f;
   return r;
 }
@@ -210,7 +222,7 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jmin(const JXP_D& a, const JXP_D& 
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jatan2(const JXP_D& y, const JXP_D& x) {
   JXP_D r;
   r.v = jatan2(y.v, x.v);
-  T inv = T(1) / (x.v * x.v + y.v * y.v);
+  T inv = jrcp(x.v * x.v + y.v * y.v);
   T fy = x.v * inv, fx = -y.v * inv;
   JXP_FOR r.d[i] = fy * y.d[i] + fx * x.d[i];
   return r;

@@ -462,3 +462,137 @@ def test_positions_and_impact_parameter():
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * bd["semimajor"])
     xs, ys, zs = system.relative_position(t)
     assert xs.shape == (1, 500)
+
+
+# ----------------------------------------------------------------------------- K5
+def _partials_oracle(theta, t, u_shared=True):
+    """Per-point partials from torch-f64 autograd over the restatement: every parameter is
+    expanded to one copy per time sample so that one backward pass yields d flux_t / d theta_k."""
+    import torch
+
+    TH = ref.torch_backend()
+    n_t = t.shape[0]
+    tt = torch.tensor(t)
+    names = ("period", "time_transit", "eccentricity", "omega_peri", "impact_param", "radius")
+    par = {k: torch.full((n_t,), float(theta[i]), dtype=torch.float64, requires_grad=True)
+           for i, k in enumerate(names)}
+    u = torch.tensor(theta[6:8], requires_grad=True)
+    bd = ref.orbital_body(xp=TH, **par)
+    flux = ref.system_light_curve([bd], u, tt, xp=TH)[:, 0]
+    grads = torch.autograd.grad(flux.sum(), list(par.values()), allow_unused=True)
+    part = np.zeros((8, n_t))
+    for i, g in enumerate(grads):
+        if g is not None:
+            part[i] = g.numpy()
+    # d flux / d u per point: flux = s . g(u) - 1 (limb_dark.py:45-47)
+    x, y, z = ref.relative_position({k: (v.detach().numpy() if hasattr(v, "detach") else v) for k, v in bd.items()}, t)
+    b = np.sqrt(x**2 + y**2)
+    s = ref.solution_vector(2, b, np.full_like(b, theta[5]))
+    s = [np.where(z > 0, sk, 0.0) for sk in s]
+    uu = torch.tensor(theta[6:8], requires_grad=True)
+    g = ref.greens_basis_transform(uu, TH)
+    g = g / (np.pi * (g[0] + g[1] / 1.5))
+    J = np.stack([torch.autograd.grad(g[k], uu, retain_graph=True)[0].numpy() for k in range(3)])  # [3, 2]
+    for j in range(2):
+        part[6 + j] = sum(s[k] * J[k, j] for k in range(3))
+    return flux.detach().numpy(), part
+
+
+def _theta_sets(rng, n_sets):
+    P = rng.uniform(2, 5, n_sets)
+    q = rng.uniform(0.05, 0.95, (n_sets, 2))
+    return np.stack([P, rng.uniform(0, 1, n_sets) * P, rng.uniform(0.01, 0.3, n_sets),
+                     rng.uniform(-np.pi, np.pi, n_sets), rng.uniform(0.02, 0.95, n_sets),
+                     rng.uniform(0.03, 0.15, n_sets), 2 * np.sqrt(q[:, 0]) * q[:, 1],
+                     np.sqrt(q[:, 0]) * (1 - 2 * q[:, 1])], 1)
+
+
+def test_transit_partials_vs_autograd_oracle():
+    # BASELINE config 5 at test size; tolerance 1e-9 relative (north_star), contact points
+    # excluded as the reference does (tests/core/limb_dark_test.py:42-45)
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    rng = np.random.default_rng(3)
+    n_sets, n_t = 5, 6000
+    theta = _theta_sets(rng, n_sets)
+    t = np.arange(n_t) * (2.0 / 1440.0)
+    res = transit_partials(theta, t)
+    assert res["flux"].shape == (n_sets, n_t) and res["partials"].shape == (n_sets, 8, n_t)
+    n_checked = 0
+    for s in range(n_sets):
+        flux0, part0 = _partials_oracle(theta[s], t)
+        _flux_close(res["flux"][s], flux0)
+        bd = ref.orbital_body(**dict(zip(("period", "time_transit", "eccentricity", "omega_peri",
+                                          "impact_param", "radius"), theta[s, :6])))
+        x, y, z = ref.relative_position(bd, t)
+        b = np.sqrt(x**2 + y**2)
+        r = theta[s, 5]
+        ok = (np.abs(b - r) > 1e-6) & (np.abs(np.abs(b - r) - 1) > 1e-6) & (np.abs(b - 1 - r) > 1e-6) & (b > 1e-6)
+        got = res["partials"][s]
+        scale = np.array([1e-1, 1e-1, 1e-2, 1e-2, 1e-2, 1e-2, 1e-3, 1e-3])[:, None]
+        err = np.abs(got - part0) / np.maximum(np.abs(part0), scale)
+        assert np.max(err[:, ok]) <= 1e-9, (s, np.max(err[:, ok], axis=1))
+        assert np.all(got[:, flux0 == 0] == 0)
+        n_checked += int(np.sum(flux0 != 0))
+    assert n_checked > 200
+
+
+def test_transit_partials_loglike_gradient_and_supersampling():
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    rng = np.random.default_rng(4)
+    n_sets, n_t = 9, 8000
+    theta = _theta_sets(rng, n_sets)
+    t = np.arange(n_t) * (10.0 / 1440.0)
+    texp = 10.0 / 1440.0
+    res0 = transit_partials(theta, t, exposure_time=texp, exp_order=0, num_samples=5)
+    flux = res0["flux"]
+    y = 1 + flux[0] + 5e-4 * np.random.default_rng(42).normal(size=n_t)
+    sigma = 5e-4 * (1 + 0.2 * rng.uniform(size=n_t))
+    res = transit_partials(theta, t, exposure_time=texp, exp_order=0, num_samples=5, y=y, sigma=sigma)
+    np.testing.assert_array_equal(res["flux"], flux)
+    # the fused reductions against numpy reductions of the kernel's own per-point outputs
+    m = 1 + flux
+    want_ll = ref.gaussian_loglike(m, y[None, :], sigma[None, :])
+    np.testing.assert_allclose(res["loglike"], want_ll, rtol=1e-12)
+    want_g = np.einsum("st,skt->sk", (y[None, :] - m) / sigma[None, :] ** 2, res["partials"])
+    np.testing.assert_allclose(res["dloglike"], want_g, rtol=1e-9, atol=1e-9 * np.abs(want_g).max())
+    # supersampled flux against the oracle
+    for s in range(3):
+        bd = ref.orbital_body(**dict(zip(("period", "time_transit", "eccentricity", "omega_peri",
+                                          "impact_param", "radius"), theta[s, :6])))
+        want = ref.integrate(lambda tt: ref.system_light_curve([bd], theta[s, 6:8], tt), texp, 0, 5)(t)[:, 0]
+        _flux_close(flux[s], want)
+    # finite-difference check of d loglike / d theta (independent of the autograd oracle)
+    k_scale = [1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-8, 1e-7, 1e-7]
+    for k in range(8):
+        h = k_scale[k]
+        tp, tm = theta.copy(), theta.copy()
+        tp[:, k] += h
+        tm[:, k] -= h
+        lp = transit_partials(tp, t, exposure_time=texp, num_samples=5, y=y, sigma=sigma, want_partials=False)["loglike"]
+        lm = transit_partials(tm, t, exposure_time=texp, num_samples=5, y=y, sigma=sigma, want_partials=False)["loglike"]
+        fd = (lp - lm) / (2 * h)
+        np.testing.assert_allclose(res["dloglike"][:, k], fd, rtol=2e-4, atol=2e-4 * np.abs(fd).max())
+
+
+def test_transit_partials_f32_and_autograd_function():
+    import torch
+
+    from jaxoplanet_b200.light_curves.partials import TransitLightCurve, transit_partials
+
+    rng = np.random.default_rng(5)
+    theta = _theta_sets(rng, 4)
+    t = 500.0 + np.arange(5000) * (2.0 / 1440.0)
+    r64 = transit_partials(theta, t)
+    r32 = transit_partials(theta, t, dtype=torch.float32)
+    assert r32["flux"].dtype == np.float32
+    assert np.max(np.abs(r32["flux"] - r64["flux"])) <= 1e-6
+    scale = np.maximum(np.abs(r64["partials"]).max(axis=2, keepdims=True), 1e-3)
+    assert np.max(np.abs(r32["partials"] - r64["partials"]) / scale) <= 5e-3
+    th = torch.tensor(theta, device="cuda", requires_grad=True)
+    f = TransitLightCurve.apply(th, torch.tensor(t, device="cuda"), 1.0, 1.0)
+    w = torch.tensor(rng.normal(size=f.shape), device="cuda")
+    (g,) = torch.autograd.grad((f * w).sum(), th)
+    want = np.einsum("st,skt->sk", w.cpu().numpy(), r64["partials"])
+    np.testing.assert_allclose(g.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
