@@ -148,6 +148,13 @@ int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_b
                                const float* sigma, int64_t sigma_stride, float* loglike,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement helper: how much work the LAST jxp_system_light_curve_* call on this workspace
+ * actually executed -- stats_host[0] = Kepler solves, stats_host[1] = limb-darkening
+ * evaluations (host memory, 2 x int64).  Copies device -> host and SYNCHRONISES `stream`;
+ * bench.py uses it so that the roofline counts executed work, not skipped samples. */
+int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, int64_t n_times,
+                     int64_t* stats_host, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K5  flux and its forward-mode partials w.r.t. the 8 sampled parameters of a single
  *     transiting planet, theta = (period, time_transit, eccentricity, omega_peri,

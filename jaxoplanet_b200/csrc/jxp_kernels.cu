@@ -372,7 +372,7 @@ template <typename T>
 __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
                            BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
-                           double widen, double margin) {
+                           unsigned long long* __restrict__ counters, double widen, double margin) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sets * n_bodies) return;
   const double* p = bodies + (size_t)i * JXP_BODY_NFIELDS;
@@ -407,6 +407,10 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
   c.onepr = T(1.0 + fabs(rr));
   transit_window(c, a, rstar, e, widen, margin);
   out_b[i] = c;
+  if (i == 0) {  // executed-work counters of this call (jxp_system_stats)
+    counters[0] = 0ull;
+    counters[1] = 0ull;
+  }
   if (i % n_bodies == 0) {
     const int s = i / n_bodies;
     const double* us = u + (size_t)s * u_stride;
@@ -494,17 +498,23 @@ struct SysArgs {
   const T* y;
   const T* winv;
   double* partial;  // [n_sets][n_tiles]
+  unsigned long long* counters;  // [2]: Kepler solves, limb-darkening evaluations executed
   Stencil st;
   GLTable tab;
 };
 
 // CTA = (tile of blockDim.x * SYS_K time samples) x (group of sets_per_cta parameter sets).
-// Each thread keeps its SYS_K time stamps (and, for the likelihood, the zero-model
-// residuals) in registers and walks over the sets of the group, whose records were staged
-// in shared memory once per CTA; the per-set record is read as a warp-wide broadcast.
+// A warp owns 32 * SYS_K consecutive time samples as SYS_K rows of 32 (lane = column), kept in
+// registers, and walks over the sets of the group, whose records were staged in shared memory
+// once per CTA (read back as warp-wide broadcasts).  Per (set, body, sub-sample) a thread first
+// rejects its samples against the body's transit window (one interval test for all SYS_K when
+// they are time-ordered, else one phase test each) and then runs the in-transit code -- a
+// single instance in the kernel -- only for the surviving samples; lanes whose surviving
+// samples sit in different rows proceed together.
 template <typename T, int ORDER, bool LOGLIKE>
-__global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int K = SYS_K;
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   const int tile = blockIdx.x % a.n_tiles;
@@ -529,62 +539,89 @@ __global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<
     for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
   }
 
-  const int64_t tile_base = (int64_t)tile * nthreads * SYS_K;
-  double tk[SYS_K];
-  T r0k[SYS_K], wk[SYS_K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // first owned sample; sample k of this thread is idx0 + 32 k
+  const int64_t idx0 = ((int64_t)tile * nthreads + warp * 32) * K + lane;
+  double tk[K];
+  unsigned valid = 0;
+  SpanK sp;
+  sp.mono = true;
 #pragma unroll
-  for (int k = 0; k < SYS_K; ++k) {
-    const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
-    const bool ok = idx < a.n_times;
-    tk[k] = ok ? a.t[idx] : 0.0;
-    if (LOGLIKE) {
-      wk[k] = ok ? a.winv[idx] : T(0);
-      r0k[k] = ok ? (a.y[idx] - T(1)) * wk[k] : T(0);
-    }
+  for (int k = 0; k < K; ++k) {
+    const bool ok = idx0 + 32 * k < a.n_times;
+    tk[k] = ok ? a.t[idx0 + 32 * k] : (k > 0 ? tk[k - 1] : 0.0);
+    valid |= ok ? (1u << k) : 0u;
+    if (k > 0) sp.mono = sp.mono && (tk[k] >= tk[k - 1]);
   }
+  sp.first = tk[0];
+  sp.span = tk[K - 1] - tk[0];
   __syncthreads();
 
   const int nsub = a.st.n;
   const bool use_window = a.use_window != 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned n_kep = 0, n_ld = 0;
 
   for (int sl = 0; sl < nsl; ++sl) {
     const int set = set_base + sl;
     const SetC<T> sc = sset[sl];
-    double dchi = 0.0;
-    bool hit = false;
-    // not unrolled: ONE instance of the in-transit code per kernel (instruction-cache footprint)
+    T total[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) total[k] = T(0);
+    unsigned any_hit = 0;
 #pragma unroll 1
-    for (int k = 0; k < SYS_K; ++k) {
-      const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
-      if (idx >= a.n_times) continue;
-      const double tkk = pick(tk, k);
-      T total = T(0);
+    for (int body = 0; body < a.n_bodies; ++body) {
+      const BodyC<T>& c = sbody[sl * a.n_bodies + body];
+      T accb[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) accb[k] = T(0);
 #pragma unroll 1
-      for (int body = 0; body < a.n_bodies; ++body) {
-        const BodyC<T>& c = sbody[sl * a.n_bodies + body];
-        T acc = T(0);
+      for (int j = 0; j < nsub; ++j) {
+        const double dtj = a.st.dt[j];
+        unsigned mask = window_mask<T, K>(c, tk, sp, dtj, valid, use_window);
+        any_hit |= mask;
+        const T wj = T(a.st.w[j]);
+        // ONE instance of the in-transit code; each lane walks its own surviving samples
 #pragma unroll 1
-        for (int j = 0; j < nsub; ++j) {
-          const T v = eval_sample<T, ORDER>(c, sc, &a.tab, tkk + a.st.dt[j], use_window);
-          acc = (nsub == 1) ? v : jfma(T(a.st.w[j]), v, acc);
-        }
-        if (a.flux) a.flux[((size_t)set * a.n_times + idx) * a.n_bodies + body] = acc;
-        total += acc;
-      }
-      if (a.flux_sum) a.flux_sum[(size_t)set * a.n_times + idx] = total;
-      if (LOGLIKE) {
-        if (total != T(0)) {
-          // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: the change of chi^2 w.r.t. the zero model
-          const T wkk = pick(wk, k);
-          const T mw = total * wkk;
-          dchi += (double)(-mw) * (double)(T(2) * pick(r0k, k) - mw);
-          hit = true;
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ++n_kep;
+          const T v = eval_in_window<T, ORDER>(c, sc, &a.tab, pick(tk, k) + dtj, n_ld);
+          const T wv = (nsub == 1) ? v : wj * v;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) accb[kk] += (kk == k) ? wv : T(0);
         }
       }
+      if (a.flux) {
+        T* dst = a.flux + ((size_t)set * a.n_times + idx0) * a.n_bodies + body;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (valid & (1u << k)) dst[(size_t)(32 * k) * a.n_bodies] = accb[k];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) total[k] += accb[k];
+    }
+    if (a.flux_sum) {
+      T* dst = a.flux_sum + (size_t)set * a.n_times + idx0;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (valid & (1u << k)) dst[32 * k] = total[k];  // 256 B (128 B in fp32) per warp store
     }
     if (LOGLIKE) {
-      if (__any_sync(0xffffffffu, hit)) {
+      double dchi = 0.0;
+      if (any_hit) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (total[k] != T(0)) {
+            // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: change of chi^2 w.r.t. the zero model
+            const T w = a.winv[idx0 + 32 * k];
+            const T r0 = (a.y[idx0 + 32 * k] - T(1)) * w;
+            const T mw = total[k] * w;
+            dchi += (double)(-mw) * (double)(T(2) * r0 - mw);
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, any_hit != 0)) {
         for (int o = 16; o > 0; o >>= 1) dchi += __shfl_down_sync(0xffffffffu, dchi, o);
       }
       if (lane == 0) spart[warp * a.sets_per_cta + sl] = dchi;
@@ -597,6 +634,13 @@ __global__ void __launch_bounds__(256) k_system(const __grid_constant__ SysArgs<
       for (int w = 0; w < nwarps; ++w) acc += spart[w * a.sets_per_cta + sl];
       a.partial[(size_t)(set_base + sl) * a.n_tiles + tile] = acc;
     }
+  }
+  // executed-work counters (two atomics per warp per CTA)
+  n_kep = __reduce_add_sync(0xffffffffu, n_kep);
+  n_ld = __reduce_add_sync(0xffffffffu, n_ld);
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, (unsigned long long)n_kep);
+    atomicAdd(a.counters + 1, (unsigned long long)n_ld);
   }
 }
 
@@ -660,8 +704,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   {
     const int n = n_sets * n_bodies;
     k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride,
-                                                  d_bodies, d_sets, f32 ? 1.0 + 2e-4 : 1.0 + 1e-9,
-                                                  1e-7);
+                                                  d_bodies, d_sets,
+                                                  reinterpret_cast<unsigned long long*>(d_scalars + 2),
+                                                  f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7);
     rc = check_launch("jxp_system_light_curve(prep)");
     if (rc != JXP_OK) return rc;
   }
@@ -702,6 +747,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   a.y = y;
   a.winv = d_winv;
   a.partial = d_partial;
+  a.counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);
   a.tab.order = gl_order;
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
 
@@ -728,6 +774,22 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     rc = check_launch("jxp_system_light_curve(loglike final)");
   }
   return rc;
+}
+
+extern "C" int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
+                                int64_t n_times, int64_t* stats_host, void* stream) {
+  if (!workspace || !stats_host) return fail(JXP_ERR_NULL_POINTER, "jxp_system_stats: null pointer");
+  if (n_sets <= 0 || n_bodies <= 0 || n_times <= 0)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_stats: empty problem");
+  const SysLayout L = sys_layout(n_sets, n_bodies, n_times, sizeof(BodyC<double>),
+                                 sizeof(SetC<double>), sizeof(double));
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(stats_host, ws + L.off_scalars + 2 * sizeof(double),
+                                  2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_stats: %s", cudaGetErrorString(e));
+  return JXP_OK;
 }
 
 extern "C" int jxp_system_light_curve_f64(const double* bodies, int32_t n_sets, int32_t n_bodies,

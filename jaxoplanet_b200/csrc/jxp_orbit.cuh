@@ -43,11 +43,17 @@ __device__ inline double mean_from_true(double f, double e) {
   return E - e * sin(E);
 }
 
-// Conservative transit window in orbital phase.  A sample can only be in transit
-// (z > 0 and b < 1 + r) if |cos(f + omega)| < (1 + r) R* / (a (1 - e)), because
-// b R* >= |X| = |r0 cos(f + omega)| and |r0| >= a (1 - e).  The true-anomaly interval is
-// mapped to mean anomaly and widened by `widen` (relative, on the bound) and `margin`
-// (cycles).  Anything not provably narrow is flagged BODY_ALWAYS (no skipping).
+// Conservative transit window in orbital phase.  With theta = f + omega - theta_c the angle
+// from mid-transit, the sky-projected separation obeys
+//     (b R*)^2 = r0^2 (cos^2 i + sin^2 i sin^2 theta)        (keplerian.py:568-576, 630)
+// so a sample can only be in transit (z > 0 and b < 1 + r) if
+//     sin^2 theta < ((1 + r)^2 R*^2 / r_min^2 - cos^2 i) / sin^2 i =: S,
+// r_min a lower bound of |r0| over the samples considered.  Two passes: r_min = a (1 - e)
+// gives a first interval; |r0| >= a (1 - e^2) / (1 + e max cos f) over THAT interval gives the
+// final one.  S <= 0: the body never transits (empty window).  The true-anomaly interval is
+// mapped to mean anomaly; `widen` (relative, on (1 + r) R*) and `margin` (cycles) cover
+// rounding (and the fp32 mode's coarser b).  Anything not provably narrow is flagged
+// BODY_ALWAYS (no skipping).
 template <typename T>
 __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, double e,
                                       double widen, double margin) {
@@ -56,14 +62,33 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
   c.wlo = -1.0;
   c.whi = 1.0;
   const double sw = (double)c.sw, cw = (double)c.cw;
+  const double ci = (double)c.ci, si = (double)c.si;
   const double rho = sqrt(sw * sw + cw * cw);
-  const double bound = (1.0 + fabs((double)c.rr)) * rstar / (a * (1.0 - e) * rho) * widen;
-  if (!(bound < 0.95) || !(bound > 0.0)) return;
-  if (!(e >= 0.0) || !(e < 0.99)) return;
-  const double delta = asin(bound);
+  if (!(e >= 0.0) || !(e < 0.99) || !(rho > 0.0) || !(si * si > 1e-6)) return;
+  const double reach = (1.0 + fabs((double)c.rr)) * rstar * widen;  // (1 + r) R*
   const double omega = atan2(sw, cw);
-  const double theta_c = ((double)c.si >= 0.0) ? Num<double>::half_pi : 3.0 * Num<double>::half_pi;
+  const double theta_c = (si >= 0.0) ? Num<double>::half_pi : 3.0 * Num<double>::half_pi;
   const double fc = theta_c - omega;
+  double rmin = rho * a * (1.0 - e);
+  double delta = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double q = reach / rmin;
+    const double S = (q * q - ci * ci) / (si * si);
+    if (!(S < 0.9)) return;  // wide (or NaN): evaluate everything
+    if (S <= 0.0) {          // never in transit: empty window
+      if (!isfinite(c.inv_period) || !isfinite(c.t0ref)) return;
+      c.wlo = 1.0;
+      c.whi = -1.0;
+      c.flags &= ~BODY_ALWAYS;
+      return;
+    }
+    delta = asin(sqrt(S));
+    if (pass == 0) {
+      const double fcr = fc - Num<double>::two_pi * rint(fc * Num<double>::inv_two_pi);
+      const double cmax = (fabs(fcr) <= delta) ? 1.0 : fmax(cos(fc - delta), cos(fc + delta));
+      rmin = rho * a * (1.0 - e * e) / (1.0 + e * cmax) * (1.0 - 1e-12);
+    }
+  }
   const double Mc = mean_from_true(fc, e);
   double lo = mean_from_true(fc - delta, e) - Mc;
   double hi = mean_from_true(fc + delta, e) - Mc;
@@ -130,12 +155,12 @@ __device__ __forceinline__ V pick(const V (&a)[K], int k) {
   return r;
 }
 
-// flux - 1 of one body at one time (0 when not in transit).
+// flux - 1 of one body at one time (0 when not in transit); the caller has already applied
+// the transit-window pre-test.
 template <typename T, int ORDER>
-__device__ __forceinline__ T eval_sample(const BodyC<T>& c, const SetC<T>& sc,
-                                         const GLTable* __restrict__ tab, double tm,
-                                         bool use_window) {
-  if (use_window && !(c.flags & BODY_ALWAYS) && outside_window(c, tm)) return T(0);
+__device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc,
+                                            const GLTable* __restrict__ tab, double tm,
+                                            unsigned& n_ld) {
   const T Mr = T(mean_anomaly_reduced(c, tm));
   T sf, cf, Edummy;
   if (c.flags & BODY_CIRCULAR) {
@@ -146,9 +171,42 @@ __device__ __forceinline__ T eval_sample(const BodyC<T>& c, const SetC<T>& sc,
   T b, Z;
   sky_position(c, sf, cf, b, Z);
   if (!(Z > T(0)) || (b >= c.onepr)) return T(0);  // limb_dark.py:58 mask, :60 no_occ
+  ++n_ld;
   T s0, s1, s2;
   ld_solution<T, ORDER>(b, c.rr, sc.lmax, tab, s0, s1, s2);
   return ld_combine(sc.lmax, s0, s1, s2, sc.g0, sc.g1, sc.g2);
+}
+
+// Per-thread view of the K consecutive time samples a thread owns: used to reject all K
+// against a body's transit window with one test when the samples are time-ordered.
+struct SpanK {
+  double first;  // t of the first valid sample
+  double span;   // t_last - t_first (>= 0 when monotone)
+  bool mono;     // samples non-decreasing
+};
+
+// Candidate mask (bit k set: sample k may be in transit) for one (body, sub-sample offset).
+template <typename T, int K>
+__device__ __forceinline__ unsigned window_mask(const BodyC<T>& c, const double (&tk)[K],
+                                                const SpanK& sp, double dtj, unsigned valid,
+                                                bool use_window) {
+  if (!use_window || (c.flags & BODY_ALWAYS)) return valid;
+  const double t0ref = c.t0ref, invP = c.inv_period, phc = c.phase_c, wlo = c.wlo, whi = c.whi;
+  if (sp.mono) {
+    const double ph0 = fma((sp.first + dtj) - t0ref, invP, -phc);
+    const double d0 = ph0 - rint(ph0);
+    const double d1 = fma(sp.span, invP, d0);
+    // whole interval before this cycle's window, or between this window and the next one
+    if ((d1 < wlo) | ((d0 > whi) & (d1 < 1.0 + wlo))) return 0u;
+  }
+  unsigned mask = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double ph = fma((tk[k] + dtj) - t0ref, invP, -phc);
+    const double d = ph - rint(ph);
+    mask |= ((d >= wlo) & (d <= whi)) ? (1u << k) : 0u;
+  }
+  return mask & valid;
 }
 
 }  // namespace jxp

@@ -160,13 +160,13 @@ __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
   out[s] = o;
 }
 
-// One sample: flux - 1 and its 8 partials (all zero when not in transit).
+// One sample that passed the window test: flux - 1 and its 8 partials; false (outputs
+// untouched) when the sample is not in transit.
 template <typename T, int ORDER>
 __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
                                                      const GLTable* __restrict__ tab, double tm,
-                                                     bool use_window, T& flux, T* __restrict__ part) {
+                                                     T& flux, T* __restrict__ part) {
   const BodyC<T>& c = bd.c;
-  if (use_window && !(c.flags & BODY_ALWAYS) && outside_window(c, tm)) return false;
   typedef Dual<T, NO> D;
   // mean anomaly and its tangents (double): M = 2 pi ((t - t0) - t_ref) / P
   const double x = (tm - c.t0) - c.tref;
@@ -227,9 +227,14 @@ struct TrArgs {
   GLTable tab;
 };
 
+// Same CTA structure as k_system (jxp_kernels.cu): warp-owned rows of 32 samples in registers,
+// sets of the group staged in shared memory, window rejection first, one instance of the
+// in-transit code.  Every output row is one fully coalesced warp store.
 template <typename T, int ORDER, bool LOGLIKE>
 __global__ void __launch_bounds__(256, 2) k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int K = TR_K;
+  constexpr int NQ = 1 + JXP_NTHETA;
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   const int tile = blockIdx.x % a.n_tiles;
@@ -244,94 +249,108 @@ __global__ void __launch_bounds__(256, 2) k_transit_partials(const __grid_consta
     const int nw = nsl * (int)(sizeof(BodyD<T>) / 8);
     for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
   }
-  const int64_t tile_base = (int64_t)tile * nthreads * TR_K;
-  double tk[TR_K];
-  T r0k[TR_K], wk[TR_K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx0 = ((int64_t)tile * nthreads + warp * 32) * K + lane;
+  double tk[K];
+  unsigned valid = 0;
+  SpanK sp;
+  sp.mono = true;
 #pragma unroll
-  for (int k = 0; k < TR_K; ++k) {
-    const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
-    const bool ok = idx < a.n_times;
-    tk[k] = ok ? a.t[idx] : 0.0;
-    if (LOGLIKE) {
-      wk[k] = ok ? a.winv[idx] : T(0);
-      r0k[k] = ok ? (a.y[idx] - T(1)) * wk[k] : T(0);
-    }
+  for (int k = 0; k < K; ++k) {
+    const bool ok = idx0 + 32 * k < a.n_times;
+    tk[k] = ok ? a.t[idx0 + 32 * k] : (k > 0 ? tk[k - 1] : 0.0);
+    valid |= ok ? (1u << k) : 0u;
+    if (k > 0) sp.mono = sp.mono && (tk[k] >= tk[k - 1]);
   }
+  sp.first = tk[0];
+  sp.span = tk[K - 1] - tk[0];
   __syncthreads();
   const int nsub = a.st.n;
   const bool use_window = a.use_window != 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int sl = 0; sl < nsl; ++sl) {
     const int set = set_base + sl;
     const BodyD<T>& bd = sbody[sl];
-    double acc9[1 + JXP_NTHETA];
+    T out[K][NQ];  // flux, 8 partials
 #pragma unroll
-    for (int q = 0; q < 1 + JXP_NTHETA; ++q) acc9[q] = 0.0;
-    bool hit = false;
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) out[k][q] = T(0);
+    unsigned hitmask = 0;
 #pragma unroll 1
-    for (int k = 0; k < TR_K; ++k) {
-      const int64_t idx = tile_base + (int64_t)k * nthreads + threadIdx.x;
-      if (idx >= a.n_times) continue;
-      const double tkk = pick(tk, k);
-      T flux = T(0);
-      T part[JXP_NTHETA];
+    for (int j = 0; j < nsub; ++j) {
+      const double dtj = a.st.dt[j];
+      unsigned mask = window_mask<T, K>(bd.c, tk, sp, dtj, valid, use_window);
+      const T wj = T(a.st.w[j]);
+#pragma unroll 1
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        T f1 = T(0);
+        T p1[JXP_NTHETA];
+        if (eval_sample_partials<T, ORDER>(bd, &a.tab, pick(tk, k) + dtj, f1, p1)) {
+          const T w = (nsub == 1) ? T(1) : wj;
+          hitmask |= 1u << k;
 #pragma unroll
-      for (int q = 0; q < JXP_NTHETA; ++q) part[q] = T(0);
-      bool any = false;
-      if (nsub == 1) {
-        any = eval_sample_partials<T, ORDER>(bd, &a.tab, tkk, use_window, flux, part);
-        if (!any) {
-          flux = T(0);
+          for (int kk = 0; kk < K; ++kk) {
+            if (kk == k) {
+              out[kk][0] = jfma(w, f1, out[kk][0]);
 #pragma unroll
-          for (int q = 0; q < JXP_NTHETA; ++q) part[q] = T(0);
-        }
-      } else {
-        for (int j = 0; j < nsub; ++j) {
-          T f1 = T(0);
-          T p1[JXP_NTHETA];
-          if (eval_sample_partials<T, ORDER>(bd, &a.tab, tkk + a.st.dt[j], use_window, f1, p1)) {
-            const T w = T(a.st.w[j]);
-            flux = jfma(w, f1, flux);
-#pragma unroll
-            for (int q = 0; q < JXP_NTHETA; ++q) part[q] = jfma(w, p1[q], part[q]);
-            any = true;
+              for (int q = 0; q < JXP_NTHETA; ++q) out[kk][1 + q] = jfma(w, p1[q], out[kk][1 + q]);
+            }
           }
         }
       }
-      if (a.flux) a.flux[(size_t)set * a.n_times + idx] = flux;
-      if (a.partials) {
+    }
+    if (a.flux) {
+      T* dst = a.flux + (size_t)set * a.n_times + idx0;
 #pragma unroll
-        for (int q = 0; q < JXP_NTHETA; ++q)
-          a.partials[((size_t)set * JXP_NTHETA + q) * a.n_times + idx] = part[q];
-      }
-      if (LOGLIKE && any) {
-        const T wkk = pick(wk, k), r0kk = pick(r0k, k);
-        const T mw = flux * wkk;
-        const T rm = r0kk - mw;  // ((y - 1) - m) / sigma
-        acc9[0] += (double)(-mw) * (double)(T(2) * r0kk - mw);
-        const double g = (double)(rm * wkk);  // d loglike / d m
+      for (int k = 0; k < K; ++k)
+        if (valid & (1u << k)) dst[32 * k] = out[k][0];
+    }
+    if (a.partials) {
 #pragma unroll
-        for (int q = 0; q < JXP_NTHETA; ++q) acc9[1 + q] += g * (double)part[q];
-        hit = true;
+      for (int q = 0; q < JXP_NTHETA; ++q) {
+        T* dst = a.partials + ((size_t)set * JXP_NTHETA + q) * a.n_times + idx0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (valid & (1u << k)) dst[32 * k] = out[k][1 + q];
       }
     }
     if (LOGLIKE) {
-      __syncthreads();  // spart reuse across sets
-      if (__any_sync(0xffffffffu, hit)) {
+      double acc9[NQ];
 #pragma unroll
-        for (int q = 0; q < 1 + JXP_NTHETA; ++q)
+      for (int q = 0; q < NQ; ++q) acc9[q] = 0.0;
+      if (hitmask) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (hitmask & (1u << k)) {
+            const T w = a.winv[idx0 + 32 * k];
+            const T r0 = (a.y[idx0 + 32 * k] - T(1)) * w;
+            const T mw = out[k][0] * w;
+            const T rm = r0 - mw;  // ((y - 1) - m) / sigma
+            acc9[0] += (double)(-mw) * (double)(T(2) * r0 - mw);
+            const double g = (double)(rm * w);  // d loglike / d m
+#pragma unroll
+            for (int q = 0; q < JXP_NTHETA; ++q) acc9[1 + q] += g * (double)out[k][1 + q];
+          }
+        }
+      }
+      __syncthreads();  // spart is reused by every set of the group
+      if (__any_sync(0xffffffffu, hitmask != 0)) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
           for (int o = 16; o > 0; o >>= 1) acc9[q] += __shfl_down_sync(0xffffffffu, acc9[q], o);
       }
       if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 1 + JXP_NTHETA; ++q) spart[warp * (1 + JXP_NTHETA) + q] = acc9[q];
+        for (int q = 0; q < NQ; ++q) spart[warp * NQ + q] = acc9[q];
       }
       __syncthreads();
-      if (threadIdx.x < 1 + JXP_NTHETA) {
+      if (threadIdx.x < NQ) {
         double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += spart[w * (1 + JXP_NTHETA) + threadIdx.x];
-        a.partial[((size_t)set * a.n_tiles + tile) * (1 + JXP_NTHETA) + threadIdx.x] = s;
+        for (int w = 0; w < nwarps; ++w) s += spart[w * NQ + threadIdx.x];
+        a.partial[((size_t)set * a.n_tiles + tile) * NQ + threadIdx.x] = s;
       }
     }
   }

@@ -71,4 +71,21 @@ for flags,label in ((0,"window"),(1,"dense")):
     tmin,tmed=ev_time(f,n=3,warm=1)
     out[f"c3_flux_{label}"]={"ms":tmin,"points_per_s":ns*td.numel()/tmin*1e3,"f_in":float((fs!=0).double().mean())}
     print(label, json.dumps(out[f"c3_flux_{label}"])); sys.stdout.flush()
+del fs
+torch.cuda.empty_cache()
+from jaxoplanet_b200 import workloads as W
+theta,t5=W.c5(16384,50_000)
+thd=torch.as_tensor(theta).to(dev).contiguous(); t5d=torch.as_tensor(t5).to(dev)
+star=torch.tensor([1.0,1.0],dtype=torch.float64,device=dev)
+ns5=thd.shape[0]; nt5=t5d.numel()
+wsb5=_lib.load().jxp_transit_workspace_bytes(ns5,nt5); ws5=torch.empty(wsb5,dtype=torch.uint8,device=dev)
+for dt,nm in ((torch.float64,"f64"),(torch.float32,"f32")):
+    fl=torch.empty((ns5,nt5),dtype=dt,device=dev); pt=torch.empty((ns5,8,nt5),dtype=dt,device=dev)
+    for flags,label in ((0,"window"),(1,"dense")):
+        f=lambda: _lib.call("jxp_transit_partials_"+nm, thd.data_ptr(),ns5,star.data_ptr(),0,t5d.data_ptr(),nt5,0.0,0,0,10,flags,fl.data_ptr(),pt.data_ptr(),0,0,0,0,0,ws5.data_ptr(),wsb5,A.stream_ptr())
+        tmin,tmed=ev_time(f,n=3,warm=1)
+        bytes_=ns5*nt5*9*fl.element_size()
+        out[f"c5_{nm}_{label}"]={"ms":tmin,"points_per_s":ns5*nt5/tmin*1e3,"GBps":bytes_/tmin/1e6}
+        print("c5",nm,label,json.dumps(out[f"c5_{nm}_{label}"])); sys.stdout.flush()
+    del fl,pt
 json.dump(out, open("gpurun_out/quick_bench.json","w"), indent=1)
