@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""Benchmark of the jaxoplanet hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json config 3 -- 4096 parameter sets x 1e5 time samples
+of a Keplerian transit light curve with quadratic limb darkening, fused with the Gaussian
+log-likelihood -- PER GPU (weak scaling: rank g evaluates its own 4096 sets; the per-set
+log-likelihoods are all-gathered over NCCL).  A "step" is one evaluation of that batch, the
+unit a sampler performs per proposal.  metric = light-curve points/s (one point = one time
+sample of one parameter set).
+
+value    device-resident inputs, CUDA events around each step, L2 flushed between steps
+e2e      same step through the C ABI with pinned HOST buffers: H2D of every input and D2H of
+         the log-likelihoods inside the timed region
+roofline dominant kernel (k_system) timed alone with CUDA events inside the timed steps;
+         achieved = A-table flops of the work it EXECUTED (counters read back from the
+         device) / its mean duration; peak = FP64 FMA peak measured in this run
+cpu_baseline / --impl reference: the C/OpenMP restatement of the reference (oracle/ref_c.c)
+         on the host cores, on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# A-table v1 (SURVEY.md 8d / DESIGN.md): algorithmic flops per unit of the reference formulas
+W_KEPLER = 266.0
+W_ORBIT = 36.0
+W_LD = 746.0
+N_SETS = 4096
+N_TIMES = 100_000
+METRIC = "light-curve points/s (Keplerian orbit + quadratic limb darkening + Gaussian log-likelihood, fp64)"
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {
+        "workload": f"C3: {N_SETS} parameter sets x {N_TIMES} times (2-min cadence), 1 planet, quadratic LD, "
+                    "fused Gaussian log-likelihood, per GPU",
+        "sets_per_gpu": N_SETS,
+        "n_times": N_TIMES,
+        "n_bodies": 1,
+        "parallelism": f"set-sharded x{n_gpus}",
+        "cache": "L2 flushed between steps (256 MiB write); per-step CUDA events summed",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def build_inputs(seed):
+    """Host-side inputs of one rank: C-ABI body records, u, t, noise, sigma."""
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    p, u, t, noise, sigma = W.c3(N_SETS, N_TIMES, seed=seed)
+    bodies, n_sets, _ = pack_bodies(W.system_from(p))
+    return p, bodies.numpy().copy(), u, t, noise, sigma
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (C/OpenMP restatement) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_points_per_s(bodies, u, t, y, sigma, budget_s=12.0):
+    from oracle import ref_c
+
+    ref_c.build()
+    n_try = 2
+    t0 = time.perf_counter()
+    ref_c.system(bodies[:n_try], u[:n_try], t, y=y, sigma=sigma, want_flux=False)
+    dt = time.perf_counter() - t0
+    threads = ref_c.max_threads()
+    n_sample = int(min(len(bodies), max(threads, budget_s / max(dt / n_try, 1e-9))))
+    n_sample = max(threads, (n_sample // threads) * threads)
+    n_sample = min(n_sample, len(bodies))
+    t0 = time.perf_counter()
+    ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
+    dt = time.perf_counter() - t0
+    return n_sample * len(t) / dt, n_sample, threads, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    _, bodies, u, t, noise, sigma = build_inputs(seed=1)
+    y = 1.0 + noise
+    from oracle import ref_c
+
+    ref_c.build()
+    threads = ref_c.max_threads()
+    # size one step to ~2 s of CPU work
+    n_try = max(2, threads)
+    t0 = time.perf_counter()
+    ref_c.system(bodies[:n_try], u[:n_try], t, y=y, sigma=sigma, want_flux=False)
+    per_set = (time.perf_counter() - t0) / n_try
+    n_sample = int(min(N_SETS, max(threads, 2.0 / max(per_set, 1e-9))))
+    n_sample = max(threads, (n_sample // threads) * threads)
+    for _ in range(args.warmup):
+        ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_sample * N_TIMES / dt
+    sample = f"{n_sample} of {N_SETS} sets x {N_TIMES} times per step (linear in sets)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, {"cache": "n/a (CPU)"}),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": sample,
+                         "note": "C/OpenMP restatement of the reference formulas (oracle/ref_c.c); "
+                                 "jax is not installable in this image, so this is not jax[cpu]"},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t_lo, t_hi):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t_lo - 0.05 or ts > t_hi + 0.15:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    stream = A.stream_ptr
+
+    p, bodies_h, u_h, t_h, noise, sigma = build_inputs(seed=1 + rank)
+    n_sets, n_times = bodies_h.shape[0], t_h.shape[0]
+    bodies = torch.as_tensor(bodies_h).to(dev).contiguous()
+    u = torch.as_tensor(u_h).to(dev).contiguous()
+    t = torch.as_tensor(t_h).to(dev)
+    sig = torch.full((1,), sigma, dtype=torch.float64, device=dev)
+    wsb = int(lib.jxp_system_workspace_bytes(n_sets, 1, n_times))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ll = torch.empty(n_sets, dtype=torch.float64, device=dev)
+    ll_all = torch.empty(world * n_sets, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def call(flags=0, y_=None, flux_sum=None, loglike=ll, bodies_=bodies, u_=u, t_=t, sig_=sig):
+        _lib.call("jxp_system_light_curve_f64", bodies_.data_ptr(), n_sets, 1, u_.data_ptr(), 2, 2,
+                  t_.data_ptr(), n_times, 0.0, 0, 0, 10, flags, 0, A.ptr(flux_sum), A.ptr(y_),
+                  sig_.data_ptr() if y_ is not None else 0, 0, A.ptr(loglike) if y_ is not None else 0,
+                  ws.data_ptr(), wsb, stream())
+
+    # observed flux: 1 + model of this rank's set 0 + noise (synthetic), computed once, untimed
+    f0 = torch.empty((n_sets, n_times), dtype=torch.float64, device=dev)
+    call(flux_sum=f0, loglike=None)
+    y = (1.0 + f0[0] + torch.as_tensor(noise).to(dev)).contiguous()
+    f_in = float((f0 != 0).double().mean())
+    del f0
+    torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(flags=0):
+        call(flags=flags, y_=y)
+        if world > 1:
+            w = dist.all_gather_into_tensor(ll_all, ll, async_op=True)
+            w.wait()
+
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kev0 = torch.cuda.Event(enable_timing=True)
+    kev1 = torch.cuda.Event(enable_timing=True)
+    for e in (ev0, ev1, kev0, kev1):
+        e.record()
+    torch.cuda.synchronize()
+
+    def timed_steps(n, flags=0, kernel_events=True):
+        tot, ktot = 0.0, 0.0
+        for _ in range(n):
+            flush_l2()
+            if kernel_events:
+                lib.jxp_profile_events(ctypes.c_void_p(kev0.cuda_event), ctypes.c_void_p(kev1.cuda_event))
+            ev0.record()
+            step(flags)
+            ev1.record()
+            lib.jxp_profile_events(None, None)
+            torch.cuda.synchronize()
+            tot += ev0.elapsed_time(ev1)
+            if kernel_events:
+                ktot += kev0.elapsed_time(kev1)
+        return tot, ktot
+
+    # FP64 pipe peak, measured now (MEASURED_PEAKS.json has no FP64 figure)
+    def fma_peak(name, dtype):
+        blocks, threads, iters = 148 * 2, 1024, 20000
+        sink = torch.empty(blocks * threads, dtype=dtype, device=dev)
+        best = 1e30
+        for i in range(5):
+            ev0.record()
+            _lib.call(name, sink.data_ptr(), blocks, threads, iters, stream())
+            ev1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, ev0.elapsed_time(ev1))
+        return 2.0 * blocks * threads * iters * 16 / best / 1e9  # TFLOP/s
+
+    fp64_peak = fma_peak("jxp_peak_fma_f64", torch.float64)
+
+    # ---- value: device-resident inputs --------------------------------------------------
+    timed_steps(max(args.warmup, 3), kernel_events=False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t_lo = time.perf_counter()
+    tot_ms, k_ms = timed_steps(args.steps)
+    barrier()
+    t_hi = time.perf_counter()
+    clocks = sampler.stop(t_lo, t_hi) if rank == 0 else None
+    stats = (ctypes.c_int64 * 2)()
+    _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
+    n_kep, n_ld = int(stats[0]), int(stats[1])
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    tot_ms = max_over_ranks(tot_ms)
+    ms_per_step = tot_ms / args.steps
+    points_per_step = world * n_sets * n_times
+    value = points_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host buffers through the C ABI ------------------------------------------
+    hb = torch.as_tensor(bodies_h).pin_memory()
+    hu = torch.as_tensor(u_h).pin_memory()
+    ht = torch.as_tensor(t_h).pin_memory()
+    hy = y.cpu().pin_memory()
+    hs = torch.full((1,), sigma, dtype=torch.float64).pin_memory()
+    hll = torch.empty(n_sets, dtype=torch.float64).pin_memory()
+    db, du, dt_, dy, ds = (torch.empty_like(x, device=dev) for x in (hb, hu, ht, hy, hs))
+    h2d = sum(x.numel() * x.element_size() for x in (hb, hu, ht, hy, hs))
+    d2h = hll.numel() * hll.element_size()
+
+    def e2e_step():
+        db.copy_(hb, non_blocking=True)
+        du.copy_(hu, non_blocking=True)
+        dt_.copy_(ht, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        ds.copy_(hs, non_blocking=True)
+        _lib.call("jxp_system_light_curve_f64", db.data_ptr(), n_sets, 1, du.data_ptr(), 2, 2,
+                  dt_.data_ptr(), n_times, 0.0, 0, 0, 10, 0, 0, 0, dy.data_ptr(), ds.data_ptr(), 0,
+                  ll.data_ptr(), ws.data_ptr(), wsb, stream())
+        if world > 1:
+            w = dist.all_gather_into_tensor(ll_all, ll, async_op=True)
+            w.wait()
+        hll.copy_(ll, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms) / args.steps
+    e2e_value = points_per_step / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0) -------------------------------------------
+    k_ms_avg = k_ms / args.steps
+    flops = n_kep * (W_KEPLER + W_ORBIT) + n_ld * W_LD
+    achieved = flops / (k_ms_avg * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64", "kernel": "k_system<double,10,true>", "achieved": achieved, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+        "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
+        "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
+        "executed": {"kepler_solves": n_kep, "ld_evaluations": n_ld, "points": n_sets * n_times,
+                     "in_transit_fraction": f_in},
+        "flops_convention": "A-table v1: 302 flop per executed Kepler solve + orbit, 746 per executed LD evaluation; "
+                            "window pre-tests counted as 0",
+        "hbm_peak_gbs": peaks.get("hbm_gbs"),
+    }
+
+    # ---- secondary numbers (rank 0, N = 1 only): dense mode, C2 Kepler ------------------------
+    secondary = {}
+    if world == 1 and not args.no_secondary:
+        n_sec = 3
+        timed_steps(2, flags=_lib.JXP_FLAG_NO_WINDOW, kernel_events=False)
+        d_tot, d_k = timed_steps(n_sec, flags=_lib.JXP_FLAG_NO_WINDOW)
+        _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
+        dk, dl = int(stats[0]), int(stats[1])
+        d_flops = dk * (W_KEPLER + W_ORBIT) + dl * W_LD
+        secondary["c3_dense_no_window"] = {
+            "points_per_s": n_sets * n_times / (d_tot / n_sec * 1e-3), "ms_per_step": d_tot / n_sec,
+            "fp64_frac": d_flops / (d_k / n_sec * 1e-3) / 1e12 / fp64_peak,
+            "executed": {"kepler_solves": dk, "ld_evaluations": dl}}
+        n2 = 100_000_000
+        M = torch.rand(n2, dtype=torch.float64, device=dev) * (2 * np.pi)
+        e = torch.rand(n2, dtype=torch.float64, device=dev) * 0.99
+        s_ = torch.empty_like(M)
+        c_ = torch.empty_like(M)
+        best = 1e30
+        for i in range(4):
+            ev0.record()
+            _lib.call("jxp_kepler_f64", M.data_ptr(), 1, e.data_ptr(), 1, n2, s_.data_ptr(), c_.data_ptr(),
+                      0, 0, 0, stream())
+            ev1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, ev0.elapsed_time(ev1))
+        secondary["c2_kepler_1e8"] = {
+            "solves_per_s": n2 / (best * 1e-3), "ms": best,
+            "fp64_frac": n2 * W_KEPLER / (best * 1e-3) / 1e12 / fp64_peak,
+            "hbm_gbs": 32.0 * n2 / (best * 1e-3) / 1e9,
+            "hbm_frac": (32.0 * n2 / (best * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
+        del M, e, s_, c_
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, n_sample, threads, secs = cpu_points_per_s(bodies_h, u_h, t_h, y.cpu().numpy(), sigma)
+        cpu = {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": f"{n_sample} of {n_sets} sets x {n_times} times, {secs:.1f} s",
+               "note": "C/OpenMP restatement of the reference formulas (oracle/ref_c.c); not jax[cpu]"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "path": "jxp_system_light_curve_f64 (C ABI), pinned host buffers"},
+        "gpu_launches": 4 * args.steps,
+        "gpu_launches_per_step": ["k_sys_prep", "k_loglike_prep", "k_system", "k_loglike_final"],
+        "clocks": clocks, "secondary": secondary,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (WORLD_SIZE={world}); running 1 GPU", file=sys.stderr)
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

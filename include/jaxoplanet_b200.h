@@ -148,6 +148,12 @@ int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_b
                                const float* sigma, int64_t sigma_stride, float* loglike,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement helper: when both events (cudaEvent_t as void*) are non-NULL, the calling
+ * thread's subsequent jxp_system_light_curve_* calls record them on the launch stream
+ * immediately before and after the dominant kernel (k_system), so that a harness can time that
+ * kernel alone with CUDA events.  Pass NULL, NULL to switch off (the default). */
+int jxp_profile_events(void* start_event, void* stop_event);
+
 /* Measurement helper: how much work the LAST jxp_system_light_curve_* call on this workspace
  * actually executed -- stats_host[0] = Kepler solves, stats_host[1] = limb-darkening
  * evaluations (host memory, 2 x int64).  Copies device -> host and SYNCHRONISES `stream`;

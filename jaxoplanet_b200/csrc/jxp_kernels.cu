@@ -21,6 +21,13 @@ using namespace jxph;
 // ======================================================================================
 namespace {
 thread_local char g_err[512] = "";
+thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+}
+
+extern "C" int jxp_profile_events(void* start_event, void* stop_event) {
+  g_ev_start = (cudaEvent_t)start_event;
+  g_ev_stop = (cudaEvent_t)stop_event;
+  return JXP_OK;
 }
 
 namespace jxph {
@@ -759,7 +766,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
+    if (g_ev_start) cudaEventRecord(g_ev_start, st);
     kern<<<(unsigned)n_ctas, threads, smem, st>>>(a);
+    if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return check_launch("jxp_system_light_curve");
   };
   if (gl_order == 10)
