@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libjxp_b200.so")
+LIB_PATH = os.environ.get("JXP_LIB_PATH") or os.path.join(HERE, "lib", "libjxp_b200.so")
 
 JXP_BODY_NFIELDS = 12
 JXP_NTHETA = 8

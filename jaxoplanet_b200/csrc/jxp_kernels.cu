@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -356,7 +357,7 @@ struct SysLayout {
 SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, size_t set_sz,
                      size_t elem_sz) {
   SysLayout L;
-  L.tile = 128 * SYS_K;  // smallest tile any launch configuration uses
+  L.tile = 32 * SYS_K;  // smallest tile any launch configuration uses (one warp per CTA)
   L.n_tiles = (int)((n_times + L.tile - 1) / L.tile);
   size_t off = 0;
   L.off_bodies = off;
@@ -518,8 +519,11 @@ struct SysArgs {
 // they are time-ordered, else one phase test each) and then runs the in-transit code -- a
 // single instance in the kernel -- only for the surviving samples; lanes whose surviving
 // samples sit in different rows proceed together.
+#ifndef JXP_SYS_MINB
+#define JXP_SYS_MINB 2
+#endif
 template <typename T, int ORDER, bool LOGLIKE>
-__global__ void __launch_bounds__(256, 2) k_system(const __grid_constant__ SysArgs<T> a) {
+__global__ void __launch_bounds__(256, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = SYS_K;
   const int nthreads = blockDim.x;
@@ -727,12 +731,16 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // CTA as that allows (amortises the time-stamp loads and the record staging)
   const int sms = sm_count();
   int threads = 256;
+  if (const char* env = getenv("JXP_SYS_THREADS")) {  // development knob
+    const int v = atoi(env);
+    if (v >= 32 && v <= 256 && v % 32 == 0) threads = v;
+  }
   int64_t n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
-  if (n_tiles * n_sets < 2 * sms) {
-    threads = 128;
+  while (threads > 32 && n_tiles * n_sets < 2 * sms) {
+    threads /= 2;
     n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
   }
-  int spc = (int)((n_tiles * (int64_t)n_sets) / ((int64_t)sms * 32));
+  int spc = (int)((n_tiles * (int64_t)n_sets) / ((int64_t)sms * 64));
   if (spc < 1) spc = 1;
   if (spc > SYS_MAX_SETS) spc = SYS_MAX_SETS;
   if (spc > n_sets) spc = n_sets;

@@ -38,6 +38,16 @@ elif case == "ld":
     f = torch.empty_like(b)
     ms = timed(lambda: _lib.call("jxp_limb_dark_f64", u.data_ptr(), 2, b.data_ptr(), 1, r.data_ptr(), 1, n, 10, f.data_ptr(), 0, 0, 0, A.stream_ptr()))
     print("ld", n, "ms", ms, "points/s", n / ms * 1e3)
+elif case == "c5":
+    from jaxoplanet_b200 import workloads as W
+    theta, t5 = W.c5(n_sets, n_t)
+    thd = torch.as_tensor(theta).to(dev).contiguous(); t5d = torch.as_tensor(t5).to(dev)
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+    wsb5 = _lib.load().jxp_transit_workspace_bytes(n_sets, n_t); ws5 = torch.empty(wsb5, dtype=torch.uint8, device=dev)
+    fl = torch.empty((n_sets, n_t), dtype=torch.float64, device=dev); pt = torch.empty((n_sets, 8, n_t), dtype=torch.float64, device=dev)
+    ms = timed(lambda: _lib.call("jxp_transit_partials_f64", thd.data_ptr(), n_sets, star.data_ptr(), 0, t5d.data_ptr(), n_t, 0.0, 0, 0, 10, flags,
+                                 fl.data_ptr(), pt.data_ptr(), 0, 0, 0, 0, 0, ws5.data_ptr(), wsb5, A.stream_ptr()))
+    print("c5", n_sets, n_t, "flags", flags, "ms", ms, "points/s", n_sets * n_t / ms * 1e3, "GB/s", n_sets * n_t * 72 / ms / 1e6)
 else:
     rng = np.random.default_rng(1)
     P = rng.uniform(2, 5, n_sets)
