@@ -9,6 +9,7 @@ namespace jxph {
 constexpr int MAX_SUB = 64;
 struct Stencil {
   int n;
+  double dt_min, dt_max;  // extreme offsets (<= 0, >= 0)
   double dt[MAX_SUB];
   double w[MAX_SUB];
 };

@@ -307,6 +307,7 @@ int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) 
     st.n = 1;
     st.dt[0] = 0.0;
     st.w[0] = 1.0;
+    st.dt_min = st.dt_max = 0.0;
     return JXP_OK;
   }
   int ns = num_samples;
@@ -338,9 +339,13 @@ int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) 
                 "The parameter 'order' in 'integrate_exposure_time' must be 0, 1, or 2");
   }
   for (int j = 0; j < ns; ++j) sum += st.w[j];
+  st.dt_min = 0.0;
+  st.dt_max = 0.0;
   for (int j = 0; j < ns; ++j) {
     st.dt[j] *= exposure_time;
     st.w[j] /= sum;
+    st.dt_min = st.dt[j] < st.dt_min ? st.dt[j] : st.dt_min;
+    st.dt_max = st.dt[j] > st.dt_max ? st.dt[j] : st.dt_max;
   }
   return JXP_OK;
 }
@@ -500,7 +505,7 @@ struct SysArgs {
   const SetC<T>* sets;
   const double* t;
   int64_t n_times;
-  int n_sets, n_bodies, sets_per_cta, n_tiles, use_window;
+  int n_sets, n_bodies, sets_per_cta, n_tiles, n_wtiles, use_window;
   T* flux;
   T* flux_sum;
   const T* y;
@@ -511,142 +516,283 @@ struct SysArgs {
   GLTable tab;
 };
 
-// CTA = (tile of blockDim.x * SYS_K time samples) x (group of sets_per_cta parameter sets).
-// A warp owns 32 * SYS_K consecutive time samples as SYS_K rows of 32 (lane = column), kept in
-// registers, and walks over the sets of the group, whose records were staged in shared memory
-// once per CTA (read back as warp-wide broadcasts).  Per (set, body, sub-sample) a thread first
-// rejects its samples against the body's transit window (one interval test for all SYS_K when
-// they are time-ordered, else one phase test each) and then runs the in-transit code -- a
-// single instance in the kernel -- only for the surviving samples; lanes whose surviving
-// samples sit in different rows proceed together.
+// k_system -- fused light curve over (parameter set x time sample), warp-centric.
+//
+// CTA = NW warps x (group of <= SYS_MAX_SETS parameter sets).  The group's records are staged in
+// shared memory once per CTA; after that the warps are independent (no block barriers).  A warp
+// owns 32 * SYS_K consecutive time samples as SYS_K rows of 32 (lane = column), time stamps in
+// registers.  Three stages per warp:
+//  A  candidate sets.  Lanes take one SET each: the warp's whole time span [tmin, tmax] (widened
+//     by the exposure stencil) is tested against each body's transit window; a ballot gives the
+//     sets that can have any sample in transit.  Cost ~1/100 instruction per (set, sample).
+//  B  for a candidate set, lanes take their own samples again and test them one by one; hits
+//     are appended (ballot + popc compaction) to a per-warp queue of (set, row, lane) items.
+//  C  the queue is drained 32 items at a time: EVERY lane runs the Kepler + position + flux code
+//     on a different in-window sample (of possibly different sets), so the expensive code runs
+//     with full warps and a single instance of it exists in the kernel.  Inside, a lane walks
+//     its own (body, sub-sample) pairs that pass the window test, so lanes working on different
+//     bodies still execute together.
+// Outputs: flux / flux_sum rows are written as zeros by the owning lane for samples that were
+// not queued, and by the processing lane for queued ones; the likelihood uses a segmented
+// warp-shuffle reduction keyed by set into a per-warp accumulator, written as one partial per
+// (set, warp tile) and summed in fixed order by k_loglike_final (deterministic).
 #ifndef JXP_SYS_MINB
-#define JXP_SYS_MINB 2
+#define JXP_SYS_MINB 8
 #endif
+constexpr int SYS_QCAP = 256;  // queue entries per warp
+
+template <typename T>
+__device__ __forceinline__ bool phase_in_window(const BodyC<T>& c, double tm) {
+  const double ph = fma(tm - c.t0ref, c.inv_period, -c.phase_c);
+  const double d = ph - rint(ph);
+  return (d >= c.wlo) & (d <= c.whi);
+}
+
 template <typename T, int ORDER, bool LOGLIKE>
-__global__ void __launch_bounds__(256, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
+__global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = SYS_K;
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
-  const int tile = blockIdx.x % a.n_tiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % a.n_tiles;  // CTA tile = nwarps warp tiles
   const int group = blockIdx.x / a.n_tiles;
   const int set_base = group * a.sets_per_cta;
   const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
+  const int nb = a.n_bodies;
 
   BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
-  SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * a.n_bodies);
-  double* spart = reinterpret_cast<double*>(sset + a.sets_per_cta);  // [nwarps][sets_per_cta]
+  SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * nb);
+  double* sacc_all = reinterpret_cast<double*>(sset + a.sets_per_cta);  // [nwarps][sets_per_cta]
+  unsigned short* sq_all = reinterpret_cast<unsigned short*>(sacc_all + nwarps * a.sets_per_cta);
+  double* sacc = sacc_all + warp * a.sets_per_cta;
+  unsigned short* sq = sq_all + warp * SYS_QCAP;
 
   {
     // stage the group's records (plain 8-byte copies; sizeof(BodyC), sizeof(SetC) % 8 == 0)
     const unsigned long long* src =
-        reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base * a.n_bodies);
+        reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base * nb);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
-    const int nw = nsl * a.n_bodies * (int)(sizeof(BodyC<T>) / 8);
+    const int nw = nsl * nb * (int)(sizeof(BodyC<T>) / 8);
     for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
     const unsigned long long* src2 = reinterpret_cast<const unsigned long long*>(a.sets + set_base);
     unsigned long long* dst2 = reinterpret_cast<unsigned long long*>(sset);
     const int nw2 = nsl * (int)(sizeof(SetC<T>) / 8);
     for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
+    if (LOGLIKE)
+      for (int i = lane; i < a.sets_per_cta; i += 32) sacc[i] = 0.0;
+  }
+  if (a.use_window == 0) {
+    // dense mode: mark every staged body "always" so that the hot loops test one flag only
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsl * nb; i += nthreads) sbody[i].flags |= BODY_ALWAYS;
   }
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // first owned sample; sample k of this thread is idx0 + 32 k
-  const int64_t idx0 = ((int64_t)tile * nthreads + warp * 32) * K + lane;
+  // this warp's samples: sample k of lane l is wbase + 32 k + l
+  const int64_t wtile = (int64_t)tile * nwarps + warp;
+  const int64_t wbase = wtile * (32 * K);
   double tk[K];
   unsigned valid = 0;
-  SpanK sp;
-  sp.mono = true;
+  double tmin = 1e300, tmax = -1e300;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const bool ok = idx0 + 32 * k < a.n_times;
-    tk[k] = ok ? a.t[idx0 + 32 * k] : (k > 0 ? tk[k - 1] : 0.0);
+    const int64_t idx = wbase + 32 * k + lane;
+    const bool ok = idx < a.n_times;
+    tk[k] = ok ? a.t[idx] : 0.0;
     valid |= ok ? (1u << k) : 0u;
-    if (k > 0) sp.mono = sp.mono && (tk[k] >= tk[k - 1]);
+    if (ok) {
+      tmin = fmin(tmin, tk[k]);
+      tmax = fmax(tmax, tk[k]);
+    }
   }
-  sp.first = tk[0];
-  sp.span = tk[K - 1] - tk[0];
-  __syncthreads();
-
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  }
   const int nsub = a.st.n;
-  const bool use_window = a.use_window != 0;
+  const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
+  const double span_lo = tmin + dtmin, span = (tmax + dtmax) - span_lo;
+  const bool want_zero = (a.flux != nullptr) || (a.flux_sum != nullptr);
   unsigned n_kep = 0, n_ld = 0;
+  int qn = 0;  // queue fill (warp-uniform)
+  __syncthreads();
+  if (wbase >= a.n_times) return;  // (no further block barriers)
 
-  for (int sl = 0; sl < nsl; ++sl) {
-    const int set = set_base + sl;
-    const SetC<T> sc = sset[sl];
-    T total[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) total[k] = T(0);
-    unsigned any_hit = 0;
-#pragma unroll 1
-    for (int body = 0; body < a.n_bodies; ++body) {
-      const BodyC<T>& c = sbody[sl * a.n_bodies + body];
-      T accb[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) accb[k] = T(0);
-#pragma unroll 1
-      for (int j = 0; j < nsub; ++j) {
-        const double dtj = a.st.dt[j];
-        unsigned mask = window_mask<T, K>(c, tk, sp, dtj, valid, use_window);
-        any_hit |= mask;
-        const T wj = T(a.st.w[j]);
-        // ONE instance of the in-transit code; each lane walks its own surviving samples
-#pragma unroll 1
-        while (mask) {
-          const int k = __ffs(mask) - 1;
-          mask &= mask - 1;
-          ++n_kep;
-          const T v = eval_in_window<T, ORDER>(c, sc, &a.tab, pick(tk, k) + dtj, n_ld);
-          const T wv = (nsub == 1) ? v : wj * v;
-#pragma unroll
-          for (int kk = 0; kk < K; ++kk) accb[kk] += (kk == k) ? wv : T(0);
+  // fill (stages A, B) / drain (stage C) loop; ONE instance of the drain code
+  int c0 = 0, c0_cur = 0;
+  unsigned visit = 0, cmask = 0;
+  while (true) {
+    bool done = false;
+    while (qn <= SYS_QCAP - 32 * K) {
+      if (!visit) {
+        if (c0 >= nsl) {
+          done = true;
+          break;
         }
+        // ---- stage A: lane = set --------------------------------------------------------
+        bool cand = false;
+        const int sl = c0 + lane;
+        if (sl < nsl) {
+          for (int b = 0; b < nb; ++b) {
+            const BodyC<T>& c = sbody[sl * nb + b];
+            if (c.flags & BODY_ALWAYS) {
+              cand = true;
+            } else {
+              const double ph0 = fma(span_lo - c.t0ref, c.inv_period, -c.phase_c);
+              const double d0 = ph0 - rint(ph0);
+              const double d1 = fma(span, c.inv_period, d0);
+              // the span lies before this cycle's window, or between it and the next one
+              const bool miss = (d1 < c.wlo) | ((d0 > c.whi) & (d1 < 1.0 + c.wlo));
+              cand = cand || !miss;
+            }
+          }
+        }
+        cmask = __ballot_sync(0xffffffffu, cand);
+        const int nchunk = min(32, nsl - c0);
+        // in flux modes every set of the chunk is visited (zero fill)
+        visit = want_zero ? ((nchunk == 32) ? 0xffffffffu : ((1u << nchunk) - 1u)) : cmask;
+        c0_cur = c0;
+        c0 += 32;
+        continue;
       }
-      if (a.flux) {
-        T* dst = a.flux + ((size_t)set * a.n_times + idx0) * a.n_bodies + body;
+      // ---- stage B: lane = sample, one set -------------------------------------------------
+      const int s_in = __ffs(visit) - 1;
+      visit &= visit - 1;
+      const int sl = c0_cur + s_in;
+      unsigned hits = 0;
+      if (cmask & (1u << s_in)) {
+        for (int b = 0; b < nb; ++b) {
+          const BodyC<T>& c = sbody[sl * nb + b];
+          if (c.flags & BODY_ALWAYS) {
+            hits = valid;
+          } else {
+            // widened by the exposure stencil: a superset of the samples with any sub-sample hit
+            const double wlo = fma(-dtmax, c.inv_period, c.wlo), whi = fma(-dtmin, c.inv_period, c.whi);
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (valid & (1u << k)) dst[(size_t)(32 * k) * a.n_bodies] = accb[k];
-      }
-#pragma unroll
-      for (int k = 0; k < K; ++k) total[k] += accb[k];
-    }
-    if (a.flux_sum) {
-      T* dst = a.flux_sum + (size_t)set * a.n_times + idx0;
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (valid & (1u << k)) dst[32 * k] = total[k];  // 256 B (128 B in fp32) per warp store
-    }
-    if (LOGLIKE) {
-      double dchi = 0.0;
-      if (any_hit) {
+            for (int k = 0; k < K; ++k) {
+              const double ph = fma(tk[k] - c.t0ref, c.inv_period, -c.phase_c);
+              const double d = ph - rint(ph);
+              hits |= ((d >= wlo) & (d <= whi)) ? (1u << k) : 0u;
+            }
+          }
+        }
+        hits &= valid;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          if (total[k] != T(0)) {
-            // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: change of chi^2 w.r.t. the zero model
-            const T w = a.winv[idx0 + 32 * k];
-            const T r0 = (a.y[idx0 + 32 * k] - T(1)) * w;
-            const T mw = total[k] * w;
-            dchi += (double)(-mw) * (double)(T(2) * r0 - mw);
+          const unsigned mk = __ballot_sync(0xffffffffu, (hits >> k) & 1u);
+          if ((hits >> k) & 1u)
+            sq[qn + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)((sl << 7) | (k << 5) | lane);
+          qn += __popc(mk);
+        }
+      }
+      if (want_zero) {
+        const int set = set_base + sl;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if ((valid & ~hits) & (1u << k)) {
+            const int64_t idx = wbase + 32 * k + lane;
+            if (a.flux) {
+#pragma unroll 1
+              for (int b = 0; b < nb; ++b) a.flux[((size_t)set * a.n_times + idx) * nb + b] = T(0);
+            }
+            if (a.flux_sum) a.flux_sum[(size_t)set * a.n_times + idx] = T(0);
           }
         }
       }
-      if (__any_sync(0xffffffffu, any_hit != 0)) {
-        for (int o = 16; o > 0; o >>= 1) dchi += __shfl_down_sync(0xffffffffu, dchi, o);
+    }
+
+    // ---- stage C: drain the queue, 32 in-window samples at a time ---------------------------
+    __syncwarp();
+#pragma unroll 1
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+      const bool have = q0 + lane < qn;
+      const unsigned item = have ? sq[q0 + lane] : 0u;
+      const int sl = (int)(item >> 7);
+      const int k = (int)((item >> 5) & 3u);
+      const int src = (int)(item & 31u);
+      // fetch the sample's time stamp from the owning lane
+      double tm0 = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const double v = __shfl_sync(0xffffffffu, tk[kk], src);
+        tm0 = (kk == k) ? v : tm0;
       }
-      if (lane == 0) spart[warp * a.sets_per_cta + sl] = dchi;
+      const int64_t idx = wbase + 32 * k + src;
+      T total = T(0);
+      if (have) {
+        const int set = set_base + sl;
+        const SetC<T> sc = sset[sl];
+        const BodyC<T>* bodies = sbody + sl * nb;
+        const int npairs = nb * nsub;
+        int pair = 0, cur_b = 0;
+        T accb = T(0);
+        // walk this sample's (body, sub-sample) pairs that pass the window test
+#pragma unroll 1
+        while (true) {
+          int b = 0, j = 0;
+          bool found = false;
+          while (pair < npairs) {
+            b = pair / nsub;
+            j = pair - b * nsub;
+            ++pair;
+            const BodyC<T>& c = bodies[b];
+            if ((c.flags & BODY_ALWAYS) || phase_in_window(c, tm0 + a.st.dt[j])) {
+              found = true;
+              break;
+            }
+          }
+          if (!found) break;
+          if (b != cur_b) {
+            if (a.flux)
+              for (int bb = cur_b; bb < b; ++bb)
+                a.flux[((size_t)set * a.n_times + idx) * nb + bb] = (bb == cur_b) ? accb : T(0);
+            total += accb;
+            accb = T(0);
+            cur_b = b;
+          }
+          ++n_kep;
+          const T v = eval_in_window<T, ORDER>(bodies[b], sc, &a.tab, tm0 + a.st.dt[j], n_ld);
+          accb = (nsub == 1) ? v : jfma(T(a.st.w[j]), v, accb);
+        }
+        if (a.flux)
+          for (int bb = cur_b; bb < nb; ++bb)
+            a.flux[((size_t)set * a.n_times + idx) * nb + bb] = (bb == cur_b) ? accb : T(0);
+        total += accb;
+        if (a.flux_sum) a.flux_sum[(size_t)set * a.n_times + idx] = total;
+      }
+      if (LOGLIKE) {
+        // (r0 - m w)^2 - r0^2 with r0 = (y - 1) w: the change of chi^2 w.r.t. the zero model
+        double dchi = 0.0;
+        if (have && total != T(0)) {
+          const T w = a.winv[idx];
+          const T r0 = (a.y[idx] - T(1)) * w;
+          const T mw = total * w;
+          dchi = (double)(-mw) * (double)(T(2) * r0 - mw);
+        }
+        // segmented inclusive scan keyed by set (queue entries of one set are contiguous)
+        const int key = have ? sl : -1 - lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double u = __shfl_up_sync(0xffffffffu, dchi, o);
+          const int ku = __shfl_up_sync(0xffffffffu, key, o);
+          if (lane >= o && ku == key) dchi += u;
+        }
+        const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+        if (have && (lane == 31 || kn != key)) sacc[sl] += dchi;
+        __syncwarp();
+      }
     }
+    qn = 0;
+    __syncwarp();
+    if (done) break;
   }
+
   if (LOGLIKE) {
-    __syncthreads();
-    for (int sl = threadIdx.x; sl < nsl; sl += nthreads) {
-      double acc = 0.0;
-      for (int w = 0; w < nwarps; ++w) acc += spart[w * a.sets_per_cta + sl];
-      a.partial[(size_t)(set_base + sl) * a.n_tiles + tile] = acc;
-    }
+    for (int sl = lane; sl < nsl; sl += 32)
+      a.partial[(size_t)(set_base + sl) * a.n_wtiles + wtile] = sacc[sl];
   }
-  // executed-work counters (two atomics per warp per CTA)
+  // executed-work counters (two atomics per warp)
   n_kep = __reduce_add_sync(0xffffffffu, n_kep);
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
   if (lane == 0) {
@@ -730,23 +876,25 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // launch geometry: enough CTAs to fill the machine several times over, as many sets per
   // CTA as that allows (amortises the time-stamp loads and the record staging)
   const int sms = sm_count();
-  int threads = 256;
+  int threads = 128;
   if (const char* env = getenv("JXP_SYS_THREADS")) {  // development knob
     const int v = atoi(env);
-    if (v >= 32 && v <= 256 && v % 32 == 0) threads = v;
+    if (v >= 32 && v <= 128 && v % 32 == 0) threads = v;
   }
-  int64_t n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
-  while (threads > 32 && n_tiles * n_sets < 2 * sms) {
+  const int64_t n_wtiles = (n_times + 32 * SYS_K - 1) / (32 * SYS_K);
+  int64_t n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
+  while (threads > 32 && n_tiles * ((n_sets + SYS_MAX_SETS - 1) / SYS_MAX_SETS) < 4 * sms) {
     threads /= 2;
-    n_tiles = (n_times + (int64_t)threads * SYS_K - 1) / ((int64_t)threads * SYS_K);
+    n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
   }
-  int spc = (int)((n_tiles * (int64_t)n_sets) / ((int64_t)sms * 64));
-  if (spc < 1) spc = 1;
-  if (spc > SYS_MAX_SETS) spc = SYS_MAX_SETS;
+  int spc = SYS_MAX_SETS;
+  while (spc > 32 && n_tiles * ((n_sets + spc - 1) / spc) < 8 * sms) spc -= 32;
   if (spc > n_sets) spc = n_sets;
+  if (n_bodies * spc > 512) spc = (512 / n_bodies) > 0 ? (512 / n_bodies) : 1;
   const int64_t n_groups = (n_sets + spc - 1) / spc;
   const int64_t n_ctas = n_tiles * n_groups;
   if (n_ctas > 2147483647LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: grid too large");
+  if (spc > 511) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: sets per CTA");
 
   a.bodies = d_bodies;
   a.sets = d_sets;
@@ -756,6 +904,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   a.n_bodies = n_bodies;
   a.sets_per_cta = spc;
   a.n_tiles = (int)n_tiles;
+  a.n_wtiles = (int)n_wtiles;
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
   a.flux_sum = flux_sum;
@@ -767,7 +916,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
 
   const size_t smem = sizeof(BodyC<T>) * (size_t)spc * n_bodies + sizeof(SetC<T>) * (size_t)spc +
-                      sizeof(double) * (size_t)spc * (threads / 32);
+                      sizeof(double) * (size_t)spc * (threads / 32) +
+                      sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32);
   if (smem > 200 * 1024) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: shared memory");
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
@@ -780,13 +930,13 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     return check_launch("jxp_system_light_curve");
   };
   if (gl_order == 10)
-    rc = loglike ? launch(k_system<T, 10, true>) : launch(k_system<T, 10, false>);
+    rc = loglike ? launch(k_system<T, 11, true>) : launch(k_system<T, 11, false>);
   else
     rc = loglike ? launch(k_system<T, 0, true>) : launch(k_system<T, 0, false>);
   if (rc != JXP_OK) return rc;
 
   if (loglike) {
-    k_loglike_final<T><<<(n_sets + 127) / 128, 128, 0, st>>>(d_partial, (int)n_tiles, n_sets,
+    k_loglike_final<T><<<(n_sets + 127) / 128, 128, 0, st>>>(d_partial, (int)n_wtiles, n_sets,
                                                             d_scalars, loglike);
     rc = check_launch("jxp_system_light_curve(loglike final)");
   }

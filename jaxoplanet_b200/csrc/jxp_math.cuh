@@ -63,7 +63,7 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
   const T r = jfma(T(3) * alphad, d - ome, M2) * M;
   const T q = jfma(T(2) * alphad, ome, -M2);
   const T q2 = q * q;
-  T w = jcbrt(jabs(r) + jsqrt(jfma(q2, q, r * r)));
+  T w = jcbrt_lo(jabs(r) + jsqrt(jfma(q2, q, r * r)));
   w = w * w;
   const T W = jfma(w, w + q, q2);
   const T E0 = jdiv(jfma(T(2) * r, w, M * W), W * d);
@@ -121,6 +121,29 @@ struct GLTable {
 
 template <int ORDER>
 struct GL;
+
+// constant-bank copies for the rolled node loop of the fused kernels
+__device__ __constant__ double c_gl10[3][10] = {
+    {-0.9739065285171717, -0.8650633666889844, -0.6794095682990244, -0.4333953941292472,
+     -0.14887433898163116, 0.14887433898163116, 0.4333953941292472, 0.6794095682990244,
+     0.8650633666889844, 0.9739065285171717},
+    {0.06667134430868714, 0.14945134915058053, 0.21908636251598224, 0.26926671930999674,
+     0.2955242247147533, 0.2955242247147533, 0.26926671930999674, 0.21908636251598224,
+     0.14945134915058053, 0.06667134430868714},
+    {0.9991601288170098, 0.9776208824732407, 0.8758595017700398, 0.6293961480326326,
+     0.23172567069845093, -0.23172567069845082, -0.6293961480326326, -0.8758595017700398,
+     -0.9776208824732407, -0.9991601288170098}};
+
+// ORDER == 11 is a tag: order 10 with a rolled (partially unrolled) node loop reading the tables
+// from the constant bank -- small code for the fused kernels, where instruction fetch matters.
+template <>
+struct GL<11> {
+  static constexpr bool has_cpi = true;
+  __device__ __forceinline__ static int n(const GLTable*) { return 10; }
+  __device__ __forceinline__ static double x(int i, const GLTable*) { return c_gl10[0][i]; }
+  __device__ __forceinline__ static double w(int i, const GLTable*) { return c_gl10[1][i]; }
+  __device__ __forceinline__ static double cpi(int i) { return c_gl10[2][i]; }
+};
 
 template <>
 struct GL<10> {
@@ -251,15 +274,15 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
   S acc = S(B(0));
   const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
   const int order = GL<ORDER>::n(tab);
-#pragma unroll
-  for (int i = 0; i < (ORDER > 0 ? ORDER : order); ++i) {
+#pragma unroll(ORDER == 10 ? 10 : 2)
+  for (int i = 0; i < (ORDER == 10 ? 10 : order); ++i) {
     const B xi = B(GL<ORDER>::x(i, tab));
     const B wi = B(GL<ORDER>::w(i, tab));
     S c;
     if (const_nodes)
       c = S(B(GL<ORDER>::cpi(i)));
     else
-      c = jcos(rng * xi + kappa0 * B(0.5));
+      c = jcos_node(rng * xi + kappa0 * B(0.5));
     const S omz2 = jmax(S(B(0)), r2pb2 - two_br * c);
     const S z2 = B(1) - omz2;
     // limb_dark.py:164-172: the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0

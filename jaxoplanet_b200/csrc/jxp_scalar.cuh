@@ -43,6 +43,12 @@ __device__ __forceinline__ float jsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double jzsqrt(double x) { return fsqrt(x); }
 __device__ __forceinline__ float jzsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double jcbrt(double x) { return cbrt(x); }
+// cube root to float accuracy (the Kepler starter only needs ~1e-6)
+__device__ __forceinline__ double jcbrt_lo(double x) { return (double)cbrtf((float)x); }
+__device__ __forceinline__ float jcbrt_lo(float x) { return cbrtf(x); }
+// cos of a quadrature node angle in [0, pi]
+__device__ __forceinline__ double jcos_node(double x) { return fcos_0pi(x); }
+__device__ __forceinline__ float jcos_node(float x) { return cosf(x); }
 __device__ __forceinline__ float jcbrt(float x) { return cbrtf(x); }
 __device__ __forceinline__ double jabs(double x) { return fabs(x); }
 __device__ __forceinline__ float jabs(float x) { return fabsf(x); }
@@ -50,7 +56,7 @@ __device__ __forceinline__ double jmax(double a, double b) { return fmax(a, b); 
 __device__ __forceinline__ float jmax(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double jmin(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float jmin(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double jatan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ double jatan2(double y, double x) { return fatan2(y, x); }
 __device__ __forceinline__ float jatan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double jcos(double x) { return fcos(x); }
 __device__ __forceinline__ float jcos(float x) { return cosf(x); }
@@ -235,6 +241,7 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos(const JXP_D& x) {
   JXP_FOR r.d[i] = -s * x.d[i];
   return r;
 }
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos_node(const JXP_D& x) { return jcos(x); }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jsin(const JXP_D& x) {
   JXP_D r;
   T s, c;
