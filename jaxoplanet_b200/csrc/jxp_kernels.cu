@@ -548,7 +548,7 @@ __device__ __forceinline__ bool phase_in_window(const BodyC<T>& c, double tm) {
   return (d >= c.wlo) & (d <= c.whi);
 }
 
-template <typename T, int ORDER, bool LOGLIKE>
+template <typename T, int ORDER, bool LOGLIKE, bool DENSE>
 __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = SYS_K;
@@ -567,6 +567,8 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   unsigned short* sq_all = reinterpret_cast<unsigned short*>(sacc_all + nwarps * a.sets_per_cta);
   double* sacc = sacc_all + warp * a.sets_per_cta;
   unsigned short* sq = sq_all + warp * SYS_QCAP;
+  // dense variant: sky separation of the queued in-transit samples
+  T* sqb = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + warp * SYS_QCAP;
 
   {
     // stage the group's records (plain 8-byte copies; sizeof(BodyC), sizeof(SetC) % 8 == 0)
@@ -619,6 +621,94 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   __syncthreads();
   if (wbase >= a.n_times) return;  // (no further block barriers)
 
+  if constexpr (DENSE) {
+    // ---- dense variant (JXP_FLAG_NO_WINDOW, one body, no exposure integration) ----------------
+    // Every sample runs the Kepler solve + position directly from registers (full warps, like
+    // K1); samples found in transit are compacted with their separation b into the per-warp
+    // queue and the flux code then runs on 32 in-transit samples at a time.
+    int sl = 0, k = 0;
+    while (true) {
+      bool done = false;
+      while (qn <= SYS_QCAP - 32) {
+        if (sl >= nsl) {
+          done = true;
+          break;
+        }
+        const BodyC<T>& c = sbody[sl];
+        const double tm = pick(tk, k);
+        const bool ok = (valid >> k) & 1u;
+        T b = T(0), Z = T(-1);
+        if (ok) {
+          ++n_kep;
+          const T Mr = T(mean_anomaly_reduced(c, tm));
+          T sf, cf, Edummy;
+          if (c.flags & BODY_CIRCULAR) {
+            jsincos(Mr, &sf, &cf);
+          } else {
+            kepler_reduced<T, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
+          }
+          sky_position(c, sf, cf, b, Z);
+        }
+        const bool hit = ok && (Z > T(0)) && !(b >= c.onepr);
+        const unsigned mk = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int pos = qn + __popc(mk & ((1u << lane) - 1u));
+          sq[pos] = (unsigned short)((sl << 7) | (k << 5) | lane);
+          sqb[pos] = b;
+        }
+        qn += __popc(mk);
+        if (want_zero && ok && !hit) {
+          const int64_t idx = wbase + 32 * k + lane;
+          if (a.flux) a.flux[(size_t)(set_base + sl) * a.n_times + idx] = T(0);
+          if (a.flux_sum) a.flux_sum[(size_t)(set_base + sl) * a.n_times + idx] = T(0);
+        }
+        if (++k == K) {
+          k = 0;
+          ++sl;
+        }
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int q0 = 0; q0 < qn; q0 += 32) {
+        const bool have = q0 + lane < qn;
+        const unsigned item = have ? sq[q0 + lane] : 0u;
+        const int isl = (int)(item >> 7);
+        const int64_t idx = wbase + 32 * (int)((item >> 5) & 3u) + (int)(item & 31u);
+        T total = T(0);
+        if (have) {
+          const SetC<T> sc = sset[isl];
+          ++n_ld;
+          T s0, s1, s2;
+          ld_solution<T, ORDER>(sqb[q0 + lane], sbody[isl].rr, sc.lmax, &a.tab, s0, s1, s2);
+          total = ld_combine(sc.lmax, s0, s1, s2, sc.g0, sc.g1, sc.g2);
+          if (a.flux) a.flux[(size_t)(set_base + isl) * a.n_times + idx] = total;
+          if (a.flux_sum) a.flux_sum[(size_t)(set_base + isl) * a.n_times + idx] = total;
+        }
+        if (LOGLIKE) {
+          double dchi = 0.0;
+          if (have && total != T(0)) {
+            const T w = a.winv[idx];
+            const T r0 = (a.y[idx] - T(1)) * w;
+            const T mw = total * w;
+            dchi = (double)(-mw) * (double)(T(2) * r0 - mw);
+          }
+          const int key = have ? isl : -1 - lane;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, dchi, o);
+            const int ku = __shfl_up_sync(0xffffffffu, key, o);
+            if (lane >= o && ku == key) dchi += u;
+          }
+          const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+          if (have && (lane == 31 || kn != key)) sacc[isl] += dchi;
+          __syncwarp();
+        }
+      }
+      qn = 0;
+      __syncwarp();
+      if (done) break;
+    }
+  } else {
   // fill (stages A, B) / drain (stage C) loop; ONE instance of the drain code
   int c0 = 0, c0_cur = 0;
   unsigned visit = 0, cmask = 0;
@@ -787,6 +877,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
     __syncwarp();
     if (done) break;
   }
+  }  // !DENSE
 
   if (LOGLIKE) {
     for (int sl = lane; sl < nsl; sl += 32)
@@ -917,7 +1008,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
 
   const size_t smem = sizeof(BodyC<T>) * (size_t)spc * n_bodies + sizeof(SetC<T>) * (size_t)spc +
                       sizeof(double) * (size_t)spc * (threads / 32) +
-                      sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32);
+                      sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32) +
+                      sizeof(T) * (size_t)SYS_QCAP * (threads / 32);
   if (smem > 200 * 1024) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: shared memory");
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
@@ -929,10 +1021,15 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return check_launch("jxp_system_light_curve");
   };
-  if (gl_order == 10)
-    rc = loglike ? launch(k_system<T, 11, true>) : launch(k_system<T, 11, false>);
-  else
-    rc = loglike ? launch(k_system<T, 0, true>) : launch(k_system<T, 0, false>);
+  const bool dense = (a.use_window == 0) && n_bodies == 1 && a.st.n == 1;
+  if (gl_order == 10) {
+    if (dense)
+      rc = loglike ? launch(k_system<T, 11, true, true>) : launch(k_system<T, 11, false, true>);
+    else
+      rc = loglike ? launch(k_system<T, 11, true, false>) : launch(k_system<T, 11, false, false>);
+  } else {
+    rc = loglike ? launch(k_system<T, 0, true, false>) : launch(k_system<T, 0, false, false>);
+  }
   if (rc != JXP_OK) return rc;
 
   if (loglike) {

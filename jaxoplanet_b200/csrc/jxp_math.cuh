@@ -138,7 +138,10 @@ __device__ __constant__ double c_gl10[3][10] = {
 // from the constant bank -- small code for the fused kernels, where instruction fetch matters.
 template <>
 struct GL<11> {
-  static constexpr bool has_cpi = true;
+  // no constant-node shortcut: in the fused kernels a warp mixes inside-the-disk and
+  // ingress/egress samples, and a per-lane shortcut makes the warp execute BOTH loop versions
+  // (profiles/r1_c3_v3_queue.md); one uniform loop with the 17-instruction node cosine is cheaper
+  static constexpr bool has_cpi = false;
   __device__ __forceinline__ static int n(const GLTable*) { return 10; }
   __device__ __forceinline__ static double x(int i, const GLTable*) { return c_gl10[0][i]; }
   __device__ __forceinline__ static double w(int i, const GLTable*) { return c_gl10[1][i]; }
