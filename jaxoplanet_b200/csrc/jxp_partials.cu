@@ -24,7 +24,7 @@ using namespace jxph;
 namespace {
 constexpr int NO = 5;  // orbit directions: P, t0, e, omega, b
 constexpr int TR_K = 2;
-constexpr int TR_MAX_SETS = 16;
+constexpr int TR_MAX_SETS = 32;
 
 template <typename T>
 struct BodyD {
@@ -44,7 +44,7 @@ struct TrLayout {
 
 TrLayout tr_layout(int n_sets, int64_t n_times) {
   TrLayout L;
-  const int tile = 128 * TR_K;
+  const int tile = 32 * TR_K;  // one warp tile
   L.n_tiles = (int)((n_times + tile - 1) / tile);
   size_t off = 0;
   L.off_bodies = off;
@@ -217,7 +217,7 @@ struct TrArgs {
   const BodyD<T>* bodies;
   const double* t;
   int64_t n_times;
-  int n_sets, sets_per_cta, n_tiles, use_window;
+  int n_sets, sets_per_cta, n_tiles, n_wtiles, use_window;
   T* flux;      // [n_sets][n_times]
   T* partials;  // [n_sets][8][n_times]
   const T* y;
@@ -227,131 +227,238 @@ struct TrArgs {
   GLTable tab;
 };
 
-// Same CTA structure as k_system (jxp_kernels.cu): warp-owned rows of 32 samples in registers,
-// sets of the group staged in shared memory, window rejection first, one instance of the
-// in-transit code.  Every output row is one fully coalesced warp store.
+// Same warp-centric three-stage structure as k_system (jxp_kernels.cu): (A) lanes = sets, the
+// warp's time span against each set's transit window; (B) lanes = samples for candidate sets,
+// hits compacted into a per-warp queue, zero rows written for everything else; (C) the queue
+// drained 32 in-window samples at a time through ONE instance of the dual-number code.
+// Every zero row is one fully coalesced warp store (256 B in f64).
+constexpr int TR_QCAP = 128;
+#ifndef JXP_TR_MINB
+#define JXP_TR_MINB 4
+#endif
 template <typename T, int ORDER, bool LOGLIKE>
-__global__ void __launch_bounds__(256, 2) k_transit_partials(const __grid_constant__ TrArgs<T> a) {
+__global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = TR_K;
   constexpr int NQ = 1 + JXP_NTHETA;
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x % a.n_tiles;
   const int group = blockIdx.x / a.n_tiles;
   const int set_base = group * a.sets_per_cta;
   const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
   BodyD<T>* sbody = reinterpret_cast<BodyD<T>*>(smem_raw);
-  double* spart = reinterpret_cast<double*>(sbody + a.sets_per_cta);  // [nwarps][9]
+  double* sacc_all = reinterpret_cast<double*>(sbody + a.sets_per_cta);  // [nwarps][spc][9]
+  unsigned short* sq_all = reinterpret_cast<unsigned short*>(sacc_all + (size_t)nwarps * a.sets_per_cta * NQ);
+  double* sacc = sacc_all + (size_t)warp * a.sets_per_cta * NQ;
+  unsigned short* sq = sq_all + warp * TR_QCAP;
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.bodies + set_base);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
     const int nw = nsl * (int)(sizeof(BodyD<T>) / 8);
     for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
+    if (LOGLIKE)
+      for (int i = lane; i < a.sets_per_cta * NQ; i += 32) sacc[i] = 0.0;
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx0 = ((int64_t)tile * nthreads + warp * 32) * K + lane;
+  if (a.use_window == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsl; i += nthreads) sbody[i].c.flags |= BODY_ALWAYS;
+  }
+  const int64_t wtile = (int64_t)tile * nwarps + warp;
+  const int64_t wbase = wtile * (32 * K);
   double tk[K];
   unsigned valid = 0;
-  SpanK sp;
-  sp.mono = true;
+  double tmin = 1e300, tmax = -1e300;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const bool ok = idx0 + 32 * k < a.n_times;
-    tk[k] = ok ? a.t[idx0 + 32 * k] : (k > 0 ? tk[k - 1] : 0.0);
+    const int64_t idx = wbase + 32 * k + lane;
+    const bool ok = idx < a.n_times;
+    tk[k] = ok ? a.t[idx] : 0.0;
     valid |= ok ? (1u << k) : 0u;
-    if (k > 0) sp.mono = sp.mono && (tk[k] >= tk[k - 1]);
+    if (ok) {
+      tmin = fmin(tmin, tk[k]);
+      tmax = fmax(tmax, tk[k]);
+    }
   }
-  sp.first = tk[0];
-  sp.span = tk[K - 1] - tk[0];
-  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  }
   const int nsub = a.st.n;
-  const bool use_window = a.use_window != 0;
+  const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
+  const double span_lo = tmin + dtmin, span = (tmax + dtmax) - span_lo;
+  int qn = 0;
+  __syncthreads();
+  if (wbase >= a.n_times) return;  // (no further block barriers)
 
-  for (int sl = 0; sl < nsl; ++sl) {
-    const int set = set_base + sl;
-    const BodyD<T>& bd = sbody[sl];
-    T out[K][NQ];  // flux, 8 partials
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) out[k][q] = T(0);
-    unsigned hitmask = 0;
-#pragma unroll 1
-    for (int j = 0; j < nsub; ++j) {
-      const double dtj = a.st.dt[j];
-      unsigned mask = window_mask<T, K>(bd.c, tk, sp, dtj, valid, use_window);
-      const T wj = T(a.st.w[j]);
-#pragma unroll 1
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        T f1 = T(0);
-        T p1[JXP_NTHETA];
-        if (eval_sample_partials<T, ORDER>(bd, &a.tab, pick(tk, k) + dtj, f1, p1)) {
-          const T w = (nsub == 1) ? T(1) : wj;
-          hitmask |= 1u << k;
-#pragma unroll
-          for (int kk = 0; kk < K; ++kk) {
-            if (kk == k) {
-              out[kk][0] = jfma(w, f1, out[kk][0]);
-#pragma unroll
-              for (int q = 0; q < JXP_NTHETA; ++q) out[kk][1 + q] = jfma(w, p1[q], out[kk][1 + q]);
-            }
+  int c0 = 0, c0_cur = 0;
+  unsigned visit = 0, cmask = 0;
+  while (true) {
+    bool done = false;
+    while (qn <= TR_QCAP - 32 * K) {
+      if (!visit) {
+        if (c0 >= nsl) {
+          done = true;
+          break;
+        }
+        // ---- stage A: lane = set ----------------------------------------------------------
+        bool cand = false;
+        const int sl = c0 + lane;
+        if (sl < nsl) {
+          const BodyC<T>& c = sbody[sl].c;
+          if (c.flags & BODY_ALWAYS) {
+            cand = true;
+          } else {
+            const double ph0 = fma(span_lo - c.t0ref, c.inv_period, -c.phase_c);
+            const double d0 = ph0 - rint(ph0);
+            const double d1 = fma(span, c.inv_period, d0);
+            cand = !((d1 < c.wlo) | ((d0 > c.whi) & (d1 < 1.0 + c.wlo)));
           }
         }
+        cmask = __ballot_sync(0xffffffffu, cand);
+        const int nchunk = min(32, nsl - c0);
+        visit = (nchunk == 32) ? 0xffffffffu : ((1u << nchunk) - 1u);  // zero rows for every set
+        c0_cur = c0;
+        c0 += 32;
+        continue;
       }
-    }
-    if (a.flux) {
-      T* dst = a.flux + (size_t)set * a.n_times + idx0;
+      // ---- stage B: lane = sample, one set ------------------------------------------------------
+      const int s_in = __ffs(visit) - 1;
+      visit &= visit - 1;
+      const int sl = c0_cur + s_in;
+      unsigned hits = 0;
+      if (cmask & (1u << s_in)) {
+        const BodyC<T>& c = sbody[sl].c;
+        if (c.flags & BODY_ALWAYS) {
+          hits = valid;
+        } else {
+          const double wlo = fma(-dtmax, c.inv_period, c.wlo), whi = fma(-dtmin, c.inv_period, c.whi);
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (valid & (1u << k)) dst[32 * k] = out[k][0];
-    }
-    if (a.partials) {
-#pragma unroll
-      for (int q = 0; q < JXP_NTHETA; ++q) {
-        T* dst = a.partials + ((size_t)set * JXP_NTHETA + q) * a.n_times + idx0;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (valid & (1u << k)) dst[32 * k] = out[k][1 + q];
-      }
-    }
-    if (LOGLIKE) {
-      double acc9[NQ];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) acc9[q] = 0.0;
-      if (hitmask) {
+          for (int k = 0; k < K; ++k) {
+            const double ph = fma(tk[k] - c.t0ref, c.inv_period, -c.phase_c);
+            const double d = ph - rint(ph);
+            hits |= ((d >= wlo) & (d <= whi)) ? (1u << k) : 0u;
+          }
+          hits &= valid;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          if (hitmask & (1u << k)) {
-            const T w = a.winv[idx0 + 32 * k];
-            const T r0 = (a.y[idx0 + 32 * k] - T(1)) * w;
-            const T mw = out[k][0] * w;
-            const T rm = r0 - mw;  // ((y - 1) - m) / sigma
-            acc9[0] += (double)(-mw) * (double)(T(2) * r0 - mw);
-            const double g = (double)(rm * w);  // d loglike / d m
+          const unsigned mk = __ballot_sync(0xffffffffu, (hits >> k) & 1u);
+          if ((hits >> k) & 1u)
+            sq[qn + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)((sl << 7) | (k << 5) | lane);
+          qn += __popc(mk);
+        }
+      }
+      {
+        // zero rows for the samples that were not queued
+        const int set = set_base + sl;
+        const unsigned zmask = valid & ~hits;
+        if (a.flux) {
+          T* dst = a.flux + (size_t)set * a.n_times + wbase + lane;
 #pragma unroll
-            for (int q = 0; q < JXP_NTHETA; ++q) acc9[1 + q] += g * (double)out[k][1 + q];
+          for (int k = 0; k < K; ++k)
+            if (zmask & (1u << k)) dst[32 * k] = T(0);
+        }
+        if (a.partials) {
+#pragma unroll
+          for (int q = 0; q < JXP_NTHETA; ++q) {
+            T* dst = a.partials + ((size_t)set * JXP_NTHETA + q) * a.n_times + wbase + lane;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+              if (zmask & (1u << k)) dst[32 * k] = T(0);
           }
         }
       }
-      __syncthreads();  // spart is reused by every set of the group
-      if (__any_sync(0xffffffffu, hitmask != 0)) {
+    }
+
+    // ---- stage C: drain -----------------------------------------------------------------------
+    __syncwarp();
+#pragma unroll 1
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+      const bool have = q0 + lane < qn;
+      const unsigned item = have ? sq[q0 + lane] : 0u;
+      const int sl = (int)(item >> 7);
+      const int k = (int)((item >> 5) & 3u);
+      const int src = (int)(item & 31u);
+      double tm0 = 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-          for (int o = 16; o > 0; o >>= 1) acc9[q] += __shfl_down_sync(0xffffffffu, acc9[q], o);
+      for (int kk = 0; kk < K; ++kk) {
+        const double v = __shfl_sync(0xffffffffu, tk[kk], src);
+        tm0 = (kk == k) ? v : tm0;
       }
-      if (lane == 0) {
+      const int64_t idx = wbase + 32 * k + src;
+      T out[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) spart[warp * NQ + q] = acc9[q];
+      for (int q = 0; q < NQ; ++q) out[q] = T(0);
+      bool any = false;
+      if (have) {
+        const BodyD<T>& bd = sbody[sl];
+        const int set = set_base + sl;
+#pragma unroll 1
+        for (int j = 0; j < nsub; ++j) {
+          const double tm = tm0 + a.st.dt[j];
+          if (!(bd.c.flags & BODY_ALWAYS) && outside_window(bd.c, tm)) continue;
+          T f1 = T(0);
+          T p1[JXP_NTHETA];
+          if (eval_sample_partials<T, ORDER>(bd, &a.tab, tm, f1, p1)) {
+            const T w = (nsub == 1) ? T(1) : T(a.st.w[j]);
+            out[0] = jfma(w, f1, out[0]);
+#pragma unroll
+            for (int q = 0; q < JXP_NTHETA; ++q) out[1 + q] = jfma(w, p1[q], out[1 + q]);
+            any = true;
+          }
+        }
+        if (a.flux) a.flux[(size_t)set * a.n_times + idx] = out[0];
+        if (a.partials) {
+#pragma unroll
+          for (int q = 0; q < JXP_NTHETA; ++q)
+            a.partials[((size_t)set * JXP_NTHETA + q) * a.n_times + idx] = out[1 + q];
+        }
       }
-      __syncthreads();
-      if (threadIdx.x < NQ) {
-        double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += spart[w * NQ + threadIdx.x];
-        a.partial[((size_t)set * a.n_tiles + tile) * NQ + threadIdx.x] = s;
+      if (LOGLIKE) {
+        double acc9[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc9[q] = 0.0;
+        if (have && any) {
+          const T w = a.winv[idx];
+          const T r0 = (a.y[idx] - T(1)) * w;
+          const T mw = out[0] * w;
+          const T rm = r0 - mw;  // ((y - 1) - m) / sigma
+          acc9[0] = (double)(-mw) * (double)(T(2) * r0 - mw);
+          const double g = (double)(rm * w);  // d loglike / d m
+#pragma unroll
+          for (int q = 0; q < JXP_NTHETA; ++q) acc9[1 + q] = g * (double)out[1 + q];
+        }
+        // segmented inclusive scan keyed by set (queue entries of one set are contiguous)
+        const int key = have ? sl : -1 - lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int ku = __shfl_up_sync(0xffffffffu, key, o);
+          const bool take = lane >= o && ku == key;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double u = __shfl_up_sync(0xffffffffu, acc9[q], o);
+            if (take) acc9[q] += u;
+          }
+        }
+        const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+        if (have && (lane == 31 || kn != key)) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) sacc[sl * NQ + q] += acc9[q];
+        }
+        __syncwarp();
       }
+    }
+    qn = 0;
+    __syncwarp();
+    if (done) break;
+  }
+  if (LOGLIKE) {
+    for (int i = lane; i < nsl * NQ; i += 32) {
+      const int sl = i / NQ, q = i - sl * NQ;
+      a.partial[((size_t)(set_base + sl) * a.n_wtiles + wtile) * NQ + q] = sacc[i];
     }
   }
 }
@@ -444,15 +551,14 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
     if (rc != JXP_OK) return rc;
   }
   const int sms = sm_count();
-  int threads = 256;
-  int64_t n_tiles = (n_times + (int64_t)threads * TR_K - 1) / ((int64_t)threads * TR_K);
-  if (n_tiles * n_sets < 2 * sms) {
-    threads = 128;
-    n_tiles = (n_times + (int64_t)threads * TR_K - 1) / ((int64_t)threads * TR_K);
+  int threads = 128;
+  const int64_t n_wtiles = (n_times + 32 * TR_K - 1) / (32 * TR_K);
+  int64_t n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
+  while (threads > 32 && n_tiles * ((n_sets + TR_MAX_SETS - 1) / TR_MAX_SETS) < 4 * sms) {
+    threads /= 2;
+    n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
   }
-  int spc = (int)((n_tiles * (int64_t)n_sets) / ((int64_t)sms * 32));
-  if (spc < 1) spc = 1;
-  if (spc > TR_MAX_SETS) spc = TR_MAX_SETS;
+  int spc = TR_MAX_SETS;
   if (spc > n_sets) spc = n_sets;
   const int64_t n_groups = (n_sets + spc - 1) / spc;
   const int64_t n_ctas = n_tiles * n_groups;
@@ -463,6 +569,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   a.n_sets = n_sets;
   a.sets_per_cta = spc;
   a.n_tiles = (int)n_tiles;
+  a.n_wtiles = (int)n_wtiles;
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
   a.partials = partials;
@@ -471,19 +578,25 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   a.partial = d_partial;
   a.tab.order = gl_order;
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
-  const size_t smem = sizeof(BodyD<T>) * (size_t)spc + sizeof(double) * (1 + JXP_NTHETA) * (threads / 32);
+  const size_t smem = sizeof(BodyD<T>) * (size_t)spc +
+                      sizeof(double) * (1 + JXP_NTHETA) * (size_t)spc * (threads / 32) +
+                      sizeof(unsigned short) * (size_t)TR_QCAP * (threads / 32);
   auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
     kern<<<(unsigned)n_ctas, threads, smem, st>>>(a);
     return check_launch("jxp_transit_partials");
   };
   if (gl_order == 10)
-    rc = want_ll ? launch(k_transit_partials<T, 10, true>) : launch(k_transit_partials<T, 10, false>);
+    rc = want_ll ? launch(k_transit_partials<T, 11, true>) : launch(k_transit_partials<T, 11, false>);
   else
     rc = want_ll ? launch(k_transit_partials<T, 0, true>) : launch(k_transit_partials<T, 0, false>);
   if (rc != JXP_OK) return rc;
   if (want_ll) {
     const int n = n_sets * (1 + JXP_NTHETA);
-    k_tr_final<T><<<(n + 127) / 128, 128, 0, st>>>(d_partial, (int)n_tiles, n_sets, d_scalars, loglike,
+    k_tr_final<T><<<(n + 127) / 128, 128, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
                                                   dloglike);
     rc = check_launch("jxp_transit_partials(final)");
   }
