@@ -148,7 +148,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -409,6 +409,7 @@ def run_ours(args, rank, local_rank, world):
             "hbm_gbs": 32.0 * n2 / (best * 1e-3) / 1e9,
             "hbm_frac": (32.0 * n2 / (best * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
         del M, e, s_, c_
+        secondary.update(secondary_c4_c5(dev, lib, ev0, ev1, peaks))
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
@@ -433,6 +434,75 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
+    """Configs 4 and 5 at full size (timed, best of 3, device-resident inputs)."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    out = {}
+
+    def best_of(fn, n=3):
+        best = 1e30
+        for i in range(n + 1):
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, ev0.elapsed_time(ev1))
+        return best
+
+    # C4: 3 planets, 30-min cadence, 15x exposure supersampling, 1024 sets x 2e5 times
+    p, u, t, expo = W.c4()
+    bodies, n_sets, _ = pack_bodies(W.system_from(p))
+    bodies = bodies.to(dev).contiguous()
+    ud = torch.as_tensor(u).to(dev).contiguous()
+    td = torch.as_tensor(t).to(dev)
+    n_times = td.numel()
+    wsb = int(lib.jxp_system_workspace_bytes(n_sets, 3, n_times))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    fs = torch.empty((n_sets, n_times), dtype=torch.float64, device=dev)
+    ms = best_of(lambda: _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 3, ud.data_ptr(), 2, 2,
+                                   td.data_ptr(), n_times, expo["exposure_time"], expo["order"], expo["num_samples"],
+                                   10, 0, 0, fs.data_ptr(), 0, 0, 0, 0, ws.data_ptr(), wsb, A.stream_ptr()))
+    stats = (ctypes.c_int64 * 2)()
+    _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 3, n_times, ctypes.addressof(stats), A.stream_ptr())
+    out["c4_3planets_15x_supersampled"] = {
+        "points_per_s": n_sets * n_times / (ms * 1e-3), "ms": ms,
+        "inner_evaluations_per_s": n_sets * n_times * 45 / (ms * 1e-3),
+        "executed": {"kepler_solves": int(stats[0]), "ld_evaluations": int(stats[1])},
+        "tflops_executed": (int(stats[0]) * (W_KEPLER + W_ORBIT) + int(stats[1]) * W_LD) / (ms * 1e-3) / 1e12,
+        "in_transit_fraction": float((fs != 0).double().mean())}
+    del fs, ws, bodies
+    torch.cuda.empty_cache()
+
+    # C5: flux + 8 partials, 16384 sets x 5e4 times, f64 and f32
+    theta, t5 = W.c5()
+    thd = torch.as_tensor(theta).to(dev).contiguous()
+    t5d = torch.as_tensor(t5).to(dev)
+    ns5, nt5 = thd.shape[0], t5d.numel()
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+    wsb5 = int(lib.jxp_transit_workspace_bytes(ns5, nt5))
+    ws5 = torch.empty(wsb5, dtype=torch.uint8, device=dev)
+    for dt, nm in ((torch.float64, "f64"), (torch.float32, "f32")):
+        fl = torch.empty((ns5, nt5), dtype=dt, device=dev)
+        pt = torch.empty((ns5, 8, nt5), dtype=dt, device=dev)
+        ms = best_of(lambda: _lib.call("jxp_transit_partials_" + nm, thd.data_ptr(), ns5, star.data_ptr(), 0,
+                                       t5d.data_ptr(), nt5, 0.0, 0, 0, 10, 0, fl.data_ptr(), pt.data_ptr(), 0, 0, 0,
+                                       0, 0, ws5.data_ptr(), wsb5, A.stream_ptr()))
+        gbs = ns5 * nt5 * 9 * fl.element_size() / (ms * 1e-3) / 1e9
+        out["c5_flux_plus_8_partials_" + nm] = {
+            "points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms, "store_gbs": gbs,
+            "hbm_frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
+        del fl, pt
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():

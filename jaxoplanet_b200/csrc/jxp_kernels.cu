@@ -372,7 +372,7 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
   L.off_winv = off;
   off = align_up(off + elem_sz * (size_t)n_times, 256);
   L.off_scalars = off;
-  off = align_up(off + 8 * sizeof(double), 256);
+  off = align_up(off + 256 * sizeof(double), 256);
   L.off_partial = off;
   off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles, 256);
   L.total = off;
@@ -438,16 +438,22 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
   }
 }
 
-// winv[t] = 1 / sigma[t];  scalars[0] = sum_t ((y - 1) winv)^2,
-// scalars[1] = sum_t (-log sigma - log(2 pi) / 2).   One CTA, fixed summation order.
+// winv[t] = 1 / sigma[t]; per-CTA partial sums of ((y - 1) winv)^2 and of
+// (-log sigma - log(2 pi) / 2) into scalars[LL_SCAL0 + 2 cta .. ]; LL_NCTA CTAs over contiguous
+// chunks, fixed summation order (k_loglike_final / k_tr_final add the LL_NCTA pairs in order).
+constexpr int LL_NCTA = 64;
+constexpr int LL_SCAL0 = 8;
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
                T* __restrict__ winv, double* __restrict__ scalars) {
-  __shared__ double sh0[32], sh1[32];
+  __shared__ double sh0[8], sh1[8];
   double a0 = 0.0, a1 = 0.0;
   const double half_log_2pi = 0.918938533204672741780329736405617639;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = lo + chunk < n ? lo + chunk : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const T sg = sigma[i * ss];
     const T w = T(1) / sg;
     winv[i] = w;
@@ -471,20 +477,20 @@ k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss,
       t0 += sh0[k];
       t1 += sh1[k];
     }
-    scalars[0] = t0;
-    scalars[1] = t1;
+    scalars[LL_SCAL0 + 2 * blockIdx.x] = t0;
+    scalars[LL_SCAL0 + 2 * blockIdx.x + 1] = t1;
   }
 }
 
 namespace jxph {
 int launch_loglike_prep_f64(const double* y, const double* sigma, int64_t ss, int64_t n, double* winv,
                             double* scalars, cudaStream_t st) {
-  k_loglike_prep<double><<<1, 1024, 0, st>>>(y, sigma, ss, n, winv, scalars);
+  k_loglike_prep<double><<<LL_NCTA, 256, 0, st>>>(y, sigma, ss, n, winv, scalars);
   return check_launch("loglike prep");
 }
 int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int64_t n, float* winv,
                             double* scalars, cudaStream_t st) {
-  k_loglike_prep<float><<<1, 1024, 0, st>>>(y, sigma, ss, n, winv, scalars);
+  k_loglike_prep<float><<<LL_NCTA, 256, 0, st>>>(y, sigma, ss, n, winv, scalars);
   return check_launch("loglike prep");
 }
 }  // namespace jxph
@@ -494,9 +500,14 @@ __global__ void k_loglike_final(const double* __restrict__ partial, int n_tiles,
                                 const double* __restrict__ scalars, T* __restrict__ loglike) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sets) return;
+  double chi0 = 0.0, cst = 0.0;
+  for (int k = 0; k < LL_NCTA; ++k) {
+    chi0 += scalars[LL_SCAL0 + 2 * k];
+    cst += scalars[LL_SCAL0 + 2 * k + 1];
+  }
   double acc = 0.0;
-  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)s * n_tiles + k];
-  loglike[s] = T(-0.5 * (scalars[0] + acc) + scalars[1]);
+  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)k * n_sets + s];  // coalesced over s
+  loglike[s] = T(-0.5 * (chi0 + acc) + cst);
 }
 
 template <typename T>
@@ -510,7 +521,7 @@ struct SysArgs {
   T* flux_sum;
   const T* y;
   const T* winv;
-  double* partial;  // [n_sets][n_tiles]
+  double* partial;  // [n_wtiles][n_sets]
   unsigned long long* counters;  // [2]: Kepler solves, limb-darkening evaluations executed
   Stencil st;
   GLTable tab;
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
 
   if (LOGLIKE) {
     for (int sl = lane; sl < nsl; sl += 32)
-      a.partial[(size_t)(set_base + sl) * a.n_wtiles + wtile] = sacc[sl];
+      a.partial[(size_t)wtile * a.n_sets + (set_base + sl)] = sacc[sl];
   }
   // executed-work counters (two atomics per warp)
   n_kep = __reduce_add_sync(0xffffffffu, n_kep);
@@ -959,7 +970,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     if (rc != JXP_OK) return rc;
   }
   if (loglike) {
-    k_loglike_prep<T><<<1, 1024, 0, st>>>(y, sigma, sigma_stride, n_times, d_winv, d_scalars);
+    k_loglike_prep<T><<<LL_NCTA, 256, 0, st>>>(y, sigma, sigma_stride, n_times, d_winv, d_scalars);
     rc = check_launch("jxp_system_light_curve(loglike prep)");
     if (rc != JXP_OK) return rc;
   }

@@ -52,7 +52,7 @@ TrLayout tr_layout(int n_sets, int64_t n_times) {
   L.off_winv = off;
   off = align_up(off + sizeof(double) * (size_t)n_times, 256);
   L.off_scalars = off;
-  off = align_up(off + 8 * sizeof(double), 256);
+  off = align_up(off + 256 * sizeof(double), 256);
   L.off_partial = off;
   off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles * (1 + JXP_NTHETA), 256);
   L.total = off;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
   if (LOGLIKE) {
     for (int i = lane; i < nsl * NQ; i += 32) {
       const int sl = i / NQ, q = i - sl * NQ;
-      a.partial[((size_t)(set_base + sl) * a.n_wtiles + wtile) * NQ + q] = sacc[i];
+      a.partial[((size_t)wtile * a.n_sets + (set_base + sl)) * NQ + q] = sacc[i];
     }
   }
 }
@@ -468,13 +468,21 @@ template <typename T>
 __global__ void k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
                            const double* __restrict__ scalars, T* __restrict__ loglike,
                            T* __restrict__ dloglike) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_sets * (1 + JXP_NTHETA)) return;
-  const int s = i / (1 + JXP_NTHETA), q = i % (1 + JXP_NTHETA);
+  constexpr int NQ = 1 + JXP_NTHETA;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = set * NQ + q
+  if (i >= n_sets * NQ) return;
+  const int s = i / NQ, q = i % NQ;
   double acc = 0.0;
-  for (int k = 0; k < n_tiles; ++k) acc += partial[((size_t)s * n_tiles + k) * (1 + JXP_NTHETA) + q];
+  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)k * n_sets * NQ + i];  // coalesced over i
   if (q == 0) {
-    if (loglike) loglike[s] = T(-0.5 * (scalars[0] + acc) + scalars[1]);
+    if (loglike) {
+      double chi0 = 0.0, cst = 0.0;
+      for (int k = 0; k < LL_NCTA_H; ++k) {
+        chi0 += scalars[LL_SCAL0_H + 2 * k];
+        cst += scalars[LL_SCAL0_H + 2 * k + 1];
+      }
+      loglike[s] = T(-0.5 * (chi0 + acc) + cst);
+    }
   } else if (dloglike) {
     dloglike[(size_t)s * JXP_NTHETA + (q - 1)] = T(acc);
   }
