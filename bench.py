@@ -46,6 +46,27 @@ N_TIMES = 100_000
 METRIC = "light-curve points/s (Keplerian orbit + quadratic limb darkening + Gaussian log-likelihood, fp64)"
 
 
+_STDOUT_FD = None
+
+
+def capture_stdout():
+    """Libraries (NCCL banners, torchrun notices) may print to stdout; the contract is ONE JSON
+    line there.  Route fd 1 to stderr for the run and keep the real stdout for emit()."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def workload_config(n_gpus, extra=None):
     cfg = {
         "workload": f"C3: {N_SETS} parameter sets x {N_TIMES} times (2-min cadence), 1 planet, quadratic LD, "
@@ -78,6 +99,7 @@ def cpu_points_per_s(bodies, u, t, y, sigma, budget_s=12.0):
     from oracle import ref_c
 
     ref_c.build()
+    ref_c.use_all_cores()
     n_try = 2
     t0 = time.perf_counter()
     ref_c.system(bodies[:n_try], u[:n_try], t, y=y, sigma=sigma, want_flux=False)
@@ -100,7 +122,7 @@ def run_reference(args, rank, world):
     from oracle import ref_c
 
     ref_c.build()
-    threads = ref_c.max_threads()
+    threads = ref_c.use_all_cores()
     # size one step to ~2 s of CPU work
     n_try = max(2, threads)
     t0 = time.perf_counter()
@@ -129,7 +151,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -431,7 +453,7 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches_per_step": ["k_sys_prep", "k_loglike_prep", "k_system", "k_loglike_final"],
         "clocks": clocks, "secondary": secondary,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -514,6 +536,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

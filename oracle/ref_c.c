@@ -21,6 +21,14 @@
 #define PI 3.14159265358979323846
 #define EPS 2.220446049250313e-16
 
+void refc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int refc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -28,6 +28,7 @@ def load():
         lib = C.CDLL(LIB)
         dp = C.POINTER(C.c_double)
         lib.refc_max_threads.restype = C.c_int
+        lib.refc_set_threads.argtypes = [C.c_int]
         lib.refc_kepler.argtypes = [dp, dp, C.c_int64, dp, dp]
         lib.refc_ld_quad.argtypes = [C.c_double, C.c_double, dp, dp, C.c_int64, dp]
         lib.refc_system.argtypes = [dp, C.c_int32, C.c_int32, dp, C.c_int64, dp, C.c_int64, dp, dp,
@@ -42,6 +43,17 @@ def _p(a):
 
 def max_threads() -> int:
     return load().refc_max_threads()
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (launchers such as torchrun export
+    OMP_NUM_THREADS=1, which would silently make the CPU baseline single-threaded)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().refc_set_threads(n)
+    return max_threads()
 
 
 def kepler(M, ecc):
