@@ -386,9 +386,16 @@ def run_ours(args, rank, local_rank, world):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_system"]
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "fp64", "kernel": "k_system<double,10,true>", "achieved": achieved, "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+        "bound": "fp64", "kernel": "k_system<double,11,true,false>", "achieved": achieved, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
+        "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (FP64-bound kernel: HBM is idle)",
         "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
         "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
         "executed": {"kepler_solves": n_kep, "ld_evaluations": n_ld, "points": n_sets * n_times,

@@ -495,19 +495,31 @@ int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int6
 }
 }  // namespace jxph
 
+// loglike[s] = -(chi0 + sum_tiles partial[tile][s]) / 2 + const.  Block = 32 sets x 8 tile
+// slices: slice j adds tiles j, j + 8, ... in order, the 8 slice sums are then added in order
+// (fixed summation order -> deterministic); loads are coalesced over sets.
 template <typename T>
-__global__ void k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
-                                const double* __restrict__ scalars, T* __restrict__ loglike) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_sets) return;
-  double chi0 = 0.0, cst = 0.0;
-  for (int k = 0; k < LL_NCTA; ++k) {
-    chi0 += scalars[LL_SCAL0 + 2 * k];
-    cst += scalars[LL_SCAL0 + 2 * k + 1];
-  }
+__global__ void __launch_bounds__(256)
+k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
+                const double* __restrict__ scalars, T* __restrict__ loglike) {
+  __shared__ double sh[8][33];
+  const int ls = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int s = blockIdx.x * 32 + ls;
   double acc = 0.0;
-  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)k * n_sets + s];  // coalesced over s
-  loglike[s] = T(-0.5 * (chi0 + acc) + cst);
+  if (s < n_sets)
+    for (int k = slice; k < n_tiles; k += 8) acc += partial[(size_t)k * n_sets + s];
+  sh[slice][ls] = acc;
+  __syncthreads();
+  if (slice == 0 && s < n_sets) {
+    double chi0 = 0.0, cst = 0.0;
+    for (int k = 0; k < LL_NCTA; ++k) {
+      chi0 += scalars[LL_SCAL0 + 2 * k];
+      cst += scalars[LL_SCAL0 + 2 * k + 1];
+    }
+    double tot = 0.0;
+    for (int j = 0; j < 8; ++j) tot += sh[j][ls];
+    loglike[s] = T(-0.5 * (chi0 + tot) + cst);
+  }
 }
 
 template <typename T>
@@ -1044,7 +1056,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   if (rc != JXP_OK) return rc;
 
   if (loglike) {
-    k_loglike_final<T><<<(n_sets + 127) / 128, 128, 0, st>>>(d_partial, (int)n_wtiles, n_sets,
+    k_loglike_final<T><<<(n_sets + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets,
                                                             d_scalars, loglike);
     rc = check_launch("jxp_system_light_curve(loglike final)");
   }

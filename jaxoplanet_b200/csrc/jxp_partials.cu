@@ -464,16 +464,25 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
 }
 
 // loglike[s] = -chi2/2 + const, dloglike[s][k] = sum of the per-tile gradient partials
+// Block = 32 consecutive (set, q) entries x 8 tile slices; fixed summation order.
 template <typename T>
-__global__ void k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
-                           const double* __restrict__ scalars, T* __restrict__ loglike,
-                           T* __restrict__ dloglike) {
+__global__ void __launch_bounds__(256)
+k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
+           const double* __restrict__ scalars, T* __restrict__ loglike, T* __restrict__ dloglike) {
   constexpr int NQ = 1 + JXP_NTHETA;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = set * NQ + q
-  if (i >= n_sets * NQ) return;
-  const int s = i / NQ, q = i % NQ;
+  __shared__ double sh[8][33];
+  const int li = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + li;  // i = set * NQ + q
+  const int n = n_sets * NQ;
   double acc = 0.0;
-  for (int k = 0; k < n_tiles; ++k) acc += partial[(size_t)k * n_sets * NQ + i];  // coalesced over i
+  if (i < n)
+    for (int k = slice; k < n_tiles; k += 8) acc += partial[(size_t)k * n + i];  // coalesced over i
+  sh[slice][li] = acc;
+  __syncthreads();
+  if (slice != 0 || i >= n) return;
+  double tot = 0.0;
+  for (int j = 0; j < 8; ++j) tot += sh[j][li];
+  const int s = i / NQ, q = i % NQ;
   if (q == 0) {
     if (loglike) {
       double chi0 = 0.0, cst = 0.0;
@@ -481,10 +490,10 @@ __global__ void k_tr_final(const double* __restrict__ partial, int n_tiles, int 
         chi0 += scalars[LL_SCAL0_H + 2 * k];
         cst += scalars[LL_SCAL0_H + 2 * k + 1];
       }
-      loglike[s] = T(-0.5 * (chi0 + acc) + cst);
+      loglike[s] = T(-0.5 * (chi0 + tot) + cst);
     }
   } else if (dloglike) {
-    dloglike[(size_t)s * JXP_NTHETA + (q - 1)] = T(acc);
+    dloglike[(size_t)s * JXP_NTHETA + (q - 1)] = T(tot);
   }
 }
 
@@ -604,7 +613,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   if (rc != JXP_OK) return rc;
   if (want_ll) {
     const int n = n_sets * (1 + JXP_NTHETA);
-    k_tr_final<T><<<(n + 127) / 128, 128, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
+    k_tr_final<T><<<(n + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
                                                   dloglike);
     rc = check_launch("jxp_transit_partials(final)");
   }
