@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   unsigned visit = 0, cmask = 0;
   while (true) {
     bool done = false;
-    while (qn <= SYS_QCAP - 32 * K) {
+    while (qn <= SYS_QCAP - 32 * K) {  // room for one more set (<= 32 K hits)
       if (!visit) {
         if (c0 >= nsl) {
           done = true;
@@ -816,9 +816,12 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
     }
 
     // ---- stage C: drain the queue, 32 in-window samples at a time ---------------------------
+    // Only FULL groups of 32 are drained while more samples may still arrive; the remainder
+    // (< 32 items) stays at the front of the queue, so partial warps run once per warp tile.
     __syncwarp();
+    const int q_end = done ? qn : (qn & ~31);
 #pragma unroll 1
-    for (int q0 = 0; q0 < qn; q0 += 32) {
+    for (int q0 = 0; q0 < q_end; q0 += 32) {
       const bool have = q0 + lane < qn;
       const unsigned item = have ? sq[q0 + lane] : 0u;
       const int sl = (int)(item >> 7);
@@ -896,7 +899,13 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
         __syncwarp();
       }
     }
-    qn = 0;
+    {
+      const int rem = qn - q_end;  // 0 when done
+      const unsigned short keep = (lane < rem) ? sq[q_end + lane] : (unsigned short)0;
+      __syncwarp();
+      if (lane < rem) sq[lane] = keep;
+      qn = rem;
+    }
     __syncwarp();
     if (done) break;
   }
