@@ -632,3 +632,109 @@ def test_window_is_conservative_on_adversarial_orbits():
     a = _run_fused(FusedSpec(sys_, u), tu)
     b = _run_fused(FusedSpec(sys_, u, flags=_lib.JXP_FLAG_NO_WINDOW), tu)
     assert torch.equal(a, b)
+
+
+def test_no_out_of_bounds_writes_ragged_sizes():
+    # compute-sanitizer is closed on this pool: guard regions around every output buffer instead.
+    # Ragged sizes: n_sets not a multiple of the CTA group, n_times not a multiple of the warp tile.
+    import torch
+
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    dev = A.device()
+    rng = np.random.default_rng(9)
+    n_sets, n_times, nb = 67, 1001, 2
+    p, u = W.transit_sets(n_sets, seed=9)
+    with jxp.batched():
+        sys_ = System(Central()).add_body(**p).add_body(period=p["period"] * 2.3, radius=0.04, impact_param=0.2)
+    bodies, _, _ = pack_bodies(sys_)
+    bodies = bodies.to(dev).contiguous()
+    ud = torch.as_tensor(u).to(dev).contiguous()
+    t = torch.as_tensor(np.arange(n_times) * (10.0 / 1440.0)).to(dev)
+    y = torch.as_tensor(1 + 1e-3 * rng.normal(size=n_times)).to(dev)
+    sig = torch.full((1,), 1e-3, dtype=torch.float64, device=dev)
+    G, S = 4096, 777.25
+
+    def guarded(n):
+        buf = torch.full((n + 2 * G,), S, dtype=torch.float64, device=dev)
+        return buf, buf[G:G + n]
+
+    fbuf, flux = guarded(n_sets * n_times * nb)
+    sbuf, fsum = guarded(n_sets * n_times)
+    lbuf, ll = guarded(n_sets)
+    wsb = int(_lib.load().jxp_system_workspace_bytes(n_sets, nb, n_times))
+    wbuf = torch.zeros(wsb + 2 * G, dtype=torch.uint8, device=dev)
+    wbuf[:G] = 171
+    wbuf[G + wsb:] = 171
+    ws = wbuf[G:G + wsb]
+    assert ws.data_ptr() % 256 == 0
+    for flags in (0, _lib.JXP_FLAG_NO_WINDOW):
+        for expo in ((0.0, 0, 0), (0.02, 1, 5)):
+            _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, nb, ud.data_ptr(), 2, 2, t.data_ptr(),
+                      n_times, expo[0], expo[1], expo[2], 10, flags, flux.data_ptr(), fsum.data_ptr(), y.data_ptr(),
+                      sig.data_ptr(), 0, ll.data_ptr(), ws.data_ptr(), wsb, A.stream_ptr())
+            torch.cuda.synchronize()
+            for buf, n in ((fbuf, flux.numel()), (sbuf, fsum.numel()), (lbuf, ll.numel())):
+                assert torch.all(buf[:G] == S) and torch.all(buf[G + n:] == S)
+                assert not torch.any(buf[G:G + n] == S)  # every element written
+            assert torch.all(wbuf[:G] == 171) and torch.all(wbuf[G + wsb:] == 171)
+            np.testing.assert_allclose(fsum.reshape(n_sets, n_times).cpu().numpy(),
+                                       flux.reshape(n_sets, n_times, nb).sum(-1).cpu().numpy(),
+                                       rtol=0, atol=1e-15)
+    # K5
+    theta = torch.as_tensor(W.theta_from(p, u)).to(dev).contiguous()
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+    fbuf, flux = guarded(n_sets * n_times)
+    pbuf, part = guarded(n_sets * 8 * n_times)
+    lbuf, ll = guarded(n_sets)
+    dbuf, dll = guarded(n_sets * 8)
+    wsb = int(_lib.load().jxp_transit_workspace_bytes(n_sets, n_times))
+    wbuf = torch.zeros(wsb + 2 * G, dtype=torch.uint8, device=dev)
+    wbuf[:G] = 171
+    wbuf[G + wsb:] = 171
+    ws = wbuf[G:G + wsb]
+    for flags in (0, _lib.JXP_FLAG_NO_WINDOW):
+        _lib.call("jxp_transit_partials_f64", theta.data_ptr(), n_sets, star.data_ptr(), 0, t.data_ptr(), n_times,
+                  0.02, 0, 3, 10, flags, flux.data_ptr(), part.data_ptr(), y.data_ptr(), sig.data_ptr(), 0,
+                  ll.data_ptr(), dll.data_ptr(), ws.data_ptr(), wsb, A.stream_ptr())
+        torch.cuda.synchronize()
+        for buf, n in ((fbuf, flux.numel()), (pbuf, part.numel()), (lbuf, ll.numel()), (dbuf, dll.numel())):
+            assert torch.all(buf[:G] == S) and torch.all(buf[G + n:] == S)
+            assert not torch.any(buf[G:G + n] == S)
+        assert torch.all(wbuf[:G] == 171) and torch.all(wbuf[G + wsb:] == 171)
+
+
+def test_multi_body_loglike_with_overlapping_transits():
+    # two planets forced to transit simultaneously: the likelihood must use the SUMMED model
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    rng = np.random.default_rng(12)
+    n_sets, n_t = 5, 6000
+    P1 = rng.uniform(2, 3, n_sets)
+    b1 = dict(period=P1, time_transit=np.full(n_sets, 1.0), impact_param=rng.uniform(0, 0.5, n_sets),
+              radius=rng.uniform(0.05, 0.1, n_sets), eccentricity=rng.uniform(0, 0.2, n_sets),
+              omega_peri=rng.uniform(-3, 3, n_sets))
+    b2 = dict(period=P1 * 1.5, time_transit=np.full(n_sets, 1.01), impact_param=rng.uniform(0, 0.5, n_sets),
+              radius=rng.uniform(0.05, 0.1, n_sets))
+    u = np.array([0.3, 0.2])
+    t = np.arange(n_t) * (2.0 / 1440.0)
+    y = 1 + 3e-4 * rng.normal(size=n_t)
+    sigma = 3e-4
+    with jxp.batched():
+        ll = log_likelihood(System(Central()).add_body(**b1).add_body(**b2), u, exposure_time=0.005,
+                            num_samples=3)(t, y, sigma)
+    for s in range(n_sets):
+        bodies = [ref.orbital_body(**{k: v[s] for k, v in b1.items()}),
+                  ref.orbital_body(**{k: v[s] for k, v in b2.items()})]
+        m = 1 + ref.integrate(lambda tt: ref.system_light_curve(bodies, u, tt), 0.005, 0, 3)(t).sum(-1)
+        both = (ref.system_light_curve(bodies, u, t) != 0).all(-1).sum()
+        assert both > 20  # the transits really overlap
+        want = ref.gaussian_loglike(m, y, np.full(n_t, sigma))
+        assert abs(ll[s] - want) <= 1e-12 * abs(want)
