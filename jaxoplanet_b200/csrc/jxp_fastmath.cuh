@@ -60,6 +60,26 @@ __device__ __forceinline__ double fsqrt(double x) {
   return (x > 2.3e-308) ? g : ((x >= 0.0) ? 0.0 : nan(""));
 }
 
+// sqrt(x) for x known to be positive and normal (no zero / negative handling)
+__device__ __forceinline__ double fsqrt_pos(double x) {
+  double y = rsqrt_seed(x);
+  double g = x * y;
+  double h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  double p = fma(r, 1.5, 1.0) * r;
+  g = fma(g, p, g);
+  h = fma(h, p, h);
+  double d = fma(-g, g, x);
+  return fma(d, h, g);
+}
+
+__device__ __constant__ double c_sin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                           -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                           -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__device__ __constant__ double c_cosk[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03,
+                                            2.48015872894767294178e-05, -2.75573143513906633035e-07,
+                                            2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
 // sin and cos for |x| <~ 1e4: two-term Cody-Waite reduction by pi/2 and the classic
 // minimax kernels on [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin.c / k_cos.c, public domain).
 __device__ __forceinline__ void fsincos(double x, double* sp, double* cp) {
@@ -73,19 +93,13 @@ __device__ __forceinline__ void fsincos(double x, double* sp, double* cp) {
   double r = fma(-qd, pio2_hi, x);
   r = fma(-qd, pio2_lo, r);
   const double z = r * r;
-  double ps = 1.58969099521155010221e-10;
-  ps = fma(ps, z, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double ps = c_sin[5];
+#pragma unroll
+  for (int k = 4; k >= 0; --k) ps = fma(ps, z, c_sin[k]);
   const double s = fma(r * z, ps, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = fma(pc, z, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double pc = c_cosk[5];
+#pragma unroll
+  for (int k = 4; k >= 0; --k) pc = fma(pc, z, c_cosk[k]);
   const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
   const bool swap = q & 1;
   double so = swap ? c : s;
@@ -102,28 +116,48 @@ __device__ __forceinline__ double fcos(double x) {
   return c;
 }
 
+// Taylor coefficients (-1)^k / (2k)! of cos, in the constant bank: a DFMA takes them as a direct
+// operand, whereas 64-bit immediates cost two extra moves each under register pressure.
+__device__ __constant__ double c_cos0pi[15] = {
+    1.0,
+    -0.5,
+    0.041666666666666664,
+    -0.001388888888888889,
+    2.48015873015873e-05,
+    -2.755731922398589e-07,
+    2.08767569878681e-09,
+    -1.1470745597729725e-11,
+    4.779477332387385e-14,
+    -1.5619206968586225e-16,
+    4.110317623312165e-19,
+    -8.896791392450574e-22,
+    1.6117375710961184e-24,
+    -2.4795962632247976e-27,
+    3.279889237069838e-30};
+
 // cos(x) for 0 <= x <= pi (the quadrature node angles): even Taylor polynomial in x^2 through
 // x^28 (remainder < 3e-18 at pi), no range reduction and no selects; absolute error ~1e-15
 // at x ~ pi from the alternating partial sums, far below what the flux needs (1e-12).
 __device__ __forceinline__ double fcos_0pi(double x) {
   const double z = x * x;
-  double p = 3.279889237069838e-30;
-  p = fma(p, z, -2.4795962632247976e-27);
-  p = fma(p, z, 1.6117375710961184e-24);
-  p = fma(p, z, -8.896791392450574e-22);
-  p = fma(p, z, 4.110317623312165e-19);
-  p = fma(p, z, -1.5619206968586225e-16);
-  p = fma(p, z, 4.779477332387385e-14);
-  p = fma(p, z, -1.1470745597729725e-11);
-  p = fma(p, z, 2.08767569878681e-09);
-  p = fma(p, z, -2.755731922398589e-07);
-  p = fma(p, z, 2.48015873015873e-05);
-  p = fma(p, z, -0.001388888888888889);
-  p = fma(p, z, 0.041666666666666664);
-  p = fma(p, z, -0.5);
-  p = fma(p, z, 1.0);
+  double p = c_cos0pi[14];
+#pragma unroll
+  for (int k = 13; k >= 0; --k) p = fma(p, z, c_cos0pi[k]);  // coefficients as constant-bank operands
   return p;
 }
+
+__device__ __constant__ double c_atan[11] = {
+    -0.33333333333333120084,
+    0.19999999999940620353,
+    -0.14285714279223825339,
+    0.11111110743605271685,
+    -0.090908967710695170919,
+    0.076920446486449617822,
+    -0.066629439708755771522,
+    0.058468205483397593716,
+    -0.050348390947738729638,
+    0.037958485922477833544,
+    -0.01779789458017953007};
 
 // atan2(y, x), any signs, |result error| ~ 1e-16.  One division: t = min/max of (|y|, |x|) is
 // reduced to |t'| <= tan(pi/8) with t' = (min - max) / (min + max) and an offset of pi/4, then
@@ -138,17 +172,9 @@ __device__ __forceinline__ double fatan2(double y, double x) {
   double t = fdiv(num, den);
   t = (den == 0.0) ? 0.0 : t;  // atan2(0, 0) = 0
   const double s = t * t;
-  double p = -0.01779789458017953007;
-  p = fma(p, s, 0.037958485922477833544);
-  p = fma(p, s, -0.050348390947738729638);
-  p = fma(p, s, 0.058468205483397593716);
-  p = fma(p, s, -0.066629439708755771522);
-  p = fma(p, s, 0.076920446486449617822);
-  p = fma(p, s, -0.090908967710695170919);
-  p = fma(p, s, 0.11111110743605271685);
-  p = fma(p, s, -0.14285714279223825339);
-  p = fma(p, s, 0.19999999999940620353);
-  p = fma(p, s, -0.33333333333333120084);
+  double p = c_atan[10];
+#pragma unroll
+  for (int k = 9; k >= 0; --k) p = fma(p, s, c_atan[k]);
   double a = fma(t * s, p, t);
   a = big ? a + 0.78539816339744830962 : a;
   a = swap ? 1.57079632679489661923 - a : a;

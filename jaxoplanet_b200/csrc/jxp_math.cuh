@@ -286,14 +286,16 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
       c = S(B(GL<ORDER>::cpi(i)));
     else
       c = jcos_node(rng * xi + kappa0 * B(0.5));
-    const S omz2 = jmax(S(B(0)), r2pb2 - two_br * c);
-    const S z2 = B(1) - omz2;
-    // limb_dark.py:164-172: the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0
-    // where z^2 < 10 eps (z2 := 1 there) or 1 - z^2 < 10 eps.  (1 - z^3) / (1 - z^2) is evaluated
-    // as 1 + z^2 / (1 + z): the same function without the cancellation in 1 - z^3.
-    const bool dead = (val(z2) < eps10) || (val(omz2) < eps10);
-    const S z2s = jsel(dead, S(B(1)), z2);
-    const S z = jzsqrt(z2s);
+    // limb_dark.py:160-172.  max(0, .) only matters for the guard below (a negative value is
+    // < 10 eps and the term is forced to 0 either way), so the primal path skips it; the dual
+    // path keeps it for the derivative.  z^2 < 10 eps  <=>  1 - z^2 > 1 - 10 eps exactly.
+    const S omz2 = jclamp0_lazy(r2pb2 - two_br * c);
+    const bool dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
+    // the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0 where z^2 < 10 eps or
+    // 1 - z^2 < 10 eps.  (1 - z^3) / (1 - z^2) is evaluated as 1 + z^2 / (1 + z): the same
+    // function without the cancellation in 1 - z^3.
+    const S z2s = jsel(dead, S(B(1)), B(1) - omz2);
+    const S z = jsqrt_pos(z2s);
     S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
     res = jsel(dead, S(B(0)), res);
     acc = acc + res * wi;

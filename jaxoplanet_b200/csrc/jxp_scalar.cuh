@@ -46,6 +46,11 @@ __device__ __forceinline__ double jcbrt(double x) { return cbrt(x); }
 // cube root to float accuracy (the Kepler starter only needs ~1e-6)
 __device__ __forceinline__ double jcbrt_lo(double x) { return (double)cbrtf((float)x); }
 __device__ __forceinline__ float jcbrt_lo(float x) { return cbrtf(x); }
+// sqrt of a value known to be positive and normal; clamp-at-zero that the primal path may skip
+__device__ __forceinline__ double jsqrt_pos(double x) { return fsqrt_pos(x); }
+__device__ __forceinline__ float jsqrt_pos(float x) { return sqrtf(x); }
+__device__ __forceinline__ double jclamp0_lazy(double x) { return x; }
+__device__ __forceinline__ float jclamp0_lazy(float x) { return x; }
 // cos of a quadrature node angle in [0, pi]
 __device__ __forceinline__ double jcos_node(double x) { return fcos_0pi(x); }
 __device__ __forceinline__ float jcos_node(float x) { return cosf(x); }
@@ -242,6 +247,10 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos(const JXP_D& x) {
   return r;
 }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos_node(const JXP_D& x) { return jcos(x); }
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jsqrt_pos(const JXP_D& x) { return jzsqrt(x); }
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jclamp0_lazy(const JXP_D& x) {
+  return jmax(JXP_D(T(0)), x);
+}
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jsin(const JXP_D& x) {
   JXP_D r;
   T s, c;
