@@ -139,11 +139,16 @@ __device__ __constant__ double c_cos0pi[15] = {
 // x^28 (remainder < 3e-18 at pi), no range reduction and no selects; absolute error ~1e-15
 // at x ~ pi from the alternating partial sums, far below what the flux needs (1e-12).
 __device__ __forceinline__ double fcos_0pi(double x) {
+  // even/odd split in z = x^2: two independent Horner chains of depth 7 instead of one of 14
   const double z = x * x;
-  double p = c_cos0pi[14];
+  const double z2 = z * z;
+  double pa = c_cos0pi[14];
+  double pb = c_cos0pi[13];
 #pragma unroll
-  for (int k = 13; k >= 0; --k) p = fma(p, z, c_cos0pi[k]);  // coefficients as constant-bank operands
-  return p;
+  for (int k = 12; k >= 0; k -= 2) pa = fma(pa, z2, c_cos0pi[k]);
+#pragma unroll
+  for (int k = 11; k >= 1; k -= 2) pb = fma(pb, z2, c_cos0pi[k]);
+  return fma(pb, z, pa);
 }
 
 __device__ __constant__ double c_atan[11] = {
