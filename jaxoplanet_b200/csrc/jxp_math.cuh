@@ -26,6 +26,40 @@ __device__ __forceinline__ T mod_two_pi(T M) {
   return r;
 }
 
+// Markley starter E0(M, e) on M in [0, pi], kepler.py:82-92, with the two divisions merged.
+// The single correction that follows is 5th order, so the starter only has to be good to
+// ~1e-4: the double-precision kernels evaluate it in FLOAT (FP32 pipe, otherwise idle) for
+// 1 - e > 1e-5 -- measured final |E - E_true| identical to the all-double path down to
+// 1 - e = 1e-6 (DESIGN.md "numerics") -- and in double beyond that.
+template <typename T>
+__device__ __forceinline__ T kepler_starter_t(T M, T e, T ome, T inv_ope) {
+  const T pi = Num<T>::pi;
+  const T k_a = T(3.0 * 3.141592653589793238462643383279502884 /
+                  (3.141592653589793238462643383279502884 -
+                   6.0 / 3.141592653589793238462643383279502884));
+  const T k_b = T(1.6 / (3.141592653589793238462643383279502884 -
+                         6.0 / 3.141592653589793238462643383279502884));
+  const T M2 = M * M;
+  const T alpha = jfma(k_b * (pi - M), inv_ope, k_a);
+  const T d = jfma(alpha, e, T(3) * ome);
+  const T alphad = alpha * d;
+  const T r = jfma(T(3) * alphad, d - ome, M2) * M;
+  const T q = jfma(T(2) * alphad, ome, -M2);
+  const T q2 = q * q;
+  T w = jcbrt_lo(jabs(r) + jsqrt(jfma(q2, q, r * r)));
+  w = w * w;
+  const T W = jfma(w, w + q, q2);
+  return jdiv(jfma(T(2) * r, w, M * W), W * d);
+}
+__device__ __forceinline__ float kepler_starter(float M, float e, float ome, float inv_ope) {
+  return kepler_starter_t<float>(M, e, ome, inv_ope);
+}
+__device__ __forceinline__ double kepler_starter(double M, double e, double ome, double inv_ope) {
+  if (ome > 1e-5)
+    return (double)kepler_starter_t<float>((float)M, (float)e, (float)ome, (float)inv_ope);
+  return kepler_starter_t<double>(M, e, ome, inv_ope);
+}
+
 // ------------------------------------------------------------------------------------
 // Kepler solve for one (M, e):  src/jaxoplanet/core/kepler.py:28-56, 82-108.
 //   in : Mr in [0, 2pi) (already reduced), e, ome = 1 - e, ope = 1 + e,
@@ -51,22 +85,7 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
   const T M = high ? Num<T>::two_pi - Mr : Mr;
 
   // starter, kepler.py:82-92
-  const T k_a = T(3.0 * 3.141592653589793238462643383279502884 /
-                  (3.141592653589793238462643383279502884 -
-                   6.0 / 3.141592653589793238462643383279502884));
-  const T k_b = T(1.6 / (3.141592653589793238462643383279502884 -
-                         6.0 / 3.141592653589793238462643383279502884));
-  const T M2 = M * M;
-  const T alpha = jfma(k_b * (pi - M), inv_ope, k_a);
-  const T d = jfma(alpha, e, T(3) * ome);
-  const T alphad = alpha * d;
-  const T r = jfma(T(3) * alphad, d - ome, M2) * M;
-  const T q = jfma(T(2) * alphad, ome, -M2);
-  const T q2 = q * q;
-  T w = jcbrt_lo(jabs(r) + jsqrt(jfma(q2, q, r * r)));
-  w = w * w;
-  const T W = jfma(w, w + q, q2);
-  const T E0 = jdiv(jfma(T(2) * r, w, M * W), W * d);
+  const T E0 = kepler_starter(M, e, ome, inv_ope);
 
   // refine, kepler.py:95-108
   T hs, hc;
