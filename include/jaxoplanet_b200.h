@@ -98,8 +98,8 @@ int jxp_limb_dark_f32(const float* u, int32_t n_u, const float* b, int64_t b_str
  * bodies: [n_sets][n_bodies][JXP_BODY_NFIELDS] derived per-body constants, i.e. the
  *         fields OrbitalBody.__init__ computes (keplerian.py:262-340); ALWAYS double (a float
  *         period or epoch cannot place a transit to 1 ppm of flux).
- * u:      [n_sets or 1][n_u] limb-darkening coefficients (u_set_stride = n_u or 0), n_u <= 2,
- *         ALWAYS double.
+ * u:      [n_sets or 1][n_u] limb-darkening coefficients (u_set_stride = n_u or 0),
+ *         0 <= n_u <= JXP_MAX_LD_COEFFS (general polynomial law), ALWAYS double.
  * t:      [n_times] time stamps, ALWAYS double, shared by all sets.
  * exposure_time <= 0 or num_samples <= 0: no exposure integration.  exp_order in {0,1,2}.
  * Outputs (any may be NULL):

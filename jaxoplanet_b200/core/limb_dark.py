@@ -16,15 +16,22 @@ __all__ = ["light_curve"]
 
 
 def greens_normalised(u: torch.Tensor) -> torch.Tensor:
-    """g(u) / (pi (g0 + g1 / 1.5)) for len(u) <= 2; limb_dark.py:42-45, 87-99 (host, tiny)."""
+    """g(u) / (pi (g0 + g1 / 1.5)); limb_dark.py:42-45, 87-99 (host side, tiny, differentiable)."""
     n = u.shape[0]
     if n == 0:
         return torch.full((1,), 1.0 / math.pi, dtype=u.dtype, device=u.device)
-    if n == 1:
-        g = torch.stack([1 - u[0], u[0]])
-    else:
-        g2 = -0.25 * u[1]
-        g = torch.stack([(1 - u[0] - u[1]) + 2 * g2, u[0] + 2 * u[1], g2])
+    ue = torch.cat((-torch.ones(1, dtype=u.dtype, device=u.device), u))
+    size = n + 1
+    B = torch.tensor([[math.comb(i, j) for i in range(size)] for j in range(size)], dtype=u.dtype,
+                     device=u.device)
+    sign = torch.tensor([(-1.0) ** (j + 1) for j in range(size)], dtype=u.dtype, device=u.device)
+    p = sign * (B @ ue)
+    g = [torch.zeros((), dtype=u.dtype, device=u.device) for _ in range(size + 2)]
+    for k in range(size - 1, 1, -1):
+        g[k] = p[k] / (k + 2) + g[k + 2]
+    g[1] = p[1] + 3 * g[3]
+    g[0] = p[0] + 2 * g[2]
+    g = torch.stack(g[:-2])
     return g / (math.pi * (g[0] + g[1] / 1.5))
 
 
@@ -80,7 +87,7 @@ def light_curve(u, b, r, *, order: int = 10):
     """Compute the light curve for polynomial limb darkening (flux - 1).
 
     Args:
-        u: The coefficients of the polynomial limb darkening model (1-D, len <= 2 here)
+        u: The coefficients of the polynomial limb darkening model (1-D, len <= 8)
         b: The center-to-center distance between the occultor and the occulted body
         r: The radius ratio between the occultor and the occulted body
         order: The quadrature order of the 1D line integral

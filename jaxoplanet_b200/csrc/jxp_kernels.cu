@@ -195,12 +195,18 @@ struct LdArgs {
   GLTable tab;
 };
 
-template <typename T, int ORDER, bool GRAD>
+template <typename T, int ORDER, bool GRAD, bool HI>
 __global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArgs<T> a) {
-  T u1 = a.n_u >= 1 ? a.u[0] : T(0);
-  T u2 = a.n_u >= 2 ? a.u[1] : T(0);
-  T g0, g1, g2;
-  ld_greens<T>(a.n_u, u1, u2, g0, g1, g2);
+  T uu[JXP_MAX_LD_COEFFS], g[JXP_MAX_LD_COEFFS + 1];
+#pragma unroll
+  for (int k = 0; k < JXP_MAX_LD_COEFFS; ++k) uu[k] = (k < a.n_u) ? a.u[k] : T(0);
+#pragma unroll
+  for (int k = 0; k <= JXP_MAX_LD_COEFFS; ++k) g[k] = T(0);
+  if (HI) {
+    ld_greens_n<T>(a.n_u, uu, g);
+  } else {
+    ld_greens<T>(a.n_u, uu[0], uu[1], g[0], g[1], g[2]);
+  }
   const int lmax = a.n_u;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
@@ -208,9 +214,14 @@ __global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArg
     const T r = a.r[i * a.rs];
     if (GRAD) {
       typedef Dual<T, 2> D;
-      D s0, s1, s2;
-      ld_solution<D, ORDER>(D::seed(b, 0), D::seed(r, 1), lmax, &a.tab, s0, s1, s2);
-      D f = ld_combine(lmax, s0, s1, s2, D(g0), D(g1), D(g2));
+      D s0, s1, s2, shi[6];
+      ld_solution<D, ORDER, HI>(D::seed(b, 0), D::seed(r, 1), lmax, &a.tab, s0, s1, s2, shi);
+      D f = ld_combine(lmax < 2 ? lmax : 2, s0, s1, s2, D(g[0]), D(g[1]), D(g[2]));
+      if (HI) {
+#pragma unroll
+        for (int n = 3; n <= 8; ++n)
+          if (n <= lmax) f = f + shi[n - 3] * g[n];
+      }
       a.flux[i] = f.v;
       if (a.db) a.db[i] = f.d[0];
       if (a.dr) a.dr[i] = f.d[1];
@@ -218,11 +229,22 @@ __global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArg
         a.svec[i] = s0.v;
         if (lmax >= 1) a.svec[a.n + i] = s1.v;
         if (lmax >= 2) a.svec[2 * a.n + i] = s2.v;
+        if (HI) {
+#pragma unroll
+          for (int n = 3; n <= 8; ++n)
+            if (n <= lmax) a.svec[(int64_t)n * a.n + i] = shi[n - 3].v;
+        }
       }
     } else {
-      T s0, s1, s2;
-      ld_solution<T, ORDER>(b, r, lmax, &a.tab, s0, s1, s2);
-      a.flux[i] = ld_combine(lmax, s0, s1, s2, g0, g1, g2);
+      T s0, s1, s2, shi[6];
+      ld_solution<T, ORDER, HI>(b, r, lmax, &a.tab, s0, s1, s2, shi);
+      T f = ld_combine(lmax < 2 ? lmax : 2, s0, s1, s2, g[0], g[1], g[2]);
+      if (HI) {
+#pragma unroll
+        for (int n = 3; n <= 8; ++n)
+          if (n <= lmax) f = jfma(shi[n - 3], g[n], f);
+      }
+      a.flux[i] = f;
     }
   }
 }
@@ -234,11 +256,6 @@ static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, con
   if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_limb_dark: n = %lld < 0", (long long)n);
   if (n_u < 0 || n_u > JXP_MAX_LD_COEFFS)
     return fail(JXP_ERR_BAD_SHAPE, "jxp_limb_dark: n_u = %d out of range", n_u);
-  if (n_u > 2)
-    return fail(JXP_ERR_UNSUPPORTED,
-                "jxp_limb_dark: %d limb-darkening coefficients; only l_max <= 2 (uniform, linear, "
-                "quadratic) is implemented",
-                n_u);
   if (order < 1 || order > JXP_MAX_GL_ORDER)
     return fail(JXP_ERR_UNSUPPORTED, "jxp_limb_dark: order = %d outside 1..%d", order,
                 JXP_MAX_GL_ORDER);
@@ -267,16 +284,19 @@ static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, con
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   const bool grad = db || dr || svec;
-  if (order == 10) {
-    if (grad)
-      k_limb_dark<T, 10, true><<<(unsigned)blocks, threads, 0, st>>>(a);
-    else
-      k_limb_dark<T, 10, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  const bool hi = n_u > 2;
+  auto go = [&](auto kern) { kern<<<(unsigned)blocks, threads, 0, st>>>(a); };
+  if (hi) {
+    // general polynomial law: rolled node loop (order 10 from the constant bank, or the table)
+    if (order == 10) {
+      if (grad) go(k_limb_dark<T, 11, true, true>); else go(k_limb_dark<T, 11, false, true>);
+    } else {
+      if (grad) go(k_limb_dark<T, 0, true, true>); else go(k_limb_dark<T, 0, false, true>);
+    }
+  } else if (order == 10) {
+    if (grad) go(k_limb_dark<T, 10, true, false>); else go(k_limb_dark<T, 10, false, false>);
   } else {
-    if (grad)
-      k_limb_dark<T, 0, true><<<(unsigned)blocks, threads, 0, st>>>(a);
-    else
-      k_limb_dark<T, 0, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+    if (grad) go(k_limb_dark<T, 0, true, false>); else go(k_limb_dark<T, 0, false, false>);
   }
   return check_launch("jxp_limb_dark");
 }
@@ -427,12 +447,18 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
   if (i % n_bodies == 0) {
     const int s = i / n_bodies;
     const double* us = u + (size_t)s * u_stride;
-    double g0, g1, g2;
-    ld_greens<double>(n_u, n_u >= 1 ? us[0] : 0.0, n_u >= 2 ? us[1] : 0.0, g0, g1, g2);
+    double gg[JXP_MAX_LD_COEFFS + 1], uu[JXP_MAX_LD_COEFFS];
+    for (int k = 0; k <= JXP_MAX_LD_COEFFS; ++k) gg[k] = 0.0;
+    for (int k = 0; k < JXP_MAX_LD_COEFFS; ++k) uu[k] = (k < n_u) ? us[k] : 0.0;
+    if (n_u > 2)
+      ld_greens_n<double>(n_u, uu, gg);
+    else
+      ld_greens<double>(n_u, uu[0], uu[1], gg[0], gg[1], gg[2]);
     SetC<T> sc;
-    sc.g0 = T(g0);
-    sc.g1 = T(g1);
-    sc.g2 = T(g2);
+    sc.g0 = T(gg[0]);
+    sc.g1 = T(gg[1]);
+    sc.g2 = T(gg[2]);
+    for (int k = 0; k < 6; ++k) sc.ghi[k] = T(gg[3 + k]);
     sc.lmax = n_u;
     out_s[s] = sc;
   }
@@ -571,7 +597,7 @@ __device__ __forceinline__ bool phase_in_window(const BodyC<T>& c, double tm) {
   return (d >= c.wlo) & (d <= c.whi);
 }
 
-template <typename T, int ORDER, bool LOGLIKE, bool DENSE>
+template <typename T, int ORDER, bool LOGLIKE, bool DENSE, bool HI = false>
 __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = SYS_K;
@@ -868,7 +894,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
             cur_b = b;
           }
           ++n_kep;
-          const T v = eval_in_window<T, ORDER>(bodies[b], sc, &a.tab, tm0 + a.st.dt[j], n_ld);
+          const T v = eval_in_window<T, ORDER, HI>(bodies[b], sc, &a.tab, tm0 + a.st.dt[j], n_ld);
           accb = (nsub == 1) ? v : jfma(T(a.st.w[j]), v, accb);
         }
         if (a.flux)
@@ -942,9 +968,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   static_assert(sizeof(BodyC<T>) % 8 == 0 && sizeof(SetC<T>) % 8 == 0, "record sizes");
   if (n_sets < 0 || n_bodies < 0 || n_times < 0)
     return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: negative size");
-  if (n_u < 0 || n_u > 2)
-    return fail(JXP_ERR_UNSUPPORTED,
-                "jxp_system_light_curve: n_u = %d; only l_max <= 2 is implemented", n_u);
+  if (n_u < 0 || n_u > JXP_MAX_LD_COEFFS)
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: n_u = %d outside 0..%d", n_u,
+                JXP_MAX_LD_COEFFS);
   if (gl_order < 1 || gl_order > JXP_MAX_GL_ORDER)
     return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: order = %d outside 1..%d", gl_order,
                 JXP_MAX_GL_ORDER);
@@ -1053,8 +1079,14 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return check_launch("jxp_system_light_curve");
   };
-  const bool dense = (a.use_window == 0) && n_bodies == 1 && a.st.n == 1;
-  if (gl_order == 10) {
+  const bool dense = (a.use_window == 0) && n_bodies == 1 && a.st.n == 1 && n_u <= 2;
+  if (n_u > 2) {
+    // general polynomial limb darkening: queue kernel with the l >= 3 terms compiled in
+    if (gl_order == 10)
+      rc = loglike ? launch(k_system<T, 11, true, false, true>) : launch(k_system<T, 11, false, false, true>);
+    else
+      rc = loglike ? launch(k_system<T, 0, true, false, true>) : launch(k_system<T, 0, false, false, true>);
+  } else if (gl_order == 10) {
     if (dense)
       rc = loglike ? launch(k_system<T, 11, true, true>) : launch(k_system<T, 11, false, true>);
     else

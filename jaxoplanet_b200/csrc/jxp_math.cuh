@@ -225,9 +225,10 @@ __device__ __forceinline__ S kite_area(S a, S b, S c) {
 // Solution vector (s0, s1, s2) for l_max <= 2, limb_dark.py:50-84 with kappas :102-108,
 // s0s2 :111-137 and the l = 1 term of p_integral :140-173.
 //   lmax 0: only s0 is meaningful; lmax 1: s0, s1; lmax 2: all.
-template <typename S, int ORDER>
+//   HI: also the l = 3..lmax terms (limb_dark.py:149-153, 175-182) into shi[0..lmax-3].
+template <typename S, int ORDER, bool HI = false>
 __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* __restrict__ tab,
-                                            S& s0, S& s1, S& s2) {
+                                            S& s0, S& s1, S& s2, S* __restrict__ shi = nullptr) {
   using B = typename BaseOf<S>::type;
   const B pi = Num<B>::pi;
   const B eps10 = B(10) * Num<B>::eps;
@@ -259,6 +260,10 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     if (full_occ) s0 = S(B(0));
     s2 = S(B(0));
     s1 = -(kappa1 - pi) * B(2.0 / 3.0);
+    if (HI) {
+#pragma unroll
+      for (int n = 0; n < 6; ++n) shi[n] = S(B(0));
+    }
     return;
   }
 
@@ -294,6 +299,18 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
   const S r2pb2 = r2 + b2;
   const S two_r_3 = r * B(2.0 / 3.0);
   S acc = S(B(0));
+  // l >= 3 (limb_dark.py:149-153): k^2 with the "factor" hack for b r -> 0
+  S acch[6];
+  S k2 = S(B(0)), factor4 = S(B(1));
+  bool k2_cond = false;
+  if (HI) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) acch[n] = S(B(0));
+    factor4 = b * r * B(4);
+    k2_cond = val(factor4) < eps10;
+    factor4 = jsel(k2_cond, S(B(1)), factor4);
+    k2 = jmax(S(B(0)), jdiv(B(1) - r2 - b2 + two_br, factor4));
+  }
   const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
   const int order = GL<ORDER>::n(tab);
 #pragma unroll(ORDER == 10 ? 10 : 2)
@@ -318,6 +335,19 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
     res = jsel(dead, S(B(0)), res);
     acc = acc + res * wi;
+    if (HI) {
+      // sin^2((phi + rng) / 2) = (1 - cos(phi + kappa0 / 2)) / 2   (limb_dark.py:161-162)
+      const S sn2 = (B(1) - c) * B(0.5);
+      const S f0 = jmax(S(B(0)), jsel(k2_cond, B(1) - r2, factor4 * (k2 - sn2)));
+      const S common = two_r_3 * B(3) * (r - b + b * sn2 * B(2));  // 2 r (r - b + 2 b s^2)
+#pragma unroll
+      for (int n = 3; n <= 8; ++n)
+        if (n <= lmax) acch[n - 3] = acch[n - 3] + jpow_half(f0, n) * common * wi;
+    }
+  }
+  if (HI) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) shi[n] = -(rng * acch[n]);
   }
   const S P0 = rng * acc;
   s1 = -P0 - (kappa1 - pi) * B(2.0 / 3.0);
@@ -347,6 +377,36 @@ __device__ __forceinline__ void ld_greens(int n_u, S u1, S u2, S& g0, S& g1, S& 
   g0 = g0 / norm;
   g1 = g1 / norm;
   g2 = g2 / norm;
+}
+
+// Normalised Green's-basis coefficients for any n_u <= 8 (g[0..n_u]), limb_dark.py:42-45, 87-99.
+template <typename S>
+__device__ inline void ld_greens_n(int n_u, const S* __restrict__ u, S* __restrict__ g) {
+  using B = typename BaseOf<S>::type;
+  const B pi = Num<B>::pi;
+  if (n_u == 0) {
+    g[0] = S(B(1) / pi);
+    return;
+  }
+  const int size = n_u + 1;  // u_ext = (-1, u_0, ..)
+  S p[11], gg[13];
+  for (int n = 0; n < 13; ++n) gg[n] = S(B(0));
+  for (int n = 0; n < size; ++n) {
+    // arg_n = sum_i binom(i, n) u_ext[i]
+    S arg = S(B(0));
+    B binom = B(1);  // C(n, n)
+    for (int i = n; i < size; ++i) {
+      const S ui = (i == 0) ? S(B(-1)) : u[i - 1];
+      arg = arg + ui * binom;
+      binom = binom * B(i + 1) / B(i + 1 - n);  // C(i + 1, n)
+    }
+    p[n] = (n % 2 == 0) ? -arg : arg;  // (-1)^(n + 1)
+  }
+  for (int n = size - 1; n > 1; --n) gg[n] = p[n] / B(n + 2) + gg[n + 2];
+  gg[1] = p[1] + gg[3] * B(3);
+  gg[0] = p[0] + gg[2] * B(2);
+  const S norm = (gg[0] + gg[1] / B(1.5)) * pi;
+  for (int n = 0; n < size; ++n) g[n] = gg[n] / norm;
 }
 
 template <typename S>

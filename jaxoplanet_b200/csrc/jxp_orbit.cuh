@@ -32,6 +32,7 @@ struct BodyC {
 template <typename T>
 struct SetC {
   T g0, g1, g2;  // normalised Green's coefficients
+  T ghi[6];      // g_3 .. g_8 (general polynomial limb darkening, used by the HI kernels only)
   int lmax;
 };
 
@@ -157,7 +158,7 @@ __device__ __forceinline__ V pick(const V (&a)[K], int k) {
 
 // flux - 1 of one body at one time (0 when not in transit); the caller has already applied
 // the transit-window pre-test.
-template <typename T, int ORDER>
+template <typename T, int ORDER, bool HI = false>
 __device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc,
                                             const GLTable* __restrict__ tab, double tm,
                                             unsigned& n_ld) {
@@ -173,6 +174,15 @@ __device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc
   if (!(Z > T(0)) || (b >= c.onepr)) return T(0);  // limb_dark.py:58 mask, :60 no_occ
   ++n_ld;
   T s0, s1, s2;
+  if (HI) {
+    T shi[6];
+    ld_solution<T, ORDER, true>(b, c.rr, sc.lmax, tab, s0, s1, s2, shi);
+    T f = ld_combine(2, s0, s1, s2, sc.g0, sc.g1, sc.g2);
+#pragma unroll
+    for (int n = 3; n <= 8; ++n)
+      if (n <= sc.lmax) f = jfma(shi[n - 3], sc.ghi[n - 3], f);
+    return f;
+  }
   ld_solution<T, ORDER>(b, c.rr, sc.lmax, tab, s0, s1, s2);
   return ld_combine(sc.lmax, s0, s1, s2, sc.g0, sc.g1, sc.g2);
 }

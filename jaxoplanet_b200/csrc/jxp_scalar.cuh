@@ -51,6 +51,16 @@ __device__ __forceinline__ double jsqrt_pos(double x) { return fsqrt_pos(x); }
 __device__ __forceinline__ float jsqrt_pos(float x) { return sqrtf(x); }
 __device__ __forceinline__ double jclamp0_lazy(double x) { return x; }
 __device__ __forceinline__ float jclamp0_lazy(float x) { return x; }
+// x^(n/2) for x >= 0, 3 <= n <= 8 (general polynomial limb darkening)
+template <typename T>
+__device__ __forceinline__ T jpow_half_m1(T x, int n) {  // x^(n/2 - 1)
+  const T sq = jsqrt(x);
+  T p = (n & 1) ? sq : x;       // n = 3: x^0.5, n = 4: x
+  for (int k = (n & 1) ? 3 : 4; k < n; k += 2) p = p * x;
+  return p;
+}
+__device__ __forceinline__ double jpow_half(double x, int n) { return jpow_half_m1(x, n) * x; }
+__device__ __forceinline__ float jpow_half(float x, int n) { return jpow_half_m1(x, n) * x; }
 // cos of a quadrature node angle in [0, pi]
 __device__ __forceinline__ double jcos_node(double x) { return fcos_0pi(x); }
 __device__ __forceinline__ float jcos_node(float x) { return cosf(x); }
@@ -247,6 +257,15 @@ JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos(const JXP_D& x) {
   return r;
 }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jcos_node(const JXP_D& x) { return jcos(x); }
+// d x^(n/2) = (n/2) x^(n/2 - 1) dx   (jnp.power rule; finite at x = 0 for n >= 3)
+JXP_DUAL_TPL __device__ __forceinline__ JXP_D jpow_half(const JXP_D& x, int n) {
+  JXP_D r;
+  const T m1 = jpow_half_m1(x.v, n);
+  r.v = m1 * x.v;
+  const T f = T(0.5) * T(n) * m1;
+  JXP_FOR r.d[i] = f * x.d[i];
+  return r;
+}
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jsqrt_pos(const JXP_D& x) { return jzsqrt(x); }
 JXP_DUAL_TPL __device__ __forceinline__ JXP_D jclamp0_lazy(const JXP_D& x) {
   return jmax(JXP_D(T(0)), x);

@@ -48,8 +48,8 @@ def test_argument_validation_messages(lib):
     rc = lib.jxp_kepler_f64(None, 1, None, 1, -5, None, None, None, None, None, None)
     assert rc == -2
     assert lib.jxp_kepler_f64(None, 1, None, 1, 0, None, None, None, None, None, None) == 0
-    rc = lib.jxp_limb_dark_f64(None, 5, None, 1, None, 1, 10, 10, None, None, None, None, None)
-    assert rc == -3 and b"l_max" in lib.jxp_last_error()
+    rc = lib.jxp_limb_dark_f64(None, 9, None, 1, None, 1, 10, 10, None, None, None, None, None)
+    assert rc == -2 and b"n_u" in lib.jxp_last_error()
     rc = lib.jxp_limb_dark_f64(None, 2, None, 1, None, 1, 10, 0, None, None, None, None, None)
     assert rc == -3
     rc = lib.jxp_system_light_curve_f64(None, 4, 1, None, 2, 0, None, 100, 0.02, 3, 7, 10, 0,

@@ -738,3 +738,53 @@ def test_multi_body_loglike_with_overlapping_transits():
         assert both > 20  # the transits really overlap
         want = ref.gaussian_loglike(m, y, np.full(n_t, sigma))
         assert abs(ll[s] - want) <= 1e-12 * abs(want)
+
+
+# ----------------------------------------------------------------------------- general polynomial LD
+@pytest.mark.parametrize("r", [0.01, 0.1, 0.5, 1.1, 2.0])
+def test_polynomial_limb_dark_general(r):
+    # tests/core/limb_dark_test.py:26-39 uses u = [0.2, 0.3, 0.1, 0.5, 0.02] (l_max = 5)
+    from jaxoplanet_b200.core.limb_dark import light_curve
+
+    for u in ([0.2, 0.3, 0.1], [0.2, 0.3, 0.1, 0.5, 0.02], [0.1, 0.1, 0.05, 0.1, 0.02, 0.03, 0.01, 0.02]):
+        u = np.array(u)
+        b = np.concatenate([np.linspace(-1 - 2 * r, 1 + 2 * r, 2001), [0.0, 0.5, 1.0, r, abs(1 - r), 1 + r]])
+        got = light_curve(u, b, r)
+        want = ref.ld_light_curve(u, b, np.full_like(b, r))
+        assert np.all(np.isfinite(got))
+        _flux_close(got, want)
+        got7 = light_curve(u, b, r, order=7)
+        _flux_close(got7, ref.ld_light_curve(u, b, np.full_like(b, r), order=7))
+
+
+def test_polynomial_limb_dark_grad_and_system():
+    import torch
+
+    from jaxoplanet_b200.core.limb_dark import light_curve
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve
+
+    TH = ref.torch_backend()
+    rng = np.random.default_rng(21)
+    n = 4000
+    r = rng.uniform(0.02, 0.3, n)
+    b = rng.uniform(0, 1.02, n) * (1 + r)
+    ok = (np.abs(b - r) > 1e-6) & (np.abs(np.abs(b - r) - 1) > 1e-6) & (np.abs(b - 1 - r) > 1e-6) & (b > 1e-6)
+    b, r = b[ok], r[ok]
+    u = np.array([0.2, 0.3, 0.1, 0.5, 0.02])
+    bt, rt, ut = (torch.tensor(x, requires_grad=True) for x in (b, r, u))
+    f0 = ref.ld_light_curve(ut, bt, rt, xp=TH)
+    gb0, gr0, gu0 = torch.autograd.grad(f0.sum(), (bt, rt, ut))
+    bc, rc, uc = (torch.tensor(x, device="cuda", requires_grad=True) for x in (b, r, u))
+    f = light_curve(uc, bc, rc)
+    gb, gr, gu = torch.autograd.grad(f.sum(), (bc, rc, uc))
+    np.testing.assert_allclose(f.detach().cpu().numpy(), f0.detach().numpy(), rtol=0, atol=1e-12)
+    for got, want in ((gb, gb0), (gr, gr0)):
+        got, want = got.cpu().numpy(), want.numpy()
+        assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-2)) <= 1e-9
+    np.testing.assert_allclose(gu.cpu().numpy(), gu0.numpy(), rtol=1e-9)
+    # the fused system kernel with a 6-term law (docs/tutorials/quickstart.ipynb cell 15 pattern)
+    u6 = np.array([0.3, 0.2, 0.05, 0.04, 0.03, 0.01])
+    t = np.linspace(-0.3, 0.3, 3001)
+    lc = limb_dark_light_curve(_c1_system(), u6)(t)
+    _flux_close(lc, _c1_oracle(t, u6))
+    assert np.sum(lc < 0) > 500
