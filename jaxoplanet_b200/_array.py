@@ -91,7 +91,7 @@ def like_input(out: torch.Tensor, *inputs):
     """Return torch tensors to torch callers and numpy arrays to everyone else."""
     if any(isinstance(x, torch.Tensor) for x in inputs):
         return out
-    return out.cpu().numpy()
+    return out.detach().cpu().numpy()
 
 
 def ptr(t) -> int:

@@ -174,20 +174,21 @@ def light_curve(orbit, *u, order: int = 10):
         return light_curve_impl
 
     def light_curve_generic(time):
-        # light_curves/limb_dark.py:49-60 for a foreign orbit object
-        r_star = orbit.central_radius
-        x, y, z = orbit.relative_position(time)
+        # light_curves/limb_dark.py:49-60 for a foreign orbit object (LightCurveOrbit protocol)
         dt = A.result_dtype(time)
-        x, y, z = (A.to_dev(v, dt) for v in (x, y, z))
-        r_star = A.to_dev(r_star, dt)
+        pos = orbit.relative_position(time)
+        x, y, z = (A.to_dev(v, dt) for v in pos)
+        t_ndim = np.ndim(time) if not isinstance(time, torch.Tensor) else time.ndim
+        r_star = A.to_dev(orbit.central_radius, dt)
         radius = A.to_dev(orbit.radius, dt)
-        n_b = x.shape[0] if x.ndim > np.ndim(time) else None
-        if n_b is not None:  # (n_bodies, *t.shape) -> t.shape + (n_bodies,)
+        if x.ndim > t_ndim:  # (n_bodies, *t.shape) -> t.shape + (n_bodies,)
             x, y, z = (torch.movedim(v, 0, -1) for v in (x, y, z))
         b = torch.sqrt(x**2 + y**2) / r_star
         r = (radius / r_star).expand(b.shape).contiguous()
         lc = _limb_dark_light_curve(A.to_dev(ld_u, dt), b.contiguous(), r, order=order)
         lc = torch.where(z > 0, lc, torch.zeros_like(lc))
+        if orbit.shape == () and lc.ndim == t_ndim:
+            pass
         return A.like_input(lc, time)
 
     return light_curve_generic

@@ -15,7 +15,7 @@ import torch
 
 from jaxoplanet_b200 import _array as A
 
-__all__ = ["integrate"]
+__all__ = ["integrate", "interpolate"]
 
 
 def _stencil(exposure_time, order, num_samples):
@@ -78,5 +78,35 @@ def integrate(func, exposure_time=None, order: int = 0, num_samples: int = 7):
             term = term * float(w)
             res = term if res is None else res + term
         return res
+
+    return wrapped
+
+
+def interpolate(func, *, period, time_transit, num_samples: int, duration=None, args=(), kwargs=None):
+    """Pre-compute ``func`` on a grid around the transit and linearly interpolate it at the
+    (period-wrapped) requested times: drop-in for src/jaxoplanet/light_curves/transforms.py:119-185
+    (``jnp.interp(..., period=period)`` semantics).  The grid evaluation runs in the CUDA path; the
+    interpolation is a host-side NumPy lerp over the small pre-computed table."""
+    kwargs = kwargs or {}
+    period = float(period)
+    time_transit = float(time_transit)
+    if duration is None:
+        duration = period
+    time_grid = time_transit + float(duration) * np.linspace(-0.5, 0.5, int(num_samples))
+    flux_grid = func(time_grid, *args, **kwargs)
+    flux_grid = flux_grid.detach().cpu().numpy() if isinstance(flux_grid, torch.Tensor) else np.asarray(flux_grid)
+
+    @wraps(func)
+    def wrapped(time, *a, **k):
+        del a, k
+        tnp = time.detach().cpu().numpy() if isinstance(time, torch.Tensor) else np.asarray(time, dtype=np.float64)
+        wrapped_t = np.mod(tnp - time_transit + 0.5 * period, period) + 0.5 * period + time_transit
+        # jnp.interp with period: xp and x are wrapped to [0, period) and xp sorted (numpy does the same)
+        flat = flux_grid.reshape(flux_grid.shape[0], -1)
+        cols = [np.interp(wrapped_t.ravel(), time_grid, flat[:, j], period=period) for j in range(flat.shape[1])]
+        out = np.stack(cols, -1).reshape(tnp.shape + flux_grid.shape[1:])
+        if isinstance(time, torch.Tensor):
+            return torch.as_tensor(out, device=time.device)
+        return out
 
     return wrapped

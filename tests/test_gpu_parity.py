@@ -788,3 +788,48 @@ def test_polynomial_limb_dark_grad_and_system():
     lc = limb_dark_light_curve(_c1_system(), u6)(t)
     _flux_close(lc, _c1_oracle(t, u6))
     assert np.sum(lc < 0) > 500
+
+
+# ----------------------------------------------------------------------------- "next" rows
+def test_transit_orbit_depth_and_system_equivalence():
+    # tests/light_curves/transit_test.py:9-37
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve
+    from jaxoplanet_b200.orbits import TransitOrbit
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    period, central_radius, body_radius = 1.0, 0.5, 0.1
+    ror = body_radius / central_radius
+    transit_orbit = TransitOrbit(period=period, radius_ratio=ror, duration=0.1)
+    system_orbit = System(Central(radius=central_radius, mass=0.5)).add_body(period=period, radius=body_radius)
+    time = np.linspace(-0.1, 0.1, 10)
+    transit_flux = limb_dark_light_curve(transit_orbit, (0,))(time)
+    system_flux = limb_dark_light_curve(system_orbit, (0,))(time)
+    np.testing.assert_allclose(transit_flux.min(), -(ror**2), rtol=5e-7)
+    np.testing.assert_allclose(transit_flux.min(), system_flux.min(), rtol=5e-7)
+    # shape-path: vector of planets
+    orb2 = TransitOrbit(period=np.array([1.0, 2.0]), radius_ratio=np.array([0.1, 0.05]), duration=np.array([0.1, 0.2]),
+                        impact_param=np.array([0.1, 0.3]))
+    t = np.linspace(-0.3, 0.3, 501)
+    lc2 = limb_dark_light_curve(orb2, [0.3, 0.2])(t[:, None])
+    assert lc2.shape == (501, 2)
+    x = orb2.speed.numpy() * ((t[:, None] + 0.5 * orb2.period.numpy()) % orb2.period.numpy() - 0.5 * orb2.period.numpy())
+    b = np.sqrt(x**2 + orb2.impact_param.numpy() ** 2)
+    want = ref.ld_light_curve(np.array([0.3, 0.2]), b, np.broadcast_to(orb2.radius_ratio.numpy(), b.shape).copy())
+    inside = np.abs(x / orb2.speed.numpy()) < 0.5 * orb2.duration.numpy()
+    _flux_close(lc2, np.where(inside, want, 0.0))
+
+
+def test_interpolate_transform():
+    # transforms.py:119-185: pre-computed grid + periodic linear interpolation
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve, transforms
+
+    sys_ = _c1_system()
+    u = np.array([0.3, 0.2])
+    f = limb_dark_light_curve(sys_, u)
+    fi = transforms.interpolate(f, period=3.456, time_transit=0.0, num_samples=4001, duration=0.6)
+    t = np.linspace(-5.0, 12.0, 3000)
+    got = fi(t)
+    assert got.shape == (3000, 1)
+    exact = f(t)
+    assert np.max(np.abs(got - exact)) < 2e-5  # lerp error of the 1.5e-4 d grid
+    assert np.sum(got < 0) > 50
