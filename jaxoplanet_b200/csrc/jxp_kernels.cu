@@ -866,20 +866,32 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
         const int set = set_base + sl;
         const SetC<T> sc = sset[sl];
         const BodyC<T>* bodies = sbody + sl * nb;
-        const int npairs = nb * nsub;
-        int pair = 0, cur_b = 0;
+        int nxt_b = 0, nxt_j = 0, cur_b = 0;
         T accb = T(0);
-        // walk this sample's (body, sub-sample) pairs that pass the window test
+        // walk this sample's (body, sub-sample) pairs that pass the window test: a body whose
+        // exposure-widened window misses the sample is skipped with one test
 #pragma unroll 1
         while (true) {
           int b = 0, j = 0;
           bool found = false;
-          while (pair < npairs) {
-            b = pair / nsub;
-            j = pair - b * nsub;
-            ++pair;
-            const BodyC<T>& c = bodies[b];
-            if ((c.flags & BODY_ALWAYS) || phase_in_window(c, tm0 + a.st.dt[j])) {
+          while (nxt_b < nb) {
+            const BodyC<T>& c = bodies[nxt_b];
+            const bool always = (c.flags & BODY_ALWAYS) != 0;
+            if (nxt_j == 0 && !always) {
+              const double ph = fma(tm0 - c.t0ref, c.inv_period, -c.phase_c);
+              const double d = ph - rint(ph);
+              if ((d < fma(-dtmax, c.inv_period, c.wlo)) | (d > fma(-dtmin, c.inv_period, c.whi))) {
+                ++nxt_b;
+                continue;
+              }
+            }
+            b = nxt_b;
+            j = nxt_j;
+            if (++nxt_j == nsub) {
+              nxt_j = 0;
+              ++nxt_b;
+            }
+            if (always || nsub == 1 || phase_in_window(c, tm0 + a.st.dt[j])) {
               found = true;
               break;
             }

@@ -38,6 +38,17 @@ elif case == "ld":
     f = torch.empty_like(b)
     ms = timed(lambda: _lib.call("jxp_limb_dark_f64", u.data_ptr(), 2, b.data_ptr(), 1, r.data_ptr(), 1, n, 10, f.data_ptr(), 0, 0, 0, A.stream_ptr()))
     print("ld", n, "ms", ms, "points/s", n / ms * 1e3)
+elif case == "c4":
+    from jaxoplanet_b200 import workloads as W
+    p4, u4, t4, expo = W.c4(n_sets, n_t)
+    bodies, ns, _ = pack_bodies(W.system_from(p4))
+    bodies = bodies.to(dev).contiguous(); ud = torch.as_tensor(u4).to(dev).contiguous(); td = torch.as_tensor(t4).to(dev)
+    wsb = _lib.load().jxp_system_workspace_bytes(ns, 3, n_t); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    fs = torch.empty((ns, n_t), dtype=torch.float64, device=dev)
+    ms = timed(lambda: _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), ns, 3, ud.data_ptr(), 2, 2, td.data_ptr(), n_t,
+                                 expo["exposure_time"], expo["order"], expo["num_samples"], 10, flags, 0, fs.data_ptr(), 0, 0, 0, 0,
+                                 ws.data_ptr(), wsb, A.stream_ptr()))
+    print("c4", ns, n_t, "flags", flags, "ms", ms, "points/s", ns * n_t / ms * 1e3, "inner/s", ns * n_t * 45 / ms * 1e3)
 elif case == "c5":
     from jaxoplanet_b200 import workloads as W
     theta, t5 = W.c5(n_sets, n_t)
