@@ -19,9 +19,14 @@ Contents
 
 Pinning status
 --------------
-The reference is pure JAX and JAX is not installable in this image (no wheel,
-no network), so the oracle cannot be compared with reference outputs produced
-here.  It IS pinned against every self-contained known-answer test the
-reference's own suite holds for this path (tests/test_oracle_kats.py lists them
-with reference file:line).  Against real ``jax[cpu]`` outputs: parity unpinned.
+Pinned two ways.  (1) Against outputs of the reference's OWN source files: jax/jaxlib/equinox
+are not installable in this image, but the reference's unmodified ``core/kepler.py``,
+``core/limb_dark.py``, ``orbits/keplerian.py``, ``orbits/transit.py``, ``light_curves/*.py``
+execute eagerly on a NumPy-backed ``jax`` shim (tests/golden/jax_shim); their outputs are committed
+as tests/golden/reference_v1.npz (made by tests/golden/make_reference_vectors.py) and
+tests/test_reference_vectors.py holds the oracle to them: bit-exact for Kepler, orbit constants,
+positions; <= 4 eps for fluxes (summation order of the final dot product).  (2) Against every
+self-contained known-answer test of the reference's suite (tests/test_oracle_kats.py).
+What stays unpinned: XLA's own libm/fusion versus NumPy's (<= 1 ulp per call) and derivatives
+produced by JAX tracing (the reference's two hand-written JVP rules ARE executed and compared).
 """

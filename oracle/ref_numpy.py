@@ -1,9 +1,10 @@
 """NumPy restatement of the jaxoplanet hot path.  TEST INFRASTRUCTURE ONLY.
 
 Each function follows the cited lines of ``/root/reference`` operation by
-operation (same association order, same guards).  Parity vs real jax[cpu]
-outputs is unpinned (JAX cannot be installed here); the restatement is pinned
-against the reference's own known-answer tests in tests/test_oracle_kats.py.
+operation (same association order, same guards).  Pinned (tests/test_reference_vectors.py)
+against outputs of the reference's own source files executed on a NumPy-backed jax shim
+(tests/golden/reference_v1.npz) and against the reference's known-answer tests
+(tests/test_oracle_kats.py); only XLA's libm/fusion vs NumPy's remains unpinned.
 
 Every numerical function takes an optional backend ``xp`` (``NP`` default, or
 ``TH`` = torch) so that the very same formulas are differentiated by torch-f64
