@@ -151,6 +151,59 @@ __device__ __forceinline__ double fcos_0pi(double x) {
   return fma(pb, z, pa);
 }
 
+// cos(a) = Pc(a^2) and sin(a) = a Ps(a^2) for |a| <= pi/2 + 1e-6: degree-8 near-minimax fits
+// (Chebyshev interpolation in mpmath; truncation 2.5e-18 / 2e-19, evaluated error <= 2.3e-16).
+__device__ __constant__ double c_pc[9] = {1.0,
+                                          -0.4999999999999997,
+                                          0.04166666666666388,
+                                          -0.0013888888888772988,
+                                          2.480158727741477e-05,
+                                          -2.755731639101142e-07,
+                                          2.087656183919406e-09,
+                                          -1.1462901882009371e-11,
+                                          4.608976789597796e-14};
+__device__ __constant__ double c_ps[9] = {1.0,
+                                          -0.16666666666666666,
+                                          0.008333333333333186,
+                                          -0.00019841269841208676,
+                                          2.7557319211229526e-06,
+                                          -2.5052106890561953e-08,
+                                          1.6058940878096299e-10,
+                                          -7.643026547544204e-13,
+                                          2.7215748296140716e-15};
+
+// sin and cos of a first-quadrant-sized angle, no reduction, two independent Horner chains
+__device__ __forceinline__ void fsincos_q1(double a, double* sp, double* cp) {
+  const double z = a * a;
+  double pc = c_pc[8], ps = c_ps[8];
+#pragma unroll
+  for (int k = 7; k >= 0; --k) {
+    pc = fma(pc, z, c_pc[k]);
+    ps = fma(ps, z, c_ps[k]);
+  }
+  *cp = pc;
+  *sp = a * ps;
+}
+
+// sqrt(x), x positive and normal: third-order step on the 2^-20 seed (error ~3 e^3 ~ 2^-58 before
+// the last rounding, i.e. <= ~0.51 ulp); no residual correction
+__device__ __forceinline__ double fsqrt_fast(double x) {
+  const double y = rsqrt_seed(x);
+  const double g = x * y;
+  const double h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  const double p = fma(r, 1.5, 1.0) * r;
+  return fma(g, p, g);
+}
+
+// 1 / x to ~2^-60 (third-order step on the seed), no residual correction
+__device__ __forceinline__ double frcp_fast(double x) {
+  const double y = rcp_seed(x);
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  return fma(y, e, y);
+}
+
 __device__ __constant__ double c_atan[11] = {
     -0.33333333333333120084,
     0.19999999999940620353,

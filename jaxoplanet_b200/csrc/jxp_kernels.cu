@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "jxp_host.h"
 #include "jxp_orbit.cuh"
@@ -113,13 +114,42 @@ extern "C" const char* jxp_last_error(void) { return g_err; }
 // ======================================================================================
 // K1  Kepler
 // ======================================================================================
+#ifndef JXP_KEP_ILP
+#define JXP_KEP_ILP 2
+#endif
 template <typename T, bool EXTRA>
 __global__ void __launch_bounds__(256)
 k_kepler(const T* __restrict__ M, int64_t Ms, const T* __restrict__ ecc, int64_t es, int64_t n,
          T* __restrict__ sinf_o, T* __restrict__ cosf_o, T* __restrict__ E_o,
          T* __restrict__ dfdM_o, T* __restrict__ dfde_o) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (!EXTRA && std::is_same<T, double>::value) {
+    // JXP_KEP_ILP independent solves per thread and iteration (see kepler_reduced_n)
+    constexpr int NI = JXP_KEP_ILP;
+    for (; i + (NI - 1) * stride < n; i += NI * stride) {
+      double Mr[NI], e[NI], ome[NI], ope[NI], s1[NI], iope[NI], sf[NI], cf[NI];
+#pragma unroll
+      for (int q = 0; q < NI; ++q) {
+        const double m = M[(i + q * stride) * Ms];
+        e[q] = ecc[(i + q * stride) * es];
+        ome[q] = 1.0 - e[q];
+        ope[q] = 1.0 + e[q];
+        Mr[q] = mod_two_pi(m);
+      }
+#pragma unroll
+      for (int q = 0; q < NI; ++q) s1[q] = jsqrt(ome[q] * ope[q]);
+#pragma unroll
+      for (int q = 0; q < NI; ++q) iope[q] = jrcp(ope[q]);
+      kepler_reduced_n<NI>(Mr, e, ome, ope, s1, iope, sf, cf);
+#pragma unroll
+      for (int q = 0; q < NI; ++q) {
+        sinf_o[i + q * stride] = sf[q];
+        cosf_o[i + q * stride] = cf[q];
+      }
+    }
+  }
+  for (; i < n; i += stride) {
     const T m = M[i * Ms];
     const T e = ecc[i * es];
     const T ome = T(1) - e, ope = T(1) + e;
@@ -375,7 +405,7 @@ namespace {
 
 // workspace carving shared by the size query and the launchers
 struct SysLayout {
-  size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, total;
+  size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, off_tilectr, total;
   int tile, n_tiles;
 };
 
@@ -395,6 +425,8 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
   off = align_up(off + 256 * sizeof(double), 256);
   L.off_partial = off;
   off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles, 256);
+  L.off_tilectr = off;  // [0]: next unclaimed set group, [1 + g]: next warp tile of group g
+  off = align_up(off + sizeof(int) * ((size_t)n_sets + 1), 256);
   L.total = off;
   return L;
 }
@@ -405,9 +437,12 @@ template <typename T>
 __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
                            BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
-                           unsigned long long* __restrict__ counters, double widen, double margin) {
+                           unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr,
+                           double widen, double margin) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sets * n_bodies) return;
+  if (i <= n_sets) tile_ctr[i] = 0;  // work distribution state of k_system (n_sets + 1 entries)
+  if (i == 0 && n_sets * n_bodies <= n_sets) tile_ctr[n_sets] = 0;
   const double* p = bodies + (size_t)i * JXP_BODY_NFIELDS;
   BodyC<T> c;
   c.t0 = p[JXP_BODY_TIME_TRANSIT];
@@ -554,7 +589,8 @@ struct SysArgs {
   const SetC<T>* sets;
   const double* t;
   int64_t n_times;
-  int n_sets, n_bodies, sets_per_cta, n_tiles, n_wtiles, use_window;
+  int n_sets, n_bodies, sets_per_cta, n_groups, n_wtiles, use_window;
+  int* tile_ctr;  // [1 + n_groups] work distribution (zeroed by k_sys_prep)
   T* flux;
   T* flux_sum;
   const T* y;
@@ -585,8 +621,11 @@ struct SysArgs {
 // not queued, and by the processing lane for queued ones; the likelihood uses a segmented
 // warp-shuffle reduction keyed by set into a per-warp accumulator, written as one partial per
 // (set, warp tile) and summed in fixed order by k_loglike_final (deterministic).
+// 5 CTAs of 128 threads per SM = 96 registers per thread: with 64 (8 CTAs) ptxas serialises the
+// independent chains of the node loop to save registers and spills inside it; measured config 3
+// 1.09 -> 1.00 ms, config 4 26.6 -> 19.8 ms (gpurun_out/variants*.log)
 #ifndef JXP_SYS_MINB
-#define JXP_SYS_MINB 8
+#define JXP_SYS_MINB 5
 #endif
 constexpr int SYS_QCAP = 256;  // queue entries per warp
 
@@ -597,18 +636,16 @@ __device__ __forceinline__ bool phase_in_window(const BodyC<T>& c, double tm) {
   return (d >= c.wlo) & (d <= c.whi);
 }
 
-template <typename T, int ORDER, bool LOGLIKE, bool DENSE, bool HI = false>
+template <typename T, int ORDER, bool LOGLIKE, bool DENSE, bool HI = false, int PU = 1>
 __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_constant__ SysArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_pick[2];
   constexpr int K = SYS_K;
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x % a.n_tiles;  // CTA tile = nwarps warp tiles
-  const int group = blockIdx.x / a.n_tiles;
-  const int set_base = group * a.sets_per_cta;
-  const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
   const int nb = a.n_bodies;
+  const int n_groups = a.n_groups;
 
   BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
   SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * nb);
@@ -619,56 +656,109 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   // dense variant: sky separation of the queued in-transit samples
   T* sqb = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + warp * SYS_QCAP;
 
-  {
-    // stage the group's records (plain 8-byte copies; sizeof(BodyC), sizeof(SetC) % 8 == 0)
-    const unsigned long long* src =
-        reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base * nb);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
-    const int nw = nsl * nb * (int)(sizeof(BodyC<T>) / 8);
-    for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
-    const unsigned long long* src2 = reinterpret_cast<const unsigned long long*>(a.sets + set_base);
-    unsigned long long* dst2 = reinterpret_cast<unsigned long long*>(sset);
-    const int nw2 = nsl * (int)(sizeof(SetC<T>) / 8);
-    for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
-    if (LOGLIKE)
-      for (int i = lane; i < a.sets_per_cta; i += 32) sacc[i] = 0.0;
-  }
-  if (a.use_window == 0) {
-    // dense mode: mark every staged body "always" so that the hot loops test one flag only
-    __syncthreads();
-    for (int i = threadIdx.x; i < nsl * nb; i += nthreads) sbody[i].flags |= BODY_ALWAYS;
-  }
-
-  // this warp's samples: sample k of lane l is wbase + 32 k + l
-  const int64_t wtile = (int64_t)tile * nwarps + warp;
-  const int64_t wbase = wtile * (32 * K);
-  double tk[K];
-  unsigned valid = 0;
-  double tmin = 1e300, tmax = -1e300;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int64_t idx = wbase + 32 * k + lane;
-    const bool ok = idx < a.n_times;
-    tk[k] = ok ? a.t[idx] : 0.0;
-    valid |= ok ? (1u << k) : 0u;
-    if (ok) {
-      tmin = fmin(tmin, tk[k]);
-      tmax = fmax(tmax, tk[k]);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-    tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-  }
   const int nsub = a.st.n;
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
-  const double span_lo = tmin + dtmin, span = (tmax + dtmax) - span_lo;
   const bool want_zero = (a.flux != nullptr) || (a.flux_sum != nullptr);
   unsigned n_kep = 0, n_ld = 0;
-  int qn = 0;  // queue fill (warp-uniform)
-  __syncthreads();
-  if (wbase >= a.n_times) return;  // (no further block barriers)
+  int* const group_ctr = a.tile_ctr;     // next unclaimed set group
+  int* const tile_ctr = a.tile_ctr + 1;  // per group: next warp tile
+
+  // Persistent CTAs.  Phase 1: claim whole set groups from a global counter.  Phase 2 (no
+  // unclaimed group left): scan the groups cyclically from a home position and help with the
+  // ones that still have warp tiles.  Inside a group every WARP pulls its next tile from the
+  // group's counter, so a warp that drew light tiles simply processes more of them.
+  int scan = -1;  // -1: claiming; >= 0: groups scanned so far in phase 2
+  const int home = (int)(blockIdx.x % (unsigned)n_groups);
+  for (int iter = 0;; ++iter) {
+    int group;
+    if (scan < 0) {
+      if (threadIdx.x == 0) s_pick[iter & 1] = atomicAdd(group_ctr, 1);
+      __syncthreads();
+      group = s_pick[iter & 1];
+      if (group >= n_groups) {
+        scan = 0;
+        continue;
+      }
+    } else {
+      if (scan >= n_groups) break;
+      // every thread looks at one group; the first one with tiles left is taken
+      const int gi = scan + (int)threadIdx.x;
+      bool has = false;
+      if (gi < n_groups) {
+        int g = home + gi;
+        g -= (g >= n_groups) ? n_groups : 0;
+        has = *reinterpret_cast<volatile int*>(tile_ctr + g) < a.n_wtiles;
+      }
+      if (threadIdx.x == 0) s_pick[iter & 1] = 0x7fffffff;
+      __syncthreads();
+      const unsigned hb = __ballot_sync(0xffffffffu, has);
+      if (hb && lane == 0) atomicMin(&s_pick[iter & 1], warp * 32 + __ffs(hb) - 1);
+      __syncthreads();
+      const int first = s_pick[iter & 1];
+      if (first == 0x7fffffff) {
+        scan += nthreads;
+        continue;
+      }
+      group = home + scan + first;
+      group -= (group >= n_groups) ? n_groups : 0;
+      scan += first + 1;
+    }
+    const int set_base = group * a.sets_per_cta;
+    const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
+    {
+      // stage the group's records (plain 8-byte copies; sizeof(BodyC), sizeof(SetC) % 8 == 0)
+      const unsigned long long* src =
+          reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base * nb);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
+      const int nw = nsl * nb * (int)(sizeof(BodyC<T>) / 8);
+      for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
+      const unsigned long long* src2 = reinterpret_cast<const unsigned long long*>(a.sets + set_base);
+      unsigned long long* dst2 = reinterpret_cast<unsigned long long*>(sset);
+      const int nw2 = nsl * (int)(sizeof(SetC<T>) / 8);
+      for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
+    }
+    if (a.use_window == 0) {
+      // dense mode: mark every staged body "always" so that the hot loops test one flag only
+      __syncthreads();
+      for (int i = threadIdx.x; i < nsl * nb; i += nthreads) sbody[i].flags |= BODY_ALWAYS;
+    }
+    __syncthreads();
+
+    // ---- warp tiles of this group (no block barriers inside) -----------------------------
+    int wnext = 0;
+    if (lane == 0) wnext = atomicAdd(tile_ctr + group, 1);
+    while (true) {
+    const int wtile_i = __shfl_sync(0xffffffffu, wnext, 0);
+    if (wtile_i >= a.n_wtiles) break;
+    if (lane == 0) wnext = atomicAdd(tile_ctr + group, 1);  // in flight while this tile runs
+    // this warp's samples: sample k of lane l is wbase + 32 k + l
+    const int64_t wtile = wtile_i;
+    const int64_t wbase = wtile * (32 * K);
+    double tk[K];
+    unsigned valid = 0;
+    double tmin = 1e300, tmax = -1e300;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int64_t idx = wbase + 32 * k + lane;
+      const bool ok = idx < a.n_times;
+      tk[k] = ok ? a.t[idx] : 0.0;
+      valid |= ok ? (1u << k) : 0u;
+      if (ok) {
+        tmin = fmin(tmin, tk[k]);
+        tmax = fmax(tmax, tk[k]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+      tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    const double span_lo = tmin + dtmin, span = (tmax + dtmax) - span_lo;
+    int qn = 0;  // queue fill (warp-uniform)
+    if (LOGLIKE) {
+      for (int i = lane; i < a.sets_per_cta; i += 32) sacc[i] = 0.0;
+      __syncwarp();
+    }
 
   if constexpr (DENSE) {
     // ---- dense variant (JXP_FLAG_NO_WINDOW, one body, no exposure integration) ----------------
@@ -906,7 +996,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
             cur_b = b;
           }
           ++n_kep;
-          const T v = eval_in_window<T, ORDER, HI>(bodies[b], sc, &a.tab, tm0 + a.st.dt[j], n_ld);
+          const T v = eval_in_window<T, ORDER, HI, PU>(bodies[b], sc, &a.tab, tm0 + a.st.dt[j], n_ld);
           accb = (nsub == 1) ? v : jfma(T(a.st.w[j]), v, accb);
         }
         if (a.flux)
@@ -949,10 +1039,14 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   }
   }  // !DENSE
 
-  if (LOGLIKE) {
-    for (int sl = lane; sl < nsl; sl += 32)
-      a.partial[(size_t)wtile * a.n_sets + (set_base + sl)] = sacc[sl];
-  }
+    if (LOGLIKE) {
+      for (int sl = lane; sl < nsl; sl += 32)
+        a.partial[(size_t)wtile * a.n_sets + (set_base + sl)] = sacc[sl];
+      __syncwarp();
+    }
+    }  // warp tiles
+    __syncthreads();  // the staged records are replaced in the next iteration
+  }  // set groups
   // executed-work counters (two atomics per warp)
   n_kep = __reduce_add_sync(0xffffffffu, n_kep);
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
@@ -1024,6 +1118,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride,
                                                   d_bodies, d_sets,
                                                   reinterpret_cast<unsigned long long*>(d_scalars + 2),
+                                                  reinterpret_cast<int*>(ws + L.off_tilectr),
                                                   f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7);
     rc = check_launch("jxp_system_light_curve(prep)");
     if (rc != JXP_OK) return rc;
@@ -1034,8 +1129,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     if (rc != JXP_OK) return rc;
   }
 
-  // launch geometry: enough CTAs to fill the machine several times over, as many sets per
-  // CTA as that allows (amortises the time-stamp loads and the record staging)
+  // launch geometry: persistent CTAs (as many as are resident at once) that pull set groups and
+  // warp tiles from counters in the workspace; as many sets per group as keeps >= 8 groups per
+  // SM worth of (group, CTA tile) work (amortises the record staging)
   const int sms = sm_count();
   int threads = 128;
   if (const char* env = getenv("JXP_SYS_THREADS")) {  // development knob
@@ -1053,8 +1149,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   if (spc > n_sets) spc = n_sets;
   if (n_bodies * spc > 512) spc = (512 / n_bodies) > 0 ? (512 / n_bodies) : 1;
   const int64_t n_groups = (n_sets + spc - 1) / spc;
-  const int64_t n_ctas = n_tiles * n_groups;
-  if (n_ctas > 2147483647LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: grid too large");
+  const int64_t n_units = n_tiles * n_groups;  // CTA-sized pieces of work
+  if (n_wtiles > 2000000000LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: too many time samples");
   if (spc > 511) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: sets per CTA");
 
   a.bodies = d_bodies;
@@ -1064,7 +1160,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   a.n_sets = n_sets;
   a.n_bodies = n_bodies;
   a.sets_per_cta = spc;
-  a.n_tiles = (int)n_tiles;
+  a.n_groups = (int)n_groups;
+  a.tile_ctr = reinterpret_cast<int*>(ws + L.off_tilectr);
   a.n_wtiles = (int)n_wtiles;
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
@@ -1086,8 +1183,14 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
+    int per_sm = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (eo != cudaSuccess || per_sm < 1)
+      return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
+    const int64_t resident = (int64_t)per_sm * sms;
+    const unsigned n_ctas = (unsigned)(n_units < resident ? n_units : resident);
     if (g_ev_start) cudaEventRecord(g_ev_start, st);
-    kern<<<(unsigned)n_ctas, threads, smem, st>>>(a);
+    kern<<<n_ctas, threads, smem, st>>>(a);
     if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return check_launch("jxp_system_light_curve");
   };
@@ -1101,6 +1204,10 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   } else if (gl_order == 10) {
     if (dense)
       rc = loglike ? launch(k_system<T, 11, true, true>) : launch(k_system<T, 11, false, true>);
+    else if (sizeof(T) == 8 && (int64_t)n_bodies * a.st.n > 1)
+      // several flux evaluations per queued sample: the unrolled node loop pays (config 4)
+      rc = loglike ? launch(k_system<T, 11, true, false, false, 5>)
+                   : launch(k_system<T, 11, false, false, false, 5>);
     else
       rc = loglike ? launch(k_system<T, 11, true, false>) : launch(k_system<T, 11, false, false>);
   } else {

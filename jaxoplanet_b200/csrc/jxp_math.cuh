@@ -5,6 +5,7 @@
 // is re-arranged relative to the reference the comment says why it stays inside the
 // parity tolerance (DESIGN.md "numerics").
 #pragma once
+#include <type_traits>
 
 #include "jxp_scalar.cuh"
 
@@ -123,6 +124,80 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
   }
 }
 
+// N independent solves per thread, written statement by statement over the N items so that the
+// instruction stream interleaves N dependency chains.  Why: the solve is one long chain (three
+// dependent divisions) and a warp's DEPENDENT DFMAs issue 8 cycles apart; measured on B200
+// (tools/ubench/dfma_lat.cu) a stream with one chain per warp saturates at 67 % of the FP64 pipe
+// however many warps are resident, two chains reach 80 %, four 92 %.  Same arithmetic as
+// kepler_reduced, operation for operation.
+template <int N>
+__device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const double (&e)[N],
+                                                 const double (&ome)[N], const double (&ope)[N],
+                                                 const double (&s1me2)[N], const double (&inv_ope)[N],
+                                                 double (&sinf)[N], double (&cosf)[N]) {
+  const double pi = Num<double>::pi;
+  bool high[N], slow = false;
+  double M[N], E0[N], hs[N], hc[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    high[q] = Mr[q] > pi;
+    M[q] = high[q] ? Num<double>::two_pi - Mr[q] : Mr[q];
+    slow = slow || !(ome[q] > 1e-5);
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q)
+    E0[q] = (double)kepler_starter_t<float>((float)M[q], (float)e[q], (float)ome[q], (float)inv_ope[q]);
+  if (slow) {
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (!(ome[q] > 1e-5)) E0[q] = kepler_starter_t<double>(M[q], e[q], ome[q], inv_ope[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) jsincos(0.5 * E0[q], &hs[q], &hc[q]);
+  double f0[N], f1[N], f2[N], f3[N], d3[N], d4[N], dE[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double sinE = 2.0 * hs[q] * hc[q];
+    const double cE = 2.0 * hs[q] * hs[q];
+    const double sE = E0[q] - sinE;
+    f0[q] = fma(e[q], sE, fma(E0[q], ome[q], -M[q]));
+    f1[q] = fma(e[q], cE, ome[q]);
+    f2[q] = e[q] * sinE;
+    f3[q] = 1.0 - f1[q];
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) d3[q] = jdiv(-f0[q] * f1[q], fma(-0.5 * f0[q], f2[q], f1[q] * f1[q]));
+#pragma unroll
+  for (int q = 0; q < N; ++q)
+    d4[q] = jdiv(-f0[q], fma(d3[q] * d3[q], f3[q] * (1.0 / 6.0), fma(0.5 * d3[q], f2[q], f1[q])));
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double d42 = d4[q] * d4[q];
+    dE[q] = jdiv(-f0[q], fma(-d42 * d4[q], f2[q] * (1.0 / 24.0),
+                              fma(d42, f3[q] * (1.0 / 6.0), fma(0.5 * d4[q], f2[q], f1[q]))));
+  }
+  double s[N], c[N], a[N], b[N], invD[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double h = 0.5 * dE[q];
+    const double h2 = h * h;
+    const double sh = fma(-h * h2, 1.0 / 6.0, h);
+    const double ch = fma(h2, fma(h2, 1.0 / 24.0, -0.5), 1.0);
+    s[q] = fma(hs[q], ch, hc[q] * sh);
+    c[q] = fma(hc[q], ch, -hs[q] * sh);
+    a[q] = ome[q] * (c[q] * c[q]);
+    b[q] = ope[q] * (s[q] * s[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) invD[q] = jrcp(a[q] + b[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double sf = 2.0 * s1me2[q] * s[q] * c[q] * invD[q];
+    sinf[q] = high[q] ? -sf : sf;
+    cosf[q] = (a[q] - b[q]) * invD[q];
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // Limb darkening, src/jaxoplanet/core/limb_dark.py.  S is T or Dual<T, N>.
 // ------------------------------------------------------------------------------------
@@ -226,7 +301,9 @@ __device__ __forceinline__ S kite_area(S a, S b, S c) {
 // s0s2 :111-137 and the l = 1 term of p_integral :140-173.
 //   lmax 0: only s0 is meaningful; lmax 1: s0, s1; lmax 2: all.
 //   HI: also the l = 3..lmax terms (limb_dark.py:149-153, 175-182) into shi[0..lmax-3].
-template <typename S, int ORDER, bool HI = false>
+//   PU: unroll factor of the mirror-pair node loop of the fused double kernels (1: smallest code,
+//       matters when the hot code would otherwise outgrow the 32 KB instruction cache; 5: most ILP).
+template <typename S, int ORDER, bool HI = false, int PU = 1>
 __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* __restrict__ tab,
                                             S& s0, S& s1, S& s2, S* __restrict__ shi = nullptr) {
   using B = typename BaseOf<S>::type;
@@ -311,6 +388,38 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     factor4 = jsel(k2_cond, S(B(1)), factor4);
     k2 = jmax(S(B(0)), jdiv(B(1) - r2 - b2 + two_br, factor4));
   }
+  if constexpr (ORDER == 11 && !HI && std::is_same<S, double>::value) {
+    // fused kernels, double: the 10 nodes as 5 mirror pairs +-x_p.  With h = kappa0 / 2 the node
+    // angles are h (1 +- x_p), so cos = cos h cos(h x_p) -+ sin h sin(h x_p): one short sin/cos
+    // polynomial pair (|h x_p| <= 1.53, no reduction) serves two nodes.  sqrt and the division use
+    // the uncorrected third-order steps (<= ~1 ulp) and 2 r / 3 is applied once after the loop.
+    double sh, ch;
+    fsincos_q1(rng, &sh, &ch);
+    double accp = 0.0;
+#pragma unroll PU
+    for (int p = 0; p < 5; ++p) {
+      const double xp = c_gl10[0][5 + p], wp = c_gl10[1][5 + p];
+      double sa, ca;
+      fsincos_q1(rng * xp, &sa, &ca);
+      const double t1 = ch * ca;
+      const double cm = fma(-sh, sa, t1);  // node +x_p: angle h + h x_p
+      const double cq = fma(sh, sa, t1);   // node -x_p: angle h - h x_p
+      double pair = 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double c = q ? cq : cm;
+        const double omz2 = fma(-two_br, c, r2pb2);
+        const bool dead = !((omz2 >= eps10) && (omz2 <= 1.0 - eps10));
+        const double z2s = dead ? 1.0 : 1.0 - omz2;
+        const double z = fsqrt_fast(z2s);
+        const double t = fma(z2s, frcp_fast(z + 1.0), 1.0);  // (1 - z^3) / (1 - z^2)
+        const double res = fma(-b, c, r) * t;
+        pair += dead ? 0.0 : res;
+      }
+      accp = fma(wp, pair, accp);
+    }
+    acc = accp * two_r_3;
+  } else {
   const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
   const int order = GL<ORDER>::n(tab);
 #pragma unroll(ORDER == 10 ? 10 : 2)
@@ -344,6 +453,7 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
       for (int n = 3; n <= 8; ++n)
         if (n <= lmax) acch[n - 3] = acch[n - 3] + jpow_half(f0, n) * common * wi;
     }
+  }
   }
   if (HI) {
 #pragma unroll

@@ -158,7 +158,7 @@ __device__ __forceinline__ V pick(const V (&a)[K], int k) {
 
 // flux - 1 of one body at one time (0 when not in transit); the caller has already applied
 // the transit-window pre-test.
-template <typename T, int ORDER, bool HI = false>
+template <typename T, int ORDER, bool HI = false, int PU = 1>
 __device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc,
                                             const GLTable* __restrict__ tab, double tm,
                                             unsigned& n_ld) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc
       if (n <= sc.lmax) f = jfma(shi[n - 3], sc.ghi[n - 3], f);
     return f;
   }
-  ld_solution<T, ORDER>(b, c.rr, sc.lmax, tab, s0, s1, s2);
+  ld_solution<T, ORDER, false, PU>(b, c.rr, sc.lmax, tab, s0, s1, s2);
   return ld_combine(sc.lmax, s0, s1, s2, sc.g0, sc.g1, sc.g2);
 }
 
