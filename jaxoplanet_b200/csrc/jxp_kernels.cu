@@ -628,6 +628,7 @@ struct SysArgs {
 #define JXP_SYS_MINB 5
 #endif
 constexpr int SYS_QCAP = 256;  // queue entries per warp
+constexpr int SYS_MB = 8;       // bodies the multi variant of stage C supports
 
 template <typename T>
 __device__ __forceinline__ bool phase_in_window(const BodyC<T>& c, double tm) {
@@ -655,6 +656,12 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   unsigned short* sq = sq_all + warp * SYS_QCAP;
   // dense variant: sky separation of the queued in-transit samples
   T* sqb = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + warp * SYS_QCAP;
+  // multi variant (PU == 5): per-warp evaluation queue and per-(queued sample, body) sums
+  constexpr bool MULTI = (PU == 5);
+  T* macc = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + nwarps * SYS_QCAP + warp * (32 * SYS_MB);
+  unsigned short* meq =
+      reinterpret_cast<unsigned short*>(reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + nwarps * SYS_QCAP +
+                                        nwarps * (32 * SYS_MB)) + warp * 64;
 
   const int nsub = a.st.n;
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
@@ -952,7 +959,95 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
       }
       const int64_t idx = wbase + 32 * k + src;
       T total = T(0);
-      if (have) {
+      if constexpr (MULTI) {
+        // Several (body, sub-sample) evaluations per queued sample (multi-planet systems, exposure
+        // integration).  Lanes own different numbers of them -- at the edge of an exposure-widened
+        // window only a few sub-samples are in -- so a per-lane walk leaves most lanes idle
+        // (17.9 of 32 active on config 4).  Instead the (sample, body, sub-sample) triples that
+        // pass the window test are compacted into a second queue and evaluated 32 at a time, one
+        // per lane; the weighted values are added into per-(sample, body) sums in shared memory
+        // in queue order (= increasing sub-sample index, the order of the reference's dot product),
+        // lanes with the same target taking turns by lane index: deterministic.
+        const BodyC<T>* bodies = sbody + sl * nb;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) macc[lane * SYS_MB + b] = T(0);
+        __syncwarp();
+        const unsigned lt = (1u << lane) - 1u;
+        const int nsteps = nb * nsub;
+        int en = 0, b = 0, j = 0;
+        bool bpass = false, always = false;
+#pragma unroll 1
+        for (int step = 0; step <= nsteps; ++step) {
+          if (step < nsteps) {
+            if (j == 0) {
+              // body-level test against the exposure-widened window, once per body
+              bpass = false;
+              always = false;
+              if (have) {
+                const BodyC<T>& c = bodies[b];
+                always = (c.flags & BODY_ALWAYS) != 0;
+                const double ph = fma(tm0 - c.t0ref, c.inv_period, -c.phase_c);
+                const double d = ph - rint(ph);
+                bpass = always || !((d < fma(-dtmax, c.inv_period, c.wlo)) | (d > fma(-dtmin, c.inv_period, c.whi)));
+              }
+              if (!__any_sync(0xffffffffu, bpass)) {
+                step += nsub - 1;
+                ++b;
+                continue;
+              }
+            }
+            const bool pass = bpass && (always || nsub == 1 || phase_in_window(bodies[b], tm0 + a.st.dt[j]));
+            const unsigned mk = __ballot_sync(0xffffffffu, pass);
+            if (pass) meq[en + __popc(mk & lt)] = (unsigned short)((b << 11) | (j << 5) | lane);
+            en += __popc(mk);
+            if (++j == nsub) {
+              j = 0;
+              ++b;
+            }
+            __syncwarp();
+          }
+          if (en >= 32 || (step == nsteps && en > 0)) {
+            const int nbatch = en < 32 ? en : 32;
+            const bool ev = lane < nbatch;
+            const unsigned it = ev ? meq[lane] : 0u;
+            const int esrc = (int)(it & 31u), ej = (int)((it >> 5) & 63u), eb = (int)(it >> 11);
+            const double tms = __shfl_sync(0xffffffffu, tm0, esrc);
+            const int sls = __shfl_sync(0xffffffffu, sl, esrc);
+            T v = T(0);
+            if (ev) {
+              ++n_kep;
+              v = eval_in_window<T, ORDER, HI, PU>(sbody[sls * nb + eb], sset[sls], &a.tab, tms + a.st.dt[ej], n_ld);
+            }
+            const int tgt = ev ? (esrc * SYS_MB + eb) : (-1 - lane);
+            const unsigned same = __match_any_sync(0xffffffffu, tgt);
+            const int rank = __popc(same & lt);
+            const int maxr = (int)__reduce_max_sync(0xffffffffu, (unsigned)(ev ? rank : 0));
+#pragma unroll 1
+            for (int r = 0; r <= maxr; ++r) {
+              if (ev && rank == r) macc[tgt] = (nsub == 1) ? v : jfma(T(a.st.w[ej]), v, macc[tgt]);
+              __syncwarp();
+            }
+            // keep what did not fit into this batch
+            const int rem = en - nbatch;
+            const unsigned short keep = (lane < rem) ? meq[32 + lane] : (unsigned short)0;
+            __syncwarp();
+            if (lane < rem) meq[lane] = keep;
+            en = rem;
+            __syncwarp();
+          }
+        }
+        if (have) {
+          const int set = set_base + sl;
+#pragma unroll 1
+          for (int bb = 0; bb < nb; ++bb) {
+            const T accb = macc[lane * SYS_MB + bb];
+            if (a.flux) a.flux[((size_t)set * a.n_times + idx) * nb + bb] = accb;
+            total += accb;
+          }
+          if (a.flux_sum) a.flux_sum[(size_t)set * a.n_times + idx] = total;
+        }
+        __syncwarp();
+      } else if (have) {
         const int set = set_base + sl;
         const SetC<T> sc = sset[sl];
         const BodyC<T>* bodies = sbody + sl * nb;
@@ -1148,6 +1243,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   while (spc > 32 && n_tiles * ((n_sets + spc - 1) / spc) < 8 * sms) spc -= 32;
   if (spc > n_sets) spc = n_sets;
   if (n_bodies * spc > 512) spc = (512 / n_bodies) > 0 ? (512 / n_bodies) : 1;
+  // keep the staged records of a group under ~24 KB so that shared memory never limits residency
+  // below the JXP_SYS_MINB CTAs per SM the register budget allows
+  while (spc > 16 && sizeof(BodyC<T>) * (size_t)spc * n_bodies > 24 * 1024) spc -= 16;
   const int64_t n_groups = (n_sets + spc - 1) / spc;
   const int64_t n_units = n_tiles * n_groups;  // CTA-sized pieces of work
   if (n_wtiles > 2000000000LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_system_light_curve: too many time samples");
@@ -1173,10 +1271,14 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   a.tab.order = gl_order;
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
 
+  // multi variant of stage C: double, order 10, <= SYS_MB bodies, more than one evaluation per sample
+  const bool multi = sizeof(T) == 8 && n_u <= 2 && gl_order == 10 && n_bodies <= SYS_MB &&
+                     (int64_t)n_bodies * a.st.n > 1 && !(((flags & JXP_FLAG_NO_WINDOW) != 0) && n_bodies == 1 && a.st.n == 1);
   const size_t smem = sizeof(BodyC<T>) * (size_t)spc * n_bodies + sizeof(SetC<T>) * (size_t)spc +
                       sizeof(double) * (size_t)spc * (threads / 32) +
                       sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32) +
-                      sizeof(T) * (size_t)SYS_QCAP * (threads / 32);
+                      sizeof(T) * (size_t)SYS_QCAP * (threads / 32) +
+                      (multi ? (sizeof(T) * 32 * SYS_MB + sizeof(unsigned short) * 64) * (size_t)(threads / 32) : 0);
   if (smem > 200 * 1024) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: shared memory");
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
@@ -1204,7 +1306,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   } else if (gl_order == 10) {
     if (dense)
       rc = loglike ? launch(k_system<T, 11, true, true>) : launch(k_system<T, 11, false, true>);
-    else if (sizeof(T) == 8 && (int64_t)n_bodies * a.st.n > 1)
+    else if (multi)
       // several flux evaluations per queued sample: the unrolled node loop pays (config 4)
       rc = loglike ? launch(k_system<T, 11, true, false, false, 5>)
                    : launch(k_system<T, 11, false, false, false, 5>);

@@ -463,6 +463,128 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
   s1 = -P0 - (kappa1 - pi) * B(2.0 / 3.0);
 }
 
+// Branch-free solution vector for N independent (b, r) points per thread, double, order 10,
+// l_max <= 2: the same formulas as ld_solution with every `where` of limb_dark.py kept as a
+// select (the reference evaluates both sides too), written statement by statement over the N
+// items so that N dependency chains interleave (see kepler_reduced_n for why that matters).
+// atan2(+0, x) is exactly 0 or pi, so the kappa selects of the scalar version are not needed.
+template <int N, int PU>
+__device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const double (&r_in)[N],
+                                              int lmax, double (&s0)[N], double (&s1)[N],
+                                              double (&s2)[N]) {
+  const double pi = Num<double>::pi;
+  const double eps10 = 10.0 * Num<double>::eps;
+  double b[N], r[N], area[N], k0[N], k1[N], b2[N], r2[N];
+  bool no_occ[N], full_occ[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    b[q] = fabs(b_in[q]);
+    r[q] = fabs(r_in[q]);
+  }
+  // kite_area(r, b, 1) on the original b, limb_dark.py:187-196 (sorted Heron form)
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const bool cond_k = (b[q] > fabs(1.0 - r[q])) && (b[q] < 1.0 + r[q]);
+    double x = r[q], y = b[q], z = 1.0, t;
+    t = (x < y) ? x : y; y = (x < y) ? y : x; x = t;  // x <= y
+    t = (y < z) ? y : z; z = (y < z) ? z : y; y = t;  // z = max
+    t = (x < y) ? x : y; y = (x < y) ? y : x; x = t;  // x <= y <= z
+    const double sq = (x + (y + z)) * (z - (x - y)) * (z + (x - y)) * (x + (y - z));
+    area[q] = cond_k ? sq : 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) area[q] = fsqrt(fmax(area[q], 0.0));
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double b2o = b[q] * b[q];
+    const double factor = (r[q] - 1.0) * (r[q] + 1.0);
+    k0[q] = b2o + factor;
+    k1[q] = b2o - factor;
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) k0[q] = fatan2(area[q], k0[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) k1[q] = fatan2(area[q], k1[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    no_occ[q] = b[q] >= 1.0 + r[q];
+    full_occ[q] = 1.0 + b[q] <= r[q];
+    b[q] = (no_occ[q] || full_occ[q]) ? 1.0 : b[q];  // b_ of limb_dark.py:63
+    b2[q] = b[q] * b[q];
+    r2[q] = r[q] * r[q];
+  }
+  // s0s2, limb_dark.py:111-137
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double bpr = b[q] + r[q];
+    const double onembpr2 = (1.0 + bpr) * (1.0 - bpr);
+    const double eta2 = r2[q] * (r2[q] + b2[q] * 2.0) * 0.5;
+    const double delta = b[q] * r[q] * 4.0;
+    const bool large = onembpr2 + delta > delta;
+    const double s0l = (1.0 - r2[q]) * pi;
+    const double s2l = s0l * 2.0 + (eta2 - 0.5) * (4.0 * pi);
+    const double Alens = k1[q] + r2[q] * k0[q] - area[q] * 0.5;
+    const double s0s = pi - Alens;
+    const double s2s = s0s * 2.0 + (-(pi - k1[q]) + eta2 * k0[q] * 2.0 -
+                                    area[q] * (1.0 + r2[q] * 5.0 + b2[q]) * 0.25) * 2.0;
+    const double s0v = large ? s0l : s0s;
+    const double s2v = large ? s2l : s2s;
+    s0[q] = no_occ[q] ? pi : (full_occ[q] ? 0.0 : s0v);
+    s2[q] = (no_occ[q] || full_occ[q]) ? 0.0 : s2v;
+  }
+  if (lmax < 1) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = 0.0;
+    return;
+  }
+  // l = 1 term of p_integral (limb_dark.py:140-173, 184) over the 5 mirror pairs of nodes
+  double sh[N], ch[N], rng[N], two_br[N], r2pb2[N], acc[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    rng[q] = k0[q] * 0.5;
+    two_br[q] = b[q] * r[q] * 2.0;
+    r2pb2[q] = r2[q] + b2[q];
+    acc[q] = 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) fsincos_q1(rng[q], &sh[q], &ch[q]);
+#pragma unroll PU
+  for (int p = 0; p < 5; ++p) {
+    const double xp = c_gl10[0][5 + p], wp = c_gl10[1][5 + p];
+    double c[2 * N], z2s[2 * N], z[2 * N], t[2 * N];
+    bool dead[2 * N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double sa, ca;
+      fsincos_q1(rng[q] * xp, &sa, &ca);
+      const double t1 = ch[q] * ca;
+      c[2 * q] = fma(-sh[q], sa, t1);
+      c[2 * q + 1] = fma(sh[q], sa, t1);
+    }
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) {
+      const double omz2 = fma(-two_br[m >> 1], c[m], r2pb2[m >> 1]);
+      dead[m] = !((omz2 >= eps10) && (omz2 <= 1.0 - eps10));
+      z2s[m] = dead[m] ? 1.0 : 1.0 - omz2;
+    }
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2s[m]);
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2s[m], frcp_fast(z[m] + 1.0), 1.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const double ra = fma(-b[q], c[2 * q], r[q]) * t[2 * q];
+      const double rb = fma(-b[q], c[2 * q + 1], r[q]) * t[2 * q + 1];
+      acc[q] = fma(wp, (dead[2 * q] ? 0.0 : ra) + (dead[2 * q + 1] ? 0.0 : rb), acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double P0 = (no_occ[q] || full_occ[q]) ? 0.0 : rng[q] * (acc[q] * (r[q] * (2.0 / 3.0)));
+    s1[q] = -P0 - (k1[q] - pi) * (2.0 / 3.0);
+  }
+}
+
 // Normalised Green's-basis coefficients for n_u <= 2, limb_dark.py:42-45, 87-99.
 template <typename S>
 __device__ __forceinline__ void ld_greens(int n_u, S u1, S u2, S& g0, S& g1, S& g2) {
