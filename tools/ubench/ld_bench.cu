@@ -55,6 +55,6 @@ int main() {
 #define RUN_S(PU, MINB) { float ms = timeit([&] { k_scalar<PU, MINB><<<148 * MINB, 128>>>(b, r, o0, n); }); if (PU == 1 && MINB == 8) cudaMemcpy(h0.data(), o0, n * 8, cudaMemcpyDeviceToHost); report("scalar PU" #PU " MINB" #MINB, ms, o0); }
 #define RUN_M(N, PU, MINB) { float ms = timeit([&] { k_multi<N, PU, MINB><<<148 * MINB, 128>>>(b, r, o1, n); }); report("multi N" #N " PU" #PU " MINB" #MINB, ms, o1); }
   RUN_S(1, 8) RUN_S(1, 5) RUN_S(5, 5) RUN_S(5, 4)
-  RUN_M(1, 1, 8) RUN_M(1, 5, 5) RUN_M(2, 1, 5) RUN_M(2, 5, 4) RUN_M(2, 1, 4) RUN_M(2, 5, 3) RUN_M(2, 1, 8) RUN_M(4, 1, 2) RUN_M(3, 1, 3)
+  RUN_M(1, 5, 5) RUN_M(2, 5, 4)
   return 0;
 }
