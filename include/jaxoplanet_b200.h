@@ -197,6 +197,39 @@ int jxp_transit_partials_f32(const double* theta, int32_t n_sets, const double* 
                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K6  light_curves.limb_dark.light_curve(TransitOrbit | TTVOrbit, u)(t)
+ *     src/jaxoplanet/orbits/transit.py:7-107 (linear motion across the disk, no Kepler solve),
+ *     src/jaxoplanet/orbits/ttv.py:46-225 (searchsorted time warp around each observed transit),
+ *     src/jaxoplanet/light_curves/limb_dark.py:49-60, src/jaxoplanet/core/limb_dark.py:19-196
+ * planets: [n_planets][JXP_TO_NFIELDS] (device) -- the fields TransitOrbit.__init__ derives.
+ * TTV tables (device; bin_edges == NULL means a plain TransitOrbit): for planet p the edges
+ * bin_edges[bin_offsets[p] .. bin_offsets[p+1]) and the values
+ * bin_values[bin_offsets[p] + p .. bin_offsets[p+1] + p + 1) (one more value than edges) are the
+ * `_bin_edges` / `_bin_values` of ttv.py:21-33; ttv_t0[p] is the linear reference time (`t0`).
+ * u_host: n_u limb-darkening coefficients in HOST memory (one law for all planets, as in the
+ * reference).  flux: [n_times][n_planets] (t.shape + orbit.shape), flux - 1 per planet.
+ * ---------------------------------------------------------------------------------- */
+enum {
+  JXP_TO_PERIOD = 0,
+  JXP_TO_TIME_TRANSIT = 1,
+  JXP_TO_SPEED = 2,
+  JXP_TO_DURATION = 3,
+  JXP_TO_IMPACT_PARAM = 4,
+  JXP_TO_RADIUS_RATIO = 5,
+  JXP_TO_NFIELDS = 6
+};
+int jxp_transit_orbit_light_curve_f64(const double* planets, int32_t n_planets,
+                                      const double* bin_edges, const double* bin_values,
+                                      const int32_t* bin_offsets, const double* ttv_t0,
+                                      const double* u_host, int32_t n_u, const double* t,
+                                      int64_t n_times, int32_t gl_order, double* flux, void* stream);
+int jxp_transit_orbit_light_curve_f32(const double* planets, int32_t n_planets,
+                                      const double* bin_edges, const double* bin_values,
+                                      const int32_t* bin_offsets, const double* ttv_t0,
+                                      const double* u_host, int32_t n_u, const double* t,
+                                      int64_t n_times, int32_t gl_order, float* flux, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper (not part of the reference surface): a dependent-free DFMA (or FFMA)
  * loop that saturates the FP64 (FP32) pipe; bench.py times it with CUDA events to obtain the
  * FP64/FP32 roofline denominator MEASURED_PEAKS.json lacks.  Executes

@@ -16,6 +16,7 @@ JXP_BODY_NFIELDS = 12
 JXP_NTHETA = 8
 JXP_FLAG_NO_WINDOW = 1
 JXP_FLAG_COUNT = 2
+JXP_TO_NFIELDS = 6
 
 (BODY_PERIOD, BODY_TIME_TRANSIT, BODY_TIME_REF, BODY_ECC, BODY_COS_OMEGA, BODY_SIN_OMEGA,
  BODY_COS_INCL, BODY_SIN_INCL, BODY_SEMIMAJOR, BODY_CENTRAL_RADIUS, BODY_RADIUS,
@@ -65,6 +66,8 @@ SIGNATURES = {
         [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,
          _p, _sz, _p],
     ),
+    "jxp_transit_orbit_light_curve_f64": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
+    "jxp_transit_orbit_light_curve_f32": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),
     "jxp_peak_fma_f32": (C.c_int, [_p, _i32, _i32, _i64, _p]),
 }

@@ -1,0 +1,179 @@
+// K6: light curve of a TransitOrbit / TTVOrbit (orbits parameterised by the transit signal).
+//
+// Reference path, fused into one pass over (time sample x planet):
+//   TTVOrbit._warp_times            src/jaxoplanet/orbits/ttv.py:194-214   (searchsorted time warp)
+//   TransitOrbit.relative_position  src/jaxoplanet/orbits/transit.py:93-107 (mod, linear motion)
+//   light_curve(orbit, u)(t)        src/jaxoplanet/light_curves/limb_dark.py:49-60
+//   core.limb_dark.light_curve      src/jaxoplanet/core/limb_dark.py:19-196
+// Lanes are consecutive time samples, so in-transit samples (contiguous runs in time) fill whole
+// warps and out-of-transit warps skip the flux code: no compaction queue is needed here.
+#include "../../include/jaxoplanet_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "jxp_host.h"
+#include "jxp_math.cuh"
+
+using namespace jxp;
+using namespace jxph;
+
+namespace {
+
+template <typename T>
+struct ToArgs {
+  const double* planets;  // [n_planets][JXP_TO_NFIELDS]
+  int n_planets;
+  const double* bin_edges;   // concatenated over planets, or nullptr (no TTVs)
+  const double* bin_values;  // concatenated, one more entry per planet than bin_edges
+  const int* bin_offsets;    // [n_planets + 1] offsets into bin_edges
+  const double* ttv_t0;      // [n_planets] linear reference transit time (ttv.py:206-208)
+  const double* t;
+  int64_t n_times;
+  T g[JXP_MAX_LD_COEFFS + 1];
+  int lmax;
+  T* flux;  // [n_times][n_planets]
+  GLTable tab;
+};
+
+// jnp.mod(a, p) for p > 0: exact fmod, result moved into [0, p)  (transit.py:102)
+__device__ __forceinline__ double pymod(double a, double p) {
+  double r = fmod(a, p);
+  if (r != 0.0 && r < 0.0) r += p;
+  return r;
+}
+
+template <typename T, int ORDER, bool HI>
+__global__ void __launch_bounds__(256) k_transit_orbit(const __grid_constant__ ToArgs<T> a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_times; i += stride) {
+    const double ti = a.t[i];
+    for (int p = 0; p < a.n_planets; ++p) {
+      const double* q = a.planets + (size_t)p * JXP_TO_NFIELDS;
+      const double period = q[JXP_TO_PERIOD], t0 = q[JXP_TO_TIME_TRANSIT];
+      double tw = ti;
+      if (a.bin_edges) {
+        // jnp.searchsorted(edges, t) (side="left"): first index with edges[idx] >= t
+        const int lo0 = a.bin_offsets[p], hi0 = a.bin_offsets[p + 1];
+        int lo = lo0, hi = hi0;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (a.bin_edges[mid] < ti) lo = mid + 1; else hi = mid;
+        }
+        const double dt = a.bin_values[(lo - lo0) + lo0 + p];  // values: one extra entry per planet
+        tw = ti - (dt - a.ttv_t0[p]);
+      }
+      const double half = 0.5 * period;
+      const double ref_time = t0 - half;
+      const double dt = pymod(tw - ref_time, period) - half;
+      T out = T(0);
+      if (fabs(dt) < 0.5 * q[JXP_TO_DURATION]) {  // z > 0
+        const double x = q[JXP_TO_SPEED] * dt;
+        const double y = q[JXP_TO_IMPACT_PARAM];
+        const T b = T(sqrt(x * x + y * y));  // central_radius = 1
+        const T r = T(q[JXP_TO_RADIUS_RATIO]);
+        T s0, s1, s2, shi[6];
+        ld_solution<T, ORDER, HI>(b, r, a.lmax, &a.tab, s0, s1, s2, shi);
+        T f = ld_combine(a.lmax < 2 ? a.lmax : 2, s0, s1, s2, a.g[0], a.g[1], a.g[2]);
+        if (HI) {
+#pragma unroll
+          for (int n = 3; n <= 8; ++n)
+            if (n <= a.lmax) f = jfma(shi[n - 3], a.g[n], f);
+        }
+        out = f;
+      }
+      a.flux[(size_t)i * a.n_planets + p] = out;
+    }
+  }
+}
+
+template <typename T>
+int launch_transit_orbit(const double* planets, int32_t n_planets, const double* bin_edges,
+                         const double* bin_values, const int32_t* bin_offsets, const double* ttv_t0,
+                         const double* u_host, int32_t n_u, const double* t, int64_t n_times,
+                         int32_t gl_order, T* flux, void* stream) {
+  if (n_planets < 0 || n_times < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_orbit_light_curve: negative size");
+  if (n_u < 0 || n_u > JXP_MAX_LD_COEFFS)
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_transit_orbit_light_curve: n_u = %d outside 0..%d", n_u, JXP_MAX_LD_COEFFS);
+  if (gl_order < 1 || gl_order > JXP_MAX_GL_ORDER)
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_transit_orbit_light_curve: order = %d outside 1..%d", gl_order,
+                JXP_MAX_GL_ORDER);
+  if (n_planets == 0 || n_times == 0) return JXP_OK;
+  if (!planets || !t || !flux || (n_u > 0 && !u_host))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_transit_orbit_light_curve: null planets/u/t/flux");
+  if (bin_edges && (!bin_values || !bin_offsets || !ttv_t0))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_transit_orbit_light_curve: TTV tables need edges, values, offsets and t0");
+  ToArgs<T> a;
+  a.planets = planets;
+  a.n_planets = n_planets;
+  a.bin_edges = bin_edges;
+  a.bin_values = bin_values;
+  a.bin_offsets = bin_offsets;
+  a.ttv_t0 = ttv_t0;
+  a.t = t;
+  a.n_times = n_times;
+  a.lmax = n_u;
+  a.flux = flux;
+  a.tab.order = gl_order;
+  if (gl_order != 10) gl_table_host(gl_order, a.tab);
+  // Green's-basis coefficients on the host (limb_dark.py:42-45, 87-99): u is a host array here,
+  // one law for all planets as in the reference
+  {
+    double g[JXP_MAX_LD_COEFFS + 1] = {0};
+    const double pi = 3.141592653589793238462643383279502884;
+    if (n_u == 0) {
+      g[0] = 1.0 / pi;
+    } else {
+      const int size = n_u + 1;
+      double pcoef[JXP_MAX_LD_COEFFS + 1], gg[JXP_MAX_LD_COEFFS + 5] = {0};
+      for (int n = 0; n < size; ++n) {
+        double arg = 0.0, binom = 1.0;
+        for (int i = n; i < size; ++i) {
+          const double ui = (i == 0) ? -1.0 : u_host[i - 1];
+          arg += ui * binom;
+          binom = binom * (double)(i + 1) / (double)(i + 1 - n);
+        }
+        pcoef[n] = (n % 2 == 0) ? -arg : arg;
+      }
+      for (int n = size - 1; n > 1; --n) gg[n] = pcoef[n] / (double)(n + 2) + gg[n + 2];
+      if (size > 1) gg[1] = pcoef[1] + 3.0 * gg[3];
+      gg[0] = pcoef[0] + 2.0 * gg[2];
+      const double norm = pi * (gg[0] + gg[1] / 1.5);
+      for (int n = 0; n < size; ++n) g[n] = gg[n] / norm;
+    }
+    for (int n = 0; n <= JXP_MAX_LD_COEFFS; ++n) a.g[n] = T(g[n]);
+  }
+  const int threads = 256;
+  int64_t blocks = (n_times + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool hi = n_u > 2;
+  if (gl_order == 10) {
+    if (hi) k_transit_orbit<T, 10, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+    else k_transit_orbit<T, 10, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  } else {
+    if (hi) k_transit_orbit<T, 0, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+    else k_transit_orbit<T, 0, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  }
+  return check_launch("jxp_transit_orbit_light_curve");
+}
+}  // namespace
+
+extern "C" int jxp_transit_orbit_light_curve_f64(const double* planets, int32_t n_planets,
+                                                 const double* bin_edges, const double* bin_values,
+                                                 const int32_t* bin_offsets, const double* ttv_t0,
+                                                 const double* u_host, int32_t n_u, const double* t,
+                                                 int64_t n_times, int32_t gl_order, double* flux,
+                                                 void* stream) {
+  return launch_transit_orbit<double>(planets, n_planets, bin_edges, bin_values, bin_offsets, ttv_t0,
+                                      u_host, n_u, t, n_times, gl_order, flux, stream);
+}
+extern "C" int jxp_transit_orbit_light_curve_f32(const double* planets, int32_t n_planets,
+                                                 const double* bin_edges, const double* bin_values,
+                                                 const int32_t* bin_offsets, const double* ttv_t0,
+                                                 const double* u_host, int32_t n_u, const double* t,
+                                                 int64_t n_times, int32_t gl_order, float* flux,
+                                                 void* stream) {
+  return launch_transit_orbit<float>(planets, n_planets, bin_edges, bin_values, bin_offsets, ttv_t0,
+                                     u_host, n_u, t, n_times, gl_order, flux, stream);
+}

@@ -5,7 +5,8 @@ For a Keplerian ``System`` the whole chain time -> mean anomaly -> Kepler -> sky
 -> b -> limb-darkened flux (and optionally exposure integration and a Gaussian
 log-likelihood) runs in ONE fused CUDA kernel (jxp_system_light_curve_*).  Any other
 object satisfying the ``LightCurveOrbit`` protocol (src/jaxoplanet/proto.py:8-20) goes
-through its own ``relative_position`` and the K2 kernel.
+through its own ``relative_position`` and the K2 kernel; ``TransitOrbit`` / ``TTVOrbit`` have their own
+fused kernel (jxp_transit_orbit_light_curve_*).
 """
 
 from __future__ import annotations
@@ -19,6 +20,7 @@ from jaxoplanet_b200 import _array as A
 from jaxoplanet_b200 import _lib, constants
 from jaxoplanet_b200.core.limb_dark import light_curve as _limb_dark_light_curve
 from jaxoplanet_b200.orbits.keplerian import System
+from jaxoplanet_b200.orbits.transit import TransitOrbit
 
 __all__ = ["light_curve", "log_likelihood"]
 
@@ -172,6 +174,37 @@ def light_curve(orbit, *u, order: int = 10):
 
         light_curve_impl._jxp_spec = spec
         return light_curve_impl
+
+    if isinstance(orbit, TransitOrbit):
+        # TransitOrbit / TTVOrbit: time warp + linear motion + flux fused in k_transit_orbit (K6)
+        def light_curve_transit(time):
+            dt = A.result_dtype(time)
+            td = A.to_dev(time, torch.float64)
+            n_p = int(np.prod(orbit.shape)) if len(orbit.shape) else 1
+            fields = [orbit.period, orbit.time_transit, orbit.speed, orbit.duration, orbit.impact_param,
+                      orbit.radius_ratio]
+            planets = torch.stack([torch.broadcast_to(torch.as_tensor(f, dtype=torch.float64).reshape(-1), (n_p,))
+                                   for f in fields], dim=-1)
+            planets = A.to_dev(planets, torch.float64)
+            u_host = np.ascontiguousarray(ld_u.detach().cpu().numpy() if isinstance(ld_u, torch.Tensor) else ld_u,
+                                          dtype=np.float64)
+            if u_host.ndim != 1:
+                raise ValueError("TransitOrbit light curves take one limb-darkening law (u.ndim == 1)")
+            tabs = [None, None, None, None]
+            if hasattr(orbit, "_ttv_tables"):
+                e, v, off, t0 = orbit._ttv_tables()
+                tabs = [A.to_dev(e, torch.float64), A.to_dev(v, torch.float64),
+                        torch.as_tensor(off, dtype=torch.int32, device=A.device()), A.to_dev(t0, torch.float64)]
+            flux = torch.empty(tuple(td.shape) + (n_p,), dtype=dt, device=td.device)
+            name = "jxp_transit_orbit_light_curve_f64" if dt == torch.float64 else "jxp_transit_orbit_light_curve_f32"
+            _lib.call(name, planets.data_ptr(), n_p, A.ptr(tabs[0]), A.ptr(tabs[1]), A.ptr(tabs[2]), A.ptr(tabs[3]),
+                      u_host.ctypes.data, int(u_host.shape[0]), td.data_ptr(), td.numel(), int(order),
+                      flux.data_ptr(), A.stream_ptr())
+            if len(orbit.shape) == 0:
+                flux = flux.reshape(td.shape)
+            return A.like_input(flux, time)
+
+        return light_curve_transit
 
     def light_curve_generic(time):
         # light_curves/limb_dark.py:49-60 for a foreign orbit object (LightCurveOrbit protocol)

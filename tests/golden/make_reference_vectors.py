@@ -28,6 +28,40 @@ KW_CIRC = [
 ]
 
 
+def main_ttv():
+    """TTVOrbit (orbits/ttv.py:46-225) -> tests/golden/reference_ttv_v1.npz (kept separate so that
+    reference_v1.npz does not have to be regenerated)."""
+    R = reference_shim.load()
+    rng = np.random.default_rng(20261021)
+    out = {}
+    us = np.array([0.3, 0.2])
+    with np.errstate(all="ignore"):
+        # two planets given by observed transit times (linear fit + residuals), ttv.py CASE 1
+        tt0 = 1.3 + 3.1 * np.arange(9) + 0.02 * np.sin(np.arange(9) * 0.9)
+        tt1 = 0.4 + 7.45 * np.arange(4) + np.array([0.01, -0.015, 0.02, -0.005])
+        orb = R.ttv.TTVOrbit(duration=np.array([0.15, 0.25]), impact_param=np.array([0.2, 0.55]),
+                             radius_ratio=np.array([0.08, 0.12]), transit_times=(tt0, tt1))
+        t = np.sort(np.concatenate([np.linspace(-1.0, 29.0, 700),
+                                    tt0[rng.integers(0, 9, 500)] + rng.uniform(-0.12, 0.12, 500),
+                                    tt1[rng.integers(0, 4, 400)] + rng.uniform(-0.2, 0.2, 400)]))
+        out.update(ttv_tt0=tt0, ttv_tt1=tt1, ttv_t=t, ttv_u=us,
+                   ttv_flux=np.asarray(R.lc_limb_dark.light_curve(orb, us)(t)),
+                   ttv_t0=np.asarray(orb.t0), ttv_period=np.asarray(orb.ttv_period),
+                   ttv_res0=np.asarray(orb.ttvs[0]), ttv_res1=np.asarray(orb.ttvs[1]))
+        # one planet given by ttvs + period + time_transit, CASE 2, with a speed instead of a duration
+        ttvs = 0.03 * np.cos(np.arange(7) * 1.1)
+        orb2 = R.ttv.TTVOrbit(period=4.2, time_transit=0.7, speed=9.0, impact_param=0.4, radius_ratio=0.1, ttvs=(ttvs,))
+        t2 = np.sort(np.concatenate([np.linspace(-2.0, 28.0, 400),
+                                     np.asarray(orb2.transit_times[0])[rng.integers(0, 7, 500)] + rng.uniform(-0.15, 0.15, 500)]))
+        out.update(ttv2_ttvs=ttvs, ttv2_t=t2, ttv2_flux=np.asarray(R.lc_limb_dark.light_curve(orb2, us)(t2)),
+                   ttv2_transit_times=np.asarray(orb2.transit_times[0]))
+        exp = R.ttv.compute_expected_transit_times(0.0, 30.0, np.array([3.1, 7.45]), np.array([1.3, 0.4]))
+        out.update(ttv_expected0=np.asarray(exp[0]), ttv_expected1=np.asarray(exp[1]))
+    path = os.path.join(HERE, "reference_ttv_v1.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes;", len(out), "arrays; in transit:", np.mean(out["ttv_flux"] != 0))
+
+
 def main():
     R = reference_shim.load()
     K = R.keplerian
@@ -143,4 +177,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ttv":
+        main_ttv()
+    else:
+        main()

@@ -40,12 +40,16 @@ def load():
             sys.modules[f"jaxoplanet.{sub}"] = m
             setattr(pkg, sub, m)
     ns = types.SimpleNamespace()
+    if not hasattr(sys.modules["jaxoplanet.orbits"], "TransitOrbit"):
+        # ttv.py does `from jaxoplanet.orbits import TransitOrbit` (normally set by the package __init__)
+        sys.modules["jaxoplanet.orbits"].TransitOrbit = importlib.import_module("jaxoplanet.orbits.transit").TransitOrbit
     for name, mod in (
         ("kepler", "jaxoplanet.core.kepler"),
         ("limb_dark", "jaxoplanet.core.limb_dark"),
         ("utils", "jaxoplanet.utils"),
         ("keplerian", "jaxoplanet.orbits.keplerian"),
         ("transit", "jaxoplanet.orbits.transit"),
+        ("ttv", "jaxoplanet.orbits.ttv"),
         ("lc_limb_dark", "jaxoplanet.light_curves.limb_dark"),
         ("transforms", "jaxoplanet.light_curves.transforms"),
     ):

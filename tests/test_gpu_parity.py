@@ -810,7 +810,7 @@ def test_transit_orbit_depth_and_system_equivalence():
     orb2 = TransitOrbit(period=np.array([1.0, 2.0]), radius_ratio=np.array([0.1, 0.05]), duration=np.array([0.1, 0.2]),
                         impact_param=np.array([0.1, 0.3]))
     t = np.linspace(-0.3, 0.3, 501)
-    lc2 = limb_dark_light_curve(orb2, [0.3, 0.2])(t[:, None])
+    lc2 = limb_dark_light_curve(orb2, [0.3, 0.2])(t)
     assert lc2.shape == (501, 2)
     x = orb2.speed.numpy() * ((t[:, None] + 0.5 * orb2.period.numpy()) % orb2.period.numpy() - 0.5 * orb2.period.numpy())
     b = np.sqrt(x**2 + orb2.impact_param.numpy() ** 2)

@@ -234,6 +234,56 @@ def test_cuda_transit_orbit_and_interpolate_match_reference_vectors():
     assert _flux_err(fi(G["itp_t"]), G["itp_flux"]) <= 1e-12
 
 
+# ----------------------------------------------------------------------------- TTVOrbit (orbits/ttv.py)
+GT = np.load(os.path.join(HERE, "golden", "reference_ttv_v1.npz"))
+
+
+def test_ttv_orbit_host_setup_matches_reference():
+    """Linear ephemeris fit, residuals, bins, expected transit times: host-side NumPy, no GPU needed."""
+    from jaxoplanet_b200.orbits.ttv import TTVOrbit, compute_expected_transit_times
+
+    orb = TTVOrbit(duration=np.array([0.15, 0.25]), impact_param=np.array([0.2, 0.55]),
+                   radius_ratio=np.array([0.08, 0.12]), transit_times=(GT["ttv_tt0"], GT["ttv_tt1"]))
+    np.testing.assert_allclose(orb.t0, GT["ttv_t0"], rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(orb.ttv_period, GT["ttv_period"], rtol=1e-14)
+    np.testing.assert_allclose(orb.ttvs[0], GT["ttv_res0"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(orb.ttvs[1], GT["ttv_res1"], rtol=0, atol=1e-13)
+    orb2 = TTVOrbit(period=4.2, time_transit=0.7, speed=9.0, impact_param=0.4, radius_ratio=0.1, ttvs=(GT["ttv2_ttvs"],))
+    np.testing.assert_allclose(orb2.transit_times[0], GT["ttv2_transit_times"], rtol=1e-15, atol=1e-15)
+    exp = compute_expected_transit_times(0.0, 30.0, np.array([3.1, 7.45]), np.array([1.3, 0.4]))
+    np.testing.assert_array_equal(exp[0], GT["ttv_expected0"])
+    np.testing.assert_array_equal(exp[1], GT["ttv_expected1"])
+    with pytest.raises(ValueError, match="Supply either ttvs or transit_times, not both."):
+        TTVOrbit(period=1.0, duration=0.1, ttvs=(np.zeros(3),), transit_times=(np.arange(3.0),))
+    with pytest.raises(ValueError, match="You must supply either transit_times or ttvs."):
+        TTVOrbit(period=1.0, duration=0.1)
+    with pytest.raises(ValueError, match="When supplying ttvs, period must be provided."):
+        TTVOrbit(duration=0.1, ttvs=(np.zeros(3),))
+
+
+@pytest.mark.gpu
+def test_cuda_ttv_orbit_matches_reference_vectors():
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve
+    from jaxoplanet_b200.orbits import TTVOrbit
+
+    u = GT["ttv_u"]
+    orb = TTVOrbit(duration=np.array([0.15, 0.25]), impact_param=np.array([0.2, 0.55]),
+                   radius_ratio=np.array([0.08, 0.12]), transit_times=(GT["ttv_tt0"], GT["ttv_tt1"]))
+    got = limb_dark_light_curve(orb, u)(GT["ttv_t"])
+    assert np.mean(GT["ttv_flux"] != 0) > 0.15
+    assert _flux_err(got, GT["ttv_flux"]) <= 1e-12
+    orb2 = TTVOrbit(period=4.2, time_transit=0.7, speed=9.0, impact_param=0.4, radius_ratio=0.1, ttvs=(GT["ttv2_ttvs"],))
+    got2 = limb_dark_light_curve(orb2, u)(GT["ttv2_t"])
+    assert _flux_err(got2, GT["ttv2_flux"]) <= 1e-12
+    # the orbit protocol path (relative_position + K2) agrees with the fused kernel
+    x, y, z = orb.relative_position(GT["ttv_t"])
+    b = np.sqrt(x**2 + y**2)
+    from jaxoplanet_b200.core.limb_dark import light_curve as core_lc
+
+    want = np.where(z > 0, core_lc(u, b, np.broadcast_to(np.array([0.08, 0.12]), b.shape).copy()), 0.0)
+    assert _flux_err(got, want) <= 1e-12
+
+
 # ----------------------------------------------------------------------------- build container only
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/jaxoplanet"), reason="reference checkout only exists in the build container")
 def test_live_reference_source_on_shim_agrees_with_oracle_on_fresh_inputs():
