@@ -230,6 +230,21 @@ int jxp_transit_orbit_light_curve_f32(const double* planets, int32_t n_planets,
                                       int64_t n_times, int32_t gl_order, float* flux, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K7  the per-time half of transforms.interpolate(func, period=, time_transit=, num_samples=,
+ *     duration=)(t): src/jaxoplanet/light_curves/transforms.py:163-183, i.e.
+ *     jnp.interp(wrapped(t), time_grid, flux_grid, period=period).
+ * xp: [n] the time grid reduced mod period, sorted and extended by one wrapped point on each
+ * side (what jnp.interp builds internally); fp: [n][n_cols] the pre-computed flux at those
+ * points (n_cols = number of bodies); out: [n_times][n_cols].  All device pointers.
+ * ---------------------------------------------------------------------------------- */
+int jxp_interp_periodic_f64(const double* xp, const double* fp, int32_t n, int32_t n_cols,
+                            double period, double time_transit, const double* t, int64_t n_times,
+                            double* out, void* stream);
+int jxp_interp_periodic_f32(const double* xp, const float* fp, int32_t n, int32_t n_cols,
+                            double period, double time_transit, const double* t, int64_t n_times,
+                            float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper (not part of the reference surface): a dependent-free DFMA (or FFMA)
  * loop that saturates the FP64 (FP32) pipe; bench.py times it with CUDA events to obtain the
  * FP64/FP32 roofline denominator MEASURED_PEAKS.json lacks.  Executes

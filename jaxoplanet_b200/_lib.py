@@ -68,6 +68,8 @@ SIGNATURES = {
     ),
     "jxp_transit_orbit_light_curve_f64": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_transit_orbit_light_curve_f32": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
+    "jxp_interp_periodic_f64": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
+    "jxp_interp_periodic_f32": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),
     "jxp_peak_fma_f32": (C.c_int, [_p, _i32, _i32, _i64, _p]),
 }

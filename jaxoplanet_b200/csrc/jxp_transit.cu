@@ -159,6 +159,63 @@ int launch_transit_orbit(const double* planets, int32_t n_planets, const double*
 }
 }  // namespace
 
+// K7: periodic linear interpolation of a pre-computed light curve, the per-time half of
+// transforms.interpolate (src/jaxoplanet/light_curves/transforms.py:163-183) with the semantics of
+// jnp.interp(x, xp, fp, period=period): xp is the host-prepared table (reduced mod period, sorted,
+// extended by one wrapped point on each side), fp[n][n_cols] its values.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_interp_periodic(const double* __restrict__ xp, const T* __restrict__ fp, int n, int n_cols, double period,
+                  double time_transit, const double* __restrict__ t, int64_t n_times, T* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double eps = 2.220446049250313e-16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_times; i += stride) {
+    // transforms.py:167-171, then the `x % period` of jnp.interp
+    const double tw = pymod(t[i] - time_transit + 0.5 * period, period) + 0.5 * period + time_transit;
+    const double x = pymod(tw, period);
+    int lo = 0, hi = n;  // searchsorted(xp, x, side="right")
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (xp[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    int j = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+    const double x0 = xp[j - 1], dx = xp[j] - x0, delta = x - x0;
+    const bool flat = fabs(dx) <= eps;
+    const double w = flat ? 0.0 : delta / dx;
+    for (int c = 0; c < n_cols; ++c) {
+      const T f0 = fp[(size_t)(j - 1) * n_cols + c], f1 = fp[(size_t)j * n_cols + c];
+      out[(size_t)i * n_cols + c] = flat ? f0 : T(f0 + T(w) * (f1 - f0));
+    }
+  }
+}
+
+template <typename T>
+static int launch_interp(const double* xp, const T* fp, int32_t n, int32_t n_cols, double period,
+                         double time_transit, const double* t, int64_t n_times, T* out, void* stream) {
+  if (n < 2 || n_cols < 1 || n_times < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_interp_periodic: bad sizes");
+  if (!(period > 0.0)) return fail(JXP_ERR_BAD_SHAPE, "jxp_interp_periodic: period must be positive");
+  if (n_times == 0) return JXP_OK;
+  if (!xp || !fp || !t || !out) return fail(JXP_ERR_NULL_POINTER, "jxp_interp_periodic: null pointer");
+  const int threads = 256;
+  int64_t blocks = (n_times + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  k_interp_periodic<T><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(xp, fp, n, n_cols, period,
+                                                                            time_transit, t, n_times, out);
+  return check_launch("jxp_interp_periodic");
+}
+
+extern "C" int jxp_interp_periodic_f64(const double* xp, const double* fp, int32_t n, int32_t n_cols,
+                                       double period, double time_transit, const double* t,
+                                       int64_t n_times, double* out, void* stream) {
+  return launch_interp<double>(xp, fp, n, n_cols, period, time_transit, t, n_times, out, stream);
+}
+extern "C" int jxp_interp_periodic_f32(const double* xp, const float* fp, int32_t n, int32_t n_cols,
+                                       double period, double time_transit, const double* t,
+                                       int64_t n_times, float* out, void* stream) {
+  return launch_interp<float>(xp, fp, n, n_cols, period, time_transit, t, n_times, out, stream);
+}
+
 extern "C" int jxp_transit_orbit_light_curve_f64(const double* planets, int32_t n_planets,
                                                  const double* bin_edges, const double* bin_values,
                                                  const int32_t* bin_offsets, const double* ttv_t0,

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from jaxoplanet_b200 import _array as A
+from jaxoplanet_b200 import _lib
 
 __all__ = ["integrate", "interpolate"]
 
@@ -85,8 +86,10 @@ def integrate(func, exposure_time=None, order: int = 0, num_samples: int = 7):
 def interpolate(func, *, period, time_transit, num_samples: int, duration=None, args=(), kwargs=None):
     """Pre-compute ``func`` on a grid around the transit and linearly interpolate it at the
     (period-wrapped) requested times: drop-in for src/jaxoplanet/light_curves/transforms.py:119-185
-    (``jnp.interp(..., period=period)`` semantics).  The grid evaluation runs in the CUDA path; the
-    interpolation is a host-side NumPy lerp over the small pre-computed table."""
+    (``jnp.interp(..., period=period)`` semantics).  The grid evaluation runs in the fused CUDA path;
+    the table jnp.interp builds (grid reduced mod period, sorted, one wrapped point added on each side)
+    is prepared once here, and every call evaluates it on the device (kernel K7,
+    ``jxp_interp_periodic_*``)."""
     kwargs = kwargs or {}
     period = float(period)
     time_transit = float(time_transit)
@@ -94,19 +97,28 @@ def interpolate(func, *, period, time_transit, num_samples: int, duration=None, 
         duration = period
     time_grid = time_transit + float(duration) * np.linspace(-0.5, 0.5, int(num_samples))
     flux_grid = func(time_grid, *args, **kwargs)
-    flux_grid = flux_grid.detach().cpu().numpy() if isinstance(flux_grid, torch.Tensor) else np.asarray(flux_grid)
+    grid_dtype = flux_grid.dtype if isinstance(flux_grid, torch.Tensor) else A.result_dtype(np.asarray(flux_grid))
+    flux_np = flux_grid.detach().cpu().numpy() if isinstance(flux_grid, torch.Tensor) else np.asarray(flux_grid)
+    cols_shape = flux_np.shape[1:]
+    flat = flux_np.reshape(flux_np.shape[0], -1)
+    xp = np.mod(time_grid, period)
+    order = np.argsort(xp, kind="stable")
+    xp = xp[order]
+    fp = flat[order]
+    xp = np.concatenate([xp[-1:] - period, xp, xp[:1] + period])
+    fp = np.concatenate([fp[-1:], fp, fp[:1]])
+    xp_d = A.to_dev(xp, torch.float64)
+    fp_d = A.to_dev(fp, grid_dtype)
 
     @wraps(func)
     def wrapped(time, *a, **k):
         del a, k
-        tnp = time.detach().cpu().numpy() if isinstance(time, torch.Tensor) else np.asarray(time, dtype=np.float64)
-        wrapped_t = np.mod(tnp - time_transit + 0.5 * period, period) + 0.5 * period + time_transit
-        # jnp.interp with period: xp and x are wrapped to [0, period) and xp sorted (numpy does the same)
-        flat = flux_grid.reshape(flux_grid.shape[0], -1)
-        cols = [np.interp(wrapped_t.ravel(), time_grid, flat[:, j], period=period) for j in range(flat.shape[1])]
-        out = np.stack(cols, -1).reshape(tnp.shape + flux_grid.shape[1:])
-        if isinstance(time, torch.Tensor):
-            return torch.as_tensor(out, device=time.device)
-        return out
+        td = A.to_dev(time, torch.float64)
+        out = torch.empty(tuple(td.shape) + (fp_d.shape[1],), dtype=grid_dtype, device=td.device)
+        name = "jxp_interp_periodic_f64" if grid_dtype == torch.float64 else "jxp_interp_periodic_f32"
+        _lib.call(name, xp_d.data_ptr(), fp_d.data_ptr(), int(xp_d.shape[0]), int(fp_d.shape[1]), period,
+                  time_transit, td.data_ptr(), td.numel(), out.data_ptr(), A.stream_ptr())
+        out = out.reshape(tuple(td.shape) + tuple(cols_shape))
+        return A.like_input(out, time)
 
     return wrapped
