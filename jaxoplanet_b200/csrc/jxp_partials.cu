@@ -233,8 +233,11 @@ struct TrArgs {
 // drained 32 in-window samples at a time through ONE instance of the dual-number code.
 // Every zero row is one fully coalesced warp store (256 B in f64).
 constexpr int TR_QCAP = 128;
+// 3 CTAs/SM = 168 registers: with 128 the dual-number code spills (100 B stores / 124 B loads per
+// thread) and the local-memory traffic competes with the 59 GB row-store stream (config 5: 11.7 ms;
+// 96 registers 13.3 ms; 168 registers 11.15 ms; 200 registers, no spill at all, 12.4 ms)
 #ifndef JXP_TR_MINB
-#define JXP_TR_MINB 4
+#define JXP_TR_MINB 3
 #endif
 template <typename T, int ORDER, bool LOGLIKE>
 __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __grid_constant__ TrArgs<T> a) {
