@@ -420,20 +420,11 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     }
     acc = accp * two_r_3;
   } else {
-  const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
-  const int order = GL<ORDER>::n(tab);
-#pragma unroll(ORDER == 10 ? 10 : 2)
-  for (int i = 0; i < (ORDER == 10 ? 10 : order); ++i) {
-    const B xi = B(GL<ORDER>::x(i, tab));
-    const B wi = B(GL<ORDER>::w(i, tab));
-    S c;
-    if (const_nodes)
-      c = S(B(GL<ORDER>::cpi(i)));
-    else
-      c = jcos_node(rng * xi + kappa0 * B(0.5));
-    // limb_dark.py:160-172.  max(0, .) only matters for the guard below (a negative value is
-    // < 10 eps and the term is forced to 0 either way), so the primal path skips it; the dual
-    // path keeps it for the derivative.  z^2 < 10 eps  <=>  1 - z^2 > 1 - 10 eps exactly.
+  // one node of limb_dark.py:160-172 (and :149-153, 175-182 when HI), given c = cos of its angle
+  auto node_term = [&](const S& c, B wi) {
+    // max(0, .) only matters for the guard below (a negative value is < 10 eps and the term is
+    // forced to 0 either way), so the primal path skips it; the dual path keeps it for the
+    // derivative.  z^2 < 10 eps  <=>  1 - z^2 > 1 - 10 eps exactly.
     const S omz2 = jclamp0_lazy(r2pb2 - two_br * c);
     const bool dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
     // the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0 where z^2 < 10 eps or
@@ -453,6 +444,42 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
       for (int n = 3; n <= 8; ++n)
         if (n <= lmax) acch[n - 3] = acch[n - 3] + jpow_half(f0, n) * common * wi;
     }
+  };
+  if constexpr (ORDER == 11 && !HI && !std::is_same<S, B>::value && std::is_same<B, double>::value) {
+    // dual numbers, fused kernels (K5): the mirror-pair form gives sin AND cos of both node angles
+    // from the same four products, which is exactly what d cos(angle) = -sin(angle) d angle needs;
+    // d angle = (1 +- x_p) d(kappa0 / 2).  The rest of the node term stays on the generic dual rules.
+    double sh, ch;
+    fsincos_q1(val(rng), &sh, &ch);
+#pragma unroll 1
+    for (int p = 0; p < 5; ++p) {
+      const double xp = c_gl10[0][5 + p], wp = c_gl10[1][5 + p];
+      double sa, ca;
+      fsincos_q1(val(rng) * xp, &sa, &ca);
+      const double t1 = ch * ca, t2 = sh * sa, u1 = sh * ca, u2 = ch * sa;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double cosv = q ? t1 + t2 : t1 - t2;                 // angle h -+ ... : q = 0 is node +x_p
+        const double msin = q ? -(u1 - u2) * (1.0 - xp) : -(u1 + u2) * (1.0 + xp);
+        S c = rng * msin;  // derivative part: -sin(angle) (1 +- x_p) d rng
+        c.v = cosv;
+        node_term(c, wp);
+      }
+    }
+  } else {
+  const bool const_nodes = GL<ORDER>::has_cpi && !cond_k && (val(kappa0) != B(0));
+  const int order = GL<ORDER>::n(tab);
+#pragma unroll(ORDER == 10 ? 10 : 2)
+  for (int i = 0; i < (ORDER == 10 ? 10 : order); ++i) {
+    const B xi = B(GL<ORDER>::x(i, tab));
+    const B wi = B(GL<ORDER>::w(i, tab));
+    S c;
+    if (const_nodes)
+      c = S(B(GL<ORDER>::cpi(i)));
+    else
+      c = jcos_node(rng * xi + kappa0 * B(0.5));
+    node_term(c, wi);
+  }
   }
   }
   if (HI) {
