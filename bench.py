@@ -438,6 +438,24 @@ def run_ours(args, rank, local_rank, world):
             "hbm_gbs": 32.0 * n2 / (best * 1e-3) / 1e9,
             "hbm_frac": (32.0 * n2 / (best * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
         del M, e, s_, c_
+        # K2: core.limb_dark.light_curve on 1e8 random in-transit (b, r) points
+        rr = torch.rand(n2, dtype=torch.float64, device=dev) * 0.12 + 0.03
+        bb = torch.rand(n2, dtype=torch.float64, device=dev) * (1 + rr)
+        u2 = torch.tensor([0.3, 0.2], dtype=torch.float64, device=dev)
+        f_ = torch.empty_like(bb)
+        best = 1e30
+        for i in range(4):
+            ev0.record()
+            _lib.call("jxp_limb_dark_f64", u2.data_ptr(), 2, bb.data_ptr(), 1, rr.data_ptr(), 1, n2, 10,
+                      f_.data_ptr(), 0, 0, 0, stream())
+            ev1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, ev0.elapsed_time(ev1))
+        secondary["k2_limb_dark_1e8_in_transit"] = {
+            "evaluations_per_s": n2 / (best * 1e-3), "ms": best,
+            "fp64_frac": n2 * W_LD / (best * 1e-3) / 1e12 / fp64_peak}
+        del rr, bb, f_
         secondary.update(secondary_c4_c5(dev, lib, ev0, ev1, peaks))
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
