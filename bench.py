@@ -372,6 +372,30 @@ def run_ours(args, rank, local_rank, world):
     e2e_ms = max_over_ranks(e2e_ms) / args.steps
     e2e_value = points_per_step / (e2e_ms * 1e-3)
 
+    # ---- the same step through the Python facade (what a user of the reference API writes): the
+    # sampled orbital elements, t and y are HOST NumPy arrays, System(...) is rebuilt (per-set
+    # constants of OrbitalBody.__init__ re-derived) every step, the result comes back as NumPy
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood as _facade_ll
+
+    y_np = y.cpu().numpy()
+
+    def facade_step():
+        return _facade_ll(W.system_from(p), u_h)(t_h, y_np, sigma)
+
+    for _ in range(5):
+        facade_step()
+    barrier()
+    py_ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ll_np = facade_step()
+        py_ms += (time.perf_counter() - t0) * 1e3
+    assert isinstance(ll_np, np.ndarray) and ll_np.shape == (n_sets,)
+    py_ms = max_over_ranks(py_ms) / args.steps
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -473,7 +497,10 @@ def run_ours(args, rank, local_rank, world):
         "config": workload_config(world),
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "path": "jxp_system_light_curve_f64 (C ABI), pinned host buffers"},
+                "ms_per_step": e2e_ms, "path": "jxp_system_light_curve_f64 (C ABI), pinned host buffers",
+                "python_api": {"value": points_per_step / (py_ms * 1e-3), "unit": "points/s", "ms_per_step": py_ms,
+                               "path": "light_curves.limb_dark.log_likelihood(System(...).add_body(**sampled elements), u)"
+                                       "(t, y, sigma): NumPy in, NumPy out, System rebuilt every step"}},
         "gpu_launches": 4 * args.steps,
         "gpu_launches_per_step": ["k_sys_prep", "k_loglike_prep", "k_system", "k_loglike_final"],
         "clocks": clocks, "secondary": secondary,
