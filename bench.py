@@ -417,7 +417,7 @@ def run_ours(args, rank, local_rank, world):
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_system<double,11,true,false>", "achieved": achieved, "peak": fp64_peak,
+        "bound": "fp64", "kernel": "k_system_pair<1>", "achieved": achieved, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
         "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (FP64-bound kernel: HBM is idle)",
         "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",

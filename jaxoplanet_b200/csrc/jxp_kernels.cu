@@ -1156,6 +1156,336 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   }
 }
 
+// k_system_pair -- the log-likelihood of single-planet systems without exposure integration
+// (config 3) with TWO queued samples per lane.
+//
+// Same persistent-CTA / set-group / warp-tile skeleton and the same stages A and B as k_system.
+// What changes is stage C: the fused kernel is latency-bound, not FP64-issue bound (FP64 pipe 49 %
+// active, `wait` the top stall at ~5 warps per scheduler), so every lane evaluates two queued
+// samples at once through kepler_reduced_n<2> / ld_solution_n<2>, whose statements interleave the
+// two dependency chains.  To keep 64-wide drains full, queue items carry the absolute sample index
+// and what is left (< 64 items) is carried over to the warp's next tile; the last partial drain
+// happens once per warp and set group instead of once per tile.
+// Determinism with carried-over items: the chi^2 terms of one (tile, set) are contiguous in the
+// queue; they are added SEQUENTIALLY in queue order by one lane, continuing from a running sum when
+// a segment is split across drains, and the total is stored once, when the segment closes -- so
+// the result does not depend on how the dynamic tile assignment happened to split the segments.
+constexpr int SP_QCAP = 256;
+#ifndef JXP_PAIR_MINB
+#define JXP_PAIR_MINB 4
+#endif
+template <int PU>
+__global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid_constant__ SysArgs<double> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_pick[2];
+  using T = double;
+  constexpr int K = SYS_K;
+  const int nthreads = blockDim.x;
+  const int nwarps = nthreads >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_groups = a.n_groups;
+  BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
+  SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta);
+  double* sdchi = reinterpret_cast<double*>(sset + a.sets_per_cta) + warp * 66;  // 64 terms + open sum
+  unsigned* sq = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(sset + a.sets_per_cta) + nwarps * 66) +
+                 warp * (SP_QCAP + 64 + 2);
+  unsigned* skey = sq + SP_QCAP;  // keys of the 64 items of the current drain, then the open key
+  unsigned n_kep = 0, n_ld = 0;
+  int* const group_ctr = a.tile_ctr;
+  int* const tile_ctr = a.tile_ctr + 1;
+  const unsigned lt = (1u << lane) - 1u;
+
+  int scan = -1;
+  const int home = (int)(blockIdx.x % (unsigned)n_groups);
+  for (int iter = 0;; ++iter) {
+    int group;
+    if (scan < 0) {
+      if (threadIdx.x == 0) s_pick[iter & 1] = atomicAdd(group_ctr, 1);
+      __syncthreads();
+      group = s_pick[iter & 1];
+      if (group >= n_groups) {
+        scan = 0;
+        continue;
+      }
+    } else {
+      if (scan >= n_groups) break;
+      const int gi = scan + (int)threadIdx.x;
+      bool has = false;
+      if (gi < n_groups) {
+        int g = home + gi;
+        g -= (g >= n_groups) ? n_groups : 0;
+        has = *reinterpret_cast<volatile int*>(tile_ctr + g) < a.n_wtiles;
+      }
+      if (threadIdx.x == 0) s_pick[iter & 1] = 0x7fffffff;
+      __syncthreads();
+      const unsigned hb = __ballot_sync(0xffffffffu, has);
+      if (hb && lane == 0) atomicMin(&s_pick[iter & 1], warp * 32 + __ffs(hb) - 1);
+      __syncthreads();
+      const int first = s_pick[iter & 1];
+      if (first == 0x7fffffff) {
+        scan += nthreads;
+        continue;
+      }
+      group = home + scan + first;
+      group -= (group >= n_groups) ? n_groups : 0;
+      scan += first + 1;
+    }
+    const int set_base = group * a.sets_per_cta;
+    const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
+    {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.bodies + (size_t)set_base);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
+      const int nw = nsl * (int)(sizeof(BodyC<T>) / 8);
+      for (int i = threadIdx.x; i < nw; i += nthreads) dst[i] = src[i];
+      const unsigned long long* src2 = reinterpret_cast<const unsigned long long*>(a.sets + set_base);
+      unsigned long long* dst2 = reinterpret_cast<unsigned long long*>(sset);
+      const int nw2 = nsl * (int)(sizeof(SetC<T>) / 8);
+      for (int i = threadIdx.x; i < nw2; i += nthreads) dst2[i] = src2[i];
+    }
+    __syncthreads();
+
+    int qn = 0;                       // queue fill (warp-uniform)
+    unsigned open_key = 0xffffffffu;  // (tile, set) segment still open at the end of the last drain
+    int wnext = 0;
+    if (lane == 0) wnext = atomicAdd(tile_ctr + group, 1);
+    // fill state (warp-uniform except tk / valid)
+    bool have_tile = false, more = true;
+    int64_t wbase = 0;
+    double tk[K];
+    unsigned valid = 0, visit = 0;
+    double span_lo = 0.0, span = 0.0;
+    int c0 = 0, c0_cur = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) tk[k] = 0.0;
+    while (true) {
+      // ---- fill: stages A and B until 64 items are queued or the group has no tile left -------
+      while (more && qn < 64) {
+        if (!have_tile) {
+          const int wtile_i = __shfl_sync(0xffffffffu, wnext, 0);
+          if (wtile_i >= a.n_wtiles) {
+            more = false;
+            break;
+          }
+          if (lane == 0) wnext = atomicAdd(tile_ctr + group, 1);  // in flight while this tile runs
+          wbase = (int64_t)wtile_i * (32 * K);
+          valid = 0;
+          double tmin = 1e300, tmax = -1e300;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int64_t idx = wbase + 32 * k + lane;
+            const bool ok = idx < a.n_times;
+            tk[k] = ok ? a.t[idx] : 0.0;
+            valid |= ok ? (1u << k) : 0u;
+            if (ok) {
+              tmin = fmin(tmin, tk[k]);
+              tmax = fmax(tmax, tk[k]);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+            tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+          }
+          span_lo = tmin;
+          span = tmax - tmin;
+          // zero partial sums of this tile (closed segments overwrite theirs later)
+          for (int sl = lane; sl < nsl; sl += 32) a.partial[(size_t)wtile_i * a.n_sets + (set_base + sl)] = 0.0;
+          __syncwarp();
+          c0 = 0;
+          visit = 0;
+          have_tile = true;
+        }
+        if (!visit) {
+          if (c0 >= nsl) {
+            have_tile = false;
+            continue;
+          }
+          // stage A: lane = set
+          bool cand = false;
+          const int sla = c0 + lane;
+          if (sla < nsl) {
+            const BodyC<T>& c = sbody[sla];
+            if (c.flags & BODY_ALWAYS) {
+              cand = true;
+            } else {
+              const double ph0 = fma(span_lo - c.t0ref, c.inv_period, -c.phase_c);
+              const double d0 = ph0 - rint(ph0);
+              const double d1 = fma(span, c.inv_period, d0);
+              cand = !((d1 < c.wlo) | ((d0 > c.whi) & (d1 < 1.0 + c.wlo)));
+            }
+          }
+          visit = __ballot_sync(0xffffffffu, cand);
+          c0_cur = c0;
+          c0 += 32;
+          continue;
+        }
+        // stage B: lane = sample, one candidate set
+        const int s_in = __ffs(visit) - 1;
+        visit &= visit - 1;
+        const int sl = c0_cur + s_in;
+        const BodyC<T>& c = sbody[sl];
+        unsigned hits = 0;
+        if (c.flags & BODY_ALWAYS) {
+          hits = valid;
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const double ph = fma(tk[k] - c.t0ref, c.inv_period, -c.phase_c);
+            const double d = ph - rint(ph);
+            hits |= ((d >= c.wlo) & (d <= c.whi)) ? (1u << k) : 0u;
+          }
+          hits &= valid;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const unsigned mk = __ballot_sync(0xffffffffu, (hits >> k) & 1u);
+          if ((hits >> k) & 1u)
+            sq[qn + __popc(mk & lt)] = ((unsigned)sl << 25) | (unsigned)(wbase + 32 * k + lane);
+          qn += __popc(mk);
+        }
+        __syncwarp();
+      }
+      if (qn == 0) break;  // no tile left and nothing queued
+
+      // ---- stage C: 64 queued samples (fewer only at the very end of the group), two per lane ----
+      const int cnt = qn < 64 ? qn : 64;
+      bool have[2];
+      double Mr[2], e[2], ome[2], ope[2], s1[2], iope[2], sf[2], cf[2], bq[2], rq[2], tot[2];
+      int slq[2];
+      int64_t idxq[2];
+      bool circ = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        have[h] = 32 * h + lane < cnt;
+        const unsigned item = have[h] ? sq[32 * h + lane] : sq[0];
+        slq[h] = (int)(item >> 25);
+        idxq[h] = (int64_t)(item & 0x1ffffffu);
+        const BodyC<T>& c = sbody[slq[h]];
+        Mr[h] = mean_anomaly_reduced(c, a.t[idxq[h]]);
+        e[h] = c.e;
+        ome[h] = c.ome;
+        ope[h] = c.ope;
+        s1[h] = c.s1me2;
+        iope[h] = c.inv_ope;
+        circ = circ || (c.flags & BODY_CIRCULAR);
+      }
+      kepler_reduced_n<2>(Mr, e, ome, ope, s1, iope, sf, cf);
+      if (__any_sync(0xffffffffu, circ)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (sbody[slq[h]].flags & BODY_CIRCULAR) jsincos(Mr[h], &sf[h], &cf[h]);  // keplerian.py:539-540
+      }
+      bool intr[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const BodyC<T>& c = sbody[slq[h]];
+        double Z;
+        sky_position(c, sf[h], cf[h], bq[h], Z);
+        rq[h] = c.rr;
+        intr[h] = have[h] && (Z > 0.0) && !(bq[h] >= c.onepr);
+        n_kep += have[h] ? 1u : 0u;
+        n_ld += intr[h] ? 1u : 0u;
+      }
+      {
+        double s0[2], s1v[2], s2[2];
+        const int lmax = sset[slq[0]].lmax;  // one law length per call
+        ld_solution_n<2, PU>(bq, rq, lmax, s0, s1v, s2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const SetC<T>& sc = sset[slq[h]];
+          tot[h] = intr[h] ? ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2) : 0.0;
+        }
+      }
+      // chi^2 terms and (tile, set) keys to shared memory
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double dchi = 0.0;
+        if (have[h] && tot[h] != 0.0) {
+          const double w = a.winv[idxq[h]];
+          const double r0 = (a.y[idxq[h]] - 1.0) * w;
+          const double mw = tot[h] * w;
+          dchi = (-mw) * (2.0 * r0 - mw);
+        }
+        sdchi[32 * h + lane] = dchi;
+        skey[32 * h + lane] =
+            have[h] ? (((unsigned)slq[h] << 25) | (unsigned)(idxq[h] / (32 * K))) : 0xfffffffeu;
+      }
+      if (lane == 0) skey[65] = 0xfffffffdu;  // "no segment left open by this drain" until one says so
+      __syncwarp();
+      // sequential sums per (tile, set) segment, in queue order, one lane per segment start; the
+      // segment ends come from a ballot of the starts, so the loop is only load + add
+      bool start[2];
+      unsigned keyh[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 32 * h + lane;
+        keyh[h] = skey[i];
+        const unsigned prev = (i == 0) ? open_key : skey[i == 0 ? 0 : i - 1];
+        start[h] = (i < cnt) && (i == 0 || keyh[h] != prev);
+      }
+      const unsigned long long starts = (unsigned long long)__ballot_sync(0xffffffffu, start[0]) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, start[1]) << 32);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 32 * h + lane;
+        if (start[h]) {
+          const unsigned key = keyh[h];
+          const unsigned long long rest = (i == 63) ? 0ull : (starts >> (i + 1));
+          const int j_end = rest ? (i + __ffsll((long long)rest)) : cnt;
+          double sum = (i == 0 && key == open_key) ? sdchi[64] : 0.0;
+#pragma unroll 4
+          for (int j = i; j < j_end; ++j) sum += sdchi[j];
+          const size_t slot = (size_t)(key & 0x1ffffffu) * a.n_sets + (set_base + (int)(key >> 25));
+          if (j_end < cnt) {
+            a.partial[slot] = sum;  // closed: every term of this (tile, set) is in
+          } else {
+            sdchi[65] = sum;  // still open at the end of this drain
+            skey[65] = key;
+          }
+          // the segment left open by the previous drain does not continue here: it closes as it was
+          if (i == 0 && key != open_key && open_key != 0xffffffffu) {
+            const size_t oslot =
+                (size_t)(open_key & 0x1ffffffu) * a.n_sets + (set_base + (int)(open_key >> 25));
+            a.partial[oslot] = sdchi[64];
+          }
+        }
+      }
+      __syncwarp();
+      {
+        const unsigned ok65 = skey[65];
+        const bool still_open = (ok65 == skey[cnt - 1]);
+        const double osum = sdchi[65];
+        __syncwarp();
+        open_key = still_open ? ok65 : 0xffffffffu;
+        if (lane == 0) sdchi[64] = still_open ? osum : 0.0;
+      }
+      // shift the rest of the queue down
+      const int rem = qn - cnt;
+      unsigned keep[(SP_QCAP - 64) / 32];
+#pragma unroll
+      for (int m = 0; m < (SP_QCAP - 64) / 32; ++m) keep[m] = (32 * m + lane < rem) ? sq[cnt + 32 * m + lane] : 0u;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < (SP_QCAP - 64) / 32; ++m)
+        if (32 * m + lane < rem) sq[32 * m + lane] = keep[m];
+      qn = rem;
+      __syncwarp();
+    }
+    // close the last open segment of this group
+    if (open_key != 0xffffffffu && lane == 0) {
+      const size_t oslot = (size_t)(open_key & 0x1ffffffu) * a.n_sets + (set_base + (int)(open_key >> 25));
+      a.partial[oslot] = sdchi[64];
+    }
+    __syncthreads();
+  }
+  n_kep = __reduce_add_sync(0xffffffffu, n_kep);
+  n_ld = __reduce_add_sync(0xffffffffu, n_ld);
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, (unsigned long long)n_kep);
+    atomicAdd(a.counters + 1, (unsigned long long)n_ld);
+  }
+}
+
 extern "C" size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times) {
   if (n_sets <= 0 || n_bodies <= 0 || n_times < 0) return 0;
   // sized for the wider (double) records so one query serves both precisions
@@ -1302,6 +1632,33 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     return check_launch("jxp_system_light_curve");
   };
   const bool dense = (a.use_window == 0) && n_bodies == 1 && a.st.n == 1 && n_u <= 2;
+  if constexpr (sizeof(T) == 8) {
+    // log-likelihood of single-planet systems, no exposure integration: two samples per lane
+    const bool pair = loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 && n_u <= 2 &&
+                      gl_order == 10 && a.use_window && n_times < (1LL << 25) && spc <= 64 &&
+                      getenv("JXP_NO_PAIR") == nullptr;
+    if (pair) {
+      const size_t smem2 = sizeof(BodyC<T>) * (size_t)spc + sizeof(SetC<T>) * (size_t)spc +
+                           (size_t)(threads / 32) * (66 * sizeof(double) + (SP_QCAP + 64 + 2) * sizeof(unsigned));
+#ifndef JXP_PAIR_PU
+#define JXP_PAIR_PU 1
+#endif
+      auto kern = k_system_pair<JXP_PAIR_PU>;
+      int per_sm = 0;
+      cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem2);
+      if (eo != cudaSuccess || per_sm < 1)
+        return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
+      const int64_t resident = (int64_t)per_sm * sms;
+      const unsigned n_ctas = (unsigned)(n_units < resident ? n_units : resident);
+      if (g_ev_start) cudaEventRecord(g_ev_start, st);
+      kern<<<n_ctas, threads, smem2, st>>>(a);
+      if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
+      rc = check_launch("jxp_system_light_curve(pair)");
+      if (rc != JXP_OK) return rc;
+      k_loglike_final<T><<<(n_sets + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike);
+      return check_launch("jxp_system_light_curve(loglike final)");
+    }
+  }
   if (n_u > 2) {
     // general polynomial limb darkening: queue kernel with the l >= 3 terms compiled in
     if (gl_order == 10)

@@ -303,6 +303,46 @@ def test_system_window_flag_is_bit_identical():
     assert torch.equal(a, b)
 
 
+def test_loglike_is_bit_reproducible_under_dynamic_scheduling():
+    """The persistent kernels hand warp tiles to warps dynamically and the pair kernel carries queued
+    samples from one tile to the next: the per-set log-likelihood must not depend on that schedule.
+    Repeated calls, a different CTA size (different tile -> warp assignment) and the one-sample-per-lane
+    kernel (JXP_NO_PAIR) are compared bit for bit / to rounding."""
+    import os
+
+    import torch
+
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood
+
+    p, ub, tb, noise, sigma = W.c3(640, 30_000)
+    y = 1.0 + noise
+    f = log_likelihood(W.system_from(p), ub)
+    td, yd = torch.as_tensor(tb).cuda(), torch.as_tensor(y).cuda()
+    base = f(td, yd, sigma).clone()
+    for _ in range(4):
+        assert torch.equal(f(td, yd, sigma), base)
+    old = os.environ.get("JXP_SYS_THREADS")
+    try:
+        os.environ["JXP_SYS_THREADS"] = "64"
+        assert torch.equal(f(td, yd, sigma), base)
+        os.environ["JXP_SYS_THREADS"] = "32"
+        assert torch.equal(f(td, yd, sigma), base)
+    finally:
+        if old is None:
+            os.environ.pop("JXP_SYS_THREADS", None)
+        else:
+            os.environ["JXP_SYS_THREADS"] = old
+    try:
+        os.environ["JXP_NO_PAIR"] = "1"
+        single = f(td, yd, sigma).clone()
+        assert torch.equal(f(td, yd, sigma), single)
+    finally:
+        os.environ.pop("JXP_NO_PAIR", None)
+    # different rounding of the flux (1e-16) times 1 / sigma^2 = 4e6 per term
+    assert torch.max(torch.abs(single - base) / torch.abs(base)).item() <= 2e-12
+
+
 def test_system_shape_and_depth_kats():
     # tests/light_curves/transit_test.py:9-37 and limb_dark_test.py:7-25
     from jaxoplanet_b200.light_curves import limb_dark_light_curve
