@@ -412,7 +412,7 @@ def run_ours(args, rank, local_rank, world):
         pass
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_system"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_system_pair"]
         traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
