@@ -532,6 +532,24 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
                 best = min(best, ev0.elapsed_time(ev1))
         return best
 
+    # C1: the reference's own CPU-runnable case, 1 planet x 1e5 times, flux materialised
+    from jaxoplanet_b200.orbits.keplerian import System
+
+    body1, u1, t1 = W.c1()
+    b1, _, _ = pack_bodies(System().add_body(**body1))
+    b1 = b1.to(dev).contiguous()
+    u1d = torch.as_tensor(np.asarray(u1, dtype=np.float64)).to(dev)
+    t1d = torch.as_tensor(t1).to(dev)
+    n1 = t1d.numel()
+    wsb1 = int(lib.jxp_system_workspace_bytes(1, 1, n1))
+    ws1 = torch.empty(wsb1, dtype=torch.uint8, device=dev)
+    f1 = torch.empty((1, n1, 1), dtype=torch.float64, device=dev)
+    ms = best_of(lambda: _lib.call("jxp_system_light_curve_f64", b1.data_ptr(), 1, 1, u1d.data_ptr(), 2, 0,
+                                   t1d.data_ptr(), n1, 0.0, 0, 0, 10, 0, f1.data_ptr(), 0, 0, 0, 0, 0,
+                                   ws1.data_ptr(), wsb1, A.stream_ptr()), n=5)
+    out["c1_single_planet_1e5_times"] = {"points_per_s": n1 / (ms * 1e-3), "ms": ms,
+                                         "in_transit_fraction": float((f1 != 0).double().mean())}
+
     # C4: 3 planets, 30-min cadence, 15x exposure supersampling, 1024 sets x 2e5 times
     p, u, t, expo = W.c4()
     bodies, n_sets, _ = pack_bodies(W.system_from(p))
