@@ -197,6 +197,36 @@ int jxp_transit_partials_f32(const double* theta, int32_t n_sets, const double* 
                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K0  OrbitalBody.__init__(central, body): the per-set derived constants
+ *     src/jaxoplanet/orbits/keplerian.py:262-340
+ * elements: [n][JXP_EL_NFIELDS] (device) the sampled Body arguments of one body per row, NaN =
+ * "not given" (None in the reference); exactly one of period / semimajor, at most one of
+ * impact_param / inclination and of time_transit / time_peri, omega as an angle or as sin and cos,
+ * eccentricity NaN = circular.  central_mass / central_radius: the resolved Central (:30-70).
+ * bodies: [n][JXP_BODY_NFIELDS] (device) the records jxp_system_light_curve_* takes.
+ * ---------------------------------------------------------------------------------- */
+enum {
+  JXP_EL_PERIOD = 0,
+  JXP_EL_SEMIMAJOR = 1,
+  JXP_EL_TIME_TRANSIT = 2,
+  JXP_EL_TIME_PERI = 3,
+  JXP_EL_ECC = 4,
+  JXP_EL_OMEGA = 5,
+  JXP_EL_SIN_OMEGA = 6,
+  JXP_EL_COS_OMEGA = 7,
+  JXP_EL_IMPACT_PARAM = 8,
+  JXP_EL_INCLINATION = 9,
+  JXP_EL_MASS = 10,
+  JXP_EL_RADIUS = 11,
+  JXP_EL_CENTRAL_MASS = 12,
+  JXP_EL_CENTRAL_RADIUS = 13,
+  JXP_EL_PARALLAX = 14,
+  JXP_EL_RESERVED = 15,
+  JXP_EL_NFIELDS = 16
+};
+int jxp_orbital_elements_f64(const double* elements, int64_t n, double* bodies, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K6  light_curves.limb_dark.light_curve(TransitOrbit | TTVOrbit, u)(t)
  *     src/jaxoplanet/orbits/transit.py:7-107 (linear motion across the disk, no Kepler solve),
  *     src/jaxoplanet/orbits/ttv.py:46-225 (searchsorted time warp around each observed transit),

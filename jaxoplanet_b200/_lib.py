@@ -17,6 +17,10 @@ JXP_NTHETA = 8
 JXP_FLAG_NO_WINDOW = 1
 JXP_FLAG_COUNT = 2
 JXP_TO_NFIELDS = 6
+JXP_EL_NFIELDS = 16
+(EL_PERIOD, EL_SEMIMAJOR, EL_TIME_TRANSIT, EL_TIME_PERI, EL_ECC, EL_OMEGA, EL_SIN_OMEGA, EL_COS_OMEGA,
+ EL_IMPACT_PARAM, EL_INCLINATION, EL_MASS, EL_RADIUS, EL_CENTRAL_MASS, EL_CENTRAL_RADIUS, EL_PARALLAX,
+ EL_RESERVED) = range(16)
 
 (BODY_PERIOD, BODY_TIME_TRANSIT, BODY_TIME_REF, BODY_ECC, BODY_COS_OMEGA, BODY_SIN_OMEGA,
  BODY_COS_INCL, BODY_SIN_INCL, BODY_SEMIMAJOR, BODY_CENTRAL_RADIUS, BODY_RADIUS,
@@ -68,6 +72,7 @@ SIGNATURES = {
     ),
     "jxp_transit_orbit_light_curve_f64": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_transit_orbit_light_curve_f32": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
+    "jxp_orbital_elements_f64": (C.c_int, [_p, _i64, _p, _p]),
     "jxp_interp_periodic_f64": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_interp_periodic_f32": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),

@@ -216,6 +216,86 @@ extern "C" int jxp_interp_periodic_f32(const double* xp, const float* fp, int32_
   return launch_interp<float>(xp, fp, n, n_cols, period, time_transit, t, n_times, out, stream);
 }
 
+// K0: OrbitalBody.__init__ on the device -- the per-set derived constants of
+// src/jaxoplanet/orbits/keplerian.py:262-340 (and Central's two-of-three rule :30-70 is the caller's:
+// central mass and radius come in resolved).  One thread per (set, body); NaN marks "not given"
+// (None in the reference).  Same operation order as the reference; libm calls are CUDA's (<= 1-2 ulp
+// from XLA's / NumPy's).
+__global__ void __launch_bounds__(128)
+k_orbital_elements(const double* __restrict__ el, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* p = el + i * JXP_EL_NFIELDS;
+  const double pi = 3.141592653589793238462643383279502884;
+  const double G = 2942.2062175044193;  // src/jaxoplanet/constants.py:2
+  const double central_mass = p[JXP_EL_CENTRAL_MASS], central_radius = p[JXP_EL_CENTRAL_RADIUS];
+  const double mass = p[JXP_EL_MASS];
+  const double total_mass = isnan(mass) ? central_mass : mass + central_mass;  // :265-268
+  const double mass_factor = G * total_mass;
+  double period = p[JXP_EL_PERIOD], semimajor = p[JXP_EL_SEMIMAJOR];
+  if (isnan(semimajor)) {
+    semimajor = cbrt(mass_factor * (period * period) / (4.0 * (pi * pi)));  // :275
+  } else {
+    period = 2.0 * pi * semimajor * sqrt(semimajor / mass_factor);  // :281
+  }
+  double sw = p[JXP_EL_SIN_OMEGA], cw = p[JXP_EL_COS_OMEGA];
+  if (!isnan(p[JXP_EL_OMEGA])) {
+    sw = sin(p[JXP_EL_OMEGA]);  // :286-287
+    cw = cos(p[JXP_EL_OMEGA]);
+  }
+  const double ecc = p[JXP_EL_ECC];
+  const bool circular = isnan(ecc);
+  double M0, incl_factor;
+  if (circular) {
+    M0 = 0.5 * pi;  // :302
+    incl_factor = 1.0;
+  } else {
+    const double opsw = 1.0 + sw;
+    const double E0 = 2.0 * atan2(sqrt(1.0 - ecc) * cw, sqrt(1.0 + ecc) * opsw);  // :308-311
+    M0 = E0 - ecc * sin(E0);                                                       // :312
+    const double ome2 = 1.0 - ecc * ecc;
+    incl_factor = (1.0 + ecc * sw) / ome2;  // :315
+  }
+  const double dcosidb = incl_factor * central_radius / semimajor;  // :318
+  double cos_i, sin_i;
+  if (!isnan(p[JXP_EL_IMPACT_PARAM])) {
+    cos_i = dcosidb * p[JXP_EL_IMPACT_PARAM];  // :321-322
+    sin_i = sqrt(1.0 - cos_i * cos_i);
+  } else if (!isnan(p[JXP_EL_INCLINATION])) {
+    cos_i = cos(p[JXP_EL_INCLINATION]);  // :325-327
+    sin_i = sin(p[JXP_EL_INCLINATION]);
+  } else {
+    cos_i = 0.0;  // :329-331
+    sin_i = 1.0;
+  }
+  const double time_ref = -M0 * period / (2.0 * pi);  // :334
+  double time_transit = p[JXP_EL_TIME_TRANSIT];
+  if (isnan(time_transit)) time_transit = isnan(p[JXP_EL_TIME_PERI]) ? 0.0 : p[JXP_EL_TIME_PERI] - time_ref;  // :336-340
+  double a_out = semimajor;
+  if (!isnan(p[JXP_EL_PARALLAX])) a_out = semimajor * p[JXP_EL_PARALLAX] / 215.03215567054764;  // :620-625 (au in R_sun)
+  double* o = out + i * JXP_BODY_NFIELDS;
+  o[JXP_BODY_PERIOD] = period;
+  o[JXP_BODY_TIME_TRANSIT] = time_transit;
+  o[JXP_BODY_TIME_REF] = time_ref;
+  o[JXP_BODY_ECC] = circular ? -1.0 : ecc;
+  o[JXP_BODY_COS_OMEGA] = circular ? 1.0 : cw;
+  o[JXP_BODY_SIN_OMEGA] = circular ? 0.0 : sw;
+  o[JXP_BODY_COS_INCL] = cos_i;
+  o[JXP_BODY_SIN_INCL] = sin_i;
+  o[JXP_BODY_SEMIMAJOR] = a_out;
+  o[JXP_BODY_CENTRAL_RADIUS] = central_radius;
+  o[JXP_BODY_RADIUS] = isnan(p[JXP_EL_RADIUS]) ? 0.0 : p[JXP_EL_RADIUS];
+  o[JXP_BODY_RESERVED] = 0.0;
+}
+
+extern "C" int jxp_orbital_elements_f64(const double* elements, int64_t n, double* bodies, void* stream) {
+  if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_orbital_elements: n = %lld < 0", (long long)n);
+  if (n == 0) return JXP_OK;
+  if (!elements || !bodies) return fail(JXP_ERR_NULL_POINTER, "jxp_orbital_elements: null pointer");
+  k_orbital_elements<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(elements, n, bodies);
+  return check_launch("jxp_orbital_elements");
+}
+
 extern "C" int jxp_transit_orbit_light_curve_f64(const double* planets, int32_t n_planets,
                                                  const double* bin_edges, const double* bin_values,
                                                  const int32_t* bin_offsets, const double* ttv_t0,

@@ -68,6 +68,37 @@ def pack_bodies(system: System):
     return bodies, n_sets, batched
 
 
+def pack_elements(n, *, central_mass=1.0, central_radius=1.0, **body):
+    """Sampled ``Body`` arguments -> the [n, JXP_EL_NFIELDS] element records of kernel K0
+    (include/jaxoplanet_b200.h); arguments that are not given become NaN (None in the reference)."""
+    names = dict(period=_lib.EL_PERIOD, semimajor=_lib.EL_SEMIMAJOR, time_transit=_lib.EL_TIME_TRANSIT,
+                 time_peri=_lib.EL_TIME_PERI, eccentricity=_lib.EL_ECC, omega_peri=_lib.EL_OMEGA,
+                 sin_omega_peri=_lib.EL_SIN_OMEGA, cos_omega_peri=_lib.EL_COS_OMEGA,
+                 impact_param=_lib.EL_IMPACT_PARAM, inclination=_lib.EL_INCLINATION, mass=_lib.EL_MASS,
+                 radius=_lib.EL_RADIUS, parallax=_lib.EL_PARALLAX)
+    el = np.full((n, _lib.JXP_EL_NFIELDS), np.nan)
+    el[:, _lib.EL_CENTRAL_MASS] = central_mass
+    el[:, _lib.EL_CENTRAL_RADIUS] = central_radius
+    el[:, _lib.EL_RESERVED] = 0.0
+    for k, v in body.items():
+        if v is None:
+            continue
+        if k not in names:
+            raise TypeError(f"unknown Body argument {k!r}")
+        el[:, names[k]] = v
+    return el
+
+
+def derive_bodies(elements):
+    """``OrbitalBody.__init__`` (src/jaxoplanet/orbits/keplerian.py:262-340) on the device: element
+    records [..., JXP_EL_NFIELDS] -> body records [..., JXP_BODY_NFIELDS] (CUDA tensor), kernel K0."""
+    el = A.to_dev(elements, torch.float64)
+    out = torch.empty(tuple(el.shape[:-1]) + (_lib.JXP_BODY_NFIELDS,), dtype=torch.float64, device=el.device)
+    _lib.call("jxp_orbital_elements_f64", el.data_ptr(), el.numel() // _lib.JXP_EL_NFIELDS, out.data_ptr(),
+              A.stream_ptr())
+    return out
+
+
 @dataclass(frozen=True)
 class FusedSpec:
     """Everything the fused kernel needs besides the time stamps."""

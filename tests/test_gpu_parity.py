@@ -343,6 +343,52 @@ def test_loglike_is_bit_reproducible_under_dynamic_scheduling():
     assert torch.max(torch.abs(single - base) / torch.abs(base)).item() <= 2e-12
 
 
+def test_orbital_elements_on_device_match_oracle():
+    """K0: OrbitalBody.__init__ on the device vs the oracle (keplerian.py:262-340), all parametrisations."""
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200.light_curves.limb_dark import derive_bodies, pack_bodies, pack_elements
+
+    rng = np.random.default_rng(5)
+    n = 257
+    P = rng.uniform(1, 30, n)
+    cases = [
+        dict(period=P, time_transit=rng.uniform(0, 3, n), eccentricity=rng.uniform(0, 0.8, n),
+             omega_peri=rng.uniform(-np.pi, np.pi, n), impact_param=rng.uniform(0, 1.2, n), radius=rng.uniform(0.01, 0.2, n)),
+        dict(semimajor=rng.uniform(5, 40, n), time_peri=rng.uniform(0, 3, n), eccentricity=rng.uniform(0, 0.5, n),
+             sin_omega_peri=np.sin(P), cos_omega_peri=np.cos(P), inclination=rng.uniform(1.4, 1.6, n),
+             mass=rng.uniform(0, 0.01, n), radius=rng.uniform(0.01, 0.2, n)),
+        dict(period=P, impact_param=rng.uniform(0, 1, n), radius=rng.uniform(0.01, 0.2, n)),  # circular
+        dict(period=P),  # nothing else: b = 0, radius None
+    ]
+    for kw, (cm, cr) in zip(cases, ((1.0, 1.0), (0.8, 0.75), (1.3, 1.1), (1.0, 1.0))):
+        got = derive_bodies(pack_elements(n, central_mass=cm, central_radius=cr, **kw)).cpu().numpy()
+        bd = ref.orbital_body(central_mass=cm, central_radius=cr, **kw)
+        circular = bd["eccentricity"] is None
+        want = np.zeros((n, _lib.JXP_BODY_NFIELDS))
+        want[:, _lib.BODY_PERIOD] = bd["period"]
+        want[:, _lib.BODY_TIME_TRANSIT] = bd["time_transit"]
+        want[:, _lib.BODY_TIME_REF] = bd["time_ref"]
+        want[:, _lib.BODY_ECC] = -1.0 if circular else bd["eccentricity"]
+        want[:, _lib.BODY_COS_OMEGA] = 1.0 if circular else bd["cos_omega_peri"]
+        want[:, _lib.BODY_SIN_OMEGA] = 0.0 if circular else bd["sin_omega_peri"]
+        want[:, _lib.BODY_COS_INCL] = bd["cos_inclination"]
+        want[:, _lib.BODY_SIN_INCL] = bd["sin_inclination"]
+        want[:, _lib.BODY_SEMIMAJOR] = bd["semimajor"]
+        want[:, _lib.BODY_CENTRAL_RADIUS] = cr
+        want[:, _lib.BODY_RADIUS] = 0.0 if bd["radius"] is None else bd["radius"]
+        scale = np.maximum(np.abs(want), 1e-3)
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), ok)
+        assert np.max(np.abs(got - want)[ok] / scale[ok]) <= 2e-14, kw.keys()
+    # and the records feed the fused kernel like the host-built ones
+    from jaxoplanet_b200 import workloads as W
+
+    p, ub, tb, noise, sigma = W.c3(64, 4000)
+    host, _, _ = pack_bodies(W.system_from(p))
+    dev = derive_bodies(pack_elements(64, **p)).reshape(64, 1, -1)
+    assert np.max(np.abs(dev.cpu().numpy() - host.numpy()) / np.maximum(np.abs(host.numpy()), 1e-3)) <= 2e-14
+
+
 def test_system_shape_and_depth_kats():
     # tests/light_curves/transit_test.py:9-37 and limb_dark_test.py:7-25
     from jaxoplanet_b200.light_curves import limb_dark_light_curve
