@@ -601,6 +601,15 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
             "hbm_frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
         del fl, pt
         torch.cuda.empty_cache()
+    # C5 as a gradient step: log-likelihood and its 8-gradient reduced in the kernel, no rows stored
+    y5 = torch.ones(nt5, dtype=torch.float64, device=dev)
+    sg5 = torch.full((1,), 5e-4, dtype=torch.float64, device=dev)
+    ll5 = torch.empty(ns5, dtype=torch.float64, device=dev)
+    dll5 = torch.empty((ns5, 8), dtype=torch.float64, device=dev)
+    ms = best_of(lambda: _lib.call("jxp_transit_partials_f64", thd.data_ptr(), ns5, star.data_ptr(), 0,
+                                   t5d.data_ptr(), nt5, 0.0, 0, 0, 10, 0, 0, 0, y5.data_ptr(), sg5.data_ptr(), 0,
+                                   ll5.data_ptr(), dll5.data_ptr(), ws5.data_ptr(), wsb5, A.stream_ptr()))
+    out["c5_loglike_plus_8_gradient_f64"] = {"points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms}
     return out
 
 

@@ -15,6 +15,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "jxp_host.h"
 #include "jxp_orbit.cuh"
 
@@ -54,7 +56,7 @@ TrLayout tr_layout(int n_sets, int64_t n_times) {
   L.off_scalars = off;
   off = align_up(off + 256 * sizeof(double), 256);
   L.off_partial = off;
-  off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles * (1 + JXP_NTHETA), 256);
+  off = align_up(off + sizeof(double) * (size_t)n_sets * (L.n_tiles + 4) * (1 + JXP_NTHETA), 256);
   L.total = off;
   return L;
 }
@@ -218,6 +220,7 @@ struct TrArgs {
   const double* t;
   int64_t n_times;
   int n_sets, sets_per_cta, n_tiles, n_wtiles, use_window;
+  int run;  // consecutive warp tiles one warp processes (queued samples are carried from one to the next)
   T* flux;      // [n_sets][n_times]
   T* partials;  // [n_sets][8][n_times]
   const T* y;
@@ -253,9 +256,9 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
   const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
   BodyD<T>* sbody = reinterpret_cast<BodyD<T>*>(smem_raw);
   double* sacc_all = reinterpret_cast<double*>(sbody + a.sets_per_cta);  // [nwarps][spc][9]
-  unsigned short* sq_all = reinterpret_cast<unsigned short*>(sacc_all + (size_t)nwarps * a.sets_per_cta * NQ);
+  unsigned* sq_all = reinterpret_cast<unsigned*>(sacc_all + (size_t)nwarps * a.sets_per_cta * NQ);
   double* sacc = sacc_all + (size_t)warp * a.sets_per_cta * NQ;
-  unsigned short* sq = sq_all + warp * TR_QCAP;
+  unsigned* sq = sq_all + warp * TR_QCAP;
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.bodies + set_base);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
@@ -268,90 +271,111 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
     __syncthreads();
     for (int i = threadIdx.x; i < nsl; i += nthreads) sbody[i].c.flags |= BODY_ALWAYS;
   }
-  const int64_t wtile = (int64_t)tile * nwarps + warp;
-  const int64_t wbase = wtile * (32 * K);
-  double tk[K];
-  unsigned valid = 0;
-  double tmin = 1e300, tmax = -1e300;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int64_t idx = wbase + 32 * k + lane;
-    const bool ok = idx < a.n_times;
-    tk[k] = ok ? a.t[idx] : 0.0;
-    valid |= ok ? (1u << k) : 0u;
-    if (ok) {
-      tmin = fmin(tmin, tk[k]);
-      tmax = fmax(tmax, tk[k]);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-    tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-  }
+  // this warp's run of consecutive warp tiles
+  // Step r of the run handles warp tile (r * n_tiles + tile) * nwarps + warp: at every step the warps
+  // of a CTA, and the CTAs running side by side, write ADJACENT pieces of each output row (the row
+  // stores then stream through DRAM pages like a plain fill; with contiguous runs per warp the same
+  // fill was 15 % slower).  Queued samples carry their absolute index, so the tiles of a run need
+  // not be neighbours.
+  const int64_t wrun = (int64_t)tile * nwarps + warp;
   const int nsub = a.st.n;
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
-  const double span_lo = tmin + dtmin, span = (tmax + dtmax) - span_lo;
+  const bool want_rows = (a.flux != nullptr) || (a.partials != nullptr);
   int qn = 0;
   __syncthreads();
-  if (wbase >= a.n_times) return;  // (no further block barriers)
 
-  // Zero rows first: the whole (sets of the group) x (flux + 8 partials) x (this warp's 64 samples)
-  // block is written as one 128-bit store per lane and row (512 contiguous bytes per warp store in
-  // f64), stage C then overwrites the in-window samples (3 % of them on config 5).  Before, every
-  // zero was a predicated 64-bit store inside stage B with its own address arithmetic (20 executed
-  // instructions per stored row; the kernel was latency-bound at 5.0 TB/s).
-  const bool want_rows = (a.flux != nullptr) || (a.partials != nullptr);
-  if (want_rows) {
-    static_assert(TR_K == 2, "the zero fill assumes 2 samples per lane");
-    struct alignas(2 * sizeof(T)) V2 {
-      T x, y;
-    };
-    const int64_t s0 = wbase + 2 * lane;
-    const bool two = s0 + 1 < a.n_times, one = s0 < a.n_times;
-    const bool vec = ((a.n_times & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.flux) & (2 * sizeof(T) - 1)) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(a.partials) & (2 * sizeof(T) - 1)) == 0);
-    V2 z;
-    z.x = T(0);
-    z.y = T(0);
-#pragma unroll 1
-    for (int sl = 0; sl < nsl; ++sl) {
-      const size_t set = (size_t)(set_base + sl);
-      if (a.flux) {
-        T* row = a.flux + set * a.n_times + s0;
-        if (vec && two) {
-          *reinterpret_cast<V2*>(row) = z;
-        } else {
-          if (one) row[0] = T(0);
-          if (two) row[1] = T(0);
-        }
-      }
-      if (a.partials) {
-        T* row = a.partials + set * JXP_NTHETA * a.n_times + s0;
-#pragma unroll
-        for (int q = 0; q < JXP_NTHETA; ++q) {
-          if (vec && two) {
-            *reinterpret_cast<V2*>(row) = z;
-          } else {
-            if (one) row[0] = T(0);
-            if (two) row[1] = T(0);
-          }
-          row += a.n_times;
-        }
-      }
-    }
-    __syncwarp();  // orders these stores before stage C's stores of other lanes to the same rows
-  }
-
+  // fill state
+  bool have_tile = false, more = true;
+  int r_next = 0;
+  int64_t wbase = 0;
+  double tk[K];
+  unsigned valid = 0, visit = 0;
+  double span_lo = 0.0, span = 0.0;
   int c0 = 0, c0_cur = 0;
-  unsigned visit = 0, cmask = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) tk[k] = 0.0;
   while (true) {
-    bool done = false;
-    while (qn <= TR_QCAP - 32 * K) {
+    // ---- fill: stages A and B until 32 samples are queued or the run has no tile left ------------
+    while (more && qn < 32) {
+      if (!have_tile) {
+        wbase = (((int64_t)r_next * a.n_tiles + tile) * nwarps + warp) * (32 * K);
+        if (r_next >= a.run || wbase >= a.n_times) {
+          more = false;
+          break;
+        }
+        ++r_next;
+        valid = 0;
+        double tmin = 1e300, tmax = -1e300;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int64_t idx = wbase + 32 * k + lane;
+          const bool ok = idx < a.n_times;
+          tk[k] = ok ? a.t[idx] : 0.0;
+          valid |= ok ? (1u << k) : 0u;
+          if (ok) {
+            tmin = fmin(tmin, tk[k]);
+            tmax = fmax(tmax, tk[k]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+          tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        }
+        span_lo = tmin + dtmin;
+        span = (tmax + dtmax) - span_lo;
+        // Zero rows first: the whole (sets of the group) x (flux + 8 partials) x (this tile's 64
+        // samples) block is written as one 128-bit store per lane and row (512 contiguous bytes per
+        // warp store in f64); stage C then overwrites the in-window samples (3 % of them on config 5).
+        if (want_rows) {
+          static_assert(TR_K == 2, "the zero fill assumes 2 samples per lane");
+          struct alignas(2 * sizeof(T)) V2 {
+            T x, y;
+          };
+          const int64_t s0 = wbase + 2 * lane;
+          const bool two = s0 + 1 < a.n_times, one = s0 < a.n_times;
+          const bool vec = ((a.n_times & 1) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(a.flux) & (2 * sizeof(T) - 1)) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(a.partials) & (2 * sizeof(T) - 1)) == 0);
+          V2 z;
+          z.x = T(0);
+          z.y = T(0);
+#pragma unroll 1
+          for (int sl = 0; sl < nsl; ++sl) {
+            const size_t set = (size_t)(set_base + sl);
+            if (a.flux) {
+              T* row = a.flux + set * a.n_times + s0;
+              if (vec && two) {
+                *reinterpret_cast<V2*>(row) = z;
+              } else {
+                if (one) row[0] = T(0);
+                if (two) row[1] = T(0);
+              }
+            }
+            if (a.partials) {
+              T* row = a.partials + set * JXP_NTHETA * a.n_times + s0;
+#pragma unroll
+              for (int q = 0; q < JXP_NTHETA; ++q) {
+                if (vec && two) {
+                  *reinterpret_cast<V2*>(row) = z;
+                } else {
+                  if (one) row[0] = T(0);
+                  if (two) row[1] = T(0);
+                }
+                row += a.n_times;
+              }
+            }
+          }
+          __syncwarp();  // orders these stores before stage C's stores of other lanes to the same rows
+        }
+        c0 = 0;
+        visit = 0;
+        have_tile = true;
+      }
       if (!visit) {
         if (c0 >= nsl) {
-          done = true;
-          break;
+          have_tile = false;
+          continue;
         }
         // ---- stage A: lane = set ----------------------------------------------------------
         bool cand = false;
@@ -367,59 +391,51 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
             cand = !((d1 < c.wlo) | ((d0 > c.whi) & (d1 < 1.0 + c.wlo)));
           }
         }
-        cmask = __ballot_sync(0xffffffffu, cand);
-        const int nchunk = min(32, nsl - c0);
-        (void)nchunk;
-        visit = cmask;  // only candidate sets are looked at sample by sample
+        visit = __ballot_sync(0xffffffffu, cand);  // only candidate sets are looked at sample by sample
         c0_cur = c0;
         c0 += 32;
         continue;
       }
-      // ---- stage B: lane = sample, one set ------------------------------------------------------
+      // ---- stage B: lane = sample, one candidate set ------------------------------------------
       const int s_in = __ffs(visit) - 1;
       visit &= visit - 1;
       const int sl = c0_cur + s_in;
       unsigned hits = 0;
-      if (cmask & (1u << s_in)) {
-        const BodyC<T>& c = sbody[sl].c;
-        if (c.flags & BODY_ALWAYS) {
-          hits = valid;
-        } else {
-          const double wlo = fma(-dtmax, c.inv_period, c.wlo), whi = fma(-dtmin, c.inv_period, c.whi);
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const double ph = fma(tk[k] - c.t0ref, c.inv_period, -c.phase_c);
-            const double d = ph - rint(ph);
-            hits |= ((d >= wlo) & (d <= whi)) ? (1u << k) : 0u;
-          }
-          hits &= valid;
-        }
+      const BodyC<T>& c = sbody[sl].c;
+      if (c.flags & BODY_ALWAYS) {
+        hits = valid;
+      } else {
+        const double wlo = fma(-dtmax, c.inv_period, c.wlo), whi = fma(-dtmin, c.inv_period, c.whi);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const unsigned mk = __ballot_sync(0xffffffffu, (hits >> k) & 1u);
-          if ((hits >> k) & 1u)
-            sq[qn + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)((sl << 7) | (k << 5) | lane);
-          qn += __popc(mk);
+          const double ph = fma(tk[k] - c.t0ref, c.inv_period, -c.phase_c);
+          const double d = ph - rint(ph);
+          hits |= ((d >= wlo) & (d <= whi)) ? (1u << k) : 0u;
         }
+        hits &= valid;
       }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const unsigned mk = __ballot_sync(0xffffffffu, (hits >> k) & 1u);
+        if ((hits >> k) & 1u)
+          sq[qn + __popc(mk & ((1u << lane) - 1u))] = ((unsigned)sl << 26) | (unsigned)(wbase + 32 * k + lane);
+        qn += __popc(mk);
+      }
+      __syncwarp();
     }
+    if (qn == 0) break;  // no tile left in the run and nothing queued
 
     // ---- stage C: drain -----------------------------------------------------------------------
+    // 32 queued samples (fewer only at the very end of the run): queued samples carry their absolute
+    // index and are carried from one tile of the run to the next, so the drains stay full
     __syncwarp();
-#pragma unroll 1
-    for (int q0 = 0; q0 < qn; q0 += 32) {
-      const bool have = q0 + lane < qn;
-      const unsigned item = have ? sq[q0 + lane] : 0u;
-      const int sl = (int)(item >> 7);
-      const int k = (int)((item >> 5) & 3u);
-      const int src = (int)(item & 31u);
-      double tm0 = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < K; ++kk) {
-        const double v = __shfl_sync(0xffffffffu, tk[kk], src);
-        tm0 = (kk == k) ? v : tm0;
-      }
-      const int64_t idx = wbase + 32 * k + src;
+    {
+      const int cnt = qn < 32 ? qn : 32;
+      const bool have = lane < cnt;
+      const unsigned item = have ? sq[lane] : sq[0];
+      const int sl = (int)(item >> 26);
+      const int64_t idx = (int64_t)(item & 0x3ffffffu);
+      const double tm0 = a.t[idx];
       T out[NQ];
 #pragma unroll
       for (int q = 0; q < NQ; ++q) out[q] = T(0);
@@ -481,15 +497,23 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
         }
         __syncwarp();
       }
+      // shift the rest of the queue down
+      const int rem = qn - cnt;
+      unsigned keep[(TR_QCAP - 32) / 32];
+#pragma unroll
+      for (int m = 0; m < (TR_QCAP - 32) / 32; ++m) keep[m] = (32 * m + lane < rem) ? sq[cnt + 32 * m + lane] : 0u;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < (TR_QCAP - 32) / 32; ++m)
+        if (32 * m + lane < rem) sq[32 * m + lane] = keep[m];
+      qn = rem;
+      __syncwarp();
     }
-    qn = 0;
-    __syncwarp();
-    if (done) break;
   }
   if (LOGLIKE) {
     for (int i = lane; i < nsl * NQ; i += 32) {
       const int sl = i / NQ, q = i - sl * NQ;
-      a.partial[((size_t)wtile * a.n_sets + (set_base + sl)) * NQ + q] = sacc[i];
+      a.partial[((size_t)wrun * a.n_sets + (set_base + sl)) * NQ + q] = sacc[i];
     }
   }
 }
@@ -601,10 +625,23 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   const int sms = sm_count();
   int threads = 128;
   const int64_t n_wtiles = (n_times + 32 * TR_K - 1) / (32 * TR_K);
-  int64_t n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
+  if (n_times >= (1LL << 26)) return fail(JXP_ERR_UNSUPPORTED, "jxp_transit_partials: n_times >= 2^26");
+  // a warp processes `run` consecutive warp tiles and carries queued samples from one to the next
+  // (full 32-wide drains); shorter runs when the problem is too small to fill the machine otherwise
+  // measured on config 5 (run = 1 / 4 / 16): the arithmetic alone 6.8 / 5.4 / 4.9 ms, the row stores alone
+  // 8.7 / 9.9 / 10.8 ms -- long runs keep the drains full, short ones keep the store stream smooth
+  int run = (flux || partials) ? 1 : 16;
+  if (const char* env = getenv("JXP_TR_RUN")) {  // development knob
+    const int v = atoi(env);
+    if (v >= 1 && v <= 64) run = v;
+  }
+  auto n_wruns_of = [&](int r) { return (n_wtiles + r - 1) / r; };
+  while (run > 1 && n_wruns_of(run) / 4 * ((n_sets + TR_MAX_SETS - 1) / TR_MAX_SETS) < 8 * sms) run /= 2;
+  const int64_t n_wruns = n_wruns_of(run);
+  int64_t n_tiles = (n_wruns + threads / 32 - 1) / (threads / 32);
   while (threads > 32 && n_tiles * ((n_sets + TR_MAX_SETS - 1) / TR_MAX_SETS) < 4 * sms) {
     threads /= 2;
-    n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
+    n_tiles = (n_wruns + threads / 32 - 1) / (threads / 32);
   }
   int spc = TR_MAX_SETS;
   if (spc > n_sets) spc = n_sets;
@@ -618,6 +655,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   a.sets_per_cta = spc;
   a.n_tiles = (int)n_tiles;
   a.n_wtiles = (int)n_wtiles;
+  a.run = run;
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
   a.partials = partials;
@@ -628,7 +666,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
   const size_t smem = sizeof(BodyD<T>) * (size_t)spc +
                       sizeof(double) * (1 + JXP_NTHETA) * (size_t)spc * (threads / 32) +
-                      sizeof(unsigned short) * (size_t)TR_QCAP * (threads / 32);
+                      sizeof(unsigned) * (size_t)TR_QCAP * (threads / 32);
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -644,7 +682,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   if (rc != JXP_OK) return rc;
   if (want_ll) {
     const int n = n_sets * (1 + JXP_NTHETA);
-    k_tr_final<T><<<(n + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
+    k_tr_final<T><<<(n + 31) / 32, 256, 0, st>>>(d_partial, (int)(n_tiles * (threads / 32)), n_sets, d_scalars, loglike,
                                                   dloglike);
     rc = check_launch("jxp_transit_partials(final)");
   }
