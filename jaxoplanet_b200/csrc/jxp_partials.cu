@@ -478,8 +478,13 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
 #pragma unroll
           for (int q = 0; q < JXP_NTHETA; ++q) acc9[1 + q] = g * (double)out[1 + q];
         }
-        // segmented inclusive scan keyed by set (queue entries of one set are contiguous)
-        const int key = have ? sl : -1 - lane;
+        // segmented inclusive scan.  Entries of one set are contiguous within a tile, but with samples
+        // carried over from earlier tiles of the run a set can occur in several separate pieces of a
+        // batch, so the scan is keyed by the piece number (count of piece starts up to this lane).
+        const int skey = have ? sl : -1 - lane;
+        const int skey_prev = __shfl_up_sync(0xffffffffu, skey, 1);
+        const unsigned starts = __ballot_sync(0xffffffffu, lane == 0 || skey != skey_prev);
+        const int key = __popc(starts & (0xffffffffu >> (31 - lane)));
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int ku = __shfl_up_sync(0xffffffffu, key, o);
@@ -491,11 +496,20 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
           }
         }
         const int kn = __shfl_down_sync(0xffffffffu, key, 1);
-        if (have && (lane == 31 || kn != key)) {
+        // With samples carried over from earlier tiles of the run the same set can end more than one
+        // segment of a batch: those lanes take turns by lane index (= queue order, deterministic).
+        const bool endl = have && (lane == 31 || kn != key);
+        const unsigned same = __match_any_sync(0xffffffffu, endl ? sl : -1 - lane);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int maxr = (int)__reduce_max_sync(0xffffffffu, (unsigned)(endl ? rank : 0));
+#pragma unroll 1
+        for (int rr = 0; rr <= maxr; ++rr) {
+          if (endl && rank == rr) {
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) sacc[sl * NQ + q] += acc9[q];
+            for (int q = 0; q < NQ; ++q) sacc[sl * NQ + q] += acc9[q];
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // shift the rest of the queue down
       const int rem = qn - cnt;

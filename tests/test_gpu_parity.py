@@ -686,6 +686,34 @@ def test_transit_partials_f32_and_autograd_function():
     np.testing.assert_allclose(g.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
 
 
+def test_transit_partials_runs_with_carried_queue_match_single_tiles():
+    """K5's reduced mode lets a warp process a run of tiles and carry queued samples across them; the
+    log-likelihood and gradient must equal those of the one-tile-per-warp geometry (a set can then occur
+    in several separate pieces of one 32-wide batch: regression test for the piece-keyed scan)."""
+    import os
+
+    import torch
+
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    p, ub = W.transit_sets(96, seed=11)
+    theta = torch.as_tensor(W.theta_from(p, ub)).cuda()
+    t = torch.as_tensor(np.arange(30_000) * W.TWO_MIN).cuda()
+    y = 1.0 + transit_partials(theta[5:6], t, want_partials=False)["flux"][0] + 1e-4 * torch.sin(t)
+    out = {}
+    try:
+        for run in ("1", "4", "16"):
+            os.environ["JXP_TR_RUN"] = run
+            out[run] = transit_partials(theta, t, y=y, sigma=5e-4, want_flux=False, want_partials=False)
+    finally:
+        os.environ.pop("JXP_TR_RUN", None)
+    scale = torch.abs(out["1"]["dloglike"]).amax(dim=0, keepdim=True)
+    for run in ("4", "16"):
+        assert float(torch.max(torch.abs(out[run]["loglike"] - out["1"]["loglike"]) / torch.abs(out["1"]["loglike"]))) <= 1e-13
+        assert float(torch.max(torch.abs(out[run]["dloglike"] - out["1"]["dloglike"]) / scale)) <= 1e-12
+
+
 def test_window_is_conservative_on_adversarial_orbits():
     # the transit-window pre-test must never drop an in-transit sample: windowed and dense
     # evaluations have to agree bit for bit on short-period, eccentric, grazing and
