@@ -64,3 +64,53 @@ def test_two_rank_gather_matches_single(tmp_path):
     for r in range(2):
         got = np.load(tmp_path / f"ll_{r}.npy")
         np.testing.assert_array_equal(got, np.array(want))
+
+
+def _oracle_eval(params, u, t, y, sigma):
+    from oracle import ref_numpy as ref
+
+    out = []
+    n = np.shape(params["period"])[0]
+    for s in range(n):
+        bd = ref.orbital_body(**{k: v[s] for k, v in params.items()})
+        us = u[s] if np.ndim(u) == 2 else u
+        m = 1 + ref.system_light_curve([bd], us, t).sum(-1)
+        out.append(ref.gaussian_loglike(m, y, np.broadcast_to(sigma, t.shape)))
+    return torch.tensor(out, dtype=torch.float64)
+
+
+def _worker_dist(rank, world, port, n_sets, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.distributed import log_likelihood_distributed
+
+    p, u, t, noise, sigma = W.c3(n_sets, 600, seed=9)
+    y = 1 + noise
+    sig = np.full_like(t, sigma) * (1 + 0.1 * np.sin(t))  # per-sample sigma
+    full = log_likelihood_distributed(p, u, t, y, sig, evaluate=_oracle_eval)
+    np.save(os.path.join(out_dir, f"lld_{n_sets}_{rank}.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_set_and_time_sharding_match_single(tmp_path):
+    """n_sets >= world: set-sharded + all-gather; n_sets < world (1 set, 2 ranks): time-sharded +
+    all-reduce(sum) of the partial log-likelihoods (SURVEY 8e fallback)."""
+    from jaxoplanet_b200 import workloads as W
+
+    for n_sets in (5, 1):
+        port = 31500 + (os.getpid() + n_sets) % 2000
+        mp.spawn(_worker_dist, args=(2, port, n_sets, str(tmp_path)), nprocs=2, join=True)
+        p, u, t, noise, sigma = W.c3(n_sets, 600, seed=9)
+        sig = np.full_like(t, sigma) * (1 + 0.1 * np.sin(t))
+        want = _oracle_eval(p, u, t, 1 + noise, sig).numpy()
+        for r in range(2):
+            got = np.load(tmp_path / f"lld_{n_sets}_{r}.npy")
+            if n_sets >= 2:
+                np.testing.assert_array_equal(got, want)
+            else:  # the sum over time is split in two: rounding of the last bits
+                np.testing.assert_allclose(got, want, rtol=1e-13)
