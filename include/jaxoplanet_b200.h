@@ -161,6 +161,15 @@ int jxp_profile_events(void* start_event, void* stop_event);
 int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, int64_t n_times,
                      int64_t* stats_host, void* stream);
 
+/* Measurement helper: which kernels the LAST log-likelihood call on this workspace used.  With
+ * sorted time stamps, one body and no exposure integration the in-window samples are expanded
+ * into a work list in the workspace (DESIGN.md "transit list"); the choice is made on the device.
+ * stats_host[0] = items in the list, stats_host[1] = 0 when the list kernels produced the
+ * result (and stats_host[0] > 0), bit 0: time stamps not sorted, bit 1: the list did not fit
+ * the workspace -- in both cases the window-test kernels produced it.  SYNCHRONISES `stream`. */
+int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
+                          int64_t n_times, int64_t* stats_host, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K5  flux and its forward-mode partials w.r.t. the 8 sampled parameters of a single
  *     transiting planet, theta = (period, time_transit, eccentricity, omega_peri,

@@ -58,6 +58,7 @@ SIGNATURES = {
          _i64, _p, _p, _sz, _p],
     ),
     "jxp_system_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
+    "jxp_system_list_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "jxp_profile_events": (C.c_int, [_p, _p]),
     "jxp_transit_workspace_bytes": (_sz, [_i32, _i64]),
     "jxp_transit_partials_f64": (

@@ -26,6 +26,13 @@ thread_local char g_err[512] = "";
 thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 }
 
+// development knob: JXP_PROFILE_KERNEL=prep|build|reduce moves the profile events of the
+// list path from its dominant kernel (k_tl_eval) to another one
+static bool ev_on(const char* which) {
+  const char* env = getenv("JXP_PROFILE_KERNEL");
+  return env ? strcmp(env, which) == 0 : strcmp(which, "eval") == 0;
+}
+
 extern "C" int jxp_profile_events(void* start_event, void* stop_event) {
   g_ev_start = (cudaEvent_t)start_event;
   g_ev_stop = (cudaEvent_t)stop_event;
@@ -411,6 +418,8 @@ namespace {
 // workspace carving shared by the size query and the launchers
 struct SysLayout {
   size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, off_tilectr, total;
+  size_t off_tl_off, off_tl_cnt, off_tl_items;  // transit-list path (single-body systems)
+  unsigned long long tl_cap;                     // items the list can hold
   int tile, n_tiles;
 };
 
@@ -432,6 +441,19 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
   off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles, 256);
   L.off_tilectr = off;  // [0]: next unclaimed set group, [1 + g]: next warp tile of group g
   off = align_up(off + sizeof(int) * ((size_t)n_sets + 1), 256);
+  // transit list: one 8-byte slot per in-window (set, sample); room for 1/8 of the grid (a list
+  // that would not fit makes the call fall back to the window-test kernels, on the device)
+  L.off_tl_off = L.off_tl_cnt = L.off_tl_items = off;
+  L.tl_cap = 0;
+  if (n_bodies == 1) {
+    L.off_tl_off = off;
+    off = align_up(off + sizeof(unsigned long long) * (size_t)n_sets, 256);
+    L.off_tl_cnt = off;
+    off = align_up(off + sizeof(unsigned) * (size_t)n_sets, 256);
+    L.off_tl_items = off;
+    L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 8ull + 65536ull;
+    off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
+  }
   L.total = off;
   return L;
 }
@@ -439,12 +461,11 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
 
 // one thread per (set, body): derived constants -> BodyC (+ transit window), u -> SetC
 template <typename T>
-__global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
+__device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
                            BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
                            unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr,
                            double widen, double margin) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sets * n_bodies) return;
   if (i <= n_sets) tile_ctr[i] = 0;  // work distribution state of k_system (n_sets + 1 entries)
   if (i == 0 && n_sets * n_bodies <= n_sets) tile_ctr[n_sets] = 0;
@@ -483,6 +504,8 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
   if (i == 0) {  // executed-work counters of this call (jxp_system_stats)
     counters[0] = 0ull;
     counters[1] = 0ull;
+    counters[2] = 0ull;  // transit list: items allocated
+    counters[3] = 0ull;  // transit list: TL_UNSORTED | TL_OVERFLOW (non-zero: list path off)
   }
   if (i % n_bodies == 0) {
     const int s = i / n_bodies;
@@ -509,15 +532,30 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
 // chunks, fixed summation order (k_loglike_final / k_tr_final add the LL_NCTA pairs in order).
 constexpr int LL_NCTA = 64;
 constexpr int LL_SCAL0 = 8;
+constexpr int LL_FLAG0 = LL_SCAL0 + 2 * 64;  // per-CTA "time stamps not sorted" flags (list path)
+// tl_state[1] of the transit-list path (tl_state[0] = items allocated); zeroed by k_sys_prep
+constexpr unsigned long long TL_UNSORTED = 1ull, TL_OVERFLOW = 2ull;
 template <typename T>
-__global__ void __launch_bounds__(256)
-k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
-               T* __restrict__ winv, double* __restrict__ scalars) {
+__global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
+                           const double* __restrict__ u, int n_u, int64_t u_stride,
+                           BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
+                           unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr,
+                           double widen, double margin) {
+  sys_prep_body<T>(blockIdx.x * blockDim.x + threadIdx.x, bodies, n_sets, n_bodies, u, n_u, u_stride, out_b,
+                   out_s, counters, tile_ctr, widen, margin);
+}
+
+// CTA `cta` of `ncta` (256 threads); t != nullptr: also flag time stamps that are not sorted
+template <typename T>
+__device__ __forceinline__ void
+loglike_prep_body(int cta, int ncta, const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
+                  T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t) {
   __shared__ double sh0[8], sh1[8];
   double a0 = 0.0, a1 = 0.0;
+  int bad = 0;
   const double half_log_2pi = 0.918938533204672741780329736405617639;
-  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t chunk = (n + ncta - 1) / ncta;
+  const int64_t lo = (int64_t)cta * chunk;
   const int64_t hi = lo + chunk < n ? lo + chunk : n;
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const T sg = sigma[i * ss];
@@ -526,6 +564,12 @@ k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss,
     const double r0 = (double)((y[i] - T(1)) * w);
     a0 += r0 * r0;
     a1 -= log((double)sg) + half_log_2pi;
+    // the transit-list path needs non-decreasing, NaN-free time stamps
+    if (t != nullptr && i + 1 < n && !(t[i + 1] >= t[i])) bad = 1;
+  }
+  if (t != nullptr) {
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) scalars[LL_FLAG0 + cta] = bad ? 1.0 : 0.0;
   }
   for (int o = 16; o > 0; o >>= 1) {
     a0 += __shfl_down_sync(0xffffffffu, a0, o);
@@ -543,9 +587,32 @@ k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss,
       t0 += sh0[k];
       t1 += sh1[k];
     }
-    scalars[LL_SCAL0 + 2 * blockIdx.x] = t0;
-    scalars[LL_SCAL0 + 2 * blockIdx.x + 1] = t1;
+    scalars[LL_SCAL0 + 2 * cta] = t0;
+    scalars[LL_SCAL0 + 2 * cta + 1] = t1;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
+               T* __restrict__ winv, double* __restrict__ scalars) {
+  loglike_prep_body<T>(blockIdx.x, gridDim.x, y, sigma, ss, n, winv, scalars, nullptr);
+}
+
+// k_sys_prep and k_loglike_prep in one launch (they are independent): the first n_prep CTAs derive
+// the records, the next LL_NCTA the likelihood constants (and the sortedness flags for the list path)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_sys_prep_ll(const double* __restrict__ bodies, int n_sets, int n_bodies, const double* __restrict__ u, int n_u,
+              int64_t u_stride, BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
+              unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr, double widen, double margin,
+              int n_prep, const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
+              T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t) {
+  if ((int)blockIdx.x < n_prep)
+    sys_prep_body<T>(blockIdx.x * blockDim.x + threadIdx.x, bodies, n_sets, n_bodies, u, n_u, u_stride, out_b,
+                     out_s, counters, tile_ctr, widen, margin);
+  else
+    loglike_prep_body<T>((int)blockIdx.x - n_prep, LL_NCTA, y, sigma, ss, n, winv, scalars, t);
 }
 
 namespace jxph {
@@ -567,8 +634,10 @@ int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int6
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
-                const double* __restrict__ scalars, T* __restrict__ loglike) {
+                const double* __restrict__ scalars, T* __restrict__ loglike,
+                const unsigned long long* __restrict__ tl_state = nullptr) {
   __shared__ double sh[8][33];
+  if (tl_state != nullptr && tl_state[1] == 0ull) return;  // the transit-list kernels did the work
   const int ls = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int s = blockIdx.x * 32 + ls;
   double acc = 0.0;
@@ -602,6 +671,14 @@ struct SysArgs {
   const T* winv;
   double* partial;  // [n_wtiles][n_sets]
   unsigned long long* counters;  // [2]: Kepler solves, limb-darkening evaluations executed
+  // transit-list path (nullptr: not used by this call)
+  unsigned long long* tl_state;  // [0] items allocated, [1] TL_UNSORTED | TL_OVERFLOW
+  unsigned long long* tl_items;  // [tl_cap] (set << 32 | sample), overwritten by the chi^2 term
+  unsigned long long* tl_off;    // [n_sets] first item of the set
+  unsigned* tl_cnt;              // [n_sets] items of the set
+  unsigned long long tl_cap;
+  const double* scalars;
+  double* loglike;
   Stencil st;
   GLTable tab;
 };
@@ -1194,6 +1271,7 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
   int* const group_ctr = a.tile_ctr;
   int* const tile_ctr = a.tile_ctr + 1;
   const unsigned lt = (1u << lane) - 1u;
+  if (a.tl_state != nullptr && a.tl_state[1] == 0ull) return;  // the transit-list kernels did the work
 
   int scan = -1;
   const int home = (int)(blockIdx.x % (unsigned)n_groups);
@@ -1486,6 +1564,324 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
   }
 }
 
+
+// --------------------------------------------------------------------------------------
+// Transit-list path -- the log-likelihood of single-planet systems without exposure integration
+// when the time stamps are sorted (the headline case, config 3).
+//
+// The window-test kernels above look at every (set, sample) pair to find the ~3 % that can be in
+// transit.  With sorted time stamps the in-window samples of a set are a few dozen contiguous index
+// ranges (one per transit), found by binary search.  HBM is idle in this path, so the ranges are
+// expanded into an explicit work list in the caller's workspace:
+//   k_tl_build   one warp per set: transits that intersect [t_first, t_last] -> index ranges ->
+//                count -> one atomicAdd allocates the set's slice of the list -> items
+//                (set << 32 | sample) written coalesced.
+//   k_tl_eval    a flat, perfectly balanced map over the list, two items per lane through the same
+//                kepler_reduced_n<2> / ld_solution_n<2> code as k_system_pair: every lane of every
+//                warp does useful work, there is no queue, no window test and no reduction; the
+//                item's slot is overwritten with its chi^2 term.
+//   k_tl_reduce  one warp per set adds the set's slice in a fixed order (lane-strided sums, then
+//                a shuffle tree) -> loglike.  Which slice a set got depends on the atomics, the
+//                order of the terms inside it does not: bit-reproducible.
+// The decision is taken on the device (no synchronisation in the ABI): k_loglike_prep flags
+// unsorted / NaN time stamps, k_tl_build flags a list that does not fit the workspace; with a flag
+// set these kernels return at once and k_system_pair / k_loglike_final run, otherwise those two
+// return at once.  A sample outside the window costs nothing and one inside it is evaluated in
+// full (the reference's value, 0 when it is not in transit), so the list only has to be a
+// superset of the in-transit samples -- the same rigorous window as stage A/B.
+// --------------------------------------------------------------------------------------
+// First index i in [0, n] with !pred(t[i]), pred(v) = (v < x) (lower bound) or (v <= x) (upper
+// bound), on sorted t.  The estimate from a uniform grid through the end points is bracketed by
+// doubling, then bisected: ~4 dependent loads on a regular cadence instead of log2(n).
+template <bool UPPER>
+__device__ __forceinline__ unsigned tl_search(const double* __restrict__ t, unsigned n, double x,
+                                              double t_first, double inv_dt) {
+  auto pred = [&](unsigned i) {
+    const double v = t[i];
+    return UPPER ? (v <= x) : (v < x);
+  };
+  double gd = (x - t_first) * inv_dt;
+  gd = fmin(fmax(gd, 0.0), (double)n);
+  const unsigned g = (unsigned)gd;
+  unsigned w = 2;
+  unsigned lo = g > w ? g - w : 0u;
+  while (lo > 0u && !pred(lo - 1u)) {
+    w = (w < 0x40000000u) ? (w << 1) : 0xffffffffu;
+    lo = g > w ? g - w : 0u;
+  }
+  w = 2;
+  unsigned hi = (n - g > w) ? g + w : n;
+  while (hi < n && pred(hi)) {
+    w = (w < 0x40000000u) ? (w << 1) : 0xffffffffu;
+    hi = (n - g > w) ? g + w : n;
+  }
+  while (lo < hi) {
+    const unsigned mid = lo + ((hi - lo) >> 1);
+    if (pred(mid)) lo = mid + 1u; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) k_tl_build(const __grid_constant__ SysArgs<double> a) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= a.n_sets) return;
+  {  // sortedness flags of k_sys_prep_ll (one per CTA of the likelihood prep)
+    const bool bad = a.scalars[LL_FLAG0 + lane] != 0.0 || a.scalars[LL_FLAG0 + 32 + lane] != 0.0;
+    if (__any_sync(0xffffffffu, bad)) {
+      if (s == 0 && lane == 0) atomicOr(a.tl_state + 1, TL_UNSORTED);
+      return;
+    }
+  }
+  const BodyC<double>& c = a.bodies[s];
+  const unsigned n = (unsigned)a.n_times;
+  const double P = c.period, t0ref = c.t0ref, phc = c.phase_c, wlo = c.wlo, whi = c.whi;
+  const double t_first = a.t[0], t_last = a.t[n - 1];
+  const double inv_dt = (t_last > t_first) ? (double)(n - 1) / (t_last - t_first) : 0.0;
+  bool all = (c.flags & BODY_ALWAYS) != 0;
+  long long n_tr = 1;
+  double k_first = 0.0;
+  if (!all) {
+    if (!(wlo <= whi)) {
+      n_tr = 0;  // never in transit
+    } else {
+      const double pa = (t_first - t0ref) * c.inv_period - phc;
+      const double pb = (t_last - t0ref) * c.inv_period - phc;
+      const double lo_d = floor(fmin(pa, pb) - whi) - 1.0;
+      const double hi_d = ceil(fmax(pa, pb) - wlo) + 1.0;
+      if (!(hi_d - lo_d < 4.0 * (double)n + 64.0)) {
+        all = true;  // more transits than samples (or not finite): take every sample
+      } else {
+        k_first = lo_d;
+        n_tr = (long long)(hi_d - lo_d) + 1;
+      }
+    }
+  }
+  auto interval = [&](long long k, unsigned& lo, unsigned& hi) {
+    lo = 0;
+    hi = 0;
+    if (k >= n_tr) return;
+    if (all) {
+      hi = n;
+      return;
+    }
+    const double base = phc + (k_first + (double)k);
+    const double ta = fma(base + wlo, P, t0ref), tb = fma(base + whi, P, t0ref);
+    lo = tl_search<false>(a.t, n, fmin(ta, tb), t_first, inv_dt);
+    hi = tl_search<true>(a.t, n, fmax(ta, tb), t_first, inv_dt);
+  };
+  // the first 64 transits stay in registers between the counting and the writing pass
+  unsigned lo0, hi0, lo1, hi1;
+  interval(lane, lo0, hi0);
+  interval(32 + lane, lo1, hi1);
+  unsigned long long cnt = (unsigned long long)(hi0 - lo0) + (hi1 - lo1);
+  for (long long k0 = 64; k0 < n_tr; k0 += 32) {
+    unsigned lo, hi;
+    interval(k0 + lane, lo, hi);
+    cnt += hi - lo;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  unsigned long long off = 0;
+  if (lane == 0) off = atomicAdd(a.tl_state, cnt);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (lane == 0) {
+    a.tl_off[s] = off;
+    a.tl_cnt[s] = (unsigned)cnt;
+  }
+  if (off + cnt > a.tl_cap) {
+    if (lane == 0) atomicOr(a.tl_state + 1, TL_OVERFLOW);
+    return;
+  }
+  unsigned long long* out = a.tl_items + off;
+  const unsigned long long tag = (unsigned long long)s << 32;
+  for (long long k0 = 0; k0 < n_tr; k0 += 32) {
+    unsigned lo, hi;
+    if (k0 == 0) {
+      lo = lo0;
+      hi = hi0;
+    } else if (k0 == 32) {
+      lo = lo1;
+      hi = hi1;
+    } else {
+      interval(k0 + lane, lo, hi);
+    }
+    const unsigned cl = hi - lo;
+    unsigned incl = cl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned excl = incl - cl;
+    unsigned nz = __ballot_sync(0xffffffffu, cl != 0u);
+    while (nz) {
+      const int j = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const unsigned lj = __shfl_sync(0xffffffffu, lo, j);
+      const unsigned cj = __shfl_sync(0xffffffffu, cl, j);
+      const unsigned ej = __shfl_sync(0xffffffffu, excl, j);
+      for (unsigned i = lane; i < cj; i += 32) out[ej + i] = tag | (unsigned long long)(lj + i);
+    }
+    out += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+#ifndef JXP_TL_MINB
+#define JXP_TL_MINB 4
+#endif
+#ifndef JXP_TL_PU
+#define JXP_TL_PU 1
+#endif
+template <int PU>
+__global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_constant__ SysArgs<double> a) {
+  if (a.tl_state[1] != 0ull) return;
+  const unsigned long long total = a.tl_state[0];
+  const unsigned long long n_chunks = (total + 63ull) >> 6;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  unsigned long long ch = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  unsigned n_kep = 0, n_ld = 0;
+  if (ch >= n_chunks) return;
+  const BodyC<double>* __restrict__ bodies = a.bodies;
+  const SetC<double>* __restrict__ sets = a.sets;
+  const int lmax = sets[0].lmax;  // one law length per call
+  unsigned long long nxt[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const unsigned long long p = ch * 64ull + 32 * h + lane;
+    nxt[h] = a.tl_items[p < total ? p : ch * 64ull];
+  }
+  for (; ch < n_chunks; ch += nw) {
+    bool have[2], intr[2];
+    double Mr[2], e[2], ome[2], ope[2], s1[2], iope[2], sf[2], cf[2], bq[2], rq[2], tot[2];
+    unsigned slq[2], idxq[2];
+    bool circ = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      have[h] = ch * 64ull + 32 * h + lane < total;
+      slq[h] = (unsigned)(nxt[h] >> 32);
+      idxq[h] = (unsigned)nxt[h];
+    }
+    if (ch + nw < n_chunks) {  // next chunk's items in flight while this one is evaluated
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned long long p = (ch + nw) * 64ull + 32 * h + lane;
+        nxt[h] = a.tl_items[p < total ? p : (ch + nw) * 64ull];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const BodyC<double>& c = bodies[slq[h]];
+      Mr[h] = mean_anomaly_reduced(c, a.t[idxq[h]]);
+      e[h] = c.e;
+      ome[h] = c.ome;
+      ope[h] = c.ope;
+      s1[h] = c.s1me2;
+      iope[h] = c.inv_ope;
+      circ = circ || (c.flags & BODY_CIRCULAR);
+    }
+    kepler_reduced_n<2>(Mr, e, ome, ope, s1, iope, sf, cf);
+    if (__any_sync(0xffffffffu, circ)) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (bodies[slq[h]].flags & BODY_CIRCULAR) jsincos(Mr[h], &sf[h], &cf[h]);  // keplerian.py:539-540
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const BodyC<double>& c = bodies[slq[h]];
+      double Z;
+      sky_position(c, sf[h], cf[h], bq[h], Z);
+      rq[h] = c.rr;
+      intr[h] = have[h] && (Z > 0.0) && !(bq[h] >= c.onepr);
+      n_kep += have[h] ? 1u : 0u;
+      n_ld += intr[h] ? 1u : 0u;
+    }
+    {
+      double s0[2], s1v[2], s2[2];
+      ld_solution_n<2, PU>(bq, rq, lmax, s0, s1v, s2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const SetC<double>& sc = sets[slq[h]];
+        tot[h] = intr[h] ? ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double dchi = 0.0;
+      if (have[h] && tot[h] != 0.0) {
+        const double w = a.winv[idxq[h]];
+        const double r0 = (a.y[idxq[h]] - 1.0) * w;
+        const double mw = tot[h] * w;
+        dchi = (-mw) * (2.0 * r0 - mw);
+      }
+      if (have[h]) reinterpret_cast<double*>(a.tl_items)[ch * 64ull + 32 * h + lane] = dchi;
+    }
+  }
+  n_kep = __reduce_add_sync(0xffffffffu, n_kep);
+  n_ld = __reduce_add_sync(0xffffffffu, n_ld);
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, (unsigned long long)n_kep);
+    atomicAdd(a.counters + 1, (unsigned long long)n_ld);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_tl_reduce(const __grid_constant__ SysArgs<double> a) {
+  if (a.tl_state[1] != 0ull) return;
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= a.n_sets) return;
+  const double* __restrict__ d = reinterpret_cast<const double*>(a.tl_items) + a.tl_off[s];
+  const unsigned cnt = a.tl_cnt[s];
+  // 8 independent lane-strided sums (fixed order); the 8 loads of a round are issued together
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  const unsigned full = cnt & ~255u;
+  unsigned i = lane;
+  if (i < full) {  // software-pipelined: round r + 1 is in flight while round r is added
+    double v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = __ldcs(d + i + 32 * m);
+#pragma unroll 1
+    for (i += 256; i < full; i += 256) {
+      double w[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) w[m] = __ldcs(d + i + 32 * m);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) acc[m] += v[m];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) v[m] = w[m];
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] += v[m];
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    if (i + 32 * m < cnt) acc[m] += d[i + 32 * m];  // i + 224 < full + 256: no wrap for cnt < 2^32 - 256
+  double tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  // set-independent terms: the LL_NCTA pairs of k_loglike_prep added in order (as k_loglike_final does)
+  static_assert(LL_NCTA == 64, "two pairs per lane");
+  const double2 pa = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[lane];
+  const double2 pb = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[32 + lane];
+  double chi0 = 0.0, cst = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    chi0 += __shfl_sync(0xffffffffu, pa.x, k);
+    cst += __shfl_sync(0xffffffffu, pa.y, k);
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    chi0 += __shfl_sync(0xffffffffu, pb.x, k);
+    cst += __shfl_sync(0xffffffffu, pb.y, k);
+  }
+  if (lane == 0) {
+    a.loglike[s] = -0.5 * (chi0 + tot) + cst;
+  }
+}
+
 extern "C" size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times) {
   if (n_sets <= 0 || n_bodies <= 0 || n_times < 0) return 0;
   // sized for the wider (double) records so one query serves both precisions
@@ -1543,19 +1939,28 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   cudaStream_t st = (cudaStream_t)stream;
 
   const bool f32 = sizeof(T) == 4;
+  // transit-list path (see k_tl_build): eligibility is decided here, use on the device
+  const bool use_tl = sizeof(T) == 8 && loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 &&
+                      n_u <= 2 && gl_order == 10 && !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL &&
+                      L.tl_cap > 0 && getenv("JXP_NO_TL") == nullptr && getenv("JXP_NO_PAIR") == nullptr;
   {
     const int n = n_sets * n_bodies;
-    k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride,
-                                                  d_bodies, d_sets,
-                                                  reinterpret_cast<unsigned long long*>(d_scalars + 2),
-                                                  reinterpret_cast<int*>(ws + L.off_tilectr),
-                                                  f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7);
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);
+    int* tile_ctr = reinterpret_cast<int*>(ws + L.off_tilectr);
+    const double widen = f32 ? 1.0 + 2e-4 : 1.0 + 1e-9;
+    if (loglike) {
+      const int n_prep = (n + 255) / 256;
+      if (g_ev_start && use_tl && ev_on("prep")) cudaEventRecord(g_ev_start, st);
+      k_sys_prep_ll<T><<<n_prep + LL_NCTA, 256, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride, d_bodies,
+                                                         d_sets, counters, tile_ctr, widen, 1e-7, n_prep, y,
+                                                         sigma, sigma_stride, n_times, d_winv, d_scalars,
+                                                         use_tl ? t : nullptr);
+      if (g_ev_stop && use_tl && ev_on("prep")) cudaEventRecord(g_ev_stop, st);
+    } else {
+      k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride, d_bodies,
+                                                    d_sets, counters, tile_ctr, widen, 1e-7);
+    }
     rc = check_launch("jxp_system_light_curve(prep)");
-    if (rc != JXP_OK) return rc;
-  }
-  if (loglike) {
-    k_loglike_prep<T><<<LL_NCTA, 256, 0, st>>>(y, sigma, sigma_stride, n_times, d_winv, d_scalars);
-    rc = check_launch("jxp_system_light_curve(loglike prep)");
     if (rc != JXP_OK) return rc;
   }
 
@@ -1603,6 +2008,13 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   a.winv = d_winv;
   a.partial = d_partial;
   a.counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);
+  a.tl_state = nullptr;
+  a.tl_items = nullptr;
+  a.tl_off = nullptr;
+  a.tl_cnt = nullptr;
+  a.tl_cap = 0;
+  a.scalars = d_scalars;
+  a.loglike = nullptr;
   a.tab.order = gl_order;
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
 
@@ -1637,12 +2049,45 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     const bool pair = loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 && n_u <= 2 &&
                       gl_order == 10 && a.use_window && n_times < (1LL << 25) && spc <= 64 &&
                       getenv("JXP_NO_PAIR") == nullptr;
+    if (pair && use_tl) {
+      a.tl_state = reinterpret_cast<unsigned long long*>(d_scalars + 4);
+      a.tl_items = reinterpret_cast<unsigned long long*>(ws + L.off_tl_items);
+      a.tl_off = reinterpret_cast<unsigned long long*>(ws + L.off_tl_off);
+      a.tl_cnt = reinterpret_cast<unsigned*>(ws + L.off_tl_cnt);
+      a.tl_cap = L.tl_cap;
+      a.loglike = reinterpret_cast<double*>(loglike);
+      if (g_ev_start && ev_on("build")) cudaEventRecord(g_ev_start, st);
+      k_tl_build<<<(n_sets + 3) / 4, 128, 0, st>>>(a);
+      if (g_ev_stop && ev_on("build")) cudaEventRecord(g_ev_stop, st);
+      rc = check_launch("jxp_system_light_curve(transit list)");
+      if (rc != JXP_OK) return rc;
+      auto kern = k_tl_eval<JXP_TL_PU>;
+      int per_sm = 0;
+      cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+      if (eo != cudaSuccess || per_sm < 1)
+        return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
+      // the list length is only known on the device: a resident grid, chunks strided over it
+      const int64_t max_chunks = (int64_t)((L.tl_cap + 63ull) / 64ull);
+      const int64_t want = (max_chunks + 3) / 4;
+      const int64_t resident = (int64_t)per_sm * sms;
+      if (g_ev_start && ev_on("eval")) cudaEventRecord(g_ev_start, st);
+      kern<<<(unsigned)(want < resident ? want : resident), 128, 0, st>>>(a);
+      if (g_ev_stop && ev_on("eval")) cudaEventRecord(g_ev_stop, st);
+      rc = check_launch("jxp_system_light_curve(transit list eval)");
+      if (rc != JXP_OK) return rc;
+      if (g_ev_start && ev_on("reduce")) cudaEventRecord(g_ev_start, st);
+      k_tl_reduce<<<(n_sets + 3) / 4, 128, 0, st>>>(a);
+      if (g_ev_stop && ev_on("reduce")) cudaEventRecord(g_ev_stop, st);
+      rc = check_launch("jxp_system_light_curve(transit list reduce)");
+      if (rc != JXP_OK) return rc;
+    }
     if (pair) {
       const size_t smem2 = sizeof(BodyC<T>) * (size_t)spc + sizeof(SetC<T>) * (size_t)spc +
                            (size_t)(threads / 32) * (66 * sizeof(double) + (SP_QCAP + 64 + 2) * sizeof(unsigned));
 #ifndef JXP_PAIR_PU
 #define JXP_PAIR_PU 1
 #endif
+
       auto kern = k_system_pair<JXP_PAIR_PU>;
       int per_sm = 0;
       cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem2);
@@ -1650,12 +2095,14 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
         return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
       const int64_t resident = (int64_t)per_sm * sms;
       const unsigned n_ctas = (unsigned)(n_units < resident ? n_units : resident);
-      if (g_ev_start) cudaEventRecord(g_ev_start, st);
+      // with the list path in front this launch is the fallback: the events stay on k_tl_eval
+      if (g_ev_start && !a.tl_state) cudaEventRecord(g_ev_start, st);
       kern<<<n_ctas, threads, smem2, st>>>(a);
-      if (g_ev_stop) cudaEventRecord(g_ev_stop, st);
+      if (g_ev_stop && !a.tl_state) cudaEventRecord(g_ev_stop, st);
       rc = check_launch("jxp_system_light_curve(pair)");
       if (rc != JXP_OK) return rc;
-      k_loglike_final<T><<<(n_sets + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike);
+      k_loglike_final<T><<<(n_sets + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
+                                                              a.tl_state);
       return check_launch("jxp_system_light_curve(loglike final)");
     }
   }
@@ -1700,6 +2147,22 @@ extern "C" int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n
                                   2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_stats: %s", cudaGetErrorString(e));
+  return JXP_OK;
+}
+
+extern "C" int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
+                                     int64_t n_times, int64_t* stats_host, void* stream) {
+  if (!workspace || !stats_host) return fail(JXP_ERR_NULL_POINTER, "jxp_system_list_stats: null pointer");
+  if (n_sets <= 0 || n_bodies <= 0 || n_times <= 0)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_list_stats: empty problem");
+  const SysLayout L = sys_layout(n_sets, n_bodies, n_times, sizeof(BodyC<double>),
+                                 sizeof(SetC<double>), sizeof(double));
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(stats_host, ws + L.off_scalars + 4 * sizeof(double),
+                                  2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_list_stats: %s", cudaGetErrorString(e));
   return JXP_OK;
 }
 

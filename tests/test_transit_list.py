@@ -1,0 +1,254 @@
+"""GPU tests of the transit-list path of the fused log-likelihood (k_tl_build / k_tl_eval /
+k_tl_reduce, DESIGN.md "transit list"): sorted time stamps, one body, no exposure integration.
+
+The list kernels and the window-test kernels (k_system_pair) are two different programs for the
+same function; both are compared with the CPU oracle at the north-star tolerance, with each other,
+and the device-side choice between them (sorted? fits the workspace?) is checked through
+jxp_system_list_stats.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _loglike_abi(system, u, t, y, sigma):
+    """Log-likelihood through the C ABI with a workspace we keep -> (loglike, list items, list flags)."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    dev = A.device()
+    bodies, n_sets, _ = pack_bodies(system)
+    bodies = bodies.to(dev).contiguous()
+    u = torch.as_tensor(np.asarray(u, dtype=np.float64), device=dev).contiguous()
+    u_stride = u.shape[1] if u.ndim == 2 else 0
+    n_u = u.shape[-1]
+    td = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev).contiguous()
+    yd = torch.as_tensor(np.asarray(y, dtype=np.float64), device=dev).contiguous()
+    sg = np.atleast_1d(np.asarray(sigma, dtype=np.float64))
+    sd = torch.as_tensor(sg, device=dev).contiguous()
+    n_t = td.numel()
+    nbytes = _lib.load().jxp_system_workspace_bytes(n_sets, 1, n_t)
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    out = torch.full((n_sets,), float("nan"), dtype=torch.float64, device=dev)
+    _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 1, u.data_ptr(), n_u, u_stride,
+              td.data_ptr(), n_t, 0.0, 0, 0, 10, 0, None, None, yd.data_ptr(), sd.data_ptr(),
+              1 if sg.size > 1 else 0, out.data_ptr(), ws.data_ptr(), ws.numel(), A.stream_ptr())
+    stats = (ctypes.c_int64 * 2)()
+    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(stats), A.stream_ptr())
+    return out.cpu().numpy(), int(stats[0]), int(stats[1])
+
+
+def _without_list(fn):
+    os.environ["JXP_NO_TL"] = "1"
+    try:
+        return fn()
+    finally:
+        os.environ.pop("JXP_NO_TL", None)
+
+
+def _oracle_loglike(p, u, t, y, sigma, sets):
+    want = {}
+    for s in sets:
+        kw = {k: (None if v is None else v[s]) for k, v in p.items()}
+        bd = ref.orbital_body(**{k: v for k, v in kw.items() if v is not None})
+        m = 1 + ref.system_light_curve([bd], u if np.ndim(u) == 1 else u[s], t).sum(-1)
+        want[s] = ref.gaussian_loglike(m, y, sigma * np.ones(t.size))
+    return want
+
+
+def _system(p, central=None):
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    with jxp.batched():
+        return System(central or Central()).add_body(**p)
+
+
+def test_list_path_matches_oracle_and_window_kernels_c3_like():
+    from jaxoplanet_b200 import workloads as W
+
+    p, ub, t, noise, sigma = W.c3(300, 40_000)
+    truth = ref.system_light_curve([ref.orbital_body(**{k: v[0] for k, v in p.items()})], ub[0], t)[:, 0]
+    y = 1 + truth + noise
+    sys_ = _system(p)
+    ll, items, flags = _loglike_abi(sys_, ub, t, y, sigma)
+    assert flags == 0 and 0.01 * 300 * 40_000 < items < 0.08 * 300 * 40_000
+    ll2, items2, flags2 = _without_list(lambda: _loglike_abi(sys_, ub, t, y, sigma))
+    assert items2 == 0  # the list kernels were not launched
+    # two programs, different summation orders: terms of 1e-16 * 1 / sigma^2
+    assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
+    want = _oracle_loglike(p, ub, t, y, sigma, range(0, 300, 7))
+    for s, w in want.items():
+        assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    # bit-reproducible although the slices of the list are handed out by atomics
+    for _ in range(3):
+        again, _, _ = _loglike_abi(sys_, ub, t, y, sigma)
+        assert np.array_equal(again, ll)
+    # per-sample sigma
+    sig_t = sigma * (1 + 0.2 * np.random.default_rng(5).uniform(size=t.size))
+    ll3, _, f3 = _loglike_abi(sys_, ub, t, y, sig_t)
+    assert f3 == 0
+    want = _oracle_loglike(p, ub, t, y, sig_t, [0, 11, 299])
+    for s, w in want.items():
+        assert abs(ll3[s] - w) <= 1e-12 * abs(w)
+
+
+def test_list_path_adversarial_orbits_and_irregular_times():
+    # short and long periods, e up to 0.93, grazing and non-transiting bodies, a non-default star;
+    # irregular sorted time stamps with duplicates, gaps and negative times.  Bodies without a
+    # provable window put every sample on the list, so the sets go in small batches (a list that
+    # does not fit falls back, which the last test covers).
+    from jaxoplanet_b200.orbits.keplerian import Central
+
+    rng = np.random.default_rng(123)
+    u = np.array([0.3, 0.2])
+    t = np.sort(np.concatenate([rng.uniform(-40, -5, 9_000), rng.uniform(3, 30, 9_000)]))
+    t[100:110] = t[100]
+    t[-5:] = t[-5]
+    y = 1 + 1e-3 * rng.normal(size=t.size)
+    sigma = 1e-3
+    central = Central(mass=0.8, radius=1.3)
+    n_list = 0
+    for batch in range(24):
+        n_sets = 16
+        P = 10 ** rng.uniform(-0.7, 1.6, n_sets)
+        p = dict(period=P, time_transit=rng.uniform(-1, 1, n_sets) * P,
+                 eccentricity=rng.uniform(0, 0.93, n_sets), omega_peri=rng.uniform(-np.pi, np.pi, n_sets),
+                 impact_param=rng.uniform(0, 1.4, n_sets), radius=10 ** rng.uniform(-2.3, -0.5, n_sets))
+        sys_ = _system(p, central)
+        ll, items, flags = _loglike_abi(sys_, u, t, y, sigma)
+        assert flags in (0, 2)
+        n_list += flags == 0
+        ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, sigma))
+        assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
+        for s in range(batch % 3, n_sets, 3):
+            bd = ref.orbital_body(central_mass=0.8, central_radius=1.3, **{k: v[s] for k, v in p.items()})
+            m = 1 + ref.system_light_curve([bd], u, t).sum(-1)
+            w = ref.gaussian_loglike(m, y, sigma * np.ones(t.size))
+            assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    assert n_list >= 12  # most batches went through the list kernels
+
+
+def test_list_path_circular_bodies_and_single_sample():
+    rng = np.random.default_rng(9)
+    n_sets = 64
+    P = rng.uniform(0.8, 12, n_sets)
+    p = dict(period=P, time_transit=rng.uniform(0, 1, n_sets) * P, impact_param=rng.uniform(0, 1.1, n_sets),
+             radius=rng.uniform(0.02, 0.2, n_sets))
+    u = np.array([0.4, 0.1])
+    t = np.arange(15_000) * (10.0 / 1440.0) - 20.0
+    y = 1 + 2e-4 * rng.normal(size=t.size)
+    sys_ = _system(p)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 2e-4)
+    assert flags == 0 and items > 0
+    want = _oracle_loglike(p, u, t, y, 2e-4, range(0, n_sets, 5))
+    for s, w in want.items():
+        assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    # one time stamp: the list has at most n_sets items
+    ll1, items1, flags1 = _loglike_abi(sys_, u, t[7000:7001], y[7000:7001], 2e-4)
+    assert flags1 == 0 and items1 <= n_sets
+    want = _oracle_loglike(p, u, t[7000:7001], y[7000:7001], 2e-4, range(0, n_sets, 5))
+    for s, w in want.items():
+        assert abs(ll1[s] - w) <= 1e-12 * abs(w)
+
+
+def test_unsorted_or_nan_times_fall_back_on_the_device():
+    from jaxoplanet_b200 import workloads as W
+
+    p, ub, t, noise, sigma = W.c3(96, 12_000)
+    y = 1 + noise
+    sys_ = _system(p)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(t.size)
+    tu, yu = t[perm], y[perm]
+    ll, items, flags = _loglike_abi(sys_, ub, tu, yu, sigma)
+    assert flags & 1
+    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, ub, tu, yu, sigma))
+    assert np.array_equal(ll, ll2)  # the same kernels produced both
+    want = _oracle_loglike(p, ub, tu, yu, sigma, [0, 50, 95])
+    for s, w in want.items():
+        assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    # a single inversion at the very end is enough
+    t1 = t.copy()
+    t1[-1] = t1[-2] - 1e-9
+    _, _, f1 = _loglike_abi(sys_, ub, t1, y, sigma)
+    assert f1 & 1
+    # a NaN time stamp breaks the binary searches: not sorted
+    t2 = t.copy()
+    t2[777] = np.nan
+    _, _, f3 = _loglike_abi(sys_, ub, t2, y, sigma)
+    assert f3 & 1
+
+
+def test_list_overflow_falls_back_and_always_bodies_fit_when_few():
+    # e >= 0.99 bodies have no provable window (BODY_ALWAYS): every sample goes on the list
+    rng = np.random.default_rng(11)
+    n_t = 30_000
+    t = np.arange(n_t) * (2.0 / 1440.0)
+    y = 1 + 5e-4 * rng.normal(size=n_t)
+    u = np.array([0.3, 0.2])
+
+    def sets(n_sets, n_always):
+        P = rng.uniform(2, 5, n_sets)
+        e = rng.uniform(0, 0.3, n_sets)
+        e[:n_always] = 0.992
+        return dict(period=P, time_transit=rng.uniform(0, 1, n_sets) * P, eccentricity=e,
+                    omega_peri=rng.uniform(-np.pi, np.pi, n_sets), impact_param=rng.uniform(0, 1, n_sets),
+                    radius=rng.uniform(0.03, 0.15, n_sets))
+
+    p = sets(64, 64)  # 64 x 30000 items > 64 x 30000 / 8 + 65536
+    sys_ = _system(p)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)
+    assert flags == 2 and items > 64 * n_t / 8 + 65536
+    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, 5e-4))
+    assert np.array_equal(ll, ll2)
+    p = sets(64, 2)  # two full-length slices fit
+    sys_ = _system(p)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)
+    assert flags == 0 and items >= 2 * n_t
+    want = _oracle_loglike(p, u, t, y, 5e-4, [0, 1, 2, 33, 63])
+    for s, w in want.items():
+        assert abs(ll[s] - w) <= 1e-12 * abs(w)
+
+
+def test_list_path_no_out_of_bounds_writes():
+    # sentinels around the workspace and the output; ragged sizes
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    dev = A.device()
+    for n_sets, n_t in ((1, 1), (3, 77), (33, 4099), (130, 10_001)):
+        p, ub, t, noise, sigma = W.c3(n_sets, n_t)
+        bodies, _, _ = pack_bodies(_system(p))
+        bodies = bodies.to(dev).contiguous()
+        u = torch.as_tensor(ub, device=dev).contiguous()
+        td = torch.as_tensor(t, device=dev)
+        yd = torch.as_tensor(1 + noise, device=dev)
+        sd = torch.full((1,), sigma, dtype=torch.float64, device=dev)
+        nbytes = int(_lib.load().jxp_system_workspace_bytes(n_sets, 1, n_t))
+        guard = 4096
+        buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=dev)
+        ws = buf[guard:guard + nbytes]
+        assert ws.data_ptr() % 256 == 0
+        out = torch.full((n_sets + 16,), -7.0, dtype=torch.float64, device=dev)
+        _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 1, u.data_ptr(), 2, 2,
+                  td.data_ptr(), n_t, 0.0, 0, 0, 10, 0, None, None, yd.data_ptr(), sd.data_ptr(), 0,
+                  out[8:].data_ptr(), ws.data_ptr(), nbytes, A.stream_ptr())
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
+        assert bool((out[:8] == -7.0).all()) and bool((out[8 + n_sets:] == -7.0).all())
+        assert bool(torch.isfinite(out[8:8 + n_sets]).all())
