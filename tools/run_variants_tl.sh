@@ -1,7 +1,10 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-echo "== base"; python tools/tl_bench.py 2>&1 | grep -A3 '"list"' | tr -d '\n'; echo
+f() { python tools/tl_bench.py 2>&1 | python -c "
+import json,sys
+d=json.load(sys.stdin)
+print({k:(round(v['kernel_ms'],4) if isinstance(v,dict) else v) for k,v in d.items()}, 'step', round(d['list']['step_ms'],4))"; }
+echo "== base"; f
 for so in jaxoplanet_b200/lib/variants/tl_*.so; do
-  echo "== $(basename $so .so)"
-  JXP_LIB_PATH=$PWD/$so python tools/tl_bench.py 2>&1 | grep -A3 '"list"' | tr -d '\n'; echo
+  echo "== $(basename $so .so)"; JXP_LIB_PATH=$PWD/$so f
 done
