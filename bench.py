@@ -319,6 +319,13 @@ def run_ours(args, rank, local_rank, world):
     stats = (ctypes.c_int64 * 2)()
     _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
     n_kep, n_ld = int(stats[0]), int(stats[1])
+    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
+    list_items, list_used = int(stats[0]), int(stats[0]) > 0 and int(stats[1]) == 0
+    # sorted time stamps: the in-window samples go on a work list (k_tl_*); the window-test kernels are
+    # still launched behind them and return at once (the choice is made on the device)
+    launches = (["k_sys_prep_ll", "k_tl_build", "k_tl_eval", "k_tl_reduce", "k_system_pair (returns at once)",
+                 "k_loglike_final (returns at once)"] if list_used
+                else ["k_sys_prep_ll", "k_system_pair", "k_loglike_final"])
 
     def max_over_ranks(x):
         if world == 1:
@@ -419,14 +426,19 @@ def run_ours(args, rank, local_rank, world):
         pass
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_system_pair"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[
+            "k_tl_eval" if list_used else "k_system_pair"]
         traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_system_pair<1>", "achieved": achieved, "peak": fp64_peak,
+        "bound": "fp64", "kernel": "k_tl_eval<1>" if list_used else "k_system_pair<1>", "achieved": achieved,
+        "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
-        "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (FP64-bound kernel: HBM is idle)",
+        "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (FP64-bound kernel; the list "
+                        "path reads its 8-byte items and writes the chi^2 terms over them: 13 M items x 8 B each way, "
+                        "part of the writes still in L2 when the kernel ends)",
+        "list_items": list_items,
         "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
         "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
         "executed": {"kepler_solves": n_kep, "ld_evaluations": n_ld, "points": n_sets * n_times,
@@ -508,8 +520,8 @@ def run_ours(args, rank, local_rank, world):
                 "python_api": {"value": points_per_step / (py_ms * 1e-3), "unit": "points/s", "ms_per_step": py_ms,
                                "path": "light_curves.limb_dark.log_likelihood(System(...).add_body(**sampled elements), u)"
                                        "(t, y, sigma): NumPy in, NumPy out, System rebuilt every step"}},
-        "gpu_launches": 4 * args.steps,
-        "gpu_launches_per_step": ["k_sys_prep", "k_loglike_prep", "k_system_pair", "k_loglike_final"],
+        "gpu_launches": len(launches) * args.steps,
+        "gpu_launches_per_step": launches,
         "clocks": clocks, "secondary": secondary,
     }
     emit(line)
