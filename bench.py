@@ -319,8 +319,9 @@ def run_ours(args, rank, local_rank, world):
     stats = (ctypes.c_int64 * 2)()
     _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
     n_kep, n_ld = int(stats[0]), int(stats[1])
-    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
-    list_items, list_used = int(stats[0]), int(stats[0]) > 0 and int(stats[1]) == 0
+    lstats = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(lstats), stream())
+    list_items, list_used = int(lstats[0]), int(lstats[0]) > 0 and int(lstats[1]) == 0
     # sorted time stamps: the in-window samples go on a work list (k_tl_*); the window-test kernels are
     # still launched behind them and return at once (the choice is made on the device)
     launches = (["k_sys_prep_ll", "k_tl_build", "k_tl_eval", "k_tl_reduce", "k_system_pair (returns at once)",

@@ -164,9 +164,11 @@ int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, in
 /* Measurement helper: which kernels the LAST log-likelihood call on this workspace used.  With
  * sorted time stamps, one body and no exposure integration the in-window samples are expanded
  * into a work list in the workspace (DESIGN.md "transit list"); the choice is made on the device.
- * stats_host[0] = items in the list, stats_host[1] = 0 when the list kernels produced the
- * result (and stats_host[0] > 0), bit 0: time stamps not sorted, bit 1: the list did not fit
- * the workspace -- in both cases the window-test kernels produced it.  SYNCHRONISES `stream`. */
+ * stats_host (4 x int64): [0] = items in the list, [1] = 0 when the list kernels produced the
+ * result (and [0] > 0), bit 0: time stamps not sorted, bit 1: the list did not fit the workspace --
+ * in both cases the window-test kernels produced it; [2] = items on the sub-list of samples
+ * estimated to have the planet fully inside the stellar disk, [3] = 64-item chunks whose items all
+ * passed the b < 1 - r check and took the constant-node flux code.  SYNCHRONISES `stream`. */
 int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
                           int64_t n_times, int64_t* stats_host, void* stream);
 

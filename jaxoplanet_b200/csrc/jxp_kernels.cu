@@ -446,10 +446,10 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
   L.off_tl_off = L.off_tl_cnt = L.off_tl_items = off;
   L.tl_cap = 0;
   if (n_bodies == 1) {
-    L.off_tl_off = off;
-    off = align_up(off + sizeof(unsigned long long) * (size_t)n_sets, 256);
-    L.off_tl_cnt = off;
-    off = align_up(off + sizeof(unsigned) * (size_t)n_sets, 256);
+    L.off_tl_off = off;  // per set: first item on the inside list, on the edge list
+    off = align_up(off + 2 * sizeof(unsigned long long) * (size_t)n_sets, 256);
+    L.off_tl_cnt = off;  // per set: items on the inside list, on the edge list
+    off = align_up(off + 2 * sizeof(unsigned) * (size_t)n_sets, 256);
     L.off_tl_items = off;
     L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 8ull + 65536ull;
     off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
@@ -504,8 +504,10 @@ __device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ 
   if (i == 0) {  // executed-work counters of this call (jxp_system_stats)
     counters[0] = 0ull;
     counters[1] = 0ull;
-    counters[2] = 0ull;  // transit list: items allocated
+    counters[2] = 0ull;  // transit list: items on the inside list
     counters[3] = 0ull;  // transit list: TL_UNSORTED | TL_OVERFLOW (non-zero: list path off)
+    counters[4] = 0ull;  // transit list: items on the edge list
+    counters[5] = 0ull;  // transit list: chunks evaluated with the inside-the-disk flux code
   }
   if (i % n_bodies == 0) {
     const int s = i / n_bodies;
@@ -533,8 +535,12 @@ __device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ 
 constexpr int LL_NCTA = 64;
 constexpr int LL_SCAL0 = 8;
 constexpr int LL_FLAG0 = LL_SCAL0 + 2 * 64;  // per-CTA "time stamps not sorted" flags (list path)
-// tl_state[1] of the transit-list path (tl_state[0] = items allocated); zeroed by k_sys_prep
+// tl_state[1] of the transit-list path (tl_state[0], [2] = items on the inside / edge list); zeroed by
+// k_sys_prep.  The two lists share one buffer (inside from the bottom, edge from the top).
 constexpr unsigned long long TL_UNSORTED = 1ull, TL_OVERFLOW = 2ull;
+__device__ __forceinline__ bool tl_active(const unsigned long long* __restrict__ st, unsigned long long cap) {
+  return st[1] == 0ull && st[0] + st[2] <= cap;
+}
 template <typename T>
 __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
@@ -635,9 +641,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_loglike_final(const double* __restrict__ partial, int n_tiles, int n_sets,
                 const double* __restrict__ scalars, T* __restrict__ loglike,
-                const unsigned long long* __restrict__ tl_state = nullptr) {
+                const unsigned long long* __restrict__ tl_state = nullptr, unsigned long long tl_cap = 0) {
   __shared__ double sh[8][33];
-  if (tl_state != nullptr && tl_state[1] == 0ull) return;  // the transit-list kernels did the work
+  if (tl_state != nullptr && tl_active(tl_state, tl_cap)) return;  // the transit-list kernels did the work
   const int ls = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int s = blockIdx.x * 32 + ls;
   double acc = 0.0;
@@ -672,10 +678,11 @@ struct SysArgs {
   double* partial;  // [n_wtiles][n_sets]
   unsigned long long* counters;  // [2]: Kepler solves, limb-darkening evaluations executed
   // transit-list path (nullptr: not used by this call)
-  unsigned long long* tl_state;  // [0] items allocated, [1] TL_UNSORTED | TL_OVERFLOW
-  unsigned long long* tl_items;  // [tl_cap] (set << 32 | sample), overwritten by the chi^2 term
-  unsigned long long* tl_off;    // [n_sets] first item of the set
-  unsigned* tl_cnt;              // [n_sets] items of the set
+  unsigned long long* tl_state;  // [0] items on the inside list, [1] TL_UNSORTED | TL_OVERFLOW, [2] on the edge list
+  unsigned long long* tl_items;  // [tl_cap] (set << 32 | sample), overwritten by the chi^2 term; inside
+                                 // list = [0, state[0]), edge list = [cap - state[2], cap)
+  unsigned long long* tl_off;    // [n_sets][2] offset of the set's slice in the inside / edge list
+  unsigned* tl_cnt;              // [n_sets][2] items of the set on the inside / edge list
   unsigned long long tl_cap;
   const double* scalars;
   double* loglike;
@@ -1271,7 +1278,7 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
   int* const group_ctr = a.tile_ctr;
   int* const tile_ctr = a.tile_ctr + 1;
   const unsigned lt = (1u << lane) - 1u;
-  if (a.tl_state != nullptr && a.tl_state[1] == 0ull) return;  // the transit-list kernels did the work
+  if (a.tl_state != nullptr && tl_active(a.tl_state, a.tl_cap)) return;  // the transit-list kernels did the work
 
   int scan = -1;
   const int home = (int)(blockIdx.x % (unsigned)n_groups);
@@ -1657,9 +1664,11 @@ __global__ void __launch_bounds__(128) k_tl_build(const __grid_constant__ SysArg
       }
     }
   }
-  auto interval = [&](long long k, unsigned& lo, unsigned& hi) {
-    lo = 0;
-    hi = 0;
+  const double w_in = all ? 0.0 : c.win_in;
+  // transit k -> sample range [lo, hi) in the window and the part [ilo, ihi) of it estimated to have the
+  // planet fully inside the disk (at least 8 samples, else empty)
+  auto interval = [&](long long k, unsigned& lo, unsigned& hi, unsigned& ilo, unsigned& ihi) {
+    lo = hi = ilo = ihi = 0;
     if (k >= n_tr) return;
     if (all) {
       hi = n;
@@ -1669,61 +1678,91 @@ __global__ void __launch_bounds__(128) k_tl_build(const __grid_constant__ SysArg
     const double ta = fma(base + wlo, P, t0ref), tb = fma(base + whi, P, t0ref);
     lo = tl_search<false>(a.t, n, fmin(ta, tb), t_first, inv_dt);
     hi = tl_search<true>(a.t, n, fmax(ta, tb), t_first, inv_dt);
+    ilo = ihi = lo;
+    if (w_in > 0.0 && hi - lo >= 8u) {
+      const double tc = fma(base - w_in, P, t0ref), td = fma(base + w_in, P, t0ref);
+      unsigned i0 = tl_search<false>(a.t, n, fmin(tc, td), t_first, inv_dt);
+      unsigned i1 = tl_search<true>(a.t, n, fmax(tc, td), t_first, inv_dt);
+      i0 = i0 < lo ? lo : (i0 > hi ? hi : i0);
+      i1 = i1 < i0 ? i0 : (i1 > hi ? hi : i1);
+      if (i1 - i0 >= 8u) {
+        ilo = i0;
+        ihi = i1;
+      }
+    }
   };
   // the first 64 transits stay in registers between the counting and the writing pass
-  unsigned lo0, hi0, lo1, hi1;
-  interval(lane, lo0, hi0);
-  interval(32 + lane, lo1, hi1);
-  unsigned long long cnt = (unsigned long long)(hi0 - lo0) + (hi1 - lo1);
+  unsigned lo0, hi0, il0, ih0, lo1, hi1, il1, ih1;
+  interval(lane, lo0, hi0, il0, ih0);
+  interval(32 + lane, lo1, hi1, il1, ih1);
+  unsigned long long cntA = (unsigned long long)(ih0 - il0) + (ih1 - il1);
+  unsigned long long cntB = (unsigned long long)(hi0 - lo0) + (hi1 - lo1) - cntA;
   for (long long k0 = 64; k0 < n_tr; k0 += 32) {
-    unsigned lo, hi;
-    interval(k0 + lane, lo, hi);
-    cnt += hi - lo;
+    unsigned lo, hi, il, ih;
+    interval(k0 + lane, lo, hi, il, ih);
+    cntA += ih - il;
+    cntB += (hi - lo) - (ih - il);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  unsigned long long off = 0;
-  if (lane == 0) off = atomicAdd(a.tl_state, cnt);
-  off = __shfl_sync(0xffffffffu, off, 0);
-  if (lane == 0) {
-    a.tl_off[s] = off;
-    a.tl_cnt[s] = (unsigned)cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    cntA += __shfl_xor_sync(0xffffffffu, cntA, o);
+    cntB += __shfl_xor_sync(0xffffffffu, cntB, o);
   }
-  if (off + cnt > a.tl_cap) {
+  unsigned long long offA = 0, offB = 0;
+  if (lane == 0) {
+    offA = atomicAdd(a.tl_state, cntA);
+    offB = atomicAdd(a.tl_state + 2, cntB);
+    a.tl_off[2 * s] = offA;
+    a.tl_off[2 * s + 1] = offB;
+    a.tl_cnt[2 * s] = (unsigned)cntA;
+    a.tl_cnt[2 * s + 1] = (unsigned)cntB;
+  }
+  offA = __shfl_sync(0xffffffffu, offA, 0);
+  offB = __shfl_sync(0xffffffffu, offB, 0);
+  // no write may leave the buffer; whether the two lists ran into each other is only known when every
+  // set has allocated: tl_active() checks the totals in the kernels that follow
+  if (offA + cntA > a.tl_cap || offB + cntB > a.tl_cap) {
     if (lane == 0) atomicOr(a.tl_state + 1, TL_OVERFLOW);
     return;
   }
-  unsigned long long* out = a.tl_items + off;
+  unsigned long long* outA = a.tl_items + offA;
+  unsigned long long* outB = a.tl_items + (a.tl_cap - offB - cntB);
   const unsigned long long tag = (unsigned long long)s << 32;
   for (long long k0 = 0; k0 < n_tr; k0 += 32) {
-    unsigned lo, hi;
+    unsigned lo, hi, il, ih;
     if (k0 == 0) {
-      lo = lo0;
-      hi = hi0;
+      lo = lo0; hi = hi0; il = il0; ih = ih0;
     } else if (k0 == 32) {
-      lo = lo1;
-      hi = hi1;
+      lo = lo1; hi = hi1; il = il1; ih = ih1;
     } else {
-      interval(k0 + lane, lo, hi);
+      interval(k0 + lane, lo, hi, il, ih);
     }
-    const unsigned cl = hi - lo;
-    unsigned incl = cl;
+    const unsigned cA = ih - il, cB = (hi - lo) - cA;
+    unsigned inA = cA, inB = cB;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      const unsigned vA = __shfl_up_sync(0xffffffffu, inA, o);
+      const unsigned vB = __shfl_up_sync(0xffffffffu, inB, o);
+      if (lane >= o) {
+        inA += vA;
+        inB += vB;
+      }
     }
-    const unsigned excl = incl - cl;
-    unsigned nz = __ballot_sync(0xffffffffu, cl != 0u);
+    const unsigned exA = inA - cA, exB = inB - cB;
+    unsigned nz = __ballot_sync(0xffffffffu, hi != lo);
     while (nz) {
       const int j = __ffs(nz) - 1;
       nz &= nz - 1;
-      const unsigned lj = __shfl_sync(0xffffffffu, lo, j);
-      const unsigned cj = __shfl_sync(0xffffffffu, cl, j);
-      const unsigned ej = __shfl_sync(0xffffffffu, excl, j);
-      for (unsigned i = lane; i < cj; i += 32) out[ej + i] = tag | (unsigned long long)(lj + i);
+      const unsigned lj = __shfl_sync(0xffffffffu, lo, j), hj = __shfl_sync(0xffffffffu, hi, j);
+      const unsigned ilj = __shfl_sync(0xffffffffu, il, j), ihj = __shfl_sync(0xffffffffu, ih, j);
+      const unsigned eAj = __shfl_sync(0xffffffffu, exA, j), eBj = __shfl_sync(0xffffffffu, exB, j);
+      const unsigned nAj = ihj - ilj, nB0 = ilj - lj, nBj = (hj - lj) - nAj;
+      for (unsigned i = lane; i < nAj; i += 32) outA[eAj + i] = tag | (unsigned long long)(ilj + i);
+      for (unsigned i = lane; i < nBj; i += 32)
+        outB[eBj + i] = tag | (unsigned long long)(i < nB0 ? lj + i : ihj + (i - nB0));
     }
-    out += __shfl_sync(0xffffffffu, incl, 31);
+    outA += __shfl_sync(0xffffffffu, inA, 31);
+    outB += __shfl_sync(0xffffffffu, inB, 31);
   }
 }
 
@@ -1735,23 +1774,35 @@ __global__ void __launch_bounds__(128) k_tl_build(const __grid_constant__ SysArg
 #endif
 template <int PU>
 __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_constant__ SysArgs<double> a) {
-  if (a.tl_state[1] != 0ull) return;
-  const unsigned long long total = a.tl_state[0];
-  const unsigned long long n_chunks = (total + 63ull) >> 6;
+  if (!tl_active(a.tl_state, a.tl_cap)) return;
+  const unsigned long long totA = a.tl_state[0], totB = a.tl_state[2];
+  const unsigned long long nA = (totA + 63ull) >> 6, nB = (totB + 63ull) >> 6;
+  const unsigned long long n_chunks = nA + nB;  // chunks of the inside list, then of the edge list
   const int lane = threadIdx.x & 31;
   const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
   unsigned long long ch = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  unsigned n_kep = 0, n_ld = 0;
+  unsigned n_kep = 0, n_ld = 0, n_fast = 0;
   if (ch >= n_chunks) return;
   const BodyC<double>* __restrict__ bodies = a.bodies;
   const SetC<double>* __restrict__ sets = a.sets;
   const int lmax = sets[0].lmax;  // one law length per call
+  // physical index of the first item of chunk c and the number of valid items in it
+  auto chunk_base = [&](unsigned long long c, unsigned long long& base, unsigned& valid) {
+    if (c < nA) {
+      base = c * 64ull;
+      valid = (unsigned)(totA - base < 64ull ? totA - base : 64ull);
+    } else {
+      const unsigned long long p = (c - nA) * 64ull;
+      base = a.tl_cap - totB + p;
+      valid = (unsigned)(totB - p < 64ull ? totB - p : 64ull);
+    }
+  };
+  unsigned long long base, nbase = 0;
+  unsigned valid, nvalid = 0;
+  chunk_base(ch, base, valid);
   unsigned long long nxt[2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const unsigned long long p = ch * 64ull + 32 * h + lane;
-    nxt[h] = a.tl_items[p < total ? p : ch * 64ull];
-  }
+  for (int h = 0; h < 2; ++h) nxt[h] = a.tl_items[base + ((unsigned)(32 * h + lane) < valid ? 32 * h + lane : 0)];
   for (; ch < n_chunks; ch += nw) {
     bool have[2], intr[2];
     double Mr[2], e[2], ome[2], ope[2], s1[2], iope[2], sf[2], cf[2], bq[2], rq[2], tot[2];
@@ -1759,16 +1810,16 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
     bool circ = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      have[h] = ch * 64ull + 32 * h + lane < total;
+      have[h] = (unsigned)(32 * h + lane) < valid;
       slq[h] = (unsigned)(nxt[h] >> 32);
       idxq[h] = (unsigned)nxt[h];
     }
-    if (ch + nw < n_chunks) {  // next chunk's items in flight while this one is evaluated
+    const bool more = ch + nw < n_chunks;
+    if (more) {  // next chunk's items in flight while this one is evaluated
+      chunk_base(ch + nw, nbase, nvalid);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const unsigned long long p = (ch + nw) * 64ull + 32 * h + lane;
-        nxt[h] = a.tl_items[p < total ? p : (ch + nw) * 64ull];
-      }
+      for (int h = 0; h < 2; ++h)
+        nxt[h] = a.tl_items[nbase + ((unsigned)(32 * h + lane) < nvalid ? 32 * h + lane : 0)];
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -1787,6 +1838,12 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
       for (int h = 0; h < 2; ++h)
         if (bodies[slq[h]].flags & BODY_CIRCULAR) jsincos(Mr[h], &sf[h], &cf[h]);  // keplerian.py:539-540
     }
+    // Which flux code an item gets must not depend on its neighbours in the chunk (the slices of the
+    // list are handed out by atomics, so the neighbours change from run to run): an item takes the
+    // inside-the-disk code iff it is on the inside list AND itself has b < 1 - r.  A chunk whose items
+    // disagree (about 1 % of the inside list) runs both codes.
+    const bool on_inside_list = ch < nA;
+    bool fast[2], want_gen = false, want_fast = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const BodyC<double>& c = bodies[slq[h]];
@@ -1796,14 +1853,31 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
       intr[h] = have[h] && (Z > 0.0) && !(bq[h] >= c.onepr);
       n_kep += have[h] ? 1u : 0u;
       n_ld += intr[h] ? 1u : 0u;
+      const double ar = fabs(rq[h]);
+      fast[h] = on_inside_list && (bq[h] < 1.0 - ar) && (ar < 1.0);  // what ld_solution_inside_n needs
+      want_gen = want_gen || (intr[h] && !fast[h]);
+      want_fast = want_fast || (intr[h] && fast[h]);
+      tot[h] = 0.0;
     }
-    {
+    want_gen = __any_sync(0xffffffffu, want_gen);
+    want_fast = __any_sync(0xffffffffu, want_fast);
+    n_fast += (want_fast && !want_gen) ? 1u : 0u;
+    if (want_gen) {
       double s0[2], s1v[2], s2[2];
       ld_solution_n<2, PU>(bq, rq, lmax, s0, s1v, s2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const SetC<double>& sc = sets[slq[h]];
-        tot[h] = intr[h] ? ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2) : 0.0;
+        if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2);
+      }
+    }
+    if (want_fast) {
+      double s0[2], s1v[2], s2[2];
+      ld_solution_inside_n<2>(bq, rq, lmax, s0, s1v, s2);  // constant node cosines, no atan2
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const SetC<double>& sc = sets[slq[h]];
+        if (intr[h] && fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2);
       }
     }
 #pragma unroll
@@ -1815,51 +1889,59 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
         const double mw = tot[h] * w;
         dchi = (-mw) * (2.0 * r0 - mw);
       }
-      if (have[h]) reinterpret_cast<double*>(a.tl_items)[ch * 64ull + 32 * h + lane] = dchi;
+      if (have[h]) reinterpret_cast<double*>(a.tl_items)[base + 32 * h + lane] = dchi;
     }
+    base = nbase;
+    valid = nvalid;
   }
   n_kep = __reduce_add_sync(0xffffffffu, n_kep);
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
   if (lane == 0) {
     atomicAdd(a.counters + 0, (unsigned long long)n_kep);
     atomicAdd(a.counters + 1, (unsigned long long)n_ld);
+    atomicAdd(a.counters + 5, (unsigned long long)n_fast);
   }
 }
 
 __global__ void __launch_bounds__(128) k_tl_reduce(const __grid_constant__ SysArgs<double> a) {
-  if (a.tl_state[1] != 0ull) return;
+  if (!tl_active(a.tl_state, a.tl_cap)) return;
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= a.n_sets) return;
-  const double* __restrict__ d = reinterpret_cast<const double*>(a.tl_items) + a.tl_off[s];
-  const unsigned cnt = a.tl_cnt[s];
-  // 8 independent lane-strided sums (fixed order); the 8 loads of a round are issued together
-  double acc[8];
+  // one slice: 8 independent lane-strided sums (fixed order), software-pipelined so that the loads of
+  // round r + 1 are in flight while round r is added; returns this lane's share
+  auto slice_sum = [&](const double* __restrict__ d, unsigned cnt) {
+    double acc[8];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
-  const unsigned full = cnt & ~255u;
-  unsigned i = lane;
-  if (i < full) {  // software-pipelined: round r + 1 is in flight while round r is added
-    double v[8];
+    for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+    const unsigned full = cnt & ~255u;
+    unsigned i = lane;
+    if (i < full) {
+      double v[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = __ldcs(d + i + 32 * m);
+      for (int m = 0; m < 8; ++m) v[m] = __ldcs(d + i + 32 * m);
 #pragma unroll 1
-    for (i += 256; i < full; i += 256) {
-      double w[8];
+      for (i += 256; i < full; i += 256) {
+        double w[8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) w[m] = __ldcs(d + i + 32 * m);
+        for (int m = 0; m < 8; ++m) w[m] = __ldcs(d + i + 32 * m);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] += v[m];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = w[m];
+      }
 #pragma unroll
       for (int m = 0; m < 8; ++m) acc[m] += v[m];
-#pragma unroll
-      for (int m = 0; m < 8; ++m) v[m] = w[m];
     }
 #pragma unroll
-    for (int m = 0; m < 8; ++m) acc[m] += v[m];
-  }
-#pragma unroll
-  for (int m = 0; m < 8; ++m)
-    if (i + 32 * m < cnt) acc[m] += d[i + 32 * m];  // i + 224 < full + 256: no wrap for cnt < 2^32 - 256
-  double tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (int m = 0; m < 8; ++m)
+      if (i + 32 * m < cnt) acc[m] += d[i + 32 * m];  // i + 224 < full + 256: no wrap for cnt < 2^32 - 256
+    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  };
+  const double* __restrict__ d = reinterpret_cast<const double*>(a.tl_items);
+  const unsigned cntA = a.tl_cnt[2 * s], cntB = a.tl_cnt[2 * s + 1];
+  double tot = slice_sum(d + a.tl_off[2 * s], cntA);
+  tot += slice_sum(d + (a.tl_cap - a.tl_off[2 * s + 1] - cntB), cntB);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   // set-independent terms: the LL_NCTA pairs of k_loglike_prep added in order (as k_loglike_final does)
@@ -2067,7 +2149,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       if (eo != cudaSuccess || per_sm < 1)
         return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
       // the list length is only known on the device: a resident grid, chunks strided over it
-      const int64_t max_chunks = (int64_t)((L.tl_cap + 63ull) / 64ull);
+      const int64_t max_chunks = (int64_t)((L.tl_cap + 63ull) / 64ull) + 1;
       const int64_t want = (max_chunks + 3) / 4;
       const int64_t resident = (int64_t)per_sm * sms;
       if (g_ev_start && ev_on("eval")) cudaEventRecord(g_ev_start, st);
@@ -2102,7 +2184,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       rc = check_launch("jxp_system_light_curve(pair)");
       if (rc != JXP_OK) return rc;
       k_loglike_final<T><<<(n_sets + 31) / 32, 256, 0, st>>>(d_partial, (int)n_wtiles, n_sets, d_scalars, loglike,
-                                                              a.tl_state);
+                                                              a.tl_state, a.tl_cap);
       return check_launch("jxp_system_light_curve(loglike final)");
     }
   }
@@ -2159,9 +2241,14 @@ extern "C" int jxp_system_list_stats(const void* workspace, int32_t n_sets, int3
                                  sizeof(SetC<double>), sizeof(double));
   const unsigned char* ws = static_cast<const unsigned char*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemcpyAsync(stats_host, ws + L.off_scalars + 4 * sizeof(double),
-                                  2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+  int64_t raw[4] = {0, 0, 0, 0};  // inside-list items, flags, edge-list items, fast chunks
+  cudaError_t e = cudaMemcpyAsync(raw, ws + L.off_scalars + 4 * sizeof(double), 4 * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  stats_host[0] = raw[0] + raw[2];
+  stats_host[1] = raw[1] | ((unsigned long long)(raw[0] + raw[2]) > L.tl_cap ? 2 : 0);
+  stats_host[2] = raw[0];
+  stats_host[3] = raw[3];
   if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_list_stats: %s", cudaGetErrorString(e));
   return JXP_OK;
 }

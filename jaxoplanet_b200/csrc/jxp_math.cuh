@@ -612,6 +612,83 @@ __device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const dou
   }
 }
 
+// ld_solution_n for points with the planet fully inside the disk, b < 1 - r and r < 1 (the caller
+// guarantees it): there kite_area = 0, kappa0 = atan2(+0, b^2 + r^2 - 1) = pi and kappa1 =
+// atan2(+0, b^2 - r^2 + 1) = 0 exactly, so the two atan2, the kite area and the ten node cosines
+// drop out: the node angles are pi (1 +- x_p) / 2, constants (c_gl10[2], the values the reference's
+// own argument rounding produces, as in K2's GL<10>::cpi).  Same pairing and summation order as the
+// general version; the `large` select of s0s2 (limb_dark.py:118) is kept.
+template <int N>
+__device__ __forceinline__ void ld_solution_inside_n(const double (&b_in)[N], const double (&r_in)[N],
+                                                     int lmax, double (&s0)[N], double (&s1)[N],
+                                                     double (&s2)[N]) {
+  const double pi = Num<double>::pi;
+  const double eps10 = 10.0 * Num<double>::eps;
+  double b[N], r[N], b2[N], r2[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    b[q] = fabs(b_in[q]);
+    r[q] = fabs(r_in[q]);
+    b2[q] = b[q] * b[q];
+    r2[q] = r[q] * r[q];
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double bpr = b[q] + r[q];
+    const double onembpr2 = (1.0 + bpr) * (1.0 - bpr);
+    const double eta2 = r2[q] * (r2[q] + b2[q] * 2.0) * 0.5;
+    const double delta = b[q] * r[q] * 4.0;
+    const bool large = onembpr2 + delta > delta;
+    const double s0l = (1.0 - r2[q]) * pi;
+    const double s2l = s0l * 2.0 + (eta2 - 0.5) * (4.0 * pi);
+    const double Alens = 0.0 + r2[q] * pi - 0.0 * 0.5;  // kappa1 + r^2 kappa0 - area / 2
+    const double s0s = pi - Alens;
+    const double s2s = s0s * 2.0 + (-(pi - 0.0) + eta2 * pi * 2.0 - 0.0 * (1.0 + r2[q] * 5.0 + b2[q]) * 0.25) * 2.0;
+    s0[q] = large ? s0l : s0s;
+    s2[q] = large ? s2l : s2s;
+  }
+  if (lmax < 1) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = 0.0;
+    return;
+  }
+  double two_br[N], r2pb2[N], acc[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    two_br[q] = b[q] * r[q] * 2.0;
+    r2pb2[q] = r2[q] + b2[q];
+    acc[q] = 0.0;
+  }
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const double wp = c_gl10[1][5 + p];
+    const double cm = c_gl10[2][5 + p], cq = c_gl10[2][4 - p];  // nodes +x_p, -x_p
+    double z2s[2 * N], z[2 * N], t[2 * N];
+    bool dead[2 * N];
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) {
+      const double omz2 = fma(-two_br[m >> 1], (m & 1) ? cq : cm, r2pb2[m >> 1]);
+      dead[m] = !((omz2 >= eps10) && (omz2 <= 1.0 - eps10));
+      z2s[m] = dead[m] ? 1.0 : 1.0 - omz2;
+    }
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2s[m]);
+#pragma unroll
+    for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2s[m], frcp_fast(z[m] + 1.0), 1.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const double ra = fma(-b[q], cm, r[q]) * t[2 * q];
+      const double rb = fma(-b[q], cq, r[q]) * t[2 * q + 1];
+      acc[q] = fma(wp, (dead[2 * q] ? 0.0 : ra) + (dead[2 * q + 1] ? 0.0 : rb), acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double P0 = (pi * 0.5) * (acc[q] * (r[q] * (2.0 / 3.0)));
+    s1[q] = -P0 - (0.0 - pi) * (2.0 / 3.0);
+  }
+}
+
 // Normalised Green's-basis coefficients for n_u <= 2, limb_dark.py:42-45, 87-99.
 template <typename S>
 __device__ __forceinline__ void ld_greens(int n_u, S u1, S u2, S& g0, S& g1, S& g2) {

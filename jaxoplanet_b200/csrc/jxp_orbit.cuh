@@ -21,6 +21,8 @@ struct BodyC {
   double inv_period;  // 1 / period              } transit-window pre-test
   double phase_c;     // window centre [cycles]  }
   double wlo, whi;    // window edges relative to the centre [cycles], margins included
+  double win_in;      // estimated half-width [cycles] of the part of the transit with the planet fully
+                      // inside the disk, slightly short; 0: none.  Only groups work, never decides a value.
   T e, ome, ope, s1me2, inv_ope;
   T cw, sw, ci, si;
   T na_ome2;  // -a (1 - e^2)
@@ -62,6 +64,7 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
   c.phase_c = 0.0;
   c.wlo = -1.0;
   c.whi = 1.0;
+  c.win_in = 0.0;
   const double sw = (double)c.sw, cw = (double)c.cw;
   const double ci = (double)c.ci, si = (double)c.si;
   const double rho = sqrt(sw * sw + cw * cw);
@@ -103,6 +106,25 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
   c.wlo = lo;
   c.whi = hi;
   c.flags &= ~BODY_ALWAYS;
+  // Fully-inside part (b < 1 - r) around mid-transit, estimated with straight-line motion at the
+  // conjunction speed: sqrt((1 - r)^2 - b0^2) / v, v = 2 pi (a / R*) (1 + e cos f_c) / sqrt(1 - e^2)
+  // stellar radii per cycle.  The list path uses it to put those samples on a list of their own so
+  // that whole warps take the constant-node flux code; every warp still checks b < 1 - r itself.
+  {
+    const double opec = 1.0 + e * cos(fc);
+    const double r0c = rho * a * (1.0 - e * e) / opec;
+    const double b0 = r0c * fabs(ci) / rstar;
+    const double rr = fabs((double)c.rr);
+    const double v = Num<double>::two_pi * (rho * a / rstar) * opec / sqrt(1.0 - e * e);
+    const double q2 = (1.0 - rr) * (1.0 - rr) - b0 * b0;
+    if (rr < 1.0 && b0 < 1.0 - rr && q2 > 0.0 && v > 0.0 && isfinite(v)) {
+#ifndef JXP_WIN_IN_FACTOR
+#define JXP_WIN_IN_FACTOR 0.97
+#endif
+      const double half = JXP_WIN_IN_FACTOR * sqrt(q2) / v;
+      if (half > 0.0 && half < hi && -half > lo) c.win_in = half;
+    }
+  }
 }
 
 // true when the sample at time tm cannot be in transit

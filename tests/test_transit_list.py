@@ -43,9 +43,9 @@ def _loglike_abi(system, u, t, y, sigma):
     _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 1, u.data_ptr(), n_u, u_stride,
               td.data_ptr(), n_t, 0.0, 0, 0, 10, 0, None, None, yd.data_ptr(), sd.data_ptr(),
               1 if sg.size > 1 else 0, out.data_ptr(), ws.data_ptr(), ws.numel(), A.stream_ptr())
-    stats = (ctypes.c_int64 * 2)()
+    stats = (ctypes.c_int64 * 4)()
     _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(stats), A.stream_ptr())
-    return out.cpu().numpy(), int(stats[0]), int(stats[1])
+    return out.cpu().numpy(), int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3])
 
 
 def _without_list(fn):
@@ -81,22 +81,33 @@ def test_list_path_matches_oracle_and_window_kernels_c3_like():
     truth = ref.system_light_curve([ref.orbital_body(**{k: v[0] for k, v in p.items()})], ub[0], t)[:, 0]
     y = 1 + truth + noise
     sys_ = _system(p)
-    ll, items, flags = _loglike_abi(sys_, ub, t, y, sigma)
+    ll, items, flags, inside, fast = _loglike_abi(sys_, ub, t, y, sigma)
     assert flags == 0 and 0.01 * 300 * 40_000 < items < 0.08 * 300 * 40_000
-    ll2, items2, flags2 = _without_list(lambda: _loglike_abi(sys_, ub, t, y, sigma))
+    ll2, items2, flags2 = _without_list(lambda: _loglike_abi(sys_, ub, t, y, sigma))[:3]
     assert items2 == 0  # the list kernels were not launched
     # two programs, different summation orders: terms of 1e-16 * 1 / sigma^2
     assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
     want = _oracle_loglike(p, ub, t, y, sigma, range(0, 300, 7))
     for s, w in want.items():
         assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    assert inside > 0.5 * items and fast > 0.9 * (inside // 64)  # most of the list takes the inside-the-disk code
+    # flux-level check of both flux codes: with y = 1 and a tiny sigma the likelihood is dominated by
+    # sum (lc / sigma)^2, so its relative error is twice the (weighted) relative error of lc itself --
+    # a systematic 1e-12 error of 1 + lc (the north-star bound) would show as ~2e-10 here
+    sharp, _, fs = _loglike_abi(sys_, ub, t, np.ones_like(t), 1e-6)[:3]
+    assert fs == 0
+    sharp_w = _without_list(lambda: _loglike_abi(sys_, ub, t, np.ones_like(t), 1e-6))[0]
+    assert np.max(np.abs(sharp - sharp_w) / np.abs(sharp_w)) <= 2e-12
+    want = _oracle_loglike(p, ub, t, np.ones_like(t), 1e-6, range(0, 300, 13))
+    worst = max(abs(sharp[s] - w) / abs(w) for s, w in want.items())
+    assert worst <= 2e-12, worst
     # bit-reproducible although the slices of the list are handed out by atomics
     for _ in range(3):
-        again, _, _ = _loglike_abi(sys_, ub, t, y, sigma)
+        again, _, _ = _loglike_abi(sys_, ub, t, y, sigma)[:3]
         assert np.array_equal(again, ll)
     # per-sample sigma
     sig_t = sigma * (1 + 0.2 * np.random.default_rng(5).uniform(size=t.size))
-    ll3, _, f3 = _loglike_abi(sys_, ub, t, y, sig_t)
+    ll3, _, f3 = _loglike_abi(sys_, ub, t, y, sig_t)[:3]
     assert f3 == 0
     want = _oracle_loglike(p, ub, t, y, sig_t, [0, 11, 299])
     for s, w in want.items():
@@ -126,10 +137,10 @@ def test_list_path_adversarial_orbits_and_irregular_times():
                  eccentricity=rng.uniform(0, 0.93, n_sets), omega_peri=rng.uniform(-np.pi, np.pi, n_sets),
                  impact_param=rng.uniform(0, 1.4, n_sets), radius=10 ** rng.uniform(-2.3, -0.5, n_sets))
         sys_ = _system(p, central)
-        ll, items, flags = _loglike_abi(sys_, u, t, y, sigma)
+        ll, items, flags = _loglike_abi(sys_, u, t, y, sigma)[:3]
         assert flags in (0, 2)
         n_list += flags == 0
-        ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, sigma))
+        ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, sigma))[:3]
         assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
         for s in range(batch % 3, n_sets, 3):
             bd = ref.orbital_body(central_mass=0.8, central_radius=1.3, **{k: v[s] for k, v in p.items()})
@@ -149,13 +160,13 @@ def test_list_path_circular_bodies_and_single_sample():
     t = np.arange(15_000) * (10.0 / 1440.0) - 20.0
     y = 1 + 2e-4 * rng.normal(size=t.size)
     sys_ = _system(p)
-    ll, items, flags = _loglike_abi(sys_, u, t, y, 2e-4)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 2e-4)[:3]
     assert flags == 0 and items > 0
     want = _oracle_loglike(p, u, t, y, 2e-4, range(0, n_sets, 5))
     for s, w in want.items():
         assert abs(ll[s] - w) <= 1e-12 * abs(w)
     # one time stamp: the list has at most n_sets items
-    ll1, items1, flags1 = _loglike_abi(sys_, u, t[7000:7001], y[7000:7001], 2e-4)
+    ll1, items1, flags1 = _loglike_abi(sys_, u, t[7000:7001], y[7000:7001], 2e-4)[:3]
     assert flags1 == 0 and items1 <= n_sets
     want = _oracle_loglike(p, u, t[7000:7001], y[7000:7001], 2e-4, range(0, n_sets, 5))
     for s, w in want.items():
@@ -171,9 +182,9 @@ def test_unsorted_or_nan_times_fall_back_on_the_device():
     rng = np.random.default_rng(3)
     perm = rng.permutation(t.size)
     tu, yu = t[perm], y[perm]
-    ll, items, flags = _loglike_abi(sys_, ub, tu, yu, sigma)
+    ll, items, flags = _loglike_abi(sys_, ub, tu, yu, sigma)[:3]
     assert flags & 1
-    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, ub, tu, yu, sigma))
+    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, ub, tu, yu, sigma))[:3]
     assert np.array_equal(ll, ll2)  # the same kernels produced both
     want = _oracle_loglike(p, ub, tu, yu, sigma, [0, 50, 95])
     for s, w in want.items():
@@ -181,12 +192,12 @@ def test_unsorted_or_nan_times_fall_back_on_the_device():
     # a single inversion at the very end is enough
     t1 = t.copy()
     t1[-1] = t1[-2] - 1e-9
-    _, _, f1 = _loglike_abi(sys_, ub, t1, y, sigma)
+    _, _, f1 = _loglike_abi(sys_, ub, t1, y, sigma)[:3]
     assert f1 & 1
     # a NaN time stamp breaks the binary searches: not sorted
     t2 = t.copy()
     t2[777] = np.nan
-    _, _, f3 = _loglike_abi(sys_, ub, t2, y, sigma)
+    _, _, f3 = _loglike_abi(sys_, ub, t2, y, sigma)[:3]
     assert f3 & 1
 
 
@@ -208,13 +219,13 @@ def test_list_overflow_falls_back_and_always_bodies_fit_when_few():
 
     p = sets(64, 64)  # 64 x 30000 items > 64 x 30000 / 8 + 65536
     sys_ = _system(p)
-    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)[:3]
     assert flags == 2 and items > 64 * n_t / 8 + 65536
-    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, 5e-4))
+    ll2, _, _ = _without_list(lambda: _loglike_abi(sys_, u, t, y, 5e-4))[:3]
     assert np.array_equal(ll, ll2)
     p = sets(64, 2)  # two full-length slices fit
     sys_ = _system(p)
-    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)
+    ll, items, flags = _loglike_abi(sys_, u, t, y, 5e-4)[:3]
     assert flags == 0 and items >= 2 * n_t
     want = _oracle_loglike(p, u, t, y, 5e-4, [0, 1, 2, 33, 63])
     for s, w in want.items():

@@ -36,8 +36,8 @@ for label, env in (("list", None), ("list_prep", "prep"), ("list_build", "build"
         torch.cuda.synchronize()
         tot += a.elapsed_time(b); ktot += ka.elapsed_time(kb)
     st = (ctypes.c_int64 * 2)(); _lib.call("jxp_system_stats", ws.data_ptr(), ns, 1, n_t, ctypes.addressof(st), A.stream_ptr())
-    ls = (ctypes.c_int64 * 2)(); _lib.call("jxp_system_list_stats", ws.data_ptr(), ns, 1, n_t, ctypes.addressof(ls), A.stream_ptr())
-    res[label] = dict(step_ms=tot / n, kernel_ms=ktot / n, kepler=int(st[0]), ld=int(st[1]), items=int(ls[0]), flags=int(ls[1]),
+    ls = (ctypes.c_int64 * 4)(); _lib.call("jxp_system_list_stats", ws.data_ptr(), ns, 1, n_t, ctypes.addressof(ls), A.stream_ptr())
+    res[label] = dict(step_ms=tot / n, kernel_ms=ktot / n, kepler=int(st[0]), ld=int(st[1]), items=int(ls[0]), flags=int(ls[1]), inside_items=int(ls[2]), fast_chunks=int(ls[3]),
                       ll0=float(ll[0]), tflops=(st[0] * 302 + st[1] * 746) / (ktot / n * 1e-3) / 1e12)
     res[label + "_ll"] = ll.clone()
 d = (res["list_ll"] - res["window_ll"]).abs() / res["window_ll"].abs()
