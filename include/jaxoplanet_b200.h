@@ -130,6 +130,11 @@ enum {
  * either way; this exists for measurement (DESIGN.md "window test"). */
 #define JXP_FLAG_NO_WINDOW 1
 
+/* Bytes of caller-provided device workspace (256-byte aligned) for one call of that shape: the
+ * derived records, 1 / sigma, partial sums and, for single-body systems, room for the work list of
+ * the log-likelihood path (8 bytes per in-window sample, sized for 1/8 of the grid + 65536
+ * items; when the list does not fit, or the time stamps are not sorted, the same call falls back
+ * to the window-test kernels on the device -- results agree to rounding either way). */
 size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times);
 
 int jxp_system_light_curve_f64(const double* bodies, int32_t n_sets, int32_t n_bodies,

@@ -1581,15 +1581,19 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
 // ranges (one per transit), found by binary search.  HBM is idle in this path, so the ranges are
 // expanded into an explicit work list in the caller's workspace:
 //   k_tl_build   one warp per set: transits that intersect [t_first, t_last] -> index ranges ->
-//                count -> one atomicAdd allocates the set's slice of the list -> items
-//                (set << 32 | sample) written coalesced.
-//   k_tl_eval    a flat, perfectly balanced map over the list, two items per lane through the same
-//                kepler_reduced_n<2> / ld_solution_n<2> code as k_system_pair: every lane of every
-//                warp does useful work, there is no queue, no window test and no reduction; the
-//                item's slot is overwritten with its chi^2 term.
-//   k_tl_reduce  one warp per set adds the set's slice in a fixed order (lane-strided sums, then
-//                a shuffle tree) -> loglike.  Which slice a set got depends on the atomics, the
-//                order of the terms inside it does not: bit-reproducible.
+//                count -> one atomicAdd per list allocates the set's slices -> items
+//                (set << 32 | sample) written coalesced.  Two lists share the buffer: samples
+//                estimated to have the planet fully inside the disk (BodyC::win_in) from the bottom,
+//                ingress / egress samples from the top.
+//   k_tl_eval    a flat, statically balanced map over the chunks of both lists, two items per lane
+//                through the same kepler_reduced_n<2> / ld_solution_n<2> code as k_system_pair:
+//                every lane of every warp does useful work, there is no queue, no window test and no
+//                reduction; the item's slot is overwritten with its chi^2 term.  Items of the inside
+//                list that really have b < 1 - r take ld_solution_inside_n<2> (constant node
+//                cosines, no atan2).
+//   k_tl_reduce  one warp per set adds the set's two slices in a fixed order (lane-strided sums,
+//                then a shuffle tree) -> loglike.  Which slice a set got depends on the atomics,
+//                the order of the terms inside it does not: bit-reproducible.
 // The decision is taken on the device (no synchronisation in the ABI): k_loglike_prep flags
 // unsorted / NaN time stamps, k_tl_build flags a list that does not fit the workspace; with a flag
 // set these kernels return at once and k_system_pair / k_loglike_final run, otherwise those two
