@@ -495,6 +495,7 @@ __device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ 
   c.ci = T(p[JXP_BODY_COS_INCL]);
   c.si = T(p[JXP_BODY_SIN_INCL]);
   c.na_ome2 = T(-a * (1.0 - e * e));
+  c.na = T(-a);
   c.inv_rstar = T(1.0 / rstar);
   const double rr = p[JXP_BODY_RADIUS] / rstar;
   c.rr = T(rr);
@@ -1836,7 +1837,7 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
       iope[h] = c.inv_ope;
       circ = circ || (c.flags & BODY_CIRCULAR);
     }
-    kepler_reduced_n<2>(Mr, e, ome, ope, s1, iope, sf, cf);
+    kepler_reduced_n<2, true>(Mr, e, ome, ope, s1, iope, sf, cf);  // (sin f, cos f) D
     if (__any_sync(0xffffffffu, circ)) {
 #pragma unroll
       for (int h = 0; h < 2; ++h)
@@ -1852,7 +1853,7 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
     for (int h = 0; h < 2; ++h) {
       const BodyC<double>& c = bodies[slq[h]];
       double Z;
-      sky_position(c, sf[h], cf[h], bq[h], Z);
+      sky_position_xy(c, sf[h], cf[h], bq[h], Z);
       rq[h] = c.rr;
       intr[h] = have[h] && (Z > 0.0) && !(bq[h] >= c.onepr);
       n_kep += have[h] ? 1u : 0u;

@@ -130,7 +130,11 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
 // (tools/ubench/dfma_lat.cu) a stream with one chain per warp saturates at 67 % of the FP64 pipe
 // however many warps are resident, two chains reach 80 %, four 92 %.  Same arithmetic as
 // kepler_reduced, operation for operation.
-template <int N>
+// XY: return (sin f, cos f) times D = (1-e) c^2 + (1+e) s^2 instead (no division).  The position
+// needs exactly these: 1 + e cos f = (1 - e^2) (c^2 + s^2) / D, so r0 = -a (1 - e^2) / (1 + e cos f)
+// = -a D and (r0 cos f, r0 sin f) = -a (cos f D, sin f D) -- keplerian.py:630-632 without its division
+// and without the 1 / D of the half-angle formulas (c^2 + s^2 = 1 to rounding).
+template <int N, bool XY = false>
 __device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const double (&e)[N],
                                                  const double (&ome)[N], const double (&ope)[N],
                                                  const double (&s1me2)[N], const double (&inv_ope)[N],
@@ -187,6 +191,15 @@ __device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const do
     c[q] = fma(hc[q], ch, -hs[q] * sh);
     a[q] = ome[q] * (c[q] * c[q]);
     b[q] = ope[q] * (s[q] * s[q]);
+  }
+  if (XY) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const double sf = 2.0 * s1me2[q] * s[q] * c[q];
+      sinf[q] = high[q] ? -sf : sf;
+      cosf[q] = a[q] - b[q];
+    }
+    return;
   }
 #pragma unroll
   for (int q = 0; q < N; ++q) invD[q] = jrcp(a[q] + b[q]);

@@ -26,6 +26,7 @@ struct BodyC {
   T e, ome, ope, s1me2, inv_ope;
   T cw, sw, ci, si;
   T na_ome2;  // -a (1 - e^2)
+  T na;       // -a
   T inv_rstar, rr, onepr;
   int flags;
   int pad;
@@ -156,6 +157,17 @@ __device__ __forceinline__ void sky_position_g(const S& e, const S& cw, const S&
   const S Y = ci * y1;  // :575-576
   Z = -(si * y1);
   b = jsqrt(x1 * x1 + Y * Y) * inv_rstar;  // light_curves/limb_dark.py:53
+}
+
+// The same from (yD, xD) = (sin f, cos f) D of kepler_reduced_n<N, true>: (x0, y0) = -a (xD, yD).
+template <typename T>
+__device__ __forceinline__ void sky_position_xy(const BodyC<T>& c, T yD, T xD, T& b, T& Z) {
+  const T x0 = c.na * xD, y0 = c.na * yD;
+  const T x1 = jfma(c.cw, x0, -c.sw * y0);       // keplerian.py:568-569
+  const T y1 = jfma(c.sw, x0, c.cw * y0);
+  const T Y = c.ci * y1;                         // :575-576
+  Z = -c.si * y1;
+  b = jsqrt(jfma(x1, x1, Y * Y)) * c.inv_rstar;  // light_curves/limb_dark.py:53
 }
 
 template <typename T>

@@ -132,6 +132,7 @@ __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
   c.si = T(si.v);
   const D na = -(a * ome2);
   c.na_ome2 = T(na.v);
+  c.na = T(-a.v);
   c.inv_rstar = T(1.0 / rstar);
   const double rr = radius / rstar;
   c.rr = T(rr);
