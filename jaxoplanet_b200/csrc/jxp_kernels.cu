@@ -1837,7 +1837,7 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
       iope[h] = c.inv_ope;
       circ = circ || (c.flags & BODY_CIRCULAR);
     }
-    kepler_reduced_n<2, true>(Mr, e, ome, ope, s1, iope, sf, cf);  // (sin f, cos f) D
+    kepler_reduced_n<2, true, true>(Mr, e, ome, ope, s1, iope, sf, cf);  // (sin f, cos f) D
     if (__any_sync(0xffffffffu, circ)) {
 #pragma unroll
       for (int h = 0; h < 2; ++h)

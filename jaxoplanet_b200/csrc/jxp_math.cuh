@@ -134,7 +134,7 @@ __device__ __forceinline__ void kepler_reduced(T Mr, T e, T ome, T ope, T s1me2,
 // needs exactly these: 1 + e cos f = (1 - e^2) (c^2 + s^2) / D, so r0 = -a (1 - e^2) / (1 + e cos f)
 // = -a D and (r0 cos f, r0 sin f) = -a (cos f D, sin f D) -- keplerian.py:630-632 without its division
 // and without the 1 / D of the half-angle formulas (c^2 + s^2 = 1 to rounding).
-template <int N, bool XY = false>
+template <int N, bool XY = false, bool ONE_DIV = false>
 __device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const double (&e)[N],
                                                  const double (&ome)[N], const double (&ope)[N],
                                                  const double (&s1me2)[N], const double (&inv_ope)[N],
@@ -169,6 +169,29 @@ __device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const do
     f2[q] = e[q] * sinE;
     f3[q] = 1.0 - f1[q];
   }
+  if (ONE_DIV && !slow) {
+    // the three nested corrections d3 -> d4 -> dE of kepler.py:101-107 carried as fractions, ONE
+    // division instead of three dependent ones (each a MUFU seed + a Newton chain, ~60 cycles of
+    // latency): d3 = N3 / D3, d4 = -f0 D3^2 / Q4 = N4 / D4, dE = -f0 D4^3 / Q.  Same function; with
+    // 1 - e > 1e-5 (the float-starter range) f1 >= 1e-5 and D4^3 >= 1e-75: no underflow.
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const double N3 = -f0[q] * f1[q];
+      const double D3 = fma(-0.5 * f0[q], f2[q], f1[q] * f1[q]);
+      const double D32 = D3 * D3;
+      const double hf2 = 0.5 * f2[q], f36 = f3[q] * (1.0 / 6.0);
+      const double D4 = fma(N3, fma(hf2, D3, N3 * f36), f1[q] * D32);
+      const double N4 = -f0[q] * D32;
+      const double D42 = D4 * D4;
+      const double N42 = N4 * N4;
+      // Q = f1 D4^3 + f2/2 N4 D4^2 + f3/6 N4^2 D4 - f2/24 N4^3
+      const double Q = fma(D42, fma(f1[q], D4, hf2 * N4), N42 * fma(f36, D4, -(f2[q] * (1.0 / 24.0)) * N4));
+      d3[q] = D42 * D4;  // numerator factor D4^3 (d3 itself is not needed any more)
+      d4[q] = Q;
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) dE[q] = jdiv(-f0[q] * d3[q], d4[q]);
+  } else {
 #pragma unroll
   for (int q = 0; q < N; ++q) d3[q] = jdiv(-f0[q] * f1[q], fma(-0.5 * f0[q], f2[q], f1[q] * f1[q]));
 #pragma unroll
@@ -179,6 +202,7 @@ __device__ __forceinline__ void kepler_reduced_n(const double (&Mr)[N], const do
     const double d42 = d4[q] * d4[q];
     dE[q] = jdiv(-f0[q], fma(-d42 * d4[q], f2[q] * (1.0 / 24.0),
                               fma(d42, f3[q] * (1.0 / 6.0), fma(0.5 * d4[q], f2[q], f1[q]))));
+  }
   }
   double s[N], c[N], a[N], b[N], invD[N];
 #pragma unroll
