@@ -148,7 +148,7 @@ k_kepler(const T* __restrict__ M, int64_t Ms, const T* __restrict__ ecc, int64_t
       for (int q = 0; q < NI; ++q) s1[q] = jsqrt(ome[q] * ope[q]);
 #pragma unroll
       for (int q = 0; q < NI; ++q) iope[q] = jrcp(ope[q]);
-      kepler_reduced_n<NI>(Mr, e, ome, ope, s1, iope, sf, cf);
+      kepler_reduced_n<NI, false, true>(Mr, e, ome, ope, s1, iope, sf, cf);  // one division for d3 -> d4 -> dE
 #pragma unroll
       for (int q = 0; q < NI; ++q) {
         sinf_o[i + q * stride] = sf[q];
