@@ -23,6 +23,7 @@ HEADERS = [
     os.path.join(CSRC, "jxp_host.h"),
     os.path.join(CSRC, "jxp_math.cuh"),
     os.path.join(CSRC, "jxp_orbit.cuh"),
+    os.path.join(CSRC, "jxp_list.cuh"),
     os.path.join(ROOT, "include", "jaxoplanet_b200.h"),
 ]
 

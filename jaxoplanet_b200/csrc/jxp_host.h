@@ -21,5 +21,6 @@ void gl_table_host(int order, jxp::GLTable& tab);
 int make_stencil(double exposure_time, int order, int num_samples, Stencil& st);
 constexpr int LL_NCTA_H = 64;   // CTAs of k_loglike_prep (jxp_kernels.cu)
 constexpr int LL_SCAL0_H = 8;   // first per-CTA partial in the scalars block
+constexpr int LL_FLAG0_H = LL_SCAL0_H + 2 * LL_NCTA_H;  // per-CTA "time stamps not sorted" flags
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace jxph

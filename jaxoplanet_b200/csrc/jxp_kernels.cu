@@ -14,6 +14,7 @@
 
 #include "jxp_host.h"
 #include "jxp_orbit.cuh"
+#include "jxp_list.cuh"
 
 using namespace jxp;
 using namespace jxph;
@@ -536,12 +537,6 @@ __device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ 
 constexpr int LL_NCTA = 64;
 constexpr int LL_SCAL0 = 8;
 constexpr int LL_FLAG0 = LL_SCAL0 + 2 * 64;  // per-CTA "time stamps not sorted" flags (list path)
-// tl_state[1] of the transit-list path (tl_state[0], [2] = items on the inside / edge list); zeroed by
-// k_sys_prep.  The two lists share one buffer (inside from the bottom, edge from the top).
-constexpr unsigned long long TL_UNSORTED = 1ull, TL_OVERFLOW = 2ull;
-__device__ __forceinline__ bool tl_active(const unsigned long long* __restrict__ st, unsigned long long cap) {
-  return st[1] == 0ull && st[0] + st[2] <= cap;
-}
 template <typename T>
 __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
@@ -623,9 +618,18 @@ k_sys_prep_ll(const double* __restrict__ bodies, int n_sets, int n_bodies, const
 }
 
 namespace jxph {
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_loglike_prep_t(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
+                 T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t) {
+  loglike_prep_body<T>(blockIdx.x, gridDim.x, y, sigma, ss, n, winv, scalars, t);
+}
 int launch_loglike_prep_f64(const double* y, const double* sigma, int64_t ss, int64_t n, double* winv,
-                            double* scalars, cudaStream_t st) {
-  k_loglike_prep<double><<<LL_NCTA, 256, 0, st>>>(y, sigma, ss, n, winv, scalars);
+                            double* scalars, cudaStream_t st, const double* t_sorted_check) {
+  if (t_sorted_check)
+    k_loglike_prep_t<double><<<LL_NCTA, 256, 0, st>>>(y, sigma, ss, n, winv, scalars, t_sorted_check);
+  else
+    k_loglike_prep<double><<<LL_NCTA, 256, 0, st>>>(y, sigma, ss, n, winv, scalars);
   return check_launch("loglike prep");
 }
 int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int64_t n, float* winv,
@@ -1602,175 +1606,6 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
 // full (the reference's value, 0 when it is not in transit), so the list only has to be a
 // superset of the in-transit samples -- the same rigorous window as stage A/B.
 // --------------------------------------------------------------------------------------
-// First index i in [0, n] with !pred(t[i]), pred(v) = (v < x) (lower bound) or (v <= x) (upper
-// bound), on sorted t.  The estimate from a uniform grid through the end points is bracketed by
-// doubling, then bisected: ~4 dependent loads on a regular cadence instead of log2(n).
-template <bool UPPER>
-__device__ __forceinline__ unsigned tl_search(const double* __restrict__ t, unsigned n, double x,
-                                              double t_first, double inv_dt) {
-  auto pred = [&](unsigned i) {
-    const double v = t[i];
-    return UPPER ? (v <= x) : (v < x);
-  };
-  double gd = (x - t_first) * inv_dt;
-  gd = fmin(fmax(gd, 0.0), (double)n);
-  const unsigned g = (unsigned)gd;
-  unsigned w = 2;
-  unsigned lo = g > w ? g - w : 0u;
-  while (lo > 0u && !pred(lo - 1u)) {
-    w = (w < 0x40000000u) ? (w << 1) : 0xffffffffu;
-    lo = g > w ? g - w : 0u;
-  }
-  w = 2;
-  unsigned hi = (n - g > w) ? g + w : n;
-  while (hi < n && pred(hi)) {
-    w = (w < 0x40000000u) ? (w << 1) : 0xffffffffu;
-    hi = (n - g > w) ? g + w : n;
-  }
-  while (lo < hi) {
-    const unsigned mid = lo + ((hi - lo) >> 1);
-    if (pred(mid)) lo = mid + 1u; else hi = mid;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(128) k_tl_build(const __grid_constant__ SysArgs<double> a) {
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= a.n_sets) return;
-  {  // sortedness flags of k_sys_prep_ll (one per CTA of the likelihood prep)
-    const bool bad = a.scalars[LL_FLAG0 + lane] != 0.0 || a.scalars[LL_FLAG0 + 32 + lane] != 0.0;
-    if (__any_sync(0xffffffffu, bad)) {
-      if (s == 0 && lane == 0) atomicOr(a.tl_state + 1, TL_UNSORTED);
-      return;
-    }
-  }
-  const BodyC<double>& c = a.bodies[s];
-  const unsigned n = (unsigned)a.n_times;
-  const double P = c.period, t0ref = c.t0ref, phc = c.phase_c, wlo = c.wlo, whi = c.whi;
-  const double t_first = a.t[0], t_last = a.t[n - 1];
-  const double inv_dt = (t_last > t_first) ? (double)(n - 1) / (t_last - t_first) : 0.0;
-  bool all = (c.flags & BODY_ALWAYS) != 0;
-  long long n_tr = 1;
-  double k_first = 0.0;
-  if (!all) {
-    if (!(wlo <= whi)) {
-      n_tr = 0;  // never in transit
-    } else {
-      const double pa = (t_first - t0ref) * c.inv_period - phc;
-      const double pb = (t_last - t0ref) * c.inv_period - phc;
-      const double lo_d = floor(fmin(pa, pb) - whi) - 1.0;
-      const double hi_d = ceil(fmax(pa, pb) - wlo) + 1.0;
-      if (!(hi_d - lo_d < 4.0 * (double)n + 64.0)) {
-        all = true;  // more transits than samples (or not finite): take every sample
-      } else {
-        k_first = lo_d;
-        n_tr = (long long)(hi_d - lo_d) + 1;
-      }
-    }
-  }
-  const double w_in = all ? 0.0 : c.win_in;
-  // transit k -> sample range [lo, hi) in the window and the part [ilo, ihi) of it estimated to have the
-  // planet fully inside the disk (at least 8 samples, else empty)
-  auto interval = [&](long long k, unsigned& lo, unsigned& hi, unsigned& ilo, unsigned& ihi) {
-    lo = hi = ilo = ihi = 0;
-    if (k >= n_tr) return;
-    if (all) {
-      hi = n;
-      return;
-    }
-    const double base = phc + (k_first + (double)k);
-    const double ta = fma(base + wlo, P, t0ref), tb = fma(base + whi, P, t0ref);
-    lo = tl_search<false>(a.t, n, fmin(ta, tb), t_first, inv_dt);
-    hi = tl_search<true>(a.t, n, fmax(ta, tb), t_first, inv_dt);
-    ilo = ihi = lo;
-    if (w_in > 0.0 && hi - lo >= 8u) {
-      const double tc = fma(base - w_in, P, t0ref), td = fma(base + w_in, P, t0ref);
-      unsigned i0 = tl_search<false>(a.t, n, fmin(tc, td), t_first, inv_dt);
-      unsigned i1 = tl_search<true>(a.t, n, fmax(tc, td), t_first, inv_dt);
-      i0 = i0 < lo ? lo : (i0 > hi ? hi : i0);
-      i1 = i1 < i0 ? i0 : (i1 > hi ? hi : i1);
-      if (i1 - i0 >= 8u) {
-        ilo = i0;
-        ihi = i1;
-      }
-    }
-  };
-  // the first 64 transits stay in registers between the counting and the writing pass
-  unsigned lo0, hi0, il0, ih0, lo1, hi1, il1, ih1;
-  interval(lane, lo0, hi0, il0, ih0);
-  interval(32 + lane, lo1, hi1, il1, ih1);
-  unsigned long long cntA = (unsigned long long)(ih0 - il0) + (ih1 - il1);
-  unsigned long long cntB = (unsigned long long)(hi0 - lo0) + (hi1 - lo1) - cntA;
-  for (long long k0 = 64; k0 < n_tr; k0 += 32) {
-    unsigned lo, hi, il, ih;
-    interval(k0 + lane, lo, hi, il, ih);
-    cntA += ih - il;
-    cntB += (hi - lo) - (ih - il);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cntA += __shfl_xor_sync(0xffffffffu, cntA, o);
-    cntB += __shfl_xor_sync(0xffffffffu, cntB, o);
-  }
-  unsigned long long offA = 0, offB = 0;
-  if (lane == 0) {
-    offA = atomicAdd(a.tl_state, cntA);
-    offB = atomicAdd(a.tl_state + 2, cntB);
-    a.tl_off[2 * s] = offA;
-    a.tl_off[2 * s + 1] = offB;
-    a.tl_cnt[2 * s] = (unsigned)cntA;
-    a.tl_cnt[2 * s + 1] = (unsigned)cntB;
-  }
-  offA = __shfl_sync(0xffffffffu, offA, 0);
-  offB = __shfl_sync(0xffffffffu, offB, 0);
-  // no write may leave the buffer; whether the two lists ran into each other is only known when every
-  // set has allocated: tl_active() checks the totals in the kernels that follow
-  if (offA + cntA > a.tl_cap || offB + cntB > a.tl_cap) {
-    if (lane == 0) atomicOr(a.tl_state + 1, TL_OVERFLOW);
-    return;
-  }
-  unsigned long long* outA = a.tl_items + offA;
-  unsigned long long* outB = a.tl_items + (a.tl_cap - offB - cntB);
-  const unsigned long long tag = (unsigned long long)s << 32;
-  for (long long k0 = 0; k0 < n_tr; k0 += 32) {
-    unsigned lo, hi, il, ih;
-    if (k0 == 0) {
-      lo = lo0; hi = hi0; il = il0; ih = ih0;
-    } else if (k0 == 32) {
-      lo = lo1; hi = hi1; il = il1; ih = ih1;
-    } else {
-      interval(k0 + lane, lo, hi, il, ih);
-    }
-    const unsigned cA = ih - il, cB = (hi - lo) - cA;
-    unsigned inA = cA, inB = cB;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned vA = __shfl_up_sync(0xffffffffu, inA, o);
-      const unsigned vB = __shfl_up_sync(0xffffffffu, inB, o);
-      if (lane >= o) {
-        inA += vA;
-        inB += vB;
-      }
-    }
-    const unsigned exA = inA - cA, exB = inB - cB;
-    unsigned nz = __ballot_sync(0xffffffffu, hi != lo);
-    while (nz) {
-      const int j = __ffs(nz) - 1;
-      nz &= nz - 1;
-      const unsigned lj = __shfl_sync(0xffffffffu, lo, j), hj = __shfl_sync(0xffffffffu, hi, j);
-      const unsigned ilj = __shfl_sync(0xffffffffu, il, j), ihj = __shfl_sync(0xffffffffu, ih, j);
-      const unsigned eAj = __shfl_sync(0xffffffffu, exA, j), eBj = __shfl_sync(0xffffffffu, exB, j);
-      const unsigned nAj = ihj - ilj, nB0 = ilj - lj, nBj = (hj - lj) - nAj;
-      for (unsigned i = lane; i < nAj; i += 32) outA[eAj + i] = tag | (unsigned long long)(ilj + i);
-      for (unsigned i = lane; i < nBj; i += 32)
-        outB[eBj + i] = tag | (unsigned long long)(i < nB0 ? lj + i : ihj + (i - nB0));
-    }
-    outA += __shfl_sync(0xffffffffu, inA, 31);
-    outB += __shfl_sync(0xffffffffu, inB, 31);
-  }
-}
-
 #ifndef JXP_TL_MINB
 #define JXP_TL_MINB 4
 #endif
@@ -1913,40 +1748,10 @@ __global__ void __launch_bounds__(128) k_tl_reduce(const __grid_constant__ SysAr
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= a.n_sets) return;
-  // one slice: 8 independent lane-strided sums (fixed order), software-pipelined so that the loads of
-  // round r + 1 are in flight while round r is added; returns this lane's share
-  auto slice_sum = [&](const double* __restrict__ d, unsigned cnt) {
-    double acc[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) acc[m] = 0.0;
-    const unsigned full = cnt & ~255u;
-    unsigned i = lane;
-    if (i < full) {
-      double v[8];
-#pragma unroll
-      for (int m = 0; m < 8; ++m) v[m] = __ldcs(d + i + 32 * m);
-#pragma unroll 1
-      for (i += 256; i < full; i += 256) {
-        double w[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) w[m] = __ldcs(d + i + 32 * m);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) acc[m] += v[m];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = w[m];
-      }
-#pragma unroll
-      for (int m = 0; m < 8; ++m) acc[m] += v[m];
-    }
-#pragma unroll
-    for (int m = 0; m < 8; ++m)
-      if (i + 32 * m < cnt) acc[m] += d[i + 32 * m];  // i + 224 < full + 256: no wrap for cnt < 2^32 - 256
-    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  };
   const double* __restrict__ d = reinterpret_cast<const double*>(a.tl_items);
   const unsigned cntA = a.tl_cnt[2 * s], cntB = a.tl_cnt[2 * s + 1];
-  double tot = slice_sum(d + a.tl_off[2 * s], cntA);
-  tot += slice_sum(d + (a.tl_cap - a.tl_off[2 * s + 1] - cntB), cntB);
+  double tot = tl_slice_sum(d + a.tl_off[2 * s], cntA, lane);
+  tot += tl_slice_sum(d + (a.tl_cap - a.tl_off[2 * s + 1] - cntB), cntB, lane);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   // set-independent terms: the LL_NCTA pairs of k_loglike_prep added in order (as k_loglike_final does)
@@ -2143,8 +1948,20 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       a.tl_cnt = reinterpret_cast<unsigned*>(ws + L.off_tl_cnt);
       a.tl_cap = L.tl_cap;
       a.loglike = reinterpret_cast<double*>(loglike);
+      TlBuildArgs ba;
+      ba.bodies = reinterpret_cast<const unsigned char*>(d_bodies);
+      ba.body_stride = sizeof(BodyC<T>);
+      ba.n_sets = n_sets;
+      ba.t = t;
+      ba.n_times = n_times;
+      ba.sorted_flags = d_scalars + LL_FLAG0;
+      ba.tl_state = a.tl_state;
+      ba.tl_items = a.tl_items;
+      ba.tl_off = a.tl_off;
+      ba.tl_cnt = a.tl_cnt;
+      ba.tl_cap = a.tl_cap;
       if (g_ev_start && ev_on("build")) cudaEventRecord(g_ev_start, st);
-      k_tl_build<<<(n_sets + 3) / 4, 128, 0, st>>>(a);
+      k_tl_build<0><<<(n_sets + 3) / 4, 128, 0, st>>>(ba);
       if (g_ev_stop && ev_on("build")) cudaEventRecord(g_ev_stop, st);
       rc = check_launch("jxp_system_light_curve(transit list)");
       if (rc != JXP_OK) return rc;

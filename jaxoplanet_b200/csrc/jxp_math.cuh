@@ -649,6 +649,58 @@ __device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const dou
   }
 }
 
+// ld_solution (l_max = 2, order 10) for a point with the planet fully inside the disk, b < 1 - r and
+// r < 1 (the caller guarantees it), S = T or Dual<T, N>: kite_area = 0, kappa0 = pi and kappa1 = 0 are
+// CONSTANTS there (the general code takes the same branch: `cond_k` false, derivative 0), so the
+// node angles pi (1 +- x_p) / 2 and their cosines are constants too (GL<10>::cpi) and carry no
+// derivative.  Node order of the mirror-pair loops (+x_p, -x_p for p = 0..4).
+template <typename S>
+__device__ __forceinline__ void ld_solution_inside(S b, S r, S& s0, S& s1, S& s2) {
+  using B = typename BaseOf<S>::type;
+  const B pi = Num<B>::pi;
+  const B eps10 = B(10) * Num<B>::eps;
+  b = jabs(b);
+  r = jabs(r);
+  const S b2 = b * b;
+  const S r2 = r * r;
+  {
+    const S bpr = b + r;
+    const S onembpr2 = (B(1) + bpr) * (B(1) - bpr);
+    const S eta2 = r2 * (r2 + b2 * B(2)) * B(0.5);
+    const S delta = b * r * B(4);
+    const bool large = val(onembpr2) + val(delta) > val(delta);
+    if (large) {
+      s0 = (B(1) - r2) * pi;
+      s2 = s0 * B(2) + (eta2 - B(0.5)) * (B(4) * pi);
+    } else {
+      const S Alens = r2 * pi;  // kappa1 + r^2 kappa0 - area / 2
+      s0 = pi - Alens;
+      s2 = s0 * B(2) + (eta2 * (pi * B(2)) - pi) * B(2);
+    }
+  }
+  const S two_br = b * r * B(2);
+  const S r2pb2 = r2 + b2;
+  const S two_r_3 = r * B(2.0 / 3.0);
+  S acc = S(B(0));
+#pragma unroll 1
+  for (int p = 0; p < 5; ++p) {
+    const B wi = B(c_gl10[1][5 + p]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const B c = B(q ? c_gl10[2][4 - p] : c_gl10[2][5 + p]);
+      const S omz2 = jclamp0_lazy(r2pb2 - two_br * c);
+      const bool dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
+      const S z2s = jsel(dead, S(B(1)), B(1) - omz2);
+      const S z = jsqrt_pos(z2s);
+      S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
+      res = jsel(dead, S(B(0)), res);
+      acc = acc + res * wi;
+    }
+  }
+  const S P0 = acc * (pi * B(0.5));
+  s1 = -P0 + pi * B(2.0 / 3.0);
+}
+
 // ld_solution_n for points with the planet fully inside the disk, b < 1 - r and r < 1 (the caller
 // guarantees it): there kite_area = 0, kappa0 = atan2(+0, b^2 + r^2 - 1) = pi and kappa1 =
 // atan2(+0, b^2 - r^2 + 1) = 0 exactly, so the two atan2, the kite area and the ten node cosines

@@ -19,6 +19,7 @@
 
 #include "jxp_host.h"
 #include "jxp_orbit.cuh"
+#include "jxp_list.cuh"
 
 using namespace jxp;
 using namespace jxph;
@@ -41,6 +42,8 @@ struct BodyD {
 
 struct TrLayout {
   size_t off_bodies, off_winv, off_scalars, off_partial, total;
+  size_t off_tl_off, off_tl_cnt, off_tl_items, off_tl_vals;  // transit list of the gradient step
+  unsigned long long tl_cap;
   int n_tiles;
 };
 
@@ -57,6 +60,17 @@ TrLayout tr_layout(int n_sets, int64_t n_times) {
   off = align_up(off + 256 * sizeof(double), 256);
   L.off_partial = off;
   off = align_up(off + sizeof(double) * (size_t)n_sets * (L.n_tiles + 4) * (1 + JXP_NTHETA), 256);
+  // transit list (log-likelihood + gradient without stored rows): an 8-byte item and 9 doubles (chi^2
+  // term and the 8 gradient terms) per in-window sample, room for 1/16 of the grid
+  L.off_tl_off = off;
+  off = align_up(off + 2 * sizeof(unsigned long long) * (size_t)n_sets, 256);
+  L.off_tl_cnt = off;
+  off = align_up(off + 2 * sizeof(unsigned) * (size_t)n_sets, 256);
+  L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 16ull + 65536ull;
+  L.off_tl_items = off;
+  off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
+  L.off_tl_vals = off;
+  off = align_up(off + sizeof(double) * (1 + JXP_NTHETA) * (size_t)L.tl_cap, 256);
   L.total = off;
   return L;
 }
@@ -75,9 +89,11 @@ __device__ __forceinline__ Dual<T, N> cast_dual(const Dual<double, N>& x) {
 template <typename T>
 __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
                           const double* __restrict__ star, int64_t star_stride,
-                          BodyD<T>* __restrict__ out, double widen, double margin) {
+                          BodyD<T>* __restrict__ out, double widen, double margin,
+                          unsigned long long* __restrict__ tl_state) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sets) return;
+  if (s == 0) tl_state[0] = tl_state[1] = tl_state[2] = tl_state[3] = 0ull;  // transit list of this call
   typedef Dual<double, NO> D;
   const double* th = theta + (size_t)s * JXP_NTHETA;
   const double mstar = star[(size_t)s * star_stride + 0];
@@ -165,10 +181,14 @@ __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
 
 // One sample that passed the window test: flux - 1 and its 8 partials; false (outputs
 // untouched) when the sample is not in transit.
+// on_inside_list (transit-list path): a sample on the inside list that has b < 1 - r itself takes
+// ld_solution_inside (constant kappas and node cosines: no atan2, no node sin/cos, no derivative through
+// them) -- decided per sample, never by its neighbours.
 template <typename T, int ORDER>
 __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
                                                      const GLTable* __restrict__ tab, double tm,
-                                                     T& flux, T* __restrict__ part) {
+                                                     T& flux, T* __restrict__ part,
+                                                     bool on_inside_list = false) {
   const BodyC<T>& c = bd.c;
   typedef Dual<T, NO> D;
   // mean anomaly and its tangents (double): M = 2 pi ((t - t0) - t_ref) / P
@@ -204,7 +224,11 @@ __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
   if (!(Z.v > T(0)) || (b.v >= c.onepr)) return false;
   typedef Dual<T, 2> L;
   L s0, s1, s2;
-  ld_solution<L, ORDER>(L::seed(b.v, 0), L::seed(c.rr, 1), 2, tab, s0, s1, s2);
+  const T ar = jabs(c.rr);
+  if (ORDER == 11 && on_inside_list && (b.v < T(1) - ar) && (ar < T(1)))
+    ld_solution_inside<L>(L::seed(b.v, 0), L::seed(c.rr, 1), s0, s1, s2);
+  else
+    ld_solution<L, ORDER>(L::seed(b.v, 0), L::seed(c.rr, 1), 2, tab, s0, s1, s2);
   const L f = ld_combine(2, s0, s1, s2, L(bd.sc.g0), L(bd.sc.g1), L(bd.sc.g2));
   flux = f.v;
 #pragma unroll
@@ -227,6 +251,16 @@ struct TrArgs {
   const T* y;
   const T* winv;
   double* partial;  // [n_sets][n_tiles][9]
+  // transit-list path of the gradient step (nullptr: not used by this call)
+  unsigned long long* tl_state;
+  unsigned long long* tl_items;
+  unsigned long long* tl_off;
+  unsigned* tl_cnt;
+  unsigned long long tl_cap;
+  double* tl_vals;  // [9][tl_cap]
+  const double* scalars;
+  T* loglike;
+  T* dloglike;
   Stencil st;
   GLTable tab;
 };
@@ -248,6 +282,7 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = TR_K;
   constexpr int NQ = 1 + JXP_NTHETA;
+  if (a.tl_state != nullptr && tl_active(a.tl_state, a.tl_cap)) return;  // the transit-list kernels did the work
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -538,9 +573,11 @@ __global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __g
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
-           const double* __restrict__ scalars, T* __restrict__ loglike, T* __restrict__ dloglike) {
+           const double* __restrict__ scalars, T* __restrict__ loglike, T* __restrict__ dloglike,
+           const unsigned long long* __restrict__ tl_state, unsigned long long tl_cap) {
   constexpr int NQ = 1 + JXP_NTHETA;
   __shared__ double sh[8][33];
+  if (tl_state != nullptr && tl_active(tl_state, tl_cap)) return;  // the transit-list kernels did the work
   const int li = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + li;  // i = set * NQ + q
   const int n = n_sets * NQ;
@@ -567,6 +604,96 @@ k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
   }
 }
 
+// --------------------------------------------------------------------------------------
+// Transit-list path of the gradient step (log-likelihood and its 8-gradient, no rows stored, no
+// exposure integration, double, sorted time stamps) -- the K5 counterpart of k_tl_eval / k_tl_reduce in
+// jxp_kernels.cu; k_tl_build (jxp_list.cuh) makes the two lists from the BodyC at the head of each
+// BodyD record.  One item per lane (the dual-number code needs the registers); the chi^2 term and the
+// 8 gradient terms of an item go to 9 planes of tl_vals at the item's slot, k_tlg_reduce adds each
+// set's slices plane by plane in a fixed order.  Falls back to k_transit_partials / k_tr_final on the
+// device exactly like the log-likelihood path (tl_active()).
+// --------------------------------------------------------------------------------------
+#ifndef JXP_TLG_MINB
+#define JXP_TLG_MINB 3
+#endif
+__global__ void __launch_bounds__(128, JXP_TLG_MINB) k_tlg_eval(const __grid_constant__ TrArgs<double> a) {
+  constexpr int NQ = 1 + JXP_NTHETA;
+  if (!tl_active(a.tl_state, a.tl_cap)) return;
+  const unsigned long long totA = a.tl_state[0], totB = a.tl_state[2];
+  const unsigned long long nA = (totA + 31ull) >> 5, nB = (totB + 31ull) >> 5;
+  const unsigned long long n_chunks = nA + nB;  // 32-item chunks of the inside list, then of the edge list
+  const int lane = threadIdx.x & 31;
+  const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  for (unsigned long long ch = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+       ch < n_chunks; ch += nw) {
+    const bool on_inside_list = ch < nA;
+    unsigned long long slot;
+    bool have;
+    if (on_inside_list) {
+      slot = ch * 32ull + lane;
+      have = slot < totA;
+    } else {
+      const unsigned long long p = (ch - nA) * 32ull + lane;
+      slot = a.tl_cap - totB + p;
+      have = p < totB;
+    }
+    double out[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = 0.0;
+    if (have) {
+      const unsigned long long item = a.tl_items[slot];
+      const BodyD<double>& bd = a.bodies[(unsigned)(item >> 32)];
+      const unsigned idx = (unsigned)item;
+      double f1 = 0.0, p1[JXP_NTHETA];
+      if (eval_sample_partials<double, 11>(bd, &a.tab, a.t[idx], f1, p1, on_inside_list)) {
+        const double w = a.winv[idx];
+        const double r0 = (a.y[idx] - 1.0) * w;
+        const double mw = f1 * w;
+        const double g = (r0 - mw) * w;  // d loglike / d model
+        out[0] = (-mw) * (2.0 * r0 - mw);
+#pragma unroll
+        for (int q = 0; q < JXP_NTHETA; ++q) out[1 + q] = g * p1[q];
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) a.tl_vals[(size_t)q * a.tl_cap + slot] = out[q];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_tlg_reduce(const __grid_constant__ TrArgs<double> a) {
+  constexpr int NQ = 1 + JXP_NTHETA;
+  if (!tl_active(a.tl_state, a.tl_cap)) return;
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= a.n_sets) return;
+  const unsigned cntA = a.tl_cnt[2 * s], cntB = a.tl_cnt[2 * s + 1];
+  const unsigned long long offA = a.tl_off[2 * s], offB = a.tl_cap - a.tl_off[2 * s + 1] - cntB;
+  double tot[NQ];
+#pragma unroll 1
+  for (int q = 0; q < NQ; ++q) {
+    const double* __restrict__ d = a.tl_vals + (size_t)q * a.tl_cap;
+    double v = tl_slice_sum(d + offA, cntA, lane);
+    v += tl_slice_sum(d + offB, cntB, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    tot[q] = v;
+  }
+  if (lane == 0) {
+    if (a.loglike) {
+      double chi0 = 0.0, cst = 0.0;
+      for (int k = 0; k < LL_NCTA_H; ++k) {
+        chi0 += a.scalars[LL_SCAL0_H + 2 * k];
+        cst += a.scalars[LL_SCAL0_H + 2 * k + 1];
+      }
+      a.loglike[s] = -0.5 * (chi0 + tot[0]) + cst;
+    }
+    if (a.dloglike) {
+#pragma unroll
+      for (int q = 0; q < JXP_NTHETA; ++q) a.dloglike[(size_t)s * JXP_NTHETA + q] = tot[1 + q];
+    }
+  }
+}
+
 extern "C" size_t jxp_transit_workspace_bytes(int32_t n_sets, int64_t n_times) {
   if (n_sets <= 0 || n_times < 0) return 0;
   return tr_layout(n_sets, n_times).total;
@@ -575,17 +702,17 @@ extern "C" size_t jxp_transit_workspace_bytes(int32_t n_sets, int64_t n_times) {
 namespace jxph {
 // launches k_loglike_prep<T> (instantiated in jxp_kernels.cu)
 int launch_loglike_prep_f64(const double* y, const double* sigma, int64_t ss, int64_t n, double* winv,
-                            double* scalars, cudaStream_t st);
+                            double* scalars, cudaStream_t st, const double* t_sorted_check = nullptr);
 int launch_loglike_prep_f32(const float* y, const float* sigma, int64_t ss, int64_t n, float* winv,
                             double* scalars, cudaStream_t st);
 }  // namespace jxph
 
 static int loglike_prep(const double* y, const double* s, int64_t ss, int64_t n, double* w, double* sc,
-                        cudaStream_t st) {
-  return launch_loglike_prep_f64(y, s, ss, n, w, sc, st);
+                        cudaStream_t st, const double* t_check) {
+  return launch_loglike_prep_f64(y, s, ss, n, w, sc, st, t_check);
 }
 static int loglike_prep(const float* y, const float* s, int64_t ss, int64_t n, float* w, double* sc,
-                        cudaStream_t st) {
+                        cudaStream_t st, const double*) {
   return launch_loglike_prep_f32(y, s, ss, n, w, sc, st);
 }
 
@@ -629,12 +756,16 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = sizeof(T) == 4;
 
+  unsigned long long* tl_state = reinterpret_cast<unsigned long long*>(d_scalars + 4);
+  // transit-list path (see k_tlg_eval): eligibility is decided here, use on the device
+  const bool use_tl = sizeof(T) == 8 && want_ll && !flux && !partials && a.st.n == 1 && gl_order == 10 &&
+                      !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL && getenv("JXP_NO_TL") == nullptr;
   k_tr_prep<T><<<(n_sets + 127) / 128, 128, 0, st>>>(theta, n_sets, star, star_stride, d_bodies,
-                                                    f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7);
+                                                    f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7, tl_state);
   rc = check_launch("jxp_transit_partials(prep)");
   if (rc != JXP_OK) return rc;
   if (want_ll) {
-    rc = loglike_prep(y, sigma, sigma_stride, n_times, d_winv, d_scalars, st);
+    rc = loglike_prep(y, sigma, sigma_stride, n_times, d_winv, d_scalars, st, use_tl ? t : nullptr);
     if (rc != JXP_OK) return rc;
   }
   const int sms = sm_count();
@@ -677,8 +808,56 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   a.y = y;
   a.winv = d_winv;
   a.partial = d_partial;
+  a.tl_state = nullptr;
+  a.tl_items = nullptr;
+  a.tl_off = nullptr;
+  a.tl_cnt = nullptr;
+  a.tl_cap = 0;
+  a.tl_vals = nullptr;
+  a.scalars = d_scalars;
+  a.loglike = loglike;
+  a.dloglike = dloglike;
   a.tab.order = gl_order;
   if (gl_order != 10) gl_table_host(gl_order, a.tab);
+  if constexpr (sizeof(T) == 8) {
+    if (use_tl) {
+      a.tl_state = tl_state;
+      a.tl_items = reinterpret_cast<unsigned long long*>(ws + L.off_tl_items);
+      a.tl_off = reinterpret_cast<unsigned long long*>(ws + L.off_tl_off);
+      a.tl_cnt = reinterpret_cast<unsigned*>(ws + L.off_tl_cnt);
+      a.tl_cap = L.tl_cap;
+      a.tl_vals = reinterpret_cast<double*>(ws + L.off_tl_vals);
+      TlBuildArgs ba;
+      ba.bodies = reinterpret_cast<const unsigned char*>(d_bodies);
+      ba.body_stride = sizeof(BodyD<T>);
+      ba.n_sets = n_sets;
+      ba.t = t;
+      ba.n_times = n_times;
+      ba.sorted_flags = d_scalars + LL_FLAG0_H;
+      ba.tl_state = a.tl_state;
+      ba.tl_items = a.tl_items;
+      ba.tl_off = a.tl_off;
+      ba.tl_cnt = a.tl_cnt;
+      ba.tl_cap = a.tl_cap;
+      k_tl_build<1><<<(n_sets + 3) / 4, 128, 0, st>>>(ba);
+      rc = check_launch("jxp_transit_partials(transit list)");
+      if (rc != JXP_OK) return rc;
+      int per_sm = 0;
+      cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tlg_eval, 128, 0);
+      if (eo != cudaSuccess || per_sm < 1)
+        return fail(JXP_ERR_CUDA, "jxp_transit_partials: occupancy query: %s", cudaGetErrorString(eo));
+      // the list length is only known on the device: a resident grid, chunks strided over it
+      const int64_t max_chunks = (int64_t)((L.tl_cap + 31ull) / 32ull) + 1;
+      const int64_t want = (max_chunks + 3) / 4;
+      const int64_t resident = (int64_t)per_sm * sms;
+      k_tlg_eval<<<(unsigned)(want < resident ? want : resident), 128, 0, st>>>(a);
+      rc = check_launch("jxp_transit_partials(transit list eval)");
+      if (rc != JXP_OK) return rc;
+      k_tlg_reduce<<<(n_sets + 3) / 4, 128, 0, st>>>(a);
+      rc = check_launch("jxp_transit_partials(transit list reduce)");
+      if (rc != JXP_OK) return rc;
+    }
+  }
   const size_t smem = sizeof(BodyD<T>) * (size_t)spc +
                       sizeof(double) * (1 + JXP_NTHETA) * (size_t)spc * (threads / 32) +
                       sizeof(unsigned) * (size_t)TR_QCAP * (threads / 32);
@@ -698,7 +877,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   if (want_ll) {
     const int n = n_sets * (1 + JXP_NTHETA);
     k_tr_final<T><<<(n + 31) / 32, 256, 0, st>>>(d_partial, (int)(n_tiles * (threads / 32)), n_sets, d_scalars, loglike,
-                                                  dloglike);
+                                                  dloglike, a.tl_state, a.tl_cap);
     rc = check_launch("jxp_transit_partials(final)");
   }
   return rc;
