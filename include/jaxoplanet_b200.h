@@ -192,7 +192,11 @@ int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodie
  *   flux      [n_sets][n_times]      flux - 1
  *   partials  [n_sets][8][n_times]   d(flux)/d(theta_k)
  *   loglike   [n_sets], dloglike [n_sets][8]   Gaussian log-likelihood of (y, sigma) and its
- *             gradient, reduced in-kernel (workspace: jxp_transit_workspace_bytes)
+ *             gradient, reduced in-kernel (workspace: jxp_transit_workspace_bytes).  With flux
+ *             and partials NULL, no exposure integration and sorted time stamps the in-window
+ *             samples go on a work list in the workspace (80 bytes per item, room for 1/16 of
+ *             the grid; DESIGN.md "gradient step on the transit list"); otherwise, or when the
+ *             list does not fit, the window-test kernel does the same work -- decided on the device.
  * ---------------------------------------------------------------------------------- */
 #define JXP_NTHETA 8
 size_t jxp_transit_workspace_bytes(int32_t n_sets, int64_t n_times);

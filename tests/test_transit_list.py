@@ -263,3 +263,61 @@ def test_list_path_no_out_of_bounds_writes():
         assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
         assert bool((out[:8] == -7.0).all()) and bool((out[8 + n_sets:] == -7.0).all())
         assert bool(torch.isfinite(out[8:8 + n_sets]).all())
+
+
+# ----------------------------------------------------------------------------- gradient step (K5)
+def _grad_step(theta, t, y, sigma):
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    r = transit_partials(theta, t, y=y, sigma=sigma, want_flux=False, want_partials=False)
+    return r["loglike"], r["dloglike"]
+
+
+def test_gradient_step_list_path_matches_rows_reduction_window_kernels_and_autograd_oracle():
+    """Log-likelihood + 8-gradient without stored rows goes through k_tl_build / k_tlg_eval /
+    k_tlg_reduce (sorted time stamps).  Checked against (1) the reductions of the per-point flux and
+    partials the row-storing kernel writes -- which tests/test_gpu_parity.py checks point by point against
+    the torch-autograd oracle -- at the north-star tolerance for gradients (1e-9 relative), and (2) the
+    window-test kernels (JXP_NO_TL)."""
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    n_sets, n_t = 200, 30_000
+    theta, t = W.c5(n_sets, n_t)
+    rows = transit_partials(theta, t)  # flux (n_sets, n_t), partials (n_sets, 8, n_t)
+    rng = np.random.default_rng(8)
+    y = 1 + rows["flux"][3] + 5e-4 * rng.normal(size=n_t)
+    sigma = 5e-4 * (1 + 0.2 * rng.uniform(size=n_t))
+    ll, g = _grad_step(theta, t, y, sigma)
+    assert ll.shape == (n_sets,) and g.shape == (n_sets, 8)
+    # (1) reductions of the stored rows (different kernel, general flux code everywhere)
+    m = 1 + rows["flux"]
+    want_ll = ref.gaussian_loglike(m, y[None, :], sigma[None, :])
+    want_g = np.einsum("st,skt->sk", (y[None, :] - m) / sigma[None, :] ** 2, rows["partials"])
+    scale = np.abs(want_g).max(0, keepdims=True)
+    assert np.max(np.abs(ll - want_ll) / np.abs(want_ll)) <= 1e-11
+    assert np.max(np.abs(g - want_g) / np.maximum(np.abs(want_g), scale)) <= 1e-9
+    # (2) the window-test kernels
+    ll_w, g_w = _without_list(lambda: _grad_step(theta, t, y, sigma))
+    assert np.max(np.abs(ll - ll_w) / np.abs(ll_w)) <= 1e-11
+    assert np.max(np.abs(g - g_w) / np.maximum(np.abs(g_w), scale)) <= 1e-11
+    # bit-reproducible
+    for _ in range(2):
+        ll2, g2 = _grad_step(theta, t, y, sigma)
+        assert np.array_equal(ll2, ll) and np.array_equal(g2, g)
+
+
+def test_gradient_step_falls_back_on_unsorted_times():
+    from jaxoplanet_b200 import workloads as W
+
+    theta, t = W.c5(64, 9_000)
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(t.size)
+    y = 1 + 5e-4 * rng.normal(size=t.size)
+    ll, g = _grad_step(theta, t[perm], y[perm], 5e-4)
+    ll_w, g_w = _without_list(lambda: _grad_step(theta, t[perm], y[perm], 5e-4))
+    assert np.array_equal(ll, ll_w) and np.array_equal(g, g_w)  # the same kernels produced both
+    ll_s, g_s = _grad_step(theta, t, y, 5e-4)
+    assert np.max(np.abs(ll - ll_s) / np.abs(ll_s)) <= 1e-11
+    scale = np.abs(g_s).max(0, keepdims=True)
+    assert np.max(np.abs(g - g_s) / np.maximum(np.abs(g_s), scale)) <= 1e-11
