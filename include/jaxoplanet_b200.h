@@ -200,6 +200,10 @@ int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodie
  * ---------------------------------------------------------------------------------- */
 #define JXP_NTHETA 8
 size_t jxp_transit_workspace_bytes(int32_t n_sets, int64_t n_times);
+/* Measurement helper, the K5 counterpart of jxp_system_list_stats (same 4 x int64 layout; [3] = 0):
+ * which kernels the LAST gradient-step call on this workspace used.  SYNCHRONISES `stream`. */
+int jxp_transit_list_stats(const void* workspace, int32_t n_sets, int64_t n_times,
+                           int64_t* stats_host, void* stream);
 
 int jxp_transit_partials_f64(const double* theta, int32_t n_sets, const double* star,
                              int64_t star_set_stride, const double* t, int64_t n_times,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "jxp_system_list_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "jxp_profile_events": (C.c_int, [_p, _p]),
     "jxp_transit_workspace_bytes": (_sz, [_i32, _i64]),
+    "jxp_transit_list_stats": (C.c_int, [_p, _i32, _i64, _p, _p]),
     "jxp_transit_partials_f64": (
         C.c_int,
         [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,

@@ -883,6 +883,25 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   return rc;
 }
 
+extern "C" int jxp_transit_list_stats(const void* workspace, int32_t n_sets, int64_t n_times,
+                                      int64_t* stats_host, void* stream) {
+  if (!workspace || !stats_host) return fail(JXP_ERR_NULL_POINTER, "jxp_transit_list_stats: null pointer");
+  if (n_sets <= 0 || n_times <= 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_list_stats: empty problem");
+  const TrLayout L = tr_layout(n_sets, n_times);
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t raw[4] = {0, 0, 0, 0};  // inside-list items, flags, edge-list items, unused
+  cudaError_t e = cudaMemcpyAsync(raw, ws + L.off_scalars + 4 * sizeof(double), 4 * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_transit_list_stats: %s", cudaGetErrorString(e));
+  stats_host[0] = raw[0] + raw[2];
+  stats_host[1] = raw[1] | ((unsigned long long)(raw[0] + raw[2]) > L.tl_cap ? 2 : 0);
+  stats_host[2] = raw[0];
+  stats_host[3] = 0;
+  return JXP_OK;
+}
+
 extern "C" int jxp_transit_partials_f64(const double* theta, int32_t n_sets, const double* star,
                                         int64_t star_set_stride, const double* t, int64_t n_times,
                                         double exposure_time, int32_t exp_order,

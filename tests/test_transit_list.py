@@ -307,6 +307,48 @@ def test_gradient_step_list_path_matches_rows_reduction_window_kernels_and_autog
         assert np.array_equal(ll2, ll) and np.array_equal(g2, g)
 
 
+def _grad_step_abi(theta, t, y, sigma):
+    """The gradient step through the C ABI with a workspace we keep -> (loglike, dloglike, list stats)."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+
+    dev = A.device()
+    th = torch.as_tensor(theta, device=dev).contiguous()
+    td = torch.as_tensor(t, device=dev)
+    yd = torch.as_tensor(y, device=dev)
+    sd = torch.full((1,), sigma, dtype=torch.float64, device=dev)
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+    ns, nt = th.shape[0], td.numel()
+    wsb = int(_lib.load().jxp_transit_workspace_bytes(ns, nt))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ll = torch.empty(ns, dtype=torch.float64, device=dev)
+    dll = torch.empty((ns, 8), dtype=torch.float64, device=dev)
+    _lib.call("jxp_transit_partials_f64", th.data_ptr(), ns, star.data_ptr(), 0, td.data_ptr(), nt, 0.0, 0, 0,
+              10, 0, None, None, yd.data_ptr(), sd.data_ptr(), 0, ll.data_ptr(), dll.data_ptr(), ws.data_ptr(), wsb,
+              A.stream_ptr())
+    st = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_transit_list_stats", ws.data_ptr(), ns, nt, ctypes.addressof(st), A.stream_ptr())
+    return ll.cpu().numpy(), dll.cpu().numpy(), [int(v) for v in st]
+
+
+def test_gradient_step_uses_the_list_and_reports_it():
+    from jaxoplanet_b200 import workloads as W
+
+    theta, t = W.c5(128, 20_000)
+    y = 1 + 5e-4 * np.random.default_rng(1).normal(size=t.size)
+    ll, g, st = _grad_step_abi(theta, t, y, 5e-4)
+    assert st[1] == 0 and 0.01 * 128 * 20_000 < st[0] < 0.06 * 128 * 20_000 and st[2] > 0.5 * st[0]
+    ll2, g2 = _grad_step(theta, t, y, 5e-4)
+    assert np.array_equal(ll, ll2) and np.array_equal(g, g2)
+    perm = np.random.default_rng(2).permutation(t.size)
+    _, _, st = _grad_step_abi(theta, t[perm], y[perm], 5e-4)
+    assert st[1] & 1  # unsorted: the window-test kernels did the work
+    _, _, st = _without_list(lambda: _grad_step_abi(theta, t, y, 5e-4))
+    assert st[0] == 0
+
+
 def test_gradient_step_falls_back_on_unsorted_times():
     from jaxoplanet_b200 import workloads as W
 

@@ -22,6 +22,9 @@ for label in ("list", "window"):
     for _ in range(5):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record(); call(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+    import ctypes
+    ls = (ctypes.c_int64 * 4)(); _lib.call("jxp_transit_list_stats", ws.data_ptr(), ns, nt, ctypes.addressof(ls), A.stream_ptr())
+    print(label, "list items", int(ls[0]), "flags", int(ls[1]), "inside", int(ls[2]))
     res[label] = (best, ll.clone(), dll.clone())
     print(label, "ms", best, "points/s", ns * nt / best * 1e3, "workspace GB", wsb / 1e9)
 l, w = res["list"], res["window"]
