@@ -622,7 +622,13 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
     ms = best_of(lambda: _lib.call("jxp_transit_partials_f64", thd.data_ptr(), ns5, star.data_ptr(), 0,
                                    t5d.data_ptr(), nt5, 0.0, 0, 0, 10, 0, 0, 0, y5.data_ptr(), sg5.data_ptr(), 0,
                                    ll5.data_ptr(), dll5.data_ptr(), ws5.data_ptr(), wsb5, A.stream_ptr()))
-    out["c5_loglike_plus_8_gradient_f64"] = {"points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms}
+    ls5 = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_transit_list_stats", ws5.data_ptr(), ns5, nt5, ctypes.addressof(ls5), A.stream_ptr())
+    out["c5_loglike_plus_8_gradient_f64"] = {
+        "points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms,
+        "path": "transit list (k_tl_build, k_tlg_eval, k_tlg_reduce)" if (ls5[0] > 0 and ls5[1] == 0)
+                else "window-test kernel (k_transit_partials)",
+        "list_items": int(ls5[0])}
     return out
 
 
