@@ -63,7 +63,14 @@ def pack_bodies(system: System):
         f[_lib.BODY_CENTRAL_RADIUS] = body.central_radius
         f[_lib.BODY_RADIUS] = 0.0 if body.radius is None else body.radius
         f[_lib.BODY_RESERVED] = 0.0
-        recs.append(torch.stack([_field(x, n_sets).to(dev) for x in f], dim=-1))
+        # fields that already live on one device are stacked there: ONE host-to-device copy of the
+        # record array later instead of one per field
+        fs = [_field(x, n_sets) for x in f]
+        if len({x.device for x in fs}) > 1:
+            fs = [x.to(dev) for x in fs]
+        recs.append(torch.stack(fs, dim=-1))
+    if len({r.device for r in recs}) > 1:
+        recs = [r.to(A.device()) for r in recs]
     bodies = torch.stack(recs, dim=1)  # [n_sets, n_bodies, 12]
     return bodies, n_sets, batched
 
