@@ -601,6 +601,19 @@ k_loglike_prep(const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss,
   loglike_prep_body<T>(blockIdx.x, gridDim.x, y, sigma, ss, n, winv, scalars, nullptr);
 }
 
+// the sortedness flags alone (list path of calls without a likelihood): LL_NCTA CTAs of 256 threads
+__global__ void __launch_bounds__(256)
+k_tl_sorted_check(const double* __restrict__ t, int64_t n, double* __restrict__ scalars) {
+  int bad = 0;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = lo + chunk < n ? lo + chunk : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+    if (i + 1 < n && !(t[i + 1] >= t[i])) bad = 1;
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) scalars[LL_FLAG0 + blockIdx.x] = bad ? 1.0 : 0.0;
+}
+
 // k_sys_prep and k_loglike_prep in one launch (they are independent): the first n_prep CTAs derive
 // the records, the next LL_NCTA the likelihood constants (and the sortedness flags for the list path)
 template <typename T>
@@ -741,6 +754,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.n_bodies;
   const int n_groups = a.n_groups;
+  if (a.tl_state != nullptr && tl_active(a.tl_state, a.tl_cap)) return;  // the transit-list kernels did the work
 
   BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
   SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * nb);
@@ -1612,7 +1626,8 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
 #ifndef JXP_TL_PU
 #define JXP_TL_PU 1
 #endif
-template <int PU>
+// FLUX: the per-item flux goes to flux / flux_sum (zeroed by the launcher) instead of a chi^2 term.
+template <int PU, bool FLUX = false>
 __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_constant__ SysArgs<double> a) {
   if (!tl_active(a.tl_state, a.tl_cap)) return;
   const unsigned long long totA = a.tl_state[0], totB = a.tl_state[2];
@@ -1720,6 +1735,18 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
         if (intr[h] && fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2);
       }
     }
+    if (FLUX) {
+      // the rows were zeroed before the launch: only a non-zero flux needs a store (positions of
+      // different items are disjoint, so there is no ordering between them)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (have[h] && tot[h] != 0.0) {
+          const size_t o = (size_t)slq[h] * (size_t)a.n_times + idxq[h];
+          if (a.flux_sum) a.flux_sum[o] = tot[h];
+          if (a.flux) a.flux[o] = tot[h];
+        }
+      }
+    } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       double dchi = 0.0;
@@ -1730,6 +1757,7 @@ __global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_const
         dchi = (-mw) * (2.0 * r0 - mw);
       }
       if (have[h]) reinterpret_cast<double*>(a.tl_items)[base + 32 * h + lane] = dchi;
+    }
     }
     base = nbase;
     valid = nvalid;
@@ -1832,9 +1860,12 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
 
   const bool f32 = sizeof(T) == 4;
   // transit-list path (see k_tl_build): eligibility is decided here, use on the device
-  const bool use_tl = sizeof(T) == 8 && loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 &&
-                      n_u <= 2 && gl_order == 10 && !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL &&
-                      L.tl_cap > 0 && getenv("JXP_NO_TL") == nullptr && getenv("JXP_NO_PAIR") == nullptr;
+  const bool tl_ok = sizeof(T) == 8 && n_bodies == 1 && a.st.n == 1 && n_u <= 2 && gl_order == 10 &&
+                     !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL && L.tl_cap > 0 &&
+                     getenv("JXP_NO_TL") == nullptr;
+  const bool use_tl = tl_ok && loglike && !flux && !flux_sum && getenv("JXP_NO_PAIR") == nullptr;
+  // ... and of calls that want the flux itself (light_curve(orbit, u)(t) of a batch of single-planet systems)
+  const bool use_tl_flux = tl_ok && !loglike && (flux || flux_sum);
   {
     const int n = n_sets * n_bodies;
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);
@@ -1851,6 +1882,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     } else {
       k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride, d_bodies,
                                                     d_sets, counters, tile_ctr, widen, 1e-7);
+      if (use_tl_flux) k_tl_sorted_check<<<LL_NCTA, 256, 0, st>>>(t, n_times, d_scalars);
     }
     rc = check_launch("jxp_system_light_curve(prep)");
     if (rc != JXP_OK) return rc;
@@ -1941,7 +1973,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
     const bool pair = loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 && n_u <= 2 &&
                       gl_order == 10 && a.use_window && n_times < (1LL << 25) && spc <= 64 &&
                       getenv("JXP_NO_PAIR") == nullptr;
-    if (pair && use_tl) {
+    // list + evaluation launches shared by the log-likelihood and the flux form of the list path
+    auto list_launch = [&](auto kern) -> int {
       a.tl_state = reinterpret_cast<unsigned long long*>(d_scalars + 4);
       a.tl_items = reinterpret_cast<unsigned long long*>(ws + L.off_tl_items);
       a.tl_off = reinterpret_cast<unsigned long long*>(ws + L.off_tl_off);
@@ -1963,9 +1996,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       if (g_ev_start && ev_on("build")) cudaEventRecord(g_ev_start, st);
       k_tl_build<0><<<(n_sets + 3) / 4, 128, 0, st>>>(ba);
       if (g_ev_stop && ev_on("build")) cudaEventRecord(g_ev_stop, st);
-      rc = check_launch("jxp_system_light_curve(transit list)");
-      if (rc != JXP_OK) return rc;
-      auto kern = k_tl_eval<JXP_TL_PU>;
+      int rcl = check_launch("jxp_system_light_curve(transit list)");
+      if (rcl != JXP_OK) return rcl;
       int per_sm = 0;
       cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
       if (eo != cudaSuccess || per_sm < 1)
@@ -1977,7 +2009,20 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       if (g_ev_start && ev_on("eval")) cudaEventRecord(g_ev_start, st);
       kern<<<(unsigned)(want < resident ? want : resident), 128, 0, st>>>(a);
       if (g_ev_stop && ev_on("eval")) cudaEventRecord(g_ev_stop, st);
-      rc = check_launch("jxp_system_light_curve(transit list eval)");
+      return check_launch("jxp_system_light_curve(transit list eval)");
+    };
+    if (use_tl_flux) {
+      // zero rows by the copy engine's fill, the in-transit samples scattered over them by k_tl_eval;
+      // with unsorted time stamps (or a list that does not fit) k_system below rewrites every row
+      cudaError_t em = cudaSuccess;
+      if (flux_sum) em = cudaMemsetAsync(flux_sum, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
+      if (em == cudaSuccess && flux) em = cudaMemsetAsync(flux, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
+      if (em != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve: memset: %s", cudaGetErrorString(em));
+      rc = list_launch(k_tl_eval<JXP_TL_PU, true>);
+      if (rc != JXP_OK) return rc;
+    }
+    if (pair && use_tl) {
+      rc = list_launch(k_tl_eval<JXP_TL_PU, false>);
       if (rc != JXP_OK) return rc;
       if (g_ev_start && ev_on("reduce")) cudaEventRecord(g_ev_start, st);
       k_tl_reduce<<<(n_sets + 3) / 4, 128, 0, st>>>(a);

@@ -295,12 +295,22 @@ def test_system_window_flag_is_bit_identical():
     from jaxoplanet_b200 import _lib
     from jaxoplanet_b200.light_curves.limb_dark import FusedSpec, _run_fused
 
+    import os
+
     t = np.linspace(-0.5, 27.0, 50_000)
     u = np.array([0.3, 0.2])
     sys_ = _c1_system()
-    a = _run_fused(FusedSpec(sys_, u), t)
+    # the window-test kernel against the dense one: bit for bit (sorted time stamps of a single-planet
+    # system would otherwise take the transit-list kernels, a different program: tests/test_transit_list.py)
+    os.environ["JXP_NO_TL"] = "1"
+    try:
+        a = _run_fused(FusedSpec(sys_, u), t)
+    finally:
+        os.environ.pop("JXP_NO_TL", None)
     b = _run_fused(FusedSpec(sys_, u, flags=_lib.JXP_FLAG_NO_WINDOW), t)
     assert torch.equal(a, b)
+    c = _run_fused(FusedSpec(sys_, u), t)  # transit list
+    assert torch.equal(c != 0, b != 0) and float(torch.max(torch.abs(c - b))) <= 1e-15
 
 
 def test_loglike_is_bit_reproducible_under_dynamic_scheduling():

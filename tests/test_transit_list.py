@@ -363,3 +363,59 @@ def test_gradient_step_falls_back_on_unsorted_times():
     assert np.max(np.abs(ll - ll_s) / np.abs(ll_s)) <= 1e-11
     scale = np.abs(g_s).max(0, keepdims=True)
     assert np.max(np.abs(g - g_s) / np.maximum(np.abs(g_s), scale)) <= 1e-11
+
+
+# ----------------------------------------------------------------------------- flux outputs
+def _flux_abi(system, u, t, per_body=False):
+    """light_curve(orbit, u)(t) of a batch of single-planet systems through the C ABI -> (flux, list stats)."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    dev = A.device()
+    bodies, n_sets, _ = pack_bodies(system)
+    bodies = bodies.to(dev).contiguous()
+    ud = torch.as_tensor(np.asarray(u, dtype=np.float64), device=dev).contiguous()
+    u_stride = ud.shape[1] if ud.ndim == 2 else 0
+    td = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev).contiguous()
+    n_t = td.numel()
+    nbytes = int(_lib.load().jxp_system_workspace_bytes(n_sets, 1, n_t))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.full((n_sets, n_t), float("nan"), dtype=torch.float64, device=dev)
+    _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 1, ud.data_ptr(), ud.shape[-1], u_stride,
+              td.data_ptr(), n_t, 0.0, 0, 0, 10, 0, out.data_ptr() if per_body else None,
+              None if per_body else out.data_ptr(), None, None, 0, None, ws.data_ptr(), nbytes, A.stream_ptr())
+    st = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(st), A.stream_ptr())
+    return out.cpu().numpy(), [int(v) for v in st]
+
+
+def test_flux_outputs_take_the_list_and_match_oracle_and_window_kernels():
+    from jaxoplanet_b200 import workloads as W
+
+    p, ub, t, _, _ = W.c3(150, 25_000)
+    sys_ = _system(p)
+    for per_body in (False, True):
+        f, st = _flux_abi(sys_, ub, t, per_body)
+        assert st[1] == 0 and st[0] > 0 and st[2] > 0.5 * st[0]
+        fw, stw = _without_list(lambda: _flux_abi(sys_, ub, t, per_body))
+        assert stw[0] == 0
+        assert np.array_equal(f != 0, fw != 0) and np.max(np.abs(f - fw)) <= 1e-15
+        for s in range(0, 150, 11):
+            bd = ref.orbital_body(**{k: v[s] for k, v in p.items()})
+            want = ref.system_light_curve([bd], ub[s], t)[:, 0]
+            assert np.max(np.abs(f[s] - want)) <= 1e-12
+    # unsorted time stamps: the window-test kernel writes every row
+    perm = np.random.default_rng(0).permutation(t.size)
+    f, st = _flux_abi(sys_, ub, t[perm])
+    fw, _ = _without_list(lambda: _flux_abi(sys_, ub, t[perm]))
+    assert st[1] & 1 and np.array_equal(f, fw)
+    # the facade call a reference user writes
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve
+
+    lc = limb_dark_light_curve(sys_, ub)(t)
+    assert lc.shape == (150, 25_000, 1)
+    f, _ = _flux_abi(sys_, ub, t)
+    assert np.array_equal(lc[..., 0], f)
