@@ -133,7 +133,7 @@ enum {
 /* Bytes of caller-provided device workspace (256-byte aligned) for one call of that shape: the
  * derived records, 1 / sigma, partial sums and, for single-body systems, room for the work list of
  * the log-likelihood path (8 bytes per in-window sample, sized for 1/8 of the grid + 65536
- * items; when the list does not fit, or the time stamps are not sorted, the same call falls back
+ * items, at most 2^28 items; when the list does not fit, or the time stamps are not sorted, the same call falls back
  * to the window-test kernels on the device -- results agree to rounding either way). */
 size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times);
 

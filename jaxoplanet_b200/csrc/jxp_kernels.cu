@@ -453,6 +453,7 @@ SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, 
     off = align_up(off + 2 * sizeof(unsigned) * (size_t)n_sets, 256);
     L.off_tl_items = off;
     L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 8ull + 65536ull;
+    if (L.tl_cap > (1ull << 28)) L.tl_cap = 1ull << 28;  // at most 2 GB of list; beyond it the call falls back
     off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
   }
   L.total = off;

@@ -67,6 +67,7 @@ TrLayout tr_layout(int n_sets, int64_t n_times) {
   L.off_tl_cnt = off;
   off = align_up(off + 2 * sizeof(unsigned) * (size_t)n_sets, 256);
   L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 16ull + 65536ull;
+  if (L.tl_cap > (1ull << 26)) L.tl_cap = 1ull << 26;  // at most 5.4 GB of list; beyond it the call falls back
   L.off_tl_items = off;
   off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
   L.off_tl_vals = off;
