@@ -287,6 +287,83 @@ __global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArg
   }
 }
 
+// K2 with the points of a tile sorted by what they need (double, quadratic law, order 10, no
+// derivatives): a planet fully inside the disk (b < 1 - r, r < 1) takes ld_solution_inside_n (constant
+// kappas and node cosines), everything else the general mirror-pair code.  Unlike the fused kernels
+// K2 sees (b, r) in any order, so a CTA classifies a tile of LDC_TILE points, compacts the two classes
+// into index lists in shared memory and its warps pull 32-point chunks of one class at a time: full
+// warps on one code.  Which code a point gets depends on the point alone.
+constexpr int LDC_TILE = 2048;
+__global__ void __launch_bounds__(128, 4) k_limb_dark_cls(const __grid_constant__ LdArgs<double> a) {
+  __shared__ unsigned short s_list[2][LDC_TILE];
+  __shared__ double s_b[LDC_TILE], s_r[LDC_TILE];  // the tile's points: the evaluation reads them from here
+  __shared__ int s_cnt[2], s_next[2];
+  double g0, g1, g2;
+  ld_greens<double>(a.n_u, a.n_u > 0 ? a.u[0] : 0.0, a.n_u > 1 ? a.u[1] : 0.0, g0, g1, g2);
+  const int lmax = a.n_u;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + LDC_TILE - 1) / LDC_TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * LDC_TILE;
+    if (threadIdx.x < 2) {
+      s_cnt[threadIdx.x] = 0;
+      s_next[threadIdx.x] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LDC_TILE / 128; ++k) {
+      const int j = k * 128 + threadIdx.x;
+      const int64_t i = base + j;
+      int cls = -1;
+      if (i < a.n) {
+        const double b0 = a.b[i * a.bs], r0 = a.r[i * a.rs];
+        s_b[j] = b0;
+        s_r[j] = r0;
+        const double b = fabs(b0), r = fabs(r0);
+        cls = ((b < 1.0 - r) && (r < 1.0)) ? 0 : 1;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        int off = 0;
+        if (lane == 0 && m) off = atomicAdd(&s_cnt[c], __popc(m));
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (cls == c) s_list[c][off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int cnt = s_cnt[c];
+      while (true) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&s_next[c], 64);  // two points per lane: two dependency chains
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= cnt) break;
+        bool have[2];
+        int64_t i[2];
+        double b[2], r[2], s0[2], s1[2], s2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          have[h] = q + 32 * h + lane < cnt;
+          const int j = s_list[c][have[h] ? q + 32 * h + lane : q];
+          i[h] = base + j;
+          b[h] = s_b[j];
+          r[h] = s_r[j];
+        }
+        if (c == 0)
+          ld_solution_inside_n<2>(b, r, lmax, s0, s1, s2);
+        else
+          ld_solution_n<2, 1>(b, r, lmax, s0, s1, s2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (have[h]) a.flux[i[h]] = ld_combine(lmax, s0[h], s1[h], s2[h], g0, g1, g2);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, const T* r,
                             int64_t rs, int64_t n, int32_t order, T* flux, T* db, T* dr, T* svec,
@@ -334,7 +411,16 @@ static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, con
   } else if (order == 10) {
     if (sizeof(T) == 8) {
       // double: the mirror-pair node loop (ORDER tag 11), 2.9e10 vs 2.0e10 evaluations/s
-      if (grad) go(k_limb_dark<T, 11, true, false>); else go(k_limb_dark<T, 11, false, false>);
+      if (grad) {
+        go(k_limb_dark<T, 11, true, false>);
+      } else if (n >= 4 * LDC_TILE && getenv("JXP_NO_LD_CLASSES") == nullptr) {
+        if constexpr (sizeof(T) == 8) {
+          const int64_t tiles = (n + LDC_TILE - 1) / LDC_TILE, capc = (int64_t)sm_count() * 4;
+          k_limb_dark_cls<<<(unsigned)(tiles < capc ? tiles : capc), 128, 0, st>>>(a);
+        }
+      } else {
+        go(k_limb_dark<T, 11, false, false>);
+      }
     } else {
       if (grad) go(k_limb_dark<T, 10, true, false>); else go(k_limb_dark<T, 10, false, false>);
     }

@@ -360,9 +360,12 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     kappa0 = jatan2(area, b2o + factor);
     kappa1 = jatan2(area, b2o - factor);
   } else {
-    // area == 0 (constant): atan2(+0, x) is 0 for x >= +0 and pi for x < 0, derivative 0
-    kappa0 = S((val(b2o) + val(factor) < B(0)) ? pi : B(0));
-    kappa1 = S((val(b2o) - val(factor) < B(0)) ? pi : B(0));
+    // area == 0 (constant): atan2(+0, x) is 0 for x >= +0 and pi for x < 0, derivative 0; a NaN b or
+    // r has to stay a NaN as it does through the reference's atan2 (the comparisons above are all
+    // false for it, and s0 of the uniform-disk term would otherwise come out finite)
+    const B k0x = val(b2o) + val(factor), k1x = val(b2o) - val(factor);
+    kappa0 = S((k0x != k0x) ? k0x : ((k0x < B(0)) ? pi : B(0)));
+    kappa1 = S((k1x != k1x) ? k1x : ((k1x < B(0)) ? pi : B(0)));
   }
 
   const bool no_occ = val(b) >= B(1) + val(r);

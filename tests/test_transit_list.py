@@ -419,3 +419,43 @@ def test_flux_outputs_take_the_list_and_match_oracle_and_window_kernels():
     assert lc.shape == (150, 25_000, 1)
     f, _ = _flux_abi(sys_, ub, t)
     assert np.array_equal(lc[..., 0], f)
+
+
+# ----------------------------------------------------------------------------- K2 sorted by class
+def test_limb_dark_class_sorted_kernel_matches_plain_kernel_and_oracle():
+    """core.limb_dark.light_curve on >= 8192 points (double, quadratic, order 10) sorts each tile's points
+    into "planet fully inside the disk" and "everything else" and runs one flux code per class
+    (k_limb_dark_cls); the plain kernel (JXP_NO_LD_CLASSES) and the oracle are the references.  Edge
+    values of the reference's own test (tests/core/limb_dark_test.py:27-31) are mixed in."""
+    from jaxoplanet_b200.core.limb_dark import light_curve
+
+    rng = np.random.default_rng(17)
+    n = 60_001
+    r = rng.uniform(0.01, 1.3, n)
+    b = rng.uniform(0, 1, n) * (1.2 + r)
+    r[:5] = [0.01, 0.1, 0.5, 1.1, 2.0]
+    for k, rk in enumerate([0.01, 0.1, 0.5, 1.1, 2.0]):  # contact points and the centre
+        sl = slice(10 + 8 * k, 18 + 8 * k)
+        r[sl] = rk
+        b[sl] = [0.0, abs(1 - rk), 1 + rk, rk, abs(1 - rk) - 1e-14, abs(1 - rk) + 1e-14, 1 + rk - 1e-14, 1e-300]
+    b[100] = np.nan
+    r[101] = np.nan
+    b[102] = -0.3  # the reference takes |b|
+    for u in ([0.3, 0.2], [0.4], []):
+        got = light_curve(np.array(u), b, r)
+        os.environ["JXP_NO_LD_CLASSES"] = "1"
+        try:
+            plain = light_curve(np.array(u), b, r)
+        finally:
+            os.environ.pop("JXP_NO_LD_CLASSES", None)
+        with np.errstate(all="ignore"):
+            want = ref.ld_light_curve(np.array(u), b[:20_000], r[:20_000])
+        ok = np.isfinite(want)
+        # a NaN b or r is a NaN flux in the reference (it goes through atan2 and the kite area), for every
+        # law length; both kernels must agree with that
+        assert not ok[100] and not ok[101] and ok[102]
+        assert np.array_equal(np.isfinite(got[:20_000]), ok) and np.array_equal(np.isfinite(plain[:20_000]), ok)
+        fin = np.isfinite(plain)
+        assert np.array_equal(np.isfinite(got), fin)
+        assert np.max(np.abs(got[fin] - plain[fin])) <= 2e-15
+        assert np.max(np.abs(got[:20_000][ok] - want[ok])) <= 1e-12
