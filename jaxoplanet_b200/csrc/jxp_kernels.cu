@@ -287,81 +287,84 @@ __global__ void __launch_bounds__(256) k_limb_dark(const __grid_constant__ LdArg
   }
 }
 
-// K2 with the points of a tile sorted by what they need (double, quadratic law, order 10, no
-// derivatives): a planet fully inside the disk (b < 1 - r, r < 1) takes ld_solution_inside_n (constant
-// kappas and node cosines), everything else the general mirror-pair code.  Unlike the fused kernels
-// K2 sees (b, r) in any order, so a CTA classifies a tile of LDC_TILE points, compacts the two classes
-// into index lists in shared memory and its warps pull 32-point chunks of one class at a time: full
-// warps on one code.  Which code a point gets depends on the point alone.
-constexpr int LDC_TILE = 2048;
+// K2 with the points sorted by what they need (double, quadratic law, order 10, no derivatives): a
+// planet fully inside the disk (b < 1 - r, r < 1) takes ld_solution_inside_n (constant kappas and node
+// cosines: 6.1e10 evaluations/s dense against 2.9e10 for the general mirror-pair code,
+// tools/ubench/ld_bench.cu), everything else the general code.  Unlike the fused kernels K2 sees (b, r)
+// in any order, so every WARP keeps two private queues of (b, r, index) in shared memory, one per class:
+// it classifies 128 consecutive points at a time into them and, whenever a queue holds 64 entries,
+// evaluates 64 points of that class, two per lane, from the top of the queue.  No block barriers, no
+// partial warps before the very end, and the code a point gets depends on the point alone.
+constexpr int LDC_SUB = 128;   // points classified per round
+constexpr int LDC_QCAP = 192;  // per class: up to 63 left over + 128 new
 __global__ void __launch_bounds__(128, 4) k_limb_dark_cls(const __grid_constant__ LdArgs<double> a) {
-  __shared__ unsigned short s_list[2][LDC_TILE];
-  __shared__ double s_b[LDC_TILE], s_r[LDC_TILE];  // the tile's points: the evaluation reads them from here
-  __shared__ int s_cnt[2], s_next[2];
+  __shared__ double s_b[4][2][LDC_QCAP], s_r[4][2][LDC_QCAP];
+  __shared__ unsigned long long s_i[4][2][LDC_QCAP];
   double g0, g1, g2;
   ld_greens<double>(a.n_u, a.n_u > 0 ? a.u[0] : 0.0, a.n_u > 1 ? a.u[1] : 0.0, g0, g1, g2);
   const int lmax = a.n_u;
-  const int lane = threadIdx.x & 31;
-  const int64_t n_tiles = (a.n + LDC_TILE - 1) / LDC_TILE;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = tile * LDC_TILE;
-    if (threadIdx.x < 2) {
-      s_cnt[threadIdx.x] = 0;
-      s_next[threadIdx.x] = 0;
-    }
-    __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  int qn[2] = {0, 0};
+  // 64 entries (fewer only in the final flush) from the top of queue c
+  auto drain = [&](int c) {
+    const int take = qn[c] < 64 ? qn[c] : 64;
+    const int first = qn[c] - take;
+    bool have[2];
+    unsigned long long i[2];
+    double b[2], r[2], s0[2], s1[2], s2[2];
 #pragma unroll
-    for (int k = 0; k < LDC_TILE / 128; ++k) {
-      const int j = k * 128 + threadIdx.x;
-      const int64_t i = base + j;
+    for (int h = 0; h < 2; ++h) {
+      have[h] = 32 * h + lane < take;
+      const int e = first + (have[h] ? 32 * h + lane : 0);
+      b[h] = s_b[warp][c][e];
+      r[h] = s_r[warp][c][e];
+      i[h] = s_i[warp][c][e];
+    }
+    if (c == 0)
+      ld_solution_inside_n<2>(b, r, lmax, s0, s1, s2);
+    else
+      ld_solution_n<2, 1>(b, r, lmax, s0, s1, s2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (have[h]) a.flux[i[h]] = ld_combine(lmax, s0[h], s1[h], s2[h], g0, g1, g2);
+    qn[c] = first;
+    __syncwarp();
+  };
+  const int64_t n_sub = (a.n + LDC_SUB - 1) / LDC_SUB;
+  const int64_t nw = (int64_t)gridDim.x * 4;
+  for (int64_t sub = (int64_t)blockIdx.x * 4 + warp; sub < n_sub; sub += nw) {
+#pragma unroll
+    for (int k = 0; k < LDC_SUB / 32; ++k) {
+      const int64_t i = sub * LDC_SUB + 32 * k + lane;
       int cls = -1;
+      double b0 = 0.0, r0 = 0.0;
       if (i < a.n) {
-        const double b0 = a.b[i * a.bs], r0 = a.r[i * a.rs];
-        s_b[j] = b0;
-        s_r[j] = r0;
+        b0 = a.b[i * a.bs];
+        r0 = a.r[i * a.rs];
         const double b = fabs(b0), r = fabs(r0);
         cls = ((b < 1.0 - r) && (r < 1.0)) ? 0 : 1;
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
-        int off = 0;
-        if (lane == 0 && m) off = atomicAdd(&s_cnt[c], __popc(m));
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (cls == c) s_list[c][off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
-      }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int cnt = s_cnt[c];
-      while (true) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(&s_next[c], 64);  // two points per lane: two dependency chains
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= cnt) break;
-        bool have[2];
-        int64_t i[2];
-        double b[2], r[2], s0[2], s1[2], s2[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          have[h] = q + 32 * h + lane < cnt;
-          const int j = s_list[c][have[h] ? q + 32 * h + lane : q];
-          i[h] = base + j;
-          b[h] = s_b[j];
-          r[h] = s_r[j];
+        if (cls == c) {
+          const int e = qn[c] + __popc(m & lt);
+          s_b[warp][c][e] = b0;
+          s_r[warp][c][e] = r0;
+          s_i[warp][c][e] = (unsigned long long)i;
         }
-        if (c == 0)
-          ld_solution_inside_n<2>(b, r, lmax, s0, s1, s2);
-        else
-          ld_solution_n<2, 1>(b, r, lmax, s0, s1, s2);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (have[h]) a.flux[i[h]] = ld_combine(lmax, s0[h], s1[h], s2[h], g0, g1, g2);
+        qn[c] += __popc(m);
       }
     }
-    __syncthreads();
+    __syncwarp();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c)
+      while (qn[c] >= 64) drain(c);
   }
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c)
+    while (qn[c] > 0) drain(c);
 }
 
 template <typename T>
@@ -413,10 +416,10 @@ static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, con
       // double: the mirror-pair node loop (ORDER tag 11), 2.9e10 vs 2.0e10 evaluations/s
       if (grad) {
         go(k_limb_dark<T, 11, true, false>);
-      } else if (n >= 4 * LDC_TILE && getenv("JXP_NO_LD_CLASSES") == nullptr) {
+      } else if (n >= 8192 && getenv("JXP_NO_LD_CLASSES") == nullptr) {
         if constexpr (sizeof(T) == 8) {
-          const int64_t tiles = (n + LDC_TILE - 1) / LDC_TILE, capc = (int64_t)sm_count() * 4;
-          k_limb_dark_cls<<<(unsigned)(tiles < capc ? tiles : capc), 128, 0, st>>>(a);
+          const int64_t ctas = (n + 4 * LDC_SUB - 1) / (4 * LDC_SUB), capc = (int64_t)sm_count() * 4;
+          k_limb_dark_cls<<<(unsigned)(ctas < capc ? ctas : capc), 128, 0, st>>>(a);
         }
       } else {
         go(k_limb_dark<T, 11, false, false>);

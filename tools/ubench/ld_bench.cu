@@ -28,6 +28,19 @@ __global__ void __launch_bounds__(128, MINB) k_multi(const double* b, const doub
     for (int q = 0; q < N; ++q) out[i + q * stride] = ld_combine(2, s0[q], s1[q], s2[q], 0.3, 0.2, 0.1);
   }
 }
+// planet fully inside the disk: the constant-node code, N points per thread
+template <int N, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_inside(const double* b, const double* r, double* out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + (N - 1) * stride < n; i += N * stride) {
+    double bb[N], rr[N], s0[N], s1[N], s2[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) { bb[q] = b[i + q * stride]; rr[q] = r[i + q * stride]; }
+    ld_solution_inside_n<N>(bb, rr, 2, s0, s1, s2);
+#pragma unroll
+    for (int q = 0; q < N; ++q) out[i + q * stride] = ld_combine(2, s0[q], s1[q], s2[q], 0.3, 0.2, 0.1);
+  }
+}
 template <typename F>
 float timeit(F f) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -56,5 +69,11 @@ int main() {
 #define RUN_M(N, PU, MINB) { float ms = timeit([&] { k_multi<N, PU, MINB><<<148 * MINB, 128>>>(b, r, o1, n); }); report("multi N" #N " PU" #PU " MINB" #MINB, ms, o1); }
   RUN_S(1, 8) RUN_S(1, 5) RUN_S(5, 5) RUN_S(5, 4)
   RUN_M(1, 5, 5) RUN_M(2, 5, 4)
+  // inside-the-disk points only (b < 1 - r)
+  for (int64_t i = 0; i < n; ++i) hb[i] = U(g) * (1 - hr[i]) * 0.999;
+  cudaMemcpy(b, hb.data(), n * 8, cudaMemcpyHostToDevice);
+  { float ms = timeit([&] { k_scalar<5, 5><<<148 * 5, 128>>>(b, r, o0, n); }); cudaMemcpy(h0.data(), o0, n * 8, cudaMemcpyDeviceToHost); report("inside pts: general", ms, o0); }
+#define RUN_I(N, MINB) { float ms = timeit([&] { k_inside<N, MINB><<<148 * MINB, 128>>>(b, r, o1, n); }); report("inside N" #N " MINB" #MINB, ms, o1); }
+  RUN_I(1, 8) RUN_I(1, 5) RUN_I(2, 5) RUN_I(2, 4) RUN_I(3, 4) RUN_I(4, 3) RUN_I(4, 2)
   return 0;
 }
