@@ -1957,7 +1957,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // ... and of calls that want the flux itself (light_curve(orbit, u)(t) of a batch of single-planet systems)
   // (from 2^20 points: below that the extra launches cost more than the list saves -- config 1, one set x
   // 1e5 samples, takes 39 us with the window-test kernel and 47 us with the list)
-  const bool use_tl_flux = tl_ok && !loglike && (flux || flux_sum) && (int64_t)n_sets * n_times >= (1LL << 20);
+  int64_t flux_min_points = 1LL << 20;
+  if (const char* env = getenv("JXP_TL_FLUX_MIN_POINTS")) flux_min_points = atoll(env);  // development knob
+  const bool use_tl_flux = tl_ok && !loglike && (flux || flux_sum) && (int64_t)n_sets * n_times >= flux_min_points;
   {
     const int n = n_sets * n_bodies;
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);

@@ -459,3 +459,17 @@ def test_limb_dark_class_sorted_kernel_matches_plain_kernel_and_oracle():
         assert np.array_equal(np.isfinite(got), fin)
         assert np.max(np.abs(got[fin] - plain[fin])) <= 2e-15
         assert np.max(np.abs(got[:20_000][ok] - want[ok])) <= 1e-12
+
+
+def test_randomised_list_kernels_against_window_kernels():
+    """tools/tl_fuzz.py: 80 small random problems (irregular sorted time stamps with duplicates, circular and
+    eccentric bodies, grazing / non-transiting / huge planets, periods from 0.03 to 1000 d): log-likelihood,
+    flux and gradient step of the list kernels against the window-test kernels -- same support, same
+    finiteness, differences at rounding level."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "tl_fuzz.py"), "80", "3"], capture_output=True,
+                       text=True, cwd=root)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
