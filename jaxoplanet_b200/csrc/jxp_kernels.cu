@@ -860,6 +860,13 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   unsigned short* meq =
       reinterpret_cast<unsigned short*>(reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + nwarps * SYS_QCAP +
                                         nwarps * (32 * SYS_MB)) + warp * 64;
+  // multi variant, double, quadratic law, order 10: the in-transit (sample, body, sub-sample) triples are
+  // sorted by flux code after the position stage (see "class queues" below).  Two queues of (b, meta)
+  // alias the dense variant's sqb (unused here); the edge class has its own per-(sample, body) sums.
+  constexpr bool CLS = MULTI && !HI && ORDER == 11 && std::is_same<T, double>::value;
+  double* cqb = reinterpret_cast<double*>(sqb);                // [2][64]
+  unsigned* cqm = reinterpret_cast<unsigned*>(cqb + 2 * 64);   // [2][64]
+  T* maccE = reinterpret_cast<T*>(meq - warp * 64 + nwarps * 64) + warp * (32 * nb);  // [32][nb]
 
   const int nsub = a.st.n;
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
@@ -1168,9 +1175,13 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
         // lanes with the same target taking turns by lane index: deterministic.
         const BodyC<T>* bodies = sbody + sl * nb;
 #pragma unroll 1
-        for (int b = 0; b < nb; ++b) macc[lane * SYS_MB + b] = T(0);
+        for (int b = 0; b < nb; ++b) {
+          macc[lane * SYS_MB + b] = T(0);
+          if (CLS) maccE[lane * nb + b] = T(0);
+        }
         __syncwarp();
         const unsigned lt = (1u << lane) - 1u;
+        int cqn[2] = {0, 0};  // class queue fills (warp-uniform)
         const int nsteps = nb * nsub;
         int en = 0, b = 0, j = 0;
         bool bpass = false, always = false;
@@ -1204,13 +1215,92 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
             }
             __syncwarp();
           }
-          if (en >= 32 || (step == nsteps && en > 0)) {
+          if (en >= 32 || (step == nsteps && (en > 0 || (CLS && (cqn[0] | cqn[1]) != 0)))) {
             const int nbatch = en < 32 ? en : 32;
             const bool ev = lane < nbatch;
             const unsigned it = ev ? meq[lane] : 0u;
             const int esrc = (int)(it & 31u), ej = (int)((it >> 5) & 63u), eb = (int)(it >> 11);
             const double tms = __shfl_sync(0xffffffffu, tm0, esrc);
             const int sls = __shfl_sync(0xffffffffu, sl, esrc);
+            if constexpr (CLS) {
+              // Class queues.  Position stage for the 32 triples; the ones in transit go to one of two
+              // queues by the flux code they need -- planet fully inside the disk (ld_solution_inside_n:
+              // constant kappas and node cosines, 2.1x the rate of the general code) or not -- and a
+              // queue is evaluated 32 entries at a time, first in first out.  Each class adds into its
+              // own per-(sample, body) sum in increasing sub-sample order whatever the grouping, and the
+              // two sums are added at the end: the result does not depend on which samples share a drain
+              // (windowed and dense evaluation stay bit-identical).
+              int cls = -1;
+              double bsep = 0.0;
+              if (ev) {
+                ++n_kep;
+                const BodyC<T>& c = sbody[sls * nb + eb];
+                const double Mr = mean_anomaly_reduced(c, tms + a.st.dt[ej]);
+                double sf, cf, Ed;
+                if (c.flags & BODY_CIRCULAR)
+                  jsincos(Mr, &sf, &cf);
+                else
+                  kepler_reduced<double, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Ed);
+                double Z;
+                sky_position(c, sf, cf, bsep, Z);
+                if ((Z > 0.0) && !(bsep >= c.onepr)) {
+                  const double ar = fabs(c.rr);
+                  cls = ((bsep < 1.0 - ar) && (ar < 1.0)) ? 0 : 1;
+                  ++n_ld;
+                }
+              }
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == cc);
+                if (cls == cc) {
+                  const int e = cqn[cc] + __popc(m & lt);
+                  cqb[cc * 64 + e] = bsep;
+                  cqm[cc * 64 + e] = (unsigned)esrc | ((unsigned)eb << 5) | ((unsigned)ej << 8) | ((unsigned)sls << 14);
+                }
+                cqn[cc] += __popc(m);
+              }
+              __syncwarp();
+              const bool last = (step == nsteps) && (en - nbatch == 0);
+#pragma unroll 1
+              for (int cc = 0; cc < 2; ++cc) {
+                while (cqn[cc] >= 32 || (last && cqn[cc] > 0)) {
+                  const int nb2 = cqn[cc] < 32 ? cqn[cc] : 32;
+                  const bool ev2 = lane < nb2;
+                  const unsigned meta = cqm[cc * 64 + (ev2 ? lane : 0)];
+                  const int tgt2 = ev2 ? (int)(meta & 255u) : (-1 - lane);  // (queued sample, body)
+                  const int ej2 = (int)((meta >> 8) & 63u), sls2 = (int)(meta >> 14), eb2 = (int)((meta >> 5) & 7u);
+                  double bb1[1] = {cqb[cc * 64 + (ev2 ? lane : 0)]}, rr1[1] = {(double)sbody[sls2 * nb + eb2].rr};
+                  double s0[1], s1[1], s2[1];
+                  const SetC<T>& sc2 = sset[sls2];
+                  if (cc == 0)
+                    ld_solution_inside_n<1>(bb1, rr1, sc2.lmax, s0, s1, s2);
+                  else
+                    ld_solution<double, ORDER, false, PU>(bb1[0], rr1[0], sc2.lmax, &a.tab, s0[0], s1[0], s2[0]);
+                  const double v2 = ld_combine(sc2.lmax, s0[0], s1[0], s2[0], (double)sc2.g0, (double)sc2.g1, (double)sc2.g2);
+                  T* acc2 = cc == 0 ? macc : maccE;
+                  const int slot = ev2 ? ((int)(meta & 31u) * (cc == 0 ? SYS_MB : nb) + eb2) : 0;
+                  const unsigned same = __match_any_sync(0xffffffffu, tgt2);
+                  const int rank = __popc(same & lt);
+                  const int maxr = (int)__reduce_max_sync(0xffffffffu, (unsigned)(ev2 ? rank : 0));
+#pragma unroll 1
+                  for (int r = 0; r <= maxr; ++r) {
+                    if (ev2 && rank == r) acc2[slot] = jfma(T(a.st.w[ej2]), T(v2), acc2[slot]);
+                    __syncwarp();
+                  }
+                  // first in, first out: move the rest of the queue to the front
+                  const int rem2 = cqn[cc] - nb2;
+                  const double kb = (lane < rem2) ? cqb[cc * 64 + 32 + lane] : 0.0;
+                  const unsigned km = (lane < rem2) ? cqm[cc * 64 + 32 + lane] : 0u;
+                  __syncwarp();
+                  if (lane < rem2) {
+                    cqb[cc * 64 + lane] = kb;
+                    cqm[cc * 64 + lane] = km;
+                  }
+                  cqn[cc] = rem2;
+                  __syncwarp();
+                }
+              }
+            } else {
             T v = T(0);
             if (ev) {
               ++n_kep;
@@ -1225,6 +1315,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
               if (ev && rank == r) macc[tgt] = (nsub == 1) ? v : jfma(T(a.st.w[ej]), v, macc[tgt]);
               __syncwarp();
             }
+            }
             // keep what did not fit into this batch
             const int rem = en - nbatch;
             const unsigned short keep = (lane < rem) ? meq[32 + lane] : (unsigned short)0;
@@ -1238,7 +1329,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
           const int set = set_base + sl;
 #pragma unroll 1
           for (int bb = 0; bb < nb; ++bb) {
-            const T accb = macc[lane * SYS_MB + bb];
+            const T accb = CLS ? macc[lane * SYS_MB + bb] + maccE[lane * nb + bb] : macc[lane * SYS_MB + bb];
             if (a.flux) a.flux[((size_t)set * a.n_times + idx) * nb + bb] = accb;
             total += accb;
           }
@@ -2043,7 +2134,8 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
                       sizeof(double) * (size_t)spc * (threads / 32) +
                       sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32) +
                       sizeof(T) * (size_t)SYS_QCAP * (threads / 32) +
-                      (multi ? (sizeof(T) * 32 * SYS_MB + sizeof(unsigned short) * 64) * (size_t)(threads / 32) : 0);
+                      (multi ? (sizeof(T) * 32 * SYS_MB + sizeof(unsigned short) * 64 + sizeof(T) * 32 * n_bodies) *
+                                   (size_t)(threads / 32) : 0);
   if (smem > 200 * 1024) return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve: shared memory");
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
