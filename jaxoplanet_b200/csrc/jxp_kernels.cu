@@ -1236,13 +1236,16 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
                 ++n_kep;
                 const BodyC<T>& c = sbody[sls * nb + eb];
                 const double Mr = mean_anomaly_reduced(c, tms + a.st.dt[ej]);
-                double sf, cf, Ed;
-                if (c.flags & BODY_CIRCULAR)
-                  jsincos(Mr, &sf, &cf);
-                else
-                  kepler_reduced<double, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Ed);
+                double sf1[1], cf1[1];  // (sin f, cos f) D: the position needs no division (sky_position_xy)
+                if (c.flags & BODY_CIRCULAR) {
+                  jsincos(Mr, &sf1[0], &cf1[0]);
+                } else {
+                  const double Mr1[1] = {Mr}, e1[1] = {c.e}, ome1[1] = {c.ome}, ope1[1] = {c.ope}, s11[1] = {c.s1me2},
+                               io1[1] = {c.inv_ope};
+                  kepler_reduced_n<1, true, true>(Mr1, e1, ome1, ope1, s11, io1, sf1, cf1);
+                }
                 double Z;
-                sky_position(c, sf, cf, bsep, Z);
+                sky_position_xy(c, sf1[0], cf1[0], bsep, Z);
                 if ((Z > 0.0) && !(bsep >= c.onepr)) {
                   const double ar = fabs(c.rr);
                   cls = ((bsep < 1.0 - ar) && (ar < 1.0)) ? 0 : 1;
