@@ -794,6 +794,10 @@ struct SysArgs {
   unsigned long long tl_cap;
   const double* scalars;
   double* loglike;
+  // byte offsets of the regions of k_system's dynamic shared memory (computed once by the launcher: the
+  // kernel re-derived them from sets_per_cta / n_bodies / warps at every use under register pressure --
+  // 9 % of config 4's instructions)
+  int so_sset, so_sacc, so_sq, so_sqb, so_macc, so_meq, so_maccE;
   Stencil st;
   GLTable tab;
 };
@@ -847,26 +851,22 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
   if (a.tl_state != nullptr && tl_active(a.tl_state, a.tl_cap)) return;  // the transit-list kernels did the work
 
   BodyC<T>* sbody = reinterpret_cast<BodyC<T>*>(smem_raw);
-  SetC<T>* sset = reinterpret_cast<SetC<T>*>(sbody + a.sets_per_cta * nb);
-  double* sacc_all = reinterpret_cast<double*>(sset + a.sets_per_cta);  // [nwarps][sets_per_cta]
-  unsigned short* sq_all = reinterpret_cast<unsigned short*>(sacc_all + nwarps * a.sets_per_cta);
-  double* sacc = sacc_all + warp * a.sets_per_cta;
-  unsigned short* sq = sq_all + warp * SYS_QCAP;
+  SetC<T>* sset = reinterpret_cast<SetC<T>*>(smem_raw + a.so_sset);
+  double* sacc = reinterpret_cast<double*>(smem_raw + a.so_sacc) + warp * a.sets_per_cta;  // [nwarps][sets_per_cta]
+  unsigned short* sq = reinterpret_cast<unsigned short*>(smem_raw + a.so_sq) + warp * SYS_QCAP;
   // dense variant: sky separation of the queued in-transit samples
-  T* sqb = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + warp * SYS_QCAP;
+  T* sqb = reinterpret_cast<T*>(smem_raw + a.so_sqb) + warp * SYS_QCAP;
   // multi variant (PU == 5): per-warp evaluation queue and per-(queued sample, body) sums
   constexpr bool MULTI = (PU == 5);
-  T* macc = reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + nwarps * SYS_QCAP + warp * (32 * SYS_MB);
-  unsigned short* meq =
-      reinterpret_cast<unsigned short*>(reinterpret_cast<T*>(sq_all + nwarps * SYS_QCAP) + nwarps * SYS_QCAP +
-                                        nwarps * (32 * SYS_MB)) + warp * 64;
+  T* macc = reinterpret_cast<T*>(smem_raw + a.so_macc) + warp * (32 * SYS_MB);
+  unsigned short* meq = reinterpret_cast<unsigned short*>(smem_raw + a.so_meq) + warp * 64;
   // multi variant, double, quadratic law, order 10: the in-transit (sample, body, sub-sample) triples are
   // sorted by flux code after the position stage (see "class queues" below).  Two queues of (b, meta)
   // alias the dense variant's sqb (unused here); the edge class has its own per-(sample, body) sums.
   constexpr bool CLS = MULTI && !HI && ORDER == 11 && std::is_same<T, double>::value;
   double* cqb = reinterpret_cast<double*>(sqb);                // [2][64]
   unsigned* cqm = reinterpret_cast<unsigned*>(cqb + 2 * 64);   // [2][64]
-  T* maccE = reinterpret_cast<T*>(meq - warp * 64 + nwarps * 64) + warp * (32 * nb);  // [32][nb]
+  T* maccE = reinterpret_cast<T*>(smem_raw + a.so_maccE) + warp * (32 * nb);  // [32][nb]
 
   const int nsub = a.st.n;
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
@@ -2133,6 +2133,23 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // multi variant of stage C: double, order 10, <= SYS_MB bodies, more than one evaluation per sample
   const bool multi = sizeof(T) == 8 && n_u <= 2 && gl_order == 10 && n_bodies <= SYS_MB &&
                      (int64_t)n_bodies * a.st.n > 1 && !(((flags & JXP_FLAG_NO_WINDOW) != 0) && n_bodies == 1 && a.st.n == 1);
+  {
+    const size_t nwp = threads / 32;
+    size_t o = sizeof(BodyC<T>) * (size_t)spc * n_bodies;
+    a.so_sset = (int)o;
+    o += sizeof(SetC<T>) * (size_t)spc;
+    a.so_sacc = (int)o;
+    o += sizeof(double) * (size_t)spc * nwp;
+    a.so_sq = (int)o;
+    o += sizeof(unsigned short) * (size_t)SYS_QCAP * nwp;
+    a.so_sqb = (int)o;
+    o += sizeof(T) * (size_t)SYS_QCAP * nwp;
+    a.so_macc = (int)o;
+    o += sizeof(T) * 32 * SYS_MB * nwp;
+    a.so_meq = (int)o;
+    o += sizeof(unsigned short) * 64 * nwp;
+    a.so_maccE = (int)o;  // regions from so_macc on exist in the multi variant only
+  }
   const size_t smem = sizeof(BodyC<T>) * (size_t)spc * n_bodies + sizeof(SetC<T>) * (size_t)spc +
                       sizeof(double) * (size_t)spc * (threads / 32) +
                       sizeof(unsigned short) * (size_t)SYS_QCAP * (threads / 32) +
