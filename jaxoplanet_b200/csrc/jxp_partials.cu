@@ -615,7 +615,7 @@ k_tr_final(const double* __restrict__ partial, int n_tiles, int n_sets,
 // device exactly like the log-likelihood path (tl_active()).
 // --------------------------------------------------------------------------------------
 #ifndef JXP_TLG_MINB
-#define JXP_TLG_MINB 3
+#define JXP_TLG_MINB 4
 #endif
 __global__ void __launch_bounds__(128, JXP_TLG_MINB) k_tlg_eval(const __grid_constant__ TrArgs<double> a) {
   constexpr int NQ = 1 + JXP_NTHETA;
