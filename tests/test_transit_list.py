@@ -473,3 +473,59 @@ def test_randomised_list_kernels_against_window_kernels():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "tl_fuzz.py"), "80", "3"], capture_output=True,
                        text=True, cwd=root)
     assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_gradient_and_flux_list_paths_no_out_of_bounds_writes():
+    # sentinels around the workspace and every output; ragged sizes
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    dev = A.device()
+    guard = 4096
+    os.environ["JXP_TL_FLUX_MIN_POINTS"] = "0"
+    try:
+        for n_sets, n_t in ((1, 1), (5, 333), (33, 4099), (70, 9001)):
+            theta, t = W.c5(n_sets, n_t)
+            th = torch.as_tensor(theta, device=dev).contiguous()
+            td = torch.as_tensor(t, device=dev)
+            yd = torch.ones(n_t, dtype=torch.float64, device=dev)
+            sd = torch.full((1,), 5e-4, dtype=torch.float64, device=dev)
+            star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+            nbytes = int(_lib.load().jxp_transit_workspace_bytes(n_sets, n_t))
+            buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=dev)
+            ws = buf[guard:guard + nbytes]
+            ll = torch.full((n_sets + 16,), -7.0, dtype=torch.float64, device=dev)
+            dll = torch.full((n_sets * 8 + 16,), -7.0, dtype=torch.float64, device=dev)
+            _lib.call("jxp_transit_partials_f64", th.data_ptr(), n_sets, star.data_ptr(), 0, td.data_ptr(), n_t, 0.0, 0,
+                      0, 10, 0, None, None, yd.data_ptr(), sd.data_ptr(), 0, ll[8:].data_ptr(), dll[8:].data_ptr(),
+                      ws.data_ptr(), nbytes, A.stream_ptr())
+            torch.cuda.synchronize()
+            assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
+            assert bool((ll[:8] == -7.0).all()) and bool((ll[8 + n_sets:] == -7.0).all())
+            assert bool((dll[:8] == -7.0).all()) and bool((dll[8 + 8 * n_sets:] == -7.0).all())
+            assert bool(torch.isfinite(ll[8:8 + n_sets]).all()) and bool(torch.isfinite(dll[8:8 + 8 * n_sets]).all())
+            # flux list
+            p, ub, t3, _, _ = W.c3(n_sets, n_t)
+            bodies, _, _ = pack_bodies(_system(p))
+            bodies = bodies.to(dev).contiguous()
+            u = torch.as_tensor(ub, device=dev).contiguous()
+            t3d = torch.as_tensor(t3, device=dev)
+            nbytes = int(_lib.load().jxp_system_workspace_bytes(n_sets, 1, n_t))
+            buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=dev)
+            ws = buf[guard:guard + nbytes]
+            out = torch.full((n_sets * n_t + 16,), -7.0, dtype=torch.float64, device=dev)
+            _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, 1, u.data_ptr(), 2, 2, t3d.data_ptr(), n_t,
+                      0.0, 0, 0, 10, 0, None, out[8:].data_ptr(), None, None, 0, None, ws.data_ptr(), nbytes,
+                      A.stream_ptr())
+            st = (ctypes.c_int64 * 4)()
+            _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(st), A.stream_ptr())
+            assert st[1] == 0
+            assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
+            assert bool((out[:8] == -7.0).all()) and bool((out[8 + n_sets * n_t:] == -7.0).all())
+            assert bool(torch.isfinite(out[8:8 + n_sets * n_t]).all()) and bool((out[8:8 + n_sets * n_t] <= 0).all())
+    finally:
+        os.environ.pop("JXP_TL_FLUX_MIN_POINTS", None)
