@@ -445,7 +445,10 @@ def run_ours(args, rank, local_rank, world):
         "executed": {"kepler_solves": n_kep, "ld_evaluations": n_ld, "points": n_sets * n_times,
                      "in_transit_fraction": f_in},
         "flops_convention": "A-table v1: 302 flop per executed Kepler solve + orbit, 746 per executed LD evaluation; "
-                            "window pre-tests counted as 0",
+                            "window pre-tests counted as 0. The A-table charges every flux evaluation the reference's "
+                            "formula (10 node cosines, 2 atan2); for samples with the planet fully inside the disk the list "
+                            "path evaluates the same function with constant kappas and node cosines, i.e. fewer executed "
+                            "instructions than charged (hardware side: FP64 pipe 58 % active, profiles/r1_bench_tl_eval.md)",
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
     }
 
