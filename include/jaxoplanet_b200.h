@@ -131,10 +131,12 @@ enum {
 #define JXP_FLAG_NO_WINDOW 1
 
 /* Bytes of caller-provided device workspace (256-byte aligned) for one call of that shape: the
- * derived records, 1 / sigma, partial sums and, for single-body systems, room for the work list of
- * the log-likelihood path (8 bytes per in-window sample, sized for 1/8 of the grid + 65536
- * items, at most 2^28 items; when the list does not fit, or the time stamps are not sorted, the same call falls back
- * to the window-test kernels on the device -- results agree to rounding either way). */
+ * derived records, 1 / sigma, partial sums and, for single-body systems, the tables of the transit
+ * walk: a 256-byte record and a few dozen 8-byte (first position, first sample) segments
+ * per set, a 16-byte entry and an 8-byte partial sum per chunk of in-window samples -- nothing per
+ * sample.  Sized for 1/8 of the grid in transit and 384 transits per set on average; when that does
+ * not fit, or the time stamps are not sorted, the same call falls back to the window-test kernels
+ * on the device -- results agree to rounding either way. */
 size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times);
 
 int jxp_system_light_curve_f64(const double* bodies, int32_t n_sets, int32_t n_bodies,
@@ -153,6 +155,21 @@ int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_b
                                const float* sigma, int64_t sigma_stride, float* loglike,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Development / measurement options, process-wide (one atomic word; the library never reads the
+ * environment).  They select between code paths that return the same results; tests use them to
+ * compare the paths with each other.  Default 0. */
+#define JXP_DEV_NO_WALK 1u        /* single-body calls: window-test kernels instead of the transit walk */
+#define JXP_DEV_NO_PAIR 2u        /* log-likelihood: generic window-test kernel instead of k_system_pair */
+#define JXP_DEV_WALK_ANY_SIZE 4u  /* flux outputs: no minimum problem size for the transit walk */
+#define JXP_DEV_NO_LD_CLASSES 8u  /* jxp_limb_dark_f64: plain kernel instead of the class-sorted one */
+#define JXP_DEV_PROFILE_PLAN 16u  /* jxp_profile_events brackets the plan launch instead of the evaluation */
+#define JXP_DEV_CTA_WARPS(n) (((uint32_t)(n) & 0xfu) << 8)   /* window-test kernels: warps per CTA (1..4) */
+#define JXP_DEV_GET_CTA_WARPS(m) (((m) >> 8) & 0xfu)
+#define JXP_DEV_TR_RUN(n) (((uint32_t)(n) & 0x7fu) << 16)    /* jxp_transit_partials: warp tiles per run */
+#define JXP_DEV_GET_TR_RUN(m) (((m) >> 16) & 0x7fu)
+int jxp_set_dev_options(uint32_t mask);
+uint32_t jxp_get_dev_options(void);
+
 /* Measurement helper: when both events (cudaEvent_t as void*) are non-NULL, the calling
  * thread's subsequent jxp_system_light_curve_* calls record them on the launch stream
  * immediately before and after the dominant kernel (k_system), so that a harness can time that
@@ -166,14 +183,14 @@ int jxp_profile_events(void* start_event, void* stop_event);
 int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, int64_t n_times,
                      int64_t* stats_host, void* stream);
 
-/* Measurement helper: which kernels the LAST log-likelihood call on this workspace used.  With
- * sorted time stamps, one body and no exposure integration the in-window samples are expanded
- * into a work list in the workspace (DESIGN.md "transit list"); the choice is made on the device.
- * stats_host (4 x int64): [0] = items in the list, [1] = 0 when the list kernels produced the
- * result (and [0] > 0), bit 0: time stamps not sorted, bit 1: the list did not fit the workspace --
- * in both cases the window-test kernels produced it; [2] = items on the sub-list of samples
- * estimated to have the planet fully inside the stellar disk, [3] = 64-item chunks whose items all
- * passed the b < 1 - r check and took the constant-node flux code.  SYNCHRONISES `stream`. */
+/* Measurement helper: which kernels the LAST single-body call on this workspace used.  With
+ * sorted time stamps, one body and no exposure integration only the in-window samples are visited
+ * (DESIGN.md "transit walk"); the choice is made on the device.
+ * stats_host (4 x int64): [0] = in-window samples visited, [1] = 0 when the walk produced the
+ * result (and [0] > 0), bit 0: time stamps not sorted, bit 1: the tables did not fit the workspace --
+ * in both cases the window-test kernels produced it; [2] = samples on the sub-list estimated to have
+ * the planet fully inside the stellar disk, [3] = in-transit samples that passed the b < 1 - r check
+ * and took the constant-kappa flux code.  SYNCHRONISES `stream`. */
 int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
                           int64_t n_times, int64_t* stats_host, void* stream);
 

@@ -16,6 +16,22 @@ JXP_BODY_NFIELDS = 12
 JXP_NTHETA = 8
 JXP_FLAG_NO_WINDOW = 1
 JXP_FLAG_COUNT = 2
+# development / measurement options (jxp_set_dev_options): paths that return the same results
+JXP_DEV_NO_WALK = 1
+JXP_DEV_NO_PAIR = 2
+JXP_DEV_WALK_ANY_SIZE = 4
+JXP_DEV_NO_LD_CLASSES = 8
+JXP_DEV_PROFILE_PLAN = 16
+
+
+def JXP_DEV_CTA_WARPS(n):
+    return (int(n) & 0xF) << 8
+
+
+def JXP_DEV_TR_RUN(n):
+    return (int(n) & 0x7F) << 16
+
+
 JXP_TO_NFIELDS = 6
 JXP_EL_NFIELDS = 16
 (EL_PERIOD, EL_SEMIMAJOR, EL_TIME_TRANSIT, EL_TIME_PERI, EL_ECC, EL_OMEGA, EL_SIN_OMEGA, EL_COS_OMEGA,
@@ -42,6 +58,8 @@ _sz = C.c_size_t
 SIGNATURES = {
     "jxp_version": (C.c_int, []),
     "jxp_last_error": (C.c_char_p, []),
+    "jxp_set_dev_options": (C.c_int, [C.c_uint32]),
+    "jxp_get_dev_options": (C.c_uint32, []),
     "jxp_kepler_f64": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "jxp_kepler_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "jxp_limb_dark_f64": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
@@ -111,3 +129,21 @@ def check(code: int):
 
 def call(name: str, *args):
     check(getattr(load(), name)(*args))
+
+
+class dev_options:
+    """``with dev_options(JXP_DEV_NO_WALK): ...`` -- OR the mask into the library's development options
+    for the duration of the block (tests compare code paths that return the same results)."""
+
+    def __init__(self, mask: int):
+        self.mask = int(mask)
+
+    def __enter__(self):
+        lib = load()
+        self.old = int(lib.jxp_get_dev_options())
+        lib.jxp_set_dev_options(self.old | self.mask)
+        return self
+
+    def __exit__(self, *exc):
+        load().jxp_set_dev_options(self.old)
+        return False

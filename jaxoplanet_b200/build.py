@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libjxp_b200.so")
-SOURCES = ["jxp_kernels.cu", "jxp_partials.cu", "jxp_transit.cu"]
+SOURCES = ["jxp_kernels.cu", "jxp_partials.cu", "jxp_transit.cu", "jxp_walk.cu"]
 HEADERS = [
     os.path.join(CSRC, "jxp_scalar.cuh"),
     os.path.join(CSRC, "jxp_fastmath.cuh"),
@@ -24,6 +24,7 @@ HEADERS = [
     os.path.join(CSRC, "jxp_math.cuh"),
     os.path.join(CSRC, "jxp_orbit.cuh"),
     os.path.join(CSRC, "jxp_list.cuh"),
+    os.path.join(CSRC, "jxp_prep.cuh"),
     os.path.join(ROOT, "include", "jaxoplanet_b200.h"),
 ]
 

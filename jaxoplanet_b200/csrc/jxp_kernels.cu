@@ -9,12 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <type_traits>
 
 #include "jxp_host.h"
 #include "jxp_orbit.cuh"
 #include "jxp_list.cuh"
+#include "jxp_prep.cuh"
 
 using namespace jxp;
 using namespace jxph;
@@ -27,11 +29,16 @@ thread_local char g_err[512] = "";
 thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 }
 
-// development knob: JXP_PROFILE_KERNEL=prep|build|reduce moves the profile events of the
-// list path from its dominant kernel (k_tl_eval) to another one
-static bool ev_on(const char* which) {
-  const char* env = getenv("JXP_PROFILE_KERNEL");
-  return env ? strcmp(env, which) == 0 : strcmp(which, "eval") == 0;
+// development / measurement options (include/jaxoplanet_b200.h, JXP_DEV_*): one atomic word, read once
+// per call; the library never reads the environment
+static std::atomic<uint32_t> g_dev_options{0u};
+extern "C" int jxp_set_dev_options(uint32_t mask) {
+  g_dev_options.store(mask, std::memory_order_relaxed);
+  return JXP_OK;
+}
+extern "C" uint32_t jxp_get_dev_options(void) { return g_dev_options.load(std::memory_order_relaxed); }
+namespace jxph {
+uint32_t dev_options() { return g_dev_options.load(std::memory_order_relaxed); }
 }
 
 extern "C" int jxp_profile_events(void* start_event, void* stop_event) {
@@ -416,7 +423,7 @@ static int launch_limb_dark(const T* u, int32_t n_u, const T* b, int64_t bs, con
       // double: the mirror-pair node loop (ORDER tag 11), 2.9e10 vs 2.0e10 evaluations/s
       if (grad) {
         go(k_limb_dark<T, 11, true, false>);
-      } else if (n >= 8192 && getenv("JXP_NO_LD_CLASSES") == nullptr) {
+      } else if (n >= 8192 && !(dev_options() & JXP_DEV_NO_LD_CLASSES)) {
         if constexpr (sizeof(T) == 8) {
           const int64_t ctas = (n + 4 * LDC_SUB - 1) / (4 * LDC_SUB), capc = (int64_t)sm_count() * 4;
           k_limb_dark_cls<<<(unsigned)(ctas < capc ? ctas : capc), 128, 0, st>>>(a);
@@ -448,7 +455,7 @@ extern "C" int jxp_limb_dark_f32(const float* u, int32_t n_u, const float* b, in
 // K3/K4  fused system light curve (+ exposure integration, + Gaussian log-likelihood)
 // ======================================================================================
 namespace {
-constexpr int SYS_K = 4;          // time samples held in registers per thread
+constexpr int SYS_K = SYS_K_H;    // time samples held in registers per thread
 constexpr int SYS_MAX_SETS = 64;  // parameter sets per CTA (upper bound)
 }  // namespace
 
@@ -503,130 +510,7 @@ int make_stencil(double exposure_time, int order, int num_samples, Stencil& st) 
 }
 }  // namespace jxph
 
-namespace {
 
-// workspace carving shared by the size query and the launchers
-struct SysLayout {
-  size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, off_tilectr, total;
-  size_t off_tl_off, off_tl_cnt, off_tl_items;  // transit-list path (single-body systems)
-  unsigned long long tl_cap;                     // items the list can hold
-  int tile, n_tiles;
-};
-
-SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t body_sz, size_t set_sz,
-                     size_t elem_sz) {
-  SysLayout L;
-  L.tile = 32 * SYS_K;  // smallest tile any launch configuration uses (one warp per CTA)
-  L.n_tiles = (int)((n_times + L.tile - 1) / L.tile);
-  size_t off = 0;
-  L.off_bodies = off;
-  off = align_up(off + body_sz * (size_t)n_sets * n_bodies, 256);
-  L.off_sets = off;
-  off = align_up(off + set_sz * (size_t)n_sets, 256);
-  L.off_winv = off;
-  off = align_up(off + elem_sz * (size_t)n_times, 256);
-  L.off_scalars = off;
-  off = align_up(off + 256 * sizeof(double), 256);
-  L.off_partial = off;
-  off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles, 256);
-  L.off_tilectr = off;  // [0]: next unclaimed set group, [1 + g]: next warp tile of group g
-  off = align_up(off + sizeof(int) * ((size_t)n_sets + 1), 256);
-  // transit list: one 8-byte slot per in-window (set, sample); room for 1/8 of the grid (a list
-  // that would not fit makes the call fall back to the window-test kernels, on the device)
-  L.off_tl_off = L.off_tl_cnt = L.off_tl_items = off;
-  L.tl_cap = 0;
-  if (n_bodies == 1) {
-    L.off_tl_off = off;  // per set: first item on the inside list, on the edge list
-    off = align_up(off + 2 * sizeof(unsigned long long) * (size_t)n_sets, 256);
-    L.off_tl_cnt = off;  // per set: items on the inside list, on the edge list
-    off = align_up(off + 2 * sizeof(unsigned) * (size_t)n_sets, 256);
-    L.off_tl_items = off;
-    L.tl_cap = (unsigned long long)n_sets * (unsigned long long)n_times / 8ull + 65536ull;
-    if (L.tl_cap > (1ull << 28)) L.tl_cap = 1ull << 28;  // at most 2 GB of list; beyond it the call falls back
-    off = align_up(off + sizeof(unsigned long long) * (size_t)L.tl_cap, 256);
-  }
-  L.total = off;
-  return L;
-}
-}  // namespace
-
-// one thread per (set, body): derived constants -> BodyC (+ transit window), u -> SetC
-template <typename T>
-__device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ bodies, int n_sets, int n_bodies,
-                           const double* __restrict__ u, int n_u, int64_t u_stride,
-                           BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
-                           unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr,
-                           double widen, double margin) {
-  if (i >= n_sets * n_bodies) return;
-  if (i <= n_sets) tile_ctr[i] = 0;  // work distribution state of k_system (n_sets + 1 entries)
-  if (i == 0 && n_sets * n_bodies <= n_sets) tile_ctr[n_sets] = 0;
-  const double* p = bodies + (size_t)i * JXP_BODY_NFIELDS;
-  BodyC<T> c;
-  c.t0 = p[JXP_BODY_TIME_TRANSIT];
-  c.tref = p[JXP_BODY_TIME_REF];
-  c.period = p[JXP_BODY_PERIOD];
-  c.t0ref = c.t0 + c.tref;
-  c.inv_period = 1.0 / c.period;
-  double e = p[JXP_BODY_ECC];
-  c.flags = 0;
-  c.pad = 0;
-  if (e < 0.0) {
-    c.flags |= BODY_CIRCULAR;
-    e = 0.0;
-  }
-  const double a = p[JXP_BODY_SEMIMAJOR];
-  const double rstar = p[JXP_BODY_CENTRAL_RADIUS];
-  c.e = T(e);
-  c.ome = T(1.0 - e);
-  c.ope = T(1.0 + e);
-  c.s1me2 = T(sqrt((1.0 - e) * (1.0 + e)));
-  c.inv_ope = T(1.0 / (1.0 + e));
-  c.cw = T(p[JXP_BODY_COS_OMEGA]);
-  c.sw = T(p[JXP_BODY_SIN_OMEGA]);
-  c.ci = T(p[JXP_BODY_COS_INCL]);
-  c.si = T(p[JXP_BODY_SIN_INCL]);
-  c.na_ome2 = T(-a * (1.0 - e * e));
-  c.na = T(-a);
-  c.inv_rstar = T(1.0 / rstar);
-  const double rr = p[JXP_BODY_RADIUS] / rstar;
-  c.rr = T(rr);
-  c.onepr = T(1.0 + fabs(rr));
-  transit_window(c, a, rstar, e, widen, margin);
-  out_b[i] = c;
-  if (i == 0) {  // executed-work counters of this call (jxp_system_stats)
-    counters[0] = 0ull;
-    counters[1] = 0ull;
-    counters[2] = 0ull;  // transit list: items on the inside list
-    counters[3] = 0ull;  // transit list: TL_UNSORTED | TL_OVERFLOW (non-zero: list path off)
-    counters[4] = 0ull;  // transit list: items on the edge list
-    counters[5] = 0ull;  // transit list: chunks evaluated with the inside-the-disk flux code
-  }
-  if (i % n_bodies == 0) {
-    const int s = i / n_bodies;
-    const double* us = u + (size_t)s * u_stride;
-    double gg[JXP_MAX_LD_COEFFS + 1], uu[JXP_MAX_LD_COEFFS];
-    for (int k = 0; k <= JXP_MAX_LD_COEFFS; ++k) gg[k] = 0.0;
-    for (int k = 0; k < JXP_MAX_LD_COEFFS; ++k) uu[k] = (k < n_u) ? us[k] : 0.0;
-    if (n_u > 2)
-      ld_greens_n<double>(n_u, uu, gg);
-    else
-      ld_greens<double>(n_u, uu[0], uu[1], gg[0], gg[1], gg[2]);
-    SetC<T> sc;
-    sc.g0 = T(gg[0]);
-    sc.g1 = T(gg[1]);
-    sc.g2 = T(gg[2]);
-    for (int k = 0; k < 6; ++k) sc.ghi[k] = T(gg[3 + k]);
-    sc.lmax = n_u;
-    out_s[s] = sc;
-  }
-}
-
-// winv[t] = 1 / sigma[t]; per-CTA partial sums of ((y - 1) winv)^2 and of
-// (-log sigma - log(2 pi) / 2) into scalars[LL_SCAL0 + 2 cta .. ]; LL_NCTA CTAs over contiguous
-// chunks, fixed summation order (k_loglike_final / k_tr_final add the LL_NCTA pairs in order).
-constexpr int LL_NCTA = 64;
-constexpr int LL_SCAL0 = 8;
-constexpr int LL_FLAG0 = LL_SCAL0 + 2 * 64;  // per-CTA "time stamps not sorted" flags (list path)
 template <typename T>
 __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
@@ -635,53 +519,6 @@ __global__ void k_sys_prep(const double* __restrict__ bodies, int n_sets, int n_
                            double widen, double margin) {
   sys_prep_body<T>(blockIdx.x * blockDim.x + threadIdx.x, bodies, n_sets, n_bodies, u, n_u, u_stride, out_b,
                    out_s, counters, tile_ctr, widen, margin);
-}
-
-// CTA `cta` of `ncta` (256 threads); t != nullptr: also flag time stamps that are not sorted
-template <typename T>
-__device__ __forceinline__ void
-loglike_prep_body(int cta, int ncta, const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
-                  T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t) {
-  __shared__ double sh0[8], sh1[8];
-  double a0 = 0.0, a1 = 0.0;
-  int bad = 0;
-  const double half_log_2pi = 0.918938533204672741780329736405617639;
-  const int64_t chunk = (n + ncta - 1) / ncta;
-  const int64_t lo = (int64_t)cta * chunk;
-  const int64_t hi = lo + chunk < n ? lo + chunk : n;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const T sg = sigma[i * ss];
-    const T w = T(1) / sg;
-    winv[i] = w;
-    const double r0 = (double)((y[i] - T(1)) * w);
-    a0 += r0 * r0;
-    a1 -= log((double)sg) + half_log_2pi;
-    // the transit-list path needs non-decreasing, NaN-free time stamps
-    if (t != nullptr && i + 1 < n && !(t[i + 1] >= t[i])) bad = 1;
-  }
-  if (t != nullptr) {
-    bad = __syncthreads_or(bad);
-    if (threadIdx.x == 0) scalars[LL_FLAG0 + cta] = bad ? 1.0 : 0.0;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_down_sync(0xffffffffu, a0, o);
-    a1 += __shfl_down_sync(0xffffffffu, a1, o);
-  }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) {
-    sh0[w] = a0;
-    sh1[w] = a1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
-      t0 += sh0[k];
-      t1 += sh1[k];
-    }
-    scalars[LL_SCAL0 + 2 * cta] = t0;
-    scalars[LL_SCAL0 + 2 * cta + 1] = t1;
-  }
 }
 
 template <typename T>
@@ -1775,217 +1612,6 @@ __global__ void __launch_bounds__(128, JXP_PAIR_MINB) k_system_pair(const __grid
 }
 
 
-// --------------------------------------------------------------------------------------
-// Transit-list path -- the log-likelihood of single-planet systems without exposure integration
-// when the time stamps are sorted (the headline case, config 3).
-//
-// The window-test kernels above look at every (set, sample) pair to find the ~3 % that can be in
-// transit.  With sorted time stamps the in-window samples of a set are a few dozen contiguous index
-// ranges (one per transit), found by binary search.  HBM is idle in this path, so the ranges are
-// expanded into an explicit work list in the caller's workspace:
-//   k_tl_build   one warp per set: transits that intersect [t_first, t_last] -> index ranges ->
-//                count -> one atomicAdd per list allocates the set's slices -> items
-//                (set << 32 | sample) written coalesced.  Two lists share the buffer: samples
-//                estimated to have the planet fully inside the disk (BodyC::win_in) from the bottom,
-//                ingress / egress samples from the top.
-//   k_tl_eval    a flat, statically balanced map over the chunks of both lists, two items per lane
-//                through the same kepler_reduced_n<2> / ld_solution_n<2> code as k_system_pair:
-//                every lane of every warp does useful work, there is no queue, no window test and no
-//                reduction; the item's slot is overwritten with its chi^2 term.  Items of the inside
-//                list that really have b < 1 - r take ld_solution_inside_n<2> (constant node
-//                cosines, no atan2).
-//   k_tl_reduce  one warp per set adds the set's two slices in a fixed order (lane-strided sums,
-//                then a shuffle tree) -> loglike.  Which slice a set got depends on the atomics,
-//                the order of the terms inside it does not: bit-reproducible.
-// The decision is taken on the device (no synchronisation in the ABI): k_loglike_prep flags
-// unsorted / NaN time stamps, k_tl_build flags a list that does not fit the workspace; with a flag
-// set these kernels return at once and k_system_pair / k_loglike_final run, otherwise those two
-// return at once.  A sample outside the window costs nothing and one inside it is evaluated in
-// full (the reference's value, 0 when it is not in transit), so the list only has to be a
-// superset of the in-transit samples -- the same rigorous window as stage A/B.
-// --------------------------------------------------------------------------------------
-#ifndef JXP_TL_MINB
-#define JXP_TL_MINB 4
-#endif
-#ifndef JXP_TL_PU
-#define JXP_TL_PU 1
-#endif
-// FLUX: the per-item flux goes to flux / flux_sum (zeroed by the launcher) instead of a chi^2 term.
-template <int PU, bool FLUX = false>
-__global__ void __launch_bounds__(128, JXP_TL_MINB) k_tl_eval(const __grid_constant__ SysArgs<double> a) {
-  if (!tl_active(a.tl_state, a.tl_cap)) return;
-  const unsigned long long totA = a.tl_state[0], totB = a.tl_state[2];
-  const unsigned long long nA = (totA + 63ull) >> 6, nB = (totB + 63ull) >> 6;
-  const unsigned long long n_chunks = nA + nB;  // chunks of the inside list, then of the edge list
-  const int lane = threadIdx.x & 31;
-  const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-  unsigned long long ch = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  unsigned n_kep = 0, n_ld = 0, n_fast = 0;
-  if (ch >= n_chunks) return;
-  const BodyC<double>* __restrict__ bodies = a.bodies;
-  const SetC<double>* __restrict__ sets = a.sets;
-  const int lmax = sets[0].lmax;  // one law length per call
-  // physical index of the first item of chunk c and the number of valid items in it
-  auto chunk_base = [&](unsigned long long c, unsigned long long& base, unsigned& valid) {
-    if (c < nA) {
-      base = c * 64ull;
-      valid = (unsigned)(totA - base < 64ull ? totA - base : 64ull);
-    } else {
-      const unsigned long long p = (c - nA) * 64ull;
-      base = a.tl_cap - totB + p;
-      valid = (unsigned)(totB - p < 64ull ? totB - p : 64ull);
-    }
-  };
-  unsigned long long base, nbase = 0;
-  unsigned valid, nvalid = 0;
-  chunk_base(ch, base, valid);
-  unsigned long long nxt[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) nxt[h] = a.tl_items[base + ((unsigned)(32 * h + lane) < valid ? 32 * h + lane : 0)];
-  for (; ch < n_chunks; ch += nw) {
-    bool have[2], intr[2];
-    double Mr[2], e[2], ome[2], ope[2], s1[2], iope[2], sf[2], cf[2], bq[2], rq[2], tot[2];
-    unsigned slq[2], idxq[2];
-    bool circ = false;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      have[h] = (unsigned)(32 * h + lane) < valid;
-      slq[h] = (unsigned)(nxt[h] >> 32);
-      idxq[h] = (unsigned)nxt[h];
-    }
-    const bool more = ch + nw < n_chunks;
-    if (more) {  // next chunk's items in flight while this one is evaluated
-      chunk_base(ch + nw, nbase, nvalid);
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        nxt[h] = a.tl_items[nbase + ((unsigned)(32 * h + lane) < nvalid ? 32 * h + lane : 0)];
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const BodyC<double>& c = bodies[slq[h]];
-      Mr[h] = mean_anomaly_reduced(c, a.t[idxq[h]]);
-      e[h] = c.e;
-      ome[h] = c.ome;
-      ope[h] = c.ope;
-      s1[h] = c.s1me2;
-      iope[h] = c.inv_ope;
-      circ = circ || (c.flags & BODY_CIRCULAR);
-    }
-    kepler_reduced_n<2, true, true>(Mr, e, ome, ope, s1, iope, sf, cf);  // (sin f, cos f) D
-    if (__any_sync(0xffffffffu, circ)) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if (bodies[slq[h]].flags & BODY_CIRCULAR) jsincos(Mr[h], &sf[h], &cf[h]);  // keplerian.py:539-540
-    }
-    // Which flux code an item gets must not depend on its neighbours in the chunk (the slices of the
-    // list are handed out by atomics, so the neighbours change from run to run): an item takes the
-    // inside-the-disk code iff it is on the inside list AND itself has b < 1 - r.  A chunk whose items
-    // disagree (about 1 % of the inside list) runs both codes.
-    const bool on_inside_list = ch < nA;
-    bool fast[2], want_gen = false, want_fast = false;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const BodyC<double>& c = bodies[slq[h]];
-      double Z;
-      sky_position_xy(c, sf[h], cf[h], bq[h], Z);
-      rq[h] = c.rr;
-      intr[h] = have[h] && (Z > 0.0) && !(bq[h] >= c.onepr);
-      n_kep += have[h] ? 1u : 0u;
-      n_ld += intr[h] ? 1u : 0u;
-      const double ar = fabs(rq[h]);
-      fast[h] = on_inside_list && (bq[h] < 1.0 - ar) && (ar < 1.0);  // what ld_solution_inside_n needs
-      want_gen = want_gen || (intr[h] && !fast[h]);
-      want_fast = want_fast || (intr[h] && fast[h]);
-      tot[h] = 0.0;
-    }
-    want_gen = __any_sync(0xffffffffu, want_gen);
-    want_fast = __any_sync(0xffffffffu, want_fast);
-    n_fast += (want_fast && !want_gen) ? 1u : 0u;
-    if (want_gen) {
-      double s0[2], s1v[2], s2[2];
-      ld_solution_n<2, PU>(bq, rq, lmax, s0, s1v, s2);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const SetC<double>& sc = sets[slq[h]];
-        if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2);
-      }
-    }
-    if (want_fast) {
-      double s0[2], s1v[2], s2[2];
-      ld_solution_inside_n<2>(bq, rq, lmax, s0, s1v, s2);  // constant node cosines, no atan2
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const SetC<double>& sc = sets[slq[h]];
-        if (intr[h] && fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], sc.g0, sc.g1, sc.g2);
-      }
-    }
-    if (FLUX) {
-      // the rows were zeroed before the launch: only a non-zero flux needs a store (positions of
-      // different items are disjoint, so there is no ordering between them)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (have[h] && tot[h] != 0.0) {
-          const size_t o = (size_t)slq[h] * (size_t)a.n_times + idxq[h];
-          if (a.flux_sum) a.flux_sum[o] = tot[h];
-          if (a.flux) a.flux[o] = tot[h];
-        }
-      }
-    } else {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double dchi = 0.0;
-      if (have[h] && tot[h] != 0.0) {
-        const double w = a.winv[idxq[h]];
-        const double r0 = (a.y[idxq[h]] - 1.0) * w;
-        const double mw = tot[h] * w;
-        dchi = (-mw) * (2.0 * r0 - mw);
-      }
-      if (have[h]) reinterpret_cast<double*>(a.tl_items)[base + 32 * h + lane] = dchi;
-    }
-    }
-    base = nbase;
-    valid = nvalid;
-  }
-  n_kep = __reduce_add_sync(0xffffffffu, n_kep);
-  n_ld = __reduce_add_sync(0xffffffffu, n_ld);
-  if (lane == 0) {
-    atomicAdd(a.counters + 0, (unsigned long long)n_kep);
-    atomicAdd(a.counters + 1, (unsigned long long)n_ld);
-    atomicAdd(a.counters + 5, (unsigned long long)n_fast);
-  }
-}
-
-__global__ void __launch_bounds__(128) k_tl_reduce(const __grid_constant__ SysArgs<double> a) {
-  if (!tl_active(a.tl_state, a.tl_cap)) return;
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= a.n_sets) return;
-  const double* __restrict__ d = reinterpret_cast<const double*>(a.tl_items);
-  const unsigned cntA = a.tl_cnt[2 * s], cntB = a.tl_cnt[2 * s + 1];
-  double tot = tl_slice_sum(d + a.tl_off[2 * s], cntA, lane);
-  tot += tl_slice_sum(d + (a.tl_cap - a.tl_off[2 * s + 1] - cntB), cntB, lane);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  // set-independent terms: the LL_NCTA pairs of k_loglike_prep added in order (as k_loglike_final does)
-  static_assert(LL_NCTA == 64, "two pairs per lane");
-  const double2 pa = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[lane];
-  const double2 pb = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[32 + lane];
-  double chi0 = 0.0, cst = 0.0;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    chi0 += __shfl_sync(0xffffffffu, pa.x, k);
-    cst += __shfl_sync(0xffffffffu, pa.y, k);
-  }
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    chi0 += __shfl_sync(0xffffffffu, pb.x, k);
-    cst += __shfl_sync(0xffffffffu, pb.y, k);
-  }
-  if (lane == 0) {
-    a.loglike[s] = -0.5 * (chi0 + tot) + cst;
-  }
-}
-
 extern "C" size_t jxp_system_workspace_bytes(int32_t n_sets, int32_t n_bodies, int64_t n_times) {
   if (n_sets <= 0 || n_bodies <= 0 || n_times < 0) return 0;
   // sized for the wider (double) records so one query serves both precisions
@@ -2043,34 +1669,44 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   cudaStream_t st = (cudaStream_t)stream;
 
   const bool f32 = sizeof(T) == 4;
-  // transit-list path (see k_tl_build): eligibility is decided here, use on the device
+  // transit-walk path (jxp_walk.cu): eligibility is decided here, use on the device (sorted time stamps)
+  const uint32_t dev = dev_options();
+  const bool env_no_tl = (dev & JXP_DEV_NO_WALK) != 0, env_no_pair = (dev & JXP_DEV_NO_PAIR) != 0;
   const bool tl_ok = sizeof(T) == 8 && n_bodies == 1 && a.st.n == 1 && n_u <= 2 && gl_order == 10 &&
-                     !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL && L.tl_cap > 0 &&
-                     getenv("JXP_NO_TL") == nullptr;
-  const bool use_tl = tl_ok && loglike && !flux && !flux_sum && getenv("JXP_NO_PAIR") == nullptr;
+                     !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0x7ffffe00LL && !env_no_tl;
+  const bool use_tl = tl_ok && loglike && !flux && !flux_sum && !env_no_pair && n_times < (1LL << 25);
   // ... and of calls that want the flux itself (light_curve(orbit, u)(t) of a batch of single-planet systems)
-  // (from 2^20 points: below that the extra launches cost more than the list saves -- config 1, one set x
-  // 1e5 samples, takes 39 us with the window-test kernel and 47 us with the list)
-  int64_t flux_min_points = 1LL << 20;
-  if (const char* env = getenv("JXP_TL_FLUX_MIN_POINTS")) flux_min_points = atoll(env);  // development knob
+  // (from 2^20 points: below that the extra launch costs more than the walk saves -- config 1, one set x
+  // 1e5 samples, takes 39 us with the window-test kernel)
+  const int64_t flux_min_points = (dev & JXP_DEV_WALK_ANY_SIZE) ? 0 : (1LL << 20);
   const bool use_tl_flux = tl_ok && !loglike && (flux || flux_sum) && (int64_t)n_sets * n_times >= flux_min_points;
-  {
+  const double widen = f32 ? 1.0 + 2e-4 : 1.0 + 1e-9;
+  if (use_tl || use_tl_flux) {
+    if constexpr (sizeof(T) == 8) {
+      if (use_tl_flux) {
+        // zero rows by the copy engine's fill, the in-transit samples scattered over them by k_walk_eval;
+        // with unsorted time stamps (or a table that does not fit) k_system below rewrites every row
+        cudaError_t em = cudaSuccess;
+        if (flux_sum) em = cudaMemsetAsync(flux_sum, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
+        if (em == cudaSuccess && flux) em = cudaMemsetAsync(flux, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
+        if (em != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve: memset: %s", cudaGetErrorString(em));
+      }
+      rc = launch_walk_f64(bodies, n_sets, u, n_u, u_stride, t, n_times, flux, flux_sum, y, sigma, sigma_stride,
+                           loglike, ws, L, widen, 1e-7, st, g_ev_start, g_ev_stop, (dev & JXP_DEV_PROFILE_PLAN) ? 1 : 0);
+      if (rc != JXP_OK) return rc;
+    }
+  } else {
     const int n = n_sets * n_bodies;
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_scalars + 2);
     int* tile_ctr = reinterpret_cast<int*>(ws + L.off_tilectr);
-    const double widen = f32 ? 1.0 + 2e-4 : 1.0 + 1e-9;
     if (loglike) {
       const int n_prep = (n + 255) / 256;
-      if (g_ev_start && use_tl && ev_on("prep")) cudaEventRecord(g_ev_start, st);
       k_sys_prep_ll<T><<<n_prep + LL_NCTA, 256, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride, d_bodies,
                                                          d_sets, counters, tile_ctr, widen, 1e-7, n_prep, y,
-                                                         sigma, sigma_stride, n_times, d_winv, d_scalars,
-                                                         use_tl ? t : nullptr);
-      if (g_ev_stop && use_tl && ev_on("prep")) cudaEventRecord(g_ev_stop, st);
+                                                         sigma, sigma_stride, n_times, d_winv, d_scalars, nullptr);
     } else {
       k_sys_prep<T><<<(n + 127) / 128, 128, 0, st>>>(bodies, n_sets, n_bodies, u, n_u, u_stride, d_bodies,
                                                     d_sets, counters, tile_ctr, widen, 1e-7);
-      if (use_tl_flux) k_tl_sorted_check<<<LL_NCTA, 256, 0, st>>>(t, n_times, d_scalars);
     }
     rc = check_launch("jxp_system_light_curve(prep)");
     if (rc != JXP_OK) return rc;
@@ -2081,9 +1717,9 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // SM worth of (group, CTA tile) work (amortises the record staging)
   const int sms = sm_count();
   int threads = 128;
-  if (const char* env = getenv("JXP_SYS_THREADS")) {  // development knob
-    const int v = atoi(env);
-    if (v >= 32 && v <= 128 && v % 32 == 0) threads = v;
+  {  // development option: CTA size of the window-test kernels
+    const int v = 32 * (int)JXP_DEV_GET_CTA_WARPS(dev);
+    if (v >= 32 && v <= 128) threads = v;
   }
   const int64_t n_wtiles = (n_times + 32 * SYS_K - 1) / (32 * SYS_K);
   int64_t n_tiles = (n_wtiles + threads / 32 - 1) / (threads / 32);
@@ -2177,64 +1813,13 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   if constexpr (sizeof(T) == 8) {
     // log-likelihood of single-planet systems, no exposure integration: two samples per lane
     const bool pair = loglike && !flux && !flux_sum && n_bodies == 1 && a.st.n == 1 && n_u <= 2 &&
-                      gl_order == 10 && a.use_window && n_times < (1LL << 25) && spc <= 64 &&
-                      getenv("JXP_NO_PAIR") == nullptr;
-    // list + evaluation launches shared by the log-likelihood and the flux form of the list path
-    auto list_launch = [&](auto kern) -> int {
+                      gl_order == 10 && a.use_window && n_times < (1LL << 25) && spc <= 64 && !env_no_pair;
+    // the transit walk was launched in front (use_tl / use_tl_flux): the kernels below are then its
+    // on-device fallback -- they return at once unless k_walk_eval left a flag in counters[3]
+    // (unsorted / NaN time stamps, tables that do not fit)
+    if (use_tl || use_tl_flux) {
       a.tl_state = reinterpret_cast<unsigned long long*>(d_scalars + 4);
-      a.tl_items = reinterpret_cast<unsigned long long*>(ws + L.off_tl_items);
-      a.tl_off = reinterpret_cast<unsigned long long*>(ws + L.off_tl_off);
-      a.tl_cnt = reinterpret_cast<unsigned*>(ws + L.off_tl_cnt);
-      a.tl_cap = L.tl_cap;
-      a.loglike = reinterpret_cast<double*>(loglike);
-      TlBuildArgs ba;
-      ba.bodies = reinterpret_cast<const unsigned char*>(d_bodies);
-      ba.body_stride = sizeof(BodyC<T>);
-      ba.n_sets = n_sets;
-      ba.t = t;
-      ba.n_times = n_times;
-      ba.sorted_flags = d_scalars + LL_FLAG0;
-      ba.tl_state = a.tl_state;
-      ba.tl_items = a.tl_items;
-      ba.tl_off = a.tl_off;
-      ba.tl_cnt = a.tl_cnt;
-      ba.tl_cap = a.tl_cap;
-      if (g_ev_start && ev_on("build")) cudaEventRecord(g_ev_start, st);
-      k_tl_build<0><<<(n_sets + 3) / 4, 128, 0, st>>>(ba);
-      if (g_ev_stop && ev_on("build")) cudaEventRecord(g_ev_stop, st);
-      int rcl = check_launch("jxp_system_light_curve(transit list)");
-      if (rcl != JXP_OK) return rcl;
-      int per_sm = 0;
-      cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
-      if (eo != cudaSuccess || per_sm < 1)
-        return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
-      // the list length is only known on the device: a resident grid, chunks strided over it
-      const int64_t max_chunks = (int64_t)((L.tl_cap + 63ull) / 64ull) + 1;
-      const int64_t want = (max_chunks + 3) / 4;
-      const int64_t resident = (int64_t)per_sm * sms;
-      if (g_ev_start && ev_on("eval")) cudaEventRecord(g_ev_start, st);
-      kern<<<(unsigned)(want < resident ? want : resident), 128, 0, st>>>(a);
-      if (g_ev_stop && ev_on("eval")) cudaEventRecord(g_ev_stop, st);
-      return check_launch("jxp_system_light_curve(transit list eval)");
-    };
-    if (use_tl_flux) {
-      // zero rows by the copy engine's fill, the in-transit samples scattered over them by k_tl_eval;
-      // with unsorted time stamps (or a list that does not fit) k_system below rewrites every row
-      cudaError_t em = cudaSuccess;
-      if (flux_sum) em = cudaMemsetAsync(flux_sum, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
-      if (em == cudaSuccess && flux) em = cudaMemsetAsync(flux, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
-      if (em != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve: memset: %s", cudaGetErrorString(em));
-      rc = list_launch(k_tl_eval<JXP_TL_PU, true>);
-      if (rc != JXP_OK) return rc;
-    }
-    if (pair && use_tl) {
-      rc = list_launch(k_tl_eval<JXP_TL_PU, false>);
-      if (rc != JXP_OK) return rc;
-      if (g_ev_start && ev_on("reduce")) cudaEventRecord(g_ev_start, st);
-      k_tl_reduce<<<(n_sets + 3) / 4, 128, 0, st>>>(a);
-      if (g_ev_stop && ev_on("reduce")) cudaEventRecord(g_ev_stop, st);
-      rc = check_launch("jxp_system_light_curve(transit list reduce)");
-      if (rc != JXP_OK) return rc;
+      a.tl_cap = ~0ull;
     }
     if (pair) {
       const size_t smem2 = sizeof(BodyC<T>) * (size_t)spc + sizeof(SetC<T>) * (size_t)spc +
@@ -2250,7 +1835,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
         return fail(JXP_ERR_CUDA, "jxp_system_light_curve: occupancy query: %s", cudaGetErrorString(eo));
       const int64_t resident = (int64_t)per_sm * sms;
       const unsigned n_ctas = (unsigned)(n_units < resident ? n_units : resident);
-      // with the list path in front this launch is the fallback: the events stay on k_tl_eval
+      // with the transit walk in front this launch is the fallback: the events stay on k_walk_eval
       if (g_ev_start && !a.tl_state) cudaEventRecord(g_ev_start, st);
       kern<<<n_ctas, threads, smem2, st>>>(a);
       if (g_ev_stop && !a.tl_state) cudaEventRecord(g_ev_stop, st);
@@ -2314,14 +1899,17 @@ extern "C" int jxp_system_list_stats(const void* workspace, int32_t n_sets, int3
                                  sizeof(SetC<double>), sizeof(double));
   const unsigned char* ws = static_cast<const unsigned char*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t raw[4] = {0, 0, 0, 0};  // inside-list items, flags, edge-list items, fast chunks
+  // counters[2..5]: samples on the inside lists, flags, samples on the edge lists, samples on the constant-kappa code
+  int64_t raw[4] = {0, 0, 0, 0};
   cudaError_t e = cudaMemcpyAsync(raw, ws + L.off_scalars + 4 * sizeof(double), 4 * sizeof(int64_t),
                                   cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  stats_host[0] = raw[0] + raw[2];
-  stats_host[1] = raw[1] | ((unsigned long long)(raw[0] + raw[2]) > L.tl_cap ? 2 : 0);
-  stats_host[2] = raw[0];
-  stats_host[3] = raw[3];
+  if (e == cudaSuccess) {
+    stats_host[0] = raw[0] + raw[2];
+    stats_host[1] = raw[1];
+    stats_host[2] = raw[0];
+    stats_host[3] = raw[3];
+  }
   if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_list_stats: %s", cudaGetErrorString(e));
   return JXP_OK;
 }

@@ -760,7 +760,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   unsigned long long* tl_state = reinterpret_cast<unsigned long long*>(d_scalars + 4);
   // transit-list path (see k_tlg_eval): eligibility is decided here, use on the device
   const bool use_tl = sizeof(T) == 8 && want_ll && !flux && !partials && a.st.n == 1 && gl_order == 10 &&
-                      !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL && getenv("JXP_NO_TL") == nullptr;
+                      !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0xfffffe00LL && !(dev_options() & JXP_DEV_NO_WALK);
   k_tr_prep<T><<<(n_sets + 127) / 128, 128, 0, st>>>(theta, n_sets, star, star_stride, d_bodies,
                                                     f32 ? 1.0 + 2e-4 : 1.0 + 1e-9, 1e-7, tl_state);
   rc = check_launch("jxp_transit_partials(prep)");
@@ -778,8 +778,8 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   // measured on config 5 (run = 1 / 4 / 16): the arithmetic alone 6.8 / 5.4 / 4.9 ms, the row stores alone
   // 8.7 / 9.9 / 10.8 ms -- long runs keep the drains full, short ones keep the store stream smooth
   int run = (flux || partials) ? 1 : 16;
-  if (const char* env = getenv("JXP_TR_RUN")) {  // development knob
-    const int v = atoi(env);
+  {  // development option: warp tiles per run
+    const int v = (int)JXP_DEV_GET_TR_RUN(dev_options());
     if (v >= 1 && v <= 64) run = v;
   }
   auto n_wruns_of = [&](int r) { return (n_wtiles + r - 1) / r; };

@@ -57,11 +57,14 @@ def test_argument_validation_messages(lib):
     assert rc == -3 and b"must be 0, 1, or 2" in lib.jxp_last_error()
     assert lib.jxp_system_workspace_bytes(4096, 1, 100000) > 4096 * 100
     assert lib.jxp_system_workspace_bytes(0, 1, 10) == 0
-    # single-body systems: room for the transit list (8 B per item, 1/8 of the grid + 65536 items);
-    # multi-body systems do not carry it
+    # the transit walk keeps nothing per sample: records, segments and one 24-byte slot per chunk of 32
+    # in-window samples for 1/8 of the grid -- well under one byte per (set, sample)
     one = lib.jxp_system_workspace_bytes(4096, 1, 100000)
-    three = lib.jxp_system_workspace_bytes(4096, 3, 100000)
-    assert one >= 8 * (4096 * 100000 // 8 + 65536) and three < one // 4
+    assert 24 * (4096 * 100000 // 256) <= one < 4096 * 100000 // 4
+    # development options: one process-wide word, default 0
+    assert lib.jxp_get_dev_options() == 0
+    assert lib.jxp_set_dev_options(5) == 0 and lib.jxp_get_dev_options() == 5
+    assert lib.jxp_set_dev_options(0) == 0
     # gradient step: 80 B per item, 1/16 of the grid + 65536 items
     assert lib.jxp_transit_workspace_bytes(16384, 50000) >= 80 * (16384 * 50000 // 16 + 65536)
     # the list statistics helpers reject null pointers before touching the device

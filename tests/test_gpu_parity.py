@@ -302,11 +302,8 @@ def test_system_window_flag_is_bit_identical():
     sys_ = _c1_system()
     # the window-test kernel against the dense one: bit for bit (sorted time stamps of a single-planet
     # system would otherwise take the transit-list kernels, a different program: tests/test_transit_list.py)
-    os.environ["JXP_NO_TL"] = "1"
-    try:
+    with _lib.dev_options(_lib.JXP_DEV_NO_WALK):
         a = _run_fused(FusedSpec(sys_, u), t)
-    finally:
-        os.environ.pop("JXP_NO_TL", None)
     b = _run_fused(FusedSpec(sys_, u, flags=_lib.JXP_FLAG_NO_WINDOW), t)
     assert torch.equal(a, b)
     c = _run_fused(FusedSpec(sys_, u), t)  # transit list
@@ -332,23 +329,21 @@ def test_loglike_is_bit_reproducible_under_dynamic_scheduling():
     base = f(td, yd, sigma).clone()
     for _ in range(4):
         assert torch.equal(f(td, yd, sigma), base)
-    old = os.environ.get("JXP_SYS_THREADS")
-    try:
-        os.environ["JXP_SYS_THREADS"] = "64"
-        assert torch.equal(f(td, yd, sigma), base)
-        os.environ["JXP_SYS_THREADS"] = "32"
-        assert torch.equal(f(td, yd, sigma), base)
-    finally:
-        if old is None:
-            os.environ.pop("JXP_SYS_THREADS", None)
-        else:
-            os.environ["JXP_SYS_THREADS"] = old
-    try:
-        os.environ["JXP_NO_PAIR"] = "1"
+    from jaxoplanet_b200 import _lib
+
+    # the window-test kernels (what unsorted time stamps get): dynamic tile -> warp assignment
+    with _lib.dev_options(_lib.JXP_DEV_NO_WALK):
+        wbase = f(td, yd, sigma).clone()
+        for _ in range(3):
+            assert torch.equal(f(td, yd, sigma), wbase)
+        with _lib.dev_options(_lib.JXP_DEV_CTA_WARPS(2)):
+            assert torch.equal(f(td, yd, sigma), wbase)
+        with _lib.dev_options(_lib.JXP_DEV_CTA_WARPS(1)):
+            assert torch.equal(f(td, yd, sigma), wbase)
+    assert torch.max(torch.abs(wbase - base) / torch.abs(base)).item() <= 2e-12
+    with _lib.dev_options(_lib.JXP_DEV_NO_PAIR):
         single = f(td, yd, sigma).clone()
         assert torch.equal(f(td, yd, sigma), single)
-    finally:
-        os.environ.pop("JXP_NO_PAIR", None)
     # different rounding of the flux (1e-16) times 1 / sigma^2 = 4e6 per term
     assert torch.max(torch.abs(single - base) / torch.abs(base)).item() <= 2e-12
 
@@ -712,12 +707,11 @@ def test_transit_partials_runs_with_carried_queue_match_single_tiles():
     t = torch.as_tensor(np.arange(30_000) * W.TWO_MIN).cuda()
     y = 1.0 + transit_partials(theta[5:6], t, want_partials=False)["flux"][0] + 1e-4 * torch.sin(t)
     out = {}
-    try:
-        for run in ("1", "4", "16"):
-            os.environ["JXP_TR_RUN"] = run
+    from jaxoplanet_b200 import _lib
+
+    for run in ("1", "4", "16"):  # the window-test kernel (sorted time stamps would otherwise take the list path)
+        with _lib.dev_options(_lib.JXP_DEV_NO_WALK | _lib.JXP_DEV_TR_RUN(int(run))):
             out[run] = transit_partials(theta, t, y=y, sigma=5e-4, want_flux=False, want_partials=False)
-    finally:
-        os.environ.pop("JXP_TR_RUN", None)
     scale = torch.abs(out["1"]["dloglike"]).amax(dim=0, keepdim=True)
     for run in ("4", "16"):
         assert float(torch.max(torch.abs(out[run]["loglike"] - out["1"]["loglike"]) / torch.abs(out["1"]["loglike"]))) <= 1e-13

@@ -15,8 +15,7 @@ call = lambda: _lib.call("jxp_transit_partials_f64", thd.data_ptr(), ns, star.da
                          None, None, y.data_ptr(), sd.data_ptr(), 0, ll.data_ptr(), dll.data_ptr(), ws.data_ptr(), wsb, A.stream_ptr())
 res = {}
 for label in ("list", "window"):
-    if label == "window": os.environ["JXP_NO_TL"] = "1"
-    else: os.environ.pop("JXP_NO_TL", None)
+    lib.jxp_set_dev_options(_lib.JXP_DEV_NO_WALK if label == "window" else 0)
     for _ in range(2): call()
     torch.cuda.synchronize(); best = 1e9
     for _ in range(5):

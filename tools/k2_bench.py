@@ -12,7 +12,7 @@ out = torch.empty(n, dtype=torch.float64, device=dev)
 f = lambda: _lib.call("jxp_limb_dark_f64", u.data_ptr(), 2, bb.data_ptr(), 1, rr.data_ptr(), 1, n, 10, out.data_ptr(), None, None, None, A.stream_ptr())
 res = {}
 for label in ("classes", "plain"):
-    if label == "plain": os.environ["JXP_NO_LD_CLASSES"] = "1"
+    _lib.load().jxp_set_dev_options(_lib.JXP_DEV_NO_LD_CLASSES if label == "plain" else 0)
     for _ in range(2): f()
     torch.cuda.synchronize(); best = 1e9
     for _ in range(5):

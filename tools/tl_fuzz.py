@@ -12,11 +12,13 @@ from jaxoplanet_b200.light_curves.partials import transit_partials
 
 n_trials = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-os.environ["JXP_TL_FLUX_MIN_POINTS"] = "0"
+from jaxoplanet_b200 import _lib
+_lib.load().jxp_set_dev_options(_lib.JXP_DEV_WALK_ANY_SIZE)
 worst = dict(ll=0.0, flux=0.0, grad=0.0)
 def both(fn):
-    os.environ.pop("JXP_NO_TL", None); a = fn()
-    os.environ["JXP_NO_TL"] = "1"; b = fn(); os.environ.pop("JXP_NO_TL", None)
+    a = fn()
+    with _lib.dev_options(_lib.JXP_DEV_NO_WALK):
+        b = fn()
     return a, b
 for trial in range(n_trials):
     n_sets = int(rng.integers(1, 40)); n_t = int(rng.integers(1, 4000))
