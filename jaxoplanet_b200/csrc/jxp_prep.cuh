@@ -15,7 +15,7 @@ constexpr int LL_FLAG0 = jxph::LL_FLAG0_H;  // per-CTA "time stamps not sorted" 
 
 // one thread per (set, body): derived constants -> BodyC (+ transit window), u -> SetC
 template <typename T>
-__device__ __forceinline__ void sys_prep_body(int i, const double* __restrict__ bodies, int n_sets, int n_bodies,
+__device__ __noinline__ void sys_prep_body(int i, const double* __restrict__ bodies, int n_sets, int n_bodies,
                            const double* __restrict__ u, int n_u, int64_t u_stride,
                            BodyC<T>* __restrict__ out_b, SetC<T>* __restrict__ out_s,
                            unsigned long long* __restrict__ counters, int* __restrict__ tile_ctr,

@@ -40,10 +40,13 @@ namespace jxp {
 
 // fields of the 32-double set record
 enum : int {
-  WK_T0 = 0, WK_TREF, WK_PERIOD, WK_INVP, WK_E, WK_OME, WK_OPE, WK_S1ME2, WK_INVOPE,
-  WK_CW, WK_SW, WK_K1, WK_K2, WK_ZS, WK_RR, WK_ONEPR, WK_G0, WK_G1, WK_G2, WK_FLAGS,
+  WK_T0 = 0, WK_TREF, WK_PERIOD, WK_INVP, WK_E, WK_OME, WK_OPE, WK_S1ME2, WK_CW, WK_SW, WK_K1, WK_K2,
+  WK_ZS, WK_ONEPR, WK_G0, WK_G1, WK_G2, WK_RR, WK_INVOPE, WK_FLAGS,
   WK_NFIELDS
 };
+static_assert(WK_T0 % 2 == 0 && WK_PERIOD % 2 == 0 && WK_E % 2 == 0 && WK_OPE % 2 == 0 && WK_CW % 2 == 0 &&
+                  WK_K1 % 2 == 0 && WK_ZS % 2 == 0 && WK_G0 % 2 == 0,
+              "pairs read as double2");
 static_assert(WK_NFIELDS <= WALK_REC, "record size");
 constexpr unsigned WKF_CIRCULAR = 1u, WKF_SLOW_STARTER = 2u;
 
@@ -82,7 +85,9 @@ struct WalkArgs {
   uint4* chunk;           // chunk entries: inside list from 0 up, edge list from cap down
   double* part;           // per-chunk partial sums (same slots)
   unsigned long long* state;  // [0] segments allocated, [1] inside chunks, [2] edge chunks, [3] flags,
-                              // [4] positions on the inside lists, [5] on the edge lists (zeroed per call)
+                              // [4] positions on the inside lists, [5] on the edge lists, [6], [7] claim counters of
+                              // k_walk_eval, [8] likelihood-prep CTAs done (all zeroed per call); scalars
+                              // [WALK_STATE0 + 10], [+ 11]: the set-independent likelihood terms
   unsigned long long cap_seg, cap_chunk;
   int n_plan_ctas;
   double widen, margin;
@@ -103,6 +108,20 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     const int cta = (int)blockIdx.x - a.n_plan_ctas;
     if (LL) {
       loglike_prep_body<double>(cta, LL_NCTA, a.y, a.sigma, a.sigma_stride, a.n_times, a.winv, a.scalars, a.t);
+      // the last of these CTAs to finish adds the LL_NCTA pairs in order: the set-independent terms
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.state + 8, 1ull) == (unsigned long long)(LL_NCTA - 1)) {
+          __threadfence();
+          double chi0 = 0.0, cst = 0.0;
+          for (int k = 0; k < LL_NCTA; ++k) {
+            chi0 += __ldcg(a.scalars + LL_SCAL0 + 2 * k);
+            cst += __ldcg(a.scalars + LL_SCAL0 + 2 * k + 1);
+          }
+          a.scalars[WALK_STATE0 + 10] = chi0;
+          a.scalars[WALK_STATE0 + 11] = cst;
+        }
+      }
     } else {
       int bad = 0;
       const int64_t n = a.n_times;
@@ -179,6 +198,37 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     }
   }
   const double w_in = all ? 0.0 : c.win_in;
+  // First index i in [0, n] with !(t[i] < x) (lower bound) or !(t[i] <= x) (UPPER) on sorted t: the four
+  // samples around the uniform-grid estimate are loaded at once and decide it when the boundary lies among
+  // them (one round trip on a regular cadence); anything else goes to the bracketing search of jxp_list.cuh.
+  auto search4 = [&](double x0, double x1, double x2, double x3, unsigned (&r)[4]) {
+    const double xs[4] = {x0, x1, x2, x3};
+    unsigned base[4];
+    double v[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double gd = (xs[q] - t_first) * inv_dt;
+      gd = fmin(fmax(gd, 0.0), (double)n);
+      const unsigned g = (unsigned)gd;
+      base[q] = n <= 4u ? 0u : (g < 2u ? 0u : (g - 2u > n - 4u ? n - 4u : g - 2u));
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v[q][m] = a.t[base[q] + ((unsigned)m < n ? (unsigned)m : n - 1u)];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool upper = (q & 1) != 0;  // x0, x2: lower bounds; x1, x3: upper bounds
+      const unsigned span = n < 4u ? n : 4u;
+      unsigned cnt = 0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if ((unsigned)m < span) cnt += (upper ? (v[q][m] <= xs[q]) : (v[q][m] < xs[q])) ? 1u : 0u;
+      const bool decided = (cnt > 0u || base[q] == 0u) && (cnt < span || base[q] + span == n);
+      if (decided)
+        r[q] = base[q] + cnt;
+      else
+        r[q] = upper ? tl_search<true>(a.t, n, xs[q], t_first, inv_dt) : tl_search<false>(a.t, n, xs[q], t_first, inv_dt);
+    }
+  };
   auto interval = [&](long long k, unsigned& lo, unsigned& hi, unsigned& ilo, unsigned& ihi) {
     lo = hi = ilo = ihi = 0;
     if (k >= n_tr) return;
@@ -188,14 +238,16 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     }
     const double base = phc + (k_first + (double)k);
     const double ta = fma(base + wlo, P, t0ref), tb = fma(base + whi, P, t0ref);
-    lo = tl_search<false>(a.t, n, fmin(ta, tb), t_first, inv_dt);
-    hi = tl_search<true>(a.t, n, fmax(ta, tb), t_first, inv_dt);
+    const bool want_in = w_in > 0.0;
+    const double tc = fma(base - w_in, P, t0ref), td = fma(base + w_in, P, t0ref);
+    unsigned r[4];
+    search4(fmin(ta, tb), fmax(ta, tb), fmin(tc, td), fmax(tc, td), r);
+    lo = r[0];
+    hi = r[1];
     if (hi < lo) hi = lo;  // unsorted time stamps: anything in range will do, the call falls back
     ilo = ihi = lo;
-    if (w_in > 0.0 && hi - lo >= 8u) {
-      const double tc = fma(base - w_in, P, t0ref), td = fma(base + w_in, P, t0ref);
-      unsigned i0 = tl_search<false>(a.t, n, fmin(tc, td), t_first, inv_dt);
-      unsigned i1 = tl_search<true>(a.t, n, fmax(tc, td), t_first, inv_dt);
+    if (want_in && hi - lo >= 8u) {
+      unsigned i0 = r[2], i1 = r[3];
       i0 = i0 < lo ? lo : (i0 > hi ? hi : i0);
       i1 = i1 < i0 ? i0 : (i1 > hi ? hi : i1);
       if (i1 - i0 >= 8u) {
@@ -205,7 +257,8 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     }
   };
 
-  // segments: inside list [seg0, seg0 + n_tr] (sentinel last), edge list [seg0 + n_tr + 1, seg0 + 3 n_tr + 1]
+  // segments (non-empty runs only): inside list at [seg0, seg0 + nsA] (sentinel last), edge list at
+  // [seg0 + n_tr + 1, seg0 + n_tr + 1 + nsB]; room is taken for the most there can be
   const unsigned long long n_seg = 3ull * (unsigned long long)n_tr + 2ull;
   unsigned long long seg0 = 0;
   if (lane == 0) seg0 = atomicAdd(a.state, n_seg);
@@ -223,29 +276,38 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
   }
   unsigned long long* segA = a.seg + seg0;
   unsigned long long* segB = segA + n_tr + 1;
-  unsigned long long cumA = 0, cumB = 0;  // running totals (64-bit: a list may exceed 2^32 only in theory)
+  // running totals, packed (positions << 8 | segments of this block): a list may exceed 2^32 only in theory
+  unsigned long long cumA = 0, cumB = 0;
+  unsigned nsA = 0, nsB = 0;
   for (long long k0 = 0; k0 < n_tr; k0 += 32) {
     unsigned lo, hi, il, ih;
     interval(k0 + lane, lo, hi, il, ih);
     const unsigned cA = ih - il, cB0 = il - lo, cB1 = hi - ih;
-    unsigned inA = cA, inB = cB0 + cB1;
+    const unsigned long long mineA = ((unsigned long long)cA << 8) | (cA ? 1u : 0u);
+    const unsigned long long mineB = ((unsigned long long)(cB0 + cB1) << 8) | ((cB0 ? 1u : 0u) + (cB1 ? 1u : 0u));
+    unsigned long long inA = mineA, inB = mineB;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned vA = __shfl_up_sync(0xffffffffu, inA, o);
-      const unsigned vB = __shfl_up_sync(0xffffffffu, inB, o);
+      const unsigned long long vA = __shfl_up_sync(0xffffffffu, inA, o);
+      const unsigned long long vB = __shfl_up_sync(0xffffffffu, inB, o);
       if (lane >= o) {
         inA += vA;
         inB += vB;
       }
     }
-    if (k0 + lane < n_tr) {
-      const unsigned eA = (unsigned)cumA + (inA - cA), eB = (unsigned)cumB + (inB - cB0 - cB1);
-      segA[k0 + lane] = (unsigned long long)eA | ((unsigned long long)il << 32);
-      segB[2 * (k0 + lane)] = (unsigned long long)eB | ((unsigned long long)lo << 32);
-      segB[2 * (k0 + lane) + 1] = (unsigned long long)(eB + cB0) | ((unsigned long long)ih << 32);
+    {
+      const unsigned long long exA = inA - mineA, exB = inB - mineB;
+      const unsigned eA = (unsigned)(cumA + (exA >> 8)), eB = (unsigned)(cumB + (exB >> 8));
+      unsigned jA = nsA + (unsigned)(exA & 255u), jB = nsB + (unsigned)(exB & 255u);
+      if (cA) segA[jA] = (unsigned long long)eA | ((unsigned long long)il << 32);
+      if (cB0) segB[jB++] = (unsigned long long)eB | ((unsigned long long)lo << 32);
+      if (cB1) segB[jB] = (unsigned long long)(eB + cB0) | ((unsigned long long)ih << 32);
     }
-    cumA += __shfl_sync(0xffffffffu, inA, 31);
-    cumB += __shfl_sync(0xffffffffu, inB, 31);
+    const unsigned long long tA = __shfl_sync(0xffffffffu, inA, 31), tB = __shfl_sync(0xffffffffu, inB, 31);
+    cumA += tA >> 8;
+    cumB += tB >> 8;
+    nsA += (unsigned)(tA & 255u);
+    nsB += (unsigned)(tB & 255u);
   }
   if (cumA > 0xfffffff0ull || cumB > 0xfffffff0ull) {  // positions are 32-bit
     if (lane == 0) {
@@ -255,8 +317,8 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     return;
   }
   if (lane == 0) {
-    segA[n_tr] = cumA;  // sentinels: first position past the list
-    segB[2 * n_tr] = cumB;
+    segA[nsA] = cumA;  // sentinels: first position past the list
+    segB[nsB] = cumB;
   }
   unsigned nchA = (unsigned)((cumA + CH - 1) / CH), nchB = (unsigned)((cumB + CH - 1) / CH);
   // a set without any in-window sample still needs one (empty) chunk: the warp that finishes a set's
@@ -300,7 +362,7 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
 #pragma unroll 1
   for (int list = 0; list < 2; ++list) {
     const unsigned long long* sg = list ? segB : segA;
-    const unsigned nsg = list ? 2u * (unsigned)n_tr : (unsigned)n_tr;
+    const unsigned nsg = list ? nsB : nsA;
     const unsigned cnt = list ? (unsigned)cumB : (unsigned)cumA;
     uint4* ent = list ? entB : entA;
     const unsigned segbase = (unsigned)(sg - a.seg);
@@ -416,6 +478,7 @@ struct WalkEvalArgs {
   const uint4* chunk;
   double* part;
   const unsigned long long* state;
+  unsigned long long* state_rw;  // [6], [7]: claim counters of the inside / edge list (zeroed per call)
   unsigned long long cap_chunk;
   const double* scalars;
   const double* t;
@@ -440,162 +503,426 @@ __device__ __forceinline__ bool walk_eval_active(const WalkEvalArgs& a, int lane
     a.counters[2] = a.state[4];  // in-window samples on the inside / edge lists (jxp_system_list_stats)
     a.counters[4] = a.state[5];
     a.counters[3] = (unsorted ? 1ull : 0ull) | (over ? 2ull : 0ull);
+    if (!unsorted && !over) a.counters[0] = a.state[4] + a.state[5];  // Kepler solves = samples visited
   }
   return !unsorted && !over;
 }
 
+// positions p0 + 32 h + lane of a chunk -> sample indices, from the chunk's segment window `win` (shared
+// memory; entry j = segment segk + j: first position | first sample << 32, first positions strictly
+// increasing, the list's sentinel = first position past the list).  Every segment that starts inside the
+// chunk sets one bit of a position mask (warp-wide OR); a position's segment is the number of such starts
+// at or below it.
+template <int N>
+__device__ __forceinline__ void walk_indices(const WalkEvalArgs& a, const uint4& ent,
+                                             const unsigned long long* __restrict__ win, int lane,
+                                             unsigned (&idx)[N], bool (&have)[N]) {
+  const unsigned p0 = ent.y, segk = ent.z;
+  const unsigned valid = (ent.w >> 8) & 0xffffu, nrem = ent.w & 255u;
+  const unsigned off = (lane >= 1 && lane < (int)nrem) ? (unsigned)win[lane] - p0 : 0xffffffffu;  // >= 1 for real ones
+  unsigned mask[N];
+#pragma unroll
+  for (int h = 0; h < N; ++h)
+    mask[h] = __reduce_or_sync(0xffffffffu, (off >> 5) == (unsigned)h ? (1u << (off & 31u)) : 0u);
+  unsigned below = 0;
+#pragma unroll
+  for (int h = 0; h < N; ++h) {
+    const unsigned p = p0 + 32u * h + lane;
+    have[h] = 32u * h + lane < valid;
+    const unsigned j = below + __popc(mask[h] & (0xffffffffu >> (31 - lane)));
+    below += __popc(mask[h]);
+    unsigned long long sv = win[j < 31u ? j : 31u];
+    if (j >= 31u && nrem > 32u && have[h]) {
+      // more than 31 segments start inside one chunk (runs of one or two samples): walk the table itself;
+      // the list's sentinel (> p for a valid position) ends the search
+      unsigned k = segk + 31u;
+      while ((unsigned)a.seg[k + 1u] <= p) ++k;
+      sv = a.seg[k];
+    }
+    idx[h] = have[h] ? (unsigned)(sv >> 32) + (p - (unsigned)sv) : 0u;
+  }
+}
+
+// The set's partial sums added in a fixed order by ONE lane -> loglike[set] (eight interleaved sums over the
+// inside-list chunks then the edge-list chunks, combined pairwise: the order depends on the set alone, so
+// which warp or lane does it changes nothing).
+template <int CH>
+__device__ __forceinline__ void walk_finish_set(const WalkEvalArgs& a, unsigned set) {
+  __threadfence();
+  const WalkSet wsv = a.wset[set];
+  const unsigned nchB = (wsv.cntB + CH - 1) / CH;
+  const unsigned nchA = wsv.n_chunks - nchB;
+  const double* pA = a.part + wsv.chA;
+  const double* pB = a.part + ((unsigned)a.cap_chunk - wsv.chB - nchB);
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  for (unsigned i = 0; i < nchA; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = i + m < nchA ? __ldcg(pA + i + m) : 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] += v[m];
+  }
+  for (unsigned i = 0; i < nchB; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = i + m < nchB ? __ldcg(pB + i + m) : 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] += v[m];
+  }
+  const double tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  a.loglike[set] = -0.5 * (a.scalars[WALK_STATE0 + 10] + tot) + a.scalars[WALK_STATE0 + 11];
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS): staged inputs cost no registers while they fly
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(__cvta_generic_to_global(gmem))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(__cvta_generic_to_global(gmem))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Flux of core/limb_dark.py:19-84 for N points of ONE set (radius ratio r warp-uniform) with the planet
+// fully inside the disk: kappa0 = pi, kappa1 = 0 and kite_area = 0 exactly, constant node cosines (see
+// ld_solution_inside_n, jxp_math.cuh -- same formulas and summation order).  The caller guarantees
+// 2e-6 <= r < 1 and b < 1 - r - 4e-15; then every node's 1 - z^2 = r^2 + b^2 - 2 b r c lies in
+// [1.68e-3 r^2, (b + r)^2] (|c| <= 0.99916), i.e. strictly inside [10 eps, 1 - 10 eps], so the two guards of
+// limb_dark.py:163-170 never fire and are not evaluated.  Everything that depends on r alone is computed
+// once, and the closed-form terms come after the node loop so that little is live inside it.
+template <int N>
+__device__ __forceinline__ void ld_inside_u(const double (&b)[N], double r, int lmax, double g0, double g1,
+                                            double g2, double (&f)[N]) {
+  const double pi = Num<double>::pi;
+  const double r2 = r * r;
+  double s1[N];
+  if (lmax >= 1) {
+    double two_br[N], r2pb2[N], acc[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      two_br[q] = b[q] * r * 2.0;
+      r2pb2[q] = fma(b[q], b[q], r2);
+      acc[q] = 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+      const double wp = c_gl10[1][5 + p];
+      const double cm = c_gl10[2][5 + p], cq = c_gl10[2][4 - p];  // nodes +x_p, -x_p
+      double z2[2 * N], z[2 * N], t[2 * N];
+#pragma unroll
+      for (int m = 0; m < 2 * N; ++m) z2[m] = 1.0 - fma(-two_br[m >> 1], (m & 1) ? cq : cm, r2pb2[m >> 1]);
+#pragma unroll
+      for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2[m]);
+#pragma unroll
+      for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2[m], frcp_fast(z[m] + 1.0), 1.0);  // (1 - z^3) / (1 - z^2)
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        const double ra = fma(-b[q], cm, r) * t[2 * q];
+        const double rb = fma(-b[q], cq, r) * t[2 * q + 1];
+        acc[q] = fma(wp, ra + rb, acc[q]);
+      }
+    }
+    const double k1 = (pi * 0.5) * (r * (2.0 / 3.0));
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = fma(-k1, acc[q], pi * (2.0 / 3.0));
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = 0.0;
+  }
+  // s0s2, limb_dark.py:111-137 with kappa0 = pi, kappa1 = 0, area = 0
+  const double s0l = (1.0 - r2) * pi;
+  const double s0s = pi - r2 * pi;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double bpr = b[q] + r;
+    const double onembpr2 = (1.0 + bpr) * (1.0 - bpr);
+    const double eta2 = r2 * fma(b[q] * b[q], 2.0, r2) * 0.5;
+    const double delta = b[q] * r * 4.0;
+    const bool large = onembpr2 + delta > delta;
+    const double s2l = s0l * 2.0 + (eta2 - 0.5) * (4.0 * pi);
+    const double s2s = s0s * 2.0 + (eta2 * pi * 2.0 - pi) * 2.0;
+    f[q] = ld_combine(lmax, large ? s0l : s0s, s1[q], large ? s2l : s2s, g0, g1, g2);
+  }
+}
+
+constexpr unsigned WK_RMAX = 8;   // chunks per claim (upper bound)
+constexpr unsigned WK_LOG = 32;   // claims a warp remembers before it signals their completion
+template <int N>
+struct WalkWarpSmem {
+  double rec[2][WALK_REC];         // set record of the chunk being evaluated / of the next one
+  unsigned long long seg[2][32];   // segment window of the next chunk / of the one after
+  uint4 ent[3][WK_RMAX];           // chunk entries of the current claim, the next one, the one after
+  double tb[32 * N];               // time stamps of the next chunk
+  double yb[2][32 * N];            // observed flux, 1 / sigma of this chunk / of the next one
+  double wb[2][32 * N];
+  unsigned ib[2][32 * N];          // sample indices (0xffffffff: padding)
+  unsigned long long log[WK_LOG];  // finished claims: first slot | chunks << 32
+};
+
 template <int N, bool FLUX>
 __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_constant__ WalkEvalArgs a) {
   constexpr int CH = 32 * N;
-  __shared__ double s_rec[4][WALK_REC];
+  __shared__ __align__(16) WalkWarpSmem<N> s_all[4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (!walk_eval_active(a, lane)) return;
+  WalkWarpSmem<N>& sm = s_all[wid];
   const unsigned nA = (unsigned)a.state[1], nB = (unsigned)a.state[2];  // <= cap_chunk <= 2^27
-  const unsigned n_chunks = nA + nB;
   const unsigned nw = gridDim.x * 4u;
-  unsigned ch = blockIdx.x * 4u + wid;
-  if (ch >= n_chunks) return;
   const unsigned topB = (unsigned)a.cap_chunk - nB;  // slot of the first edge-list chunk
-  auto slot_of = [&](unsigned c) { return c < nA ? c : topB + (c - nA); };
-  unsigned n_kep = 0, n_ld = 0, n_fast = 0;
-  double* rec = s_rec[wid];
+  if (nA + nB == 0u) return;
 
-  // software pipeline: entry two chunks ahead, record + segment window one chunk ahead
-  uint4 ent = a.chunk[slot_of(ch)];
-  double rec_v = a.rec[(size_t)ent.x * WALK_REC + lane];
-  unsigned long long seg_v = a.seg[ent.z + (unsigned)(lane < (int)(ent.w & 255u) ? lane : (int)(ent.w & 255u) - 1)];
-  uint4 ent_n = ent;
-  if (ch + nw < n_chunks) ent_n = a.chunk[slot_of(ch + nw)];
-  for (; ch < n_chunks; ch += nw) {
-    // ---- this chunk's staged inputs; start the loads of the next one
-    const unsigned set = ent.x, p0 = ent.y, segk = ent.z, meta = ent.w;
-    const unsigned valid = (meta >> 8) & 0xffffu, nrem = meta & 255u;
-    const bool inside_list = (meta >> 31) == 0u;
-    __syncwarp();
-    rec[lane] = rec_v;
-    const unsigned long long seg_c = seg_v;
-    const bool more = ch + nw < n_chunks;
-    if (more) {
-      ent = ent_n;
-      rec_v = a.rec[(size_t)ent.x * WALK_REC + lane];
-      const int nr = (int)(ent.w & 255u);
-      seg_v = a.seg[ent.z + (unsigned)(lane < nr ? lane : nr - 1)];
-      if (ch + 2u * nw < n_chunks) ent_n = a.chunk[slot_of(ch + 2u * nw)];
+  // ---- work distribution.  A CLAIM is up to WK_RMAX consecutive chunk entries of one list (mostly one
+  // set), taken from two global counters (inside list first, then the dearer edge list); the size shrinks
+  // as the remaining work does (guided self-scheduling), so the warps finish within one chunk of each other.
+  constexpr unsigned long long CL_VALID = 1ull << 63, CL_B = 1ull << 62;
+  bool a_done = false;         // lane 0 only
+  unsigned posA = 0, posB = 0;  // lane 0 only: where this warp last saw the counters
+  auto claim_size = [&](unsigned remaining) {
+    const unsigned r = remaining / (nw * 2u);
+    return r < 1u ? 1u : (r > WK_RMAX ? WK_RMAX : r);
+  };
+  auto claim_issue = [&]() -> unsigned long long {  // lane 0 asks; the answer is read later (latency hidden)
+    unsigned long long r = 0ull;
+    if (lane == 0) {
+      if (!a_done) {
+        const unsigned R = claim_size((posA < nA ? nA - posA : 0u) + nB);
+        const unsigned s = (unsigned)atomicAdd(a.state_rw + 6, (unsigned long long)R);
+        if (s < nA) {
+          const unsigned n = nA - s < R ? nA - s : R;
+          r = CL_VALID | ((unsigned long long)n << 32) | s;
+          posA = s + n;
+        } else {
+          a_done = true;
+        }
+      }
+      if (r == 0ull) {
+        const unsigned R = claim_size(posB < nB ? nB - posB : 0u);
+        const unsigned s = (unsigned)atomicAdd(a.state_rw + 7, (unsigned long long)R);
+        if (s < nB) {
+          const unsigned n = nB - s < R ? nB - s : R;
+          r = CL_VALID | CL_B | ((unsigned long long)n << 32) | s;
+          posB = s + n;
+        }
+      }
     }
-    __syncwarp();
-
-    // ---- positions -> sample indices: largest j with cum[j] <= p among the staged 32 segments
-    const unsigned cumw = (lane < (int)nrem) ? (unsigned)seg_c : 0xffffffffu;
-    const unsigned startw = (unsigned)(seg_c >> 32);
-    bool have[N];
+    return r;
+  };
+  auto claim_decode = [&](unsigned long long raw, unsigned& slot0, unsigned& cnt) -> bool {
+    raw = __shfl_sync(0xffffffffu, raw, 0);
+    slot0 = (unsigned)raw + ((raw & CL_B) ? topB : 0u);
+    cnt = (unsigned)(raw >> 32) & 0xffffu;
+    return (raw & CL_VALID) != 0ull;
+  };
+  auto stage_entries = [&](int buf, unsigned slot0, unsigned cnt) {
+    if ((unsigned)lane < cnt) cp_async16(&sm.ent[buf][lane], a.chunk + slot0 + lane);
+  };
+  auto stage_rec_seg = [&](int buf, const uint4& e) {  // the chunk's set record and its first 32 segments
+    cp_async8(&sm.rec[buf][lane], a.rec + (size_t)e.x * WALK_REC + lane);
+    const int nr = (int)(e.w & 255u);
+    cp_async8(&sm.seg[buf][lane], a.seg + e.z + (unsigned)(lane < nr ? lane : nr - 1));
+  };
+  auto stage_samples = [&](int buf, const uint4& e, int segbuf) {  // indices -> t, y, 1 / sigma of the chunk
     unsigned idx[N];
+    bool have[N];
+    walk_indices<N>(a, e, sm.seg[segbuf], lane, idx, have);
 #pragma unroll
     for (int h = 0; h < N; ++h) {
-      const unsigned p = p0 + 32u * h + lane;
-      have[h] = 32u * h + lane < valid;
-      int j = 0;
-#pragma unroll
-      for (int st = 16; st > 0; st >>= 1) {
-        const unsigned v = __shfl_sync(0xffffffffu, cumw, j + st);
-        if (v <= p) j += st;
+      cp_async8(&sm.tb[32 * h + lane], a.t + idx[h]);
+      if (!FLUX) {
+        cp_async8(&sm.yb[buf][32 * h + lane], a.y + idx[h]);
+        cp_async8(&sm.wb[buf][32 * h + lane], a.winv + idx[h]);
       }
-      unsigned cj = __shfl_sync(0xffffffffu, cumw, j);
-      unsigned sj = __shfl_sync(0xffffffffu, startw, j);
-      if (j == 31 && nrem > 32u && have[h]) {
-        // more than 32 segments inside one chunk (runs of one or two samples): walk the table itself; the
-        // list's sentinel (first position past the list, > p for a valid position) ends the search
-        unsigned k = segk + 31u;
-        while ((unsigned)a.seg[k + 1u] <= p) ++k;
-        const unsigned long long sv = a.seg[k];
-        cj = (unsigned)sv;
-        sj = (unsigned)(sv >> 32);
-      }
-      idx[h] = have[h] ? sj + (p - cj) : 0u;
+      sm.ib[buf][32 * h + lane] = have[h] ? idx[h] : 0xffffffffu;
     }
-    double tm[N], yv[N], wv[N];
+  };
+
+  unsigned n_ld = 0, n_fast = 0;  // per lane: limb-darkening evaluations, of which with the constant-kappa code
+  unsigned nlog = 0;
+  // completion of the logged claims: one fence for all their partial sums, then lane i counts the finished
+  // chunks of claim i into their sets; the lane that completes a set adds the set's partials in a fixed
+  // order (bit-reproducible: who does it changes nothing)
+  auto flush_log = [&]() {
+    __syncwarp();
+    __threadfence();
+    if ((unsigned)lane < nlog) {
+      const unsigned long long lg = sm.log[lane];
+      const unsigned slot0 = (unsigned)lg, cnt = (unsigned)(lg >> 32);
+      unsigned sets[WK_RMAX];
 #pragma unroll
-    for (int h = 0; h < N; ++h) tm[h] = a.t[idx[h]];
-    if (!FLUX) {
+      for (unsigned k = 0; k < WK_RMAX; ++k) sets[k] = k < cnt ? a.chunk[slot0 + k].x : 0xffffffffu;
+      unsigned run = 0;
 #pragma unroll
-      for (int h = 0; h < N; ++h) {
-        yv[h] = a.y[idx[h]];
-        wv[h] = a.winv[idx[h]];
+      for (unsigned k = 0; k < WK_RMAX; ++k) {
+        if (k < cnt) {
+          ++run;
+          const unsigned nxt = k + 1u < WK_RMAX ? sets[k + 1u < WK_RMAX ? k + 1u : k] : 0xffffffffu;
+          if (k + 1u == cnt || nxt != sets[k]) {
+            const unsigned prev = atomicAdd(&a.wset_rw[sets[k]].done, run);
+            if (prev + run == a.wset[sets[k]].n_chunks) walk_finish_set<CH>(a, sets[k]);
+            run = 0;
+          }
+        }
       }
     }
-    double tot[N];
+    nlog = 0;
+    __syncwarp();
+  };
+
+  // ---- prologue: the first two claims, the first chunk's inputs (latencies exposed once per warp)
+  unsigned cur_slot0, cur_cnt, nxt_slot0 = 0, nxt_cnt = 0;
+  if (!claim_decode(claim_issue(), cur_slot0, cur_cnt)) return;
+  bool nxt_valid = claim_decode(claim_issue(), nxt_slot0, nxt_cnt);
+  stage_entries(0, cur_slot0, cur_cnt);
+  if (nxt_valid) stage_entries(1, nxt_slot0, nxt_cnt);
+  cp_async_wait_all();
+  __syncwarp();
+  stage_rec_seg(0, sm.ent[0][0]);
+  cp_async_wait_all();
+  __syncwarp();
+  stage_samples(0, sm.ent[0][0], 0);
+  int eb = 0, rb = 0, pb = 0;
+  unsigned k = 0;
+  unsigned long long raw_nn = 0ull;
+  unsigned nn_slot0 = 0, nn_cnt = 0;  // the claim after next (known from the middle of a claim's first chunk)
+  bool nn_valid = false;
+
+  for (;;) {
+    // ================= top: this chunk's inputs have landed; start the next chunk's record / segments
+    cp_async_wait_all();
+    __syncwarp();
+    const uint4 e = sm.ent[eb][k];
+    if (k == 0u && nxt_valid) raw_nn = claim_issue();  // the claim after next: answer read at mid-chunk
+    const bool same_claim = k + 1u < cur_cnt;
+    const bool has_next_chunk = same_claim || nxt_valid;
+    const int eb_next = eb == 2 ? 0 : eb + 1;
+    uint4 en = e;
+    if (has_next_chunk) {
+      en = same_claim ? sm.ent[eb][k + 1u] : sm.ent[eb_next][0];
+      stage_rec_seg(rb ^ 1, en);
+    }
+    const double* rec = sm.rec[rb];
+    const double2* rec2 = reinterpret_cast<const double2*>(rec);
+    const unsigned set = e.x;
+    const unsigned valid = (e.w >> 8) & 0xffffu;
+    const bool inside_list = (e.w >> 31) == 0u;
+    double tot[N], bq[N];
+    bool intr[N], fast[N], want_gen = false, want_fast = false;
+    int lmax = 0;
 #pragma unroll
-    for (int h = 0; h < N; ++h) tot[h] = 0.0;
+    for (int h = 0; h < N; ++h) {
+      tot[h] = 0.0;
+      bq[h] = 2.0;
+      intr[h] = fast[h] = false;
+    }
     if (valid != 0u) {
       // ---- t -> mean anomaly (keplerian.py:538, kepler.py:31), the reference's operation order; the
       // division by the period is a multiplication by fl(1 / P) with one residual correction
-      const double P = rec[WK_PERIOD], invP = rec[WK_INVP], t0 = rec[WK_T0], tref = rec[WK_TREF];
+      const double2 tt = rec2[WK_T0 / 2], pp = rec2[WK_PERIOD / 2];
       const unsigned flags = (unsigned)__double_as_longlong(rec[WK_FLAGS]);
-      const int lmax = (int)(flags >> 8);
+      lmax = (int)(flags >> 8);
       double Mr[N];
 #pragma unroll
       for (int h = 0; h < N; ++h) {
-        const double x = (tm[h] - t0) - tref;
+        const double x = (sm.tb[32 * h + lane] - tt.x) - tt.y;
         const double num = Num<double>::two_pi * x;
-        const double q = num * invP;
-        const double r = fma(-P, q, num);
-        Mr[h] = mod_two_pi(fma(r, invP, q));
+        const double q = num * pp.y;
+        const double r = fma(-pp.x, q, num);
+        Mr[h] = mod_two_pi(fma(r, pp.y, q));
       }
       double yD[N], xD[N];
+#if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 1)
+      // measurement only: no Kepler solve
+#pragma unroll
+      for (int h = 0; h < N; ++h) {
+        yD[h] = Mr[h] * 1e-3;
+        xD[h] = 1.0 - Mr[h] * 1e-4;
+      }
+      if (true) {
+      } else if (false) {
+#else
       if (flags & WKF_CIRCULAR) {
+#endif
 #pragma unroll
         for (int h = 0; h < N; ++h) fsincos(Mr[h], &yD[h], &xD[h]);  // keplerian.py:539-540
       } else {
-        kepler_xy_u<N>(Mr, rec[WK_E], rec[WK_OME], rec[WK_OPE], rec[WK_S1ME2], rec[WK_INVOPE],
-                       (flags & WKF_SLOW_STARTER) != 0u, yD, xD);
+        const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
+        kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], (flags & WKF_SLOW_STARTER) != 0u, yD, xD);
       }
       // ---- sky position (keplerian.py:568-576, 630-632; light_curves/limb_dark.py:53): with
       // (x0, y0) = -a (xD, yD) the constants -a / R*, cos i and -sin i are folded into k1, k2, zs
-      const double cw = rec[WK_CW], sw = rec[WK_SW], k1 = rec[WK_K1], k2 = rec[WK_K2], zs = rec[WK_ZS];
-      const double rr = rec[WK_RR], onepr = rec[WK_ONEPR];
-      const double ar = fabs(rr);
-      const bool r_small = ar < 1.0;
-      double bq[N], rq[N];
-      bool intr[N], fast[N], want_gen = false, want_fast = false;
+      const double2 ws2 = rec2[WK_CW / 2], kk = rec2[WK_K1 / 2], zo = rec2[WK_ZS / 2];
+      const double ar = fabs(rec[WK_RR]);
+      const bool r_ok = (ar < 1.0) && (ar >= 2e-6);      // what ld_inside_u needs of the set ...
+      const double b_lim = (1.0 - ar) - 4e-15;            // ... and of the sample
 #pragma unroll
       for (int h = 0; h < N; ++h) {
-        const double u1 = fma(cw, xD[h], -sw * yD[h]);
-        const double u2 = fma(sw, xD[h], cw * yD[h]);
-        const double v1 = k1 * u1, v2 = k2 * u2;
+        const double u1 = fma(ws2.x, xD[h], -ws2.y * yD[h]);
+        const double u2 = fma(ws2.y, xD[h], ws2.x * yD[h]);
+        const double v1 = kk.x * u1, v2 = kk.y * u2;
         bq[h] = fsqrt(fma(v1, v1, v2 * v2));
-        rq[h] = rr;
-        intr[h] = have[h] && (zs * u2 > 0.0) && !(bq[h] >= onepr);
-        n_kep += have[h] ? 1u : 0u;
+        intr[h] = (32u * h + lane < valid) && (zo.x * u2 > 0.0) && !(bq[h] >= zo.y);
+        // the flux code an item gets depends on the item alone: inside list AND b safely below 1 - r
+        fast[h] = inside_list && (bq[h] < b_lim) && r_ok;
         n_ld += intr[h] ? 1u : 0u;
-        // the flux code an item gets depends on the item alone: inside list AND b < 1 - r
-        fast[h] = inside_list && (bq[h] < 1.0 - ar) && r_small;
         n_fast += (intr[h] && fast[h]) ? 1u : 0u;
         want_gen = want_gen || (intr[h] && !fast[h]);
         want_fast = want_fast || (intr[h] && fast[h]);
       }
       want_gen = __any_sync(0xffffffffu, want_gen);
       want_fast = __any_sync(0xffffffffu, want_fast);
-      const double g0 = rec[WK_G0], g1 = rec[WK_G1], g2 = rec[WK_G2];
+    }
+    // ================= mid: the claim after next becomes known; the next chunk's samples start to fly
+    if (k == 0u && nxt_valid) {
+      nn_valid = claim_decode(raw_nn, nn_slot0, nn_cnt);
+      if (nn_valid) stage_entries(eb_next == 2 ? 0 : eb_next + 1, nn_slot0, nn_cnt);
+    }
+    if (has_next_chunk) {
+      cp_async_wait_all();
+      __syncwarp();
+      stage_samples(pb ^ 1, en, rb ^ 1);
+    }
+    // ================= flux (core/limb_dark.py:19-196)
+#if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 2)
+    // measurement only: no flux code
+#pragma unroll
+    for (int h = 0; h < N; ++h) tot[h] = intr[h] ? bq[h] * 1e-3 : 0.0;
+    if (false) {
+#else
+    if (want_fast || want_gen) {
+#endif
+      const double rr = rec[WK_RR];
+      const double2 gg = rec2[WK_G0 / 2];
+      const double g2 = rec[WK_G2];
       if (want_fast) {
-        double s0[N], s1v[N], s2[N];
-        ld_solution_inside_n<N>(bq, rq, lmax, s0, s1v, s2);  // constant node cosines, no atan2
+        double f[N];
+        ld_inside_u<N>(bq, fabs(rr), lmax, gg.x, gg.y, g2, f);  // constant node cosines, no atan2
 #pragma unroll
         for (int h = 0; h < N; ++h)
-          if (intr[h] && fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], g0, g1, g2);
+          if (intr[h] && fast[h]) tot[h] = f[h];
       }
       if (want_gen) {
-        double s0[N], s1v[N], s2[N];
+        double rq[N], s0[N], s1v[N], s2[N];
+#pragma unroll
+        for (int h = 0; h < N; ++h) rq[h] = rr;
         ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
 #pragma unroll
         for (int h = 0; h < N; ++h)
-          if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], g0, g1, g2);
+          if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
       }
     }
+    // ================= end: outputs of this chunk
     if (FLUX) {
       // rows were zeroed before the launch; positions of different items are disjoint
 #pragma unroll
       for (int h = 0; h < N; ++h) {
-        if (have[h] && tot[h] != 0.0) {
-          const size_t o = (size_t)set * (size_t)a.n_times + idx[h];
+        const unsigned ix = sm.ib[pb][32 * h + lane];
+        if (ix != 0xffffffffu && tot[h] != 0.0) {
+          const size_t o = (size_t)set * (size_t)a.n_times + ix;
           if (a.flux_sum) a.flux_sum[o] = tot[h];
           if (a.flux) a.flux[o] = tot[h];
         }
@@ -606,62 +933,48 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
 #pragma unroll
       for (int h = 0; h < N; ++h) {
         double dchi = 0.0;
-        if (have[h] && tot[h] != 0.0) {
-          const double r0 = (yv[h] - 1.0) * wv[h];
-          const double mw = tot[h] * wv[h];
+        if (tot[h] != 0.0) {
+          const double wv = sm.wb[pb][32 * h + lane];
+          const double r0 = (sm.yb[pb][32 * h + lane] - 1.0) * wv;
+          const double mw = tot[h] * wv;
           dchi = (-mw) * (2.0 * r0 - mw);
         }
         csum += dchi;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-      // the warp that finishes a set's last chunk adds the set's partials in a fixed order
-      const WalkSet wsv = a.wset[set];
-      unsigned prev = 0;
-      if (lane == 0) {
-        a.part[slot_of(ch)] = csum;
-        __threadfence();
-        prev = atomicAdd(&a.wset_rw[set].done, 1u);
-      }
-      prev = __shfl_sync(0xffffffffu, prev, 0);
-      if (prev + 1u == wsv.n_chunks) {
-        __threadfence();
-        const unsigned nchA = wsv.n_chunks - (unsigned)((wsv.cntB + CH - 1) / CH);
-        const unsigned nchB = wsv.n_chunks - nchA;
-        const double* pA = a.part + wsv.chA;
-        const double* pB = a.part + (a.cap_chunk - wsv.chB - nchB);
-        double acc = 0.0;
-        for (unsigned i = lane; i < nchA; i += 32) acc += __ldcg(pA + i);
-        for (unsigned i = lane; i < nchB; i += 32) acc += __ldcg(pB + i);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        // set-independent terms: the LL_NCTA pairs of the likelihood prep added in order
-        static_assert(LL_NCTA == 64, "two pairs per lane");
-        const double2 pa = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[lane];
-        const double2 pb = reinterpret_cast<const double2*>(a.scalars + LL_SCAL0)[32 + lane];
-        double chi0 = 0.0, cst = 0.0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          chi0 += __shfl_sync(0xffffffffu, pa.x, k);
-          cst += __shfl_sync(0xffffffffu, pa.y, k);
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          chi0 += __shfl_sync(0xffffffffu, pb.x, k);
-          cst += __shfl_sync(0xffffffffu, pb.y, k);
-        }
-        if (lane == 0) a.loglike[set] = -0.5 * (chi0 + acc) + cst;
-      }
+      if (lane == 0) a.part[cur_slot0 + k] = csum;
     }
+    // ================= advance
+    if (has_next_chunk) {
+      rb ^= 1;
+      pb ^= 1;
+    }
+    if (same_claim) {
+      ++k;
+      continue;
+    }
+    if (!FLUX) {
+      if (lane == 0) sm.log[nlog] = (unsigned long long)cur_slot0 | ((unsigned long long)cur_cnt << 32);
+      if (++nlog == WK_LOG) flush_log();
+    }
+    if (!nxt_valid) break;
+    cur_slot0 = nxt_slot0;
+    cur_cnt = nxt_cnt;
+    nxt_slot0 = nn_slot0;
+    nxt_cnt = nn_cnt;
+    nxt_valid = nn_valid;
+    nn_valid = false;
+    eb = eb_next;
+    k = 0;
   }
-  n_kep = __reduce_add_sync(0xffffffffu, n_kep);
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
   n_fast = __reduce_add_sync(0xffffffffu, n_fast);
   if (lane == 0) {
-    atomicAdd(a.counters + 0, (unsigned long long)n_kep);
     atomicAdd(a.counters + 1, (unsigned long long)n_ld);
     atomicAdd(a.counters + 5, (unsigned long long)n_fast);
   }
+  if (!FLUX && nlog) flush_log();
 }
 
 }  // namespace jxp
@@ -710,7 +1023,7 @@ int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, 
   a.flux = flux;
   a.flux_sum = flux_sum;
   a.loglike = loglike;
-  cudaError_t e = cudaMemsetAsync(a.state, 0, 8 * sizeof(unsigned long long), st);
+  cudaError_t e = cudaMemsetAsync(a.state, 0, 10 * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
   if (ev_start && ev_which == 1) cudaEventRecord(ev_start, st);
   if (loglike)
@@ -729,6 +1042,7 @@ int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, 
   b.chunk = a.chunk;
   b.part = a.part;
   b.state = a.state;
+  b.state_rw = a.state;
   b.cap_chunk = a.cap_chunk;
   b.scalars = d_scalars;
   b.t = t;
