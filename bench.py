@@ -89,7 +89,7 @@ def build_inputs(seed):
 
     p, u, t, noise, sigma = W.c3(N_SETS, N_TIMES, seed=seed)
     bodies, n_sets, _ = pack_bodies(W.system_from(p))
-    return p, bodies.numpy().copy(), u, t, noise, sigma
+    return p, bodies.cpu().numpy().copy(), u, t, noise, sigma
 
 
 # ------------------------------------------------------------------------------------------

@@ -238,6 +238,31 @@ int jxp_transit_partials_f32(const double* theta, int32_t n_sets, const double* 
                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K8  Positions and velocities of Keplerian bodies.
+ *   reference: OrbitalBody.position / central_position / relative_position / velocity /
+ *     central_velocity / relative_velocity / radial_velocity
+ *     src/jaxoplanet/orbits/keplerian.py:366-532 over _get_true_anomaly :537-541,
+ *     _get_position_and_velocity :590-637 and _rotate_vector :543-588
+ *
+ * bodies:  [n_sets][JXP_BODY_NFIELDS] as for jxp_system_light_curve_* (the semimajor, radius and
+ *          central radius fields are not used here), ALWAYS double.
+ * r_scale: [n_sets] (stride 1) or one value (stride 0): the factor of the orbital radius -- the
+ *          `semimajor` argument of _get_position_and_velocity (keplerian.py:620-625, parallax included).
+ * k_amp:   [n_sets] or one value: the velocity amplitude k0 (keplerian.py:604-618).
+ * asc_node: [n_sets][2] cos and sin of the ascending node, or NULL (keplerian.py:578-588).
+ * flags:   JXP_STATE_NO_INCLINATION: velocities rotated without the inclination (a given
+ *          semi-amplitude, keplerian.py:634 include_inclination=False).
+ * pos, vel: [3][n_sets][n_times] (x, y, z planes) or NULL; time stamps ALWAYS double.
+ * ---------------------------------------------------------------------------------- */
+#define JXP_STATE_NO_INCLINATION 1
+int jxp_orbit_state_f64(const double* bodies, int32_t n_sets, const double* r_scale, int64_t r_stride,
+                        const double* k_amp, int64_t k_stride, const double* asc_node, const double* t,
+                        int64_t n_times, int32_t flags, double* pos, double* vel, void* stream);
+int jxp_orbit_state_f32(const double* bodies, int32_t n_sets, const double* r_scale, int64_t r_stride,
+                        const double* k_amp, int64_t k_stride, const double* asc_node, const double* t,
+                        int64_t n_times, int32_t flags, float* pos, float* vel, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K0  OrbitalBody.__init__(central, body): the per-set derived constants
  *     src/jaxoplanet/orbits/keplerian.py:262-340
  * elements: [n][JXP_EL_NFIELDS] (device) the sampled Body arguments of one body per row, NaN =

@@ -84,7 +84,41 @@ def to_dev(x, dtype: torch.dtype) -> torch.Tensor:
     arr = np.asarray(x)
     if arr.dtype.kind not in "fiub":
         raise TypeError(f"unsupported input dtype {arr.dtype}")
+    if arr.size >= 4096 and arr.dtype.kind == "f":
+        return host_to_dev(arr, dtype)
     return torch.as_tensor(np.ascontiguousarray(arr), device="cpu").to(device=dev, dtype=dtype)
+
+
+_PINNED: dict = {}
+
+
+def host_to_dev(arr, dtype: torch.dtype = torch.float64) -> torch.Tensor:
+    """NumPy array -> new CUDA tensor through a cached PINNED staging buffer: one memcpy into page-locked
+    memory and one asynchronous DMA, instead of the driver's pageable-memory path (which stages the same
+    bytes itself, synchronously, at a fraction of the bandwidth).  The staging buffer is reused, so the copy
+    is ordered behind the previous one by an event."""
+    dev = device()
+    a = np.ascontiguousarray(arr)
+    src = torch.from_numpy(a)
+    if src.dtype != dtype:
+        src = src.to(dtype)
+    n = src.numel()
+    if n < 4096:  # small: the plain path is as fast
+        return src.to(dev)
+    key = (dtype, dev.index)
+    slot = _PINNED.get(key)
+    if slot is None or slot[0].numel() < n:
+        buf = torch.empty(max(n, 1 << 16), dtype=dtype).pin_memory()
+        slot = [buf, torch.cuda.Event()]
+        slot[1].record()
+        _PINNED[key] = slot
+    buf, ev = slot
+    ev.synchronize()  # the previous DMA out of this buffer has finished
+    buf[:n].copy_(src.reshape(-1))
+    out = torch.empty(src.shape, dtype=dtype, device=dev)
+    out.reshape(-1).copy_(buf[:n], non_blocking=True)
+    ev.record()
+    return out
 
 
 def like_input(out: torch.Tensor, *inputs):

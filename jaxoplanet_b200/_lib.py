@@ -16,6 +16,7 @@ JXP_BODY_NFIELDS = 12
 JXP_NTHETA = 8
 JXP_FLAG_NO_WINDOW = 1
 JXP_FLAG_COUNT = 2
+JXP_STATE_NO_INCLINATION = 1
 # development / measurement options (jxp_set_dev_options): paths that return the same results
 JXP_DEV_NO_WALK = 1
 JXP_DEV_NO_PAIR = 2
@@ -93,6 +94,8 @@ SIGNATURES = {
     "jxp_transit_orbit_light_curve_f64": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_transit_orbit_light_curve_f32": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_orbital_elements_f64": (C.c_int, [_p, _i64, _p, _p]),
+    "jxp_orbit_state_f64": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p]),
+    "jxp_orbit_state_f32": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p]),
     "jxp_interp_periodic_f64": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_interp_periodic_f32": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),

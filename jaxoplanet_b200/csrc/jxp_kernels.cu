@@ -828,14 +828,7 @@ __global__ void __launch_bounds__(128, JXP_SYS_MINB) k_system(const __grid_const
         T b = T(0), Z = T(-1);
         if (ok) {
           ++n_kep;
-          const T Mr = T(mean_anomaly_reduced(c, tm));
-          T sf, cf, Edummy;
-          if (c.flags & BODY_CIRCULAR) {
-            jsincos(Mr, &sf, &cf);
-          } else {
-            kepler_reduced<T, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
-          }
-          sky_position(c, sf, cf, b, Z);
+          position_stage(c, tm, b, Z);
         }
         const bool hit = ok && (Z > T(0)) && !(b >= c.onepr);
         const unsigned mk = __ballot_sync(0xffffffffu, hit);

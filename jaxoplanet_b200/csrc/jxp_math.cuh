@@ -334,6 +334,37 @@ __device__ __forceinline__ S kite_area(S a, S b, S c) {
   return jzsqrt(jmax(S(B(0)), sq));
 }
 
+// One node of the l = 1 line integral (limb_dark.py:160-172): (1 - z^3) / (1 - z^2) given 1 - z^2, and
+// whether the reference forces the node's term to 0.  (1 - z^3) / (1 - z^2) is evaluated as
+// 1 + z^2 / (1 + z): the same function without the cancellation in 1 - z^3.
+//   double: the reference's guards (z^2 < 10 eps or 1 - z^2 < 10 eps: term = 0).
+//   fp32 MODE: the reference's guards are at 10 eps OF THE DTYPE (utils.get_dtype_eps); in float they zero
+//   every node with z^2 < 1.2e-6, i.e. the whole integral for a planet within ~6e-7 of the outer contact --
+//   1e-4 of flux (measured on BASELINE config 3: 118 ppm) where the double evaluation of the same formula
+//   gives ~1e-11.  The fp32 mode answers to the DOUBLE reference (1 ppm), so it keeps the double guards'
+//   meaning: they fire on a set of measure zero, and in between the term is finite and smooth.  Where float
+//   cannot resolve z^2 (or 1 - z^2) the factor is taken at its limit (1 at the limb, 3 / 2 at the centre:
+//   off by <= 1.2e-6 of a term that is itself <= 1e-3 there) with zero derivative; no term is zeroed.
+template <typename S>
+__device__ __forceinline__ S ld_node_factor(const S& omz2, bool& dead) {
+  using B = typename BaseOf<S>::type;
+  const B eps10 = B(10) * Num<B>::eps;
+  if constexpr (std::is_same<B, float>::value) {
+    const bool at_limb = !(val(omz2) <= B(1) - eps10);
+    const bool at_centre = !(val(omz2) >= eps10);
+    dead = false;
+    const S z2s = jsel(at_limb || at_centre, S(B(1)), B(1) - omz2);
+    const S z = jsqrt_pos(z2s);
+    const S t = jdiv(z2s, z + B(1)) + B(1);
+    return jsel(at_limb, S(B(1)), t);  // (at the centre z2s = 1 gives the limit 3 / 2)
+  } else {
+    dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
+    const S z2s = jsel(dead, S(B(1)), B(1) - omz2);
+    const S z = jsqrt_pos(z2s);
+    return jdiv(z2s, z + B(1)) + B(1);
+  }
+}
+
 // Solution vector (s0, s1, s2) for l_max <= 2, limb_dark.py:50-84 with kappas :102-108,
 // s0s2 :111-137 and the l = 1 term of p_integral :140-173.
 //   lmax 0: only s0 is meaningful; lmax 1: s0, s1; lmax 2: all.
@@ -466,13 +497,10 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
     // forced to 0 either way), so the primal path skips it; the dual path keeps it for the
     // derivative.  z^2 < 10 eps  <=>  1 - z^2 > 1 - 10 eps exactly.
     const S omz2 = jclamp0_lazy(r2pb2 - two_br * c);
-    const bool dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
-    // the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), forced to 0 where z^2 < 10 eps or
-    // 1 - z^2 < 10 eps.  (1 - z^3) / (1 - z^2) is evaluated as 1 + z^2 / (1 + z): the same
-    // function without the cancellation in 1 - z^3.
-    const S z2s = jsel(dead, S(B(1)), B(1) - omz2);
-    const S z = jsqrt_pos(z2s);
-    S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
+    // the term is 2 r (r - b c) (1 - z^3) / (3 (1 - z^2)), guards in ld_node_factor
+    bool dead;
+    const S tf = ld_node_factor(omz2, dead);
+    S res = two_r_3 * (r - b * c) * tf;
     res = jsel(dead, S(B(0)), res);
     acc = acc + res * wi;
     if (HI) {
@@ -692,10 +720,9 @@ __device__ __forceinline__ void ld_solution_inside(S b, S r, S& s0, S& s1, S& s2
     for (int q = 0; q < 2; ++q) {
       const B c = B(q ? c_gl10[2][4 - p] : c_gl10[2][5 + p]);
       const S omz2 = jclamp0_lazy(r2pb2 - two_br * c);
-      const bool dead = !((val(omz2) >= eps10) && (val(omz2) <= B(1) - eps10));
-      const S z2s = jsel(dead, S(B(1)), B(1) - omz2);
-      const S z = jsqrt_pos(z2s);
-      S res = two_r_3 * (r - b * c) * (jdiv(z2s, z + B(1)) + B(1));
+      bool dead;
+      const S tf = ld_node_factor(omz2, dead);
+      S res = two_r_3 * (r - b * c) * tf;
       res = jsel(dead, S(B(0)), res);
       acc = acc + res * wi;
     }

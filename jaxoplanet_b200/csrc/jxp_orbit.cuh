@@ -10,8 +10,12 @@ namespace jxp {
 enum : int { BODY_CIRCULAR = 1, BODY_ALWAYS = 2 };
 
 // Device-side record of one (parameter set, body), produced once per call by the prep
-// kernel and broadcast to a CTA through shared memory.  Time-like fields stay double in
-// the fp32 mode (DESIGN.md "fp32 mode").
+// kernel and broadcast to a CTA through shared memory.  Everything the POSITION stage reads
+// (t -> mean anomaly -> Kepler solve -> sky position -> b) stays double in the fp32 mode: a float
+// angle of order pi carries 2.4e-7 rad, times a / R* ~ 15 that is 4e-6 of a stellar radius in b and
+// several ppm of flux on ingress (measured on BASELINE config 3: 6.8 ppm).  Only in-window samples
+// reach that stage, so the fp32 mode keeps its speed where it has it: the flux code (DESIGN.md
+// "fp32 mode").
 template <typename T>
 struct BodyC {
   double t0;          // time_transit
@@ -23,11 +27,12 @@ struct BodyC {
   double wlo, whi;    // window edges relative to the centre [cycles], margins included
   double win_in;      // estimated half-width [cycles] of the part of the transit with the planet fully
                       // inside the disk, slightly short; 0: none.  Only groups work, never decides a value.
-  T e, ome, ope, s1me2, inv_ope;
-  T cw, sw, ci, si;
-  T na_ome2;  // -a (1 - e^2)
-  T na;       // -a
-  T inv_rstar, rr, onepr;
+  double e, ome, ope, s1me2, inv_ope;
+  double cw, sw, ci, si;
+  double na_ome2;  // -a (1 - e^2)
+  double na;       // -a
+  double inv_rstar;
+  T rr, onepr;
   int flags;
   int pad;
 };
@@ -39,12 +44,16 @@ struct SetC {
   int lmax;
 };
 
-// Mean anomaly at true anomaly f (monotone map used only for the window edges).
-__device__ inline double mean_from_true(double f, double e) {
+// Mean anomaly at true anomaly f (monotone map used only for the window edges).  The window is widened by
+// 1e-9 (relative) and 1e-7 cycles, so the branch-free primitives of jxp_fastmath.cuh (<= 1e-15) serve here:
+// the CUDA library versions made the per-set preparation a ~10 us serial chain.
+__device__ inline double mean_from_true(double f, double sq1me, double sq1pe, double e) {
   double sh, ch;
-  sincos(0.5 * f, &sh, &ch);
-  double E = 2.0 * atan2(sqrt(1.0 - e) * sh, sqrt(1.0 + e) * ch);
-  return E - e * sin(E);
+  fsincos(0.5 * f, &sh, &ch);
+  const double E = 2.0 * fatan2(sq1me * sh, sq1pe * ch);
+  double sE, cE;
+  fsincos(E, &sE, &cE);
+  return E - e * sE;
 }
 
 // Conservative transit window in orbital phase.  With theta = f + omega - theta_c the angle
@@ -68,17 +77,20 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
   c.win_in = 0.0;
   const double sw = (double)c.sw, cw = (double)c.cw;
   const double ci = (double)c.ci, si = (double)c.si;
-  const double rho = sqrt(sw * sw + cw * cw);
+  const double rho = fsqrt(sw * sw + cw * cw);
   if (!(e >= 0.0) || !(e < 0.99) || !(rho > 0.0) || !(si * si > 1e-6)) return;
   const double reach = (1.0 + fabs((double)c.rr)) * rstar * widen;  // (1 + r) R*
-  const double omega = atan2(sw, cw);
+  const double omega = fatan2(sw, cw);
   const double theta_c = (si >= 0.0) ? Num<double>::half_pi : 3.0 * Num<double>::half_pi;
   const double fc = theta_c - omega;
+  const double inv_si2 = fdiv(1.0, si * si);
+  double sfc, cfc;
+  fsincos(fc, &sfc, &cfc);
   double rmin = rho * a * (1.0 - e);
-  double delta = 0.0;
+  double delta = 0.0, sd = 0.0, cd = 1.0;
   for (int pass = 0; pass < 2; ++pass) {
-    const double q = reach / rmin;
-    const double S = (q * q - ci * ci) / (si * si);
+    const double q = fdiv(reach, rmin);
+    const double S = (q * q - ci * ci) * inv_si2;
     if (!(S < 0.9)) return;  // wide (or NaN): evaluate everything
     if (S <= 0.0) {          // never in transit: empty window
       if (!isfinite(c.inv_period) || !isfinite(c.t0ref)) return;
@@ -87,21 +99,26 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
       c.flags &= ~BODY_ALWAYS;
       return;
     }
-    delta = asin(sqrt(S));
+    sd = fsqrt(S);                              // sin(delta)
+    cd = fsqrt(1.0 - S);                        // cos(delta), delta in (0, 1.25)
+    delta = fatan2(sd, cd);                     // asin(sqrt(S))
     if (pass == 0) {
       const double fcr = fc - Num<double>::two_pi * rint(fc * Num<double>::inv_two_pi);
-      const double cmax = (fabs(fcr) <= delta) ? 1.0 : fmax(cos(fc - delta), cos(fc + delta));
-      rmin = rho * a * (1.0 - e * e) / (1.0 + e * cmax) * (1.0 - 1e-12);
+      // max of cos(fc - delta), cos(fc + delta) = cos fc cos delta + |sin fc| sin delta
+      const double cmax = (fabs(fcr) <= delta) ? 1.0 : fma(cfc, cd, fabs(sfc) * sd);
+      rmin = fdiv(rho * a * (1.0 - e * e), 1.0 + e * cmax) * (1.0 - 1e-12);
     }
   }
-  const double Mc = mean_from_true(fc, e);
-  double lo = mean_from_true(fc - delta, e) - Mc;
-  double hi = mean_from_true(fc + delta, e) - Mc;
-  while (lo > 0.0) lo -= Num<double>::two_pi;
-  while (hi < 0.0) hi += Num<double>::two_pi;
+  const double sq1me = fsqrt(1.0 - e), sq1pe = fsqrt(1.0 + e);
+  const double Mc = mean_from_true(fc, sq1me, sq1pe, e);
+  double lo = mean_from_true(fc - delta, sq1me, sq1pe, e) - Mc;
+  double hi = mean_from_true(fc + delta, sq1me, sq1pe, e) - Mc;
+  // (the differences are multiples of 2 pi away from the wanted branch by at most a few turns)
+  for (int it = 0; it < 8 && lo > 0.0; ++it) lo -= Num<double>::two_pi;
+  for (int it = 0; it < 8 && hi < 0.0; ++it) hi += Num<double>::two_pi;
   lo = lo * Num<double>::inv_two_pi - margin;
   hi = hi * Num<double>::inv_two_pi + margin;
-  if (!(lo > -0.45) || !(hi < 0.45)) return;
+  if (!(lo > -0.45) || !(hi < 0.45) || !(lo <= 0.0) || !(hi >= 0.0)) return;
   if (!isfinite(Mc) || !isfinite(c.inv_period) || !isfinite(c.t0ref)) return;
   c.phase_c = Mc * Num<double>::inv_two_pi;
   c.wlo = lo;
@@ -112,17 +129,18 @@ __device__ inline void transit_window(BodyC<T>& c, double a, double rstar, doubl
   // stellar radii per cycle.  The list path uses it to put those samples on a list of their own so
   // that whole warps take the constant-node flux code; every warp still checks b < 1 - r itself.
   {
-    const double opec = 1.0 + e * cos(fc);
-    const double r0c = rho * a * (1.0 - e * e) / opec;
-    const double b0 = r0c * fabs(ci) / rstar;
+    const double opec = 1.0 + e * cfc;
+    const double ome2 = 1.0 - e * e;
+    const double r0c = fdiv(rho * a * ome2, opec);
+    const double b0 = fdiv(r0c * fabs(ci), rstar);
     const double rr = fabs((double)c.rr);
-    const double v = Num<double>::two_pi * (rho * a / rstar) * opec / sqrt(1.0 - e * e);
+    const double v = fdiv(Num<double>::two_pi * fdiv(rho * a, rstar) * opec, fsqrt(ome2));
     const double q2 = (1.0 - rr) * (1.0 - rr) - b0 * b0;
     if (rr < 1.0 && b0 < 1.0 - rr && q2 > 0.0 && v > 0.0 && isfinite(v)) {
 #ifndef JXP_WIN_IN_FACTOR
 #define JXP_WIN_IN_FACTOR 0.97
 #endif
-      const double half = JXP_WIN_IN_FACTOR * sqrt(q2) / v;
+      const double half = fdiv(JXP_WIN_IN_FACTOR * fsqrt(q2), v);
       if (half > 0.0 && half < hi && -half > lo) c.win_in = half;
     }
   }
@@ -161,24 +179,41 @@ __device__ __forceinline__ void sky_position_g(const S& e, const S& cw, const S&
 
 // The same from (yD, xD) = (sin f, cos f) D of kepler_reduced_n<N, true>: (x0, y0) = -a (xD, yD).
 template <typename T>
-__device__ __forceinline__ void sky_position_xy(const BodyC<T>& c, T yD, T xD, T& b, T& Z) {
-  const T x0 = c.na * xD, y0 = c.na * yD;
-  const T x1 = jfma(c.cw, x0, -c.sw * y0);       // keplerian.py:568-569
-  const T y1 = jfma(c.sw, x0, c.cw * y0);
-  const T Y = c.ci * y1;                         // :575-576
+__device__ __forceinline__ void sky_position_xy(const BodyC<T>& c, double yD, double xD, double& b, double& Z) {
+  const double x0 = c.na * xD, y0 = c.na * yD;
+  const double x1 = jfma(c.cw, x0, -c.sw * y0);  // keplerian.py:568-569
+  const double y1 = jfma(c.sw, x0, c.cw * y0);
+  const double Y = c.ci * y1;                    // :575-576
   Z = -c.si * y1;
   b = jsqrt(jfma(x1, x1, Y * Y)) * c.inv_rstar;  // light_curves/limb_dark.py:53
 }
 
 template <typename T>
-__device__ __forceinline__ void sky_position(const BodyC<T>& c, T sf, T cf, T& b, T& Z) {
-  const T r0 = jdiv(c.na_ome2, jfma(c.e, cf, T(1)));  // keplerian.py:630
-  const T x0 = r0 * cf, y0 = r0 * sf;
-  const T x1 = jfma(c.cw, x0, -c.sw * y0);       // :568-569
-  const T y1 = jfma(c.sw, x0, c.cw * y0);
-  const T Y = c.ci * y1;                         // :575-576
+__device__ __forceinline__ void sky_position(const BodyC<T>& c, double sf, double cf, double& b, double& Z) {
+  const double r0 = jdiv(c.na_ome2, jfma(c.e, cf, 1.0));  // keplerian.py:630
+  const double x0 = r0 * cf, y0 = r0 * sf;
+  const double x1 = jfma(c.cw, x0, -c.sw * y0);  // :568-569
+  const double y1 = jfma(c.sw, x0, c.cw * y0);
+  const double Y = c.ci * y1;                    // :575-576
   Z = -c.si * y1;
   b = jsqrt(jfma(x1, x1, Y * Y)) * c.inv_rstar;  // light_curves/limb_dark.py:53
+}
+
+// The position stage of one sample: t -> M -> (sin f, cos f) -> (b, Z).  Always double (see BodyC); the fp32
+// mode rounds b and Z once, at the end.
+template <typename T>
+__device__ __forceinline__ void position_stage(const BodyC<T>& c, double tm, T& b, T& Z) {
+  const double Mr = mean_anomaly_reduced(c, tm);
+  double sf, cf, Edummy;
+  if (c.flags & BODY_CIRCULAR) {
+    jsincos(Mr, &sf, &cf);  // keplerian.py:539-540
+  } else {
+    kepler_reduced<double, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
+  }
+  double bd, Zd;
+  sky_position(c, sf, cf, bd, Zd);
+  b = T(bd);
+  Z = T(Zd);
 }
 
 // Register-array element by a runtime index (select chain; keeps the array in registers).
@@ -196,15 +231,8 @@ template <typename T, int ORDER, bool HI = false, int PU = 1>
 __device__ __forceinline__ T eval_in_window(const BodyC<T>& c, const SetC<T>& sc,
                                             const GLTable* __restrict__ tab, double tm,
                                             unsigned& n_ld) {
-  const T Mr = T(mean_anomaly_reduced(c, tm));
-  T sf, cf, Edummy;
-  if (c.flags & BODY_CIRCULAR) {
-    jsincos(Mr, &sf, &cf);  // keplerian.py:539-540
-  } else {
-    kepler_reduced<T, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
-  }
   T b, Z;
-  sky_position(c, sf, cf, b, Z);
+  position_stage(c, tm, b, Z);
   if (!(Z > T(0)) || (b >= c.onepr)) return T(0);  // limb_dark.py:58 mask, :60 no_occ
   ++n_ld;
   T s0, s1, s2;

@@ -138,19 +138,19 @@ __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
   c.inv_period = 1.0 / c.period;
   c.flags = 0;
   c.pad = 0;
-  c.e = T(e.v);
-  c.ome = T(1.0 - e.v);
-  c.ope = T(1.0 + e.v);
-  c.s1me2 = T(sqrt((1.0 - e.v) * (1.0 + e.v)));
-  c.inv_ope = T(1.0 / (1.0 + e.v));
-  c.cw = T(cw.v);
-  c.sw = T(sw.v);
-  c.ci = T(ci.v);
-  c.si = T(si.v);
+  c.e = e.v;
+  c.ome = 1.0 - e.v;
+  c.ope = 1.0 + e.v;
+  c.s1me2 = sqrt((1.0 - e.v) * (1.0 + e.v));
+  c.inv_ope = 1.0 / (1.0 + e.v);
+  c.cw = cw.v;
+  c.sw = sw.v;
+  c.ci = ci.v;
+  c.si = si.v;
   const D na = -(a * ome2);
-  c.na_ome2 = T(na.v);
-  c.na = T(-a.v);
-  c.inv_rstar = T(1.0 / rstar);
+  c.na_ome2 = na.v;
+  c.na = -a.v;
+  c.inv_rstar = 1.0 / rstar;
   const double rr = radius / rstar;
   c.rr = T(rr);
   c.onepr = T(1.0 + fabs(rr));
@@ -201,11 +201,14 @@ __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
   for (int i = 0; i < NO; ++i) Md[i] = T(-k * bd.tref.d[i]);
   Md[0] += T(-M / c.period);
   Md[1] += T(-k);
-  const T Mr = T(mod_two_pi(M));
-  T sf, cf, Edummy;
-  kepler_reduced<T, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
+  // the primal of the position stage is always double (BodyC, jxp_orbit.cuh); the tangents run in T
+  const double Mr = mod_two_pi(M);
+  double sf_p, cf_p, Edummy;
+  kepler_reduced<double, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf_p, cf_p, Edummy);
+  const T sf = T(sf_p), cf = T(cf_p);
+  const T e_t = T(c.e), inv_rstar_t = T(c.inv_rstar);
   // kepler.py:64-79
-  const T ecosf = c.e * cf;
+  const T ecosf = e_t * cf;
   const T opc = T(1) + ecosf;
   const T dfdM = opc * opc * bd.inv_ome2_32;
   const T dfde = (T(2) + ecosf) * sf * bd.inv_ome2;
@@ -219,9 +222,18 @@ __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
     sfd.d[i] = cf * fdot;
     cfd.d[i] = -sf * fdot;
   }
-  const D ed = D::seed(c.e, 2);
+  const D ed = D::seed(e_t, 2);
   D b, Z;
-  sky_position_g<D, T>(ed, bd.cw, bd.sw, bd.ci, bd.si, bd.na_ome2, c.inv_rstar, sfd, cfd, b, Z);
+  sky_position_g<D, T>(ed, bd.cw, bd.sw, bd.ci, bd.si, bd.na_ome2, inv_rstar_t, sfd, cfd, b, Z);
+  if (sizeof(T) < sizeof(double)) {
+    // fp32 mode: (x0, y0) = r0 (cos f, sin f) are of order a / R* ~ 15 stellar radii and cancel to O(1) in
+    // the rotation; in float that alone costs 1e-6 of a stellar radius in b.  The primal comes from the
+    // double position stage, the float chain above supplies the tangents.
+    double bp, Zp;
+    sky_position(c, sf_p, cf_p, bp, Zp);
+    b.v = T(bp);
+    Z.v = T(Zp);
+  }
   if (!(Z.v > T(0)) || (b.v >= c.onepr)) return false;
   typedef Dual<T, 2> L;
   L s0, s1, s2;
@@ -234,7 +246,7 @@ __device__ __forceinline__ bool eval_sample_partials(const BodyD<T>& bd,
   flux = f.v;
 #pragma unroll
   for (int i = 0; i < NO; ++i) part[i] = f.d[0] * b.d[i];
-  part[5] = f.d[1] * c.inv_rstar;
+  part[5] = f.d[1] * inv_rstar_t;
   part[6] = s0.v * bd.dg[0][0] + s1.v * bd.dg[1][0] + s2.v * bd.dg[2][0];
   part[7] = s0.v * bd.dg[0][1] + s1.v * bd.dg[1][1] + s2.v * bd.dg[2][1];
   return true;

@@ -39,18 +39,18 @@ __device__ __noinline__ void sys_prep_body(int i, const double* __restrict__ bod
   }
   const double a = p[JXP_BODY_SEMIMAJOR];
   const double rstar = p[JXP_BODY_CENTRAL_RADIUS];
-  c.e = T(e);
-  c.ome = T(1.0 - e);
-  c.ope = T(1.0 + e);
-  c.s1me2 = T(sqrt((1.0 - e) * (1.0 + e)));
-  c.inv_ope = T(1.0 / (1.0 + e));
-  c.cw = T(p[JXP_BODY_COS_OMEGA]);
-  c.sw = T(p[JXP_BODY_SIN_OMEGA]);
-  c.ci = T(p[JXP_BODY_COS_INCL]);
-  c.si = T(p[JXP_BODY_SIN_INCL]);
-  c.na_ome2 = T(-a * (1.0 - e * e));
-  c.na = T(-a);
-  c.inv_rstar = T(1.0 / rstar);
+  c.e = e;
+  c.ome = 1.0 - e;
+  c.ope = 1.0 + e;
+  c.s1me2 = sqrt((1.0 - e) * (1.0 + e));
+  c.inv_ope = 1.0 / (1.0 + e);
+  c.cw = p[JXP_BODY_COS_OMEGA];
+  c.sw = p[JXP_BODY_SIN_OMEGA];
+  c.ci = p[JXP_BODY_COS_INCL];
+  c.si = p[JXP_BODY_SIN_INCL];
+  c.na_ome2 = -a * (1.0 - e * e);
+  c.na = -a;
+  c.inv_rstar = 1.0 / rstar;
   const double rr = p[JXP_BODY_RADIUS] / rstar;
   c.rr = T(rr);
   c.onepr = T(1.0 + fabs(rr));

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256)
 k_interp_periodic(const double* __restrict__ xp, const T* __restrict__ fp, int n, int n_cols, double period,
                   double time_transit, const double* __restrict__ t, int64_t n_times, T* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const double eps = 2.220446049250313e-16;
+  // jnp.interp's flat-segment guard: |dx| <= np.spacing(np.finfo(xp.dtype).eps), xp in float64
+  const double eps = 4.930380657631324e-32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_times; i += stride) {
     // transforms.py:167-171, then the `x % period` of jnp.interp
     const double tw = pymod(t[i] - time_transit + 0.5 * period, period) + 0.5 * period + time_transit;

@@ -48,7 +48,6 @@ static_assert(WK_T0 % 2 == 0 && WK_PERIOD % 2 == 0 && WK_E % 2 == 0 && WK_OPE % 
                   WK_K1 % 2 == 0 && WK_ZS % 2 == 0 && WK_G0 % 2 == 0,
               "pairs read as double2");
 static_assert(WK_NFIELDS <= WALK_REC, "record size");
-constexpr unsigned WKF_CIRCULAR = 1u, WKF_SLOW_STARTER = 2u;
 
 struct WalkSet {
   unsigned seg_off;   // first segment of the inside list; the edge list follows its sentinel
@@ -97,13 +96,13 @@ struct WalkArgs {
   double* loglike;
 };
 
-constexpr unsigned long long WK_OVERFLOW = 2ull;
+constexpr unsigned long long WK_OVERFLOW = 2ull, WK_UNSUPPORTED = 4ull;
 
 // --------------------------------------------------------------------------------------------
 // plan
 // --------------------------------------------------------------------------------------------
 template <int CH, bool LL>
-__global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkArgs a) {
+__global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ WalkArgs a) {
   if ((int)blockIdx.x >= a.n_plan_ctas) {
     const int cta = (int)blockIdx.x - a.n_plan_ctas;
     if (LL) {
@@ -165,10 +164,11 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
     r[WK_G0] = sc.g0;
     r[WK_G1] = sc.g1;
     r[WK_G2] = sc.g2;
-    unsigned f = (c.flags & BODY_CIRCULAR) ? WKF_CIRCULAR : 0u;
-    if (!(c.ome > 1e-5)) f |= WKF_SLOW_STARTER;
-    f |= (unsigned)sc.lmax << 8;
+    const unsigned f = (unsigned)sc.lmax << 8;
     r[WK_FLAGS] = __longlong_as_double((long long)f);
+    // 1 - e <= 1e-5: the float starter and the one-division correction are not good there (and such a body
+    // has no provable transit window anyway): the whole call goes to the window-test kernels
+    if (!(c.ome > 1e-5)) atomicOr(a.state + 3, WK_UNSUPPORTED);
 #pragma unroll
     for (int k = WK_NFIELDS; k < WALK_REC; ++k) r[k] = 0.0;
   }
@@ -390,12 +390,15 @@ __global__ void __launch_bounds__(256) k_walk_plan(const __grid_constant__ WalkA
 #endif
 
 // Kepler solve for N mean anomalies of ONE orbit (e, 1 - e, 1 + e, sqrt(1 - e^2), 1 / (1 + e) warp-uniform):
-// core/kepler.py:28-56, 82-108 with the re-arrangements of kepler_reduced_n<N, XY, ONE_DIV> (jxp_math.cuh);
-// returns (sin f, cos f) D, D = (1 - e) c^2 + (1 + e) s^2.
+// core/kepler.py:28-56, 82-108 with the re-arrangements of kepler_reduced_n<N, XY, ONE_DIV> (jxp_math.cuh):
+// Markley starter in float (1 - e > 1e-5: the plan sends anything else to the window-test kernels), half
+// angle from a degree-8 sin / cos pair without range reduction, the three nested corrections carried as
+// fractions (one division), half-angle rotation by dE / 2.  Returns (sin f, cos f) D, D = (1 - e) c^2 +
+// (1 + e) s^2.  A circular body (keplerian.py:539-540: f = M) is the e = 0 case: the correction then lands
+// on E = M exactly (f1 = 1, f2 = f3 = 0) and the half-angle products give (sin M, cos M).
 template <int N>
 __device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, double ome, double ope,
-                                            double s1me2, double inv_ope, bool slow, double (&yD)[N],
-                                            double (&xD)[N]) {
+                                            double s1me2, double inv_ope, double (&yD)[N], double (&xD)[N]) {
   const double pi = Num<double>::pi;
   bool high[N];
   double M[N], E0[N], hs[N], hc[N];
@@ -404,58 +407,36 @@ __device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, dou
     high[q] = Mr[q] > pi;
     M[q] = high[q] ? Num<double>::two_pi - Mr[q] : Mr[q];
   }
-  if (!slow) {
-    const float ef = (float)e, omef = (float)ome, iopef = (float)inv_ope;
+  const float ef = (float)e, omef = (float)ome, iopef = (float)inv_ope;
 #pragma unroll
-    for (int q = 0; q < N; ++q) E0[q] = (double)kepler_starter_t<float>((float)M[q], ef, omef, iopef);
-  } else {
-#pragma unroll
-    for (int q = 0; q < N; ++q) E0[q] = kepler_starter_t<double>(M[q], e, ome, inv_ope);
-  }
+  for (int q = 0; q < N; ++q) E0[q] = (double)kepler_starter_t<float>((float)M[q], ef, omef, iopef);
   // E0 / 2 lies in [0, pi / 2] (to the starter's 1e-6): no range reduction
 #pragma unroll
   for (int q = 0; q < N; ++q) fsincos_q1(0.5 * E0[q], &hs[q], &hc[q]);
-  double f0[N], num[N], den[N], dE[N];
-  if (!slow) {
-    // d3 -> d4 -> dE of kepler.py:101-107 carried as fractions: one division (see kepler_reduced_n)
+  double num[N], den[N], dE[N];
+  // d3 -> d4 -> dE of kepler.py:101-107 carried as fractions: one division (see kepler_reduced_n)
 #pragma unroll
-    for (int q = 0; q < N; ++q) {
-      const double sinE = 2.0 * hs[q] * hc[q];
-      const double cE = 2.0 * hs[q] * hs[q];
-      const double sE = E0[q] - sinE;
-      f0[q] = fma(e, sE, fma(E0[q], ome, -M[q]));
-      const double f1 = fma(e, cE, ome);
-      const double f2 = e * sinE;
-      const double f3 = 1.0 - f1;
-      const double N3 = -f0[q] * f1;
-      const double D3 = fma(-0.5 * f0[q], f2, f1 * f1);
-      const double D32 = D3 * D3;
-      const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
-      const double D4 = fma(N3, fma(hf2, D3, N3 * f36), f1 * D32);
-      const double N4 = -f0[q] * D32;
-      const double D42 = D4 * D4;
-      const double N42 = N4 * N4;
-      den[q] = fma(D42, fma(f1, D4, hf2 * N4), N42 * fma(f36, D4, -(f2 * (1.0 / 24.0)) * N4));
-      num[q] = -f0[q] * (D42 * D4);
-    }
-#pragma unroll
-    for (int q = 0; q < N; ++q) dE[q] = fdiv(num[q], den[q]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-      const double sinE = 2.0 * hs[q] * hc[q];
-      const double cE = 2.0 * hs[q] * hs[q];
-      const double sE = E0[q] - sinE;
-      f0[q] = fma(e, sE, fma(E0[q], ome, -M[q]));
-      const double f1 = fma(e, cE, ome);
-      const double f2 = e * sinE;
-      const double f3 = 1.0 - f1;
-      const double d3 = fdiv(-f0[q] * f1, fma(-0.5 * f0[q], f2, f1 * f1));
-      const double d4 = fdiv(-f0[q], fma(d3 * d3, f3 * (1.0 / 6.0), fma(0.5 * d3, f2, f1)));
-      const double d42 = d4 * d4;
-      dE[q] = fdiv(-f0[q], fma(-d42 * d4, f2 * (1.0 / 24.0), fma(d42, f3 * (1.0 / 6.0), fma(0.5 * d4, f2, f1))));
-    }
+  for (int q = 0; q < N; ++q) {
+    const double sinE = 2.0 * hs[q] * hc[q];
+    const double cE = 2.0 * hs[q] * hs[q];
+    const double sE = E0[q] - sinE;
+    const double f0 = fma(e, sE, fma(E0[q], ome, -M[q]));
+    const double f1 = fma(e, cE, ome);
+    const double f2 = e * sinE;
+    const double f3 = 1.0 - f1;
+    const double N3 = -f0 * f1;
+    const double D3 = fma(-0.5 * f0, f2, f1 * f1);
+    const double D32 = D3 * D3;
+    const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
+    const double D4 = fma(N3, fma(hf2, D3, N3 * f36), f1 * D32);
+    const double N4 = -f0 * D32;
+    const double D42 = D4 * D4;
+    const double N42 = N4 * N4;
+    den[q] = fma(D42, fma(f1, D4, hf2 * N4), N42 * fma(f36, D4, -(f2 * (1.0 / 24.0)) * N4));
+    num[q] = -f0 * (D42 * D4);
   }
+#pragma unroll
+  for (int q = 0; q < N; ++q) dE[q] = fdiv(num[q], den[q]);
   const double two_s = 2.0 * s1me2;
 #pragma unroll
   for (int q = 0; q < N; ++q) {
@@ -510,36 +491,34 @@ __device__ __forceinline__ bool walk_eval_active(const WalkEvalArgs& a, int lane
 
 // positions p0 + 32 h + lane of a chunk -> sample indices, from the chunk's segment window `win` (shared
 // memory; entry j = segment segk + j: first position | first sample << 32, first positions strictly
-// increasing, the list's sentinel = first position past the list).  Every segment that starts inside the
-// chunk sets one bit of a position mask (warp-wide OR); a position's segment is the number of such starts
-// at or below it.
+// increasing, the list's sentinel = first position past the list).  The window holds 32 N segments: every
+// segment is at least one position long, so no chunk of 32 N positions needs more.  Every segment that
+// starts inside the chunk sets one bit of a position mask (warp-wide OR); a position's segment is the
+// number of such starts at or below it.  No loop, no branch.
 template <int N>
-__device__ __forceinline__ void walk_indices(const WalkEvalArgs& a, const uint4& ent,
-                                             const unsigned long long* __restrict__ win, int lane,
-                                             unsigned (&idx)[N], bool (&have)[N]) {
-  const unsigned p0 = ent.y, segk = ent.z;
+__device__ __forceinline__ void walk_indices(const uint4& ent, const unsigned long long* __restrict__ win,
+                                             int lane, unsigned (&idx)[N], bool (&have)[N]) {
+  const unsigned p0 = ent.y;
   const unsigned valid = (ent.w >> 8) & 0xffffu, nrem = ent.w & 255u;
-  const unsigned off = (lane >= 1 && lane < (int)nrem) ? (unsigned)win[lane] - p0 : 0xffffffffu;  // >= 1 for real ones
-  unsigned mask[N];
+  unsigned bits[N];
 #pragma unroll
-  for (int h = 0; h < N; ++h)
-    mask[h] = __reduce_or_sync(0xffffffffu, (off >> 5) == (unsigned)h ? (1u << (off & 31u)) : 0u);
+  for (int h = 0; h < N; ++h) bits[h] = 0u;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const unsigned j = 32u * n + lane;
+    const unsigned off = (j >= 1u && j < nrem) ? (unsigned)win[j] - p0 : 0xffffffffu;  // >= 1 for real ones
+#pragma unroll
+    for (int h = 0; h < N; ++h) bits[h] |= (off >> 5) == (unsigned)h ? (1u << (off & 31u)) : 0u;
+  }
   unsigned below = 0;
 #pragma unroll
   for (int h = 0; h < N; ++h) {
-    const unsigned p = p0 + 32u * h + lane;
+    const unsigned mask = __reduce_or_sync(0xffffffffu, bits[h]);
     have[h] = 32u * h + lane < valid;
-    const unsigned j = below + __popc(mask[h] & (0xffffffffu >> (31 - lane)));
-    below += __popc(mask[h]);
-    unsigned long long sv = win[j < 31u ? j : 31u];
-    if (j >= 31u && nrem > 32u && have[h]) {
-      // more than 31 segments start inside one chunk (runs of one or two samples): walk the table itself;
-      // the list's sentinel (> p for a valid position) ends the search
-      unsigned k = segk + 31u;
-      while ((unsigned)a.seg[k + 1u] <= p) ++k;
-      sv = a.seg[k];
-    }
-    idx[h] = have[h] ? (unsigned)(sv >> 32) + (p - (unsigned)sv) : 0u;
+    const unsigned j = below + __popc(mask & (0xffffffffu >> (31 - lane)));
+    below += __popc(mask);
+    const unsigned long long sv = win[j];
+    idx[h] = have[h] ? (unsigned)(sv >> 32) + (p0 + 32u * h + lane - (unsigned)sv) : 0u;
   }
 }
 
@@ -654,19 +633,20 @@ constexpr unsigned WK_RMAX = 8;   // chunks per claim (upper bound)
 constexpr unsigned WK_LOG = 32;   // claims a warp remembers before it signals their completion
 template <int N>
 struct WalkWarpSmem {
-  double rec[2][WALK_REC];         // set record of the chunk being evaluated / of the next one
-  unsigned long long seg[2][32];   // segment window of the next chunk / of the one after
-  uint4 ent[3][WK_RMAX];           // chunk entries of the current claim, the next one, the one after
-  double tb[32 * N];               // time stamps of the next chunk
-  double yb[2][32 * N];            // observed flux, 1 / sigma of this chunk / of the next one
+  double rec[2][WALK_REC];            // set record of the chunk being evaluated / of the next one
+  unsigned long long seg[2][32 * N];  // segment window of the next chunk / of the one after
+  uint4 ent[3][WK_RMAX];              // chunk entries of the current claim, the next one, the one after
+  double tb[32 * N];                  // time stamps of the next chunk
+  double yb[2][32 * N];               // observed flux, 1 / sigma of this chunk / of the next one
   double wb[2][32 * N];
-  unsigned ib[2][32 * N];          // sample indices (0xffffffff: padding)
-  unsigned long long log[WK_LOG];  // finished claims: first slot | chunks << 32
+  unsigned ib[2][32 * N];             // sample indices (0xffffffff: padding)
+  unsigned long long log[WK_LOG];     // finished claims: first slot | chunks << 32
 };
 
 template <int N, bool FLUX>
 __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_constant__ WalkEvalArgs a) {
   constexpr int CH = 32 * N;
+  static_assert(CH <= 255, "segments left in a window are an 8-bit field of the chunk entry");
   __shared__ __align__(16) WalkWarpSmem<N> s_all[4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (!walk_eval_active(a, lane)) return;
@@ -686,7 +666,7 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     const unsigned r = remaining / (nw * 2u);
     return r < 1u ? 1u : (r > WK_RMAX ? WK_RMAX : r);
   };
-  auto claim_issue = [&]() -> unsigned long long {  // lane 0 asks; the answer is read later (latency hidden)
+  auto claim_issue = [&]() -> unsigned long long {  // lane 0 asks; the answer is read a claim later
     unsigned long long r = 0ull;
     if (lane == 0) {
       if (!a_done) {
@@ -721,15 +701,19 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   auto stage_entries = [&](int buf, unsigned slot0, unsigned cnt) {
     if ((unsigned)lane < cnt) cp_async16(&sm.ent[buf][lane], a.chunk + slot0 + lane);
   };
-  auto stage_rec_seg = [&](int buf, const uint4& e) {  // the chunk's set record and its first 32 segments
+  auto stage_rec_seg = [&](int buf, const uint4& e) {  // the chunk's set record and its segment window
     cp_async8(&sm.rec[buf][lane], a.rec + (size_t)e.x * WALK_REC + lane);
-    const int nr = (int)(e.w & 255u);
-    cp_async8(&sm.seg[buf][lane], a.seg + e.z + (unsigned)(lane < nr ? lane : nr - 1));
+    const unsigned nr = e.w & 255u;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const unsigned j = 32u * n + lane;
+      cp_async8(&sm.seg[buf][j], a.seg + e.z + (j < nr ? j : nr - 1u));
+    }
   };
   auto stage_samples = [&](int buf, const uint4& e, int segbuf) {  // indices -> t, y, 1 / sigma of the chunk
     unsigned idx[N];
     bool have[N];
-    walk_indices<N>(a, e, sm.seg[segbuf], lane, idx, have);
+    walk_indices<N>(e, sm.seg[segbuf], lane, idx, have);
 #pragma unroll
     for (int h = 0; h < N; ++h) {
       cp_async8(&sm.tb[32 * h + lane], a.t + idx[h]);
@@ -752,16 +736,16 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     if ((unsigned)lane < nlog) {
       const unsigned long long lg = sm.log[lane];
       const unsigned slot0 = (unsigned)lg, cnt = (unsigned)(lg >> 32);
-      unsigned sets[WK_RMAX];
+      unsigned sets[WK_RMAX + 1];
 #pragma unroll
       for (unsigned k = 0; k < WK_RMAX; ++k) sets[k] = k < cnt ? a.chunk[slot0 + k].x : 0xffffffffu;
+      sets[WK_RMAX] = 0xffffffffu;
       unsigned run = 0;
 #pragma unroll
       for (unsigned k = 0; k < WK_RMAX; ++k) {
         if (k < cnt) {
           ++run;
-          const unsigned nxt = k + 1u < WK_RMAX ? sets[k + 1u < WK_RMAX ? k + 1u : k] : 0xffffffffu;
-          if (k + 1u == cnt || nxt != sets[k]) {
+          if (sets[k + 1u] != sets[k]) {  // (entries past the claim hold 0xffffffff)
             const unsigned prev = atomicAdd(&a.wset_rw[sets[k]].done, run);
             if (prev + run == a.wset[sets[k]].n_chunks) walk_finish_set<CH>(a, sets[k]);
             run = 0;
@@ -774,9 +758,11 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   };
 
   // ---- prologue: the first two claims, the first chunk's inputs (latencies exposed once per warp)
-  unsigned cur_slot0, cur_cnt, nxt_slot0 = 0, nxt_cnt = 0;
+  unsigned cur_slot0, cur_cnt, nxt_slot0 = 0, nxt_cnt = 0, nn_slot0 = 0, nn_cnt = 0;
   if (!claim_decode(claim_issue(), cur_slot0, cur_cnt)) return;
   bool nxt_valid = claim_decode(claim_issue(), nxt_slot0, nxt_cnt);
+  bool nn_valid = false;
+  unsigned long long raw_nn = nxt_valid ? claim_issue() : 0ull;  // the claim after next: read a claim later
   stage_entries(0, cur_slot0, cur_cnt);
   if (nxt_valid) stage_entries(1, nxt_slot0, nxt_cnt);
   cp_async_wait_all();
@@ -787,134 +773,114 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   stage_samples(0, sm.ent[0][0], 0);
   int eb = 0, rb = 0, pb = 0;
   unsigned k = 0;
-  unsigned long long raw_nn = 0ull;
-  unsigned nn_slot0 = 0, nn_cnt = 0;  // the claim after next (known from the middle of a claim's first chunk)
-  bool nn_valid = false;
+  double pend_sum = 0.0;        // the previous chunk's chi^2 terms, one per lane: reduced while this chunk's
+  unsigned pend_slot = 0;       // Kepler code runs (the shuffle tree is pure latency)
+  bool pend = false;
 
   for (;;) {
-    // ================= top: this chunk's inputs have landed; start the next chunk's record / segments
+    // ================= top: this chunk's inputs have landed; the next chunk's record / segments start to fly
     cp_async_wait_all();
     __syncwarp();
     const uint4 e = sm.ent[eb][k];
-    if (k == 0u && nxt_valid) raw_nn = claim_issue();  // the claim after next: answer read at mid-chunk
     const bool same_claim = k + 1u < cur_cnt;
     const bool has_next_chunk = same_claim || nxt_valid;
     const int eb_next = eb == 2 ? 0 : eb + 1;
-    uint4 en = e;
-    if (has_next_chunk) {
-      en = same_claim ? sm.ent[eb][k + 1u] : sm.ent[eb_next][0];
-      stage_rec_seg(rb ^ 1, en);
-    }
+    // (without a next chunk this one is staged again: harmless, and the code stays free of branches)
+    const uint4 en = same_claim ? sm.ent[eb][k + 1u] : (nxt_valid ? sm.ent[eb_next][0] : e);
+    stage_rec_seg(rb ^ 1, en);
     const double* rec = sm.rec[rb];
     const double2* rec2 = reinterpret_cast<const double2*>(rec);
     const unsigned set = e.x;
     const unsigned valid = (e.w >> 8) & 0xffffu;
     const bool inside_list = (e.w >> 31) == 0u;
-    double tot[N], bq[N];
-    bool intr[N], fast[N], want_gen = false, want_fast = false;
-    int lmax = 0;
+    if (!FLUX) {
+      // the previous chunk's partial sum: fixed shuffle tree, one store
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pend_sum += __shfl_xor_sync(0xffffffffu, pend_sum, o);
+      if (pend && lane == 0) a.part[pend_slot] = pend_sum;
+    }
+    // ---- t -> mean anomaly (keplerian.py:538, kepler.py:31), the reference's operation order; the
+    // division by the period is a multiplication by fl(1 / P) with one residual correction
+    const double2 tt = rec2[WK_T0 / 2], pp = rec2[WK_PERIOD / 2];
+    const int lmax = (int)((unsigned)__double_as_longlong(rec[WK_FLAGS]) >> 8);
+    double Mr[N];
 #pragma unroll
     for (int h = 0; h < N; ++h) {
-      tot[h] = 0.0;
-      bq[h] = 2.0;
-      intr[h] = fast[h] = false;
+      const double x = (sm.tb[32 * h + lane] - tt.x) - tt.y;
+      const double num = Num<double>::two_pi * x;
+      const double q = num * pp.y;
+      const double r = fma(-pp.x, q, num);
+      Mr[h] = mod_two_pi(fma(r, pp.y, q));
     }
-    if (valid != 0u) {
-      // ---- t -> mean anomaly (keplerian.py:538, kepler.py:31), the reference's operation order; the
-      // division by the period is a multiplication by fl(1 / P) with one residual correction
-      const double2 tt = rec2[WK_T0 / 2], pp = rec2[WK_PERIOD / 2];
-      const unsigned flags = (unsigned)__double_as_longlong(rec[WK_FLAGS]);
-      lmax = (int)(flags >> 8);
-      double Mr[N];
-#pragma unroll
-      for (int h = 0; h < N; ++h) {
-        const double x = (sm.tb[32 * h + lane] - tt.x) - tt.y;
-        const double num = Num<double>::two_pi * x;
-        const double q = num * pp.y;
-        const double r = fma(-pp.x, q, num);
-        Mr[h] = mod_two_pi(fma(r, pp.y, q));
-      }
-      double yD[N], xD[N];
+    double yD[N], xD[N];
 #if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 1)
-      // measurement only: no Kepler solve
+    // measurement only: no Kepler solve
 #pragma unroll
-      for (int h = 0; h < N; ++h) {
-        yD[h] = Mr[h] * 1e-3;
-        xD[h] = 1.0 - Mr[h] * 1e-4;
-      }
-      if (true) {
-      } else if (false) {
+    for (int h = 0; h < N; ++h) {
+      yD[h] = Mr[h] * 1e-3;
+      xD[h] = 1.0 - Mr[h] * 1e-4;
+    }
 #else
-      if (flags & WKF_CIRCULAR) {
+    {
+      const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
+      kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], yD, xD);
+    }
 #endif
+    // ---- sky position (keplerian.py:568-576, 630-632; light_curves/limb_dark.py:53): with
+    // (x0, y0) = -a (xD, yD) the constants -a / R*, cos i and -sin i are folded into k1, k2, zs
+    const double2 ws2 = rec2[WK_CW / 2], kk = rec2[WK_K1 / 2], zo = rec2[WK_ZS / 2];
+    const double rr = rec[WK_RR];
+    const double ar = fabs(rr);
+    const bool r_ok = (ar < 1.0) && (ar >= 2e-6);  // what ld_inside_u needs of the set ...
+    const double b_lim = (1.0 - ar) - 4e-15;       // ... and of the sample
+    double tot[N], bq[N];
+    bool intr[N], fast[N], want_gen = false, want_fast = false;
 #pragma unroll
-        for (int h = 0; h < N; ++h) fsincos(Mr[h], &yD[h], &xD[h]);  // keplerian.py:539-540
-      } else {
-        const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
-        kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], (flags & WKF_SLOW_STARTER) != 0u, yD, xD);
-      }
-      // ---- sky position (keplerian.py:568-576, 630-632; light_curves/limb_dark.py:53): with
-      // (x0, y0) = -a (xD, yD) the constants -a / R*, cos i and -sin i are folded into k1, k2, zs
-      const double2 ws2 = rec2[WK_CW / 2], kk = rec2[WK_K1 / 2], zo = rec2[WK_ZS / 2];
-      const double ar = fabs(rec[WK_RR]);
-      const bool r_ok = (ar < 1.0) && (ar >= 2e-6);      // what ld_inside_u needs of the set ...
-      const double b_lim = (1.0 - ar) - 4e-15;            // ... and of the sample
-#pragma unroll
-      for (int h = 0; h < N; ++h) {
-        const double u1 = fma(ws2.x, xD[h], -ws2.y * yD[h]);
-        const double u2 = fma(ws2.y, xD[h], ws2.x * yD[h]);
-        const double v1 = kk.x * u1, v2 = kk.y * u2;
-        bq[h] = fsqrt(fma(v1, v1, v2 * v2));
-        intr[h] = (32u * h + lane < valid) && (zo.x * u2 > 0.0) && !(bq[h] >= zo.y);
-        // the flux code an item gets depends on the item alone: inside list AND b safely below 1 - r
-        fast[h] = inside_list && (bq[h] < b_lim) && r_ok;
-        n_ld += intr[h] ? 1u : 0u;
-        n_fast += (intr[h] && fast[h]) ? 1u : 0u;
-        want_gen = want_gen || (intr[h] && !fast[h]);
-        want_fast = want_fast || (intr[h] && fast[h]);
-      }
-      want_gen = __any_sync(0xffffffffu, want_gen);
-      want_fast = __any_sync(0xffffffffu, want_fast);
+    for (int h = 0; h < N; ++h) {
+      const double u1 = fma(ws2.x, xD[h], -ws2.y * yD[h]);
+      const double u2 = fma(ws2.y, xD[h], ws2.x * yD[h]);
+      const double v1 = kk.x * u1, v2 = kk.y * u2;
+      bq[h] = fsqrt(fma(v1, v1, v2 * v2));
+      intr[h] = (32u * h + lane < valid) && (zo.x * u2 > 0.0) && !(bq[h] >= zo.y);
+      // the flux code an item gets depends on the item alone: inside list AND b safely below 1 - r
+      fast[h] = inside_list && (bq[h] < b_lim) && r_ok;
+      n_ld += intr[h] ? 1u : 0u;
+      n_fast += (intr[h] && fast[h]) ? 1u : 0u;
+      want_gen = want_gen || (intr[h] && !fast[h]);
+      want_fast = want_fast || (intr[h] && fast[h]);
+      tot[h] = 0.0;
     }
-    // ================= mid: the claim after next becomes known; the next chunk's samples start to fly
-    if (k == 0u && nxt_valid) {
-      nn_valid = claim_decode(raw_nn, nn_slot0, nn_cnt);
-      if (nn_valid) stage_entries(eb_next == 2 ? 0 : eb_next + 1, nn_slot0, nn_cnt);
-    }
-    if (has_next_chunk) {
-      cp_async_wait_all();
-      __syncwarp();
-      stage_samples(pb ^ 1, en, rb ^ 1);
-    }
+    want_gen = __any_sync(0xffffffffu, want_gen);
+    want_fast = __any_sync(0xffffffffu, want_fast);
+    // ================= mid: the next chunk's segment window has landed -> its samples start to fly
+    cp_async_wait_all();
+    __syncwarp();
+    stage_samples(pb ^ 1, en, rb ^ 1);
     // ================= flux (core/limb_dark.py:19-196)
+    const double2 gg = rec2[WK_G0 / 2];
+    const double g2 = rec[WK_G2];
 #if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 2)
     // measurement only: no flux code
 #pragma unroll
     for (int h = 0; h < N; ++h) tot[h] = intr[h] ? bq[h] * 1e-3 : 0.0;
-    if (false) {
 #else
-    if (want_fast || want_gen) {
-#endif
-      const double rr = rec[WK_RR];
-      const double2 gg = rec2[WK_G0 / 2];
-      const double g2 = rec[WK_G2];
-      if (want_fast) {
-        double f[N];
-        ld_inside_u<N>(bq, fabs(rr), lmax, gg.x, gg.y, g2, f);  // constant node cosines, no atan2
+    if (want_fast) {
+      double f[N];
+      ld_inside_u<N>(bq, ar, lmax, gg.x, gg.y, g2, f);  // constant node cosines, no atan2, no guards
 #pragma unroll
-        for (int h = 0; h < N; ++h)
-          if (intr[h] && fast[h]) tot[h] = f[h];
-      }
-      if (want_gen) {
-        double rq[N], s0[N], s1v[N], s2[N];
-#pragma unroll
-        for (int h = 0; h < N; ++h) rq[h] = rr;
-        ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
-#pragma unroll
-        for (int h = 0; h < N; ++h)
-          if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
-      }
+      for (int h = 0; h < N; ++h)
+        if (intr[h] && fast[h]) tot[h] = f[h];
     }
+    if (want_gen) {
+      double rq[N], s0[N], s1v[N], s2[N];
+#pragma unroll
+      for (int h = 0; h < N; ++h) rq[h] = rr;
+      ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
+#pragma unroll
+      for (int h = 0; h < N; ++h)
+        if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
+    }
+#endif
     // ================= end: outputs of this chunk
     if (FLUX) {
       // rows were zeroed before the launch; positions of different items are disjoint
@@ -932,23 +898,24 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
       double csum = 0.0;
 #pragma unroll
       for (int h = 0; h < N; ++h) {
-        double dchi = 0.0;
-        if (tot[h] != 0.0) {
-          const double wv = sm.wb[pb][32 * h + lane];
-          const double r0 = (sm.yb[pb][32 * h + lane] - 1.0) * wv;
-          const double mw = tot[h] * wv;
-          dchi = (-mw) * (2.0 * r0 - mw);
-        }
-        csum += dchi;
+        const double wv = sm.wb[pb][32 * h + lane];
+        const double r0 = (sm.yb[pb][32 * h + lane] - 1.0) * wv;
+        const double mw = tot[h] * wv;
+        csum += (tot[h] != 0.0) ? (-mw) * (2.0 * r0 - mw) : 0.0;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-      if (lane == 0) a.part[cur_slot0 + k] = csum;
+      pend_sum = csum;
+      pend_slot = cur_slot0 + k;
+      pend = true;
     }
-    // ================= advance
-    if (has_next_chunk) {
-      rb ^= 1;
-      pb ^= 1;
+    // ================= advance; claims are looked up two ahead (the atomic's answer is read a claim later)
+    rb ^= 1;
+    pb ^= 1;
+    if (k == 0u && nxt_valid) {
+      nn_valid = claim_decode(raw_nn, nn_slot0, nn_cnt);
+      if (nn_valid) {
+        stage_entries(eb_next == 2 ? 0 : eb_next + 1, nn_slot0, nn_cnt);
+        raw_nn = claim_issue();
+      }
     }
     if (same_claim) {
       ++k;
@@ -956,7 +923,15 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     }
     if (!FLUX) {
       if (lane == 0) sm.log[nlog] = (unsigned long long)cur_slot0 | ((unsigned long long)cur_cnt << 32);
-      if (++nlog == WK_LOG) flush_log();
+      if (++nlog == WK_LOG || !nxt_valid) {
+        // the last chunk's partial sum has to be in memory before its claim is reported
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pend_sum += __shfl_xor_sync(0xffffffffu, pend_sum, o);
+        if (pend && lane == 0) a.part[pend_slot] = pend_sum;
+        pend = false;
+        pend_sum = 0.0;
+        flush_log();
+      }
     }
     if (!nxt_valid) break;
     cur_slot0 = nxt_slot0;
@@ -974,7 +949,6 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     atomicAdd(a.counters + 1, (unsigned long long)n_ld);
     atomicAdd(a.counters + 5, (unsigned long long)n_fast);
   }
-  if (!FLUX && nlog) flush_log();
 }
 
 }  // namespace jxp

@@ -37,12 +37,25 @@ def _field(x, n_sets, default=None):
 def pack_bodies(system: System):
     """-> (bodies [n_sets, n_bodies, 12] float64 tensor, n_sets, batched flag); the record
     layout of include/jaxoplanet_b200.h (JXP_BODY_*)."""
+    # bodies whose constants were derived on the device (OrbitalBody._init_on_device): the records exist
+    recs_dev = [getattr(body, "_record", None) for body in system.bodies]
+    if recs_dev and all(r is not None for r in recs_dev) and len({r.shape[0] for r in recs_dev}) == 1:
+        n = recs_dev[0].shape[0]
+        return (recs_dev[0].unsqueeze(1) if len(recs_dev) == 1 else torch.stack(recs_dev, dim=1)), n, True
+    # the parameter-set axis: the longest leading axis over EVERY packed field of every body (a fixed
+    # ephemeris with sampled impact parameter / radius is a common vmap pattern)
     n_sets = 1
     batched = False
     for body in system.bodies:
-        if body.period.ndim == 1:
-            batched = True
-            n_sets = max(n_sets, body.period.shape[0])
+        for x in (body.period, body.time_transit, body.time_ref, body.eccentricity, body.cos_omega_peri,
+                  body.sin_omega_peri, body.cos_inclination, body.sin_inclination, body.semimajor,
+                  body.central_radius, body.radius, body.parallax):
+            if isinstance(x, torch.Tensor) and x.ndim == 1:
+                batched = True
+                if n_sets not in (1, x.shape[0]):
+                    raise ValueError(
+                        f"batched orbit parameters must share one leading axis; got lengths {n_sets} and {x.shape[0]}")
+                n_sets = x.shape[0]
     recs = []
     for body in system.bodies:
         dev = body.period.device
@@ -258,8 +271,6 @@ def light_curve(orbit, *u, order: int = 10):
         r = (radius / r_star).expand(b.shape).contiguous()
         lc = _limb_dark_light_curve(A.to_dev(ld_u, dt), b.contiguous(), r, order=order)
         lc = torch.where(z > 0, lc, torch.zeros_like(lc))
-        if orbit.shape == () and lc.ndim == t_ndim:
-            pass
         return A.like_input(lc, time)
 
     return light_curve_generic
@@ -279,11 +290,21 @@ def log_likelihood(orbit: System, *u, order: int = 10, exposure_time=None, exp_o
         return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma), time, y)
 
     impl._jxp_spec = spec
+    impl._jxp_want = "loglike"
     return impl
 
 
 def with_spec(func, **changes):
+    """The fused function of `func` with some of its spec replaced; a log-likelihood stays a log-likelihood
+    (signature (t, y, sigma)), a light curve a light curve."""
     spec = replace(func._jxp_spec, **changes)
+    if getattr(func, "_jxp_want", "flux") == "loglike":
+        def loglike_impl(time, y, sigma):
+            return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma), time, y)
+
+        loglike_impl._jxp_spec = spec
+        loglike_impl._jxp_want = "loglike"
+        return loglike_impl
 
     def light_curve_impl(time):
         return A.like_input(_run_fused(spec, time), time)

@@ -64,6 +64,8 @@ def integrate(func, exposure_time=None, order: int = 0, num_samples: int = 7):
 
     spec = getattr(func, "_jxp_spec", None)
     if spec is not None and spec.exposure_time is None:
+        # a fused light curve (or log-likelihood): the stencil goes into the same kernel launch; the wrapped
+        # function keeps the signature of `func` ((t) or (t, y, sigma))
         from jaxoplanet_b200.light_curves.limb_dark import with_spec
 
         return with_spec(func, exposure_time=float(exposure_time), exp_order=int(order),
@@ -97,6 +99,20 @@ def interpolate(func, *, period, time_transit, num_samples: int, duration=None, 
         duration = period
     time_grid = time_transit + float(duration) * np.linspace(-0.5, 0.5, int(num_samples))
     flux_grid = func(time_grid, *args, **kwargs)
+    # the table below takes axis 0 of func's output as the grid axis (what the reference's func returns for
+    # a 1-D time array).  A fused light curve of a BATCHED orbit returns (n_sets, num_samples, ...): one
+    # period / time_transit cannot serve a batch of ephemerides, and indexing the set axis with grid
+    # indices would silently build a wrong table.
+    spec_ = getattr(func, "_jxp_spec", None)
+    if spec_ is not None:
+        from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+        if pack_bodies(spec_.orbit)[2]:
+            raise ValueError("interpolate() takes the light curve of ONE parameter set (scalar period and "
+                             "time_transit); evaluate batched orbits directly, or interpolate set by set")
+    if tuple(np.shape(flux_grid))[:1] != (int(num_samples),):
+        raise ValueError(f"func(time_grid) must have the grid axis first: expected leading size {int(num_samples)}, "
+                         f"got shape {tuple(np.shape(flux_grid))}")
     grid_dtype = flux_grid.dtype if isinstance(flux_grid, torch.Tensor) else A.result_dtype(np.asarray(flux_grid))
     flux_np = flux_grid.detach().cpu().numpy() if isinstance(flux_grid, torch.Tensor) else np.asarray(flux_grid)
     cols_shape = flux_np.shape[1:]

@@ -22,7 +22,6 @@ import torch
 
 from jaxoplanet_b200 import _array as A
 from jaxoplanet_b200 import constants
-from jaxoplanet_b200.core.kepler import kepler
 
 Scalar = Any
 
@@ -169,6 +168,9 @@ class OrbitalBody:
 
     def __init__(self, central: Central, body: Body):
         self.central = central
+        self._record = None
+        if self._init_on_device(central, body):
+            return
         self.radius = _t(body.radius)
         self.mass = _t(body.mass)
         self.radial_velocity_semiamplitude = _t(body.radial_velocity_semiamplitude)
@@ -244,6 +246,80 @@ class OrbitalBody:
             self.time_transit = _t(body.time_peri) - self.time_ref
         else:
             self.time_transit = torch.zeros_like(self.time_ref)
+
+    # -- large batches: the same constants, derived on the device by kernel K0 -----------
+    _DEVICE_MIN_SETS = 1  # every batched call: results must not depend on the batch size
+
+    def _init_on_device(self, central: Central, body: Body) -> bool:
+        """``jaxoplanet_b200.batched()`` with the parameter sets given as host arrays: the sampled
+        arguments go to the device as ONE record array and kernel K0 (jxp_orbital_elements_f64) derives
+        what keplerian.py:262-340 derives; the attributes are views of its output.  Returns False when the
+        call is not of that kind (torch inputs, ascending node, RV semi-amplitude, no CUDA device): the
+        host path below then does the same arithmetic with torch."""
+        if not A.batch_ndim() or not torch.cuda.is_available():
+            return False
+        if any(getattr(body, k) is not None for k in
+               ("asc_node", "sin_asc_node", "cos_asc_node", "radial_velocity_semiamplitude")):
+            return False
+        names = ("period", "semimajor", "time_transit", "time_peri", "eccentricity", "omega_peri",
+                 "sin_omega_peri", "cos_omega_peri", "impact_param", "inclination", "mass", "radius", "parallax")
+        given = {k: getattr(body, k) for k in names if getattr(body, k) is not None}
+        vals = list(given.values()) + [central.mass, central.radius]
+        if any(isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad) for v in vals):
+            return False
+        if any(np.asarray(v).dtype == np.float32 for v in vals):
+            return False  # (the fp32 mode keeps its inputs' dtype through the host path)
+        n = max((np.shape(v)[0] for v in vals if np.ndim(v) == 1), default=0)
+        if n < self._DEVICE_MIN_SETS or any(np.ndim(v) == 1 and np.shape(v)[0] != n for v in vals):
+            return False
+        from jaxoplanet_b200 import _lib
+        from jaxoplanet_b200.light_curves.limb_dark import pack_elements
+
+        el = pack_elements(n, central_mass=np.asarray(central.mass), central_radius=np.asarray(central.radius),
+                           **{k: np.asarray(v) for k, v in given.items()})
+        dev = A.device()
+        eld = A.host_to_dev(el)
+        rec = torch.empty((n, _lib.JXP_BODY_NFIELDS), dtype=torch.float64, device=dev)
+        _lib.call("jxp_orbital_elements_f64", eld.data_ptr(), n, rec.data_ptr(), A.stream_ptr())
+        self._record = rec
+        circular = body.eccentricity is None
+        self.period = rec[:, _lib.BODY_PERIOD]
+        self.time_transit = rec[:, _lib.BODY_TIME_TRANSIT]
+        self.time_ref = rec[:, _lib.BODY_TIME_REF]
+        self.eccentricity = None if circular else rec[:, _lib.BODY_ECC]
+        self.cos_omega_peri = None if circular else rec[:, _lib.BODY_COS_OMEGA]
+        self.sin_omega_peri = None if circular else rec[:, _lib.BODY_SIN_OMEGA]
+        self.cos_inclination = rec[:, _lib.BODY_COS_INCL]
+        self.sin_inclination = rec[:, _lib.BODY_SIN_INCL]
+        self.semimajor = rec[:, _lib.BODY_SEMIMAJOR] if body.parallax is None else \
+            rec[:, _lib.BODY_SEMIMAJOR] * constants.au / eld[:, _lib.EL_PARALLAX]
+        self.radius = None if body.radius is None else rec[:, _lib.BODY_RADIUS]
+        self.mass = None if body.mass is None else eld[:, _lib.EL_MASS]
+        self.parallax = None if body.parallax is None else eld[:, _lib.EL_PARALLAX]
+        self.radial_velocity_semiamplitude = None
+        self.sin_asc_node = self.cos_asc_node = None
+        self._impact_param_given = None if body.impact_param is None else eld[:, _lib.EL_IMPACT_PARAM]
+        return True
+
+    @property
+    def impact_param(self):
+        ip = self.__dict__.get("_impact_param")
+        if ip is not None:
+            return ip
+        if self._record is None:
+            raise AttributeError("impact_param")
+        if self._impact_param_given is not None:
+            return self._impact_param_given
+        # keplerian.py:317-331: cos i / (d cos i / d b)
+        if self.eccentricity is None:
+            incl_factor = 1.0
+        else:
+            incl_factor = (1 + self.eccentricity * self.sin_omega_peri) / (1 - self.eccentricity**2)
+        return self.cos_inclination * self.semimajor / (incl_factor * _on(self.central.radius, self.semimajor))
+
+    @impact_param.setter
+    def impact_param(self, value):
+        self.__dict__["_impact_param"] = value
 
     # -- properties (keplerian.py:342-364) ------------------------------------------
     @property
@@ -321,40 +397,45 @@ class OrbitalBody:
     def _warp_times(self, t):
         return t - self.time_transit
 
-    def _get_true_anomaly(self, t: torch.Tensor):
-        """t: CUDA tensor.  keplerian.py:537-541; the solve runs in the K1 kernel."""
-        tt = _on(self.time_transit, t)
-        M = 2 * math.pi * ((t - tt) - _on(self.time_ref, t)) / _on(self.period, t)
-        if self.eccentricity is None:
-            # circular: (sin M, cos M); the kernel with e = 0 returns exactly that
-            return kepler(M, torch.zeros((), dtype=M.dtype, device=M.device))
-        return kepler(M, _on(self.eccentricity, t))
+    def _state_record(self, dev) -> torch.Tensor:
+        """[n_sets, JXP_BODY_NFIELDS] float64 record of this body on the device (the layout of
+        include/jaxoplanet_b200.h; what the orbit-state kernel K8 reads)."""
+        from jaxoplanet_b200 import _lib
 
-    def _rotate_vector(self, x, y, *, include_inclination=True):
-        if self.eccentricity is None:
-            x1, y1 = x, y
-        else:
-            cw, sw = _on(self.cos_omega_peri, x), _on(self.sin_omega_peri, x)
-            x1 = cw * x - sw * y
-            y1 = sw * x + cw * y
-        if include_inclination:
-            x2 = x1
-            y2 = _on(self.cos_inclination, x) * y1
-            Z = -_on(self.sin_inclination, x) * y1
-        else:
-            x2, y2, Z = x1, y1, -y1
-        if self.cos_asc_node is None:
-            return x2, y2, Z
-        co, so = _on(self.cos_asc_node, x), _on(self.sin_asc_node, x)
-        return co * x2 - so * y2, so * x2 + co * y2, Z
+        if self._record is not None:  # derived on the device by K0: the record exists
+            return self._record if self._record.device == dev else self._record.to(dev)
+        n = self.period.shape[0] if self.period.ndim == 1 else 1
+        circular = self.eccentricity is None
+        f = [None] * _lib.JXP_BODY_NFIELDS
+        f[_lib.BODY_PERIOD] = self.period
+        f[_lib.BODY_TIME_TRANSIT] = self.time_transit
+        f[_lib.BODY_TIME_REF] = self.time_ref
+        f[_lib.BODY_ECC] = -1.0 if circular else self.eccentricity
+        f[_lib.BODY_COS_OMEGA] = 1.0 if circular else self.cos_omega_peri
+        f[_lib.BODY_SIN_OMEGA] = 0.0 if circular else self.sin_omega_peri
+        f[_lib.BODY_COS_INCL] = self.cos_inclination
+        f[_lib.BODY_SIN_INCL] = self.sin_inclination
+        f[_lib.BODY_SEMIMAJOR] = self.semimajor
+        f[_lib.BODY_CENTRAL_RADIUS] = self.central.radius
+        f[_lib.BODY_RADIUS] = 0.0 if self.radius is None else self.radius
+        f[_lib.BODY_RESERVED] = 0.0
+        cols = [_per_set(x, n).to(dev) for x in f]
+        return torch.stack(cols, dim=-1).contiguous()
 
     def _get_position_and_velocity(self, t, semimajor=None, mass=None, semiamplitude=None,
                                    parallax=None):
+        """keplerian.py:590-637.  The per-set scalars (the factor of the orbital radius, the velocity
+        amplitude k0) are derived here; everything per time sample -- mean anomaly, Kepler solve, radius,
+        the three rotations -- runs in ONE kernel (K8, jxp_orbit_state_*)."""
+        from jaxoplanet_b200 import _lib
+
         t_in = t
         dt = A.result_dtype(t)
-        t = A.to_dev(t, dt)
-        if A.batch_ndim() and self.period.ndim == 1:
-            t = t.unsqueeze(0)  # (1, ...) against per-set (n_sets, 1, ...) constants
+        dev = A.device()
+        td = A.to_dev(t, torch.float64)
+        t_shape = tuple(td.shape)
+        batched = bool(A.batch_ndim()) and self.period.ndim == 1
+        n_sets = self.period.shape[0] if self.period.ndim == 1 else 1
 
         if semiamplitude is None:
             semiamplitude = self.radial_velocity_semiamplitude
@@ -374,26 +455,40 @@ class OrbitalBody:
         else:
             k0 = semiamplitude
 
-        r0 = 1
+        r0 = 1.0
         if semimajor is not None:
             r0 = semimajor if parallax is None else semimajor * parallax / constants.au
 
-        sinf, cosf = self._get_true_anomaly(t)
-        k0 = _on(k0, t)
-        r0 = _on(r0, t)
-        if self.eccentricity is None:
-            v1, v2 = -k0 * sinf, k0 * cosf
-        else:
-            e = _on(self.eccentricity, t)
-            v1, v2 = -k0 * sinf, k0 * (cosf + e)
-            r0 = r0 * ((1 - e**2) / (1 + e * cosf))
-
-        pos = self._rotate_vector(r0 * cosf, r0 * sinf)
-        vel = self._rotate_vector(v1, v2, include_inclination=semiamplitude is None)
+        rec = self._state_record(dev)
+        r0d = _per_set(r0, n_sets).to(device=dev, dtype=torch.float64).contiguous()
+        k0d = _per_set(k0, n_sets).to(device=dev, dtype=torch.float64).contiguous()
+        asc = None
+        if self.cos_asc_node is not None:
+            asc = torch.stack([_per_set(self.cos_asc_node, n_sets), _per_set(self.sin_asc_node, n_sets)], dim=-1)
+            asc = asc.to(device=dev, dtype=torch.float64).contiguous()
+        pos = torch.empty((3, n_sets) + t_shape, dtype=dt, device=dev)
+        vel = torch.empty((3, n_sets) + t_shape, dtype=dt, device=dev)
+        # (the reference takes include_inclination = (semiamplitude is None) AFTER the default
+        # radial_velocity_semiamplitude has been filled in, keplerian.py:600-603, 634)
+        flags = 0 if semiamplitude is None else _lib.JXP_STATE_NO_INCLINATION
+        name = "jxp_orbit_state_f64" if dt == torch.float64 else "jxp_orbit_state_f32"
+        _lib.call(name, rec.data_ptr(), n_sets, r0d.data_ptr(), 1, k0d.data_ptr(), 1, A.ptr(asc),
+                  td.data_ptr(), td.numel(), flags, pos.data_ptr(), vel.data_ptr(), A.stream_ptr())
+        if not batched:
+            pos, vel = pos[:, 0], vel[:, 0]
         return (
-            tuple(A.like_input(p, t_in) for p in pos),
-            tuple(A.like_input(v, t_in) for v in vel),
+            tuple(A.like_input(pos[i], t_in) for i in range(3)),
+            tuple(A.like_input(vel[i], t_in) for i in range(3)),
         )
+
+
+def _per_set(x, n: int) -> torch.Tensor:
+    """Per-set constant (python scalar, 0-d or (n,) tensor) -> (n,) float64 tensor."""
+    x = x if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=torch.float64)
+    x = x.detach().to(torch.float64)
+    if x.ndim == 0:
+        return x.expand(n)
+    return x
 
 
 def _cbrt(x: torch.Tensor) -> torch.Tensor:

@@ -13,18 +13,49 @@ LIB = os.path.join(HERE, "_build", "libref_c.so")
 _lib = None
 
 
+STAMP = os.path.join(HERE, "_build", "host_cpu.txt")
+
+
+def _host_cpu() -> str:
+    """Model name + ISA flags of this host: the library is built with -march=native, so a copy built on
+    another machine (the builder container vs the GPU box) must not be loaded."""
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.startswith("model name") and not model:
+                    model = ln.split(":", 1)[1].strip()
+                elif ln.startswith("flags") and not flags:
+                    flags = " ".join(sorted(ln.split(":", 1)[1].split()))
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    import hashlib
+
+    return f"{model} {hashlib.sha1(flags.encode()).hexdigest()[:12]}"
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "ref_c.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    mk = os.path.join(HERE, "Makefile")
+    stale = (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(mk)))
+    cpu = _host_cpu()
+    try:
+        same_host = open(STAMP).read().strip() == cpu
+    except OSError:
+        same_host = False
+    if force or stale or not same_host:
         subprocess.run(["make", "-C", HERE, "-B"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        with open(STAMP, "w") as fh:
+            fh.write(cpu + "\n")
     return LIB
 
 
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()  # (no-op when the library is current AND was built on this host)
         lib = C.CDLL(LIB)
         dp = C.POINTER(C.c_double)
         lib.refc_max_threads.restype = C.c_int

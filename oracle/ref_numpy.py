@@ -632,6 +632,22 @@ def system_light_curve(bodies, u, t, order=10, xp=NP):
     return xp.stack(cols, axis=-1)
 
 
+def emission_light_curve(bodies, star_u, surfaces, t, order=10, xp=NP):
+    """src/jaxoplanet/light_curves/emission.py:11-52: [star: 1 + sum of transits, amplitude_i (1 +
+    occultation_i) ...] per time; `surfaces` = [(u_i, amplitude_i)], bodies = orbital_body(...) dicts."""
+    t = np.asarray(t, dtype=np.float64)
+    star = system_light_curve(bodies, np.asarray(star_u, dtype=np.float64), t, order=order).sum(-1) + 1  # :31-38
+    cols = [star]
+    r_star = bodies[0]["central_radius"]
+    for body, (u_b, amp) in zip(bodies, surfaces):
+        x, y, z = relative_position(body, t)  # :41
+        b = np.sqrt(x**2 + y**2) / body["radius"]  # :42
+        r = r_star / body["radius"] * np.ones_like(b)  # :43
+        lc = ld_light_curve(np.asarray(u_b, dtype=np.float64), b, r, order=order)  # :45-46
+        cols.append(amp * (1 + np.where(z < 0, lc, 0.0)))  # :47
+    return np.stack(cols, -1)  # :51
+
+
 def integrate_stencil(exposure_time, order=0, num_samples=7, dtype=np.float64):
     """Offsets and weights of transforms.py:67-89."""
     num_samples = int(num_samples)

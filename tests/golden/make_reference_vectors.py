@@ -62,6 +62,57 @@ def main_ttv():
     print(path, os.path.getsize(path), "bytes;", len(out), "arrays; in transit:", np.mean(out["ttv_flux"] != 0))
 
 
+def main_emission():
+    """light_curves/emission.py:11-52 -> tests/golden/reference_emission_v1.npz.  emission.py itself is
+    executed unmodified; the `SurfaceSystem` it asserts on lives in starry (spherical-harmonic maps, outside
+    this path), so a stand-in built on the reference's own `System` carries the three attributes the
+    function reads (central_surface.u, body_surfaces[i].u / .amplitude)."""
+    import importlib
+    import types
+
+    R = reference_shim.load()
+    K = R.keplerian
+
+    class Surface:
+        def __init__(self, u=(), amplitude=1.0):
+            self.u, self.amplitude = tuple(u), amplitude
+
+    class SurfaceSystem(K.System):
+        def __init__(self, central, central_surface, bodies_and_surfaces):
+            K.System.__init__(self, central, bodies=[b for b, _ in bodies_and_surfaces])
+            object.__setattr__(self, "central_surface", central_surface)
+            object.__setattr__(self, "_surfaces", tuple(s for _, s in bodies_and_surfaces))
+
+        @property
+        def body_surfaces(self):
+            return self._surfaces
+
+    starry = types.ModuleType("jaxoplanet.starry")
+    starry.__path__ = []
+    orbit_mod = types.ModuleType("jaxoplanet.starry.orbit")
+    orbit_mod.SurfaceSystem = SurfaceSystem
+    sys.modules["jaxoplanet.starry"] = starry
+    sys.modules["jaxoplanet.starry.orbit"] = orbit_mod
+    em = importlib.import_module("jaxoplanet.light_curves.emission")
+    kws = [dict(period=3.456, time_transit=0.1, impact_param=0.3, radius=0.1, eccentricity=0.1, omega_peri=0.5),
+           dict(period=1.7, time_transit=0.6, impact_param=0.1, radius=0.25, mass=0.002)]
+    surfaces = [Surface(u=(0.4, 0.1), amplitude=0.002), Surface(u=(), amplitude=0.0005)]
+    central = K.Central(mass=1.1, radius=0.9)
+    try:
+        sysm = SurfaceSystem(central, Surface(u=(0.3, 0.2)), [(K.Body(**kw), s) for kw, s in zip(kws, surfaces)])
+    except Exception:  # an equinox-style frozen module in the shim: build through the plain System and graft
+        raise
+    t = np.linspace(-1.0, 8.0, 4001)
+    with np.errstate(all="ignore"):
+        flux = np.asarray(em.light_curve(sysm)(t))
+    out = dict(em_t=t, em_flux=flux, em_central=np.array([1.1, 0.9]), em_star_u=np.array([0.3, 0.2]),
+               em_amp=np.array([s.amplitude for s in surfaces]))
+    path = os.path.join(HERE, "reference_emission_v1.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; shape", flux.shape, "occulted:", np.mean(flux[:, 1] < 0.002),
+          np.mean(flux[:, 2] < 0.0005), "transit:", np.mean(flux[:, 0] < 1))
+
+
 def main():
     R = reference_shim.load()
     K = R.keplerian
@@ -179,5 +230,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ttv":
         main_ttv()
+    elif len(sys.argv) > 1 and sys.argv[1] == "emission":
+        main_emission()
     else:
         main()

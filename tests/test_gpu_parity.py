@@ -388,10 +388,23 @@ def test_orbital_elements_on_device_match_oracle():
     # and the records feed the fused kernel like the host-built ones
     from jaxoplanet_b200 import workloads as W
 
+    import torch
+
+    from jaxoplanet_b200.orbits.keplerian import OrbitalBody
+
     p, ub, tb, noise, sigma = W.c3(64, 4000)
-    host, _, _ = pack_bodies(W.system_from(p))
+    keep = OrbitalBody._DEVICE_MIN_SETS
+    OrbitalBody._DEVICE_MIN_SETS = 10**9  # the host arithmetic of OrbitalBody.__init__ (torch on the CPU)
+    try:
+        host, _, _ = pack_bodies(W.system_from(p))
+    finally:
+        OrbitalBody._DEVICE_MIN_SETS = keep
+    assert host.device.type == "cpu"
     dev = derive_bodies(pack_elements(64, **p)).reshape(64, 1, -1)
     assert np.max(np.abs(dev.cpu().numpy() - host.numpy()) / np.maximum(np.abs(host.numpy()), 1e-3)) <= 2e-14
+    # the facade derives batched sets on the device: the very same records
+    facade, _, _ = pack_bodies(W.system_from(p))
+    assert facade.is_cuda and torch.equal(facade.reshape(64, 1, -1), dev)
 
 
 def test_system_shape_and_depth_kats():

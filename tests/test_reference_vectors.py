@@ -315,3 +315,85 @@ def test_live_reference_source_on_shim_agrees_with_oracle_on_fresh_inputs():
         want = np.asarray(R.lc_limb_dark.light_curve(system, u[:2])(t))
         got = ref.system_light_curve([ref.orbital_body(**kw)], u[:2], t)
         assert _flux_err(got, want) <= 4 * EPS
+
+
+# ----------------------------------------------------------------------------- emission light curve
+GE = np.load(os.path.join(HERE, "golden", "reference_emission_v1.npz"))
+EM_KW = [dict(period=3.456, time_transit=0.1, impact_param=0.3, radius=0.1, eccentricity=0.1, omega_peri=0.5),
+         dict(period=1.7, time_transit=0.6, impact_param=0.1, radius=0.25, mass=0.002)]
+EM_SURF = [((0.4, 0.1), 0.002), ((), 0.0005)]
+
+
+def test_oracle_emission_light_curve_matches_reference():
+    """emission.py executed unmodified on the shim (make_reference_vectors.py emission) vs the restatement."""
+    from oracle import ref_numpy as ref
+
+    bodies = [ref.orbital_body(central_mass=1.1, central_radius=0.9, **kw) for kw in EM_KW]
+    with np.errstate(all="ignore"):
+        got = ref.emission_light_curve(bodies, GE["em_star_u"], EM_SURF, GE["em_t"])
+    assert got.shape == GE["em_flux"].shape
+    assert np.max(np.abs(got - GE["em_flux"])) <= 4 * EPS
+
+
+@pytest.mark.gpu
+def test_cuda_emission_light_curve_matches_reference_vectors():
+    from jaxoplanet_b200.light_curves.emission import Surface, SurfaceSystem, light_curve
+    from jaxoplanet_b200.orbits.keplerian import Central
+
+    sysm = SurfaceSystem(Central(mass=1.1, radius=0.9), Surface(u=(0.3, 0.2)))
+    for kw, (u_b, amp) in zip(EM_KW, EM_SURF):
+        sysm = sysm.add_body(surface=Surface(u=u_b, amplitude=amp), **kw)
+    got = np.asarray(light_curve(sysm)(GE["em_t"]))
+    want = GE["em_flux"]
+    assert got.shape == want.shape
+    # star flux to 1e-12; the companions' fluxes to 1e-12 of their amplitude
+    scale = np.array([1.0, 0.002, 0.0005])
+    assert np.max(np.abs(got - want) / scale) <= 1e-12
+    assert np.sum(want[:, 0] < 1) > 100 and np.sum(want[:, 1] < 0.002 * (1 - 1e-6)) > 20
+
+
+@pytest.mark.gpu
+def test_cuda_batched_positions_and_velocities_one_kernel_matches_oracle():
+    """OrbitalBody.position / velocity families of a BATCH of parameter sets (kernel K8, one launch per call)
+    against the oracle, set by set; large batches take the device-side constants (kernel K0)."""
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+    from oracle import ref_numpy as ref
+
+    rng = np.random.default_rng(5)
+    n = 300  # >= 256: OrbitalBody._init_on_device
+    P = rng.uniform(1, 20, n)
+    kw = dict(period=P, time_transit=rng.uniform(0, 1, n) * P, eccentricity=rng.uniform(0, 0.8, n),
+              omega_peri=rng.uniform(-np.pi, np.pi, n), impact_param=rng.uniform(0, 1.2, n),
+              radius=rng.uniform(0.01, 0.2, n), mass=rng.uniform(1e-5, 1e-2, n))
+    t = np.sort(rng.uniform(-30, 60, 257))
+    with jxp.batched():
+        sysm = System(Central(mass=1.2, radius=0.8)).add_body(**kw)
+        body = sysm.bodies[0]
+        assert body._record is not None
+        outs = {m: [np.asarray(c) for c in getattr(body, m)(t)]
+                for m in ("position", "central_position", "relative_position", "velocity", "central_velocity",
+                          "relative_velocity")}
+        rv = np.asarray(body.radial_velocity(t))
+        ip = np.asarray(body.impact_param.cpu()) if hasattr(body.impact_param, "cpu") else np.asarray(body.impact_param)
+    np.testing.assert_allclose(ip, kw["impact_param"], rtol=0, atol=1e-14)
+    for s in range(0, n, 37):
+        bd = ref.orbital_body(central_mass=1.2, central_radius=0.8, **{k: v[s] for k, v in kw.items()})
+        a = bd["semimajor"]
+        mt = bd["mass"] + 1.2
+        want = {
+            "position": ref.position(bd, t, -a * 1.2 / mt),
+            "central_position": ref.position(bd, t, a * bd["mass"] / mt),
+            "relative_position": ref.relative_position(bd, t),
+        }
+        for m, w in want.items():
+            for got, ww in zip(outs[m], w):
+                assert got.shape == (n, t.size)
+                np.testing.assert_allclose(got[s], ww, rtol=0, atol=1e-11 * a, err_msg=m)
+        for m, kind in (("velocity", ""), ("central_velocity", "central"), ("relative_velocity", "relative")):
+            w = ref.velocity(bd, t, kind)
+            vs = np.max(np.abs(np.asarray(ref.velocity(bd, t, "relative"))))
+            for got, ww in zip(outs[m], w):
+                np.testing.assert_allclose(got[s], ww, rtol=0, atol=1e-11 * vs, err_msg=m)
+        np.testing.assert_allclose(rv[s], -np.asarray(ref.velocity(bd, t, "central")[2]), rtol=0,
+                                   atol=1e-11 * np.max(np.abs(rv[s])) + 1e-300)
