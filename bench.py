@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the jaxoplanet hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the jaxoplanet hot path on B200 (contract: the task statement / DESIGN.md 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json config 3 -- 4096 parameter sets x 1e5 time samples
-of a Keplerian transit light curve with quadratic limb darkening, fused with the Gaussian
-log-likelihood -- PER GPU (weak scaling: rank g evaluates its own 4096 sets; the per-set
-log-likelihoods are all-gathered over NCCL).  A "step" is one evaluation of that batch, the
-unit a sampler performs per proposal.  metric = light-curve points/s (one point = one time
-sample of one parameter set).
+Workload (config.workload): BASELINE.json config 3 AS WRITTEN -- 4096 parameter sets x 1e5 time samples of
+a Keplerian transit light curve with quadratic limb darkening, fused with the Gaussian log-likelihood,
+the 4096 sets SHARDED over the N GPUs (strong scaling: rank g evaluates sets [g 4096/N, (g+1) 4096/N);
+t, y, sigma are replicated; the per-set log-likelihoods are all-gathered over NCCL inside every step).
+A "step" is one evaluation of the batch, the unit a sampler performs per proposal.
+metric = light-curve points/s (one point = one time sample of one parameter set).
 
-value    device-resident inputs, CUDA events around each step, L2 flushed between steps
-e2e      same step through the C ABI with pinned HOST buffers: H2D of every input and D2H of
-         the log-likelihoods inside the timed region
-roofline dominant kernel (k_system) timed alone with CUDA events inside the timed steps;
-         achieved = A-table flops of the work it EXECUTED (counters read back from the
-         device) / its mean duration; peak = FP64 FMA peak measured in this run
-cpu_baseline / --impl reference: the C/OpenMP restatement of the reference (oracle/ref_c.c)
-         on the host cores, on a bounded sample of the same workload.
+value      device-resident inputs, CUDA events around each step, L2 flushed between steps, max over ranks
+weak       (N > 1) the same step with 4096 sets PER GPU (round 1's definition), as a second field
+e2e        the same step through the repo's public Python API (the reference's call: System(...).add_body(
+           **sampled elements) -> log_likelihood(orbit, u)(t, y, sigma)) with HOST NumPy arrays in and out:
+           host-to-device copies of every input and the device-to-host read of the result inside the timed
+           region; e2e.c_abi: the same through the bare C ABI from one pinned arena
+roofline   dominant kernel k_walk_eval timed alone with CUDA events inside the timed steps.  achieved =
+           A-table flops of the work it EXECUTED (counters read back from the device; samples with the
+           planet inside the disk charged their own, smaller weight) / its mean duration; peak = FP64 FMA
+           peak measured in this run.  hardware: FP64 thread instructions of the same launch (ncu, profiles/)
+           over the live duration; pipe_fp64_pct from the same capture.
+cpu_baseline / --impl reference: the reference's algorithm on the host cores -- real jaxoplanet on jax[cpu]
+           when `import jax` and a reference checkout (baseline/_ref) exist, else the C/OpenMP restatement
+           (oracle/ref_c.c, -O3 -march=native) -- over ALL 4096 sets per step.
 """
 
 from __future__ import annotations
@@ -41,10 +48,12 @@ sys.path.insert(0, ROOT)
 W_KEPLER = 266.0
 W_ORBIT = 36.0
 W_LD = 746.0
+# a flux evaluation with the planet fully inside the disk (kappa0 = pi, kappa1 = 0, kite area 0: constants):
+# the reference formula without its 10 node cosines (250), 2 atan2 (80) and the kite area (22)
+W_LD_INSIDE = 394.0
 N_SETS = 4096
 N_TIMES = 100_000
 METRIC = "light-curve points/s (Keplerian orbit + quadratic limb darkening + Gaussian log-likelihood, fp64)"
-
 
 _STDOUT_FD = None
 
@@ -70,11 +79,12 @@ def emit(line):
 def workload_config(n_gpus, extra=None):
     cfg = {
         "workload": f"C3: {N_SETS} parameter sets x {N_TIMES} times (2-min cadence), 1 planet, quadratic LD, "
-                    "fused Gaussian log-likelihood, per GPU",
-        "sets_per_gpu": N_SETS,
+                    f"fused Gaussian log-likelihood; the {N_SETS} sets sharded over {n_gpus} GPU(s)",
+        "n_sets": N_SETS,
+        "sets_per_gpu": N_SETS // max(n_gpus, 1),
         "n_times": N_TIMES,
         "n_bodies": 1,
-        "parallelism": f"set-sharded x{n_gpus}",
+        "parallelism": f"set-sharded x{n_gpus} (no data-path collective; all-gather of 8 B per set per step)",
         "cache": "L2 flushed between steps (256 MiB write); per-step CUDA events summed",
     }
     if extra:
@@ -82,76 +92,179 @@ def workload_config(n_gpus, extra=None):
     return cfg
 
 
-def build_inputs(seed):
-    """Host-side inputs of one rank: C-ABI body records, u, t, noise, sigma."""
+def c3_inputs(seed=1):
     from jaxoplanet_b200 import workloads as W
-    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
 
-    p, u, t, noise, sigma = W.c3(N_SETS, N_TIMES, seed=seed)
-    bodies, n_sets, _ = pack_bodies(W.system_from(p))
-    return p, bodies.cpu().numpy().copy(), u, t, noise, sigma
+    return W.c3(N_SETS, N_TIMES, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (C/OpenMP restatement) on the host cores
+# reference arm: the reference's CPU algorithm on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_points_per_s(bodies, u, t, y, sigma, budget_s=12.0):
+def oracle_records(p):
+    """Oracle-side body records (host arithmetic of oracle/ref_numpy.py) for the C restatement."""
+    from oracle import ref_numpy as ref
+
+    bd = ref.orbital_body(**p)
+    n = len(p["period"])
+    rec = np.zeros((n, 1, 12))
+    rec[:, 0, 0] = bd["period"]
+    rec[:, 0, 1] = bd["time_transit"]
+    rec[:, 0, 2] = bd["time_ref"]
+    rec[:, 0, 3] = bd["eccentricity"]
+    rec[:, 0, 4] = bd["cos_omega_peri"]
+    rec[:, 0, 5] = bd["sin_omega_peri"]
+    rec[:, 0, 6] = bd["cos_inclination"]
+    rec[:, 0, 7] = bd["sin_inclination"]
+    rec[:, 0, 8] = bd["semimajor"]
+    rec[:, 0, 9] = 1.0
+    rec[:, 0, 10] = bd["radius"]
+    return rec
+
+
+def reference_y(rec, u, t, noise):
+    """y = 1 + model of set 0 + noise, from the CPU restatement (the GPU arm derives the same y from its own
+    set-0 light curve; the two agree to 1e-15, irrelevant for timing)."""
     from oracle import ref_c
 
-    ref_c.build()
-    ref_c.use_all_cores()
-    n_try = 2
-    t0 = time.perf_counter()
-    ref_c.system(bodies[:n_try], u[:n_try], t, y=y, sigma=sigma, want_flux=False)
-    dt = time.perf_counter() - t0
-    threads = ref_c.max_threads()
-    n_sample = int(min(len(bodies), max(threads, budget_s / max(dt / n_try, 1e-9))))
-    n_sample = max(threads, (n_sample // threads) * threads)
-    n_sample = min(n_sample, len(bodies))
-    t0 = time.perf_counter()
-    ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
-    dt = time.perf_counter() - t0
-    return n_sample * len(t) / dt, n_sample, threads, dt
+    f0, _ = ref_c.system(rec[:1], u[:1], t)
+    return 1.0 + f0[0] + noise
+
+
+def jax_reference():
+    """Real jaxoplanet on jax[cpu], if this box has it: `import jax` plus the reference package importable
+    (site-packages or a checkout under baseline/_ref).  Returns (callable (p, u, t, y, sigma) -> (n_sets,)
+    log-likelihoods, description) or (None, reason)."""
+    try:
+        import jax  # noqa: F401
+    except Exception as e:  # noqa: BLE001
+        return None, f"jax not importable ({type(e).__name__})"
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), os.path.join(ROOT, "baseline", "_ref", "src")):
+        if os.path.isdir(cand) and cand not in sys.path:
+            sys.path.insert(0, cand)
+    try:
+        import jax
+        import jax.numpy as jnp
+
+        jax.config.update("jax_enable_x64", True)
+        jax.config.update("jax_platform_name", "cpu")
+        from jaxoplanet.light_curves import limb_dark_light_curve
+        from jaxoplanet.orbits.keplerian import Central, System
+    except Exception as e:  # noqa: BLE001
+        return None, f"jaxoplanet not importable ({type(e).__name__}: {e})"
+
+    def one(params, uu, t, y, sigma):
+        orbit = System(Central()).add_body(**params)
+        lc = limb_dark_light_curve(orbit, uu)(t)[..., 0]
+        r = (y - (1.0 + lc)) / sigma
+        return jnp.sum(-0.5 * r * r - jnp.log(sigma) - 0.5 * jnp.log(2 * jnp.pi))
+
+    batched = jax.jit(jax.vmap(one, in_axes=(0, 0, None, None, None)))
+
+    def run(p, u, t, y, sigma):
+        return np.asarray(batched({k: jnp.asarray(v) for k, v in p.items()}, jnp.asarray(u), jnp.asarray(t),
+                                  jnp.asarray(y), sigma).block_until_ready())
+
+    return run, "jaxoplanet on jax[cpu], x64, jit + vmap over the parameter sets"
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    _, bodies, u, t, noise, sigma = build_inputs(seed=1)
-    y = 1.0 + noise
+    p, u, t, noise, sigma = c3_inputs()
     from oracle import ref_c
 
     ref_c.build()
     threads = ref_c.use_all_cores()
-    # size one step to ~2 s of CPU work
-    n_try = max(2, threads)
+    rec = oracle_records(p)
+    y = reference_y(rec, u, t, noise)
+    jax_run, how = jax_reference()
+    kind = "reference" if jax_run is not None else "port"
+
+    def step(n):
+        if jax_run is not None:
+            return jax_run({k: v[:n] for k, v in p.items()}, u[:n], t, y, sigma)
+        return ref_c.system(rec[:n], u[:n], t, y=y, sigma=sigma, want_flux=False)[1]
+
+    # every step evaluates ALL 4096 sets unless that would take the whole run past ~4 minutes
+    n_try = max(2 * threads, 32)
+    step(n_try)
     t0 = time.perf_counter()
-    ref_c.system(bodies[:n_try], u[:n_try], t, y=y, sigma=sigma, want_flux=False)
+    step(n_try)
     per_set = (time.perf_counter() - t0) / n_try
-    n_sample = int(min(N_SETS, max(threads, 2.0 / max(per_set, 1e-9))))
-    n_sample = max(threads, (n_sample // threads) * threads)
+    total_steps = args.steps + args.warmup
+    n_sample = N_SETS
+    if per_set * N_SETS * total_steps > 240.0:
+        n_sample = int(240.0 / (per_set * total_steps))
+        n_sample = max(threads, min(N_SETS, (n_sample // threads) * threads))
     for _ in range(args.warmup):
-        ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
+        step(n_sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref_c.system(bodies[:n_sample], u[:n_sample], t, y=y, sigma=sigma, want_flux=False)
+        step(n_sample)
     dt = (time.perf_counter() - t0) / args.steps
     value = n_sample * N_TIMES / dt
-    sample = f"{n_sample} of {N_SETS} sets x {N_TIMES} times per step (linear in sets)"
+    sample = (f"all {N_SETS} sets x {N_TIMES} times per step" if n_sample == N_SETS else
+              f"{n_sample} of {N_SETS} sets x {N_TIMES} times per step (bounded to keep the run within minutes; "
+              "the work is linear in sets)")
+    note = (how if jax_run is not None else
+            "C/OpenMP restatement of the reference formulas (oracle/ref_c.c, -O3 -march=native, no fast-math), every "
+            f"sample evaluated in full as the reference does; not jax[cpu]: {how}")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (N_SETS / n_sample), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, {"cache": "n/a (CPU)"}),
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": sample,
-                         "note": "C/OpenMP restatement of the reference formulas (oracle/ref_c.c); "
-                                 "jax is not installable in this image, so this is not jax[cpu]"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": kind, "sample": sample,
+                         "note": note},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def cpu_baseline_leg(p, u, t, y, sigma):
+    """N = 1 only: the CPU arm on a bounded sample (one pass over all sets, ~10-30 s of CPU work), plus the
+    Kepler solver alone (config 2) next to the reference's published 14 ns/solve."""
+    from oracle import ref_c
+
+    ref_c.build()
+    threads = ref_c.use_all_cores()
+    rec = oracle_records(p)
+    jax_run, how = jax_reference()
+    n_try = max(2 * threads, 32)
+    if jax_run is not None:
+        run = lambda n: jax_run({k: v[:n] for k, v in p.items()}, u[:n], t, y, sigma)  # noqa: E731
+    else:
+        run = lambda n: ref_c.system(rec[:n], u[:n], t, y=y, sigma=sigma, want_flux=False)  # noqa: E731
+    run(n_try)
+    t0 = time.perf_counter()
+    run(n_try)
+    per_set = (time.perf_counter() - t0) / n_try
+    n_sample = N_SETS if per_set * N_SETS <= 30.0 else max(threads, int(30.0 / per_set) // threads * threads)
+    t0 = time.perf_counter()
+    run(n_sample)
+    secs = time.perf_counter() - t0
+    out = {"value": n_sample * N_TIMES / secs, "unit": "points/s", "cores": threads,
+           "kind": "reference" if jax_run is not None else "port",
+           "sample": f"{n_sample} of {N_SETS} sets x {N_TIMES} times, one pass, {secs:.1f} s",
+           "note": how if jax_run is not None else
+           f"C/OpenMP restatement of the reference formulas (oracle/ref_c.c, -O3 -march=native); not jax[cpu]: {how}"}
+    # C2 on the CPU: the Kepler solve alone
+    rng = np.random.default_rng(0)
+    n2 = 20_000_000
+    M = rng.uniform(0.0, 2 * np.pi, n2)
+    e = rng.uniform(0.0, 0.99, n2)
+    ref_c.kepler(M[:100_000], e[:100_000])
+    t0 = time.perf_counter()
+    ref_c.kepler(M, e)
+    k_secs = time.perf_counter() - t0
+    out["c2_kepler"] = {"solves_per_s": n2 / k_secs, "ns_per_solve_per_core": k_secs / n2 * 1e9 * threads,
+                        "sample": f"{n2} (M, e) pairs, e ~ U[0, 0.99), {threads} threads",
+                        "published_reference": "14 ns/solve on one M1 core at fixed e = 0.5 "
+                                               "(docs/tutorials/core-from-scratch.ipynb:215)"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -208,12 +321,54 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------
+class Problem:
+    """Device-resident inputs + workspace of one rank's block of sets; call() = one step through the C ABI."""
+
+    def __init__(self, p, u, t, dev):
+        import torch
+
+        from jaxoplanet_b200 import _array as A
+        from jaxoplanet_b200 import _lib
+        from jaxoplanet_b200.light_curves.limb_dark import pack_elements
+
+        self.A, self._lib, self.lib = A, _lib, _lib.load()
+        self.n_sets, self.n_times = len(p["period"]), len(t)
+        self.elements_h = np.ascontiguousarray(pack_elements(self.n_sets, **p), dtype=np.float64)
+        el = torch.as_tensor(self.elements_h).to(dev)
+        self.bodies = torch.empty((self.n_sets, 1, _lib.JXP_BODY_NFIELDS), dtype=torch.float64, device=dev)
+        _lib.call("jxp_orbital_elements_f64", el.data_ptr(), self.n_sets, self.bodies.data_ptr(), A.stream_ptr())
+        self.u = torch.as_tensor(np.ascontiguousarray(u)).to(dev)
+        self.t = torch.as_tensor(t).to(dev)
+        self.wsb = int(self.lib.jxp_system_workspace_bytes(self.n_sets, 1, self.n_times))
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=dev)
+        self.ll = torch.empty(self.n_sets, dtype=torch.float64, device=dev)
+
+    def call(self, y=None, sig=None, flags=0, flux_sum=None):
+        A = self.A
+        self._lib.call("jxp_system_light_curve_f64", self.bodies.data_ptr(), self.n_sets, 1, self.u.data_ptr(), 2, 2,
+                       self.t.data_ptr(), self.n_times, 0.0, 0, 0, 10, flags, 0, A.ptr(flux_sum), A.ptr(y),
+                       A.ptr(sig) if y is not None else 0, 0, self.ll.data_ptr() if y is not None else 0,
+                       self.ws.data_ptr(), self.wsb, A.stream_ptr())
+
+    def stats(self):
+        st = (ctypes.c_int64 * 2)()
+        self._lib.call("jxp_system_stats", self.ws.data_ptr(), self.n_sets, 1, self.n_times, ctypes.addressof(st),
+                       self.A.stream_ptr())
+        ls = (ctypes.c_int64 * 4)()
+        self._lib.call("jxp_system_list_stats", self.ws.data_ptr(), self.n_sets, 1, self.n_times, ctypes.addressof(ls),
+                       self.A.stream_ptr())
+        return dict(kepler=int(st[0]), ld=int(st[1]), items=int(ls[0]), flags=int(ls[1]), inside=int(ls[2]),
+                    fast=int(ls[3]))
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
     from jaxoplanet_b200 import _array as A
     from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.distributed import log_likelihood_distributed, shard_range
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -222,31 +377,23 @@ def run_ours(args, rank, local_rank, world):
     lib = _lib.load()
     stream = A.stream_ptr
 
-    p, bodies_h, u_h, t_h, noise, sigma = build_inputs(seed=1 + rank)
-    n_sets, n_times = bodies_h.shape[0], t_h.shape[0]
-    bodies = torch.as_tensor(bodies_h).to(dev).contiguous()
-    u = torch.as_tensor(u_h).to(dev).contiguous()
-    t = torch.as_tensor(t_h).to(dev)
+    p, u_h, t_h, noise, sigma = c3_inputs(seed=1)
+    lo, hi = shard_range(N_SETS, rank, world)
+    p_loc = {k: v[lo:hi] for k, v in p.items()}
+    prob = Problem(p_loc, u_h[lo:hi], t_h, dev)
+    n_times = prob.n_times
     sig = torch.full((1,), sigma, dtype=torch.float64, device=dev)
-    wsb = int(lib.jxp_system_workspace_bytes(n_sets, 1, n_times))
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    ll = torch.empty(n_sets, dtype=torch.float64, device=dev)
-    ll_all = torch.empty(world * n_sets, dtype=torch.float64, device=dev) if world > 1 else None
 
-    def call(flags=0, y_=None, flux_sum=None, loglike=ll, bodies_=bodies, u_=u, t_=t, sig_=sig):
-        _lib.call("jxp_system_light_curve_f64", bodies_.data_ptr(), n_sets, 1, u_.data_ptr(), 2, 2,
-                  t_.data_ptr(), n_times, 0.0, 0, 0, 10, flags, 0, A.ptr(flux_sum), A.ptr(y_),
-                  sig_.data_ptr() if y_ is not None else 0, 0, A.ptr(loglike) if y_ is not None else 0,
-                  ws.data_ptr(), wsb, stream())
-
-    # observed flux: 1 + model of this rank's set 0 + noise (synthetic), computed once, untimed
-    f0 = torch.empty((n_sets, n_times), dtype=torch.float64, device=dev)
-    call(flux_sum=f0, loglike=None)
+    # observed flux: 1 + model of set 0 + noise (synthetic); every rank evaluates set 0 itself, untimed
+    p0 = Problem({k: v[:1] for k, v in p.items()}, u_h[:1], t_h, dev)
+    f0 = torch.empty((1, n_times), dtype=torch.float64, device=dev)
+    p0.call(flux_sum=f0)
     y = (1.0 + f0[0] + torch.as_tensor(noise).to(dev)).contiguous()
-    f_in = float((f0 != 0).double().mean())
-    del f0
+    y_np = y.cpu().numpy()
+    del p0, f0
     torch.cuda.synchronize()
 
+    ll_all = torch.empty(N_SETS, dtype=torch.float64, device=dev) if world > 1 else None
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def flush_l2():
@@ -258,21 +405,27 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(flags=0):
-        call(flags=flags, y_=y)
-        if world > 1:
-            w = dist.all_gather_into_tensor(ll_all, ll, async_op=True)
-            w.wait()
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    kev0 = torch.cuda.Event(enable_timing=True)
-    kev1 = torch.cuda.Event(enable_timing=True)
+    ev0, ev1, kev0, kev1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
     for e in (ev0, ev1, kev0, kev1):
         e.record()
     torch.cuda.synchronize()
 
-    def timed_steps(n, flags=0, kernel_events=True):
+    def make_step(problem, gathered):
+        def step(flags=0):
+            problem.call(y=y, sig=sig, flags=flags)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, problem.ll)
+
+        return step
+
+    def timed_steps(step, n, flags=0, kernel_events=True):
         tot, ktot = 0.0, 0.0
         for _ in range(n):
             flush_l2()
@@ -304,226 +457,204 @@ def run_ours(args, rank, local_rank, world):
 
     fp64_peak = fma_peak("jxp_peak_fma_f64", torch.float64)
 
-    # ---- value: device-resident inputs --------------------------------------------------
-    timed_steps(max(args.warmup, 3), kernel_events=False)
+    # ---- value: device-resident inputs, the 4096 sets sharded over the ranks ---------------------
+    step = make_step(prob, ll_all)
+    warm = max(args.warmup, 3)
+    timed_steps(step, warm, kernel_events=False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     barrier()
     t_lo = time.perf_counter()
-    tot_ms, k_ms = timed_steps(args.steps)
+    tot_ms, k_ms = timed_steps(step, args.steps)
     barrier()
     t_hi = time.perf_counter()
     clocks = sampler.stop(t_lo, t_hi) if rank == 0 else None
-    stats = (ctypes.c_int64 * 2)()
-    _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
-    n_kep, n_ld = int(stats[0]), int(stats[1])
-    lstats = (ctypes.c_int64 * 4)()
-    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(lstats), stream())
-    list_items, list_used = int(lstats[0]), int(lstats[0]) > 0 and int(lstats[1]) == 0
-    # sorted time stamps: the in-window samples go on a work list (k_tl_*); the window-test kernels are
-    # still launched behind them and return at once (the choice is made on the device)
-    launches = (["k_sys_prep_ll", "k_tl_build", "k_tl_eval", "k_tl_reduce", "k_system_pair (returns at once)",
-                 "k_loglike_final (returns at once)"] if list_used
-                else ["k_sys_prep_ll", "k_system_pair", "k_loglike_final"])
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
+    st = prob.stats()
+    walk_used = st["items"] > 0 and st["flags"] == 0
+    # plan launch alone (same events, other bracket)
+    lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_PLAN)
+    _, plan_ms = timed_steps(step, 5)
+    lib.jxp_set_dev_options(0)
+    plan_ms /= 5
+    # sorted time stamps: only the in-window samples are visited (k_walk_*); the window-test kernels are still
+    # launched behind them and return at once (the choice is made on the device)
+    launches = (["k_walk_plan", "k_walk_eval", "k_system_pair (returns at once)", "k_loglike_final (returns at once)"]
+                if walk_used else ["k_sys_prep_ll", "k_system_pair", "k_loglike_final"])
     tot_ms = max_over_ranks(tot_ms)
     ms_per_step = tot_ms / args.steps
-    points_per_step = world * n_sets * n_times
+    points_per_step = N_SETS * n_times
     value = points_per_step / (ms_per_step * 1e-3)
 
-    # ---- e2e: pinned host buffers through the C ABI ------------------------------------------
-    # the step starts from the SAMPLED orbital elements (what an MCMC step has on the host): K0 derives
-    # the per-set constants of OrbitalBody.__init__ on the device, inside the timed region
-    from jaxoplanet_b200.light_curves.limb_dark import pack_elements
+    # ---- weak scaling as a second field (N > 1): 4096 sets per GPU, round 1's definition -----------
+    weak = None
+    if world > 1:
+        pw, uw, _, _, _ = c3_inputs(seed=1 + rank)
+        probw = Problem(pw, uw, t_h, dev)
+        llw_all = torch.empty(world * N_SETS, dtype=torch.float64, device=dev)
+        stepw = make_step(probw, llw_all)
+        timed_steps(stepw, 3, kernel_events=False)
+        barrier()
+        w_ms, _ = timed_steps(stepw, args.steps, kernel_events=False)
+        barrier()
+        w_ms = max_over_ranks(w_ms) / args.steps
+        weak = {"value": world * N_SETS * n_times / (w_ms * 1e-3), "unit": "points/s", "ms_per_step": w_ms,
+                "sets_per_gpu": N_SETS, "scaling": "weak"}
+        del probw, llw_all
+        torch.cuda.empty_cache()
 
-    # one pinned arena on the host and its mirror on the device: [elements | u | t | y | sigma] go over in
-    # ONE copy per step (five separate copies cost ~8 us of latency each on a 2 MB transfer)
-    parts = [np.ascontiguousarray(pack_elements(n_sets, **p), dtype=np.float64).reshape(-1),
-             np.ascontiguousarray(u_h, dtype=np.float64).reshape(-1), np.ascontiguousarray(t_h, dtype=np.float64),
-             y.cpu().numpy().astype(np.float64), np.array([sigma], dtype=np.float64)]
-    offs = np.concatenate([[0], np.cumsum([((x.size + 31) // 32) * 32 for x in parts])])  # 256-byte aligned
-    harena = torch.zeros(int(offs[-1]), dtype=torch.float64).pin_memory()
-    for x, o in zip(parts, offs[:-1]):
-        harena[int(o):int(o) + x.size] = torch.as_tensor(x)
-    darena = torch.empty_like(harena, device=dev)
-    del_, du, dt_, dy, ds = (darena[int(o):int(o) + x.size] for x, o in zip(parts, offs[:-1]))
-    hll = torch.empty(n_sets, dtype=torch.float64).pin_memory()
-    db = torch.empty((n_sets, 1, _lib.JXP_BODY_NFIELDS), dtype=torch.float64, device=dev)
-    h2d = sum(x.size * 8 for x in parts)
-    d2h = hll.numel() * hll.element_size()
+    # ---- e2e through the public Python API (headline): NumPy in, NumPy out --------------------------
+    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood as facade_ll
 
-    def e2e_step():
-        darena.copy_(harena, non_blocking=True)
-        _lib.call("jxp_orbital_elements_f64", del_.data_ptr(), n_sets, db.data_ptr(), stream())
-        _lib.call("jxp_system_light_curve_f64", db.data_ptr(), n_sets, 1, du.data_ptr(), 2, 2,
-                  dt_.data_ptr(), n_times, 0.0, 0, 0, 10, 0, 0, 0, dy.data_ptr(), ds.data_ptr(), 0,
-                  ll.data_ptr(), ws.data_ptr(), wsb, stream())
-        if world > 1:
-            w = dist.all_gather_into_tensor(ll_all, ll, async_op=True)
-            w.wait()
-        hll.copy_(ll, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e2e_ms = 0.0
-    for _ in range(args.steps):
-        flush_l2()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_step()
-        e2e_ms += (time.perf_counter() - t0) * 1e3
-    barrier()
-    e2e_ms = max_over_ranks(e2e_ms) / args.steps
-    e2e_value = points_per_step / (e2e_ms * 1e-3)
-
-    # ---- the same step through the Python facade (what a user of the reference API writes): the
-    # sampled orbital elements, t and y are HOST NumPy arrays, System(...) is rebuilt (per-set
-    # constants of OrbitalBody.__init__ re-derived) every step, the result comes back as NumPy
-    from jaxoplanet_b200 import workloads as W
-    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood as _facade_ll
-
-    y_np = y.cpu().numpy()
-
-    def facade_step():
-        return _facade_ll(W.system_from(p), u_h)(t_h, y_np, sigma)
+    if world == 1:
+        def api_step():
+            return facade_ll(W.system_from(p), u_h)(t_h, y_np, sigma)
+    else:
+        def api_step():
+            return log_likelihood_distributed(p, u_h, t_h, y_np, sigma).cpu().numpy()
 
     for _ in range(5):
-        facade_step()
+        api_step()
     barrier()
     py_ms = 0.0
     for _ in range(args.steps):
         flush_l2()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ll_np = facade_step()
+        ll_np = api_step()
         py_ms += (time.perf_counter() - t0) * 1e3
-    assert isinstance(ll_np, np.ndarray) and ll_np.shape == (n_sets,)
+    assert isinstance(ll_np, np.ndarray) and ll_np.shape == (N_SETS,)
+    barrier()
     py_ms = max_over_ranks(py_ms) / args.steps
+    # the bytes the API moved per step and rank: element records, u, t, y, sigma in; the log-likelihoods out
+    n_loc = hi - lo
+    h2d = (n_loc * _lib.JXP_EL_NFIELDS + n_loc * 2 + 2 * n_times + 1) * 8
+    d2h = N_SETS * 8
+
+    # ---- e2e through the bare C ABI: one pinned arena [elements | u | t | y | sigma], one H2D copy -----
+    parts = [prob.elements_h.reshape(-1), np.ascontiguousarray(u_h[lo:hi], dtype=np.float64).reshape(-1),
+             np.ascontiguousarray(t_h, dtype=np.float64), y_np.astype(np.float64), np.array([sigma], dtype=np.float64)]
+    offs = np.concatenate([[0], np.cumsum([((x.size + 31) // 32) * 32 for x in parts])])  # 256-byte aligned
+    harena = torch.zeros(int(offs[-1]), dtype=torch.float64).pin_memory()
+    for x, o in zip(parts, offs[:-1]):
+        harena[int(o):int(o) + x.size] = torch.as_tensor(x)
+    darena = torch.empty_like(harena, device=dev)
+    del_, du, dt_, dy, ds = (darena[int(o):int(o) + x.size] for x, o in zip(parts, offs[:-1]))
+    hll = torch.empty(N_SETS, dtype=torch.float64).pin_memory()
+    db = torch.empty((n_loc, 1, _lib.JXP_BODY_NFIELDS), dtype=torch.float64, device=dev)
+
+    def c_abi_step():
+        darena.copy_(harena, non_blocking=True)
+        _lib.call("jxp_orbital_elements_f64", del_.data_ptr(), n_loc, db.data_ptr(), stream())
+        _lib.call("jxp_system_light_curve_f64", db.data_ptr(), n_loc, 1, du.data_ptr(), 2, 2,
+                  dt_.data_ptr(), n_times, 0.0, 0, 0, 10, 0, 0, 0, dy.data_ptr(), ds.data_ptr(), 0,
+                  prob.ll.data_ptr(), prob.ws.data_ptr(), prob.wsb, stream())
+        if world > 1:
+            dist.all_gather_into_tensor(ll_all, prob.ll)
+            hll.copy_(ll_all, non_blocking=True)
+        else:
+            hll.copy_(prob.ll, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        c_abi_step()
+    barrier()
+    c_ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c_abi_step()
+        c_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    c_ms = max_over_ranks(c_ms) / args.steps
+    assert np.array_equal(hll.numpy(), ll_np), "the Python API and the C ABI must return the same numbers"
+
+    # ---- secondary configs (C2 / C4 / C5), sharded over the ranks like the headline -----------------
+    secondary = {}
+    if not args.no_secondary:
+        secondary = secondary_configs(dev, lib, ev0, ev1, rank, world, fp64_peak, max_over_ranks, barrier)
+        if world == 1:
+            timed_steps(step, 2, flags=_lib.JXP_FLAG_NO_WINDOW, kernel_events=False)
+            d_tot, d_k = timed_steps(step, 3, flags=_lib.JXP_FLAG_NO_WINDOW)
+            sd = prob.stats()
+            d_flops = sd["kepler"] * (W_KEPLER + W_ORBIT) + sd["ld"] * W_LD
+            secondary["c3_dense_no_window"] = {
+                "points_per_s": N_SETS * n_times / (d_tot / 3 * 1e-3), "ms_per_step": d_tot / 3,
+                "fp64_frac": d_flops / (d_k / 3 * 1e-3) / 1e12 / fp64_peak,
+                "executed": {"kepler_solves": sd["kepler"], "ld_evaluations": sd["ld"]}}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (rank 0) -------------------------------------------
+    # ---- roofline of the dominant kernel (rank 0's shard) -------------------------------------------
     k_ms_avg = k_ms / args.steps
-    flops = n_kep * (W_KEPLER + W_ORBIT) + n_ld * W_LD
+    n_gen = st["ld"] - st["fast"]
+    flops = st["kepler"] * (W_KEPLER + W_ORBIT) + st["fast"] * W_LD_INSIDE + n_gen * W_LD
+    flops_r1 = st["kepler"] * (W_KEPLER + W_ORBIT) + st["ld"] * W_LD
     achieved = flops / (k_ms_avg * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    hw = None
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[
-            "k_tl_eval" if list_used else "k_system_pair"]
-        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_walk_eval.json")))
+        # instruction counts of a launch depend on the inputs only (same seeded workload); scale by the items
+        scale = st["items"] / cap["items"]
+        hw_flops = (2 * cap["dfma"] + cap["dmul"] + cap["dadd"]) * scale
+        hw = {"fp64_thread_flops_per_launch": hw_flops, "tflops": hw_flops / (k_ms_avg * 1e-3) / 1e12,
+              "frac_of_peak": hw_flops / (k_ms_avg * 1e-3) / 1e12 / fp64_peak,
+              "pipe_fp64_pct_ncu": cap["pipe_fp64_pct"], "issue_active_pct_ncu": cap["issue_active_pct"],
+              "source": cap["source"]}
+        traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * scale
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_tl_eval<1>" if list_used else "k_system_pair<1>", "achieved": achieved,
-        "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
-        "traffic_note": "DRAM bytes per launch from the ncu capture in profiles/ (FP64-bound kernel; the list "
-                        "path reads its 8-byte items and writes the chi^2 terms over them: 13 M items x 8 B each way, "
-                        "part of the writes still in L2 when the kernel ends)",
-        "list_items": list_items,
+        "bound": "fp64", "kernel": "k_walk_eval<2>" if walk_used else "k_system_pair<1>", "achieved": achieved,
+        "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
+        "traffic_note": "DRAM bytes per launch (ncu, profiles/r2_walk_eval.json), scaled to this rank's items; "
+                        "algorithmic bytes: 24 B per in-window sample (t, y, 1/sigma) + 256 B per set + 24 B per chunk",
+        "hardware": hw,
+        "frac_r1_convention": flops_r1 / (k_ms_avg * 1e-3) / 1e12 / fp64_peak,
+        "items": st["items"],
         "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
-        "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
-        "executed": {"kepler_solves": n_kep, "ld_evaluations": n_ld, "points": n_sets * n_times,
-                     "in_transit_fraction": f_in},
-        "flops_convention": "A-table v1: 302 flop per executed Kepler solve + orbit, 746 per executed LD evaluation; "
-                            "window pre-tests counted as 0. The A-table charges every flux evaluation the reference's "
-                            "formula (10 node cosines, 2 atan2); for samples with the planet fully inside the disk the list "
-                            "path evaluates the same function with constant kappas and node cosines, i.e. fewer executed "
-                            "instructions than charged (hardware side: FP64 pipe 58 % active, profiles/r1_bench_tl_eval.md)",
+        "kernel_ms": k_ms_avg, "plan_kernel_ms": plan_ms, "kernel_share_of_step": k_ms_avg / ms_per_step,
+        "executed": {"kepler_solves": st["kepler"], "ld_evaluations": st["ld"], "ld_inside_disk_code": st["fast"],
+                     "points": (hi - lo) * n_times},
+        "flops_convention": "A-table v1 (SURVEY 8d): 302 flop per executed Kepler solve + orbit, 746 per flux "
+                            "evaluation with the general code, 394 per evaluation with the planet fully inside the "
+                            "disk (the reference formula minus its 10 node cosines, 2 atan2 and the kite area, which "
+                            "are constants there); frac_r1_convention charges every evaluation 746 as round 1 did. "
+                            "`hardware` counts executed FP64 thread instructions instead (2 per DFMA, 1 per DMUL / DADD)",
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
     }
 
-    # ---- secondary numbers (rank 0, N = 1 only): dense mode, C2 Kepler ------------------------
-    secondary = {}
-    if world == 1 and not args.no_secondary:
-        n_sec = 3
-        timed_steps(2, flags=_lib.JXP_FLAG_NO_WINDOW, kernel_events=False)
-        d_tot, d_k = timed_steps(n_sec, flags=_lib.JXP_FLAG_NO_WINDOW)
-        _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 1, n_times, ctypes.addressof(stats), stream())
-        dk, dl = int(stats[0]), int(stats[1])
-        d_flops = dk * (W_KEPLER + W_ORBIT) + dl * W_LD
-        secondary["c3_dense_no_window"] = {
-            "points_per_s": n_sets * n_times / (d_tot / n_sec * 1e-3), "ms_per_step": d_tot / n_sec,
-            "fp64_frac": d_flops / (d_k / n_sec * 1e-3) / 1e12 / fp64_peak,
-            "executed": {"kepler_solves": dk, "ld_evaluations": dl}}
-        n2 = 100_000_000
-        M = torch.rand(n2, dtype=torch.float64, device=dev) * (2 * np.pi)
-        e = torch.rand(n2, dtype=torch.float64, device=dev) * 0.99
-        s_ = torch.empty_like(M)
-        c_ = torch.empty_like(M)
-        best = 1e30
-        for i in range(4):
-            ev0.record()
-            _lib.call("jxp_kepler_f64", M.data_ptr(), 1, e.data_ptr(), 1, n2, s_.data_ptr(), c_.data_ptr(),
-                      0, 0, 0, stream())
-            ev1.record()
-            torch.cuda.synchronize()
-            if i:
-                best = min(best, ev0.elapsed_time(ev1))
-        secondary["c2_kepler_1e8"] = {
-            "solves_per_s": n2 / (best * 1e-3), "ms": best,
-            "fp64_frac": n2 * W_KEPLER / (best * 1e-3) / 1e12 / fp64_peak,
-            "hbm_gbs": 32.0 * n2 / (best * 1e-3) / 1e9,
-            "hbm_frac": (32.0 * n2 / (best * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
-        del M, e, s_, c_
-        # K2: core.limb_dark.light_curve on 1e8 random in-transit (b, r) points
-        rr = torch.rand(n2, dtype=torch.float64, device=dev) * 0.12 + 0.03
-        bb = torch.rand(n2, dtype=torch.float64, device=dev) * (1 + rr)
-        u2 = torch.tensor([0.3, 0.2], dtype=torch.float64, device=dev)
-        f_ = torch.empty_like(bb)
-        best = 1e30
-        for i in range(4):
-            ev0.record()
-            _lib.call("jxp_limb_dark_f64", u2.data_ptr(), 2, bb.data_ptr(), 1, rr.data_ptr(), 1, n2, 10,
-                      f_.data_ptr(), 0, 0, 0, stream())
-            ev1.record()
-            torch.cuda.synchronize()
-            if i:
-                best = min(best, ev0.elapsed_time(ev1))
-        secondary["k2_limb_dark_1e8_in_transit"] = {
-            "evaluations_per_s": n2 / (best * 1e-3), "ms": best,
-            "fp64_frac": n2 * W_LD / (best * 1e-3) / 1e12 / fp64_peak}
-        del rr, bb, f_
-        secondary.update(secondary_c4_c5(dev, lib, ev0, ev1, peaks))
-
-    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, n_sample, threads, secs = cpu_points_per_s(bodies_h, u_h, t_h, y.cpu().numpy(), sigma)
-        cpu = {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
-               "sample": f"{n_sample} of {n_sets} sets x {n_times} times, {secs:.1f} s",
-               "note": "C/OpenMP restatement of the reference formulas (oracle/ref_c.c); not jax[cpu]"}
+        cpu = cpu_baseline_leg(p, u_h, t_h, y_np, sigma)
 
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
         "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 (C ABI) from the sampled elements; inputs in one pinned host arena, one H2D copy per step",
-                "python_api": {"value": points_per_step / (py_ms * 1e-3), "unit": "points/s", "ms_per_step": py_ms,
-                               "path": "light_curves.limb_dark.log_likelihood(System(...).add_body(**sampled elements), u)"
-                                       "(t, y, sigma): NumPy in, NumPy out, System rebuilt every step"}},
+        "e2e": {"value": points_per_step / (py_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": py_ms,
+                "path": ("light_curves.limb_dark.log_likelihood(System(Central()).add_body(**sampled elements), u)"
+                         "(t, y, sigma)" if world == 1 else
+                         "jaxoplanet_b200.distributed.log_likelihood_distributed(sampled elements, u, t, y, sigma)") +
+                        ": NumPy in, NumPy out, System rebuilt every step (K0 derives the constants on the device)",
+                "c_abi": {"value": points_per_step / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
+                          "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 from one pinned host arena "
+                                  "(one H2D copy per step), pinned D2H of the log-likelihoods"}},
+        "weak": weak,
         "gpu_launches": len(launches) * args.steps,
         "gpu_launches_per_step": launches,
         "clocks": clocks, "secondary": secondary,
@@ -533,19 +664,27 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
-    """Configs 4 and 5 at full size (timed, best of 3, device-resident inputs)."""
+def secondary_configs(dev, lib, ev0, ev1, rank, world, fp64_peak, max_over_ranks, barrier):
+    """Configs 1, 2, 4 and 5 at full size, their set / pair axis sharded over the ranks (no collective);
+    best of 3 per rank, max over ranks, whole-job rates."""
     import torch
 
     from jaxoplanet_b200 import _array as A
     from jaxoplanet_b200 import _lib
     from jaxoplanet_b200 import workloads as W
+    from jaxoplanet_b200.distributed import shard_range
     from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
 
     out = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
     def best_of(fn, n=3):
         best = 1e30
+        barrier()
         for i in range(n + 1):
             ev0.record()
             fn()
@@ -553,31 +692,64 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
             torch.cuda.synchronize()
             if i:
                 best = min(best, ev0.elapsed_time(ev1))
-        return best
+        return max_over_ranks(best)
 
-    # C1: the reference's own CPU-runnable case, 1 planet x 1e5 times, flux materialised
-    from jaxoplanet_b200.orbits.keplerian import System
+    # C2: batched Kepler solve, 1e8 (M, e) pairs
+    n2 = 100_000_000
+    lo, hi = shard_range(n2, rank, world)
+    g = torch.Generator(device=dev)
+    g.manual_seed(rank)
+    M = torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g) * (2 * np.pi)
+    e = torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g) * 0.99
+    s_ = torch.empty_like(M)
+    c_ = torch.empty_like(M)
+    ms = best_of(lambda: _lib.call("jxp_kepler_f64", M.data_ptr(), 1, e.data_ptr(), 1, hi - lo, s_.data_ptr(),
+                                   c_.data_ptr(), 0, 0, 0, A.stream_ptr()))
+    out["c2_kepler_1e8"] = {
+        "solves_per_s": n2 / (ms * 1e-3), "ms": ms,
+        "fp64_frac": n2 * W_KEPLER / (ms * 1e-3) / 1e12 / (fp64_peak * world),
+        "hbm_gbs": 32.0 * n2 / (ms * 1e-3) / 1e9,
+        "hbm_frac": (32.0 * n2 / (ms * 1e-3) / 1e9) / (peaks["hbm_gbs"] * world) if peaks.get("hbm_gbs") else None}
+    del M, e, s_, c_
+    if world == 1:
+        # K2: core.limb_dark.light_curve on 1e8 random in-transit (b, r) points
+        rr = torch.rand(n2, dtype=torch.float64, device=dev) * 0.12 + 0.03
+        bb = torch.rand(n2, dtype=torch.float64, device=dev) * (1 + rr)
+        u2 = torch.tensor([0.3, 0.2], dtype=torch.float64, device=dev)
+        f_ = torch.empty_like(bb)
+        ms = best_of(lambda: _lib.call("jxp_limb_dark_f64", u2.data_ptr(), 2, bb.data_ptr(), 1, rr.data_ptr(), 1, n2,
+                                       10, f_.data_ptr(), 0, 0, 0, A.stream_ptr()))
+        n_in = int((bb < 1 - rr).sum())
+        out["k2_limb_dark_1e8_in_transit"] = {
+            "evaluations_per_s": n2 / (ms * 1e-3), "ms": ms,
+            "fp64_frac": (n_in * W_LD_INSIDE + (n2 - n_in) * W_LD) / (ms * 1e-3) / 1e12 / fp64_peak,
+            "fp64_frac_r1_convention": n2 * W_LD / (ms * 1e-3) / 1e12 / fp64_peak,
+            "inside_disk_fraction": n_in / n2}
+        del rr, bb, f_
+        # C1: the reference's own CPU-runnable case, 1 planet x 1e5 times, flux materialised
+        from jaxoplanet_b200.orbits.keplerian import System
 
-    body1, u1, t1 = W.c1()
-    b1, _, _ = pack_bodies(System().add_body(**body1))
-    b1 = b1.to(dev).contiguous()
-    u1d = torch.as_tensor(np.asarray(u1, dtype=np.float64)).to(dev)
-    t1d = torch.as_tensor(t1).to(dev)
-    n1 = t1d.numel()
-    wsb1 = int(lib.jxp_system_workspace_bytes(1, 1, n1))
-    ws1 = torch.empty(wsb1, dtype=torch.uint8, device=dev)
-    f1 = torch.empty((1, n1, 1), dtype=torch.float64, device=dev)
-    ms = best_of(lambda: _lib.call("jxp_system_light_curve_f64", b1.data_ptr(), 1, 1, u1d.data_ptr(), 2, 0,
-                                   t1d.data_ptr(), n1, 0.0, 0, 0, 10, 0, f1.data_ptr(), 0, 0, 0, 0, 0,
-                                   ws1.data_ptr(), wsb1, A.stream_ptr()), n=5)
-    out["c1_single_planet_1e5_times"] = {"points_per_s": n1 / (ms * 1e-3), "ms": ms,
-                                         "in_transit_fraction": float((f1 != 0).double().mean())}
+        body1, u1, t1 = W.c1()
+        b1, _, _ = pack_bodies(System().add_body(**body1))
+        b1 = b1.to(dev).contiguous()
+        u1d = torch.as_tensor(np.asarray(u1, dtype=np.float64)).to(dev)
+        t1d = torch.as_tensor(t1).to(dev)
+        n1 = t1d.numel()
+        wsb1 = int(lib.jxp_system_workspace_bytes(1, 1, n1))
+        ws1 = torch.empty(wsb1, dtype=torch.uint8, device=dev)
+        f1 = torch.empty((1, n1, 1), dtype=torch.float64, device=dev)
+        ms = best_of(lambda: _lib.call("jxp_system_light_curve_f64", b1.data_ptr(), 1, 1, u1d.data_ptr(), 2, 0,
+                                       t1d.data_ptr(), n1, 0.0, 0, 0, 10, 0, f1.data_ptr(), 0, 0, 0, 0, 0,
+                                       ws1.data_ptr(), wsb1, A.stream_ptr()), n=5)
+        out["c1_single_planet_1e5_times"] = {"points_per_s": n1 / (ms * 1e-3), "ms": ms,
+                                             "in_transit_fraction": float((f1 != 0).double().mean())}
 
     # C4: 3 planets, 30-min cadence, 15x exposure supersampling, 1024 sets x 2e5 times
     p, u, t, expo = W.c4()
-    bodies, n_sets, _ = pack_bodies(W.system_from(p))
+    lo, hi = shard_range(1024, rank, world)
+    bodies, n_sets, _ = pack_bodies(W.system_from({k: v[lo:hi] for k, v in p.items()}))
     bodies = bodies.to(dev).contiguous()
-    ud = torch.as_tensor(u).to(dev).contiguous()
+    ud = torch.as_tensor(np.ascontiguousarray(u[lo:hi])).to(dev)
     td = torch.as_tensor(t).to(dev)
     n_times = td.numel()
     wsb = int(lib.jxp_system_workspace_bytes(n_sets, 3, n_times))
@@ -589,17 +761,18 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
     stats = (ctypes.c_int64 * 2)()
     _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 3, n_times, ctypes.addressof(stats), A.stream_ptr())
     out["c4_3planets_15x_supersampled"] = {
-        "points_per_s": n_sets * n_times / (ms * 1e-3), "ms": ms,
-        "inner_evaluations_per_s": n_sets * n_times * 45 / (ms * 1e-3),
-        "executed": {"kepler_solves": int(stats[0]), "ld_evaluations": int(stats[1])},
-        "tflops_executed": (int(stats[0]) * (W_KEPLER + W_ORBIT) + int(stats[1]) * W_LD) / (ms * 1e-3) / 1e12,
-        "in_transit_fraction": float((fs != 0).double().mean())}
+        "points_per_s": 1024 * n_times / (ms * 1e-3), "ms": ms,
+        "inner_evaluations_per_s": 1024 * n_times * 45 / (ms * 1e-3),
+        "rank0_executed": {"kepler_solves": int(stats[0]), "ld_evaluations": int(stats[1])},
+        "rank0_tflops_executed": (int(stats[0]) * (W_KEPLER + W_ORBIT) + int(stats[1]) * W_LD) / (ms * 1e-3) / 1e12,
+        "rank0_in_transit_fraction": float((fs != 0).double().mean())}
     del fs, ws, bodies
     torch.cuda.empty_cache()
 
     # C5: flux + 8 partials, 16384 sets x 5e4 times, f64 and f32
     theta, t5 = W.c5()
-    thd = torch.as_tensor(theta).to(dev).contiguous()
+    lo, hi = shard_range(16384, rank, world)
+    thd = torch.as_tensor(np.ascontiguousarray(theta[lo:hi])).to(dev)
     t5d = torch.as_tensor(t5).to(dev)
     ns5, nt5 = thd.shape[0], t5d.numel()
     star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
@@ -611,10 +784,10 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
         ms = best_of(lambda: _lib.call("jxp_transit_partials_" + nm, thd.data_ptr(), ns5, star.data_ptr(), 0,
                                        t5d.data_ptr(), nt5, 0.0, 0, 0, 10, 0, fl.data_ptr(), pt.data_ptr(), 0, 0, 0,
                                        0, 0, ws5.data_ptr(), wsb5, A.stream_ptr()))
-        gbs = ns5 * nt5 * 9 * fl.element_size() / (ms * 1e-3) / 1e9
+        gbs = 16384 * nt5 * 9 * fl.element_size() / (ms * 1e-3) / 1e9
         out["c5_flux_plus_8_partials_" + nm] = {
-            "points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms, "store_gbs": gbs,
-            "hbm_frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None}
+            "points_per_s": 16384 * nt5 / (ms * 1e-3), "ms": ms, "store_gbs": gbs,
+            "hbm_frac": gbs / (peaks["hbm_gbs"] * world) if peaks.get("hbm_gbs") else None}
         del fl, pt
         torch.cuda.empty_cache()
     # C5 as a gradient step: log-likelihood and its 8-gradient reduced in the kernel, no rows stored
@@ -628,10 +801,11 @@ def secondary_c4_c5(dev, lib, ev0, ev1, peaks):
     ls5 = (ctypes.c_int64 * 4)()
     _lib.call("jxp_transit_list_stats", ws5.data_ptr(), ns5, nt5, ctypes.addressof(ls5), A.stream_ptr())
     out["c5_loglike_plus_8_gradient_f64"] = {
-        "points_per_s": ns5 * nt5 / (ms * 1e-3), "ms": ms,
+        "points_per_s": 16384 * nt5 / (ms * 1e-3), "ms": ms,
         "path": "transit list (k_tl_build, k_tlg_eval, k_tlg_reduce)" if (ls5[0] > 0 and ls5[1] == 0)
                 else "window-test kernel (k_transit_partials)",
-        "list_items": int(ls5[0])}
+        "rank0_list_items": int(ls5[0])}
+    out["sharding"] = f"set / pair axis split over {world} rank(s), no collective; time = max over ranks"
     return out
 
 

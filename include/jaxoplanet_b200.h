@@ -291,6 +291,9 @@ enum {
   JXP_EL_NFIELDS = 16
 };
 int jxp_orbital_elements_f64(const double* elements, int64_t n, double* bodies, void* stream);
+/* The same with the element records field-major, elements[JXP_EL_NFIELDS][n]: a host that holds one array
+ * per sampled parameter (a dict of (n,) arrays) packs them with contiguous copies. */
+int jxp_orbital_elements_soa_f64(const double* elements, int64_t n, double* bodies, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K6  light_curves.limb_dark.light_curve(TransitOrbit | TTVOrbit, u)(t)

@@ -94,6 +94,7 @@ SIGNATURES = {
     "jxp_transit_orbit_light_curve_f64": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_transit_orbit_light_curve_f32": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
     "jxp_orbital_elements_f64": (C.c_int, [_p, _i64, _p, _p]),
+    "jxp_orbital_elements_soa_f64": (C.c_int, [_p, _i64, _p, _p]),
     "jxp_orbit_state_f64": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p]),
     "jxp_orbit_state_f32": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p]),
     "jxp_interp_periodic_f64": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),

@@ -222,11 +222,15 @@ extern "C" int jxp_interp_periodic_f32(const double* xp, const float* fp, int32_
 // central mass and radius come in resolved).  One thread per (set, body); NaN marks "not given"
 // (None in the reference).  Same operation order as the reference; libm calls are CUDA's (<= 1-2 ulp
 // from XLA's / NumPy's).
+// SOA: the element records come field-major, [JXP_EL_NFIELDS][n] (what a host packs with contiguous copies)
+template <bool SOA>
 __global__ void __launch_bounds__(128)
 k_orbital_elements(const double* __restrict__ el, int64_t n, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double* p = el + i * JXP_EL_NFIELDS;
+  double p[JXP_EL_NFIELDS];
+#pragma unroll
+  for (int k = 0; k < JXP_EL_NFIELDS; ++k) p[k] = SOA ? el[(int64_t)k * n + i] : el[i * JXP_EL_NFIELDS + k];
   const double pi = 3.141592653589793238462643383279502884;
   const double G = 2942.2062175044193;  // src/jaxoplanet/constants.py:2
   const double central_mass = p[JXP_EL_CENTRAL_MASS], central_radius = p[JXP_EL_CENTRAL_RADIUS];
@@ -293,8 +297,16 @@ extern "C" int jxp_orbital_elements_f64(const double* elements, int64_t n, doubl
   if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_orbital_elements: n = %lld < 0", (long long)n);
   if (n == 0) return JXP_OK;
   if (!elements || !bodies) return fail(JXP_ERR_NULL_POINTER, "jxp_orbital_elements: null pointer");
-  k_orbital_elements<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(elements, n, bodies);
+  k_orbital_elements<false><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(elements, n, bodies);
   return check_launch("jxp_orbital_elements");
+}
+
+extern "C" int jxp_orbital_elements_soa_f64(const double* elements, int64_t n, double* bodies, void* stream) {
+  if (n < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_orbital_elements_soa: n = %lld < 0", (long long)n);
+  if (n == 0) return JXP_OK;
+  if (!elements || !bodies) return fail(JXP_ERR_NULL_POINTER, "jxp_orbital_elements_soa: null pointer");
+  k_orbital_elements<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(elements, n, bodies);
+  return check_launch("jxp_orbital_elements_soa");
 }
 
 extern "C" int jxp_transit_orbit_light_curve_f64(const double* planets, int32_t n_planets,

@@ -48,10 +48,12 @@ def reduce_time_shards(local: torch.Tensor) -> torch.Tensor:
 
 
 def _cuda_evaluate(params, u, t, y, sigma):
+    """The fused CUDA path on this rank's block; the result STAYS on the device (the collective that follows
+    runs over NCCL), whatever the inputs were."""
     from jaxoplanet_b200 import workloads
-    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood
+    from jaxoplanet_b200.light_curves.limb_dark import FusedSpec, _run_fused
 
-    return log_likelihood(workloads.system_from(params), u)(t, y, sigma)
+    return _run_fused(FusedSpec(workloads.system_from(params), u), t, want="loglike", y=y, sigma=sigma)
 
 
 def log_likelihood_distributed(params: dict, u, t, y, sigma, *, evaluate=None) -> torch.Tensor:

@@ -132,15 +132,46 @@ class FusedSpec:
     flags: int = 0
 
 
-def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=None):
+def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=None, host_sync=False):
     orbit = spec.orbit
     dt = dtype or A.result_dtype(time, spec.ld_u, *[b.period for b in orbit.bodies])
     dev = A.device()
     bodies, n_sets, batched = pack_bodies(orbit)
     n_bodies = bodies.shape[1]
-    bodies = bodies.to(dev).contiguous()
+    if bodies.device != dev or not bodies.is_contiguous():
+        bodies = bodies.to(dev).contiguous()
+    if want not in ("flux", "flux_sum", "loglike"):
+        raise ValueError(want)
+    # host inputs (NumPy arrays, lists, scalars) of the call go to the device together: one pinned arena, one DMA
     u = spec.ld_u
-    u = u.detach().to(torch.float64) if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u, dtype=np.float64))
+    host, slots = [], {}
+    # host_sync: the caller reads the result back (NumPy out) before it returns to ITS caller, i.e. it
+    # synchronises: large host arrays may then be read by DMA straight out of the user's (page-locked) memory
+    sync_follows = bool(host_sync)
+
+    def place(name, x, dtype_):
+        if isinstance(x, torch.Tensor):
+            slots[name] = x.detach().to(device=dev, dtype=dtype_).contiguous()
+        elif dtype_ == torch.float64:
+            arr = np.asarray(x, dtype=np.float64)
+            direct = A.registered_to_dev(arr) if sync_follows else None
+            if direct is not None:
+                slots[name] = direct
+            else:
+                slots[name] = len(host)
+                host.append(arr)
+        else:
+            slots[name] = A.to_dev(x, dtype_)
+
+    place("u", u, torch.float64)
+    place("t", time, torch.float64)
+    if want == "loglike":
+        place("y", y, dt)
+        place("sigma", sigma, dt)
+    if host:
+        staged = A.stage_f64(host)
+        slots = {k: (staged[v] if isinstance(v, int) else v) for k, v in slots.items()}
+    u = slots["u"]
     if u.ndim == 2:
         if u.shape[0] != n_sets:
             raise ValueError("batched limb-darkening coefficients must have shape (n_sets, n_u)")
@@ -149,8 +180,7 @@ def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=
     else:
         u_stride = 0
         n_u = u.shape[0]
-    u = u.to(dev).contiguous()
-    t = A.to_dev(time, torch.float64)
+    t = slots["t"]
     t_shape = tuple(t.shape)
     t = t.reshape(-1)
     n_times = t.numel()
@@ -163,10 +193,10 @@ def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=
         flux = torch.empty((n_sets, n_times, n_bodies), dtype=dt, device=dev)
     elif want == "flux_sum":
         flux_sum = torch.empty((n_sets, n_times), dtype=dt, device=dev)
-    elif want == "loglike":
+    else:
         loglike = torch.empty((n_sets,), dtype=dt, device=dev)
-        yd = A.to_dev(y, dt).reshape(-1)
-        sd = A.to_dev(sigma, dt).reshape(-1)
+        yd = slots["y"].reshape(-1)
+        sd = slots["sigma"].reshape(-1)
         if yd.numel() != n_times:
             raise ValueError("y must have the shape of the time array")
         if sd.numel() == 1:
@@ -175,8 +205,6 @@ def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=
             s_stride = 1
         else:
             raise ValueError("sigma must be a scalar or have the shape of the time array")
-    else:
-        raise ValueError(want)
     name = "jxp_system_light_curve_f64" if dt == torch.float64 else "jxp_system_light_curve_f32"
     expo = 0.0 if spec.exposure_time is None else float(spec.exposure_time)
     _lib.call(name, A.ptr(bodies), n_sets, n_bodies, A.ptr(u), n_u, u_stride, A.ptr(t), n_times,
@@ -192,6 +220,11 @@ def _run_fused(spec: FusedSpec, time, *, want="flux", y=None, sigma=None, dtype=
     if not batched:
         out = out[0]
     return out
+
+
+def _all_host(*xs) -> bool:
+    """No torch tensor among the inputs: like_input() will hand back NumPy, after a device-to-host copy."""
+    return not any(isinstance(x, torch.Tensor) for x in xs)
 
 
 def _concat_u(u):
@@ -221,7 +254,7 @@ def light_curve(orbit, *u, order: int = 10):
         spec = FusedSpec(orbit=orbit, ld_u=ld_u, order=order)
 
         def light_curve_impl(time):
-            return A.like_input(_run_fused(spec, time), time)
+            return A.like_input(_run_fused(spec, time, host_sync=_all_host(time)), time)
 
         light_curve_impl._jxp_spec = spec
         return light_curve_impl
@@ -287,7 +320,8 @@ def log_likelihood(orbit: System, *u, order: int = 10, exposure_time=None, exp_o
                      exp_order=exp_order, num_samples=num_samples)
 
     def impl(time, y, sigma):
-        return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma), time, y)
+        return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma, host_sync=_all_host(time, y)),
+                            time, y)
 
     impl._jxp_spec = spec
     impl._jxp_want = "loglike"
@@ -300,14 +334,15 @@ def with_spec(func, **changes):
     spec = replace(func._jxp_spec, **changes)
     if getattr(func, "_jxp_want", "flux") == "loglike":
         def loglike_impl(time, y, sigma):
-            return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma), time, y)
+            return A.like_input(_run_fused(spec, time, want="loglike", y=y, sigma=sigma, host_sync=_all_host(time, y)),
+                            time, y)
 
         loglike_impl._jxp_spec = spec
         loglike_impl._jxp_want = "loglike"
         return loglike_impl
 
     def light_curve_impl(time):
-        return A.like_input(_run_fused(spec, time), time)
+        return A.like_input(_run_fused(spec, time, host_sync=_all_host(time)), time)
 
     light_curve_impl._jxp_spec = spec
     return light_curve_impl

@@ -64,8 +64,22 @@ class Central:
         if _bad_rank((mass, radius, density)):
             raise ValueError("All parameters of a KeplerianCentral must be scalars")
 
-        mass, radius, density = _t(mass), _t(radius), _t(density)
         error_msg = "Values must be provided for exactly two of mass, radius, and density"
+        if all(x is None or isinstance(x, (int, float)) for x in (mass, radius, density)):
+            # plain Python scalars (the common case, and the default Central()): the two-of-three rule in
+            # float arithmetic, three tensors at the end instead of a dozen 0-d tensor operations
+            if sum(x is None for x in (mass, radius, density)) != 1:
+                raise ValueError(error_msg)
+            if density is None:
+                density = 3 * mass / (4 * math.pi * radius**3)
+            elif radius is None:
+                radius = (3 * mass / (4 * math.pi * density)) ** (1 / 3)
+            else:
+                mass = 4 * math.pi * radius**3 * density / 3.0
+            self.mass, self.radius, self.density = (torch.tensor(float(x), dtype=torch.float64)
+                                                    for x in (mass, radius, density))
+            return
+        mass, radius, density = _t(mass), _t(radius), _t(density)
         if density is None:
             if mass is None or radius is None:
                 raise ValueError(error_msg)
@@ -163,6 +177,12 @@ class Body:
             raise ValueError("Only one of time_transit or time_peri can be specified")
 
 
+_EL_NAMES = ("period", "semimajor", "time_transit", "time_peri", "eccentricity", "omega_peri", "sin_omega_peri",
+             "cos_omega_peri", "impact_param", "inclination", "mass", "radius", "parallax")
+_EL_INDEX = dict(period=0, semimajor=1, time_transit=2, time_peri=3, eccentricity=4, omega_peri=5, sin_omega_peri=6,
+                 cos_omega_peri=7, impact_param=8, inclination=9, mass=10, radius=11, parallax=14)  # JXP_EL_*
+
+
 class OrbitalBody:
     """A body with its derived orbital constants (keplerian.py:241-637)."""
 
@@ -256,49 +276,71 @@ class OrbitalBody:
         what keplerian.py:262-340 derives; the attributes are views of its output.  Returns False when the
         call is not of that kind (torch inputs, ascending node, RV semi-amplitude, no CUDA device): the
         host path below then does the same arithmetic with torch."""
-        if not A.batch_ndim() or not torch.cuda.is_available():
+        if not A.batch_ndim():
             return False
-        if any(getattr(body, k) is not None for k in
-               ("asc_node", "sin_asc_node", "cos_asc_node", "radial_velocity_semiamplitude")):
+        if (body.asc_node is not None or body.sin_asc_node is not None or body.cos_asc_node is not None
+                or body.radial_velocity_semiamplitude is not None):
             return False
-        names = ("period", "semimajor", "time_transit", "time_peri", "eccentricity", "omega_peri",
-                 "sin_omega_peri", "cos_omega_peri", "impact_param", "inclination", "mass", "radius", "parallax")
-        given = {k: getattr(body, k) for k in names if getattr(body, k) is not None}
-        vals = list(given.values()) + [central.mass, central.radius]
-        if any(isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad) for v in vals):
+        given, n = {}, 0
+        for k in _EL_NAMES:
+            v = getattr(body, k)
+            if v is not None:
+                given[k] = v
+        for v in (*given.values(), central.mass, central.radius):
+            if isinstance(v, torch.Tensor):
+                if v.is_cuda or v.requires_grad or v.dtype == torch.float32:
+                    return False
+                nd, n0 = v.ndim, (v.shape[0] if v.ndim == 1 else 0)
+            else:
+                if isinstance(v, np.ndarray) and v.dtype == np.float32:
+                    return False  # (the fp32 mode keeps its inputs' dtype through the host path)
+                nd = np.ndim(v)
+                n0 = np.shape(v)[0] if nd == 1 else 0
+            if nd == 1:
+                if n and n0 != n:
+                    return False
+                n = n0
+        if n < self._DEVICE_MIN_SETS:
             return False
-        if any(np.asarray(v).dtype == np.float32 for v in vals):
-            return False  # (the fp32 mode keeps its inputs' dtype through the host path)
-        n = max((np.shape(v)[0] for v in vals if np.ndim(v) == 1), default=0)
-        if n < self._DEVICE_MIN_SETS or any(np.ndim(v) == 1 and np.shape(v)[0] != n for v in vals):
-            return False
+        try:
+            dev = A.device()
+        except RuntimeError:
+            return False  # no CUDA device: the host arithmetic below (records can still be packed and checked)
         from jaxoplanet_b200 import _lib
-        from jaxoplanet_b200.light_curves.limb_dark import pack_elements
 
-        el = pack_elements(n, central_mass=np.asarray(central.mass), central_radius=np.asarray(central.radius),
-                           **{k: np.asarray(v) for k, v in given.items()})
-        dev = A.device()
-        eld = A.host_to_dev(el)
+        # the element records are packed straight into a page-locked arena, FIELD-major (one contiguous row
+        # per Body argument; include/jaxoplanet_b200.h, JXP_EL_*; NaN = not given), and go over in one DMA
+        nf = _lib.JXP_EL_NFIELDS
+        view, commit = A.stage_view(n * nf)
+        el = view[: n * nf].reshape(nf, n)
+        el[_lib.EL_CENTRAL_MASS] = float(central.mass) if np.ndim(central.mass) == 0 else central.mass
+        el[_lib.EL_CENTRAL_RADIUS] = float(central.radius) if np.ndim(central.radius) == 0 else central.radius
+        el[_lib.EL_RESERVED] = 0.0
+        for k in _EL_NAMES:
+            v = given.get(k)
+            el[_EL_INDEX[k]] = np.nan if v is None else v
+        eld = commit()[: n * nf].view(nf, n)
         rec = torch.empty((n, _lib.JXP_BODY_NFIELDS), dtype=torch.float64, device=dev)
-        _lib.call("jxp_orbital_elements_f64", eld.data_ptr(), n, rec.data_ptr(), A.stream_ptr())
+        _lib.call("jxp_orbital_elements_soa_f64", eld.data_ptr(), n, rec.data_ptr(), A.stream_ptr())
         self._record = rec
         circular = body.eccentricity is None
-        self.period = rec[:, _lib.BODY_PERIOD]
-        self.time_transit = rec[:, _lib.BODY_TIME_TRANSIT]
-        self.time_ref = rec[:, _lib.BODY_TIME_REF]
-        self.eccentricity = None if circular else rec[:, _lib.BODY_ECC]
-        self.cos_omega_peri = None if circular else rec[:, _lib.BODY_COS_OMEGA]
-        self.sin_omega_peri = None if circular else rec[:, _lib.BODY_SIN_OMEGA]
-        self.cos_inclination = rec[:, _lib.BODY_COS_INCL]
-        self.sin_inclination = rec[:, _lib.BODY_SIN_INCL]
-        self.semimajor = rec[:, _lib.BODY_SEMIMAJOR] if body.parallax is None else \
-            rec[:, _lib.BODY_SEMIMAJOR] * constants.au / eld[:, _lib.EL_PARALLAX]
-        self.radius = None if body.radius is None else rec[:, _lib.BODY_RADIUS]
-        self.mass = None if body.mass is None else eld[:, _lib.EL_MASS]
-        self.parallax = None if body.parallax is None else eld[:, _lib.EL_PARALLAX]
+        cols = rec.unbind(1)
+        self.period = cols[_lib.BODY_PERIOD]
+        self.time_transit = cols[_lib.BODY_TIME_TRANSIT]
+        self.time_ref = cols[_lib.BODY_TIME_REF]
+        self.eccentricity = None if circular else cols[_lib.BODY_ECC]
+        self.cos_omega_peri = None if circular else cols[_lib.BODY_COS_OMEGA]
+        self.sin_omega_peri = None if circular else cols[_lib.BODY_SIN_OMEGA]
+        self.cos_inclination = cols[_lib.BODY_COS_INCL]
+        self.sin_inclination = cols[_lib.BODY_SIN_INCL]
+        self.semimajor = cols[_lib.BODY_SEMIMAJOR] if body.parallax is None else \
+            cols[_lib.BODY_SEMIMAJOR] * constants.au / eld[_lib.EL_PARALLAX]
+        self.radius = None if body.radius is None else cols[_lib.BODY_RADIUS]
+        self.mass = None if body.mass is None else eld[_lib.EL_MASS]
+        self.parallax = None if body.parallax is None else eld[_lib.EL_PARALLAX]
         self.radial_velocity_semiamplitude = None
         self.sin_asc_node = self.cos_asc_node = None
-        self._impact_param_given = None if body.impact_param is None else eld[:, _lib.EL_IMPACT_PARAM]
+        self._impact_param_given = None if body.impact_param is None else eld[_lib.EL_IMPACT_PARAM]
         return True
 
     @property

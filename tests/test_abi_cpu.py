@@ -136,3 +136,51 @@ def test_orbital_constants_match_oracle():
     want = ref.orbital_body(period=12.5, inclination=0.3, mass=0.1)
     for name in ("semimajor", "time_ref", "sin_inclination", "cos_inclination", "impact_param"):
         np.testing.assert_allclose(float(getattr(body, name)), want[name], rtol=4e-16, err_msg=name)
+
+
+def test_pack_bodies_batch_axis_comes_from_any_field():
+    """A fixed ephemeris with sampled impact parameter / radius (scalar period, batched b and r) is a batch
+    of parameter sets: the set axis is the longest leading axis over every packed field."""
+    import numpy as np
+
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    rng = np.random.default_rng(0)
+    b = rng.uniform(0, 1, 8)
+    with jxp.batched():
+        sysm = System(Central()).add_body(period=3.0, impact_param=b, radius=0.1)
+    recs, n_sets, batched = pack_bodies(sysm)
+    assert n_sets == 8 and batched and tuple(recs.shape) == (8, 1, 12)
+    recs = recs.cpu().numpy()
+    assert np.all(recs[:, 0, 0] == 3.0)
+    # cos i = b R* / a differs per set
+    assert len(np.unique(recs[:, 0, 6])) == 8
+    with pytest.raises((ValueError, RuntimeError)):  # two different batch lengths: refused, never mis-stacked
+        with jxp.batched():
+            pack_bodies(System(Central()).add_body(period=np.full(4, 3.0), impact_param=b, radius=0.1))
+
+
+def test_interpolate_rejects_batched_orbits_and_integrate_keeps_loglike_signature():
+    import inspect
+
+    import numpy as np
+
+    import jaxoplanet_b200 as jxp
+    from jaxoplanet_b200.light_curves import limb_dark_light_curve, transforms
+    from jaxoplanet_b200.light_curves.limb_dark import log_likelihood
+    from jaxoplanet_b200.orbits.keplerian import Central, System
+
+    with jxp.batched():
+        sysm = System(Central()).add_body(period=np.array([3.0, 4.0]), impact_param=0.2, radius=0.1)
+    lc = limb_dark_light_curve(sysm, [0.3, 0.2])
+    ll = log_likelihood(sysm, [0.3, 0.2])
+    integ = transforms.integrate(ll, exposure_time=0.01, num_samples=3)
+    assert list(inspect.signature(integ).parameters) == ["time", "y", "sigma"]
+    assert list(inspect.signature(transforms.integrate(lc, exposure_time=0.01)).parameters) == ["time"]
+    # interpolate() builds ONE table for ONE ephemeris: a batched orbit must be refused before any compute
+    with pytest.raises((ValueError, RuntimeError)) as ei:
+        transforms.interpolate(lambda tt: np.zeros((2, 16, 1)), period=3.0, time_transit=0.0, num_samples=16)(
+            np.linspace(0, 1, 5))
+    assert "grid axis" in str(ei.value) or "leading" in str(ei.value)

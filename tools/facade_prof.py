@@ -10,9 +10,24 @@ def step():
 for _ in range(5): step()
 torch.cuda.synchronize()
 t0=time.perf_counter()
-for _ in range(20): step()
-print("ms/step", (time.perf_counter()-t0)/20*1e3)
+for _ in range(50): step()
+print("ms/step", (time.perf_counter()-t0)/50*1e3)
+# host time before the result is awaited: the same step with the final D2H replaced by nothing
+from jaxoplanet_b200.light_curves.limb_dark import FusedSpec, _run_fused
+def host_only():
+    s = W.system_from(p)
+    return _run_fused(FusedSpec(s, u), t, want="loglike", y=y, sigma=sigma)
+for _ in range(3): host_only()
+torch.cuda.synchronize()
+ts=[]
+for _ in range(30):
+    torch.cuda.synchronize(); t0=time.perf_counter(); r=host_only(); ts.append(time.perf_counter()-t0)
+print("host prelude (launches issued, no sync) ms", 1e3*np.median(ts))
+ts=[]
+for _ in range(30):
+    torch.cuda.synchronize(); t0=time.perf_counter(); s=W.system_from(p); ts.append(time.perf_counter()-t0)
+print("system_from ms", 1e3*np.median(ts))
 pr=cProfile.Profile(); pr.enable()
-for _ in range(20): step()
+for _ in range(50): step()
 pr.disable()
-s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats('cumulative').print_stats(28); print(s.getvalue()[:4500])
+s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats('tottime').print_stats(45); print(s.getvalue()[:7000])
