@@ -504,6 +504,32 @@ def run_ours(args, rank, local_rank, world):
         del probw, llw_all
         torch.cuda.empty_cache()
 
+    # ---- optional flux all-gather (north_star): the materialised light curves, 3.28 GB in all, on every rank ----
+    flux_gather = None
+    if world > 1 and not args.no_secondary:
+        n_loc_ = hi - lo
+        f_loc = torch.empty((n_loc_, n_times), dtype=torch.float64, device=dev)
+        f_all = torch.empty((N_SETS, n_times), dtype=torch.float64, device=dev)
+        prob.call(flux_sum=f_loc)  # this rank's rows (transit walk, flux mode)
+        best = 1e30
+        for i in range(4):
+            barrier()
+            ev0.record()
+            dist.all_gather_into_tensor(f_all, f_loc)
+            ev1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, ev0.elapsed_time(ev1))
+        best = max_over_ranks(best)
+        recv = (N_SETS - n_loc_) * n_times * 8
+        ok = bool(torch.equal(f_all[lo:hi], f_loc))
+        flux_gather = {"ms": best, "bytes_total": N_SETS * n_times * 8, "bytes_received_per_rank": recv,
+                       "gbs_received_per_rank": recv / (best * 1e-3) / 1e9, "own_rows_intact": ok,
+                       "how": "ncclAllGather (torch.distributed.all_gather_into_tensor) of the per-rank flux rows over "
+                              "NVLink, best of 3, max over ranks; not part of the timed step"}
+        del f_loc, f_all
+        torch.cuda.empty_cache()
+
     # ---- e2e through the public Python API (headline): NumPy in, NumPy out --------------------------
     from jaxoplanet_b200.light_curves.limb_dark import log_likelihood as facade_ll
 
@@ -654,7 +680,7 @@ def run_ours(args, rank, local_rank, world):
                 "c_abi": {"value": points_per_step / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
                           "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 from one pinned host arena "
                                   "(one H2D copy per step), pinned D2H of the log-likelihoods"}},
-        "weak": weak,
+        "weak": weak, "flux_all_gather": flux_gather,
         "gpu_launches": len(launches) * args.steps,
         "gpu_launches_per_step": launches,
         "clocks": clocks, "secondary": secondary,

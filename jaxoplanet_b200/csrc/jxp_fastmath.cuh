@@ -204,6 +204,67 @@ __device__ __forceinline__ double frcp_fast(double x) {
   return fma(y, e, y);
 }
 
+// The quadrature-node versions of sqrt and 1 / x: z = sqrt(z^2) and 1 / (1 + z) inside the factor
+// 1 + z^2 / (1 + z) of one node term of limb_dark.py:160-172.  With y the 2^-20 seed of 1 / sqrt(x), g = x y
+// and the residual e = 1 - y g = -2 eps - eps^2:  sqrt(x) = g (1 + e / 2 + 3 e^2 / 8 + O(e^3)).
+//   order 3: g + (g e) (1/2 + 3 e / 8)  -- 5 FP64 instructions, <= ~0.51 ulp like fsqrt_fast (which takes 6)
+//   order 2: g + (g e) / 2              -- 4 instructions, relative error 1.5 eps^2 <= 1.4e-12
+// and for the reciprocal, e = 1 - x y:  order 3: y + y (e + e^2) (3 instructions), order 2: y + y e (2; eps^2).
+#ifndef JXP_NODE_SQRT_ORDER
+#define JXP_NODE_SQRT_ORDER 3
+#endif
+#ifndef JXP_NODE_RCP_ORDER
+#define JXP_NODE_RCP_ORDER 3
+#endif
+__device__ __forceinline__ double fsqrt_node(double x) {
+  const double y = rsqrt_seed(x);
+  const double g = x * y;
+  const double e = fma(-y, g, 1.0);
+  const double ge = g * e;
+#if JXP_NODE_SQRT_ORDER == 3
+  return fma(ge, fma(e, 0.375, 0.5), g);
+#else
+  return fma(ge, 0.5, g);
+#endif
+}
+__device__ __forceinline__ double frcp_node(double x) {
+  const double y = rcp_seed(x);
+  double e = fma(-x, y, 1.0);
+#if JXP_NODE_RCP_ORDER == 3
+  e = fma(e, e, e);
+#endif
+  return fma(y, e, y);
+}
+
+// t = (1 - z^3) / (1 - z^2) = 1 + z^2 / (1 + z) from x = z^2 in (0, 1]: the node factor of limb_dark.py:160-172.
+// Both hardware seeds are issued at the start -- the reciprocal's from 1 + g with g = x y the UNREFINED root
+// (off by 2^-20, which the third-order step absorbs: (1.5e-6)^3 ~ 3e-18) -- so that neither MUFU latency sits
+// behind the square root's refinement on the critical path.
+#ifndef JXP_NODE_EARLY_SEED
+#define JXP_NODE_EARLY_SEED 0
+#endif
+__device__ __forceinline__ double fnode_factor(double x) {
+#if JXP_NODE_EARLY_SEED
+  const double y = rsqrt_seed(x);
+  const double g = x * y;
+  const double v = rcp_seed(1.0 + g);
+  const double e = fma(-y, g, 1.0);
+  const double ge = g * e;
+#if JXP_NODE_SQRT_ORDER == 3
+  const double z = fma(ge, fma(e, 0.375, 0.5), g);
+#else
+  const double z = fma(ge, 0.5, g);
+#endif
+  double e2 = fma(-(z + 1.0), v, 1.0);
+  e2 = fma(e2, e2, e2);
+  const double w = fma(v, e2, v);
+  return fma(x, w, 1.0);
+#else
+  const double z = fsqrt_node(x);
+  return fma(x, frcp_node(z + 1.0), 1.0);
+#endif
+}
+
 __device__ __constant__ double c_atan[11] = {
     -0.33333333333333120084,
     0.19999999999940620353,

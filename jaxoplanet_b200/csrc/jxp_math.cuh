@@ -265,6 +265,14 @@ __device__ __constant__ double c_gl10[3][10] = {
      0.23172567069845093, -0.23172567069845082, -0.6293961480326326, -0.8758595017700398,
      -0.9776208824732407, -0.9991601288170098}};
 
+// w_i c_i for the constant node cosines of a planet fully inside the disk (c_gl10[1][i] * c_gl10[2][i])
+__device__ __constant__ double c_gl10_wc[10] = {
+    0.06667134430868714 * 0.9991601288170098,  0.14945134915058053 * 0.9776208824732407,
+    0.21908636251598224 * 0.8758595017700398,  0.26926671930999674 * 0.6293961480326326,
+    0.2955242247147533 * 0.23172567069845093,  0.2955242247147533 * -0.23172567069845082,
+    0.26926671930999674 * -0.6293961480326326, 0.21908636251598224 * -0.8758595017700398,
+    0.14945134915058053 * -0.9776208824732407, 0.06667134430868714 * -0.9991601288170098};
+
 // ORDER == 11 is a tag: order 10 with a rolled (partially unrolled) node loop reading the tables
 // from the constant bank -- small code for the fused kernels, where instruction fetch matters.
 template <>
@@ -482,8 +490,8 @@ __device__ __forceinline__ void ld_solution(S b, S r, int lmax, const GLTable* _
         const double omz2 = fma(-two_br, c, r2pb2);
         const bool dead = !((omz2 >= eps10) && (omz2 <= 1.0 - eps10));
         const double z2s = dead ? 1.0 : 1.0 - omz2;
-        const double z = fsqrt_fast(z2s);
-        const double t = fma(z2s, frcp_fast(z + 1.0), 1.0);  // (1 - z^3) / (1 - z^2)
+        const double z = fsqrt_node(z2s);
+        const double t = fma(z2s, frcp_node(z + 1.0), 1.0);  // (1 - z^3) / (1 - z^2)
         const double res = fma(-b, c, r) * t;
         pair += dead ? 0.0 : res;
       }
@@ -633,12 +641,12 @@ __device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const dou
     return;
   }
   // l = 1 term of p_integral (limb_dark.py:140-173, 184) over the 5 mirror pairs of nodes
-  double sh[N], ch[N], rng[N], two_br[N], r2pb2[N], acc[N];
+  double sh[N], ch[N], rng[N], two_br[N], omr2b2[N], acc[N];
 #pragma unroll
   for (int q = 0; q < N; ++q) {
     rng[q] = k0[q] * 0.5;
     two_br[q] = b[q] * r[q] * 2.0;
-    r2pb2[q] = r2[q] + b2[q];
+    omr2b2[q] = 1.0 - (r2[q] + b2[q]);
     acc[q] = 0.0;
   }
 #pragma unroll
@@ -646,7 +654,7 @@ __device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const dou
 #pragma unroll PU
   for (int p = 0; p < 5; ++p) {
     const double xp = c_gl10[0][5 + p], wp = c_gl10[1][5 + p];
-    double c[2 * N], z2s[2 * N], z[2 * N], t[2 * N];
+    double c[2 * N], z2s[2 * N], t[2 * N];
     bool dead[2 * N];
 #pragma unroll
     for (int q = 0; q < N; ++q) {
@@ -656,16 +664,17 @@ __device__ __forceinline__ void ld_solution_n(const double (&b_in)[N], const dou
       c[2 * q] = fma(-sh[q], sa, t1);
       c[2 * q + 1] = fma(sh[q], sa, t1);
     }
+    // z^2 = 1 - (r^2 + b^2 - 2 b r c) as ONE fma, (1 - r^2 - b^2) + (2 b r) c -- the same quantity to an ulp
+    // of 1, which is the precision the reference's own 1 - omz2 has; the guards 1 - z^2 < 10 eps and
+    // z^2 < 10 eps (limb_dark.py:163-170) are read off z^2
 #pragma unroll
     for (int m = 0; m < 2 * N; ++m) {
-      const double omz2 = fma(-two_br[m >> 1], c[m], r2pb2[m >> 1]);
-      dead[m] = !((omz2 >= eps10) && (omz2 <= 1.0 - eps10));
-      z2s[m] = dead[m] ? 1.0 : 1.0 - omz2;
+      const double z2 = fma(two_br[m >> 1], c[m], omr2b2[m >> 1]);
+      dead[m] = !((z2 <= 1.0 - eps10) && (z2 >= eps10));
+      z2s[m] = dead[m] ? 1.0 : z2;
     }
 #pragma unroll
-    for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2s[m]);
-#pragma unroll
-    for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2s[m], frcp_fast(z[m] + 1.0), 1.0);
+    for (int m = 0; m < 2 * N; ++m) t[m] = fnode_factor(z2s[m]);
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       const double ra = fma(-b[q], c[2 * q], r[q]) * t[2 * q];
@@ -791,9 +800,7 @@ __device__ __forceinline__ void ld_solution_inside_n(const double (&b_in)[N], co
       z2s[m] = dead[m] ? 1.0 : 1.0 - omz2;
     }
 #pragma unroll
-    for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2s[m]);
-#pragma unroll
-    for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2s[m], frcp_fast(z[m] + 1.0), 1.0);
+    for (int m = 0; m < 2 * N; ++m) t[m] = fnode_factor(z2s[m]);
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       const double ra = fma(-b[q], cm, r[q]) * t[2 * q];

@@ -290,8 +290,13 @@ constexpr int TR_QCAP = 128;
 #ifndef JXP_TR_MINB
 #define JXP_TR_MINB 3
 #endif
+// the float instantiations need ~115 registers: one more CTA per SM keeps more row stores in flight
+#ifndef JXP_TR_MINB_F32
+#define JXP_TR_MINB_F32 4
+#endif
 template <typename T, int ORDER, bool LOGLIKE>
-__global__ void __launch_bounds__(128, JXP_TR_MINB) k_transit_partials(const __grid_constant__ TrArgs<T> a) {
+__global__ void __launch_bounds__(128, sizeof(T) == 4 ? JXP_TR_MINB_F32 : JXP_TR_MINB)
+k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int K = TR_K;
   constexpr int NQ = 1 + JXP_NTHETA;

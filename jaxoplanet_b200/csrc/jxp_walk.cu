@@ -436,7 +436,8 @@ __device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, dou
     num[q] = -f0 * (D42 * D4);
   }
 #pragma unroll
-  for (int q = 0; q < N; ++q) dE[q] = fdiv(num[q], den[q]);
+  // (dE is a correction of the float starter, |dE| <~ 1e-5: its reciprocal needs 1e-8, one second-order step gives 1e-12)
+  for (int q = 0; q < N; ++q) dE[q] = num[q] * frcp_node(den[q]);
   const double two_s = 2.0 * s1me2;
 #pragma unroll
   for (int q = 0; q < N; ++q) {
@@ -581,31 +582,39 @@ __device__ __forceinline__ void ld_inside_u(const double (&b)[N], double r, int 
   const double r2 = r * r;
   double s1[N];
   if (lmax >= 1) {
-    double two_br[N], r2pb2[N], acc[N];
+    // z^2 = 1 - (r^2 + b^2 - 2 b r c) as ONE fma per node, (1 - r^2 - b^2) + (2 b r) c: the same quantity to an
+    // ulp of 1 (the reference rounds r^2 + b^2 - 2 b r c to the same absolute precision before subtracting).
+    // The node sum  sum_i w_i (r - b c_i) t_i,  t_i = (1 - z_i^3) / (1 - z_i^2),  is accumulated as
+    // r sum_i w_i t_i - b sum_i (w_i c_i) t_i: the c_i are constants here, so every node costs two fmas with
+    // a constant operand instead of (r - b c_i), a product and a share of the pair sum (rounding: ~3e-16 of
+    // a sum of order 1, i.e. ~1e-17 of flux).
+    double two_br[N], omr2b2[N], S1[N], S2[N];
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       two_br[q] = b[q] * r * 2.0;
-      r2pb2[q] = fma(b[q], b[q], r2);
-      acc[q] = 0.0;
+      omr2b2[q] = 1.0 - fma(b[q], b[q], r2);
+      S1[q] = 0.0;
+      S2[q] = 0.0;
     }
 #pragma unroll
     for (int p = 0; p < 5; ++p) {
       const double wp = c_gl10[1][5 + p];
       const double cm = c_gl10[2][5 + p], cq = c_gl10[2][4 - p];  // nodes +x_p, -x_p
-      double z2[2 * N], z[2 * N], t[2 * N];
+      const double wcm = c_gl10_wc[5 + p], wcq = c_gl10_wc[4 - p];
+      double z2[2 * N], t[2 * N];
 #pragma unroll
-      for (int m = 0; m < 2 * N; ++m) z2[m] = 1.0 - fma(-two_br[m >> 1], (m & 1) ? cq : cm, r2pb2[m >> 1]);
+      for (int m = 0; m < 2 * N; ++m) z2[m] = fma(two_br[m >> 1], (m & 1) ? cq : cm, omr2b2[m >> 1]);
 #pragma unroll
-      for (int m = 0; m < 2 * N; ++m) z[m] = fsqrt_fast(z2[m]);
-#pragma unroll
-      for (int m = 0; m < 2 * N; ++m) t[m] = fma(z2[m], frcp_fast(z[m] + 1.0), 1.0);  // (1 - z^3) / (1 - z^2)
+      for (int m = 0; m < 2 * N; ++m) t[m] = fnode_factor(z2[m]);  // (1 - z^3) / (1 - z^2)
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        const double ra = fma(-b[q], cm, r) * t[2 * q];
-        const double rb = fma(-b[q], cq, r) * t[2 * q + 1];
-        acc[q] = fma(wp, ra + rb, acc[q]);
+        S1[q] = fma(wp, t[2 * q] + t[2 * q + 1], S1[q]);
+        S2[q] = fma(wcm, t[2 * q], fma(wcq, t[2 * q + 1], S2[q]));
       }
     }
+    double acc[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) acc[q] = fma(-b[q], S2[q], r * S1[q]);
     const double k1 = (pi * 0.5) * (r * (2.0 / 3.0));
 #pragma unroll
     for (int q = 0; q < N; ++q) s1[q] = fma(-k1, acc[q], pi * (2.0 / 3.0));
@@ -872,6 +881,8 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
         if (intr[h] && fast[h]) tot[h] = f[h];
     }
     if (want_gen) {
+      // (the node guards of limb_dark.py:163-170 stay in: a guard-free variant with a rare-path fallback measured
+      // no faster -- the compares and selects run on otherwise idle pipes)
       double rq[N], s0[N], s1v[N], s2[N];
 #pragma unroll
       for (int h = 0; h < N; ++h) rq[h] = rr;
