@@ -85,7 +85,10 @@ inline SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t bo
     off = align_up(off + sizeof(double) * WALK_REC * nb, 256);
     L.off_wk_set = off;
     off = align_up(off + 32 * nb, 256);
-    L.wk_cap_seg = 384ull * nb + 4096ull;
+    // segments: up to 3 per transit and body (per-body launches share the table).  384 per (set, body) covers
+    // long baselines of single planets; a short-period planet on a long 30-min baseline (config 4: 2e5 samples
+    // = 4167 days, ~2300 transits of the inner planet) has one transit per ~40 samples, hence the n_times term
+    L.wk_cap_seg = 384ull * nb + 4096ull + (unsigned long long)n_sets * (unsigned long long)n_times / 24ull;
     L.off_wk_seg = off;
     off = align_up(off + 8 * (size_t)L.wk_cap_seg, 256);
     L.wk_cap_chunk = (unsigned long long)n_sets * (unsigned long long)n_times / 256ull + 2ull * nb + 1024ull;
@@ -99,9 +102,9 @@ inline SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t bo
   return L;
 }
 // transit walk (jxp_walk.cu); ev_which: 0 = profile events around the evaluation, 1 = around the plan
-int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, int64_t u_stride,
-                    const double* t, int64_t n_times, double* flux, double* flux_sum, const double* y,
-                    const double* sigma, int64_t sigma_stride, double* loglike, unsigned char* ws,
-                    const SysLayout& L, double widen, double margin, cudaStream_t st,
+int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double* u, int n_u, int64_t u_stride,
+                    const double* t, int64_t n_times, const Stencil& stencil, double* flux, double* flux_sum,
+                    const double* y, const double* sigma, int64_t sigma_stride, double* loglike,
+                    unsigned char* ws, const SysLayout& L, double widen, double margin, cudaStream_t st,
                     cudaEvent_t ev_start, cudaEvent_t ev_stop, int ev_which);
 }  // namespace jxph

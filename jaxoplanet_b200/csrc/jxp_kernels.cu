@@ -1665,14 +1665,18 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
   // transit-walk path (jxp_walk.cu): eligibility is decided here, use on the device (sorted time stamps)
   const uint32_t dev = dev_options();
   const bool env_no_tl = (dev & JXP_DEV_NO_WALK) != 0, env_no_pair = (dev & JXP_DEV_NO_PAIR) != 0;
-  const bool tl_ok = sizeof(T) == 8 && n_bodies == 1 && a.st.n == 1 && n_u <= 2 && gl_order == 10 &&
-                     !(flags & JXP_FLAG_NO_WINDOW) && n_times < 0x7ffffe00LL && !env_no_tl;
+  const bool tl_any = sizeof(T) == 8 && n_u <= 2 && gl_order == 10 && !(flags & JXP_FLAG_NO_WINDOW) &&
+                      n_times < 0x7ffffe00LL && !env_no_tl;
+  const bool tl_ok = tl_any && n_bodies == 1 && a.st.n == 1;
   const bool use_tl = tl_ok && loglike && !flux && !flux_sum && !env_no_pair && n_times < (1LL << 25);
   // ... and of calls that want the flux itself (light_curve(orbit, u)(t) of a batch of single-planet systems)
   // (from 2^20 points: below that the extra launch costs more than the walk saves -- config 1, one set x
   // 1e5 samples, takes 39 us with the window-test kernel)
   const int64_t flux_min_points = (dev & JXP_DEV_WALK_ANY_SIZE) ? 0 : (1LL << 20);
-  const bool use_tl_flux = tl_ok && !loglike && (flux || flux_sum) && (int64_t)n_sets * n_times >= flux_min_points;
+  // ... of systems with several bodies and of exposure integration too (config 4): one plan + evaluation per body,
+  // a lane walks the sub-samples of its sample in order
+  const bool use_tl_flux = tl_any && n_bodies <= 16 && !loglike && (flux || flux_sum) &&
+                           (int64_t)n_sets * n_times * n_bodies * a.st.n >= flux_min_points;
   const double widen = f32 ? 1.0 + 2e-4 : 1.0 + 1e-9;
   if (use_tl || use_tl_flux) {
     if constexpr (sizeof(T) == 8) {
@@ -1681,11 +1685,13 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
         // with unsorted time stamps (or a table that does not fit) k_system below rewrites every row
         cudaError_t em = cudaSuccess;
         if (flux_sum) em = cudaMemsetAsync(flux_sum, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
-        if (em == cudaSuccess && flux) em = cudaMemsetAsync(flux, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times, st);
+        if (em == cudaSuccess && flux)
+          em = cudaMemsetAsync(flux, 0, sizeof(T) * (size_t)n_sets * (size_t)n_times * (size_t)n_bodies, st);
         if (em != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve: memset: %s", cudaGetErrorString(em));
       }
-      rc = launch_walk_f64(bodies, n_sets, u, n_u, u_stride, t, n_times, flux, flux_sum, y, sigma, sigma_stride,
-                           loglike, ws, L, widen, 1e-7, st, g_ev_start, g_ev_stop, (dev & JXP_DEV_PROFILE_PLAN) ? 1 : 0);
+      rc = launch_walk_f64(bodies, n_sets, n_bodies, u, n_u, u_stride, t, n_times, a.st, flux, flux_sum, y, sigma,
+                           sigma_stride, loglike, ws, L, widen, 1e-7, st, g_ev_start, g_ev_stop,
+                           (dev & JXP_DEV_PROFILE_PLAN) ? 1 : 0);
       if (rc != JXP_OK) return rc;
     }
   } else {

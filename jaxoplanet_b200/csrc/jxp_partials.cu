@@ -290,9 +290,10 @@ constexpr int TR_QCAP = 128;
 #ifndef JXP_TR_MINB
 #define JXP_TR_MINB 3
 #endif
-// the float instantiations need ~115 registers: one more CTA per SM keeps more row stores in flight
+// the float instantiations need ~100 registers: 5 CTAs per SM keep more row stores in flight (config 5 in float:
+// 6.60 ms at 3 or 4 CTAs per SM, 6.26 ms at 5)
 #ifndef JXP_TR_MINB_F32
-#define JXP_TR_MINB_F32 4
+#define JXP_TR_MINB_F32 5
 #endif
 template <typename T, int ORDER, bool LOGLIKE>
 __global__ void __launch_bounds__(128, sizeof(T) == 4 ? JXP_TR_MINB_F32 : JXP_TR_MINB)

@@ -90,6 +90,13 @@ struct WalkArgs {
   unsigned long long cap_seg, cap_chunk;
   int n_plan_ctas;
   double widen, margin;
+  // several bodies per set: one plan + evaluation per body, this launch's body and the stride of the records
+  int n_bodies, body;
+  // exposure integration (light_curves/transforms.py:67-116): extreme offsets of the stencil (<= 0, >= 0); a
+  // sample is on the list when ANY of its sub-samples can be in transit, on the inside list when ALL of them
+  // are estimated to have the planet inside the disk
+  double dt_lo, dt_hi;
+  unsigned min_in;  // shortest run of samples worth a segment of its own on the inside list
   // outputs
   double* flux;
   double* flux_sum;
@@ -137,11 +144,12 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= a.n_sets) return;
+  const int unit = s * a.n_bodies + a.body;  // (set, body) record
   if (lane == 0)
-    sys_prep_body<double>(s, a.bodies, a.n_sets, 1, a.u, a.n_u, a.u_stride, a.out_b, a.out_s, a.counters,
-                          a.tile_ctr, a.widen, a.margin);
+    sys_prep_body<double>(unit, a.bodies, a.n_sets, a.n_bodies, a.u, a.n_u, a.u_stride, a.out_b, a.out_s,
+                          a.counters, a.tile_ctr, a.widen, a.margin);
   __syncwarp();
-  const BodyC<double>& c = a.out_b[s];
+  const BodyC<double>& c = a.out_b[unit];
   if (lane == 0) {
     const SetC<double>& sc = a.out_s[s];
     double* r = a.rec + (size_t)s * WALK_REC;
@@ -185,8 +193,8 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
     if (!(wlo <= whi)) {
       n_tr = 0;  // never in transit
     } else {
-      const double pa = (t_first - t0ref) * c.inv_period - phc;
-      const double pb = (t_last - t0ref) * c.inv_period - phc;
+      const double pa = ((t_first + a.dt_lo) - t0ref) * c.inv_period - phc;
+      const double pb = ((t_last + a.dt_hi) - t0ref) * c.inv_period - phc;
       const double lo_d = floor(fmin(pa, pb) - whi) - 1.0;
       const double hi_d = ceil(fmax(pa, pb) - wlo) + 1.0;
       if (!(hi_d - lo_d < 4.0 * (double)n + 64.0)) {
@@ -238,19 +246,21 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
     }
     const double base = phc + (k_first + (double)k);
     const double ta = fma(base + wlo, P, t0ref), tb = fma(base + whi, P, t0ref);
-    const bool want_in = w_in > 0.0;
     const double tc = fma(base - w_in, P, t0ref), td = fma(base + w_in, P, t0ref);
+    // exposure integration: the sample at t stands for the sub-samples t + dt_j, dt_lo <= dt_j <= dt_hi
+    const double x_in0 = fmin(tc, td) - a.dt_lo, x_in1 = fmax(tc, td) - a.dt_hi;
+    const bool want_in = w_in > 0.0 && x_in1 > x_in0;
     unsigned r[4];
-    search4(fmin(ta, tb), fmax(ta, tb), fmin(tc, td), fmax(tc, td), r);
+    search4(fmin(ta, tb) - a.dt_hi, fmax(ta, tb) - a.dt_lo, x_in0, x_in1, r);
     lo = r[0];
     hi = r[1];
     if (hi < lo) hi = lo;  // unsorted time stamps: anything in range will do, the call falls back
     ilo = ihi = lo;
-    if (want_in && hi - lo >= 8u) {
+    if (want_in && hi - lo >= a.min_in) {
       unsigned i0 = r[2], i1 = r[3];
       i0 = i0 < lo ? lo : (i0 > hi ? hi : i0);
       i1 = i1 < i0 ? i0 : (i1 > hi ? hi : i1);
-      if (i1 - i0 >= 8u) {
+      if (i1 - i0 >= a.min_in) {
         ilo = i0;
         ihi = i1;
       }
@@ -472,6 +482,8 @@ struct WalkEvalArgs {
   double* loglike;
   WalkSet* wset_rw;
   unsigned long long* counters;
+  int n_bodies, body;  // flux outputs: this launch's column; body > 0 adds into flux_sum and into the counters
+  Stencil st;          // exposure integration (EXPO instantiation): offsets and weights of the sub-samples
 };
 
 // Sortedness flags of the plan launch (one per likelihood-prep CTA) and the table overflow flag.  Thread 0
@@ -482,10 +494,19 @@ __device__ __forceinline__ bool walk_eval_active(const WalkEvalArgs& a, int lane
   const bool unsorted = __any_sync(0xffffffffu, bad);
   const bool over = a.state[3] != 0ull || a.state[1] + a.state[2] > a.cap_chunk;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.counters[2] = a.state[4];  // in-window samples on the inside / edge lists (jxp_system_list_stats)
-    a.counters[4] = a.state[5];
-    a.counters[3] = (unsorted ? 1ull : 0ull) | (over ? 2ull : 0ull);
-    if (!unsorted && !over) a.counters[0] = a.state[4] + a.state[5];  // Kepler solves = samples visited
+    const unsigned long long verdict = (unsorted ? 1ull : 0ull) | (over ? 2ull : 0ull);
+    const unsigned long long visited = (a.state[4] + a.state[5]) * (unsigned long long)a.st.n;
+    if (a.body == 0) {
+      a.counters[2] = a.state[4];  // in-window samples on the inside / edge lists (jxp_system_list_stats)
+      a.counters[4] = a.state[5];
+      a.counters[3] = verdict;
+      if (!verdict) a.counters[0] = visited;  // Kepler solves = (sub-)samples visited
+    } else {  // the launches of one call run one after the other on the stream: plain read-modify-write
+      a.counters[2] += a.state[4];
+      a.counters[4] += a.state[5];
+      a.counters[3] |= verdict;
+      if (!verdict) a.counters[0] += visited;
+    }
   }
   return !unsorted && !over;
 }
@@ -652,8 +673,12 @@ struct WalkWarpSmem {
   unsigned long long log[WK_LOG];     // finished claims: first slot | chunks << 32
 };
 
-template <int N, bool FLUX>
+// EXPO (flux outputs only): every item is evaluated at its n_sub sub-sample times t + dt_j and the weighted
+// sum sum_j w_j f(t + dt_j) is formed in increasing j, the order of the reference's dot product
+// (light_curves/transforms.py:113-116).
+template <int N, bool FLUX, bool EXPO = false>
 __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_constant__ WalkEvalArgs a) {
+  static_assert(!EXPO || FLUX, "exposure integration on the walk path: flux outputs only");
   constexpr int CH = 32 * N;
   static_assert(CH <= 255, "segments left in a window are an 8-bit field of the chunk entry");
   __shared__ __align__(16) WalkWarpSmem<N> s_all[4];
@@ -812,10 +837,19 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     // division by the period is a multiplication by fl(1 / P) with one residual correction
     const double2 tt = rec2[WK_T0 / 2], pp = rec2[WK_PERIOD / 2];
     const int lmax = (int)((unsigned)__double_as_longlong(rec[WK_FLAGS]) >> 8);
+    double tsamp[N], wsum[N];
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+      tsamp[h] = sm.tb[32 * h + lane];
+      wsum[h] = 0.0;
+    }
+    const int n_sub = EXPO ? a.st.n : 1;
+#pragma unroll 1
+    for (int j = 0; j < n_sub; ++j) {
     double Mr[N];
 #pragma unroll
     for (int h = 0; h < N; ++h) {
-      const double x = (sm.tb[32 * h + lane] - tt.x) - tt.y;
+      const double x = ((EXPO ? tsamp[h] + a.st.dt[j] : tsamp[h]) - tt.x) - tt.y;
       const double num = Num<double>::two_pi * x;
       const double q = num * pp.y;
       const double r = fma(-pp.x, q, num);
@@ -862,9 +896,11 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     want_gen = __any_sync(0xffffffffu, want_gen);
     want_fast = __any_sync(0xffffffffu, want_fast);
     // ================= mid: the next chunk's segment window has landed -> its samples start to fly
-    cp_async_wait_all();
-    __syncwarp();
-    stage_samples(pb ^ 1, en, rb ^ 1);
+    if (j == 0) {
+      cp_async_wait_all();
+      __syncwarp();
+      stage_samples(pb ^ 1, en, rb ^ 1);
+    }
     // ================= flux (core/limb_dark.py:19-196)
     const double2 gg = rec2[WK_G0 / 2];
     const double g2 = rec[WK_G2];
@@ -892,16 +928,28 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
         if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
     }
 #endif
+    if (EXPO) {
+#pragma unroll
+      for (int h = 0; h < N; ++h) wsum[h] = fma(a.st.w[j], tot[h], wsum[h]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < N; ++h) wsum[h] = tot[h];
+    }
+    }  // sub-samples
+    double tot[N];
+#pragma unroll
+    for (int h = 0; h < N; ++h) tot[h] = wsum[h];
     // ================= end: outputs of this chunk
     if (FLUX) {
-      // rows were zeroed before the launch; positions of different items are disjoint
+      // rows were zeroed before the first launch of the call; positions of different items are disjoint, and
+      // the launches of the bodies of one call follow one another on the stream (flux_sum: body order)
 #pragma unroll
       for (int h = 0; h < N; ++h) {
         const unsigned ix = sm.ib[pb][32 * h + lane];
         if (ix != 0xffffffffu && tot[h] != 0.0) {
           const size_t o = (size_t)set * (size_t)a.n_times + ix;
-          if (a.flux_sum) a.flux_sum[o] = tot[h];
-          if (a.flux) a.flux[o] = tot[h];
+          if (a.flux_sum) a.flux_sum[o] = (a.body > 0) ? a.flux_sum[o] + tot[h] : tot[h];
+          if (a.flux) a.flux[o * (size_t)a.n_bodies + (size_t)a.body] = tot[h];
         }
       }
     } else {
@@ -966,16 +1014,20 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
 
 namespace jxph {
 
-// Launches of the transit-walk path (double, one body per set, no exposure integration, quadratic law,
-// order 10).  prep: plan launch (records, segments, chunk entries, likelihood terms / sortedness flags);
-// then the evaluation.  The caller launches the window-test kernels behind it as the on-device fallback.
-int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, int64_t u_stride,
-                    const double* t, int64_t n_times, double* flux, double* flux_sum, const double* y,
-                    const double* sigma, int64_t sigma_stride, double* loglike, unsigned char* ws,
-                    const SysLayout& L, double widen, double margin, cudaStream_t st,
+// Launches of the transit-walk path (double, quadratic law, order 10).  Per body of the system: a plan launch
+// (records, segments, chunk entries, likelihood terms / sortedness flags), then the evaluation; the bodies of
+// one call follow one another on the stream and share the tables.  The caller launches the window-test
+// kernels behind it as the on-device fallback.
+int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double* u, int n_u, int64_t u_stride,
+                    const double* t, int64_t n_times, const Stencil& stencil, double* flux, double* flux_sum,
+                    const double* y, const double* sigma, int64_t sigma_stride, double* loglike,
+                    unsigned char* ws, const SysLayout& L, double widen, double margin, cudaStream_t st,
                     cudaEvent_t ev_start, cudaEvent_t ev_stop, int ev_which) {
   constexpr int N = JXP_WALK_N;
   constexpr int CH = 32 * N;
+  const bool expo = stencil.n > 1 || stencil.dt[0] != 0.0 || stencil.w[0] != 1.0;
+  if (loglike && (expo || n_bodies != 1))
+    return fail(JXP_ERR_UNSUPPORTED, "jxp_system_light_curve(walk): log-likelihood of one body without exposure integration only");
   double* d_scalars = reinterpret_cast<double*>(ws + L.off_scalars);
   WalkArgs a;
   a.bodies = bodies;
@@ -1005,19 +1057,14 @@ int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, 
   a.n_plan_ctas = (n_sets + 7) / 8;
   a.widen = widen;
   a.margin = margin;
+  a.n_bodies = n_bodies;
+  a.dt_lo = expo ? stencil.dt_min : 0.0;
+  a.dt_hi = expo ? stencil.dt_max : 0.0;
+  // with exposure integration a sample stands for n_sub evaluations: even a single all-inside sample pays
+  a.min_in = expo ? (stencil.n >= 8 ? 1u : 2u) : 8u;
   a.flux = flux;
   a.flux_sum = flux_sum;
   a.loglike = loglike;
-  cudaError_t e = cudaMemsetAsync(a.state, 0, 10 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
-  if (ev_start && ev_which == 1) cudaEventRecord(ev_start, st);
-  if (loglike)
-    k_walk_plan<CH, true><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
-  else
-    k_walk_plan<CH, false><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
-  if (ev_stop && ev_which == 1) cudaEventRecord(ev_stop, st);
-  int rc = check_launch("jxp_system_light_curve(walk plan)");
-  if (rc != JXP_OK) return rc;
 
   WalkEvalArgs b;
   b.rec = a.rec;
@@ -1038,10 +1085,18 @@ int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, 
   b.flux_sum = flux_sum;
   b.loglike = loglike;
   b.counters = a.counters;
-  static thread_local int per_sm_ll = 0, per_sm_fx = 0;
-  int& per_sm = loglike ? per_sm_ll : per_sm_fx;
+  b.n_bodies = n_bodies;
+  b.st = stencil;
+  if (!expo) {
+    b.st.n = 1;
+    b.st.dt[0] = 0.0;
+    b.st.w[0] = 1.0;
+  }
+  static thread_local int per_sm_ll = 0, per_sm_fx = 0, per_sm_ex = 0;
+  int& per_sm = loglike ? per_sm_ll : (expo ? per_sm_ex : per_sm_fx);
   if (per_sm == 0) {
     cudaError_t eo = loglike ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_eval<N, false>, 128, 0)
+                     : expo  ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_eval<N, true, true>, 128, 0)
                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_eval<N, true>, 128, 0);
     if (eo != cudaSuccess || per_sm < 1) {
       per_sm = 0;
@@ -1054,13 +1109,32 @@ int launch_walk_f64(const double* bodies, int n_sets, const double* u, int n_u, 
   const long long want = (long long)((bound + 3ull) / 4ull);
   const long long resident = (long long)per_sm * sm_count();
   const unsigned grid = (unsigned)(want < resident ? want : resident);
-  if (ev_start && ev_which == 0) cudaEventRecord(ev_start, st);
-  if (loglike)
-    k_walk_eval<N, false><<<grid, 128, 0, st>>>(b);
-  else
-    k_walk_eval<N, true><<<grid, 128, 0, st>>>(b);
-  if (ev_stop && ev_which == 0) cudaEventRecord(ev_stop, st);
-  return check_launch("jxp_system_light_curve(walk eval)");
+
+  for (int body = 0; body < n_bodies; ++body) {
+    a.body = body;
+    b.body = body;
+    cudaError_t e = cudaMemsetAsync(a.state, 0, 10 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
+    if (ev_start && ev_which == 1 && body == 0) cudaEventRecord(ev_start, st);
+    if (loglike)
+      k_walk_plan<CH, true><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
+    else
+      k_walk_plan<CH, false><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
+    if (ev_stop && ev_which == 1 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
+    int rc = check_launch("jxp_system_light_curve(walk plan)");
+    if (rc != JXP_OK) return rc;
+    if (ev_start && ev_which == 0 && body == 0) cudaEventRecord(ev_start, st);
+    if (loglike)
+      k_walk_eval<N, false><<<grid, 128, 0, st>>>(b);
+    else if (expo)
+      k_walk_eval<N, true, true><<<grid, 128, 0, st>>>(b);
+    else
+      k_walk_eval<N, true><<<grid, 128, 0, st>>>(b);
+    if (ev_stop && ev_which == 0 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
+    rc = check_launch("jxp_system_light_curve(walk eval)");
+    if (rc != JXP_OK) return rc;
+  }
+  return JXP_OK;
 }
 
 }  // namespace jxph

@@ -57,10 +57,11 @@ def test_argument_validation_messages(lib):
     assert rc == -3 and b"must be 0, 1, or 2" in lib.jxp_last_error()
     assert lib.jxp_system_workspace_bytes(4096, 1, 100000) > 4096 * 100
     assert lib.jxp_system_workspace_bytes(0, 1, 10) == 0
-    # the transit walk keeps nothing per sample: records, segments and one 24-byte slot per chunk of 32
-    # in-window samples for 1/8 of the grid -- well under one byte per (set, sample)
+    # the transit walk keeps nothing per sample: records, 8-byte segments (3 per transit; room for one transit
+    # per 72 samples) and one 24-byte slot per chunk of in-window samples for 1/8 of the grid -- about half a
+    # byte per (set, sample), against 1.5 bytes for round 1's materialised list
     one = lib.jxp_system_workspace_bytes(4096, 1, 100000)
-    assert 24 * (4096 * 100000 // 256) <= one < 4096 * 100000 // 4
+    assert 24 * (4096 * 100000 // 256) <= one < 6 * (4096 * 100000 // 10)
     # development options: one process-wide word, default 0
     assert lib.jxp_get_dev_options() == 0
     assert lib.jxp_set_dev_options(5) == 0 and lib.jxp_get_dev_options() == 5

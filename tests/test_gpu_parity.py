@@ -754,10 +754,17 @@ def test_window_is_conservative_on_adversarial_orbits():
         sys_ = System(Central(mass=0.8, radius=1.3)).add_body(**p)
         sys_ = sys_.add_body(period=P * 1.7, radius=0.05, inclination=np.full(n_sets, 1.52))
     for kw in (dict(), dict(exposure_time=0.05, exp_order=2, num_samples=5)):
-        a = _run_fused(FusedSpec(sys_, u, **kw), t)
         b = _run_fused(FusedSpec(sys_, u, flags=_lib.JXP_FLAG_NO_WINDOW, **kw), t)
+        with _lib.dev_options(_lib.JXP_DEV_NO_WALK):  # the window-test kernels: the same code behind the pre-test
+            a = _run_fused(FusedSpec(sys_, u, **kw), t)
         assert torch.equal(a, b)
         assert float((a != 0).double().mean()) > 0.005
+        # the transit walk (sorted time stamps; several bodies and exposure integration included) visits only
+        # the samples inside the same windows with its own arrangement of the arithmetic: the same samples
+        # are in transit -- exact zeros everywhere else -- and the values agree to rounding
+        w = _run_fused(FusedSpec(sys_, u, **kw), t)
+        assert torch.equal(w == 0, b == 0)
+        assert float(torch.max(torch.abs(w - b))) <= 5e-13
     # unsorted times take the per-sample test path
     tu = rng.permutation(t)
     a = _run_fused(FusedSpec(sys_, u), tu)

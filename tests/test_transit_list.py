@@ -524,3 +524,71 @@ def test_gradient_and_flux_list_paths_no_out_of_bounds_writes():
             assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
             assert bool((out[:8] == -7.0).all()) and bool((out[8 + n_sets * n_t:] == -7.0).all())
             assert bool(torch.isfinite(out[8:8 + n_sets * n_t]).all()) and bool((out[8:8 + n_sets * n_t] <= 0).all())
+
+
+def _system_flux_abi(system, u, t, expo=None, per_body=False):
+    """Flux of a (multi-body) batch through the C ABI with a workspace we keep -> (flux, list items, flags)."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200.light_curves.limb_dark import pack_bodies
+
+    dev = A.device()
+    bodies, n_sets, _ = pack_bodies(system)
+    n_bodies = bodies.shape[1]
+    bodies = bodies.to(dev).contiguous()
+    ud = torch.as_tensor(np.asarray(u, dtype=np.float64), device=dev).contiguous()
+    u_stride = ud.shape[1] if ud.ndim == 2 else 0
+    td = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev).contiguous()
+    n_t = td.numel()
+    nbytes = _lib.load().jxp_system_workspace_bytes(n_sets, n_bodies, n_t)
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    shape = (n_sets, n_t, n_bodies) if per_body else (n_sets, n_t)
+    out = torch.full(shape, float("nan"), dtype=torch.float64, device=dev)
+    ex = expo or dict(exposure_time=0.0, order=0, num_samples=0)
+    _lib.call("jxp_system_light_curve_f64", bodies.data_ptr(), n_sets, n_bodies, ud.data_ptr(), ud.shape[-1], u_stride,
+              td.data_ptr(), n_t, ex["exposure_time"], ex["order"], ex["num_samples"], 10, 0,
+              out.data_ptr() if per_body else None, None if per_body else out.data_ptr(), None, None, 0, None,
+              ws.data_ptr(), ws.numel(), A.stream_ptr())
+    stats = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, n_bodies, n_t, ctypes.addressof(stats), A.stream_ptr())
+    return out.cpu().numpy(), int(stats[0]), int(stats[1])
+
+
+@pytest.mark.parametrize("order,num_samples", [(0, 15), (1, 7), (2, 5), (0, 0)])
+def test_walk_with_several_bodies_and_exposure_integration_matches_oracle_and_window_kernels(order, num_samples):
+    """Config-4-shaped calls on the transit walk (one plan + evaluation per body, a lane walks the sub-samples
+    of its sample): summed and per-body flux against the oracle and against the window-test kernels, all three
+    stencils of transforms.py:67-89, eccentric + circular bodies, one body that never transits."""
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+
+    rng = np.random.default_rng(17 + order)
+    n_sets, n_t = 24, 6000
+    P = np.stack([rng.uniform(1, 3, n_sets), rng.uniform(4, 9, n_sets), rng.uniform(12, 30, n_sets)], 1)
+    p = dict(period=P, time_transit=rng.uniform(0, 1, (n_sets, 3)) * P, eccentricity=rng.uniform(0, 0.4, (n_sets, 3)),
+             omega_peri=rng.uniform(-np.pi, np.pi, (n_sets, 3)), impact_param=rng.uniform(0, 1.15, (n_sets, 3)),
+             radius=rng.uniform(0.02, 0.2, (n_sets, 3)))
+    p["impact_param"][:, 2] = np.where(np.arange(n_sets) % 5 == 0, 3.0, p["impact_param"][:, 2])  # never transits
+    u = W.kipping_u(rng.uniform(0, 1, (n_sets, 2)))
+    t = np.sort(np.arange(n_t) * W.THIRTY_MIN + rng.uniform(-2e-3, 2e-3, n_t))
+    expo = dict(exposure_time=W.THIRTY_MIN, order=order, num_samples=num_samples) if num_samples else None
+    sys_ = W.system_from(p)
+    with _lib.dev_options(_lib.JXP_DEV_WALK_ANY_SIZE):
+        summed, items, flags = _system_flux_abi(sys_, u, t, expo)
+        per_body, items_b, flags_b = _system_flux_abi(sys_, u, t, expo, per_body=True)
+    assert flags == 0 and items > 0 and flags_b == 0 and items_b == items  # the walk produced both
+    summed_w, items_w, _ = _without_list(lambda: _system_flux_abi(sys_, u, t, expo))
+    per_body_w, _, _ = _without_list(lambda: _system_flux_abi(sys_, u, t, expo, per_body=True))
+    assert items_w == 0
+    assert np.max(np.abs(summed - summed_w)) <= 2e-13 and np.max(np.abs(per_body - per_body_w)) <= 2e-13
+    assert np.array_equal(summed == 0, summed_w == 0)  # exact zeros out of transit, on both paths
+    assert np.max(np.abs(per_body.sum(-1) - summed)) <= 1e-15
+    for s in range(0, n_sets, 5):
+        bodies = [ref.orbital_body(**{k: v[s, b] for k, v in p.items()}) for b in range(3)]
+        f = lambda tt: ref.system_light_curve(bodies, u[s], tt)  # noqa: E731
+        want = ref.integrate(f, expo["exposure_time"], order, num_samples)(t) if expo else f(t)
+        assert np.max(np.abs(per_body[s] - want) / np.maximum(1.0, np.abs(1.0 + want))) <= 1e-12
+        assert np.all(per_body[s][:, 2] == 0) if s % 5 == 0 else True
+    assert np.mean(summed != 0) > 0.03
