@@ -17,11 +17,14 @@ e2e        the same step through the repo's public Python API (the reference's c
            **sampled elements) -> log_likelihood(orbit, u)(t, y, sigma)) with HOST NumPy arrays in and out:
            host-to-device copies of every input and the device-to-host read of the result inside the timed
            region; e2e.c_abi: the same through the bare C ABI from one pinned arena
-roofline   dominant kernel k_walk_eval timed alone with CUDA events inside the timed steps.  achieved =
-           A-table flops of the work it EXECUTED (counters read back from the device; samples with the
-           planet inside the disk charged their own, smaller weight) / its mean duration; peak = FP64 FMA
-           peak measured in this run.  hardware: FP64 thread instructions of the same launch (ncu, profiles/)
-           over the live duration; pipe_fp64_pct from the same capture.
+roofline   dominant kernel timed alone with CUDA events inside the timed steps: k_walk_items, which answers every
+           in-window sample from the per-set function tables (csrc/jxp_tables.cuh: two Horner chains per sample
+           instead of a Kepler solve + the ten-node quadrature).  frac = FP64 flops the launch EXECUTED (thread
+           instructions counted by ncu on the same seeded inputs, profiles/r2_walk_items.json: 2 per DFMA, 1 per
+           DMUL / DADD) / its live duration / the FP64 FMA peak measured in this run; pipe_fp64_pct from the same
+           capture.  roofline.algorithmic: the SURVEY 8d figure -- the flops of the REFERENCE formula (302 per Kepler
+           solve + orbit, 746 per flux evaluation) for the samples the launch answered / its duration; above the
+           peak because the tables replace most of those flops, not because the pipe runs faster.
 cpu_baseline / --impl reference: the reference's algorithm on the host cores -- real jaxoplanet on jax[cpu]
            when `import jax` and a reference checkout (baseline/_ref) exist, else the C/OpenMP restatement
            (oracle/ref_c.c, -O3 -march=native) -- over ALL 4096 sets per step.
@@ -357,8 +360,11 @@ class Problem:
         ls = (ctypes.c_int64 * 4)()
         self._lib.call("jxp_system_list_stats", self.ws.data_ptr(), self.n_sets, 1, self.n_times, ctypes.addressof(ls),
                        self.A.stream_ptr())
+        wk = (ctypes.c_int64 * 4)()
+        self._lib.call("jxp_system_walk_stats", self.ws.data_ptr(), self.n_sets, 1, self.n_times, ctypes.addressof(wk),
+                       self.A.stream_ptr())
         return dict(kepler=int(st[0]), ld=int(st[1]), items=int(ls[0]), flags=int(ls[1]), inside=int(ls[2]),
-                    fast=int(ls[3]))
+                    fast=int(ls[3]), tab_evals=int(wk[0]), n_fix=int(wk[1]), tab_sets=int(wk[2]), no_tables=int(wk[3]))
 
 
 def run_ours(args, rank, local_rank, world):
@@ -461,6 +467,11 @@ def run_ours(args, rank, local_rank, world):
     step = make_step(prob, ll_all)
     warm = max(args.warmup, 3)
     timed_steps(step, warm, kernel_events=False)
+    # which kernel dominates: with the per-set function tables (the default) k_walk_items, else k_walk_eval; the
+    # profile events bracket that launch (a development option that moves the event records, nothing else)
+    st_w = prob.stats()
+    tables_used = st_w["tab_evals"] > 0.5 * max(st_w["ld"], 1)
+    lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_ITEMS if tables_used else 0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -473,15 +484,24 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop(t_lo, t_hi) if rank == 0 else None
     st = prob.stats()
     walk_used = st["items"] > 0 and st["flags"] == 0
-    # plan launch alone (same events, other bracket)
+    # plan launch alone (same events, other bracket; the table launch runs beside it on a side stream), and the
+    # table launch alone (serial in that measurement)
     lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_PLAN)
     _, plan_ms = timed_steps(step, 5)
+    lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_TABLES)
+    _, tables_ms = timed_steps(step, 5)
     lib.jxp_set_dev_options(0)
     plan_ms /= 5
+    tables_ms /= 5
     # sorted time stamps: only the in-window samples are visited (k_walk_*); the window-test kernels are still
     # launched behind them and return at once (the choice is made on the device)
-    launches = (["k_walk_plan", "k_walk_eval", "k_system_pair (returns at once)", "k_loglike_final (returns at once)"]
-                if walk_used else ["k_sys_prep_ll", "k_system_pair", "k_loglike_final"])
+    if walk_used and tables_used:
+        launches = ["k_walk_tables (side stream, beside the plan)", "k_walk_plan", "k_walk_eval (sets without tables)",
+                    "k_walk_items", "k_walk_fix", "k_system_pair (returns at once)", "k_loglike_final (returns at once)"]
+    elif walk_used:
+        launches = ["k_walk_plan", "k_walk_eval", "k_system_pair (returns at once)", "k_loglike_final (returns at once)"]
+    else:
+        launches = ["k_sys_prep_ll", "k_system_pair", "k_loglike_final"]
     tot_ms = max_over_ranks(tot_ms)
     ms_per_step = tot_ms / args.steps
     points_per_step = N_SETS * n_times
@@ -619,45 +639,62 @@ def run_ours(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel (rank 0's shard) -------------------------------------------
     k_ms_avg = k_ms / args.steps
     n_gen = st["ld"] - st["fast"]
-    flops = st["kepler"] * (W_KEPLER + W_ORBIT) + st["fast"] * W_LD_INSIDE + n_gen * W_LD
-    flops_r1 = st["kepler"] * (W_KEPLER + W_ORBIT) + st["ld"] * W_LD
-    achieved = flops / (k_ms_avg * 1e-3) / 1e12
+    flops_ref = st["kepler"] * (W_KEPLER + W_ORBIT) + st["ld"] * W_LD  # the reference formula on the samples visited
+    flops_direct = st["kepler"] * (W_KEPLER + W_ORBIT) + st["fast"] * W_LD_INSIDE + n_gen * W_LD
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    kernel = ("k_walk_items" if tables_used else "k_walk_eval<2>") if walk_used else "k_system_pair<1>"
+    cap_file = "r2_walk_items.json" if tables_used else "r2_walk_eval.json"
     hw = None
     traffic = None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_walk_eval.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", cap_file)))
         # instruction counts of a launch depend on the inputs only (same seeded workload); scale by the items
         scale = st["items"] / cap["items"]
         hw_flops = (2 * cap["dfma"] + cap["dmul"] + cap["dadd"]) * scale
         hw = {"fp64_thread_flops_per_launch": hw_flops, "tflops": hw_flops / (k_ms_avg * 1e-3) / 1e12,
               "frac_of_peak": hw_flops / (k_ms_avg * 1e-3) / 1e12 / fp64_peak,
               "pipe_fp64_pct_ncu": cap["pipe_fp64_pct"], "issue_active_pct_ncu": cap["issue_active_pct"],
+              "warp_instructions_per_sample": cap["warp_inst"] * 32.0 / cap["items"] if cap.get("warp_inst") else None,
               "source": cap["source"]}
         traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * scale
     except Exception:
         pass
+    if tables_used:
+        # executed work: what the pipe did (ncu count); the A-table cannot describe a launch that replaces the
+        # reference formula by table look-ups, so it is reported beside it as `algorithmic`
+        achieved = hw["tflops"] if hw else None
+        frac = hw["frac_of_peak"] if hw else None
+    else:
+        achieved = flops_direct / (k_ms_avg * 1e-3) / 1e12
+        frac = achieved / fp64_peak
     roofline = {
-        "bound": "fp64", "kernel": "k_walk_eval<2>" if walk_used else "k_system_pair<1>", "achieved": achieved,
-        "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
-        "traffic_note": "DRAM bytes per launch (ncu, profiles/r2_walk_eval.json), scaled to this rank's items; "
-                        "algorithmic bytes: 24 B per in-window sample (t, y, 1/sigma) + 256 B per set + 24 B per chunk",
+        "bound": "fp64", "kernel": kernel, "achieved": achieved,
+        "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac, "traffic": traffic,
+        "traffic_note": "DRAM bytes per launch (ncu, profiles/%s), scaled to this rank's items; algorithmic bytes: 24 B "
+                        "per in-window sample (t, (2 r0 / sigma, 1 / sigma^2)) + 3.6 KB of tables per set + 24 B per "
+                        "transit -- read through L2, which holds all of it" % cap_file,
         "hardware": hw,
-        "frac_r1_convention": flops_r1 / (k_ms_avg * 1e-3) / 1e12 / fp64_peak,
+        "algorithmic": {"tflops": flops_ref / (k_ms_avg * 1e-3) / 1e12,
+                        "ratio_to_peak": flops_ref / (k_ms_avg * 1e-3) / 1e12 / fp64_peak,
+                        "note": "SURVEY 8d per-unit figure (302 flop per Kepler solve + orbit, 746 per flux evaluation: the "
+                                "reference formula) x the samples this launch answered / its duration.  Not a pipe "
+                                "utilisation: the tables answer a sample with ~50 FP64 instructions"},
         "items": st["items"],
         "peak_source": "DFMA loop (jxp_peak_fma_f64) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
-        "kernel_ms": k_ms_avg, "plan_kernel_ms": plan_ms, "kernel_share_of_step": k_ms_avg / ms_per_step,
-        "executed": {"kepler_solves": st["kepler"], "ld_evaluations": st["ld"], "ld_inside_disk_code": st["fast"],
+        "kernel_ms": k_ms_avg, "plan_kernel_ms": plan_ms, "tables_kernel_ms": tables_ms,
+        "kernel_share_of_step": k_ms_avg / ms_per_step,
+        "executed": {"samples_visited": st["kepler"], "flux_evaluations": st["ld"], "from_tables": st["tab_evals"],
+                     "direct_code_fix_list": st["n_fix"], "sets_with_tables": st["tab_sets"],
+                     "transiting_sets_without_tables": st["no_tables"], "ld_inside_disk_code": st["fast"],
                      "points": (hi - lo) * n_times},
-        "flops_convention": "A-table v1 (SURVEY 8d): 302 flop per executed Kepler solve + orbit, 746 per flux "
-                            "evaluation with the general code, 394 per evaluation with the planet fully inside the "
-                            "disk (the reference formula minus its 10 node cosines, 2 atan2 and the kite area, which "
-                            "are constants there); frac_r1_convention charges every evaluation 746 as round 1 did. "
-                            "`hardware` counts executed FP64 thread instructions instead (2 per DFMA, 1 per DMUL / DADD)",
+        "flops_convention": "frac: executed FP64 thread instructions of the launch (2 per DFMA, 1 per DMUL / DADD; ncu on "
+                            "the same seeded inputs) over the live duration, against the measured DFMA peak.  Without "
+                            "tables (JXP_DEV_NO_TABLES) the launch is k_walk_eval and frac is the A-table of the work it "
+                            "executed (302 per Kepler solve + orbit, 746 / 394 per flux evaluation outside / inside the disk)",
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
     }
 

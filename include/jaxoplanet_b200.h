@@ -163,6 +163,9 @@ int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_b
 #define JXP_DEV_WALK_ANY_SIZE 4u  /* flux outputs: no minimum problem size for the transit walk */
 #define JXP_DEV_NO_LD_CLASSES 8u  /* jxp_limb_dark_f64: plain kernel instead of the class-sorted one */
 #define JXP_DEV_PROFILE_PLAN 16u  /* jxp_profile_events brackets the plan launch instead of the evaluation */
+#define JXP_DEV_PROFILE_TABLES 64u /* jxp_profile_events brackets the table launch (k_walk_tables) */
+#define JXP_DEV_PROFILE_ITEMS 128u /* jxp_profile_events brackets the table-set evaluation (k_walk_items) */
+#define JXP_DEV_NO_TABLES 32u     /* transit walk: every sample by the direct Kepler + quadrature code (no per-set tables) */
 #define JXP_DEV_CTA_WARPS(n) (((uint32_t)(n) & 0xfu) << 8)   /* window-test kernels: warps per CTA (1..4) */
 #define JXP_DEV_GET_CTA_WARPS(m) (((m) >> 8) & 0xfu)
 #define JXP_DEV_TR_RUN(n) (((uint32_t)(n) & 0x7fu) << 16)    /* jxp_transit_partials: warp tiles per run */
@@ -193,6 +196,13 @@ int jxp_system_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, in
  * and took the constant-kappa flux code.  SYNCHRONISES `stream`. */
 int jxp_system_list_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
                           int64_t n_times, int64_t* stats_host, void* stream);
+
+/* Measurement helper: the per-set function tables of the transit walk (csrc/jxp_tables.cuh) in the LAST call on
+ * this workspace.  stats_host[0] = flux evaluations answered by a table, [1] = samples of table sets that took the
+ * direct code instead (k_walk_fix), [2] = (set, body) units whose tables were used, [3] = transiting units without tables.  Evaluations not counted in [0] took the direct Kepler + quadrature
+ * code (jxp_system_stats counts all of them).  SYNCHRONISES `stream`. */
+int jxp_system_walk_stats(const void* workspace, int32_t n_sets, int32_t n_bodies, int64_t n_times,
+                          int64_t* stats_host, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K5  flux and its forward-mode partials w.r.t. the 8 sampled parameters of a single

@@ -23,6 +23,9 @@ JXP_DEV_NO_PAIR = 2
 JXP_DEV_WALK_ANY_SIZE = 4
 JXP_DEV_NO_LD_CLASSES = 8
 JXP_DEV_PROFILE_PLAN = 16
+JXP_DEV_NO_TABLES = 32
+JXP_DEV_PROFILE_TABLES = 64
+JXP_DEV_PROFILE_ITEMS = 128
 
 
 def JXP_DEV_CTA_WARPS(n):
@@ -78,6 +81,7 @@ SIGNATURES = {
     ),
     "jxp_system_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "jxp_system_list_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
+    "jxp_system_walk_stats": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "jxp_profile_events": (C.c_int, [_p, _p]),
     "jxp_transit_workspace_bytes": (_sz, [_i32, _i64]),
     "jxp_transit_list_stats": (C.c_int, [_p, _i32, _i64, _p, _p]),

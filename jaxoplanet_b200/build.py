@@ -25,6 +25,8 @@ HEADERS = [
     os.path.join(CSRC, "jxp_orbit.cuh"),
     os.path.join(CSRC, "jxp_list.cuh"),
     os.path.join(CSRC, "jxp_prep.cuh"),
+    os.path.join(CSRC, "jxp_tables.cuh"),
+    os.path.join(CSRC, "jxp_tables_data.inc"),
     os.path.join(ROOT, "include", "jaxoplanet_b200.h"),
 ]
 

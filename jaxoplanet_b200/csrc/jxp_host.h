@@ -31,13 +31,15 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 constexpr int SYS_K_H = 4;          // time samples per thread of k_system (smallest tile = 32 * SYS_K_H)
 constexpr int WALK_REC = 32;        // doubles per record of the transit-walk path (jxp_walk.cu)
 constexpr int WALK_STATE0 = 200;    // scalars[200..]: segment / chunk allocation counters of the walk path
+constexpr int WALK_TAB = 440;       // doubles per set of the walk path's function tables (jxp_tables.cuh)
+constexpr int WALK_TSTAT0 = 216;    // scalars[216..219]: table statistics of the last call (jxp_system_walk_stats)
 struct SysLayout {
   size_t off_bodies, off_sets, off_winv, off_scalars, off_partial, off_tilectr, total;
   size_t off_tl_off, off_tl_cnt, off_tl_items;  // transit-list path (single-body systems)
   unsigned long long tl_cap;                     // items the list can hold
   // transit-walk path: records, per-set bookkeeping, segment table, chunk table, per-chunk partial sums
-  size_t off_wk_rec, off_wk_set, off_wk_seg, off_wk_chunk, off_wk_part;
-  unsigned long long wk_cap_seg, wk_cap_chunk;
+  size_t off_wk_rec, off_wk_set, off_wk_seg, off_wk_chunk, off_wk_part, off_wk_tab, off_wk_items, off_wk_ipart, off_wk_fix, off_wk_fixsum, off_wk_aw;
+  unsigned long long wk_cap_seg, wk_cap_chunk, wk_cap_items, wk_cap_fix;
   int tile, n_tiles;
 };
 
@@ -97,6 +99,25 @@ inline SysLayout sys_layout(int n_sets, int n_bodies, int64_t n_times, size_t bo
     off = align_up(off + 16 * (size_t)L.wk_cap_chunk, 256);
     L.off_wk_part = off;
     off = align_up(off + 8 * (size_t)L.wk_cap_chunk, 256);
+    // function tables: per set (the per-body launches of one call reuse them), 2.9 KB each
+    L.off_wk_tab = off;
+    off = align_up(off + sizeof(double) * WALK_TAB * (size_t)n_sets, 256);
+    // items of the sets with tables: 16 bytes + one partial sum per slot of a transit (only transits of >= 12
+    // samples become items; room for 1/21 of the grid in such transits -- more falls back, on the device)
+    L.wk_cap_items = 64ull * (unsigned long long)n_sets + (unsigned long long)n_sets * (unsigned long long)n_times / 256ull + 4096ull;
+    if (L.wk_cap_items > (1ull << 27)) L.wk_cap_items = 1ull << 27;
+    L.off_wk_items = off;
+    off = align_up(off + 16 * (size_t)L.wk_cap_items, 256);
+    L.off_wk_ipart = off;
+    off = align_up(off + 8 * (size_t)L.wk_cap_items, 256);
+    // samples of table sets that the tables do not answer (k_walk_fix): 16 bytes each, one fixed-point sum per set
+    L.wk_cap_fix = 64ull * (unsigned long long)n_sets + 65536ull;
+    L.off_wk_fix = off;
+    off = align_up(off + 16 * (size_t)L.wk_cap_fix, 256);
+    L.off_wk_fixsum = off;
+    off = align_up(off + 16 * (size_t)n_sets, 256);
+    L.off_wk_aw = off;  // (2 (y - 1) / sigma^2, 1 / sigma^2) per sample
+    off = align_up(off + 16 * (size_t)n_times, 256);
   }
   L.total = off;
   return L;

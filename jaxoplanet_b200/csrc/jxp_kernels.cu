@@ -1691,7 +1691,7 @@ static int launch_system(const double* bodies, int32_t n_sets, int32_t n_bodies,
       }
       rc = launch_walk_f64(bodies, n_sets, n_bodies, u, n_u, u_stride, t, n_times, a.st, flux, flux_sum, y, sigma,
                            sigma_stride, loglike, ws, L, widen, 1e-7, st, g_ev_start, g_ev_stop,
-                           (dev & JXP_DEV_PROFILE_PLAN) ? 1 : 0);
+                           (dev & JXP_DEV_PROFILE_ITEMS) ? 3 : ((dev & JXP_DEV_PROFILE_TABLES) ? 2 : ((dev & JXP_DEV_PROFILE_PLAN) ? 1 : 0)));
       if (rc != JXP_OK) return rc;
     }
   } else {
@@ -1910,6 +1910,24 @@ extern "C" int jxp_system_list_stats(const void* workspace, int32_t n_sets, int3
     stats_host[3] = raw[3];
   }
   if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_list_stats: %s", cudaGetErrorString(e));
+  return JXP_OK;
+}
+
+extern "C" int jxp_system_walk_stats(const void* workspace, int32_t n_sets, int32_t n_bodies,
+                                     int64_t n_times, int64_t* stats_host, void* stream) {
+  if (!workspace || !stats_host) return fail(JXP_ERR_NULL_POINTER, "jxp_system_walk_stats: null pointer");
+  if (n_sets <= 0 || n_bodies <= 0 || n_times <= 0)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_system_walk_stats: empty problem");
+  const SysLayout L = sys_layout(n_sets, n_bodies, n_times, sizeof(BodyC<double>),
+                                 sizeof(SetC<double>), sizeof(double));
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t raw[4] = {0, 0, 0, 0};
+  cudaError_t e = cudaMemcpyAsync(raw, ws + L.off_scalars + WALK_TSTAT0 * sizeof(double), 4 * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_walk_stats: %s", cudaGetErrorString(e));
+  for (int k = 0; k < 4; ++k) stats_host[k] = raw[k];
   return JXP_OK;
 }
 

@@ -881,4 +881,74 @@ __device__ __forceinline__ S ld_combine(int lmax, const S& s0, const S& s1, cons
   return f - B(1);
 }
 
+// Flux of core/limb_dark.py:19-84 for N points of ONE set (radius ratio r warp-uniform) with the planet
+// fully inside the disk: kappa0 = pi, kappa1 = 0 and kite_area = 0 exactly, constant node cosines (see
+// ld_solution_inside_n, jxp_math.cuh -- same formulas and summation order).  The caller guarantees
+// 2e-6 <= r < 1 and b < 1 - r - 4e-15; then every node's 1 - z^2 = r^2 + b^2 - 2 b r c lies in
+// [1.68e-3 r^2, (b + r)^2] (|c| <= 0.99916), i.e. strictly inside [10 eps, 1 - 10 eps], so the two guards of
+// limb_dark.py:163-170 never fire and are not evaluated.  Everything that depends on r alone is computed
+// once, and the closed-form terms come after the node loop so that little is live inside it.
+template <int N>
+__device__ __forceinline__ void ld_inside_u(const double (&b)[N], double r, int lmax, double g0, double g1,
+                                            double g2, double (&f)[N]) {
+  const double pi = Num<double>::pi;
+  const double r2 = r * r;
+  double s1[N];
+  if (lmax >= 1) {
+    // z^2 = 1 - (r^2 + b^2 - 2 b r c) as ONE fma per node, (1 - r^2 - b^2) + (2 b r) c: the same quantity to an
+    // ulp of 1 (the reference rounds r^2 + b^2 - 2 b r c to the same absolute precision before subtracting).
+    // The node sum  sum_i w_i (r - b c_i) t_i,  t_i = (1 - z_i^3) / (1 - z_i^2),  is accumulated as
+    // r sum_i w_i t_i - b sum_i (w_i c_i) t_i: the c_i are constants here, so every node costs two fmas with
+    // a constant operand instead of (r - b c_i), a product and a share of the pair sum (rounding: ~3e-16 of
+    // a sum of order 1, i.e. ~1e-17 of flux).
+    double two_br[N], omr2b2[N], S1[N], S2[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      two_br[q] = b[q] * r * 2.0;
+      omr2b2[q] = 1.0 - fma(b[q], b[q], r2);
+      S1[q] = 0.0;
+      S2[q] = 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+      const double wp = c_gl10[1][5 + p];
+      const double cm = c_gl10[2][5 + p], cq = c_gl10[2][4 - p];  // nodes +x_p, -x_p
+      const double wcm = c_gl10_wc[5 + p], wcq = c_gl10_wc[4 - p];
+      double z2[2 * N], t[2 * N];
+#pragma unroll
+      for (int m = 0; m < 2 * N; ++m) z2[m] = fma(two_br[m >> 1], (m & 1) ? cq : cm, omr2b2[m >> 1]);
+#pragma unroll
+      for (int m = 0; m < 2 * N; ++m) t[m] = fnode_factor(z2[m]);  // (1 - z^3) / (1 - z^2)
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        S1[q] = fma(wp, t[2 * q] + t[2 * q + 1], S1[q]);
+        S2[q] = fma(wcm, t[2 * q], fma(wcq, t[2 * q + 1], S2[q]));
+      }
+    }
+    double acc[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) acc[q] = fma(-b[q], S2[q], r * S1[q]);
+    const double k1 = (pi * 0.5) * (r * (2.0 / 3.0));
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = fma(-k1, acc[q], pi * (2.0 / 3.0));
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) s1[q] = 0.0;
+  }
+  // s0s2, limb_dark.py:111-137 with kappa0 = pi, kappa1 = 0, area = 0
+  const double s0l = (1.0 - r2) * pi;
+  const double s0s = pi - r2 * pi;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double bpr = b[q] + r;
+    const double onembpr2 = (1.0 + bpr) * (1.0 - bpr);
+    const double eta2 = r2 * fma(b[q] * b[q], 2.0, r2) * 0.5;
+    const double delta = b[q] * r * 4.0;
+    const bool large = onembpr2 + delta > delta;
+    const double s2l = s0l * 2.0 + (eta2 - 0.5) * (4.0 * pi);
+    const double s2s = s0s * 2.0 + (eta2 * pi * 2.0 - pi) * 2.0;
+    f[q] = ld_combine(lmax, large ? s0l : s0s, s1[q], large ? s2l : s2s, g0, g1, g2);
+  }
+}
+
 }  // namespace jxp

@@ -91,7 +91,8 @@ __device__ __noinline__ void sys_prep_body(int i, const double* __restrict__ bod
 template <typename T>
 __device__ __forceinline__ void
 loglike_prep_body(int cta, int ncta, const T* __restrict__ y, const T* __restrict__ sigma, int64_t ss, int64_t n,
-                  T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t) {
+                  T* __restrict__ winv, double* __restrict__ scalars, const double* __restrict__ t,
+                  double2* __restrict__ aw = nullptr) {
   __shared__ double sh0[8], sh1[8];
   double a0 = 0.0, a1 = 0.0;
   int bad = 0;
@@ -104,6 +105,8 @@ loglike_prep_body(int cta, int ncta, const T* __restrict__ y, const T* __restric
     const T w = T(1) / sg;
     winv[i] = w;
     const double r0 = (double)((y[i] - T(1)) * w);
+    // (2 r0 / sigma, 1 / sigma^2): the chi^2 term of a model value m is m (m / sigma^2 - 2 r0 / sigma) (k_walk_items)
+    if (aw != nullptr) aw[i] = make_double2(2.0 * r0 * (double)w, (double)w * (double)w);
     a0 += r0 * r0;
     a1 -= log((double)sg) + half_log_2pi;
     // the transit-list path needs non-decreasing, NaN-free time stamps

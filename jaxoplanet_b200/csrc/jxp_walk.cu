@@ -32,6 +32,7 @@
 #include "jxp_list.cuh"
 #include "jxp_orbit.cuh"
 #include "jxp_prep.cuh"
+#include "jxp_tables.cuh"
 
 using namespace jxp;
 using namespace jxph;
@@ -97,6 +98,11 @@ struct WalkArgs {
   // are estimated to have the planet inside the disk
   double dt_lo, dt_hi;
   unsigned min_in;  // shortest run of samples worth a segment of its own on the inside list
+  double* tab;      // [n_sets][TB_DOUBLES] function tables (jxp_tables.cuh); nullptr: not used
+  uint4* items;     // (set, first sample, samples, -) per slot of a transit of a set with tables; nullptr: no item sets
+  unsigned long long cap_items;
+  long long* fixsum;  // [n_sets][2] (zeroed for the item sets here)
+  double2* aw;        // [n_times] (2 (y - 1) / sigma^2, 1 / sigma^2) for k_walk_items, or nullptr
   // outputs
   double* flux;
   double* flux_sum;
@@ -104,6 +110,71 @@ struct WalkArgs {
 };
 
 constexpr unsigned long long WK_OVERFLOW = 2ull, WK_UNSUPPORTED = 4ull;
+constexpr unsigned WK_ITEM = 128;  // samples per item slot aimed at (k_walk_items walks 64 per round)
+
+// Kepler solve for N mean anomalies of ONE orbit (e, 1 - e, 1 + e, sqrt(1 - e^2), 1 / (1 + e) warp-uniform):
+// core/kepler.py:28-56, 82-108 with the re-arrangements of kepler_reduced_n<N, XY, ONE_DIV> (jxp_math.cuh):
+// Markley starter in float (1 - e > 1e-5: the plan sends anything else to the window-test kernels), half
+// angle from a degree-8 sin / cos pair without range reduction, the three nested corrections carried as
+// fractions (one division), half-angle rotation by dE / 2.  Returns (sin f, cos f) D, D = (1 - e) c^2 +
+// (1 + e) s^2.  A circular body (keplerian.py:539-540: f = M) is the e = 0 case: the correction then lands
+// on E = M exactly (f1 = 1, f2 = f3 = 0) and the half-angle products give (sin M, cos M).
+template <int N>
+__device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, double ome, double ope,
+                                            double s1me2, double inv_ope, double (&yD)[N], double (&xD)[N]) {
+  const double pi = Num<double>::pi;
+  bool high[N];
+  double M[N], E0[N], hs[N], hc[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    high[q] = Mr[q] > pi;
+    M[q] = high[q] ? Num<double>::two_pi - Mr[q] : Mr[q];
+  }
+  const float ef = (float)e, omef = (float)ome, iopef = (float)inv_ope;
+#pragma unroll
+  for (int q = 0; q < N; ++q) E0[q] = (double)kepler_starter_t<float>((float)M[q], ef, omef, iopef);
+  // E0 / 2 lies in [0, pi / 2] (to the starter's 1e-6): no range reduction
+#pragma unroll
+  for (int q = 0; q < N; ++q) fsincos_q1(0.5 * E0[q], &hs[q], &hc[q]);
+  double num[N], den[N], dE[N];
+  // d3 -> d4 -> dE of kepler.py:101-107 carried as fractions: one division (see kepler_reduced_n)
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double sinE = 2.0 * hs[q] * hc[q];
+    const double cE = 2.0 * hs[q] * hs[q];
+    const double sE = E0[q] - sinE;
+    const double f0 = fma(e, sE, fma(E0[q], ome, -M[q]));
+    const double f1 = fma(e, cE, ome);
+    const double f2 = e * sinE;
+    const double f3 = 1.0 - f1;
+    const double N3 = -f0 * f1;
+    const double D3 = fma(-0.5 * f0, f2, f1 * f1);
+    const double D32 = D3 * D3;
+    const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
+    const double D4 = fma(N3, fma(hf2, D3, N3 * f36), f1 * D32);
+    const double N4 = -f0 * D32;
+    const double D42 = D4 * D4;
+    const double N42 = N4 * N4;
+    den[q] = fma(D42, fma(f1, D4, hf2 * N4), N42 * fma(f36, D4, -(f2 * (1.0 / 24.0)) * N4));
+    num[q] = -f0 * (D42 * D4);
+  }
+#pragma unroll
+  // (dE is a correction of the float starter, |dE| <~ 1e-5: its reciprocal needs 1e-8, one second-order step gives 1e-12)
+  for (int q = 0; q < N; ++q) dE[q] = num[q] * frcp_node(den[q]);
+  const double two_s = 2.0 * s1me2;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const double h = 0.5 * dE[q];
+    const double h2 = h * h;
+    const double sh = fma(-h * h2, 1.0 / 6.0, h);
+    const double ch = fma(h2, fma(h2, 1.0 / 24.0, -0.5), 1.0);
+    const double s = fma(hs[q], ch, hc[q] * sh);
+    const double c = fma(hc[q], ch, -hs[q] * sh);
+    const double sf = two_s * s * c;
+    yD[q] = high[q] ? -sf : sf;
+    xD[q] = fma(ome, c * c, -ope * (s * s));
+  }
+}
 
 // --------------------------------------------------------------------------------------------
 // plan
@@ -113,7 +184,7 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
   if ((int)blockIdx.x >= a.n_plan_ctas) {
     const int cta = (int)blockIdx.x - a.n_plan_ctas;
     if (LL) {
-      loglike_prep_body<double>(cta, LL_NCTA, a.y, a.sigma, a.sigma_stride, a.n_times, a.winv, a.scalars, a.t);
+      loglike_prep_body<double>(cta, LL_NCTA, a.y, a.sigma, a.sigma_stride, a.n_times, a.winv, a.scalars, a.t, a.aw);
       // the last of these CTAs to finish adds the LL_NCTA pairs in order: the set-independent terms
       if (threadIdx.x == 0) {
         __threadfence();
@@ -205,6 +276,73 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
       }
     }
   }
+  // ---- b^2 series of the set (jxp_tables.cuh): lanes = the 32 Chebyshev nodes of the transit window (widened by
+  // the exposure stencil); node values from the same Kepler / sky-position code the direct path uses
+  bool tab_set = false;  // this set is evaluated from its function tables (k_walk_items)
+  if (a.tab != nullptr) {
+    double* T = a.tab + (size_t)s * TB_DOUBLES;
+    const double dlo = wlo + a.dt_lo * c.inv_period, dhi = whi + a.dt_hi * c.inv_period;
+    const double half = 0.5 * (dhi - dlo), mid = 0.5 * (dhi + dlo);
+    bool okb = !all && n_tr > 0 && c.ome > 1e-5 && c.period > 0.0 && half > 0.0 && half <= 0.1;
+    const double Mc = mod_two_pi(Num<double>::two_pi * phc);
+    double f = 0.0;
+    {
+      const double d = fma(half, d_tb_node32[lane], mid);
+      double Mn[1] = {mod_two_pi(fma(Num<double>::two_pi, d, Mc))}, yD[1], xD[1];
+      kepler_xy_u<1>(Mn, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, yD, xD);
+      const double u1 = fma(c.cw, xD[0], -c.sw * yD[0]);
+      const double u2 = fma(c.sw, xD[0], c.cw * yD[0]);
+      const double k1 = c.na * c.inv_rstar, k2 = c.ci * c.na * c.inv_rstar, zs = -c.si * c.na;
+      const double v1 = k1 * u1, v2 = k2 * u2;
+      f = fma(v1, v1, v2 * v2);
+      okb = okb && (zs * u2 > 0.0) && isfinite(f);  // in front of the star over the whole window
+    }
+    okb = __all_sync(0xffffffffu, okb);
+    // node values -> Chebyshev coefficients (lane k sums over the nodes) -> degree: the last coefficient above the
+    // rounding noise of the node values, at most 23 (eight coefficients of evidence behind it)
+    double ck = 0.0, fm = fabs(f);
+    for (int i = 0; i < 32; ++i) ck = fma(d_tb_dctT32[i][lane], __shfl_sync(0xffffffffu, f, i), ck);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fm = fmax(fm, __shfl_xor_sync(0xffffffffu, fm, o));
+    // (node values carry a few 1e-15 of rounding noise, a / R* times that of the Kepler solve: the degree is where
+    // three coefficients in a row are first below that level -- isolated noise above it further up is dropped
+    // with the rest -- provided nothing beyond stands clearly above the noise, i.e. the series has converged)
+    const unsigned big = __ballot_sync(0xffffffffu, fabs(ck) > 3e-15 * fm);
+    const unsigned loud = __ballot_sync(0xffffffffu, fabs(ck) > 2e-14 * fm);
+    const unsigned quiet3 = ~big & (~big >> 1) & (~big >> 2) & 0x3fffffffu;  // k, k + 1, k + 2 all small
+    const int DB = quiet3 ? __ffs(quiet3) - 2 : 31;                        // (first such k) - 1; >= -1
+    okb = okb && DB >= 1 && DB <= 23 && (loud >> (DB + 1)) == 0u;
+    // ... -> monomial coefficients (lane j; T_k has the parity of k)
+    double mj = 0.0;
+    for (int k = 31; k >= 0; --k) {
+      const double c_k = __shfl_sync(0xffffffffu, ck, k);
+      if (k <= DB && k >= lane && ((k - lane) & 1) == 0) mj = fma(d_tb_c2mT[k][lane], c_k, mj);
+    }
+    if (lane < TB_B2N) T[TB_B2 + lane] = (okb && lane <= DB) ? mj : 0.0;
+    // routing: tables pay when a transit spans enough samples to fill a warp's round and every evaluation is a
+    // sample (no exposure stencil: those stay on the chunk lists, whose positions pack short transits densely)
+    {
+      const double wsamp = (whi - wlo) * P * inv_dt;  // samples per window at the mean cadence
+      // (the same test k_walk_tables makes -- that launch runs beside this one; a set whose flux fits do not
+      // converge there, r near the end of the validated range, gets all-invalid pieces and its samples take the
+      // direct code through the fix list)
+      const SetC<double>& sc = a.out_s[s];
+      const double ar = fabs((double)c.rr);
+      const bool fin = ar >= TB_R_MIN && ar <= TB_R_MAX && isfinite(sc.g0) && isfinite(sc.g1) && isfinite(sc.g2);
+      tab_set = okb && fin && a.items != nullptr && wsamp >= 12.0 && n_tr < (1ll << 22);
+    }
+    if (lane == 0) {
+      double* H = T + TB_HDR;
+      unsigned long long* ts = reinterpret_cast<unsigned long long*>(a.scalars + WALK_TSTAT0);
+      if (tab_set) atomicAdd(ts + 2, 1ull);
+      else if (a.items != nullptr && n_tr > 0 && !all) atomicAdd(ts + 3, 1ull);  // transiting sets without tables
+      H[H_MC] = Mc;
+      H[H_ZSC] = 1.0 / (Num<double>::two_pi * half);
+      H[H_ZOFF] = -mid / half;
+      H[H_BINFO] = __longlong_as_double((long long)((tab_set ? TB_VALID : 0u) | (unsigned)(DB | 1)));
+      H[12] = H[13] = H[14] = H[15] = 0.0;
+    }
+  }
   const double w_in = all ? 0.0 : c.win_in;
   // First index i in [0, n] with !(t[i] < x) (lower bound) or !(t[i] <= x) (UPPER) on sorted t: the four
   // samples around the uniform-grid estimate are loaded at once and decide it when the boundary lies among
@@ -266,6 +404,57 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
       }
     }
   };
+
+  // ---- a set with tables: its transits become ITEMS (set, first sample, samples) for k_walk_items -- m slots per
+  // transit (m from the window length at the mean cadence, so that a slot holds <= ~WK_ITEM samples), contiguous
+  // per set and in time order: the set's partial sums are added in that order
+  if (tab_set) {
+    const double wsamp = (whi - wlo) * P * inv_dt;
+    const unsigned m = 1u + (unsigned)(fmin(wsamp, 1e6) / (double)WK_ITEM);
+    const unsigned long long n_it = (unsigned long long)n_tr * m;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.state + 12, n_it);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    WalkSet wi;
+    wi.seg_off = 0u;
+    wi.n_tr = (unsigned)n_tr;
+    wi.cntA = (unsigned)n_it;  // items of the set ...
+    wi.chA = (unsigned)base;   // ... from this one on
+    wi.cntB = 1u;              // (marks an item set)
+    wi.chB = wi.n_chunks = wi.done = 0u;
+    if (base + n_it > a.cap_items || n_it > 0xfffffff0ull) {
+      if (lane == 0) {
+        atomicOr(a.state + 3, WK_OVERFLOW);
+        wi.cntA = 0u;
+        a.wset[s] = wi;
+      }
+      return;
+    }
+    unsigned long long npos = 0;
+    for (long long k0 = 0; k0 < n_tr; k0 += 32) {
+      unsigned lo, hi, il, ih;
+      interval(k0 + lane, lo, hi, il, ih);
+      if (k0 + lane < n_tr) {
+        const unsigned cnt = hi - lo, per = (cnt + m - 1u) / m;
+        uint4* it = a.items + base + (unsigned long long)(k0 + lane) * m;
+        for (unsigned j = 0; j < m; ++j) {
+          const unsigned s0 = j * per < cnt ? j * per : cnt;
+          const unsigned cj = cnt - s0 < per ? cnt - s0 : per;
+          it[j] = make_uint4((unsigned)s, lo + s0, cj, 0u);
+        }
+        npos += cnt;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    if (lane == 0) {
+      a.wset[s] = wi;
+      a.fixsum[2 * (size_t)s] = 0ll;
+      a.fixsum[2 * (size_t)s + 1] = 0ll;
+      atomicAdd(a.state + 5, npos);
+    }
+    return;
+  }
 
   // segments (non-empty runs only): inside list at [seg0, seg0 + nsA] (sentinel last), edge list at
   // [seg0 + n_tr + 1, seg0 + n_tr + 1 + nsB]; room is taken for the most there can be
@@ -399,70 +588,6 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
 #define JXP_WALK_MINB 4
 #endif
 
-// Kepler solve for N mean anomalies of ONE orbit (e, 1 - e, 1 + e, sqrt(1 - e^2), 1 / (1 + e) warp-uniform):
-// core/kepler.py:28-56, 82-108 with the re-arrangements of kepler_reduced_n<N, XY, ONE_DIV> (jxp_math.cuh):
-// Markley starter in float (1 - e > 1e-5: the plan sends anything else to the window-test kernels), half
-// angle from a degree-8 sin / cos pair without range reduction, the three nested corrections carried as
-// fractions (one division), half-angle rotation by dE / 2.  Returns (sin f, cos f) D, D = (1 - e) c^2 +
-// (1 + e) s^2.  A circular body (keplerian.py:539-540: f = M) is the e = 0 case: the correction then lands
-// on E = M exactly (f1 = 1, f2 = f3 = 0) and the half-angle products give (sin M, cos M).
-template <int N>
-__device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, double ome, double ope,
-                                            double s1me2, double inv_ope, double (&yD)[N], double (&xD)[N]) {
-  const double pi = Num<double>::pi;
-  bool high[N];
-  double M[N], E0[N], hs[N], hc[N];
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    high[q] = Mr[q] > pi;
-    M[q] = high[q] ? Num<double>::two_pi - Mr[q] : Mr[q];
-  }
-  const float ef = (float)e, omef = (float)ome, iopef = (float)inv_ope;
-#pragma unroll
-  for (int q = 0; q < N; ++q) E0[q] = (double)kepler_starter_t<float>((float)M[q], ef, omef, iopef);
-  // E0 / 2 lies in [0, pi / 2] (to the starter's 1e-6): no range reduction
-#pragma unroll
-  for (int q = 0; q < N; ++q) fsincos_q1(0.5 * E0[q], &hs[q], &hc[q]);
-  double num[N], den[N], dE[N];
-  // d3 -> d4 -> dE of kepler.py:101-107 carried as fractions: one division (see kepler_reduced_n)
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    const double sinE = 2.0 * hs[q] * hc[q];
-    const double cE = 2.0 * hs[q] * hs[q];
-    const double sE = E0[q] - sinE;
-    const double f0 = fma(e, sE, fma(E0[q], ome, -M[q]));
-    const double f1 = fma(e, cE, ome);
-    const double f2 = e * sinE;
-    const double f3 = 1.0 - f1;
-    const double N3 = -f0 * f1;
-    const double D3 = fma(-0.5 * f0, f2, f1 * f1);
-    const double D32 = D3 * D3;
-    const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
-    const double D4 = fma(N3, fma(hf2, D3, N3 * f36), f1 * D32);
-    const double N4 = -f0 * D32;
-    const double D42 = D4 * D4;
-    const double N42 = N4 * N4;
-    den[q] = fma(D42, fma(f1, D4, hf2 * N4), N42 * fma(f36, D4, -(f2 * (1.0 / 24.0)) * N4));
-    num[q] = -f0 * (D42 * D4);
-  }
-#pragma unroll
-  // (dE is a correction of the float starter, |dE| <~ 1e-5: its reciprocal needs 1e-8, one second-order step gives 1e-12)
-  for (int q = 0; q < N; ++q) dE[q] = num[q] * frcp_node(den[q]);
-  const double two_s = 2.0 * s1me2;
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    const double h = 0.5 * dE[q];
-    const double h2 = h * h;
-    const double sh = fma(-h * h2, 1.0 / 6.0, h);
-    const double ch = fma(h2, fma(h2, 1.0 / 24.0, -0.5), 1.0);
-    const double s = fma(hs[q], ch, hc[q] * sh);
-    const double c = fma(hc[q], ch, -hs[q] * sh);
-    const double sf = two_s * s * c;
-    yD[q] = high[q] ? -sf : sf;
-    xD[q] = fma(ome, c * c, -ope * (s * s));
-  }
-}
-
 struct WalkEvalArgs {
   const double* rec;
   const WalkSet* wset;
@@ -588,76 +713,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Flux of core/limb_dark.py:19-84 for N points of ONE set (radius ratio r warp-uniform) with the planet
-// fully inside the disk: kappa0 = pi, kappa1 = 0 and kite_area = 0 exactly, constant node cosines (see
-// ld_solution_inside_n, jxp_math.cuh -- same formulas and summation order).  The caller guarantees
-// 2e-6 <= r < 1 and b < 1 - r - 4e-15; then every node's 1 - z^2 = r^2 + b^2 - 2 b r c lies in
-// [1.68e-3 r^2, (b + r)^2] (|c| <= 0.99916), i.e. strictly inside [10 eps, 1 - 10 eps], so the two guards of
-// limb_dark.py:163-170 never fire and are not evaluated.  Everything that depends on r alone is computed
-// once, and the closed-form terms come after the node loop so that little is live inside it.
-template <int N>
-__device__ __forceinline__ void ld_inside_u(const double (&b)[N], double r, int lmax, double g0, double g1,
-                                            double g2, double (&f)[N]) {
-  const double pi = Num<double>::pi;
-  const double r2 = r * r;
-  double s1[N];
-  if (lmax >= 1) {
-    // z^2 = 1 - (r^2 + b^2 - 2 b r c) as ONE fma per node, (1 - r^2 - b^2) + (2 b r) c: the same quantity to an
-    // ulp of 1 (the reference rounds r^2 + b^2 - 2 b r c to the same absolute precision before subtracting).
-    // The node sum  sum_i w_i (r - b c_i) t_i,  t_i = (1 - z_i^3) / (1 - z_i^2),  is accumulated as
-    // r sum_i w_i t_i - b sum_i (w_i c_i) t_i: the c_i are constants here, so every node costs two fmas with
-    // a constant operand instead of (r - b c_i), a product and a share of the pair sum (rounding: ~3e-16 of
-    // a sum of order 1, i.e. ~1e-17 of flux).
-    double two_br[N], omr2b2[N], S1[N], S2[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-      two_br[q] = b[q] * r * 2.0;
-      omr2b2[q] = 1.0 - fma(b[q], b[q], r2);
-      S1[q] = 0.0;
-      S2[q] = 0.0;
-    }
-#pragma unroll
-    for (int p = 0; p < 5; ++p) {
-      const double wp = c_gl10[1][5 + p];
-      const double cm = c_gl10[2][5 + p], cq = c_gl10[2][4 - p];  // nodes +x_p, -x_p
-      const double wcm = c_gl10_wc[5 + p], wcq = c_gl10_wc[4 - p];
-      double z2[2 * N], t[2 * N];
-#pragma unroll
-      for (int m = 0; m < 2 * N; ++m) z2[m] = fma(two_br[m >> 1], (m & 1) ? cq : cm, omr2b2[m >> 1]);
-#pragma unroll
-      for (int m = 0; m < 2 * N; ++m) t[m] = fnode_factor(z2[m]);  // (1 - z^3) / (1 - z^2)
-#pragma unroll
-      for (int q = 0; q < N; ++q) {
-        S1[q] = fma(wp, t[2 * q] + t[2 * q + 1], S1[q]);
-        S2[q] = fma(wcm, t[2 * q], fma(wcq, t[2 * q + 1], S2[q]));
-      }
-    }
-    double acc[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) acc[q] = fma(-b[q], S2[q], r * S1[q]);
-    const double k1 = (pi * 0.5) * (r * (2.0 / 3.0));
-#pragma unroll
-    for (int q = 0; q < N; ++q) s1[q] = fma(-k1, acc[q], pi * (2.0 / 3.0));
-  } else {
-#pragma unroll
-    for (int q = 0; q < N; ++q) s1[q] = 0.0;
-  }
-  // s0s2, limb_dark.py:111-137 with kappa0 = pi, kappa1 = 0, area = 0
-  const double s0l = (1.0 - r2) * pi;
-  const double s0s = pi - r2 * pi;
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    const double bpr = b[q] + r;
-    const double onembpr2 = (1.0 + bpr) * (1.0 - bpr);
-    const double eta2 = r2 * fma(b[q] * b[q], 2.0, r2) * 0.5;
-    const double delta = b[q] * r * 4.0;
-    const bool large = onembpr2 + delta > delta;
-    const double s2l = s0l * 2.0 + (eta2 - 0.5) * (4.0 * pi);
-    const double s2s = s0s * 2.0 + (eta2 * pi * 2.0 - pi) * 2.0;
-    f[q] = ld_combine(lmax, large ? s0l : s0s, s1[q], large ? s2l : s2s, g0, g1, g2);
-  }
-}
 
 constexpr unsigned WK_RMAX = 8;   // chunks per claim (upper bound)
 constexpr unsigned WK_LOG = 32;   // claims a warp remembers before it signals their completion
@@ -1010,9 +1065,419 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// items: the sets with function tables (jxp_tables.cuh)
+// --------------------------------------------------------------------------------------------
+struct WalkFix {  // a sample of a table set that its tables do not answer
+  unsigned set, idx;
+  double b2;
+};
+static_assert(sizeof(WalkFix) == 16, "WalkFix");
+constexpr double WK_FIX_SCALE = 17592186044416.0;  // 2^44: the fractions of the chi^2 terms of fixed samples are summed in fixed point
+
+struct WalkItemArgs {
+  const double* rec;
+  const double* tab;
+  const uint4* items;
+  double* part;               // per-item partial sums
+  const WalkSet* wset;
+  WalkSet* wset_rw;
+  const unsigned long long* state;
+  unsigned long long* state_rw;  // [13]: item claim counter, [14]: fix entries, [15]: CTAs of k_walk_fix done
+  unsigned long long cap_chunk, cap_fix;
+  WalkFix* fix;
+  long long* fixsum;          // [n_sets][2] fixed-point sums (integer parts, fractions) of the chi^2 terms of a set's fixed samples
+  const double* scalars;
+  const double* t;
+  int64_t n_times;
+  const double* y;
+  const double* winv;
+  const double2* aw;
+  double* flux;
+  double* flux_sum;
+  double* loglike;
+  unsigned long long* counters;
+  unsigned long long* tstat;
+  int n_sets, n_bodies, body;
+};
+
+// the verdict of walk_eval_active, read only (k_walk_eval of the same call writes it down)
+__device__ __forceinline__ bool walk_items_active(const WalkItemArgs& a, int lane) {
+  const bool bad = a.scalars[LL_FLAG0 + lane] != 0.0 || a.scalars[LL_FLAG0 + 32 + lane] != 0.0;
+  const bool unsorted = __any_sync(0xffffffffu, bad);
+  const bool over = a.state[3] != 0ull || a.state[1] + a.state[2] > a.cap_chunk;
+  return !unsorted && !over;
+}
+
+// The partial sums of an item set added in item order by ONE lane -> loglike[set] (eight interleaved sums,
+// combined pairwise: the order depends on the set alone).
+__device__ __forceinline__ void walk_finish_items(const WalkItemArgs& a, unsigned set) {
+  __threadfence();
+  const WalkSet wsv = a.wset[set];
+  const double* p = a.part + wsv.chA;
+  const unsigned n = wsv.cntA;
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  for (unsigned i = 0; i < n; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = i + m < n ? __ldcg(p + i + m) : 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] += v[m];
+  }
+  const double tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  a.loglike[set] = -0.5 * (a.scalars[WALK_STATE0 + 10] + tot) + a.scalars[WALK_STATE0 + 11];
+}
+
+constexpr unsigned WI_CLAIM = 8;  // items per claim
+struct WalkItemSmem {
+  double tabs[TB_DOUBLES];
+  double rec[WALK_REC];
+};
+#ifndef JXP_ITEMS_MINB
+#define JXP_ITEMS_MINB 5
+#endif
+
+// One warp walks whole transits: an item is a run of consecutive samples of one transit of one set, so t, y and
+// 1 / sigma are read coalesced, 64 samples per round (two per lane; 32 in an item's last round when that is all
+// it needs), and everything that depends on the set sits in shared memory (loaded when the set changes: a claim is
+// WI_CLAIM consecutive items, mostly of one set).  Per sample: mean anomaly in the reference's operation order ->
+// offset from the conjunction -> b^2 from the set's series -> the flux from the piece of the set's F table the
+// sample falls on -> chi^2 term.  A sample whose piece is missing or invalid (NaN) goes on the fix list
+// (k_walk_fix: the direct quadrature code; a few 1e-4 of the samples, next to the contact point b = 1 - r) and
+// counts as zero here.  The lane sums of an item are added by a fixed shuffle tree into the item's partial sum; the
+// lane that completes a set adds the set's partial sums in item order: bit-reproducible.
+template <bool FLUX>
+__global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid_constant__ WalkItemArgs a) {
+  __shared__ __align__(16) WalkItemSmem s_all[4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (!walk_items_active(a, lane)) return;
+  const unsigned n_items = (unsigned)a.state[12];
+  if (n_items == 0u) return;
+  WalkItemSmem& sm = s_all[wid];
+  const double* th = sm.tabs;
+  const double* rec = sm.rec;
+  const double2* rec2 = reinterpret_cast<const double2*>(rec);
+  unsigned cur_set = 0xffffffffu;
+  unsigned n_ld = 0;
+  // constants of the current set (registers; re-read when the set changes)
+  double xs = 0.0, xe = 0.0, mc = 0.0, zsc = 0.0, zoff = 0.0, t0 = 0.0, tref = 0.0, per = 0.0, iper = 0.0;
+  double ti1 = 0.0, ti2 = 0.0, ti3 = 0.0, te1 = 0.0;
+  int j0 = 0, db = 0;
+  unsigned long long nxt = 0ull;
+  if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)WI_CLAIM);
+  for (;;) {
+    const unsigned base = (unsigned)__shfl_sync(0xffffffffu, nxt, 0);
+    if (base >= n_items) break;
+    if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)WI_CLAIM);  // read a claim later
+    const unsigned n_cl = n_items - base < WI_CLAIM ? n_items - base : WI_CLAIM;
+    uint4 its = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)lane < n_cl) its = __ldg(a.items + base + lane);
+    for (unsigned ii = 0; ii < n_cl; ++ii) {
+      const unsigned set = __shfl_sync(0xffffffffu, its.x, ii);
+      const unsigned lo = __shfl_sync(0xffffffffu, its.y, ii);
+      const unsigned cnt = __shfl_sync(0xffffffffu, its.z, ii);
+      if (set != cur_set) {
+        __syncwarp();
+        const double2* T = reinterpret_cast<const double2*>(a.tab + (size_t)set * TB_DOUBLES);
+        double2* dst = reinterpret_cast<double2*>(sm.tabs);
+#pragma unroll
+        for (int i = 0; i < (TB_DOUBLES / 2 + 31) / 32; ++i)
+          if (32 * i + lane < TB_DOUBLES / 2) dst[32 * i + lane] = __ldg(T + 32 * i + lane);
+        sm.rec[lane] = __ldg(a.rec + (size_t)set * WALK_REC + lane);
+        cur_set = set;
+        __syncwarp();
+        const double* H = th + TB_HDR;
+        xs = H[H_XS]; xe = H[H_XE]; ti1 = H[H_TI1]; ti2 = H[H_TI2]; ti3 = H[H_TI3]; te1 = H[H_TE1];
+        mc = H[H_MC]; zsc = H[H_ZSC]; zoff = H[H_ZOFF];
+        j0 = (int)((unsigned)__double_as_longlong(H[H_FINFO]) & 0xffu);
+        db = (int)((unsigned)__double_as_longlong(H[H_BINFO]) & 0xffu);
+        t0 = rec[WK_T0]; tref = rec[WK_TREF]; per = rec[WK_PERIOD]; iper = rec[WK_INVP];
+      }
+      double csum = 0.0;
+      // one round: NN samples per lane from sample r0 of the item on
+      auto round = [&](auto nn_tag, unsigned r0) {
+        constexpr int NN = decltype(nn_tag)::value;
+        bool have[NN];
+        unsigned ix[NN];
+        double ts[NN];
+        double2 awv[NN];
+#pragma unroll
+        for (int h = 0; h < NN; ++h) {
+          have[h] = r0 + 32u * h + lane < cnt;
+          ix[h] = have[h] ? lo + r0 + 32u * h + lane : lo;
+          ts[h] = __ldg(a.t + ix[h]);
+          if (!FLUX) awv[h] = __ldg(a.aw + ix[h]);
+        }
+        // ---- t -> mean anomaly (keplerian.py:538, kepler.py:31) in the reference's operation order.  The
+        // reference reduces M to [0, 2 pi) by subtracting k fl(2 pi) (exactly: jxp_math.cuh mod_two_pi); here k is
+        // chosen so that the remainder lands next to the conjunction's mean anomaly instead -- the same number up
+        // to one exact step of fl(2 pi) -- and the offset from the conjunction is one more subtraction.
+        double zv[NN], b2[NN];
+#pragma unroll
+        for (int h = 0; h < NN; ++h) {
+          const double x = (ts[h] - t0) - tref;
+          const double num = Num<double>::two_pi * x;
+          const double q = num * iper;
+          const double r = fma(-per, q, num);
+          const double M = fma(r, iper, q);
+          const double kk = rint((M - mc) * Num<double>::inv_two_pi);
+          const double d = fma(-kk, Num<double>::two_pi, M) - mc;
+          zv[h] = fma(d, zsc, zoff);
+          b2[h] = 0.0;
+        }
+        // b^2 from the series, four coefficients per step (the degree is padded to 4 k + 3 with zeros); degree
+        // <= 11 (most sets) without a loop
+        auto b2_step = [&](int k) {
+          const double2 c1 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 1);  // (m_{k-1}, m_k)
+          const double2 c0 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 3);  // (m_{k-3}, m_{k-2})
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            b2[h] = fma(fma(b2[h], zv[h], c1.y), zv[h], c1.x);
+            b2[h] = fma(fma(b2[h], zv[h], c0.y), zv[h], c0.x);
+          }
+        };
+        if (db > 11) {
+#pragma unroll 1
+          for (int k = db | 3; k > 11; k -= 4) b2_step(k);
+        }
+        b2_step(11);
+        b2_step(7);
+        b2_step(3);
+        // ---- the piece of the F table: binade of dx = (1 - r)^2 - b^2 inside the disk, else the ingress / egress
+        // pieces in sqrt(b^2 - (1 - r)^2) / sqrt((1 + r)^2 - b^2)
+        bool intr[NN], ins[NN], want_edge = false;
+        double q[NN];
+        int pc[NN];
+#pragma unroll
+        for (int h = 0; h < NN; ++h) {
+          intr[h] = have[h] && (b2[h] < xe);
+          q[h] = xs - b2[h];
+          ins[h] = q[h] > 0.0;
+          const int jb = tb_binade(q[h]);
+          pc[h] = jb < j0 ? j0 : (jb >= TB_NB ? TB_P_BAD : jb);
+          want_edge = want_edge || (intr[h] && !ins[h]);
+          n_ld += intr[h] ? 1u : 0u;
+        }
+        if (__any_sync(0xffffffffu, want_edge)) {
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            const bool ing = b2[h] < 1.0;
+            const double w = fsqrt_pos(fmax(ing ? -q[h] : xe - b2[h], 1e-300));
+            const int pe = ing ? TB_P_ING + (w >= ti1 ? 1 : 0) + (w >= ti2 ? 1 : 0) + (w >= ti3 ? 1 : 0)
+                               : TB_P_EGR + (w >= te1 ? 1 : 0);
+            pc[h] = ins[h] ? pc[h] : pe;
+            q[h] = ins[h] ? q[h] : w;
+          }
+        }
+        // (a sample that is not in transit reads the all-zero piece: F = 0 without a select)
+        const double2* P[NN];
+        double v[NN], acc[NN];
+#pragma unroll
+        for (int h = 0; h < NN; ++h) {
+          P[h] = reinterpret_cast<const double2*>(th + TB_PIECE0 + (intr[h] ? pc[h] : TB_P_ZERO) * TB_PSTRIDE);
+          const double2 so = *P[h];
+          v[h] = fma(q[h], so.x, so.y);
+          acc[h] = 0.0;
+        }
+#pragma unroll
+        for (int k = TB_NC / 2; k >= 1; --k) {
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            const double2 cc = P[h][k];  // (m_{2k-2}, m_{2k-1})
+            acc[h] = fma(fma(acc[h], v[h], cc.y), v[h], cc.x);
+          }
+        }
+        // a NaN (missing / invalid piece): onto the fix list; zero here
+        bool need[NN], need_any = false;
+#pragma unroll
+        for (int h = 0; h < NN; ++h) {
+          need[h] = !(acc[h] == acc[h]);
+          need_any = need_any || need[h];
+        }
+        if (__any_sync(0xffffffffu, need_any)) {
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            const unsigned mn = __ballot_sync(0xffffffffu, need[h]);
+            unsigned long long fb = 0ull;
+            if (lane == 0 && mn) fb = atomicAdd(a.state_rw + 14, (unsigned long long)__popc(mn));
+            fb = __shfl_sync(0xffffffffu, fb, 0);
+            if (need[h]) {
+              const unsigned long long slot = fb + __popc(mn & ((1u << lane) - 1u));
+              if (slot < a.cap_fix) {
+                WalkFix f;
+                f.set = set;
+                f.idx = ix[h];
+                f.b2 = b2[h];
+                a.fix[slot] = f;
+              }
+            }
+            acc[h] = need[h] ? 0.0 : acc[h];
+          }
+        }
+        if (FLUX) {
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            if (acc[h] != 0.0) {
+              const size_t o = (size_t)set * (size_t)a.n_times + ix[h];
+              if (a.flux_sum) a.flux_sum[o] = (a.body > 0) ? a.flux_sum[o] + acc[h] : acc[h];
+              if (a.flux) a.flux[o * (size_t)a.n_bodies + (size_t)a.body] = acc[h];
+            }
+          }
+        } else {
+          // chi^2 = sum_t ((y - 1) / sigma)^2 + sum_items [ (r0 - m / sigma)^2 - r0^2 ], the bracket = m (m / sigma^2 -
+          // 2 r0 / sigma) (exactly 0 for m = 0)
+#pragma unroll
+          for (int h = 0; h < NN; ++h) csum = fma(acc[h], fma(acc[h], awv[h].y, -awv[h].x), csum);
+        }
+      };
+      unsigned r0 = 0;
+      for (; r0 + 96u < cnt; r0 += 64u) round(std::integral_constant<int, 2>{}, r0);
+      if (cnt - r0 > 64u)
+        round(std::integral_constant<int, 3>{}, r0);
+      else if (cnt - r0 > 32u)
+        round(std::integral_constant<int, 2>{}, r0);
+      else if (cnt > r0)
+        round(std::integral_constant<int, 1>{}, r0);
+      if (!FLUX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) a.part[base + ii] = csum;
+      }
+    }
+    if (!FLUX) {
+      // completion: one fence for the claim's partial sums, then the items are counted into their sets; the lane
+      // that completes a set adds the set's partials in item order
+      __syncwarp();
+      __threadfence();
+      unsigned run = 0;
+      for (unsigned ii = 0; ii < n_cl; ++ii) {
+        const unsigned set = __shfl_sync(0xffffffffu, its.x, ii);
+        const unsigned nset = __shfl_sync(0xffffffffu, its.x, ii + 1u < n_cl ? ii + 1u : ii);
+        ++run;
+        if (ii + 1u == n_cl || nset != set) {
+          if (lane == 0) {
+            const unsigned prev = atomicAdd(&a.wset_rw[set].done, run);
+            if (prev + run == a.wset[set].cntA) walk_finish_items(a, set);
+          }
+          run = 0;
+        }
+      }
+    }
+  }
+  n_ld = __reduce_add_sync(0xffffffffu, n_ld);
+  if (lane == 0) atomicAdd(a.tstat, (unsigned long long)n_ld);  // (k_walk_fix takes its samples off again)
+  if (lane == 0) atomicAdd(a.counters + 1, (unsigned long long)n_ld);
+}
+
+// The samples of table sets the tables did not answer: the direct flux code (core/limb_dark.py:19-196), one
+// sample per thread.  Flux outputs are stored; chi^2 terms are added to the set's sum in FIXED POINT (2^-40: exact
+// integer adds, so the order the list was filled in does not matter), and the last CTA to finish folds the sums
+// into the log-likelihoods the item kernel wrote: bit-reproducible.
+template <bool FLUX>
+__global__ void __launch_bounds__(256) k_walk_fix(const __grid_constant__ WalkItemArgs a) {
+  const int lane = threadIdx.x & 31;
+  if (!walk_items_active(a, lane)) return;
+  unsigned long long n_fix = a.state[14];
+  if (n_fix == 0ull) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(a.tstat, 0ull - (n_fix < a.cap_fix ? n_fix : a.cap_fix));
+    atomicAdd(a.tstat + 1, n_fix);
+  }
+  if (n_fix > a.cap_fix) {  // the list did not fit: the window-test kernels behind this one redo the call
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[3] |= 2ull;
+    return;
+  }
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_fix;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const WalkFix f = a.fix[i];
+    const double* rec = a.rec + (size_t)f.set * WALK_REC;
+    const int lmax = (int)((unsigned)__double_as_longlong(rec[WK_FLAGS]) >> 8);
+    double bq[1] = {fsqrt(fmax(f.b2, 0.0))}, rq[1] = {rec[WK_RR]}, s0[1], s1[1], s2[1];
+    ld_solution_n<1, 1>(bq, rq, lmax, s0, s1, s2);
+    const double F = ld_combine(lmax, s0[0], s1[0], s2[0], rec[WK_G0], rec[WK_G1], rec[WK_G2]);
+    if (FLUX) {
+      if (F != 0.0) {
+        const size_t o = (size_t)f.set * (size_t)a.n_times + f.idx;
+        if (a.flux_sum) a.flux_sum[o] = (a.body > 0) ? a.flux_sum[o] + F : F;
+        if (a.flux) a.flux[o * (size_t)a.n_bodies + (size_t)a.body] = F;
+      }
+    } else {
+      const double wv = a.winv[f.idx];
+      const double r0v = (a.y[f.idx] - 1.0) * wv;
+      const double mw = F * wv;
+      const double term = (F != 0.0) ? (-mw) * (2.0 * r0v - mw) : 0.0;
+      // integer part and fraction (2^-44) separately: exact adds, no overflow below ~1e6 samples per set
+      const double hi = rint(term);
+      const long long qh = __double2ll_rn(hi), ql = __double2ll_rn((term - hi) * WK_FIX_SCALE);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.fixsum + 2 * (size_t)f.set), (unsigned long long)qh);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.fixsum + 2 * (size_t)f.set + 1), (unsigned long long)ql);
+    }
+  }
+  if (!FLUX) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.state_rw + 15, 1ull) == (unsigned long long)(gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      // (eight sets per thread and step, every load of a step issued before the first use: two round trips per step)
+      const longlong2* fs = reinterpret_cast<const longlong2*>(a.fixsum);
+      for (int s0 = threadIdx.x; s0 < a.n_sets; s0 += 8 * (int)blockDim.x) {
+        longlong2 v[8];
+        unsigned isitem[8];
+        double ll[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int s = s0 + u * (int)blockDim.x;
+          const bool in = s < a.n_sets;
+          v[u] = in ? __ldcg(fs + s) : make_longlong2(0ll, 0ll);
+          isitem[u] = in ? __ldcg(&a.wset[s].cntB) : 0u;
+          ll[u] = in ? __ldcg(a.loglike + s) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int s = s0 + u * (int)blockDim.x;
+          if ((v[u].x != 0ll || v[u].y != 0ll) && isitem[u] == 1u)
+            a.loglike[s] = fma(-0.5, (double)v[u].x + (double)v[u].y * (1.0 / WK_FIX_SCALE), ll[u]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace jxp
 
 namespace jxph {
+
+
+// A side stream per (host thread, device) for work that may run beside the caller's stream (fork / join by events).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static thread_local SideStream tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = tab[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      s.stream = nullptr;
+      return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamDestroy(s.stream);
+      s.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
 
 // Launches of the transit-walk path (double, quadratic law, order 10).  Per body of the system: a plan launch
 // (records, segments, chunk entries, likelihood terms / sortedness flags), then the evaluation; the bodies of
@@ -1065,6 +1530,20 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
   a.flux = flux;
   a.flux_sum = flux_sum;
   a.loglike = loglike;
+  const bool use_tables = (dev_options() & JXP_DEV_NO_TABLES) == 0;
+  a.tab = use_tables ? reinterpret_cast<double*>(ws + L.off_wk_tab) : nullptr;
+  a.items = use_tables && !expo ? reinterpret_cast<uint4*>(ws + L.off_wk_items) : nullptr;
+  a.cap_items = L.wk_cap_items;
+  a.fixsum = reinterpret_cast<long long*>(ws + L.off_wk_fixsum);
+  a.aw = (a.items != nullptr && loglike) ? reinterpret_cast<double2*>(ws + L.off_wk_aw) : nullptr;
+  TabArgs ta;
+  ta.bodies = bodies;
+  ta.n_sets = n_sets;
+  ta.n_bodies = n_bodies;
+  ta.u = u;
+  ta.n_u = n_u;
+  ta.u_stride = u_stride;
+  ta.tab = a.tab;
 
   WalkEvalArgs b;
   b.rec = a.rec;
@@ -1113,9 +1592,35 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
   for (int body = 0; body < n_bodies; ++body) {
     a.body = body;
     b.body = body;
-    cudaError_t e = cudaMemsetAsync(a.state, 0, 10 * sizeof(unsigned long long), st);
+    cudaEvent_t join_ev = nullptr;
+    // (slots 10, 11 hold the likelihood terms the plan launch writes; 12, 13: item allocation / claims; 14, 15: k_walk_fix)
+    cudaError_t e = cudaMemsetAsync(a.state, 0, 16 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
-    if (ev_start && ev_which == 1 && body == 0) cudaEventRecord(ev_start, st);
+    if (body == 0) {
+      e = cudaMemsetAsync(d_scalars + WALK_TSTAT0, 0, 4 * sizeof(unsigned long long), st);
+      if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
+    }
+    if (ev_start && (ev_which == 1 || ev_which == 2) && body == 0) cudaEventRecord(ev_start, st);
+    bool forked = false;
+    if (use_tables) {
+      // the flux tables depend on (r, u) alone: built beside the plan on a side stream (fork / join by events, which
+      // a stream capture follows too); serial when the table launch itself is being timed
+      ta.body = body;
+      SideStream* ss = ev_which == 2 ? nullptr : side_stream();
+      if (ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess &&
+          cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+        k_walk_tables<<<(n_sets + 3) / 4, 128, 0, ss->stream>>>(ta);
+        forked = true;
+      } else {
+        k_walk_tables<<<(n_sets + 3) / 4, 128, 0, st>>>(ta);
+      }
+      int rct = check_launch("jxp_system_light_curve(walk tables)");
+      if (rct == JXP_OK && forked && cudaEventRecord(ss->join, ss->stream) != cudaSuccess)
+        rct = fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk tables): event record");
+      if (rct != JXP_OK) return rct;
+      if (forked) join_ev = ss->join;
+    }
+    if (ev_stop && ev_which == 2 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
     if (loglike)
       k_walk_plan<CH, true><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
     else
@@ -1133,6 +1638,64 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
     if (ev_stop && ev_which == 0 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
     rc = check_launch("jxp_system_light_curve(walk eval)");
     if (rc != JXP_OK) return rc;
+    if (a.items != nullptr) {
+      WalkItemArgs c;
+      c.rec = a.rec;
+      c.tab = a.tab;
+      c.items = a.items;
+      c.part = reinterpret_cast<double*>(ws + L.off_wk_ipart);
+      c.wset = a.wset;
+      c.wset_rw = a.wset;
+      c.state = a.state;
+      c.state_rw = a.state;
+      c.cap_chunk = a.cap_chunk;
+      c.scalars = d_scalars;
+      c.t = t;
+      c.n_times = n_times;
+      c.y = y;
+      c.winv = a.winv;
+      c.aw = a.aw;
+      c.flux = flux;
+      c.flux_sum = flux_sum;
+      c.loglike = loglike;
+      c.counters = a.counters;
+      c.tstat = reinterpret_cast<unsigned long long*>(d_scalars + WALK_TSTAT0);
+      c.n_bodies = n_bodies;
+      c.body = body;
+      c.cap_fix = L.wk_cap_fix;
+      c.fix = reinterpret_cast<WalkFix*>(ws + L.off_wk_fix);
+      c.fixsum = a.fixsum;
+      c.n_sets = n_sets;
+      static thread_local int it_per_sm[2] = {0, 0};
+      int& ips = it_per_sm[loglike ? 0 : 1];
+      if (ips == 0) {
+        cudaError_t eo = loglike ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ips, k_walk_items<false>, 128, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ips, k_walk_items<true>, 128, 0);
+        if (eo != cudaSuccess || ips < 1) {
+          ips = 0;
+          return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk items): occupancy query: %s", cudaGetErrorString(eo));
+        }
+      }
+      if (join_ev != nullptr && cudaStreamWaitEvent(st, join_ev, 0) != cudaSuccess)
+        return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk tables): join");
+      join_ev = nullptr;
+      const unsigned igrid = (unsigned)(ips * sm_count());
+      const unsigned fgrid = (unsigned)((n_sets + 3) / 4 < 148 ? (n_sets + 3) / 4 : 148);
+      if (ev_start && ev_which == 3 && body == 0) cudaEventRecord(ev_start, st);
+      if (loglike)
+        k_walk_items<false><<<igrid, 128, 0, st>>>(c);
+      else
+        k_walk_items<true><<<igrid, 128, 0, st>>>(c);
+      if (ev_stop && ev_which == 3 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
+      if (loglike)
+        k_walk_fix<false><<<fgrid, 256, 0, st>>>(c);
+      else
+        k_walk_fix<true><<<fgrid, 256, 0, st>>>(c);
+      rc = check_launch("jxp_system_light_curve(walk items)");
+      if (rc != JXP_OK) return rc;
+    }
+    if (join_ev != nullptr && cudaStreamWaitEvent(st, join_ev, 0) != cudaSuccess)
+      return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk tables): join");
   }
   return JXP_OK;
 }

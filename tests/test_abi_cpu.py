@@ -59,9 +59,12 @@ def test_argument_validation_messages(lib):
     assert lib.jxp_system_workspace_bytes(0, 1, 10) == 0
     # the transit walk keeps nothing per sample: records, 8-byte segments (3 per transit; room for one transit
     # per 72 samples) and one 24-byte slot per chunk of in-window samples for 1/8 of the grid -- about half a
-    # byte per (set, sample), against 1.5 bytes for round 1's materialised list
+    # byte per (set, sample), against 1.5 bytes for round 1's materialised list; the per-set function tables
+    # (3.5 KB per set), the transit items of the sets that use them (24 bytes per transit slot, room for 1/21 of
+    # the grid) and the fix list add ~0.15 byte
     one = lib.jxp_system_workspace_bytes(4096, 1, 100000)
-    assert 24 * (4096 * 100000 // 256) <= one < 6 * (4096 * 100000 // 10)
+    assert 24 * (4096 * 100000 // 256) <= one < 0.75 * 4096 * 100000
+    assert lib.jxp_system_walk_stats(None, 4, 1, 10, None, None) == -1
     # development options: one process-wide word, default 0
     assert lib.jxp_get_dev_options() == 0
     assert lib.jxp_set_dev_options(5) == 0 and lib.jxp_get_dev_options() == 5

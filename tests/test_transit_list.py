@@ -17,6 +17,17 @@ from oracle import ref_numpy as ref
 
 pytestmark = pytest.mark.gpu
 
+LAST_WALK = {}  # jxp_system_walk_stats of the last _loglike_abi / _flux_abi call (per-set function tables)
+
+
+def _walk_stats(ws, n_sets, n_t):
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+
+    st = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_system_walk_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(st), A.stream_ptr())
+    LAST_WALK.update(tab_evals=int(st[0]), n_fix=int(st[1]), tab_sets=int(st[2]), no_tables=int(st[3]))
+
 
 def _loglike_abi(system, u, t, y, sigma):
     """Log-likelihood through the C ABI with a workspace we keep -> (loglike, list items, list flags)."""
@@ -45,6 +56,7 @@ def _loglike_abi(system, u, t, y, sigma):
               1 if sg.size > 1 else 0, out.data_ptr(), ws.data_ptr(), ws.numel(), A.stream_ptr())
     stats = (ctypes.c_int64 * 4)()
     _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(stats), A.stream_ptr())
+    _walk_stats(ws, n_sets, n_t)
     return out.cpu().numpy(), int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3])
 
 
@@ -80,15 +92,28 @@ def test_list_path_matches_oracle_and_window_kernels_c3_like():
     truth = ref.system_light_curve([ref.orbital_body(**{k: v[0] for k, v in p.items()})], ub[0], t)[:, 0]
     y = 1 + truth + noise
     sys_ = _system(p)
-    ll, items, flags, inside, fast = _loglike_abi(sys_, ub, t, y, sigma)
-    assert flags == 0 and 0.01 * 300 * 40_000 < items < 0.08 * 300 * 40_000
+    from jaxoplanet_b200 import _lib
+
+    want = _oracle_loglike(p, ub, t, y, sigma, range(0, 300, 7))
     ll2, items2, flags2 = _without_list(lambda: _loglike_abi(sys_, ub, t, y, sigma))[:3]
     assert items2 == 0  # the list kernels were not launched
-    # two programs, different summation orders: terms of 1e-16 * 1 / sigma^2
-    assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
-    want = _oracle_loglike(p, ub, t, y, sigma, range(0, 300, 7))
-    for s, w in want.items():
-        assert abs(ll[s] - w) <= 1e-12 * abs(w)
+    # the walk with the per-set function tables (the default: csrc/jxp_tables.cuh) and with the direct Kepler +
+    # quadrature code on the chunk lists
+    lls = {}
+    for tables in (True, False):
+        with _lib.dev_options(0 if tables else _lib.JXP_DEV_NO_TABLES):
+            ll, items, flags, inside, fast = _loglike_abi(sys_, ub, t, y, sigma)
+        lls[tables] = ll
+        assert flags == 0 and 0.01 * 300 * 40_000 < items < 0.08 * 300 * 40_000
+        # different programs, different summation orders: terms of 1e-16 * 1 / sigma^2
+        assert np.max(np.abs(ll - ll2) / np.abs(ll2)) <= 2e-12
+        for s, w in want.items():
+            assert abs(ll[s] - w) <= 1e-12 * abs(w)
+        if tables:  # nearly every evaluation is answered by a table; the rest (next to b = 1 - r) by k_walk_fix
+            assert LAST_WALK["tab_sets"] >= 0.98 * 300 and LAST_WALK["no_tables"] <= 6
+            assert LAST_WALK["tab_evals"] > 0.9 * items and 0 < LAST_WALK["n_fix"] < 2e-3 * items
+        else:
+            assert LAST_WALK["tab_sets"] == 0 and LAST_WALK["tab_evals"] == 0
     assert inside > 0.5 * items and fast > 0.9 * (inside // 64)  # most of the list takes the inside-the-disk code
     # flux-level check of both flux codes: with y = 1 and a tiny sigma the likelihood is dominated by
     # sum (lc / sigma)^2, so its relative error is twice the (weighted) relative error of lc itself --
@@ -103,7 +128,10 @@ def test_list_path_matches_oracle_and_window_kernels_c3_like():
     # bit-reproducible although the slices of the list are handed out by atomics
     for _ in range(3):
         again, _, _ = _loglike_abi(sys_, ub, t, y, sigma)[:3]
-        assert np.array_equal(again, ll)
+        assert np.array_equal(again, lls[True])
+        with _lib.dev_options(_lib.JXP_DEV_NO_TABLES):
+            again, _, _ = _loglike_abi(sys_, ub, t, y, sigma)[:3]
+        assert np.array_equal(again, lls[False])
     # per-sample sigma
     sig_t = sigma * (1 + 0.2 * np.random.default_rng(5).uniform(size=t.size))
     ll3, _, f3 = _loglike_abi(sys_, ub, t, y, sig_t)[:3]
@@ -388,6 +416,7 @@ def _flux_abi(system, u, t, per_body=False):
               None if per_body else out.data_ptr(), None, None, 0, None, ws.data_ptr(), nbytes, A.stream_ptr())
     st = (ctypes.c_int64 * 4)()
     _lib.call("jxp_system_list_stats", ws.data_ptr(), n_sets, 1, n_t, ctypes.addressof(st), A.stream_ptr())
+    _walk_stats(ws, n_sets, n_t)
     return out.cpu().numpy(), [int(v) for v in st]
 
 
@@ -396,12 +425,20 @@ def test_flux_outputs_take_the_list_and_match_oracle_and_window_kernels():
 
     p, ub, t, _, _ = W.c3(150, 25_000)
     sys_ = _system(p)
-    for per_body in (False, True):
-        f, st = _flux_abi(sys_, ub, t, per_body)
-        assert st[1] == 0 and st[0] > 0 and st[2] > 0.5 * st[0]
+    from jaxoplanet_b200 import _lib
+
+    for per_body, tables in ((False, True), (True, True), (False, False), (True, False)):
+        with _lib.dev_options(0 if tables else _lib.JXP_DEV_NO_TABLES):
+            f, st = _flux_abi(sys_, ub, t, per_body)
+        assert st[1] == 0 and st[0] > 0
+        if tables:  # per-set function tables: the samples are items of whole transits, not list positions
+            assert LAST_WALK["tab_sets"] >= 0.98 * 150 and LAST_WALK["tab_evals"] > 0.9 * st[0]
+        else:
+            assert st[2] > 0.5 * st[0] and LAST_WALK["tab_evals"] == 0
         fw, stw = _without_list(lambda: _flux_abi(sys_, ub, t, per_body))
         assert stw[0] == 0
-        assert np.array_equal(f != 0, fw != 0) and np.max(np.abs(f - fw)) <= 1e-15
+        # (the tables reproduce the direct code to its own rounding noise, a few 1e-16)
+        assert np.array_equal(f != 0, fw != 0) and np.max(np.abs(f - fw)) <= (2e-15 if tables else 1e-15)
         for s in range(0, 150, 11):
             bd = ref.orbital_body(**{k: v[s] for k, v in p.items()})
             want = ref.system_light_curve([bd], ub[s], t)[:, 0]

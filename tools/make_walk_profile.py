@@ -1,7 +1,8 @@
-"""profiles/r2_walk_eval.json + .md from an ncu --set full report of k_walk_eval inside bench.py.
-usage: python tools/make_walk_profile.py REPORT.ncu-rep ITEMS"""
+"""profiles/r2_walk_eval.json (or r2_walk_items.json) from an ncu --set full report of k_walk_eval / k_walk_items
+inside bench.py.  usage: python tools/make_walk_profile.py REPORT.ncu-rep ITEMS [k_walk_items]"""
 import collections, csv, io, json, subprocess, sys
 rep, items = sys.argv[1], int(sys.argv[2])
+kern = sys.argv[3] if len(sys.argv) > 3 else "k_walk_eval"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); h, u, r = rows[0], rows[1], rows[2]; d = dict(zip(h, r)); un = dict(zip(h, u))
 g = lambda k: float(d[k].replace(",", ""))
@@ -30,7 +31,7 @@ out = dict(kernel=d["Kernel Name"], workload="bench.py config 3, one GPU: 4096 s
            grid=int(g("launch__grid_size")), dram_bytes_read=bytes_of("dram__bytes_read.sum"), dram_bytes_write=bytes_of("dram__bytes_write.sum"),
            note="predicated-on thread instructions summed over the SASS lines of the ncu source page; a launch on the same seeded "
                 "inputs executes the same instructions, so bench.py divides these by the LIVE kernel duration",
-           source="ncu --set full --clock-control none --import-source on -k regex:k_walk_eval -s 12 -c 1 python bench.py --steps 3 "
-                  "--warmup 3 --no-secondary --no-cpu (tools/gpu_bench_round.sh); summary: profiles/r2_bench_walk_eval.md")
-json.dump(out, open("profiles/r2_walk_eval.json", "w"), indent=1)
+           source="ncu --set full --clock-control none --import-source on -k regex:%s -s 12 -c 1 python bench.py --steps 3 "
+                  "--warmup 3 --no-secondary --no-cpu (tools/gpu_bench_round.sh); summary: profiles/r2_bench_%s.md" % (kern, kern[2:]))
+json.dump(out, open("profiles/r2_%s.json" % kern[2:], "w"), indent=1)
 print(json.dumps(out, indent=1))
