@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
   }
   // ---- b^2 series of the set (jxp_tables.cuh): lanes = the 32 Chebyshev nodes of the transit window (widened by
   // the exposure stencil); node values from the same Kepler / sky-position code the direct path uses
-  bool tab_set = false;  // this set is evaluated from its function tables (k_walk_items)
+  bool tab_set = false;  // this set is evaluated from its function tables by k_walk_items (whole transits) ...
+  bool tab_ok = false;   // ... or, from the chunk lists, by k_walk_eval (exposure stencils, short transits)
   if (a.tab != nullptr) {
     double* T = a.tab + (size_t)s * TB_DOUBLES;
     const double dlo = wlo + a.dt_lo * c.inv_period, dhi = whi + a.dt_hi * c.inv_period;
@@ -329,17 +330,18 @@ __global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ Wa
       const SetC<double>& sc = a.out_s[s];
       const double ar = fabs((double)c.rr);
       const bool fin = ar >= TB_R_MIN && ar <= TB_R_MAX && isfinite(sc.g0) && isfinite(sc.g1) && isfinite(sc.g2);
-      tab_set = okb && fin && a.items != nullptr && wsamp >= 12.0 && n_tr < (1ll << 22);
+      tab_ok = okb && fin;
+      tab_set = tab_ok && a.items != nullptr && wsamp >= 12.0 && n_tr < (1ll << 22);
     }
     if (lane == 0) {
       double* H = T + TB_HDR;
       unsigned long long* ts = reinterpret_cast<unsigned long long*>(a.scalars + WALK_TSTAT0);
-      if (tab_set) atomicAdd(ts + 2, 1ull);
-      else if (a.items != nullptr && n_tr > 0 && !all) atomicAdd(ts + 3, 1ull);  // transiting sets without tables
+      if (tab_ok) atomicAdd(ts + 2, 1ull);
+      else if (n_tr > 0 && !all) atomicAdd(ts + 3, 1ull);  // transiting sets without tables
       H[H_MC] = Mc;
       H[H_ZSC] = 1.0 / (Num<double>::two_pi * half);
       H[H_ZOFF] = -mid / half;
-      H[H_BINFO] = __longlong_as_double((long long)((tab_set ? TB_VALID : 0u) | (unsigned)(DB | 1)));
+      H[H_BINFO] = __longlong_as_double((long long)((tab_ok ? TB_VALID : 0u) | (unsigned)(DB | 1)));
       H[12] = H[13] = H[14] = H[15] = 0.0;
     }
   }
@@ -608,6 +610,9 @@ struct WalkEvalArgs {
   WalkSet* wset_rw;
   unsigned long long* counters;
   int n_bodies, body;  // flux outputs: this launch's column; body > 0 adds into flux_sum and into the counters
+  const double* tab;   // function tables (jxp_tables.cuh) or nullptr: chunks of sets that have them take two Horner
+                       // chains per (sub-)sample instead of the Kepler solve and the quadrature
+  unsigned long long* tstat;  // [0]: evaluations answered by a table
   Stencil st;          // exposure integration (EXPO instantiation): offsets and weights of the sub-samples
 };
 
@@ -726,6 +731,7 @@ struct WalkWarpSmem {
   double wb[2][32 * N];
   unsigned ib[2][32 * N];             // sample indices (0xffffffff: padding)
   unsigned long long log[WK_LOG];     // finished claims: first slot | chunks << 32
+  double tabs[2][TB_DOUBLES];         // function tables of two sets (a set's tables travel when the set changes)
 };
 
 // EXPO (flux outputs only): every item is evaluated at its n_sub sub-sample times t + dt_j and the weighted
@@ -787,11 +793,24 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     cnt = (unsigned)(raw >> 32) & 0xffffu;
     return (raw & CL_VALID) != 0ull;
   };
+  unsigned tset0 = 0xffffffffu, tset1 = 0xffffffffu;  // sets whose tables sm.tabs[0], [1] hold
+  int tcur = 0, tnext = 0;                            // table buffer of this chunk / of the next one
   auto stage_entries = [&](int buf, unsigned slot0, unsigned cnt) {
     if ((unsigned)lane < cnt) cp_async16(&sm.ent[buf][lane], a.chunk + slot0 + lane);
   };
   auto stage_rec_seg = [&](int buf, const uint4& e) {  // the chunk's set record and its segment window
     cp_async8(&sm.rec[buf][lane], a.rec + (size_t)e.x * WALK_REC + lane);
+    if (a.tab != nullptr) {
+      tnext = e.x == (tcur ? tset1 : tset0) ? tcur : tcur ^ 1;
+      if ((tnext ? tset1 : tset0) != e.x) {
+        const double2* T = reinterpret_cast<const double2*>(a.tab + (size_t)e.x * TB_DOUBLES);
+        double2* dst = reinterpret_cast<double2*>(sm.tabs[tnext]);
+#pragma unroll
+        for (int i = 0; i < (TB_DOUBLES / 2 + 31) / 32; ++i)
+          if (32 * i + lane < TB_DOUBLES / 2) cp_async16(dst + 32 * i + lane, T + 32 * i + lane);
+        if (tnext) tset1 = e.x; else tset0 = e.x;
+      }
+    }
     const unsigned nr = e.w & 255u;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
@@ -815,6 +834,7 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   };
 
   unsigned n_ld = 0, n_fast = 0;  // per lane: limb-darkening evaluations, of which with the constant-kappa code
+  unsigned n_tab = 0;             // ... and of which answered by the set's tables
   unsigned nlog = 0;
   // completion of the logged claims: one fence for all their partial sums, then lane i counts the finished
   // chunks of claim i into their sets; the lane that completes a set adds the set's partials in a fixed
@@ -857,6 +877,7 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   cp_async_wait_all();
   __syncwarp();
   stage_rec_seg(0, sm.ent[0][0]);
+  tcur = tnext;
   cp_async_wait_all();
   __syncwarp();
   stage_samples(0, sm.ent[0][0], 0);
@@ -892,6 +913,12 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     // division by the period is a multiplication by fl(1 / P) with one residual correction
     const double2 tt = rec2[WK_T0 / 2], pp = rec2[WK_PERIOD / 2];
     const int lmax = (int)((unsigned)__double_as_longlong(rec[WK_FLAGS]) >> 8);
+    unsigned finfo = 0u, binfo = 0u;
+    if (a.tab != nullptr) {
+      finfo = (unsigned)__double_as_longlong(sm.tabs[tcur][TB_HDR + H_FINFO]);
+      binfo = (unsigned)__double_as_longlong(sm.tabs[tcur][TB_HDR + H_BINFO]);
+    }
+    const bool use_tab = ((finfo & binfo) & TB_VALID) != 0u;
     double tsamp[N], wsum[N];
 #pragma unroll
     for (int h = 0; h < N; ++h) {
@@ -910,79 +937,180 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
       const double r = fma(-pp.x, q, num);
       Mr[h] = mod_two_pi(fma(r, pp.y, q));
     }
-    double yD[N], xD[N];
+    double tot[N];
+    bool intr[N];
+    if (use_tab) {
+      // ================= the set has function tables (jxp_tables.cuh): b^2 from its series in the mean anomaly, the
+      // flux from the piece of its F(b) table the (sub-)sample falls on; a piece that is missing or did not converge
+      // (NaN) sends the sample to the direct flux code below
+      const double* th = sm.tabs[tcur];
+      const double* H = th + TB_HDR;
+      const double xs = H[H_XS], xe = H[H_XE], mc = H[H_MC], zsc = H[H_ZSC], zoff = H[H_ZOFF];
+      const int j0 = (int)(finfo & 0xffu), db = (int)(binfo & 0xffu);
+      double zv[N], b2[N];
+#pragma unroll
+      for (int h = 0; h < N; ++h) {
+        double d = Mr[h] - mc;
+        d = d > Num<double>::pi ? d - Num<double>::two_pi : d;
+        d = d < -Num<double>::pi ? d + Num<double>::two_pi : d;
+        zv[h] = fma(d, zsc, zoff);
+        b2[h] = 0.0;
+      }
+#pragma unroll 1
+      for (int k = db | 3; k > 0; k -= 4) {
+        const double2 c1 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 1);  // (m_{k-1}, m_k)
+        const double2 c0 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 3);  // (m_{k-3}, m_{k-2})
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+          b2[h] = fma(fma(b2[h], zv[h], c1.y), zv[h], c1.x);
+          b2[h] = fma(fma(b2[h], zv[h], c0.y), zv[h], c0.x);
+        }
+      }
+      bool ins[N], want_edge = false;
+      double q[N];
+      int pc[N];
+#pragma unroll
+      for (int h = 0; h < N; ++h) {
+        intr[h] = (32u * h + lane < valid) && (b2[h] < xe);
+        q[h] = xs - b2[h];
+        ins[h] = q[h] > 0.0;
+        const int jb = tb_binade(q[h]);
+        pc[h] = jb < j0 ? j0 : (jb >= TB_NB ? TB_P_BAD : jb);
+        want_edge = want_edge || (intr[h] && !ins[h]);
+        n_ld += intr[h] ? 1u : 0u;
+      }
+      if (__any_sync(0xffffffffu, want_edge)) {
+        const double ti1 = H[H_TI1], ti2 = H[H_TI2], ti3 = H[H_TI3], te1 = H[H_TE1];
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+          const bool ing = b2[h] < 1.0;
+          const double w = fsqrt_pos(fmax(ing ? -q[h] : xe - b2[h], 1e-300));
+          const int pe = ing ? TB_P_ING + (w >= ti1 ? 1 : 0) + (w >= ti2 ? 1 : 0) + (w >= ti3 ? 1 : 0)
+                             : TB_P_EGR + (w >= te1 ? 1 : 0);
+          pc[h] = ins[h] ? pc[h] : pe;
+          q[h] = ins[h] ? q[h] : w;
+        }
+      }
+      const double2* P[N];
+      double v[N], acc[N];
+#pragma unroll
+      for (int h = 0; h < N; ++h) {
+        P[h] = reinterpret_cast<const double2*>(th + TB_PIECE0 + (intr[h] ? pc[h] : TB_P_ZERO) * TB_PSTRIDE);
+        const double2 so = *P[h];
+        v[h] = fma(q[h], so.x, so.y);
+        acc[h] = 0.0;
+      }
+#pragma unroll
+      for (int k = TB_NC / 2; k >= 1; --k) {
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+          const double2 cc = P[h][k];  // (m_{2k-2}, m_{2k-1})
+          acc[h] = fma(fma(acc[h], v[h], cc.y), v[h], cc.x);
+        }
+      }
+      bool need[N], need_any = false;
+#pragma unroll
+      for (int h = 0; h < N; ++h) {
+        need[h] = !(acc[h] == acc[h]);
+        need_any = need_any || need[h];
+        tot[h] = need[h] ? 0.0 : acc[h];
+        n_tab += (intr[h] && !need[h]) ? 1u : 0u;
+      }
+      // ================= mid: the next chunk's segment window has landed -> its samples start to fly
+      if (j == 0) {
+        cp_async_wait_all();
+        __syncwarp();
+        stage_samples(pb ^ 1, en, rb ^ 1);
+      }
+      if (__any_sync(0xffffffffu, need_any)) {
+        const double2 gg = rec2[WK_G0 / 2];
+        const double g2 = rec[WK_G2];
+        double bq[N], rq[N], s0[N], s1v[N], s2[N];
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+          bq[h] = fsqrt(fmax(b2[h], 0.0));
+          rq[h] = rec[WK_RR];
+        }
+        ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
+#pragma unroll
+        for (int h = 0; h < N; ++h)
+          if (need[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
+      }
+    } else {
+      double yD[N], xD[N];
 #if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 1)
-    // measurement only: no Kepler solve
+      // measurement only: no Kepler solve
 #pragma unroll
-    for (int h = 0; h < N; ++h) {
-      yD[h] = Mr[h] * 1e-3;
-      xD[h] = 1.0 - Mr[h] * 1e-4;
-    }
+      for (int h = 0; h < N; ++h) {
+        yD[h] = Mr[h] * 1e-3;
+        xD[h] = 1.0 - Mr[h] * 1e-4;
+      }
 #else
-    {
-      const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
-      kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], yD, xD);
-    }
+      {
+        const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
+        kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], yD, xD);
+      }
 #endif
-    // ---- sky position (keplerian.py:568-576, 630-632; light_curves/limb_dark.py:53): with
-    // (x0, y0) = -a (xD, yD) the constants -a / R*, cos i and -sin i are folded into k1, k2, zs
-    const double2 ws2 = rec2[WK_CW / 2], kk = rec2[WK_K1 / 2], zo = rec2[WK_ZS / 2];
-    const double rr = rec[WK_RR];
-    const double ar = fabs(rr);
-    const bool r_ok = (ar < 1.0) && (ar >= 2e-6);  // what ld_inside_u needs of the set ...
-    const double b_lim = (1.0 - ar) - 4e-15;       // ... and of the sample
-    double tot[N], bq[N];
-    bool intr[N], fast[N], want_gen = false, want_fast = false;
+      // ---- sky position (keplerian.py:568-576, 630-632; light_curves/limb_dark.py:53): with
+      // (x0, y0) = -a (xD, yD) the constants -a / R*, cos i and -sin i are folded into k1, k2, zs
+      const double2 ws2 = rec2[WK_CW / 2], kk = rec2[WK_K1 / 2], zo = rec2[WK_ZS / 2];
+      const double rr = rec[WK_RR];
+      const double ar = fabs(rr);
+      const bool r_ok = (ar < 1.0) && (ar >= 2e-6);  // what ld_inside_u needs of the set ...
+      const double b_lim = (1.0 - ar) - 4e-15;       // ... and of the sample
+      double bq[N];
+      bool fast[N], want_gen = false, want_fast = false;
 #pragma unroll
-    for (int h = 0; h < N; ++h) {
-      const double u1 = fma(ws2.x, xD[h], -ws2.y * yD[h]);
-      const double u2 = fma(ws2.y, xD[h], ws2.x * yD[h]);
-      const double v1 = kk.x * u1, v2 = kk.y * u2;
-      bq[h] = fsqrt(fma(v1, v1, v2 * v2));
-      intr[h] = (32u * h + lane < valid) && (zo.x * u2 > 0.0) && !(bq[h] >= zo.y);
-      // the flux code an item gets depends on the item alone: inside list AND b safely below 1 - r
-      fast[h] = inside_list && (bq[h] < b_lim) && r_ok;
-      n_ld += intr[h] ? 1u : 0u;
-      n_fast += (intr[h] && fast[h]) ? 1u : 0u;
-      want_gen = want_gen || (intr[h] && !fast[h]);
-      want_fast = want_fast || (intr[h] && fast[h]);
-      tot[h] = 0.0;
-    }
-    want_gen = __any_sync(0xffffffffu, want_gen);
-    want_fast = __any_sync(0xffffffffu, want_fast);
-    // ================= mid: the next chunk's segment window has landed -> its samples start to fly
-    if (j == 0) {
-      cp_async_wait_all();
-      __syncwarp();
-      stage_samples(pb ^ 1, en, rb ^ 1);
-    }
-    // ================= flux (core/limb_dark.py:19-196)
-    const double2 gg = rec2[WK_G0 / 2];
-    const double g2 = rec[WK_G2];
+      for (int h = 0; h < N; ++h) {
+        const double u1 = fma(ws2.x, xD[h], -ws2.y * yD[h]);
+        const double u2 = fma(ws2.y, xD[h], ws2.x * yD[h]);
+        const double v1 = kk.x * u1, v2 = kk.y * u2;
+        bq[h] = fsqrt(fma(v1, v1, v2 * v2));
+        intr[h] = (32u * h + lane < valid) && (zo.x * u2 > 0.0) && !(bq[h] >= zo.y);
+        // the flux code an item gets depends on the item alone: inside list AND b safely below 1 - r
+        fast[h] = inside_list && (bq[h] < b_lim) && r_ok;
+        n_ld += intr[h] ? 1u : 0u;
+        n_fast += (intr[h] && fast[h]) ? 1u : 0u;
+        want_gen = want_gen || (intr[h] && !fast[h]);
+        want_fast = want_fast || (intr[h] && fast[h]);
+        tot[h] = 0.0;
+      }
+      want_gen = __any_sync(0xffffffffu, want_gen);
+      want_fast = __any_sync(0xffffffffu, want_fast);
+      // ================= mid: the next chunk's segment window has landed -> its samples start to fly
+      if (j == 0) {
+        cp_async_wait_all();
+        __syncwarp();
+        stage_samples(pb ^ 1, en, rb ^ 1);
+      }
+      // ================= flux (core/limb_dark.py:19-196)
+      const double2 gg = rec2[WK_G0 / 2];
+      const double g2 = rec[WK_G2];
 #if defined(JXP_WALK_SKIP) && (JXP_WALK_SKIP & 2)
-    // measurement only: no flux code
+      // measurement only: no flux code
 #pragma unroll
-    for (int h = 0; h < N; ++h) tot[h] = intr[h] ? bq[h] * 1e-3 : 0.0;
+      for (int h = 0; h < N; ++h) tot[h] = intr[h] ? bq[h] * 1e-3 : 0.0;
 #else
-    if (want_fast) {
-      double f[N];
-      ld_inside_u<N>(bq, ar, lmax, gg.x, gg.y, g2, f);  // constant node cosines, no atan2, no guards
+      if (want_fast) {
+        double f[N];
+        ld_inside_u<N>(bq, ar, lmax, gg.x, gg.y, g2, f);  // constant node cosines, no atan2, no guards
 #pragma unroll
-      for (int h = 0; h < N; ++h)
-        if (intr[h] && fast[h]) tot[h] = f[h];
-    }
-    if (want_gen) {
-      // (the node guards of limb_dark.py:163-170 stay in: a guard-free variant with a rare-path fallback measured
-      // no faster -- the compares and selects run on otherwise idle pipes)
-      double rq[N], s0[N], s1v[N], s2[N];
+        for (int h = 0; h < N; ++h)
+          if (intr[h] && fast[h]) tot[h] = f[h];
+      }
+      if (want_gen) {
+        // (the node guards of limb_dark.py:163-170 stay in: a guard-free variant with a rare-path fallback measured
+        // no faster -- the compares and selects run on otherwise idle pipes)
+        double rq[N], s0[N], s1v[N], s2[N];
 #pragma unroll
-      for (int h = 0; h < N; ++h) rq[h] = rr;
-      ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
+        for (int h = 0; h < N; ++h) rq[h] = rr;
+        ld_solution_n<N, 1>(bq, rq, lmax, s0, s1v, s2);
 #pragma unroll
-      for (int h = 0; h < N; ++h)
-        if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
-    }
+        for (int h = 0; h < N; ++h)
+          if (intr[h] && !fast[h]) tot[h] = ld_combine(lmax, s0[h], s1v[h], s2[h], gg.x, gg.y, g2);
+      }
 #endif
+    }
     if (EXPO) {
 #pragma unroll
       for (int h = 0; h < N; ++h) wsum[h] = fma(a.st.w[j], tot[h], wsum[h]);
@@ -1024,6 +1152,7 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     // ================= advance; claims are looked up two ahead (the atomic's answer is read a claim later)
     rb ^= 1;
     pb ^= 1;
+    tcur = tnext;
     if (k == 0u && nxt_valid) {
       nn_valid = claim_decode(raw_nn, nn_slot0, nn_cnt);
       if (nn_valid) {
@@ -1059,9 +1188,11 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
   }
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
   n_fast = __reduce_add_sync(0xffffffffu, n_fast);
+  n_tab = __reduce_add_sync(0xffffffffu, n_tab);
   if (lane == 0) {
     atomicAdd(a.counters + 1, (unsigned long long)n_ld);
     atomicAdd(a.counters + 5, (unsigned long long)n_fast);
+    if (n_tab) atomicAdd(a.tstat, (unsigned long long)n_tab);
   }
 }
 
@@ -1565,6 +1696,8 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
   b.loglike = loglike;
   b.counters = a.counters;
   b.n_bodies = n_bodies;
+  b.tab = a.tab;
+  b.tstat = reinterpret_cast<unsigned long long*>(d_scalars + WALK_TSTAT0);
   b.st = stencil;
   if (!expo) {
     b.st.n = 1;
@@ -1628,6 +1761,10 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
     if (ev_stop && ev_which == 1 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
     int rc = check_launch("jxp_system_light_curve(walk plan)");
     if (rc != JXP_OK) return rc;
+    // (both evaluation kernels read the tables)
+    if (join_ev != nullptr && cudaStreamWaitEvent(st, join_ev, 0) != cudaSuccess)
+      return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk tables): join");
+    join_ev = nullptr;
     if (ev_start && ev_which == 0 && body == 0) cudaEventRecord(ev_start, st);
     if (loglike)
       k_walk_eval<N, false><<<grid, 128, 0, st>>>(b);
