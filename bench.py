@@ -823,11 +823,16 @@ def secondary_configs(dev, lib, ev0, ev1, rank, world, fp64_peak, max_over_ranks
                                    10, 0, 0, fs.data_ptr(), 0, 0, 0, 0, ws.data_ptr(), wsb, A.stream_ptr()))
     stats = (ctypes.c_int64 * 2)()
     _lib.call("jxp_system_stats", ws.data_ptr(), n_sets, 3, n_times, ctypes.addressof(stats), A.stream_ptr())
+    wk4 = (ctypes.c_int64 * 4)()
+    _lib.call("jxp_system_walk_stats", ws.data_ptr(), n_sets, 3, n_times, ctypes.addressof(wk4), A.stream_ptr())
     out["c4_3planets_15x_supersampled"] = {
         "points_per_s": 1024 * n_times / (ms * 1e-3), "ms": ms,
         "inner_evaluations_per_s": 1024 * n_times * 45 / (ms * 1e-3),
-        "rank0_executed": {"kepler_solves": int(stats[0]), "ld_evaluations": int(stats[1])},
-        "rank0_tflops_executed": (int(stats[0]) * (W_KEPLER + W_ORBIT) + int(stats[1]) * W_LD) / (ms * 1e-3) / 1e12,
+        "rank0_executed": {"sub_samples_visited": int(stats[0]), "flux_evaluations": int(stats[1]),
+                           "from_tables": int(wk4[0]), "set_body_units_with_tables": int(wk4[2])},
+        # the reference formula's flops for the visited sub-samples over the time; NOT a pipe utilisation (the
+        # per-set function tables answer an evaluation with ~50 FP64 instructions)
+        "rank0_reference_formula_tflops": (int(stats[0]) * (W_KEPLER + W_ORBIT) + int(stats[1]) * W_LD) / (ms * 1e-3) / 1e12,
         "rank0_in_transit_fraction": float((fs != 0).double().mean())}
     del fs, ws, bodies
     torch.cuda.empty_cache()

@@ -67,23 +67,28 @@ __device__ __forceinline__ double tb_pow2(int e) {  // 2^e, -1022 <= e <= 1023
   return __hiloint2double((1023 + e) << 20, 0);
 }
 
-// One warp per parameter set: the flux pieces of (r, u) and their header.
+// The flux pieces of (r, u) and their header: WPS warps per parameter set (1 when there are sets enough to fill the
+// machine, 4 -- one CTA per set -- when there are not: the work of a set is a ~30 us chain for one warp).
 constexpr int TB_WARPS = 4;
+template <int WPS>
 __global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_constant__ TabArgs a) {
-  __shared__ double s_f[TB_WARPS][TB_NPIECE][TB_NC];  // node values, then Chebyshev coefficients
-  __shared__ double s_c[TB_WARPS][TB_NPIECE][TB_NC];
-  __shared__ double s_q[TB_WARPS][TB_NPIECE][2];      // q-range of a piece: q = dx inside the disk,
-                                                       // sqrt(b^2 - xs) / sqrt(xe - b^2) for ingress / egress
+  constexpr int SPC = TB_WARPS / WPS;  // sets per CTA
+  __shared__ double s_f[SPC][TB_NPIECE][TB_NC];  // node values
+  __shared__ double s_c[SPC][TB_NPIECE][TB_NC];  // Chebyshev coefficients
+  __shared__ double s_q[SPC][TB_NPIECE][2];      // q-range of a piece: q = dx inside the disk,
+                                                  // sqrt(b^2 - xs) / sqrt(xe - b^2) for ingress / egress
   __shared__ double s_dct[TB_NC][TB_NC], s_c2m[TB_NC][TB_NC];
-  __shared__ unsigned char s_pl[TB_WARPS][TB_NPIECE];
+  __shared__ unsigned char s_pl[SPC][TB_NPIECE];
+  __shared__ int s_good[SPC];
   for (int i = threadIdx.x; i < TB_NC * TB_NC; i += blockDim.x) {
     s_dct[i / TB_NC][i % TB_NC] = d_tb_dctT18[i / TB_NC][i % TB_NC];
     s_c2m[i / TB_NC][i % TB_NC] = d_tb_c2mT[i / TB_NC][i % TB_NC];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int s = blockIdx.x * TB_WARPS + w;
-  if (s >= a.n_sets) return;
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) / WPS, sub = (threadIdx.x >> 5) % WPS;
+  const int sraw = blockIdx.x * SPC + w;
+  const bool live_set = sraw < a.n_sets;
+  const int s = live_set ? sraw : a.n_sets - 1;  // (a CTA's spare warps recompute the last set and write nothing)
+  if (threadIdx.x < SPC) s_good[threadIdx.x] = 1;
   const double* p = a.bodies + ((size_t)s * a.n_bodies + a.body) * JXP_BODY_NFIELDS;
   double* T = a.tab + (size_t)s * TB_DOUBLES;
   const double rstar = p[JXP_BODY_CENTRAL_RADIUS];
@@ -109,10 +114,11 @@ __global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_c
     bcut = 0.98 * b0 - 0.005;
     if (!(bcut > 0.0)) bcut = 0.0;  // (NaN: build everything)
   }
-  // lane = piece: its q-range and whether any sample can land on it
+  // lane = piece: its q-range and whether any sample can land on it (every warp of the set computes the same)
   bool active = false;
+  double qlo = 0.0, qhi = 0.0;
   if (lane < TB_P_BAD) {
-    double qlo, qhi, bhi2;
+    double bhi2;
     if (lane < TB_NB) {
       qlo = tb_pow2(-(lane + 1));
       qhi = lane == j0 ? xs : tb_pow2(-lane);
@@ -128,21 +134,27 @@ __global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_c
       qhi = We * (k == 0 ? TB_EGR1 : 1.0);
       bhi2 = fma(-qlo, qlo, xe);
     }
-    s_q[w][lane][0] = qlo;
-    s_q[w][lane][1] = qhi;
     active = ok && !(lane < TB_NB && lane < j0) && (bhi2 > bcut * bcut);
   }
   const unsigned amask = __ballot_sync(0xffffffffu, active);
   const int npl = __popc(amask);
-  if (active) s_pl[w][__popc(amask & ((1u << lane) - 1u))] = (unsigned char)lane;
-  __syncwarp();
-  // node values: the flattened (piece, node) list, two per lane and 64 at a time -- the inside-the-disk pieces
+  if (sub == 0) {
+    if (lane < TB_P_BAD) {
+      s_q[w][lane][0] = qlo;
+      s_q[w][lane][1] = qhi;
+    }
+    if (active) s_pl[w][__popc(amask & ((1u << lane) - 1u))] = (unsigned char)lane;
+  }
+  __syncthreads();
+  // node values: the flattened (piece, node) list, two per lane and 64 per round -- the inside-the-disk pieces
   // first (they come first in the list) with the constant-kappa code of the direct path, then the rest with the
-  // general code; a round never mixes the two
+  // general code; a round never mixes the two.  The set's warps take the rounds in turn.
   const int n_nodes = npl * TB_NC;
   const int n_in = __popc(amask & ((1u << TB_NB) - 1u)) * TB_NC;
-  for (int f0 = 0; f0 < n_nodes;) {
-    const bool inside = f0 < n_in;
+  const int r_in = (n_in + 63) / 64, r_all = r_in + (n_nodes - n_in + 63) / 64;
+  for (int r = sub; r < r_all; r += WPS) {
+    const bool inside = r < r_in;
+    const int f0 = inside ? 64 * r : n_in + 64 * (r - r_in);
     const int fend = inside ? n_in : n_nodes;
     double bb[2];
     int pi[2], ni[2];
@@ -154,8 +166,8 @@ __global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_c
       pi[h] = live[h] ? f / TB_NC : 0;
       ni[h] = live[h] ? f % TB_NC : 0;
       const int pid = s_pl[w][pi[h]];
-      const double qlo = s_q[w][pid][0], qhi = s_q[w][pid][1];
-      const double q = fma(0.5 * (qhi - qlo), d_tb_node18[ni[h]], 0.5 * (qhi + qlo));
+      const double lo = s_q[w][pid][0], hi = s_q[w][pid][1];
+      const double q = fma(0.5 * (hi - lo), d_tb_node18[ni[h]], 0.5 * (hi + lo));
       double b2 = pid < TB_NB ? xs - q : (pid < TB_P_EGR ? fma(q, q, xs) : fma(-q, q, xe));
       if (!(b2 > 0.0)) b2 = 0.0;
       bb[h] = fsqrt(b2);
@@ -172,47 +184,51 @@ __global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_c
 #pragma unroll
     for (int h = 0; h < 2; ++h)
       if (live[h]) s_f[w][pi[h]][ni[h]] = F[h];
-    f0 = f0 + 64 < fend ? f0 + 64 : fend;
   }
-  __syncwarp();
+  __syncthreads();
   // node values -> Chebyshev coefficients (entries <= 1 / 9: backward stable) ...
-  for (int f = lane; f < n_nodes; f += 32) {
+  for (int f = sub * 32 + lane; f < n_nodes; f += 32 * WPS) {
     const int pi = f / TB_NC, k = f % TB_NC;
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < TB_NC; ++i) acc = fma(s_dct[i][k], s_f[w][pi][i], acc);
     s_c[w][pi][k] = acc;
   }
-  __syncwarp();
+  __syncthreads();
   // ... -> monomial coefficients (integer matrix; T_k has the parity of k), highest degree first.  A fit whose
   // last two Chebyshev coefficients are not down at the rounding noise of the node values is marked invalid.
   const double tol = 4e-16 + 2e-14 * rr * rr;
   bool all_good = true;
-  for (int f = lane; f < n_nodes; f += 32) {
+  for (int f = sub * 32 + lane; f < n_nodes; f += 32 * WPS) {
     const int pi = f / TB_NC, j = f % TB_NC;
     const int pid = s_pl[w][pi];
     double acc = 0.0;
     for (int k = TB_NC - 1 - ((TB_NC - 1 - j) & 1); k >= j; k -= 2) acc = fma(s_c2m[k][j], s_c[w][pi][k], acc);
     double* P = T + TB_PIECE0 + pid * TB_PSTRIDE;
-    P[2 + j] = acc;
+    if (live_set) P[2 + j] = acc;
     if (j == 0) {
-      const double qlo = s_q[w][pid][0], qhi = s_q[w][pid][1];
+      const double lo = s_q[w][pid][0], hi = s_q[w][pid][1];
       const double tail = fmax(fabs(s_c[w][pi][TB_NC - 1]), fabs(s_c[w][pi][TB_NC - 2]));
       const bool good = tail <= tol;  // (NaN: not good)
       all_good = all_good && good;
-      const double inv = fdiv(1.0, qhi - qlo);
-      P[0] = good ? 2.0 * inv : nan("");
-      P[1] = -(qhi + qlo) * inv;
+      const double inv = fdiv(1.0, hi - lo);
+      if (live_set) {
+        P[0] = good ? 2.0 * inv : nan("");
+        P[1] = -(hi + lo) * inv;
+      }
     }
   }
-  // pieces that were not built: NaN scale, zero coefficients
+  // a set with a piece that did not converge is not evaluated from tables at all (large r / r close to the end of
+  // the validated range: the direct code is the safe and, with many samples on that piece, the faster choice)
+  if (!__all_sync(0xffffffffu, all_good) && lane == 0) atomicAnd(&s_good[w], 0);
+  __syncthreads();
+  all_good = s_good[w] != 0;
+  if (!live_set || sub != 0) return;
+  // pieces that were not built: NaN scale, zero coefficients (the all-zero piece: F = 0)
   for (int f = lane; f < TB_NPIECE * TB_PSTRIDE; f += 32) {
     const int pid = f / TB_PSTRIDE, k = f % TB_PSTRIDE;
     if (!((amask >> pid) & 1u)) T[TB_PIECE0 + f] = (k == 0 && pid != TB_P_ZERO) ? nan("") : 0.0;
   }
-  // a set with a piece that did not converge is not evaluated from tables at all (large r / r close to the
-  // validated range: the direct code is the safe and, with many samples on that piece, the faster choice)
-  all_good = __all_sync(0xffffffffu, all_good);
   if (!all_good)
     for (int pid = lane; pid < TB_P_BAD; pid += 32) T[TB_PIECE0 + pid * TB_PSTRIDE] = nan("");
   if (lane == 0) {

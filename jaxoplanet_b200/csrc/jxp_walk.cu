@@ -1262,7 +1262,10 @@ __device__ __forceinline__ void walk_finish_items(const WalkItemArgs& a, unsigne
   a.loglike[set] = -0.5 * (a.scalars[WALK_STATE0 + 10] + tot) + a.scalars[WALK_STATE0 + 11];
 }
 
-constexpr unsigned WI_CLAIM = 8;  // items per claim
+#ifndef JXP_ITEMS_CLAIM
+#define JXP_ITEMS_CLAIM 8
+#endif
+constexpr unsigned WI_CLAIM = JXP_ITEMS_CLAIM;  // items per claim
 struct WalkItemSmem {
   double tabs[TB_DOUBLES];
   double rec[WALK_REC];
@@ -1297,13 +1300,23 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
   double xs = 0.0, xe = 0.0, mc = 0.0, zsc = 0.0, zoff = 0.0, t0 = 0.0, tref = 0.0, per = 0.0, iper = 0.0;
   double ti1 = 0.0, ti2 = 0.0, ti3 = 0.0, te1 = 0.0;
   int j0 = 0, db = 0;
+  // claims: up to WI_CLAIM consecutive items, fewer as the items run out (guided self-scheduling: the warps finish
+  // within an item or two of each other); the answer of the atomic is read a claim later
+  const unsigned nw2 = gridDim.x * 4u * 2u;
+  auto claim = [&](unsigned seen) -> unsigned long long {  // lane 0: first item | items << 32
+    const unsigned left = seen < n_items ? n_items - seen : 0u;
+    const unsigned want = left / nw2;
+    const unsigned R = want < 1u ? 1u : (want > WI_CLAIM ? WI_CLAIM : want);
+    return atomicAdd(a.state_rw + 13, (unsigned long long)R) | ((unsigned long long)R << 32);
+  };
   unsigned long long nxt = 0ull;
-  if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)WI_CLAIM);
+  if (lane == 0) nxt = claim(0u);
   for (;;) {
-    const unsigned base = (unsigned)__shfl_sync(0xffffffffu, nxt, 0);
+    const unsigned long long cl = __shfl_sync(0xffffffffu, nxt, 0);
+    const unsigned base = (unsigned)cl, R = (unsigned)(cl >> 32);
     if (base >= n_items) break;
-    if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)WI_CLAIM);  // read a claim later
-    const unsigned n_cl = n_items - base < WI_CLAIM ? n_items - base : WI_CLAIM;
+    if (lane == 0) nxt = claim(base + R);
+    const unsigned n_cl = n_items - base < R ? n_items - base : R;
     uint4 its = make_uint4(0u, 0u, 0u, 0u);
     if ((unsigned)lane < n_cl) its = __ldg(a.items + base + lane);
     for (unsigned ii = 0; ii < n_cl; ++ii) {
@@ -1585,6 +1598,14 @@ __global__ void __launch_bounds__(256) k_walk_fix(const __grid_constant__ WalkIt
 namespace jxph {
 
 
+// one warp per set when the sets fill the machine, else one CTA per set (k_walk_tables)
+static void launch_tables(const jxp::TabArgs& ta, int n_sets, cudaStream_t st) {
+  if (n_sets >= 8 * sm_count())
+    jxp::k_walk_tables<1><<<(n_sets + 3) / 4, 128, 0, st>>>(ta);
+  else
+    jxp::k_walk_tables<4><<<n_sets, 128, 0, st>>>(ta);
+}
+
 // A side stream per (host thread, device) for work that may run beside the caller's stream (fork / join by events).
 struct SideStream {
   cudaStream_t stream = nullptr;
@@ -1742,10 +1763,10 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
       SideStream* ss = ev_which == 2 ? nullptr : side_stream();
       if (ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess &&
           cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
-        k_walk_tables<<<(n_sets + 3) / 4, 128, 0, ss->stream>>>(ta);
+        launch_tables(ta, n_sets, ss->stream);
         forked = true;
       } else {
-        k_walk_tables<<<(n_sets + 3) / 4, 128, 0, st>>>(ta);
+        launch_tables(ta, n_sets, st);
       }
       int rct = check_launch("jxp_system_light_curve(walk tables)");
       if (rct == JXP_OK && forked && cudaEventRecord(ss->join, ss->stream) != cudaSuccess)

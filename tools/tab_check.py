@@ -92,6 +92,8 @@ def run(p, u, t, noise, sigma, label, n_oracle=4, timing=True):
 for n_sets in [int(x) for x in os.environ.get("NS", "256,4096").split(",")]:
     p, u, t, noise, sigma = W.c3(n_sets, n_t)
     run(p, u, t, noise, sigma, "c3")
+if os.environ.get('NOADV'):
+    sys.exit(0)
 # adversarial orbits (tests/test_gpu_parity.py::test_window_is_conservative_on_adversarial_orbits)
 rng = np.random.default_rng(77)
 n_sets = 300
