@@ -179,8 +179,10 @@ __device__ __forceinline__ void kepler_xy_u(const double (&Mr)[N], double e, dou
 // --------------------------------------------------------------------------------------------
 // plan
 // --------------------------------------------------------------------------------------------
-template <int CH, bool LL>
-__global__ void __launch_bounds__(256, 4) k_walk_plan(const __grid_constant__ WalkArgs a) {
+// MINB: CTAs per SM the register budget is cut for -- 4 (64 registers, some spilled) when it takes that many to have
+// every set's warp resident at once, 2 (128 registers) for smaller batches: the launch is a latency chain per set
+template <int CH, bool LL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_walk_plan(const __grid_constant__ WalkArgs a) {
   if ((int)blockIdx.x >= a.n_plan_ctas) {
     const int cta = (int)blockIdx.x - a.n_plan_ctas;
     if (LL) {
@@ -1748,12 +1750,10 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
     b.body = body;
     cudaEvent_t join_ev = nullptr;
     // (slots 10, 11 hold the likelihood terms the plan launch writes; 12, 13: item allocation / claims; 14, 15: k_walk_fix)
-    cudaError_t e = cudaMemsetAsync(a.state, 0, 16 * sizeof(unsigned long long), st);
+    // (the table statistics sit right behind the state block: one fill for both at the first body)
+    static_assert(WALK_TSTAT0 == WALK_STATE0 + 16, "state block and table statistics are contiguous");
+    cudaError_t e = cudaMemsetAsync(a.state, 0, (body == 0 ? 20 : 16) * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
-    if (body == 0) {
-      e = cudaMemsetAsync(d_scalars + WALK_TSTAT0, 0, 4 * sizeof(unsigned long long), st);
-      if (e != cudaSuccess) return fail(JXP_ERR_CUDA, "jxp_system_light_curve(walk): memset: %s", cudaGetErrorString(e));
-    }
     if (ev_start && (ev_which == 1 || ev_which == 2) && body == 0) cudaEventRecord(ev_start, st);
     bool forked = false;
     if (use_tables) {
@@ -1775,10 +1775,25 @@ int launch_walk_f64(const double* bodies, int n_sets, int n_bodies, const double
       if (forked) join_ev = ss->join;
     }
     if (ev_stop && ev_which == 2 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
-    if (loglike)
-      k_walk_plan<CH, true><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
-    else
-      k_walk_plan<CH, false><<<a.n_plan_ctas + LL_NCTA_H, 256, 0, st>>>(a);
+    {
+      const int n_cta = a.n_plan_ctas + LL_NCTA_H;
+      const int minb = n_cta <= 2 * sm_count() ? 2 : (n_cta <= 3 * sm_count() ? 3 : 4);
+      if (loglike) {
+        if (minb == 2)
+          k_walk_plan<CH, true, 2><<<n_cta, 256, 0, st>>>(a);
+        else if (minb == 3)
+          k_walk_plan<CH, true, 3><<<n_cta, 256, 0, st>>>(a);
+        else
+          k_walk_plan<CH, true, 4><<<n_cta, 256, 0, st>>>(a);
+      } else {
+        if (minb == 2)
+          k_walk_plan<CH, false, 2><<<n_cta, 256, 0, st>>>(a);
+        else if (minb == 3)
+          k_walk_plan<CH, false, 3><<<n_cta, 256, 0, st>>>(a);
+        else
+          k_walk_plan<CH, false, 4><<<n_cta, 256, 0, st>>>(a);
+      }
+    }
     if (ev_stop && ev_which == 1 && body == n_bodies - 1) cudaEventRecord(ev_stop, st);
     int rc = check_launch("jxp_system_light_curve(walk plan)");
     if (rc != JXP_OK) return rc;
