@@ -216,12 +216,18 @@ __global__ void __launch_bounds__(256, MINB) k_walk_plan(const __grid_constant__
   }
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // the records of the CTA's sets: one lane per set of the first warp (the derivation is a ~1500-instruction
+  // serial chain; as lane 0 of every set's own warp it occupied eight warps' issue slots for one lane's work each)
+  if (threadIdx.x < (blockDim.x >> 5)) {
+    const int s2 = blockIdx.x * (blockDim.x >> 5) + (int)threadIdx.x;
+    if (s2 < a.n_sets)
+      sys_prep_body<double>(s2 * a.n_bodies + a.body, a.bodies, a.n_sets, a.n_bodies, a.u, a.n_u, a.u_stride, a.out_b,
+                            a.out_s, a.counters, a.tile_ctr, a.widen, a.margin);
+    __threadfence_block();
+  }
+  __syncthreads();
   if (s >= a.n_sets) return;
   const int unit = s * a.n_bodies + a.body;  // (set, body) record
-  if (lane == 0)
-    sys_prep_body<double>(unit, a.bodies, a.n_sets, a.n_bodies, a.u, a.n_u, a.u_stride, a.out_b, a.out_s,
-                          a.counters, a.tile_ctr, a.widen, a.margin);
-  __syncwarp();
   const BodyC<double>& c = a.out_b[unit];
   if (lane == 0) {
     const SetC<double>& sc = a.out_s[s];
