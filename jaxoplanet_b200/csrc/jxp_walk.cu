@@ -110,7 +110,8 @@ struct WalkArgs {
 };
 
 constexpr unsigned long long WK_OVERFLOW = 2ull, WK_UNSUPPORTED = 4ull;
-constexpr unsigned WK_ITEM = 128;  // samples per item slot aimed at (k_walk_items walks 64 per round)
+constexpr unsigned WK_ITEM = 128;  // samples per item slot aimed at
+constexpr unsigned WK_GROUP = 8;   // items per group: the unit k_walk_items claims and walks as one sample stream
 
 // Kepler solve for N mean anomalies of ONE orbit (e, 1 - e, 1 + e, sqrt(1 - e^2), 1 / (1 + e) warp-uniform):
 // core/kepler.py:28-56, 82-108 with the re-arrangements of kepler_reduced_n<N, XY, ONE_DIV> (jxp_math.cuh):
@@ -422,17 +423,20 @@ __global__ void __launch_bounds__(256, MINB) k_walk_plan(const __grid_constant__
     const double wsamp = (whi - wlo) * P * inv_dt;
     const unsigned m = 1u + (unsigned)(fmin(wsamp, 1e6) / (double)WK_ITEM);
     const unsigned long long n_it = (unsigned long long)n_tr * m;
+    // (items are handed out in GROUPS of WK_GROUP; a set's slice starts on a group boundary and is padded with empty
+    // items, so a group belongs to one set and holds the same items whatever else is in the call)
+    const unsigned long long n_pad = (n_it + WK_GROUP - 1ull) / WK_GROUP * WK_GROUP;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(a.state + 12, n_it);
+    if (lane == 0) base = atomicAdd(a.state + 12, n_pad);
     base = __shfl_sync(0xffffffffu, base, 0);
     WalkSet wi;
     wi.seg_off = 0u;
     wi.n_tr = (unsigned)n_tr;
-    wi.cntA = (unsigned)n_it;  // items of the set ...
-    wi.chA = (unsigned)base;   // ... from this one on
-    wi.cntB = 1u;              // (marks an item set)
+    wi.cntA = (unsigned)(2ull * (n_pad / WK_GROUP));  // half-groups of the set (one partial sum each) ...
+    wi.chA = (unsigned)(2ull * (base / WK_GROUP));    // ... from this one on
+    wi.cntB = 1u;                            // (marks an item set)
     wi.chB = wi.n_chunks = wi.done = 0u;
-    if (base + n_it > a.cap_items || n_it > 0xfffffff0ull) {
+    if (base + n_pad > a.cap_items || n_pad > 0xfffffff0ull) {
       if (lane == 0) {
         atomicOr(a.state + 3, WK_OVERFLOW);
         wi.cntA = 0u;
@@ -440,6 +444,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_plan(const __grid_constant__
       }
       return;
     }
+    for (unsigned long long k = n_it + lane; k < n_pad; k += 32) a.items[base + k] = make_uint4((unsigned)s, 0u, 0u, 0u);
     unsigned long long npos = 0;
     for (long long k0 = 0; k0 < n_tr; k0 += 32) {
       unsigned lo, hi, il, ih;
@@ -1249,7 +1254,7 @@ __device__ __forceinline__ bool walk_items_active(const WalkItemArgs& a, int lan
   return !unsorted && !over;
 }
 
-// The partial sums of an item set added in item order by ONE lane -> loglike[set] (eight interleaved sums,
+// The partial sums of an item set added in group order by ONE lane -> loglike[set] (eight interleaved sums,
 // combined pairwise: the order depends on the set alone).
 __device__ __forceinline__ void walk_finish_items(const WalkItemArgs& a, unsigned set) {
   __threadfence();
@@ -1308,29 +1313,37 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
   double xs = 0.0, xe = 0.0, mc = 0.0, zsc = 0.0, zoff = 0.0, t0 = 0.0, tref = 0.0, per = 0.0, iper = 0.0;
   double ti1 = 0.0, ti2 = 0.0, ti3 = 0.0, te1 = 0.0;
   int j0 = 0, db = 0;
-  // claims: up to WI_CLAIM consecutive items, fewer as the items run out (guided self-scheduling: the warps finish
-  // within an item or two of each other); the answer of the atomic is read a claim later
-  const unsigned nw2 = gridDim.x * 4u * 2u;
-  auto claim = [&](unsigned seen) -> unsigned long long {  // lane 0: first item | items << 32
-    const unsigned left = seen < n_items ? n_items - seen : 0u;
-    const unsigned want = left / nw2;
-    const unsigned R = want < 1u ? 1u : (want > WI_CLAIM ? WI_CLAIM : want);
-    return atomicAdd(a.state_rw + 13, (unsigned long long)R) | ((unsigned long long)R << 32);
-  };
+  // claims: a GROUP of WK_GROUP consecutive items of one set (~500 samples), or -- when there are fewer groups than
+  // two per warp -- half of one: a group's rounds are split in two halves with a partial sum each, whoever walks
+  // them, so the claim size changes nothing in the result.  The answer of the atomic is read a claim later.
+  const unsigned n_groups = n_items / WK_GROUP;
+  const unsigned n_half = 2u * n_groups;
+  const unsigned R = n_groups >= 2u * gridDim.x * 4u ? 2u : 1u;  // halves per claim
   unsigned long long nxt = 0ull;
-  if (lane == 0) nxt = claim(0u);
+  if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)R);
   for (;;) {
-    const unsigned long long cl = __shfl_sync(0xffffffffu, nxt, 0);
-    const unsigned base = (unsigned)cl, R = (unsigned)(cl >> 32);
-    if (base >= n_items) break;
-    if (lane == 0) nxt = claim(base + R);
-    const unsigned n_cl = n_items - base < R ? n_items - base : R;
+    const unsigned hg0 = (unsigned)__shfl_sync(0xffffffffu, nxt, 0);
+    if (hg0 >= n_half) break;
+    if (lane == 0) nxt = atomicAdd(a.state_rw + 13, (unsigned long long)R);
+    const unsigned grp = hg0 >> 1;
     uint4 its = make_uint4(0u, 0u, 0u, 0u);
-    if ((unsigned)lane < n_cl) its = __ldg(a.items + base + lane);
-    for (unsigned ii = 0; ii < n_cl; ++ii) {
-      const unsigned set = __shfl_sync(0xffffffffu, its.x, ii);
-      const unsigned lo = __shfl_sync(0xffffffffu, its.y, ii);
-      const unsigned cnt = __shfl_sync(0xffffffffu, its.z, ii);
+    if ((unsigned)lane < WK_GROUP) its = __ldg(a.items + (size_t)grp * WK_GROUP + lane);
+    const unsigned set = __shfl_sync(0xffffffffu, its.x, 0);
+    // the group's items as ONE sample stream: position p of the stream belongs to the item k with P_k <= p < P_k+1
+    // (P = exclusive prefix sums of the items' lengths, lanes 0..7), so every round is full but the last
+    unsigned pin = its.z;
+#pragma unroll
+    for (int o = 1; o < (int)WK_GROUP; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, pin, o);
+      if (lane >= o) pin += v;
+    }
+    const unsigned pex = pin - its.z;
+    const unsigned total = __shfl_sync(0xffffffffu, pin, WK_GROUP - 1);
+    unsigned Pj[WK_GROUP];
+#pragma unroll
+    for (int j = 1; j < (int)WK_GROUP; ++j) Pj[j] = __shfl_sync(0xffffffffu, pex, j);
+    const unsigned lo_first = __shfl_sync(0xffffffffu, its.y, 0);
+    {
       if (set != cur_set) {
         __syncwarp();
         const double2* T = reinterpret_cast<const double2*>(a.tab + (size_t)set * TB_DOUBLES);
@@ -1349,7 +1362,7 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
         t0 = rec[WK_T0]; tref = rec[WK_TREF]; per = rec[WK_PERIOD]; iper = rec[WK_INVP];
       }
       double csum = 0.0;
-      // one round: NN samples per lane from sample r0 of the item on
+      // one round: NN samples per lane from position r0 of the group's stream on
       auto round = [&](auto nn_tag, unsigned r0) {
         constexpr int NN = decltype(nn_tag)::value;
         bool have[NN];
@@ -1358,8 +1371,13 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
         double2 awv[NN];
 #pragma unroll
         for (int h = 0; h < NN; ++h) {
-          have[h] = r0 + 32u * h + lane < cnt;
-          ix[h] = have[h] ? lo + r0 + 32u * h + lane : lo;
+          const unsigned p = r0 + 32u * h + lane;
+          have[h] = p < total;
+          unsigned k = 0;
+#pragma unroll
+          for (int j = 1; j < (int)WK_GROUP; ++j) k += p >= Pj[j] ? 1u : 0u;
+          const unsigned lo_k = __shfl_sync(0xffffffffu, its.y, k), p_k = __shfl_sync(0xffffffffu, pex, k);
+          ix[h] = have[h] ? lo_k + (p - p_k) : lo_first;  // (padding lanes read a valid sample and contribute zero)
           ts[h] = __ldg(a.t + ix[h]);
           if (!FLUX) awv[h] = __ldg(a.aw + ix[h]);
         }
@@ -1485,37 +1503,33 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
           for (int h = 0; h < NN; ++h) csum = fma(acc[h], fma(acc[h], awv[h].y, -awv[h].x), csum);
         }
       };
-      unsigned r0 = 0;
-      for (; r0 + 96u < cnt; r0 += 64u) round(std::integral_constant<int, 2>{}, r0);
-      if (cnt - r0 > 64u)
-        round(std::integral_constant<int, 3>{}, r0);
-      else if (cnt - r0 > 32u)
-        round(std::integral_constant<int, 2>{}, r0);
-      else if (cnt > r0)
-        round(std::integral_constant<int, 1>{}, r0);
-      if (!FLUX) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-        if (lane == 0) a.part[base + ii] = csum;
-      }
-    }
-    if (!FLUX) {
-      // completion: one fence for the claim's partial sums, then the items are counted into their sets; the lane
-      // that completes a set adds the set's partials in item order
-      __syncwarp();
-      __threadfence();
-      unsigned run = 0;
-      for (unsigned ii = 0; ii < n_cl; ++ii) {
-        const unsigned set = __shfl_sync(0xffffffffu, its.x, ii);
-        const unsigned nset = __shfl_sync(0xffffffffu, its.x, ii + 1u < n_cl ? ii + 1u : ii);
-        ++run;
-        if (ii + 1u == n_cl || nset != set) {
-          if (lane == 0) {
-            const unsigned prev = atomicAdd(&a.wset_rw[set].done, run);
-            if (prev + run == a.wset[set].cntA) walk_finish_items(a, set);
-          }
-          run = 0;
+      const unsigned nfull = total / 96u, rem = total - 96u * nfull;
+      const unsigned nrounds = nfull + (rem ? 1u : 0u), nsplit = (nrounds + 1u) / 2u;
+      for (unsigned half = hg0 & 1u; half < (hg0 & 1u) + R; ++half) {
+        csum = 0.0;
+        const unsigned rend = half ? nrounds : nsplit;
+        for (unsigned r = half ? nsplit : 0u; r < rend; ++r) {
+          if (r < nfull)
+            round(std::integral_constant<int, 3>{}, 96u * r);
+          else if (rem > 64u)
+            round(std::integral_constant<int, 3>{}, 96u * r);
+          else if (rem > 32u)
+            round(std::integral_constant<int, 2>{}, 96u * r);
+          else
+            round(std::integral_constant<int, 1>{}, 96u * r);
         }
+        if (!FLUX) {
+          // the half-group's partial sum (fixed shuffle tree); the claim is counted into its set below, and the lane
+          // that completes a set adds the set's partial sums in order
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+          if (lane == 0) a.part[2u * grp + half] = csum;
+        }
+      }
+      if (!FLUX && lane == 0) {  // one fence and one count for the claim's partial sums
+        __threadfence();
+        const unsigned prev = atomicAdd(&a.wset_rw[set].done, R);
+        if (prev + R == a.wset[set].cntA) walk_finish_items(a, set);
       }
     }
   }
