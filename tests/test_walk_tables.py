@@ -223,3 +223,26 @@ def test_radius_ratios_near_the_end_of_the_table_range_and_two_bodies():
         f_d, _, _ = _call(None, ub, t, per_body=per_body, system=sys2, opts=_lib.JXP_DEV_NO_TABLES)
         assert wk["tab_evals"] > 0
         assert np.array_equal(f != 0, f_d != 0) and np.max(np.abs(f - f_d)) <= 3e-15
+
+
+@pytest.mark.parametrize("n_u", [0, 1])
+def test_tables_with_uniform_and_linear_limb_darkening(n_u):
+    """The tables tabulate F(b) whatever the law: uniform disk (u = []) and linear limb darkening against the direct
+    walk and the oracle."""
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+
+    p, ub, t, noise, sigma = W.c3(64, 30_000)
+    u = np.zeros((64, 0)) if n_u == 0 else ub[:, :1].copy()
+    y = 1 + noise
+    f, ls, wk = _call(p, u, t)
+    f_d, _, _ = _call(p, u, t, opts=_lib.JXP_DEV_NO_TABLES)
+    assert ls["flags"] == 0 and wk["tab_sets"] >= 60 and wk["tab_evals"] > 0.9 * ls["items"]
+    assert np.array_equal(f != 0, f_d != 0) and np.max(np.abs(f - f_d)) <= 2e-15
+    for s in (0, 17, 63):
+        bd = ref.orbital_body(**{k: v[s] for k, v in p.items()})
+        want = ref.system_light_curve([bd], u[s], t)[:, 0]
+        assert np.max(np.abs(f[s] - want)) <= 1e-14
+    ll, _, _ = _call(p, u, t, y, sigma)
+    ll_d, _, _ = _call(p, u, t, y, sigma, opts=_lib.JXP_DEV_NO_TABLES)
+    assert np.max(np.abs(ll - ll_d) / _ll_scale(ll_d, t.size, sigma)) <= 1e-12
