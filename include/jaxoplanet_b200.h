@@ -247,6 +247,21 @@ int jxp_transit_partials_f32(const double* theta, int32_t n_sets, const double* 
                              float* loglike, float* dloglike, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* K5 for general polynomial limb darkening (any n_u <= JXP_MAX_LD_COEFFS coefficients): what jax.jvp / jax.grad of
+ *   limb_dark_light_curve(System(...).add_body(...), u)(t)[..., 0]   (light_curves/limb_dark.py:15-62)
+ * evaluate for a law of any length -- the reference differentiates core.limb_dark.light_curve for any u
+ * (core/limb_dark.py:19-47, greens_basis_transform :87-99, p_integral's l >= 3 terms :149-153, 175-182).
+ * theta:    [n_sets][6 + n_u] (period, time_transit, eccentricity, omega_peri, impact_param, radius, u_1 .. u_n)
+ * partials: [n_sets][6 + n_u][n_times]; dloglike: [n_sets][6 + n_u].  Double precision, order 10, no exposure
+ * integration; a plain one-sample-per-thread kernel (the quadratic entry points above are the tuned path). */
+size_t jxp_transit_poly_workspace_bytes(int32_t n_sets, int64_t n_times);
+int jxp_transit_partials_poly_f64(const double* theta, int32_t n_sets, int32_t n_u, const double* star,
+                                  int64_t star_set_stride, const double* t, int64_t n_times,
+                                  int32_t gl_order, int32_t flags, double* flux, double* partials,
+                                  const double* y, const double* sigma, int64_t sigma_stride,
+                                  double* loglike, double* dloglike, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K8  Positions and velocities of Keplerian bodies.
  *   reference: OrbitalBody.position / central_position / relative_position / velocity /

@@ -90,6 +90,11 @@ SIGNATURES = {
         [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,
          _p, _sz, _p],
     ),
+    "jxp_transit_poly_workspace_bytes": (_sz, [_i32, _i64]),
+    "jxp_transit_partials_poly_f64": (
+        C.c_int,
+        [_p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p],
+    ),
     "jxp_transit_partials_f32": (
         C.c_int,
         [_p, _i32, _p, _i64, _p, _i64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p,

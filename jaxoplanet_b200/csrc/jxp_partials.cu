@@ -87,16 +87,24 @@ __device__ __forceinline__ Dual<T, N> cast_dual(const Dual<double, N>& x) {
 }  // namespace
 
 // one thread per set: theta -> derived constants with their derivatives
+// (general polynomial limb darkening, jxp_transit_partials_poly_f64: theta rows are 6 + n_u long and the normalised
+// Green's coefficients with their derivatives w.r.t. u go to `poly`)
+struct PolyD {
+  double g[JXP_MAX_LD_COEFFS + 1];                       // g_n / norm, limb_dark.py:42-45, 87-99
+  double dg[JXP_MAX_LD_COEFFS + 1][JXP_MAX_LD_COEFFS];   // d g_n / d u_j
+};
+
 template <typename T>
 __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
                           const double* __restrict__ star, int64_t star_stride,
                           BodyD<T>* __restrict__ out, double widen, double margin,
-                          unsigned long long* __restrict__ tl_state) {
+                          unsigned long long* __restrict__ tl_state, int theta_stride = JXP_NTHETA,
+                          int n_u = 2, PolyD* __restrict__ poly = nullptr) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sets) return;
-  if (s == 0) tl_state[0] = tl_state[1] = tl_state[2] = tl_state[3] = 0ull;  // transit list of this call
+  if (s == 0 && tl_state) tl_state[0] = tl_state[1] = tl_state[2] = tl_state[3] = 0ull;  // transit list of this call
   typedef Dual<double, NO> D;
-  const double* th = theta + (size_t)s * JXP_NTHETA;
+  const double* th = theta + (size_t)s * theta_stride;
   const double mstar = star[(size_t)s * star_stride + 0];
   const double rstar = star[(size_t)s * star_stride + 1];
   const D P = D::seed(th[0], 0);
@@ -163,7 +171,25 @@ __global__ void k_tr_prep(const double* __restrict__ theta, int n_sets,
   o.na_ome2 = cast_dual<T, NO>(na);
   o.inv_ome2 = T(1.0 / ome2.v);
   o.inv_ome2_32 = T(1.0 / (ome2.v * sqrt(ome2.v)));
-  {
+  if (poly != nullptr) {
+    typedef Dual<double, JXP_MAX_LD_COEFFS> U;
+    U uu[JXP_MAX_LD_COEFFS], gg[JXP_MAX_LD_COEFFS + 1];
+    for (int k = 0; k < JXP_MAX_LD_COEFFS; ++k) uu[k] = k < n_u ? U::seed(th[6 + k], k) : U(0.0);
+    for (int k = 0; k <= JXP_MAX_LD_COEFFS; ++k) gg[k] = U(0.0);
+    ld_greens_n<U>(n_u, uu, gg);
+    PolyD pd;
+    for (int k = 0; k <= JXP_MAX_LD_COEFFS; ++k) {
+      pd.g[k] = gg[k].v;
+      for (int j = 0; j < JXP_MAX_LD_COEFFS; ++j) pd.dg[k][j] = gg[k].d[j];
+    }
+    poly[s] = pd;
+    o.sc.g0 = T(gg[0].v);
+    o.sc.g1 = T(gg[1].v);
+    o.sc.g2 = T(gg[2].v);
+    for (int k = 0; k < 6; ++k) o.sc.ghi[k] = T(gg[3 + k].v);
+    o.sc.lmax = n_u;
+    for (int j = 0; j < 2; ++j) o.dg[0][j] = o.dg[1][j] = o.dg[2][j] = T(0);
+  } else {
     typedef Dual<double, 2> U;
     U g0, g1, g2;
     ld_greens<U>(2, U::seed(th[6], 0), U::seed(th[7], 1), g0, g1, g2);
@@ -898,6 +924,262 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
     k_tr_final<T><<<(n + 31) / 32, 256, 0, st>>>(d_partial, (int)(n_tiles * (threads / 32)), n_sets, d_scalars, loglike,
                                                   dloglike, a.tl_state, a.tl_cap);
     rc = check_launch("jxp_transit_partials(final)");
+  }
+  return rc;
+}
+
+
+// --------------------------------------------------------------------------------------
+// General polynomial limb darkening (any number of coefficients up to JXP_MAX_LD_COEFFS): flux and partials
+// w.r.t. theta = (period, time_transit, eccentricity, omega_peri, impact_param, radius, u_1 .. u_n).
+// The reference differentiates light_curve(u, b, r) for any u (core/limb_dark.py:19-47, 87-99, 140-182); here the
+// orbit tangents are those of eval_sample_partials, d flux / d(b, r) comes from dual numbers over the full solution
+// vector (the HI flux code: l = 3 .. n_u terms of p_integral), d flux / d u_j = s . d(g / norm) / d u_j.
+// A plain kernel (one sample per thread, window test per sample, rows stored coalesced): the fused quadratic path
+// above stays the tuned one.
+// --------------------------------------------------------------------------------------
+namespace {
+constexpr int POLY_NP_MAX = 6 + JXP_MAX_LD_COEFFS;
+constexpr int POLY_TILE = 256;
+
+template <int ORDER>
+__device__ __forceinline__ bool eval_sample_partials_poly(const BodyD<double>& bd, const PolyD& pd, int n_u,
+                                                          const GLTable* __restrict__ tab, double tm, double& flux,
+                                                          double* __restrict__ part) {
+  const BodyC<double>& c = bd.c;
+  typedef Dual<double, NO> D;
+  const double x = (tm - c.t0) - c.tref;
+  const double M = (Num<double>::two_pi * x) / c.period;
+  const double k = Num<double>::two_pi / c.period;
+  double Md[NO];
+#pragma unroll
+  for (int i = 0; i < NO; ++i) Md[i] = -k * bd.tref.d[i];
+  Md[0] += -M / c.period;
+  Md[1] += -k;
+  const double Mr = mod_two_pi(M);
+  double sf, cf, Edummy;
+  kepler_reduced<double, false>(Mr, c.e, c.ome, c.ope, c.s1me2, c.inv_ope, sf, cf, Edummy);
+  // kepler.py:64-79
+  const double ecosf = c.e * cf;
+  const double opc = 1.0 + ecosf;
+  const double dfdM = opc * opc * bd.inv_ome2_32;
+  const double dfde = (2.0 + ecosf) * sf * bd.inv_ome2;
+  D sfd, cfd;
+  sfd.v = sf;
+  cfd.v = cf;
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    double fdot = Md[i] * dfdM;
+    if (i == 2) fdot += dfde;
+    sfd.d[i] = cf * fdot;
+    cfd.d[i] = -sf * fdot;
+  }
+  const D ed = D::seed(c.e, 2);
+  D b, Z;
+  sky_position_g<D, double>(ed, bd.cw, bd.sw, bd.ci, bd.si, bd.na_ome2, c.inv_rstar, sfd, cfd, b, Z);
+  if (!(Z.v > 0.0) || (b.v >= c.onepr)) return false;
+  typedef Dual<double, 2> L;
+  L sv[JXP_MAX_LD_COEFFS + 1];
+  for (int n = 0; n <= JXP_MAX_LD_COEFFS; ++n) sv[n] = L(0.0);
+  ld_solution<L, ORDER, true>(L::seed(b.v, 0), L::seed(c.rr, 1), n_u, tab, sv[0], sv[1], sv[2], sv + 3);
+  // flux = s . g - 1 (limb_dark.py:45-47); only s_0 .. s_max(n_u, 0) enter
+  double f = -1.0, fb = 0.0, fr = 0.0;
+  for (int n = 0; n <= n_u; ++n) {
+    f = fma(sv[n].v, pd.g[n], f);
+    fb = fma(sv[n].d[0], pd.g[n], fb);
+    fr = fma(sv[n].d[1], pd.g[n], fr);
+  }
+  flux = f;
+#pragma unroll
+  for (int i = 0; i < NO; ++i) part[i] = fb * b.d[i];
+  part[5] = fr * c.inv_rstar;
+  for (int j = 0; j < n_u; ++j) {
+    double acc = 0.0;
+    for (int n = 0; n <= n_u; ++n) acc = fma(sv[n].v, pd.dg[n][j], acc);
+    part[6 + j] = acc;
+  }
+  return true;
+}
+
+struct PolyArgs {
+  const BodyD<double>* bodies;
+  const PolyD* poly;
+  const double* t;
+  int64_t n_times;
+  int n_sets, n_u, n_tiles, use_window;
+  double* flux;      // [n_sets][n_times] or nullptr
+  double* partials;  // [n_sets][6 + n_u][n_times] or nullptr
+  const double* y;
+  const double* winv;
+  double* partial;   // [n_sets][n_tiles][1 + 6 + n_u] per-tile sums (log-likelihood calls)
+  GLTable tab;
+};
+
+// one sample per thread, POLY_TILE consecutive samples of one set per CTA
+template <int ORDER, bool LOGLIKE>
+__global__ void __launch_bounds__(POLY_TILE) k_poly_rows(const __grid_constant__ PolyArgs a) {
+  __shared__ double s_red[POLY_TILE / 32];
+  const int set = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * POLY_TILE + threadIdx.x;
+  const int np = 6 + a.n_u;
+  const BodyD<double>& bd = a.bodies[set];
+  double flux = 0.0, part[POLY_NP_MAX];
+  for (int k = 0; k < POLY_NP_MAX; ++k) part[k] = 0.0;
+  bool hit = false;
+  if (i < a.n_times) {
+    const double tm = a.t[i];
+    if (!a.use_window || (bd.c.flags & BODY_ALWAYS) || !outside_window(bd.c, tm))
+      hit = eval_sample_partials_poly<ORDER>(bd, a.poly[set], a.n_u, &a.tab, tm, flux, part);
+    if (!hit) flux = 0.0;
+    if (a.flux) a.flux[(size_t)set * a.n_times + i] = flux;
+    if (a.partials)
+      for (int k = 0; k < np; ++k) a.partials[((size_t)set * np + k) * a.n_times + i] = hit ? part[k] : 0.0;
+  }
+  if (LOGLIKE) {
+    // per-tile sums in a fixed order: chi^2 term, then (y - 1 - f) / sigma^2 . d f / d theta_k
+    const bool any_hit = __syncthreads_or(hit ? 1 : 0) != 0;
+    double w = 0.0, res = 0.0;
+    if (i < a.n_times) {
+      w = a.winv[i];
+      res = ((a.y[i] - 1.0) - flux) * w;
+    }
+    for (int q = 0; q <= (any_hit ? np : 0); ++q) {
+      double v = q == 0 ? res * res : (hit ? res * w * part[q - 1] : 0.0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < POLY_TILE / 32; ++k) tot += s_red[k];
+        a.partial[((size_t)set * a.n_tiles + blockIdx.x) * (1 + POLY_NP_MAX) + q] = tot;
+      }
+      __syncthreads();
+    }
+    if (!any_hit && threadIdx.x < np)
+      a.partial[((size_t)set * a.n_tiles + blockIdx.x) * (1 + POLY_NP_MAX) + 1 + threadIdx.x] = 0.0;
+  }
+}
+
+// per (set, quantity): the tile sums added in tile order -> loglike, dloglike
+__global__ void __launch_bounds__(128) k_poly_final(const double* __restrict__ partial, int n_sets, int n_tiles,
+                                                    int np, const double* __restrict__ scalars,
+                                                    double* __restrict__ loglike, double* __restrict__ dloglike) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_sets * (1 + np)) return;
+  const int set = idx / (1 + np), q = idx % (1 + np);
+  const double* p = partial + (size_t)set * n_tiles * (1 + POLY_NP_MAX) + q;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < n_tiles; k += 4)
+    for (int m = 0; m < 4; ++m)
+      if (k + m < n_tiles) acc[m] += p[(size_t)(k + m) * (1 + POLY_NP_MAX)];
+  const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  if (q == 0) {
+    if (loglike) {
+      double cst = 0.0;  // sum_t (-log sigma - log(2 pi) / 2): the per-CTA sums of the likelihood prep, in order
+      for (int k = 0; k < LL_NCTA_H; ++k) cst += scalars[LL_SCAL0_H + 2 * k + 1];
+      loglike[set] = -0.5 * tot + cst;
+    }
+  } else if (dloglike) {
+    dloglike[(size_t)set * np + (q - 1)] = tot;
+  }
+}
+
+struct PolyLayout {
+  size_t off_bodies, off_poly, off_winv, off_scalars, off_partial, total;
+  int n_tiles;
+};
+PolyLayout poly_layout(int n_sets, int64_t n_times) {
+  PolyLayout L;
+  L.n_tiles = (int)((n_times + POLY_TILE - 1) / POLY_TILE);
+  size_t off = 0;
+  L.off_bodies = off;
+  off = align_up(off + sizeof(BodyD<double>) * (size_t)n_sets, 256);
+  L.off_poly = off;
+  off = align_up(off + sizeof(PolyD) * (size_t)n_sets, 256);
+  L.off_winv = off;
+  off = align_up(off + sizeof(double) * (size_t)n_times, 256);
+  L.off_scalars = off;
+  off = align_up(off + 256 * sizeof(double), 256);
+  L.off_partial = off;
+  off = align_up(off + sizeof(double) * (size_t)n_sets * L.n_tiles * (1 + POLY_NP_MAX), 256);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t jxp_transit_poly_workspace_bytes(int32_t n_sets, int64_t n_times) {
+  if (n_sets <= 0 || n_times <= 0) return 0;
+  return poly_layout(n_sets, n_times).total;
+}
+
+extern "C" int jxp_transit_partials_poly_f64(const double* theta, int32_t n_sets, int32_t n_u, const double* star,
+                                             int64_t star_stride, const double* t, int64_t n_times,
+                                             int32_t gl_order, int32_t flags, double* flux, double* partials,
+                                             const double* y, const double* sigma, int64_t sigma_stride,
+                                             double* loglike, double* dloglike, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  if (n_sets < 0 || n_times < 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_partials_poly: negative size");
+  if (n_u < 0 || n_u > JXP_MAX_LD_COEFFS)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_partials_poly: n_u = %d outside 0..%d", n_u, JXP_MAX_LD_COEFFS);
+  if (gl_order != 10) return fail(JXP_ERR_UNSUPPORTED, "jxp_transit_partials_poly: order must be 10");
+  if (star_stride != 0 && star_stride != 2)
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_partials_poly: star_set_stride must be 0 or 2");
+  if (!stride_ok(sigma_stride))
+    return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_partials_poly: sigma_stride must be 0 or 1");
+  if (n_sets == 0 || n_times == 0) return JXP_OK;
+  if (!theta || !star || !t) return fail(JXP_ERR_NULL_POINTER, "jxp_transit_partials_poly: null theta/star/t");
+  const bool want_ll = loglike || dloglike;
+  if (want_ll && (!y || !sigma))
+    return fail(JXP_ERR_NULL_POINTER, "jxp_transit_partials_poly: loglike needs y and sigma");
+  if (!flux && !partials && !want_ll)
+    return fail(JXP_ERR_NULL_POINTER, "jxp_transit_partials_poly: no output requested");
+  const PolyLayout L = poly_layout(n_sets, n_times);
+  if (!workspace || workspace_bytes < L.total)
+    return fail(JXP_ERR_WORKSPACE, "jxp_transit_partials_poly: workspace of %zu bytes needed, %zu given", L.total,
+                workspace_bytes);
+  if (((uintptr_t)workspace & 255) != 0)
+    return fail(JXP_ERR_WORKSPACE, "jxp_transit_partials_poly: workspace must be 256-byte aligned");
+  if (n_sets > 65535) return fail(JXP_ERR_UNSUPPORTED, "jxp_transit_partials_poly: more than 65535 sets per call");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  PolyArgs a;
+  a.bodies = reinterpret_cast<BodyD<double>*>(ws + L.off_bodies);
+  a.poly = reinterpret_cast<PolyD*>(ws + L.off_poly);
+  a.t = t;
+  a.n_times = n_times;
+  a.n_sets = n_sets;
+  a.n_u = n_u;
+  a.n_tiles = L.n_tiles;
+  a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
+  a.flux = flux;
+  a.partials = partials;
+  a.y = y;
+  a.winv = reinterpret_cast<double*>(ws + L.off_winv);
+  a.partial = reinterpret_cast<double*>(ws + L.off_partial);
+  a.tab.order = 10;
+  double* d_scalars = reinterpret_cast<double*>(ws + L.off_scalars);
+  k_tr_prep<double><<<(n_sets + 127) / 128, 128, 0, st>>>(theta, n_sets, star, star_stride,
+                                                         const_cast<BodyD<double>*>(a.bodies), 1.0 + 1e-9, 1e-7,
+                                                         nullptr, 6 + n_u, n_u, const_cast<PolyD*>(a.poly));
+  int rc = check_launch("jxp_transit_partials_poly(prep)");
+  if (rc != JXP_OK) return rc;
+  if (want_ll) {
+    rc = loglike_prep(y, sigma, sigma_stride, n_times, const_cast<double*>(a.winv), d_scalars, st, nullptr);
+    if (rc != JXP_OK) return rc;
+  }
+  const dim3 grid((unsigned)L.n_tiles, (unsigned)n_sets);
+  if (want_ll)
+    k_poly_rows<10, true><<<grid, POLY_TILE, 0, st>>>(a);
+  else
+    k_poly_rows<10, false><<<grid, POLY_TILE, 0, st>>>(a);
+  rc = check_launch("jxp_transit_partials_poly(rows)");
+  if (rc != JXP_OK) return rc;
+  if (want_ll) {
+    const int np = 6 + n_u;
+    k_poly_final<<<(n_sets * (1 + np) + 127) / 128, 128, 0, st>>>(a.partial, n_sets, L.n_tiles, np, d_scalars, loglike,
+                                                                 dloglike);
+    rc = check_launch("jxp_transit_partials_poly(final)");
   }
   return rc;
 }

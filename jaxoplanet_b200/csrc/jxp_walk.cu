@@ -22,6 +22,18 @@
 //                terms are added by a fixed shuffle tree into one partial; the warp that completes a
 //                set's last chunk adds the set's partials in a fixed order and writes the
 //                log-likelihood: bit-reproducible, no float atomics, no separate reduction launch.
+//   per-set function tables (jxp_tables.cuh): with many samples per set the in-window samples are not evaluated
+//                with the reference formula at all.  k_walk_plan also fits b^2 as a series in the mean anomaly
+//                across the set's transit window (lanes = 32 Chebyshev nodes, node values from the direct code);
+//                k_walk_tables (side stream, beside the plan) fits the flux F(b) of the set's (r, u) on pieces
+//                graded towards the contact points.  A set with tables whose transits span >= 12 samples becomes
+//                ITEMS (one per transit; groups of WK_GROUP per set) for
+//   k_walk_items one warp walks a group's transits as one coalesced sample stream: mean anomaly -> b^2 (Horner) ->
+//                piece of the F table -> flux (Horner) -> chi^2 term; two partial sums per group, added in order
+//                by the lane that completes the set.  Samples the tables do not answer go on a list for
+//   k_walk_fix   the direct quadrature on that list; chi^2 terms added in fixed point (order-independent).
+//                Sets with tables that stay on the chunk lists (exposure stencils, short transits) read the same
+//                tables in k_walk_eval; sets without tables (large r, wide windows) take the direct code there.
 // Unsorted / NaN time stamps or a table that does not fit are detected on the device; the kernels
 // then return at once and the window-test kernels launched behind them do the work.
 #include "../../include/jaxoplanet_b200.h"
@@ -906,7 +918,6 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     __syncwarp();
     const uint4 e = sm.ent[eb][k];
     const bool same_claim = k + 1u < cur_cnt;
-    const bool has_next_chunk = same_claim || nxt_valid;
     const int eb_next = eb == 2 ? 0 : eb + 1;
     // (without a next chunk this one is staged again: harmless, and the code stays free of branches)
     const uint4 en = same_claim ? sm.ent[eb][k + 1u] : (nxt_valid ? sm.ent[eb_next][0] : e);
@@ -1275,10 +1286,6 @@ __device__ __forceinline__ void walk_finish_items(const WalkItemArgs& a, unsigne
   a.loglike[set] = -0.5 * (a.scalars[WALK_STATE0 + 10] + tot) + a.scalars[WALK_STATE0 + 11];
 }
 
-#ifndef JXP_ITEMS_CLAIM
-#define JXP_ITEMS_CLAIM 8
-#endif
-constexpr unsigned WI_CLAIM = JXP_ITEMS_CLAIM;  // items per claim
 struct WalkItemSmem {
   double tabs[TB_DOUBLES];
   double rec[WALK_REC];
@@ -1306,8 +1313,7 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
   WalkItemSmem& sm = s_all[wid];
   const double* th = sm.tabs;
   const double* rec = sm.rec;
-  const double2* rec2 = reinterpret_cast<const double2*>(rec);
-  unsigned cur_set = 0xffffffffu;
+    unsigned cur_set = 0xffffffffu;
   unsigned n_ld = 0;
   // constants of the current set (registers; re-read when the set changes)
   double xs = 0.0, xe = 0.0, mc = 0.0, zsc = 0.0, zoff = 0.0, t0 = 0.0, tref = 0.0, per = 0.0, iper = 0.0;

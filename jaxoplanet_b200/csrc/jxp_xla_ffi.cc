@@ -14,7 +14,7 @@
 //                         light_curves.limb_dark.light_curve(System, *u)(t) (+ transforms.integrate,
 //                         + Normal(1 + lc, sigma).log_prob(y).sum())  src/jaxoplanet/light_curves/limb_dark.py:15-62,
 //                                                                    light_curves/transforms.py:21-116
-//   JxpTransitPartials* / JxpTransitGradient*
+//   JxpTransitPartials* / JxpTransitGradient* (+ ...PolyF64: polynomial limb darkening of any length)
 //                         jax.jvp / jax.grad of the above             orbits/keplerian.py:262-340, core/kepler.py:59-79
 //   JxpOrbitalElementsF64 OrbitalBody.__init__                        src/jaxoplanet/orbits/keplerian.py:262-340
 //   JxpOrbitState*        OrbitalBody.position / velocity families    src/jaxoplanet/orbits/keplerian.py:366-637
@@ -294,6 +294,45 @@ ffi::Error TransitGradientF32(cudaStream_t s, ffi::ScratchAllocator scratch, Buf
                                         dloglike, JXP_EXPO_ARGS);
 }
 
+// K5 for polynomial limb darkening of any length: theta [n_sets][6 + n_u] (n_u from the shape), double precision
+inline ffi::Error transit_poly_call(cudaStream_t stream, ffi::ScratchAllocator& scratch, const Buf<ffi::F64>& theta,
+                                    const Buf<ffi::F64>& star, const Buf<ffi::F64>& t, int64_t gl_order, int64_t flags,
+                                    double* flux, double* partials, const double* y, const double* sigma,
+                                    int64_t sigma_stride, double* loglike, double* dloglike) {
+  if (rank(theta) != 2 || dim(theta, 1) < 6 || dim(theta, 1) > 6 + JXP_MAX_LD_COEFFS)
+    return bad("jxp_transit_partials_poly: theta must be [n_sets][6 + n_u], 0 <= n_u <= 8");
+  const int32_t n_sets = static_cast<int32_t>(dim(theta, 0));
+  const int32_t n_u = static_cast<int32_t>(dim(theta, 1)) - 6;
+  const int64_t ns = static_cast<int64_t>(star.element_count());
+  if (ns != 2 && ns != 2 * static_cast<int64_t>(n_sets))
+    return bad("jxp_transit_partials_poly: star must be [2] or [n_sets][2] (central mass, central radius)");
+  const int64_t n_times = static_cast<int64_t>(t.element_count());
+  const size_t wsb = jxp_transit_poly_workspace_bytes(n_sets, n_times);
+  void* ws = nullptr;
+  if (ffi::Error e = workspace(scratch, wsb, &ws); e.failure()) return e;
+  return status(jxp_transit_partials_poly_f64(theta.typed_data(), n_sets, n_u, star.typed_data(), ns == 2 ? 0 : 2,
+                                              t.typed_data(), n_times, static_cast<int32_t>(gl_order),
+                                              static_cast<int32_t>(flags), flux, partials, y, sigma, sigma_stride,
+                                              loglike, dloglike, ws, wsb, stream));
+}
+ffi::Error TransitPartialsPolyF64(cudaStream_t s, ffi::ScratchAllocator scratch, Buf<ffi::F64> theta, Buf<ffi::F64> star,
+                                  Buf<ffi::F64> t, Out<ffi::F64> flux, Out<ffi::F64> partials, int64_t gl_order,
+                                  int64_t flags) {
+  return transit_poly_call(s, scratch, theta, star, t, gl_order, flags, flux->typed_data(), partials->typed_data(),
+                           nullptr, nullptr, 0, nullptr, nullptr);
+}
+ffi::Error TransitGradientPolyF64(cudaStream_t s, ffi::ScratchAllocator scratch, Buf<ffi::F64> theta, Buf<ffi::F64> star,
+                                  Buf<ffi::F64> t, Buf<ffi::F64> y, Buf<ffi::F64> sigma, Out<ffi::F64> loglike,
+                                  Out<ffi::F64> dloglike, int64_t gl_order, int64_t flags) {
+  const int64_t n_times = static_cast<int64_t>(t.element_count());
+  const int64_t n_sig = static_cast<int64_t>(sigma.element_count());
+  if (static_cast<int64_t>(y.element_count()) != n_times)
+    return bad("jxp_transit_partials_poly: y must have the shape of t");
+  if (n_sig != 1 && n_sig != n_times) return bad("jxp_transit_partials_poly: sigma must be a scalar or have the shape of t");
+  return transit_poly_call(s, scratch, theta, star, t, gl_order, flags, nullptr, nullptr, y.typed_data(),
+                           sigma.typed_data(), n_sig == 1 ? 0 : 1, loglike->typed_data(), dloglike->typed_data());
+}
+
 // ---------------------------------------------------------------------------------------------
 // K0  OrbitalBody.__init__: element records [n][16] -> body records [n][12]
 // ---------------------------------------------------------------------------------------------
@@ -430,6 +469,11 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpTransitGradientF64, TransitGradientF64,
                               JXP_STREAM_SCRATCH.A64.A64.A64.A64.A64.R64.R64.JXP_EXPO_ATTRS);
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpTransitGradientF32, TransitGradientF32,
                               JXP_STREAM_SCRATCH.A64.A64.A64.A32.A32.R32.R32.JXP_EXPO_ATTRS);
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpTransitPartialsPolyF64, TransitPartialsPolyF64,
+                              JXP_STREAM_SCRATCH.A64.A64.A64.R64.R64.Attr<int64_t>("gl_order").Attr<int64_t>("flags"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpTransitGradientPolyF64, TransitGradientPolyF64,
+                              JXP_STREAM_SCRATCH.A64.A64.A64.A64.A64.R64.R64.Attr<int64_t>("gl_order")
+                                  .Attr<int64_t>("flags"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpOrbitalElementsF64, OrbitalElementsF64, JXP_STREAM.A64.R64);
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpOrbitStateF64, OrbitStateF64,
                               JXP_STREAM.A64.A64.A64.A64.A64.R64.R64.Attr<int64_t>("has_asc_node").Attr<int64_t>("flags"));

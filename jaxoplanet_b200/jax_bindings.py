@@ -38,6 +38,8 @@ TARGETS = {
     "JxpSystemLogLikeF64": "jxp_system_loglike_f64", "JxpSystemLogLikeF32": "jxp_system_loglike_f32",
     "JxpTransitPartialsF64": "jxp_transit_partials_f64", "JxpTransitPartialsF32": "jxp_transit_partials_f32",
     "JxpTransitGradientF64": "jxp_transit_gradient_f64", "JxpTransitGradientF32": "jxp_transit_gradient_f32",
+    "JxpTransitPartialsPolyF64": "jxp_transit_partials_poly_f64",
+    "JxpTransitGradientPolyF64": "jxp_transit_gradient_poly_f64",
     "JxpOrbitalElementsF64": "jxp_orbital_elements_f64",
     "JxpOrbitStateF64": "jxp_orbit_state_f64", "JxpOrbitStateF32": "jxp_orbit_state_f32",
     "JxpTransitOrbitF64": "jxp_transit_orbit_f64", "JxpTransitOrbitF32": "jxp_transit_orbit_f32",
@@ -251,6 +253,59 @@ if available():
         out = _transit_lc(theta, star, jnp.asarray(t, dtype=jnp.float64).reshape(-1), dtype, exposure_time,
                           exp_order, num_samples, order)
         return out[0] if single else out
+
+    # ---- polynomial limb darkening of any length: theta [n_sets][6 + n_u] (double precision, order 10)
+    def _poly_partials_call(theta, star, t):
+        register()
+        n_sets, n_theta, n_t = theta.shape[0], theta.shape[1], t.shape[0]
+        outs = (jax.ShapeDtypeStruct((n_sets, n_t), jnp.float64), jax.ShapeDtypeStruct((n_sets, n_theta, n_t), jnp.float64))
+        return jax.ffi.ffi_call("jxp_transit_partials_poly_f64", outs, vmap_method="sequential")(
+            theta, star, t, gl_order=np.int64(10), flags=np.int64(0))
+
+    @jax.custom_jvp
+    def _transit_lc_poly(theta, star, t):
+        return _poly_partials_call(theta, star, t)[0]
+
+    @_transit_lc_poly.defjvp
+    def _transit_lc_poly_jvp(primals, tangents):
+        theta, star, t = primals
+        flux, part = _poly_partials_call(theta, star, t)
+        return flux, jnp.einsum("skt,sk->st", part, tangents[0].astype(part.dtype))
+
+    def transit_light_curve_poly(theta, t, *, central_mass=1.0, central_radius=1.0):
+        """As transit_light_curve for a polynomial limb-darkening law of any length: theta [n_sets][6 + n_u] = (period,
+        time_transit, eccentricity, omega_peri, impact_param, radius, u_1 .. u_n), n_u <= 8; differentiable w.r.t.
+        theta (the reference differentiates core.limb_dark.light_curve for any u)."""
+        theta = jnp.asarray(theta, dtype=jnp.float64)
+        single = theta.ndim == 1
+        theta = theta.reshape(-1, theta.shape[-1])
+        star = jnp.stack([jnp.asarray(central_mass, dtype=jnp.float64), jnp.asarray(central_radius, dtype=jnp.float64)])
+        out = _transit_lc_poly(theta, star, jnp.asarray(t, dtype=jnp.float64).reshape(-1))
+        return out[0] if single else out
+
+    def _poly_gradient_call(theta, star, t, y, sigma):
+        register()
+        outs = (jax.ShapeDtypeStruct((theta.shape[0],), jnp.float64), jax.ShapeDtypeStruct(theta.shape, jnp.float64))
+        return jax.ffi.ffi_call("jxp_transit_gradient_poly_f64", outs, vmap_method="sequential")(
+            theta, star, t, y, sigma, gl_order=np.int64(10), flags=np.int64(0))
+
+    @jax.custom_jvp
+    def _transit_ll_poly(theta, star, t, y, sigma):
+        return _poly_gradient_call(theta, star, t, y, sigma)[0]
+
+    @_transit_ll_poly.defjvp
+    def _transit_ll_poly_jvp(primals, tangents):
+        ll, dll = _poly_gradient_call(*primals)
+        return ll, jnp.sum(dll * tangents[0].astype(dll.dtype), axis=-1)
+
+    def transit_log_likelihood_poly(theta, t, y, sigma, *, central_mass=1.0, central_radius=1.0):
+        """Gaussian log-likelihood per parameter set for theta [n_sets][6 + n_u], differentiable w.r.t. theta."""
+        theta = jnp.asarray(theta, dtype=jnp.float64)
+        theta = theta.reshape(-1, theta.shape[-1])
+        star = jnp.stack([jnp.asarray(central_mass, dtype=jnp.float64), jnp.asarray(central_radius, dtype=jnp.float64)])
+        return _transit_ll_poly(theta, star, jnp.asarray(t, dtype=jnp.float64).reshape(-1),
+                                jnp.asarray(y, dtype=jnp.float64).reshape(-1),
+                                jnp.atleast_1d(jnp.asarray(sigma, dtype=jnp.float64)).reshape(-1))
 
     @partial(jax.custom_jvp, nondiff_argnums=(5, 6, 7, 8, 9))
     def _transit_ll(theta, star, t, y, sigma, dtype, exposure_time, exp_order, num_samples, order):

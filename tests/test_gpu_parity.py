@@ -610,6 +610,110 @@ def _partials_oracle(theta, t, u_shared=True):
     return flux.detach().numpy(), part
 
 
+def _partials_oracle_poly(theta, t):
+    """As _partials_oracle for a polynomial limb-darkening law of any length: theta = 6 orbit parameters + u."""
+    import torch
+
+    TH = ref.torch_backend()
+    n_t = t.shape[0]
+    n_u = theta.shape[0] - 6
+    tt = torch.tensor(t)
+    names = ("period", "time_transit", "eccentricity", "omega_peri", "impact_param", "radius")
+    par = {k: torch.full((n_t,), float(theta[i]), dtype=torch.float64, requires_grad=True)
+           for i, k in enumerate(names)}
+    u = torch.tensor(theta[6:], requires_grad=True)
+    bd = ref.orbital_body(xp=TH, **par)
+    flux = ref.system_light_curve([bd], u, tt, xp=TH)[:, 0]
+    grads = torch.autograd.grad(flux.sum(), list(par.values()), allow_unused=True)
+    part = np.zeros((6 + n_u, n_t))
+    for i, g in enumerate(grads):
+        if g is not None:
+            part[i] = g.numpy()
+    x, y, z = ref.relative_position({k: (v.detach().numpy() if hasattr(v, "detach") else v) for k, v in bd.items()}, t)
+    b = np.sqrt(x**2 + y**2)
+    s = ref.solution_vector(n_u, b, np.full_like(b, theta[5]))
+    s = [np.where(z > 0, sk, 0.0) for sk in s]
+    uu = torch.tensor(theta[6:], requires_grad=True)
+    g = ref.greens_basis_transform(uu, TH)
+    g = g / (np.pi * (g[0] + g[1] / 1.5))
+    J = np.stack([torch.autograd.grad(g[k], uu, retain_graph=True)[0].numpy() for k in range(n_u + 1)])
+    for j in range(n_u):
+        part[6 + j] = sum(s[k] * J[k, j] for k in range(n_u + 1))
+    return flux.detach().numpy(), part
+
+
+@pytest.mark.parametrize("n_u", [1, 3, 4, 6])
+def test_transit_partials_general_polynomial_limb_darkening(n_u):
+    """Partials w.r.t. (P, t0, e, omega, b, r, u_1 .. u_n) for laws of any length (the reference differentiates
+    core.limb_dark.light_curve for any u: core/limb_dark.py:19-47, 87-99, 149-182) against torch autograd over the
+    restatement, tolerance 1e-9 relative, contact points excluded; log-likelihood gradient against the rows."""
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    rng = np.random.default_rng(10 + n_u)
+    n_sets, n_t = 3, 5000
+    th6 = _theta_sets(rng, n_sets)[:, :6]
+    u = rng.uniform(0.02, 0.6 / n_u, (n_sets, n_u))
+    theta = np.concatenate([th6, u], 1)
+    t = np.arange(n_t) * (2.0 / 1440.0)
+    y = 1 + 5e-4 * rng.normal(size=n_t)
+    res = transit_partials(theta, t, y=y, sigma=5e-4)
+    assert res["flux"].shape == (n_sets, n_t) and res["partials"].shape == (n_sets, 6 + n_u, n_t)
+    assert res["dloglike"].shape == (n_sets, 6 + n_u)
+    n_checked = 0
+    for s in range(n_sets):
+        flux0, part0 = _partials_oracle_poly(theta[s], t)
+        _flux_close(res["flux"][s], flux0)
+        bd = ref.orbital_body(**dict(zip(("period", "time_transit", "eccentricity", "omega_peri",
+                                          "impact_param", "radius"), theta[s, :6])))
+        x, yy, z = ref.relative_position(bd, t)
+        b = np.sqrt(x**2 + yy**2)
+        r = theta[s, 5]
+        ok = (np.abs(b - r) > 1e-6) & (np.abs(np.abs(b - r) - 1) > 1e-6) & (np.abs(b - 1 - r) > 1e-6) & (b > 1e-6)
+        got = res["partials"][s]
+        scale = np.array([1e-1, 1e-1, 1e-2, 1e-2, 1e-2, 1e-2] + [1e-3] * n_u)[:, None]
+        err = np.abs(got - part0) / np.maximum(np.abs(part0), scale)
+        assert np.max(err[:, ok]) <= 1e-9, (s, np.max(err[:, ok], axis=1))
+        assert np.all(got[:, flux0 == 0] == 0)
+        n_checked += int(np.sum(flux0 != 0))
+        # log-likelihood and its gradient from the same rows
+        m = 1 + res["flux"][s]
+        ll0 = ref.gaussian_loglike(m, y, 5e-4 * np.ones(n_t))
+        assert abs(res["loglike"][s] - ll0) <= 1e-12 * abs(ll0)
+        dll0 = ((y - m) / 5e-4**2 * got).sum(-1)
+        assert np.max(np.abs(res["dloglike"][s] - dll0) / np.maximum(np.abs(dll0), 1e-3 * np.abs(dll0).max())) <= 1e-10
+    assert n_checked > 100
+
+
+def test_transit_partials_poly_entry_agrees_with_the_quadratic_kernel():
+    """n_u = 2 through the general entry point (forced) against the tuned K5 kernel."""
+    import ctypes
+
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200.light_curves.partials import transit_partials
+
+    rng = np.random.default_rng(21)
+    theta = _theta_sets(rng, 4)
+    t = np.arange(4000) * (2.0 / 1440.0)
+    res = transit_partials(theta, t)
+    dev = A.device()
+    th = torch.as_tensor(theta).to(dev).contiguous()
+    td = torch.as_tensor(t).to(dev)
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device=dev)
+    flux = torch.empty((4, 4000), dtype=torch.float64, device=dev)
+    part = torch.empty((4, 8, 4000), dtype=torch.float64, device=dev)
+    wsb = int(_lib.load().jxp_transit_poly_workspace_bytes(4, 4000))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    _lib.call("jxp_transit_partials_poly_f64", th.data_ptr(), 4, 2, star.data_ptr(), 0, td.data_ptr(), 4000, 10, 0,
+              flux.data_ptr(), part.data_ptr(), None, None, 0, None, None, ws.data_ptr(), wsb, A.stream_ptr())
+    f, pz = flux.cpu().numpy(), part.cpu().numpy()
+    assert np.array_equal(f != 0, res["flux"] != 0) and np.max(np.abs(f - res["flux"])) <= 1e-14
+    scale = np.abs(res["partials"]).max(axis=(0, 2), keepdims=True)
+    assert np.max(np.abs(pz - res["partials"]) / scale) <= 1e-10
+
+
 def _theta_sets(rng, n_sets):
     P = rng.uniform(2, 5, n_sets)
     q = rng.uniform(0.05, 0.95, (n_sets, 2))
