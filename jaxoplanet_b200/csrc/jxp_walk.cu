@@ -952,14 +952,14 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
     const int n_sub = EXPO ? a.st.n : 1;
 #pragma unroll 1
     for (int j = 0; j < n_sub; ++j) {
-    double Mr[N];
+    double Mr[N];  // the mean anomaly; reduced to [0, 2 pi) below where the Kepler solve wants it
 #pragma unroll
     for (int h = 0; h < N; ++h) {
       const double x = ((EXPO ? tsamp[h] + a.st.dt[j] : tsamp[h]) - tt.x) - tt.y;
       const double num = Num<double>::two_pi * x;
       const double q = num * pp.y;
       const double r = fma(-pp.x, q, num);
-      Mr[h] = mod_two_pi(fma(r, pp.y, q));
+      Mr[h] = fma(r, pp.y, q);
     }
     double tot[N];
     bool intr[N];
@@ -974,14 +974,13 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
       double zv[N], b2[N];
 #pragma unroll
       for (int h = 0; h < N; ++h) {
-        double d = Mr[h] - mc;
-        d = d > Num<double>::pi ? d - Num<double>::two_pi : d;
-        d = d < -Num<double>::pi ? d + Num<double>::two_pi : d;
+        // (reduced next to the conjunction's mean anomaly instead of into [0, 2 pi): see k_walk_items)
+        const double kk = rint((Mr[h] - mc) * Num<double>::inv_two_pi);
+        const double d = fma(-kk, Num<double>::two_pi, Mr[h]) - mc;
         zv[h] = fma(d, zsc, zoff);
         b2[h] = 0.0;
       }
-#pragma unroll 1
-      for (int k = db | 3; k > 0; k -= 4) {
+      auto b2_step = [&](int k) {
         const double2 c1 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 1);  // (m_{k-1}, m_k)
         const double2 c0 = *reinterpret_cast<const double2*>(th + TB_B2 + k - 3);  // (m_{k-3}, m_{k-2})
 #pragma unroll
@@ -989,7 +988,14 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
           b2[h] = fma(fma(b2[h], zv[h], c1.y), zv[h], c1.x);
           b2[h] = fma(fma(b2[h], zv[h], c0.y), zv[h], c0.x);
         }
+      };
+      if (db > 11) {
+#pragma unroll 1
+        for (int k = db | 3; k > 11; k -= 4) b2_step(k);
       }
+      b2_step(11);
+      b2_step(7);
+      b2_step(3);
       bool ins[N], want_edge = false;
       double q[N];
       int pc[N];
@@ -1072,6 +1078,8 @@ __global__ void __launch_bounds__(128, JXP_WALK_MINB) k_walk_eval(const __grid_c
 #else
       {
         const double2 ee = rec2[WK_E / 2], oo = rec2[WK_OPE / 2];
+#pragma unroll
+        for (int h = 0; h < N; ++h) Mr[h] = mod_two_pi(Mr[h]);
         kepler_xy_u<N>(Mr, ee.x, ee.y, oo.x, oo.y, rec[WK_INVOPE], yD, xD);
       }
 #endif
