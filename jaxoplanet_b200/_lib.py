@@ -26,6 +26,8 @@ JXP_DEV_PROFILE_PLAN = 16
 JXP_DEV_NO_TABLES = 32
 JXP_DEV_PROFILE_TABLES = 64
 JXP_DEV_PROFILE_ITEMS = 128
+JXP_DEV_NO_BULK_FILL = 4096
+JXP_DEV_BULK_FILL_SWAP = 8192
 
 
 def JXP_DEV_CTA_WARPS(n):

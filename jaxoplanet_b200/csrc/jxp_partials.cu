@@ -285,6 +285,8 @@ struct TrArgs {
   int64_t n_times;
   int n_sets, sets_per_cta, n_tiles, n_wtiles, use_window;
   int run;  // consecutive warp tiles one warp processes (queued samples are carried from one to the next)
+  int bulk_fill;  // zero rows written by the copy engine (cp.async.bulk from a zeroed shared-memory tile), run == 1 only:
+                  // 1 = every thread issues its share and the drains wait for the copies, 2 = warp 0 issues, results buffered
   T* flux;      // [n_sets][n_times]
   T* partials;  // [n_sets][8][n_times]
   const T* y;
@@ -310,6 +312,7 @@ struct TrArgs {
 // drained 32 in-window samples at a time through ONE instance of the dual-number code.
 // Every zero row is one fully coalesced warp store (256 B in f64).
 constexpr int TR_QCAP = 128;
+constexpr int TR_RB = 128;  // buffered results per warp (bulk_fill): four full drains
 // 3 CTAs/SM = 168 registers: with 128 the dual-number code spills (100 B stores / 124 B loads per
 // thread) and the local-memory traffic competes with the 59 GB row-store stream (config 5: 11.7 ms;
 // 96 registers 13.3 ms; 168 registers 11.15 ms; 200 registers, no spill at all, 12.4 ms)
@@ -337,9 +340,14 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   const int nsl = min(a.sets_per_cta, a.n_sets - set_base);
   BodyD<T>* sbody = reinterpret_cast<BodyD<T>*>(smem_raw);
   double* sacc_all = reinterpret_cast<double*>(sbody + a.sets_per_cta);  // [nwarps][spc][9]
-  unsigned* sq_all = reinterpret_cast<unsigned*>(sacc_all + (size_t)nwarps * a.sets_per_cta * NQ);
+  unsigned* sq_all = reinterpret_cast<unsigned*>(sacc_all + (LOGLIKE ? (size_t)nwarps * a.sets_per_cta * NQ : 0));
   double* sacc = sacc_all + (size_t)warp * a.sets_per_cta * NQ;
   unsigned* sq = sq_all + warp * TR_QCAP;
+  // (bulk_fill) results of the drains that finish before the zero rows have landed: [NQ][TR_RB] values + TR_RB items per warp
+  T* sres = reinterpret_cast<T*>(sq_all + (size_t)nwarps * TR_QCAP) + (size_t)warp * (NQ * TR_RB);
+  unsigned* sitem = reinterpret_cast<unsigned*>(reinterpret_cast<T*>(sq_all + (size_t)nwarps * TR_QCAP) +
+                                                (size_t)nwarps * (NQ * TR_RB)) + warp * TR_RB;
+  int nbuf = 0;
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.bodies + set_base);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sbody);
@@ -363,7 +371,77 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   const double dtmin = a.st.dt_min, dtmax = a.st.dt_max;
   const bool want_rows = (a.flux != nullptr) || (a.partials != nullptr);
   int qn = 0;
+  // ---- zero rows by the copy engine ---------------------------------------------------------------
+  // With one warp tile per warp (run == 1) the CTA owns `nwarps * 32 K` consecutive samples of every row of its
+  // sets: each row piece (2 KB in f64, 1 KB in f32) is ONE bulk copy from a zeroed shared-memory tile, issued by
+  // one thread -- 9 x 32 copies per CTA instead of 9 x 32 x 4 warp-wide stores.  The copy queue of the SM is the
+  // bottleneck of this kernel (the issuing thread blocks while it is full: 37 % of the stall samples of a capture in
+  // which every thread issued its share), so WARP 0 ALONE issues the copies while the other warps go straight on to
+  // the window tests and the dual-number code; the warp tiles of the CTA are claimed dynamically (warp 0 joins when
+  // its copies are queued).  The results of the drains are kept in shared memory (TR_RB per warp) and stored over
+  // the zero rows once the copies are complete (fill_wait, then flush) -- normally at the end of the warp's tiles,
+  // earlier only if the buffer fills up (sets that always transit).  With the in-kernel reduction (LOGLIKE) the
+  // tiles stay with their warps: the order of the per-warp sums must not depend on timing.
+  __shared__ __align__(128) unsigned char s_zero[4 * 32 * TR_K * sizeof(T)];
+  __shared__ int s_next;
+  bool fill_pending = false;
+  if (threadIdx.x == 0) s_next = 0;
+  if (a.bulk_fill && want_rows) {
+    for (int i = threadIdx.x; i < (int)(sizeof(s_zero) / 16); i += nthreads)
+      reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fill_pending = true;
+  }
   __syncthreads();
+  const bool decoupled = a.bulk_fill == 2;
+  const bool dyn = fill_pending && decoupled && !LOGLIKE;
+  if (fill_pending && (warp == 0 || !decoupled)) {
+    const int64_t cbase = (int64_t)tile * nwarps * (32 * K);
+    const int64_t clen = min((int64_t)nwarps * (32 * K), a.n_times - cbase);
+    if (clen > 0) {
+      const unsigned bytes = (unsigned)(clen * (int64_t)sizeof(T));
+      const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
+      const int rps = (a.flux ? 1 : 0) + (a.partials ? JXP_NTHETA : 0);
+      for (int rho = decoupled ? lane : (int)threadIdx.x; rho < nsl * rps; rho += decoupled ? 32 : nthreads) {
+        const int sl = rho / rps;
+        int q = rho - sl * rps;
+        const size_t set = (size_t)(set_base + sl);
+        T* dst;
+        if (a.flux && q == 0) {
+          dst = a.flux + set * a.n_times + cbase;
+        } else {
+          q -= a.flux ? 1 : 0;
+          dst = a.partials + (set * JXP_NTHETA + q) * a.n_times + cbase;
+        }
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  // every thread's copies complete (writes performed, not just the source read) before any lane of the CTA stores
+  // an in-window sample over them; each warp passes here exactly once (before its first drain, or on its way out)
+  auto fill_wait = [&]() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    fill_pending = false;
+  };
+  auto flush = [&]() {
+    __syncwarp();
+    for (int e = lane; e < nbuf; e += 32) {
+      const unsigned item = sitem[e];
+      const size_t set = (size_t)(set_base + (int)(item >> 26));
+      const size_t idx = (size_t)(item & 0x3ffffffu);
+      if (a.flux) a.flux[set * a.n_times + idx] = sres[e];
+      if (a.partials) {
+#pragma unroll
+        for (int q = 0; q < JXP_NTHETA; ++q) a.partials[(set * JXP_NTHETA + q) * a.n_times + idx] = sres[(1 + q) * TR_RB + e];
+      }
+    }
+    nbuf = 0;
+    __syncwarp();
+  };
 
   // fill state
   bool have_tile = false, more = true;
@@ -379,12 +457,17 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
     // ---- fill: stages A and B until 32 samples are queued or the run has no tile left ------------
     while (more && qn < 32) {
       if (!have_tile) {
-        wbase = (((int64_t)r_next * a.n_tiles + tile) * nwarps + warp) * (32 * K);
-        if (r_next >= a.run || wbase >= a.n_times) {
+        int wt = warp;
+        if (dyn) {  // (run == 1: the CTA's nwarps tiles, whoever is free)
+          if (lane == 0) wt = atomicAdd(&s_next, 1);
+          wt = __shfl_sync(0xffffffffu, wt, 0);
+        }
+        wbase = (((int64_t)r_next * a.n_tiles + tile) * nwarps + wt) * (32 * K);
+        if (wt >= nwarps || r_next >= a.run || wbase >= a.n_times) {
           more = false;
           break;
         }
-        ++r_next;
+        if (!dyn) ++r_next;
         valid = 0;
         double tmin = 1e300, tmax = -1e300;
 #pragma unroll
@@ -408,7 +491,7 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
         // Zero rows first: the whole (sets of the group) x (flux + 8 partials) x (this tile's 64
         // samples) block is written as one 128-bit store per lane and row (512 contiguous bytes per
         // warp store in f64); stage C then overwrites the in-window samples (3 % of them on config 5).
-        if (want_rows) {
+        if (want_rows && !a.bulk_fill) {
           static_assert(TR_K == 2, "the zero fill assumes 2 samples per lane");
           struct alignas(2 * sizeof(T)) V2 {
             T x, y;
@@ -505,6 +588,7 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
       __syncwarp();
     }
     if (qn == 0) break;  // no tile left in the run and nothing queued
+    if (fill_pending && !decoupled) fill_wait();
 
     // ---- stage C: drain -----------------------------------------------------------------------
     // 32 queued samples (fewer only at the very end of the run): queued samples carry their absolute
@@ -538,11 +622,35 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
             any = true;
           }
         }
-        if (a.flux) a.flux[(size_t)set * a.n_times + idx] = out[0];
-        if (a.partials) {
+        if (!fill_pending) {
+          if (a.flux) a.flux[(size_t)set * a.n_times + idx] = out[0];
+          if (a.partials) {
 #pragma unroll
-          for (int q = 0; q < JXP_NTHETA; ++q)
-            a.partials[((size_t)set * JXP_NTHETA + q) * a.n_times + idx] = out[1 + q];
+            for (int q = 0; q < JXP_NTHETA; ++q)
+              a.partials[((size_t)set * JXP_NTHETA + q) * a.n_times + idx] = out[1 + q];
+          }
+        }
+      }
+      if (fill_pending) {  // (warp-uniform)
+        if (nbuf + 32 > TR_RB) {  // buffer full: wait for the zero rows, empty it, store directly from here on
+          fill_wait();
+          flush();
+          if (have) {
+            const int set = set_base + sl;
+            if (a.flux) a.flux[(size_t)set * a.n_times + idx] = out[0];
+            if (a.partials) {
+#pragma unroll
+              for (int q = 0; q < JXP_NTHETA; ++q)
+                a.partials[((size_t)set * JXP_NTHETA + q) * a.n_times + idx] = out[1 + q];
+            }
+          }
+        } else {
+          if (have) {
+            sitem[nbuf + lane] = item;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sres[q * TR_RB + nbuf + lane] = out[q];
+          }
+          nbuf += cnt;
         }
       }
       if (LOGLIKE) {
@@ -605,6 +713,8 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
       __syncwarp();
     }
   }
+  if (fill_pending) fill_wait();
+  flush();
   if (LOGLIKE) {
     for (int i = lane; i < nsl * NQ; i += 32) {
       const int sl = i / NQ, q = i - sl * NQ;
@@ -847,6 +957,14 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   a.n_tiles = (int)n_tiles;
   a.n_wtiles = (int)n_wtiles;
   a.run = run;
+  // (bulk copies need 16-byte aligned row pieces: a tile starts at a multiple of 64 samples)
+  // In double the copy queue is the bottleneck (59 GB on config 5) and the issuing threads block on it: mode 2
+  // (one issuing warp, results buffered) 10.7 -> 10.0 ms; in float the arithmetic is, and the plain mode 1 is the
+  // faster one (6.3 -> 5.8 ms).
+  a.bulk_fill = (run == 1 && (flux || partials) && !(dev_options() & JXP_DEV_NO_BULK_FILL) &&
+                 (n_times * (int64_t)sizeof(T)) % 16 == 0 && ((uintptr_t)flux & 15) == 0 && ((uintptr_t)partials & 15) == 0)
+                    ? (((sizeof(T) == 8) != ((dev_options() & JXP_DEV_BULK_FILL_SWAP) != 0)) ? 2 : 1)
+                    : 0;
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
   a.partials = partials;
@@ -904,8 +1022,9 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
     }
   }
   const size_t smem = sizeof(BodyD<T>) * (size_t)spc +
-                      sizeof(double) * (1 + JXP_NTHETA) * (size_t)spc * (threads / 32) +
-                      sizeof(unsigned) * (size_t)TR_QCAP * (threads / 32);
+                      (want_ll ? sizeof(double) * (1 + JXP_NTHETA) * (size_t)spc * (threads / 32) : 0) +
+                      sizeof(unsigned) * (size_t)TR_QCAP * (threads / 32) +
+                      (a.bulk_fill == 2 ? (sizeof(T) * (1 + JXP_NTHETA) + sizeof(unsigned)) * (size_t)TR_RB * (threads / 32) : 0);
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

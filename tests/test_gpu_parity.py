@@ -843,6 +843,45 @@ def test_transit_partials_runs_with_carried_queue_match_single_tiles():
         assert float(torch.max(torch.abs(out[run]["dloglike"] - out["1"]["dloglike"]) / scale)) <= 1e-12
 
 
+def test_transit_partials_bulk_zero_fill_matches_warp_stores():
+    """K5 writes its zero rows with bulk copies from a zeroed shared-memory tile (cp.async.bulk) and stores the
+    in-window samples over them once the copies are complete: every row must equal, bit for bit, what the plain
+    warp-store fill produces -- on ragged sizes (last tile short, few sets, a CTA of 1 / 2 / 4 warps), in f64 and
+    f32, with a sentinel behind every buffer."""
+    import torch
+
+    from jaxoplanet_b200 import _array as A
+    from jaxoplanet_b200 import _lib
+    from jaxoplanet_b200 import workloads as W
+
+    lib = _lib.load()
+    star = torch.tensor([1.0, 1.0], dtype=torch.float64, device="cuda")
+    for n_sets, n_times in ((3, 64), (37, 1000), (70, 4098), (33, 20_004), (200, 30_000)):
+        p, ub = W.transit_sets(n_sets, seed=100 + n_sets)
+        theta = torch.as_tensor(W.theta_from(p, ub)).cuda()
+        t = torch.as_tensor(np.arange(n_times) * W.TWO_MIN).cuda()
+        wsb = int(lib.jxp_transit_workspace_bytes(n_sets, n_times))
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        for dt, nm in ((torch.float64, "f64"), (torch.float32, "f32")):
+            if (n_times * torch.empty(0, dtype=dt).element_size()) % 16:
+                continue  # (rows that are not 16-byte multiples take the warp-store fill anyway)
+            outs = []
+            for mask in (0, _lib.JXP_DEV_BULK_FILL_SWAP, _lib.JXP_DEV_NO_BULK_FILL):
+                fl = torch.full((n_sets * n_times + 64,), 7.0, dtype=dt, device="cuda")
+                pt = torch.full((n_sets * 8 * n_times + 64,), 7.0, dtype=dt, device="cuda")
+                with _lib.dev_options(mask):
+                    _lib.call("jxp_transit_partials_" + nm, theta.data_ptr(), n_sets, star.data_ptr(), 0, t.data_ptr(),
+                              n_times, 0.0, 0, 0, 10, 0, fl.data_ptr(), pt.data_ptr(), 0, 0, 0, 0, 0, ws.data_ptr(), wsb,
+                              A.stream_ptr())
+                torch.cuda.synchronize()
+                assert bool(torch.all(fl[-64:] == 7.0)) and bool(torch.all(pt[-64:] == 7.0))
+                outs.append((fl, pt))
+            for o in outs[:2]:
+                assert torch.equal(o[0], outs[2][0]) and torch.equal(o[1], outs[2][1])
+            assert n_times < 4098 or float(outs[0][0][:-64].min()) < 0.0  # (some set transits)
+            assert not bool(torch.any(outs[0][1][:-64] == 7.0)) and not bool(torch.any(outs[0][0][:-64] == 7.0))
+
+
 def test_window_is_conservative_on_adversarial_orbits():
     # the transit-window pre-test must never drop an in-transit sample: windowed and dense
     # evaluations have to agree bit for bit on short-period, eccentric, grazing and
