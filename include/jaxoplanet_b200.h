@@ -168,6 +168,8 @@ int jxp_system_light_curve_f32(const double* bodies, int32_t n_sets, int32_t n_b
 #define JXP_DEV_NO_TABLES 32u     /* transit walk: every sample by the direct Kepler + quadrature code (no per-set tables) */
 #define JXP_DEV_NO_BULK_FILL 4096u /* jxp_transit_partials: zero rows by warp stores instead of bulk copies from shared memory */
 #define JXP_DEV_BULK_FILL_SWAP 8192u /* jxp_transit_partials: the other bulk-fill mode (f64: every thread issues, f32: one warp issues) */
+#define JXP_DEV_TR_TPW(n) (((uint32_t)(n) & 0x3u) << 14)      /* jxp_transit_partials, bulk fill: warp tiles per warp (1..2) */
+#define JXP_DEV_GET_TR_TPW(m) (((m) >> 14) & 0x3u)
 #define JXP_DEV_CTA_WARPS(n) (((uint32_t)(n) & 0xfu) << 8)   /* window-test kernels: warps per CTA (1..4) */
 #define JXP_DEV_GET_CTA_WARPS(m) (((m) >> 8) & 0xfu)
 #define JXP_DEV_TR_RUN(n) (((uint32_t)(n) & 0x7fu) << 16)    /* jxp_transit_partials: warp tiles per run */

@@ -34,6 +34,10 @@ def JXP_DEV_CTA_WARPS(n):
     return (int(n) & 0xF) << 8
 
 
+def JXP_DEV_TR_TPW(n):
+    return (int(n) & 0x3) << 14
+
+
 def JXP_DEV_TR_RUN(n):
     return (int(n) & 0x7F) << 16
 

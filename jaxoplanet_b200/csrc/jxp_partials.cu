@@ -285,6 +285,7 @@ struct TrArgs {
   int64_t n_times;
   int n_sets, sets_per_cta, n_tiles, n_wtiles, use_window;
   int run;  // consecutive warp tiles one warp processes (queued samples are carried from one to the next)
+  int tpw;        // (bulk_fill) warp tiles per warp: the CTA owns nwarps * tpw consecutive warp tiles
   int bulk_fill;  // zero rows written by the copy engine (cp.async.bulk from a zeroed shared-memory tile), run == 1 only:
                   // 1 = every thread issues its share and the drains wait for the copies, 2 = warp 0 issues, results buffered
   T* flux;      // [n_sets][n_times]
@@ -312,7 +313,8 @@ struct TrArgs {
 // drained 32 in-window samples at a time through ONE instance of the dual-number code.
 // Every zero row is one fully coalesced warp store (256 B in f64).
 constexpr int TR_QCAP = 128;
-constexpr int TR_RB = 128;  // buffered results per warp (bulk_fill): four full drains
+constexpr int TR_RB = 160;  // buffered results per warp (bulk_fill): five full drains
+constexpr int TR_TPW_MAX = 2;
 // 3 CTAs/SM = 168 registers: with 128 the dual-number code spills (100 B stores / 124 B loads per
 // thread) and the local-memory traffic competes with the 59 GB row-store stream (config 5: 11.7 ms;
 // 96 registers 13.3 ms; 168 registers 11.15 ms; 200 registers, no spill at all, 12.4 ms)
@@ -382,7 +384,7 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   // the zero rows once the copies are complete (fill_wait, then flush) -- normally at the end of the warp's tiles,
   // earlier only if the buffer fills up (sets that always transit).  With the in-kernel reduction (LOGLIKE) the
   // tiles stay with their warps: the order of the per-warp sums must not depend on timing.
-  __shared__ __align__(128) unsigned char s_zero[4 * 32 * TR_K * sizeof(T)];
+  __shared__ __align__(128) unsigned char s_zero[4 * TR_TPW_MAX * 32 * TR_K * sizeof(T)];
   __shared__ int s_next;
   bool fill_pending = false;
   if (threadIdx.x == 0) s_next = 0;
@@ -396,8 +398,8 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
   const bool decoupled = a.bulk_fill == 2;
   const bool dyn = fill_pending && decoupled && !LOGLIKE;
   if (fill_pending && (warp == 0 || !decoupled)) {
-    const int64_t cbase = (int64_t)tile * nwarps * (32 * K);
-    const int64_t clen = min((int64_t)nwarps * (32 * K), a.n_times - cbase);
+    const int64_t cbase = (int64_t)tile * (nwarps * a.tpw) * (32 * K);
+    const int64_t clen = min((int64_t)(nwarps * a.tpw) * (32 * K), a.n_times - cbase);
     if (clen > 0) {
       const unsigned bytes = (unsigned)(clen * (int64_t)sizeof(T));
       const unsigned src = (unsigned)__cvta_generic_to_shared(s_zero);
@@ -457,17 +459,27 @@ k_transit_partials(const __grid_constant__ TrArgs<T> a) {
     // ---- fill: stages A and B until 32 samples are queued or the run has no tile left ------------
     while (more && qn < 32) {
       if (!have_tile) {
-        int wt = warp;
-        if (dyn) {  // (run == 1: the CTA's nwarps tiles, whoever is free)
-          if (lane == 0) wt = atomicAdd(&s_next, 1);
-          wt = __shfl_sync(0xffffffffu, wt, 0);
+        if (a.bulk_fill) {  // the CTA's nwarps * tpw consecutive tiles: whoever is free (dyn), or warp + nwarps * r
+          int wt = warp + nwarps * r_next;
+          if (dyn) {
+            if (lane == 0) wt = atomicAdd(&s_next, 1);
+            wt = __shfl_sync(0xffffffffu, wt, 0);
+          } else {
+            ++r_next;
+          }
+          wbase = ((int64_t)tile * (nwarps * a.tpw) + wt) * (32 * K);
+          if (wt >= nwarps * a.tpw || wbase >= a.n_times) {
+            more = false;
+            break;
+          }
+        } else {
+          wbase = (((int64_t)r_next * a.n_tiles + tile) * nwarps + warp) * (32 * K);
+          if (r_next >= a.run || wbase >= a.n_times) {
+            more = false;
+            break;
+          }
+          ++r_next;
         }
-        wbase = (((int64_t)r_next * a.n_tiles + tile) * nwarps + wt) * (32 * K);
-        if (wt >= nwarps || r_next >= a.run || wbase >= a.n_times) {
-          more = false;
-          break;
-        }
-        if (!dyn) ++r_next;
         valid = 0;
         double tmin = 1e300, tmax = -1e300;
 #pragma unroll
@@ -947,7 +959,7 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
   int spc = TR_MAX_SETS;
   if (spc > n_sets) spc = n_sets;
   const int64_t n_groups = (n_sets + spc - 1) / spc;
-  const int64_t n_ctas = n_tiles * n_groups;
+  int64_t n_ctas = n_tiles * n_groups;
   if (n_ctas > 2147483647LL) return fail(JXP_ERR_BAD_SHAPE, "jxp_transit_partials: grid too large");
   a.bodies = d_bodies;
   a.t = t;
@@ -965,6 +977,22 @@ static int launch_transit(const double* theta, int32_t n_sets, const double* sta
                  (n_times * (int64_t)sizeof(T)) % 16 == 0 && ((uintptr_t)flux & 15) == 0 && ((uintptr_t)partials & 15) == 0)
                     ? (((sizeof(T) == 8) != ((dev_options() & JXP_DEV_BULK_FILL_SWAP) != 0)) ? 2 : 1)
                     : 0;
+  a.tpw = 1;
+  if (a.bulk_fill) {
+    // (development option: two warp tiles per warp -- 4 KB / 2 KB copies, queued samples carried from one tile to the
+    // next -- measured slower on config 5: 10.13 against 9.96 ms in double, 6.0-6.8 against 5.84 ms in float)
+    int tpw = 1;
+    {
+      const int v = (int)JXP_DEV_GET_TR_TPW(dev_options());
+      if (v >= 1 && v <= TR_TPW_MAX) tpw = v;
+    }
+    const int nw = threads / 32;
+    while (tpw > 1 && ((n_wtiles + nw * tpw - 1) / (nw * tpw)) * ((n_sets + TR_MAX_SETS - 1) / TR_MAX_SETS) < 8 * sms) --tpw;
+    a.tpw = tpw;
+    n_tiles = (n_wtiles + nw * tpw - 1) / (nw * tpw);
+    a.n_tiles = (int)n_tiles;
+    n_ctas = n_tiles * n_groups;
+  }
   a.use_window = (flags & JXP_FLAG_NO_WINDOW) ? 0 : 1;
   a.flux = flux;
   a.partials = partials;

@@ -866,7 +866,7 @@ def test_transit_partials_bulk_zero_fill_matches_warp_stores():
             if (n_times * torch.empty(0, dtype=dt).element_size()) % 16:
                 continue  # (rows that are not 16-byte multiples take the warp-store fill anyway)
             outs = []
-            for mask in (0, _lib.JXP_DEV_BULK_FILL_SWAP, _lib.JXP_DEV_NO_BULK_FILL):
+            for mask in (0, _lib.JXP_DEV_BULK_FILL_SWAP, _lib.JXP_DEV_TR_TPW(2), _lib.JXP_DEV_NO_BULK_FILL):
                 fl = torch.full((n_sets * n_times + 64,), 7.0, dtype=dt, device="cuda")
                 pt = torch.full((n_sets * 8 * n_times + 64,), 7.0, dtype=dt, device="cuda")
                 with _lib.dev_options(mask):
@@ -876,8 +876,8 @@ def test_transit_partials_bulk_zero_fill_matches_warp_stores():
                 torch.cuda.synchronize()
                 assert bool(torch.all(fl[-64:] == 7.0)) and bool(torch.all(pt[-64:] == 7.0))
                 outs.append((fl, pt))
-            for o in outs[:2]:
-                assert torch.equal(o[0], outs[2][0]) and torch.equal(o[1], outs[2][1])
+            for o in outs[:-1]:
+                assert torch.equal(o[0], outs[-1][0]) and torch.equal(o[1], outs[-1][1])
             assert n_times < 4098 or float(outs[0][0][:-64].min()) < 0.0  # (some set transits)
             assert not bool(torch.any(outs[0][1][:-64] == 7.0)) and not bool(torch.any(outs[0][0][:-64] == 7.0))
 

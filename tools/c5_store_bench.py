@@ -12,7 +12,8 @@ wsb5 = int(lib.jxp_transit_workspace_bytes(ns5, nt5)); ws5 = torch.empty(wsb5, d
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for dt, nm in ((torch.float64, "f64"), (torch.float32, "f32")):
     fl = torch.empty((ns5, nt5), dtype=dt, device=dev); pt = torch.empty((ns5, 8, nt5), dtype=dt, device=dev)
-    for mask, what in ((0, "bulk-copy zero fill"), (_lib.JXP_DEV_BULK_FILL_SWAP, "bulk-copy zero fill, other mode"),
+    for mask, what in ((0, "bulk-copy zero fill"), (_lib.JXP_DEV_TR_TPW(2), "bulk-copy zero fill, two tiles per warp"),
+                       (_lib.JXP_DEV_BULK_FILL_SWAP, "bulk-copy zero fill, other mode"),
                        (_lib.JXP_DEV_NO_BULK_FILL, "warp-store zero fill")):
         best = 1e30
         with _lib.dev_options(mask):
