@@ -87,8 +87,8 @@ def workload_config(n_gpus, extra=None):
         "sets_per_gpu": N_SETS // max(n_gpus, 1),
         "n_times": N_TIMES,
         "n_bodies": 1,
-        "parallelism": f"set-sharded x{n_gpus} (no data-path collective; all-gather of 8 B per set per step)",
-        "cache": "L2 flushed between steps (256 MiB write); per-step CUDA events summed",
+        "parallelism": f"set-sharded x{n_gpus} (no data-path collective; all-gather of 8 B per set per step: see exchange)",
+        "cache": "L2 flushed between steps (256 MiB write); per-step CUDA events summed, the steps enqueued back to back",
     }
     if extra:
         cfg.update(extra)
@@ -374,7 +374,7 @@ def run_ours(args, rank, local_rank, world):
     from jaxoplanet_b200 import _array as A
     from jaxoplanet_b200 import _lib
     from jaxoplanet_b200 import workloads as W
-    from jaxoplanet_b200.distributed import log_likelihood_distributed, shard_range
+    from jaxoplanet_b200.distributed import log_likelihood_distributed, peer_gather_for, shard_range
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -423,28 +423,49 @@ def run_ours(args, rank, local_rank, world):
         e.record()
     torch.cuda.synchronize()
 
-    def make_step(problem, gathered):
+    # the exchange of a step: every rank's block of log-likelihoods to every rank -- peer stores over NVLink
+    # (jxp_peer_allgather_f64, one launch on the step's stream), NCCL's all-gather if the buffers cannot be shared
+    def make_step(problem, gathered, pg=None, offset=0):
         def step(flags=0):
             problem.call(y=y, sig=sig, flags=flags)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, problem.ll)
+                if pg is not None:
+                    pg.gather(problem.ll, offset)
+                else:
+                    dist.all_gather_into_tensor(gathered, problem.ll)
 
         return step
 
+    peer = peer_gather_for(N_SETS, dev) if world > 1 else None
+
+    step_events = []
+
     def timed_steps(step, n, flags=0, kernel_events=True):
+        """Sum of the per-step device times (CUDA events around every step, the L2 flush between steps outside
+        them).  Without the kernel events the n steps are enqueued back to back and the host waits once at the
+        end: at N > 1 the ranks then stay in step through the exchange itself instead of drifting apart by the
+        host's per-step jitter.  With them (one event pair inside the C-ABI call) every step is awaited."""
         tot, ktot = 0.0, 0.0
+        if not kernel_events:
+            while len(step_events) < 2 * n:
+                step_events.append(torch.cuda.Event(enable_timing=True))
+            for i in range(n):
+                flush_l2()
+                step_events[2 * i].record()
+                step(flags)
+                step_events[2 * i + 1].record()
+            torch.cuda.synchronize()
+            return sum(step_events[2 * i].elapsed_time(step_events[2 * i + 1]) for i in range(n)), 0.0
         for _ in range(n):
             flush_l2()
-            if kernel_events:
-                lib.jxp_profile_events(ctypes.c_void_p(kev0.cuda_event), ctypes.c_void_p(kev1.cuda_event))
+            lib.jxp_profile_events(ctypes.c_void_p(kev0.cuda_event), ctypes.c_void_p(kev1.cuda_event))
             ev0.record()
             step(flags)
             ev1.record()
             lib.jxp_profile_events(None, None)
             torch.cuda.synchronize()
             tot += ev0.elapsed_time(ev1)
-            if kernel_events:
-                ktot += kev0.elapsed_time(kev1)
+            ktot += kev0.elapsed_time(kev1)
         return tot, ktot
 
     # FP64 pipe peak, measured now (MEASURED_PEAKS.json has no FP64 figure)
@@ -464,7 +485,7 @@ def run_ours(args, rank, local_rank, world):
     fp64_peak = fma_peak("jxp_peak_fma_f64", torch.float64)
 
     # ---- value: device-resident inputs, the 4096 sets sharded over the ranks ---------------------
-    step = make_step(prob, ll_all)
+    step = make_step(prob, ll_all, peer, lo)
     warm = max(args.warmup, 3)
     timed_steps(step, warm, kernel_events=False)
     # which kernel dominates: with the per-set function tables (the default) k_walk_items, else k_walk_eval; the
@@ -512,13 +533,32 @@ def run_ours(args, rank, local_rank, world):
     points_per_step = N_SETS * n_times
     value = points_per_step / (ms_per_step * 1e-3)
 
+    # ---- the exchange: what was used, checked against NCCL's all-gather, and the step with NCCL beside it -----
+    exchange = None
+    if world > 1:
+        step_nccl = make_step(prob, ll_all)
+        step_nccl()
+        torch.cuda.synchronize()
+        exchange = {"kind": "ncclAllGather (torch.distributed)"}
+        if peer is not None:
+            got = peer.gather(prob.ll, lo).clone()
+            torch.cuda.synchronize()
+            timed_steps(step_nccl, 3, kernel_events=False)
+            barrier()
+            n_ms, _ = timed_steps(step_nccl, args.steps, kernel_events=False)
+            barrier()
+            exchange = {"kind": "peer stores over NVLink into CUDA-IPC exchange buffers + epoch flags, one launch per step "
+                                "(jxp_peer_allgather_f64)",
+                        "identical_to_nccl_all_gather": bool(torch.equal(got, ll_all)), "status": peer.status(),
+                        "ms_per_step_with_nccl_all_gather": max_over_ranks(n_ms) / args.steps}
+
     # ---- weak scaling as a second field (N > 1): 4096 sets per GPU, round 1's definition -----------
     weak = None
     if world > 1:
         pw, uw, _, _, _ = c3_inputs(seed=1 + rank)
         probw = Problem(pw, uw, t_h, dev)
         llw_all = torch.empty(world * N_SETS, dtype=torch.float64, device=dev)
-        stepw = make_step(probw, llw_all)
+        stepw = make_step(probw, llw_all, peer_gather_for(world * N_SETS, dev), rank * N_SETS)
         timed_steps(stepw, 3, kernel_events=False)
         barrier()
         w_ms, _ = timed_steps(stepw, args.steps, kernel_events=False)
@@ -602,8 +642,11 @@ def run_ours(args, rank, local_rank, world):
                   dt_.data_ptr(), n_times, 0.0, 0, 0, 10, 0, 0, 0, dy.data_ptr(), ds.data_ptr(), 0,
                   prob.ll.data_ptr(), prob.ws.data_ptr(), prob.wsb, stream())
         if world > 1:
-            dist.all_gather_into_tensor(ll_all, prob.ll)
-            hll.copy_(ll_all, non_blocking=True)
+            if peer is not None:
+                hll.copy_(peer.gather(prob.ll, lo), non_blocking=True)
+            else:
+                dist.all_gather_into_tensor(ll_all, prob.ll)
+                hll.copy_(ll_all, non_blocking=True)
         else:
             hll.copy_(prob.ll, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -725,7 +768,7 @@ def run_ours(args, rank, local_rank, world):
                 "c_abi": {"value": points_per_step / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
                           "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 from one pinned host arena "
                                   "(one H2D copy per step), pinned D2H of the log-likelihoods"}},
-        "weak": weak, "flux_all_gather": flux_gather,
+        "weak": weak, "exchange": exchange, "flux_all_gather": flux_gather,
         "gpu_launches": len(launches) * args.steps,
         "gpu_launches_per_step": launches,
         "clocks": clocks, "secondary": secondary,

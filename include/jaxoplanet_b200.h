@@ -383,6 +383,33 @@ int jxp_peak_fma_f64(double* sink, int32_t n_blocks, int32_t n_threads, int64_t 
 int jxp_peak_fma_f32(float* sink, int32_t n_blocks, int32_t n_threads, int64_t iters,
                      void* stream);
 
+/* ----------------------------------------------------------------------------------
+ * Peer-memory all-gather of per-set values between the ranks of one box (one process per GPU):
+ * the exchange step of the set-sharded path (the reference has no multi-device
+ * code -- under jax.pmap / sharding this is the all_gather XLA would insert after
+ * src/jaxoplanet/light_curves/limb_dark.py:62).  8 bytes per parameter set is pure latency for a
+ * collective library, so each rank stores its block into every rank's exchange buffer over
+ * NVLink and signals with an epoch flag (csrc/jxp_peer.cu).
+ *
+ *   jxp_peer_buffer_bytes(n_total)       size of one rank's exchange buffer
+ *   jxp_peer_alloc(bytes, &ptr, handle)  cudaMalloc + zero + 64-byte CUDA IPC handle to pass to the peers
+ *   jxp_peer_open(handle, &ptr)          map a peer's buffer (cudaIpcOpenMemHandle, peer access enabled)
+ *   jxp_peer_close / jxp_peer_free
+ *   jxp_peer_allgather_f64(src, n_local, offset, n_total, bufs[world], rank, world, epoch, stream)
+ *       src[0 .. n_local) -> element offset .. of every rank's buffer; returns (stream-ordered) when the
+ *       blocks of all ranks for this epoch have arrived in bufs[rank].  Epochs count up from 1, the same
+ *       on every rank; the gathered values of epoch e sit at bufs[rank] + 256 + (e & 1) * n_total * 8.
+ *   jxp_peer_status(own_buf, &status, stream)  0, or which peer a wait timed out on (5 s)
+ * ---------------------------------------------------------------------------------- */
+size_t jxp_peer_buffer_bytes(int64_t n_total);
+int jxp_peer_alloc(size_t bytes, void** ptr, void* handle_out);
+int jxp_peer_open(const void* handle, void** ptr);
+int jxp_peer_close(void* ptr);
+int jxp_peer_free(void* ptr);
+int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_t offset, int64_t n_total,
+                           const uint64_t* bufs, int32_t rank, int32_t world, uint64_t epoch, void* stream);
+int jxp_peer_status(const void* own_buf, uint64_t* status_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

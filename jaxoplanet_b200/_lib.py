@@ -116,6 +116,13 @@ SIGNATURES = {
     "jxp_interp_periodic_f32": (C.c_int, [_p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p]),
     "jxp_peak_fma_f64": (C.c_int, [_p, _i32, _i32, _i64, _p]),
     "jxp_peak_fma_f32": (C.c_int, [_p, _i32, _i32, _i64, _p]),
+    "jxp_peer_buffer_bytes": (_sz, [_i64]),
+    "jxp_peer_alloc": (C.c_int, [_sz, _p, _p]),
+    "jxp_peer_open": (C.c_int, [_p, _p]),
+    "jxp_peer_close": (C.c_int, [_p]),
+    "jxp_peer_free": (C.c_int, [_p]),
+    "jxp_peer_allgather_f64": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, C.c_uint64, _p]),
+    "jxp_peer_status": (C.c_int, [_p, _p, _p]),
 }
 
 _lib = None

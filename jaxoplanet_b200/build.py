@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libjxp_b200.so")
-SOURCES = ["jxp_kernels.cu", "jxp_partials.cu", "jxp_transit.cu", "jxp_walk.cu", "jxp_state.cu"]
+SOURCES = ["jxp_kernels.cu", "jxp_partials.cu", "jxp_transit.cu", "jxp_walk.cu", "jxp_state.cu", "jxp_peer.cu"]
 HEADERS = [
     os.path.join(CSRC, "jxp_scalar.cuh"),
     os.path.join(CSRC, "jxp_fastmath.cuh"),

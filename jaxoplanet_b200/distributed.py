@@ -3,7 +3,9 @@
 The hot path shards with no data-path communication: every (parameter set, time) point is
 independent and a set's log-likelihood only reduces over that set's own time axis
 (SURVEY.md 8e).  Rank g owns a contiguous block of sets; `t`, `y`, `sigma` are replicated.
-The only exchange is the all-gather of the per-set log-likelihoods (8 B per set).
+The only exchange is the all-gather of the per-set log-likelihoods (8 B per set): at that size a
+collective library is pure latency, so the ranks store their blocks straight into each other's
+exchange buffers over NVLink (`PeerGather`, csrc/jxp_peer.cu); NCCL is the fallback.
 """
 
 from __future__ import annotations
@@ -21,12 +23,127 @@ def shard_range(n_sets: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _RawCuda:
+    """A device pointer dressed as a CUDA array (zero-copy torch view of memory this package allocated itself)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(int(ptr), False), version=3, strides=None)
+
+
+class PeerGather:
+    """All-gather of float64 per-set values by peer stores over NVLink (jxp_peer_allgather_f64).
+
+    Every rank allocates one exchange buffer (CUDA IPC, mapped into every process of the box); `gather` is
+    ONE launch on the caller's stream: this rank's block is stored into all buffers, an epoch flag follows,
+    and the kernel returns when the blocks of all ranks have arrived.  The returned view (n_total,) stays valid
+    until the gather after the next one (the buffers are double-buffered by epoch parity).  Collective: every rank
+    constructs it and calls `gather` the same number of times."""
+
+    def __init__(self, n_total: int, device: torch.device):
+        import ctypes as C
+
+        from jaxoplanet_b200 import _lib
+
+        self._lib, self._C = _lib, C
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n_total, self.device, self.epoch = int(n_total), device, 0
+        lib = _lib.load()
+        nbytes = int(lib.jxp_peer_buffer_bytes(self.n_total))
+        own, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._opened, self.own = [], None
+        ok = True
+        try:
+            _lib.call("jxp_peer_alloc", nbytes, C.byref(own), C.addressof(handle))
+            self.own = int(own.value)
+        except Exception:  # noqa: BLE001 -- every rank must reach the collectives below
+            ok = False
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if ok else None)
+        self._bufs = (C.c_uint64 * self.world)()
+        if ok and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self._bufs[r] = self.own
+                    continue
+                try:
+                    ptr, hb = C.c_void_p(), (C.c_ubyte * 64).from_buffer_copy(h)
+                    _lib.call("jxp_peer_open", C.addressof(hb), C.byref(ptr))
+                    self._opened.append(int(ptr.value))
+                    self._bufs[r] = int(ptr.value)
+                except Exception:  # noqa: BLE001
+                    ok = False
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.ok = bool(int(flag.item()))
+        if not self.ok:
+            self.close()
+            return
+        self._views = [torch.as_tensor(_RawCuda(self.own + 256 + k * self.n_total * 8, self.n_total), device=device)
+                       for k in range(2)]
+
+    def gather(self, local: torch.Tensor, offset: int) -> torch.Tensor:
+        from jaxoplanet_b200 import _array as A
+
+        if local.dtype != torch.float64 or local.dim() != 1 or not local.is_contiguous():
+            raise ValueError("PeerGather.gather: contiguous 1-D float64 block expected")
+        self.epoch += 1
+        self._lib.call("jxp_peer_allgather_f64", local.data_ptr(), local.numel(), int(offset), self.n_total,
+                       self._C.addressof(self._bufs), self.rank, self.world, self.epoch, A.stream_ptr())
+        return self._views[self.epoch & 1]
+
+    def status(self) -> int:
+        """0, or 0x100 | peer if a wait for that peer's block timed out (the values are then incomplete)."""
+        from jaxoplanet_b200 import _array as A
+
+        st = self._C.c_uint64(0)
+        self._lib.call("jxp_peer_status", self.own, self._C.byref(st), A.stream_ptr())
+        return int(st.value)
+
+    def close(self):
+        """Collective: nobody unmaps or frees while a peer may still be storing."""
+        if dist.is_initialized():
+            torch.cuda.synchronize()
+            dist.barrier()
+        for p in self._opened:
+            self._lib.load().jxp_peer_close(p)
+        self._opened = []
+        if dist.is_initialized():
+            dist.barrier()
+        if self.own:
+            self._lib.load().jxp_peer_free(self.own)
+        self.own = None
+        self.ok = False
+
+
+_peer_gathers: dict = {}
+
+
+def peer_gather_for(n_total: int, device: torch.device):
+    """The PeerGather of (n_total, device), set up on first use by all ranks together; None when the backend is not
+    NCCL or the buffers could not be shared (the caller then takes the NCCL all-gather)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1 or dist.get_backend() != "nccl" or device.type != "cuda":
+        return None
+    key = (int(n_total), device.index)
+    if key not in _peer_gathers:
+        pg = PeerGather(n_total, device)
+        _peer_gathers[key] = pg if pg.ok else None
+    return _peer_gathers[key]
+
+
 def gather_sets(local: torch.Tensor, n_sets: int) -> torch.Tensor:
     """All-gather per-set values (leading axis = this rank's block) into the full (n_sets, ...)
-    tensor on every rank.  Ragged blocks are padded to the largest block for the collective."""
+    tensor on every rank: peer stores over NVLink for float64 vectors on CUDA (`PeerGather`), else the NCCL /
+    gloo collective (ragged blocks are padded to the largest block for it)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
+    if local.is_cuda and local.dtype == torch.float64 and local.dim() == 1:
+        pg = peer_gather_for(n_sets, local.device)
+        if pg is not None:
+            lo, _ = shard_range(n_sets, dist.get_rank(), world)
+            return pg.gather(local.contiguous(), lo).clone()
     sizes = [shard_range(n_sets, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
