@@ -13,3 +13,7 @@ timeout 300 $BCMD > gpurun_out/r2_${tag}_plain.json 2> gpurun_out/r2_${tag}_plai
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_${tag}_launches.csv $BCMD > gpurun_out/r2_${tag}_ncu_l.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kern -s 12 -c 1 -o gpurun_out/r2_${tag}_${kern} -f $BCMD > gpurun_out/r2_${tag}_ncu_f.log 2>&1
 tail -2 gpurun_out/r2_${tag}_ncu_f.log
+# K5 with rows stored (config-5 shape, 4096 sets): plain run, then one --set full capture
+timeout 300 python tools/k5_prof.py 4096 f64 > gpurun_out/r2_${tag}_k5.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_transit_partials -s 1 -c 1 -o gpurun_out/r2_${tag}_k5 -f python tools/k5_prof.py 4096 f64 >> gpurun_out/r2_${tag}_k5.log 2>&1
+tail -3 gpurun_out/r2_${tag}_k5.log
