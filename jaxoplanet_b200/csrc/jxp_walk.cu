@@ -1357,6 +1357,7 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
 #pragma unroll
     for (int j = 1; j < (int)WK_GROUP; ++j) Pj[j] = __shfl_sync(0xffffffffu, pex, j);
     const unsigned lo_first = __shfl_sync(0xffffffffu, its.y, 0);
+    const unsigned dofs = its.y - pex;  // (lanes 0..7) sample index minus stream position, constant along an item
     {
       if (set != cur_set) {
         __syncwarp();
@@ -1387,11 +1388,14 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
         for (int h = 0; h < NN; ++h) {
           const unsigned p = r0 + 32u * h + lane;
           have[h] = p < total;
-          unsigned k = 0;
-#pragma unroll
-          for (int j = 1; j < (int)WK_GROUP; ++j) k += p >= Pj[j] ? 1u : 0u;
-          const unsigned lo_k = __shfl_sync(0xffffffffu, its.y, k), p_k = __shfl_sync(0xffffffffu, pex, k);
-          ix[h] = have[h] ? lo_k + (p - p_k) : lo_first;  // (padding lanes read a valid sample and contribute zero)
+          // k = #{j : P_j <= p} (the P_j ascend): three compares of a binary search instead of seven
+          static_assert(WK_GROUP == 8, "binary search over eight items");
+          unsigned k = p >= Pj[4] ? 4u : 0u;
+          k += p >= (k ? Pj[6] : Pj[2]) ? 2u : 0u;
+          const unsigned m1 = (k & 4u) ? ((k & 2u) ? Pj[7] : Pj[5]) : ((k & 2u) ? Pj[3] : Pj[1]);
+          k += p >= m1 ? 1u : 0u;
+          const unsigned d_k = __shfl_sync(0xffffffffu, dofs, k);
+          ix[h] = have[h] ? p + d_k : lo_first;  // (padding lanes read a valid sample and contribute zero)
           ts[h] = __ldg(a.t + ix[h]);
           if (!FLUX) awv[h] = __ldg(a.aw + ix[h]);
         }
@@ -1432,7 +1436,9 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
         b2_step(3);
         // ---- the piece of the F table: binade of dx = (1 - r)^2 - b^2 inside the disk, else the ingress / egress
         // pieces in sqrt(b^2 - (1 - r)^2) / sqrt((1 + r)^2 - b^2)
-        bool intr[NN], ins[NN], want_edge = false;
+        // (the edge code runs for the 32-sample slices that have an ingress / egress lane only: a lane inside the
+        // disk keeps its binade piece either way, a lane out of transit reads the all-zero piece)
+        bool intr[NN], ins[NN];
         double q[NN];
         int pc[NN];
 #pragma unroll
@@ -1442,12 +1448,12 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
           ins[h] = q[h] > 0.0;
           const int jb = tb_binade(q[h]);
           pc[h] = jb < j0 ? j0 : (jb >= TB_NB ? TB_P_BAD : jb);
-          want_edge = want_edge || (intr[h] && !ins[h]);
           n_ld += intr[h] ? 1u : 0u;
         }
-        if (__any_sync(0xffffffffu, want_edge)) {
+        {
 #pragma unroll
           for (int h = 0; h < NN; ++h) {
+            if (!__any_sync(0xffffffffu, intr[h] && !ins[h])) continue;
             const bool ing = b2[h] < 1.0;
             const double w = fsqrt_pos(fmax(ing ? -q[h] : xe - b2[h], 1e-300));
             const int pe = ing ? TB_P_ING + (w >= ti1 ? 1 : 0) + (w >= ti2 ? 1 : 0) + (w >= ti3 ? 1 : 0)

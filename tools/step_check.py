@@ -1,24 +1,25 @@
-"""Config 3 step with and without programmatic dependent launches (device-timed, L2 flushed), 4096 and 512 sets."""
-import sys, ctypes, numpy as np, torch
+"""Config 3 step (device-timed, L2 flushed, no exchange) on the shard every rank of an N-GPU run would own."""
+import sys, numpy as np, torch
 sys.path.insert(0, ".")
 import bench
 from jaxoplanet_b200 import _lib, _array as A
 dev = A.device(); lib = _lib.load()
 p, u_h, t_h, noise, sigma = bench.c3_inputs(seed=1)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for n in (4096, 2048, 512):
-    prob = bench.Problem({k: v[:n] for k, v in p.items()}, u_h[:n], t_h, dev)
-    y = torch.as_tensor(1.0 + noise).to(dev); sig = torch.full((1,), sigma, dtype=torch.float64, device=dev)
-    ref = None
-    for mask, what in ((0, "default"), (0, "again"), (0, "default"), (0, "again")):
-        with _lib.dev_options(mask):
-            ts = []
-            for i in range(25):
-                flush.fill_(1)
-                ev0.record(); prob.call(y=y, sig=sig); ev1.record(); torch.cuda.synchronize()
-                if i >= 5: ts.append(ev0.elapsed_time(ev1))
-        ll = prob.ll.clone()
-        if ref is None: ref = ll
-        print(n, "sets", what, "ms/step mean", round(float(np.mean(ts)), 4), "min", round(min(ts), 4),
-              "identical" if torch.equal(ll, ref) else "DIFFERENT", flush=True)
+y = torch.as_tensor(1.0 + noise).to(dev); sig = torch.full((1,), sigma, dtype=torch.float64, device=dev)
+for world in (1, 2, 4, 8):
+    out = []
+    for rank in range(world):
+        lo, hi = rank * 4096 // world, (rank + 1) * 4096 // world
+        prob = bench.Problem({k: v[lo:hi] for k, v in p.items()}, u_h[lo:hi], t_h, dev)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(60)]
+        for i in range(30):
+            flush.fill_(1)
+            evs[2 * i].record(); prob.call(y=y, sig=sig); evs[2 * i + 1].record()
+        torch.cuda.synchronize()
+        ts = [evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(5, 30)]
+        st = prob.stats()
+        out.append((round(float(np.mean(ts)), 4), st["items"]))
+        del prob
+    print(f"{world} ranks: ms per step of each shard {[o[0] for o in out]} (max {max(o[0] for o in out)}; "
+          f"one GPU / N = {round(0.2776 / world, 4)}); in-window samples {[o[1] for o in out]}", flush=True)
