@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 out=jaxoplanet_b200/lib/variants; mkdir -p $out/$1.d
 name=$1; shift
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --fmad=true $*"
-for src in jxp_kernels jxp_partials jxp_transit jxp_walk jxp_state; do
+for src in jxp_kernels jxp_partials jxp_transit jxp_walk jxp_state jxp_peer; do
   nvcc $F -c jaxoplanet_b200/csrc/$src.cu -o $out/$name.d/$src.o &
 done
 wait
