@@ -1298,8 +1298,13 @@ struct WalkItemSmem {
   double tabs[TB_DOUBLES];
   double rec[WALK_REC];
 };
+// Measured on config 3 (step, ms; tools/gpu_ab.sh): 3 samples per lane at 4 / 5 / 6 CTAs per SM (128 / 96 / 80
+// registers) 0.2727 / 0.2748 / 0.2818 (2 samples per lane at 6), 4 samples per lane 0.281 (4 CTAs) / 0.292 (5).
 #ifndef JXP_ITEMS_MINB
-#define JXP_ITEMS_MINB 5
+#define JXP_ITEMS_MINB 4
+#endif
+#ifndef JXP_ITEMS_NN
+#define JXP_ITEMS_NN 3  // samples per lane and full round
 #endif
 
 // One warp walks whole transits: an item is a run of consecutive samples of one transit of one set, so t, y and
@@ -1523,20 +1528,25 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
           for (int h = 0; h < NN; ++h) csum = fma(acc[h], fma(acc[h], awv[h].y, -awv[h].x), csum);
         }
       };
-      const unsigned nfull = total / 96u, rem = total - 96u * nfull;
+      constexpr unsigned RS = 32u * JXP_ITEMS_NN;  // samples of a full round
+      const unsigned nfull = total / RS, rem = total - RS * nfull;
       const unsigned nrounds = nfull + (rem ? 1u : 0u), nsplit = (nrounds + 1u) / 2u;
       for (unsigned half = hg0 & 1u; half < (hg0 & 1u) + R; ++half) {
         csum = 0.0;
         const unsigned rend = half ? nrounds : nsplit;
         for (unsigned r = half ? nsplit : 0u; r < rend; ++r) {
           if (r < nfull)
-            round(std::integral_constant<int, 3>{}, 96u * r);
+            round(std::integral_constant<int, JXP_ITEMS_NN>{}, RS * r);
+#if JXP_ITEMS_NN >= 4
+          else if (rem > 96u)
+            round(std::integral_constant<int, 4>{}, RS * r);
+#endif
           else if (rem > 64u)
-            round(std::integral_constant<int, 3>{}, 96u * r);
+            round(std::integral_constant<int, 3>{}, RS * r);
           else if (rem > 32u)
-            round(std::integral_constant<int, 2>{}, 96u * r);
+            round(std::integral_constant<int, 2>{}, RS * r);
           else
-            round(std::integral_constant<int, 1>{}, 96u * r);
+            round(std::integral_constant<int, 1>{}, RS * r);
         }
         if (!FLUX) {
           // the half-group's partial sum (fixed shuffle tree); the claim is counted into its set below, and the lane
