@@ -1297,7 +1297,20 @@ __device__ __forceinline__ void walk_finish_items(const WalkItemArgs& a, unsigne
 struct WalkItemSmem {
   double tabs[TB_DOUBLES];
   double rec[WALK_REC];
+  double nb_b[32];     // samples of the current half-group next to the contact point: separation ...
+  unsigned nb_ix[32];  // ... and sample index (evaluated together behind the half-group's rounds)
 };
+
+// The inside-the-disk flux code for ONE sample: the rare path of k_walk_items for the samples right next to the
+// contact point b = 1 - r (dx below the last binade of the F table: 2e-4 of the samples).  They are parked in
+// shared memory during the rounds of a half-group and evaluated together behind them, one per lane, through this
+// call (not inline: the walk keeps its registers) -- instead of going through a list in HBM and a kernel of its
+// own behind the walk (k_walk_fix: 10-17 us at the end of every step, for 2 714 samples on config 3).
+__device__ __noinline__ double walk_inside_one(double b, double r, int lmax, double g0, double g1, double g2) {
+  double bb[1] = {b}, f[1];
+  ld_inside_u<1>(bb, r, lmax, g0, g1, g2, f);
+  return f[0];
+}
 // Measured on config 3 (step, ms; tools/gpu_ab.sh): 3 samples per lane at 4 / 5 / 6 CTAs per SM (128 / 96 / 80
 // registers) 0.2727 / 0.2748 / 0.2818 (2 samples per lane at 6), 4 samples per lane 0.281 (4 CTAs) / 0.292 (5).
 #ifndef JXP_ITEMS_MINB
@@ -1327,7 +1340,7 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
   const double* th = sm.tabs;
   const double* rec = sm.rec;
     unsigned cur_set = 0xffffffffu;
-  unsigned n_ld = 0;
+  unsigned n_ld = 0, n_inl = 0;
   // constants of the current set (registers; re-read when the set changes)
   double xs = 0.0, xe = 0.0, mc = 0.0, zsc = 0.0, zoff = 0.0, t0 = 0.0, tref = 0.0, per = 0.0, iper = 0.0;
   double ti1 = 0.0, ti2 = 0.0, ti3 = 0.0, te1 = 0.0;
@@ -1382,6 +1395,7 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
         t0 = rec[WK_T0]; tref = rec[WK_TREF]; per = rec[WK_PERIOD]; iper = rec[WK_INVP];
       }
       double csum = 0.0;
+      unsigned n_nb = 0;  // samples parked in sm.nb_* (warp-uniform)
       // one round: NN samples per lane from position r0 of the group's stream on
       auto round = [&](auto nn_tag, unsigned r0) {
         constexpr int NN = decltype(nn_tag)::value;
@@ -1493,6 +1507,28 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
           need_any = need_any || need[h];
         }
         if (__any_sync(0xffffffffu, need_any)) {
+          // inside the disk, below the last binade, safely below the contact point (what ld_inside_u needs: the
+          // same conditions as in k_walk_eval): the direct inside-the-disk code here and now
+          const double ar = fabs(rec[WK_RR]);
+          const bool r_ok = (ar < 1.0) && (ar >= 2e-6);
+          const double b_lim = (1.0 - ar) - 4e-15;
+#pragma unroll
+          for (int h = 0; h < NN; ++h) {
+            const double bq = fsqrt(fmax(b2[h], 0.0));
+            const bool ff = need[h] && ins[h] && pc[h] == TB_P_BAD && r_ok && bq < b_lim;
+            const unsigned mf = __ballot_sync(0xffffffffu, ff);
+            if (mf) {
+              const unsigned slot = n_nb + __popc(mf & ((1u << lane) - 1u));
+              if (ff && slot < 32u) {  // (a 33rd sample of one half-group takes the fix list)
+                sm.nb_b[slot] = bq;
+                sm.nb_ix[slot] = ix[h];
+                acc[h] = 0.0;
+                need[h] = false;
+              }
+              n_nb = min(n_nb + (unsigned)__popc(mf), 32u);
+            }
+          }
+          // what is left (a piece that did not converge): onto the fix list
 #pragma unroll
           for (int h = 0; h < NN; ++h) {
             const unsigned mn = __ballot_sync(0xffffffffu, need[h]);
@@ -1548,6 +1584,27 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
           else
             round(std::integral_constant<int, 1>{}, RS * r);
         }
+        if (n_nb) {  // the half-group's samples next to the contact point: one per lane, in the order they were parked
+          __syncwarp();
+          if ((unsigned)lane < n_nb) {
+            const unsigned ixn = sm.nb_ix[lane];
+            const int lmax = (int)((unsigned)__double_as_longlong(rec[WK_FLAGS]) >> 8);
+            const double F = walk_inside_one(sm.nb_b[lane], fabs(rec[WK_RR]), lmax, rec[WK_G0], rec[WK_G1], rec[WK_G2]);
+            if (FLUX) {
+              if (F != 0.0) {
+                const size_t o = (size_t)set * (size_t)a.n_times + ixn;
+                if (a.flux_sum) a.flux_sum[o] = (a.body > 0) ? a.flux_sum[o] + F : F;
+                if (a.flux) a.flux[o * (size_t)a.n_bodies + (size_t)a.body] = F;
+              }
+            } else {
+              const double2 awn = __ldg(a.aw + ixn);
+              csum = fma(F, fma(F, awn.y, -awn.x), csum);
+            }
+          }
+          n_inl += n_nb;  // (counted once per warp: see the end of the kernel)
+          n_nb = 0;
+          __syncwarp();
+        }
         if (!FLUX) {
           // the half-group's partial sum (fixed shuffle tree); the claim is counted into its set below, and the lane
           // that completes a set adds the set's partial sums in order
@@ -1564,7 +1621,8 @@ __global__ void __launch_bounds__(128, JXP_ITEMS_MINB) k_walk_items(const __grid
     }
   }
   n_ld = __reduce_add_sync(0xffffffffu, n_ld);
-  if (lane == 0) atomicAdd(a.tstat, (unsigned long long)n_ld);  // (k_walk_fix takes its samples off again)
+  if (lane == 0) atomicAdd(a.tstat, (unsigned long long)(n_ld - n_inl));  // (k_walk_fix takes its samples off again)
+  if (lane == 0 && n_inl) atomicAdd(a.tstat + 1, (unsigned long long)n_inl);  // (answered by the direct code)
   if (lane == 0) atomicAdd(a.counters + 1, (unsigned long long)n_ld);
 }
 
