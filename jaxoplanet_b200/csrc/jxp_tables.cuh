@@ -70,8 +70,14 @@ __device__ __forceinline__ double tb_pow2(int e) {  // 2^e, -1022 <= e <= 1023
 // The flux pieces of (r, u) and their header: WPS warps per parameter set (1 when there are sets enough to fill the
 // machine, 4 -- one CTA per set -- when there are not: the work of a set is a ~30 us chain for one warp).
 constexpr int TB_WARPS = 4;
+// 7 CTAs per SM (72 registers): the 4096 warps of config 3 are resident at once instead of in 1.7 waves of ~30 us
+// chains; step 0.2713 -> 0.2675 ms on 4096 sets, 0.0900 -> 0.0865 ms on 512 (4 / 5 / 6 / 8 / 10 CTAs per SM:
+// 0.2713 / 0.2708 / 0.2716 / 0.2690 / 0.2711; tools/gpu_ab.sh)
+#ifndef JXP_TAB_MINB
+#define JXP_TAB_MINB 7
+#endif
 template <int WPS>
-__global__ void __launch_bounds__(32 * TB_WARPS, 4) k_walk_tables(const __grid_constant__ TabArgs a) {
+__global__ void __launch_bounds__(32 * TB_WARPS, JXP_TAB_MINB) k_walk_tables(const __grid_constant__ TabArgs a) {
   constexpr int SPC = TB_WARPS / WPS;  // sets per CTA
   __shared__ double s_f[SPC][TB_NPIECE][TB_NC];  // node values
   __shared__ double s_c[SPC][TB_NPIECE][TB_NC];  // Chebyshev coefficients
