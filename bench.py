@@ -321,6 +321,53 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class NvmlSampler:
+    """Clocks and throttle reasons of this rank's GPU straight from NVML (nvidia_ml_py), sampled by the MAIN thread
+    while the GPU executes the timed steps and the host has nothing left to enqueue (timed_steps calls sample()
+    between its last launch and its wait).  The nvidia-smi loop of ClockSampler -- a second process polling the
+    driver every 50 ms -- showed up in the measurement at N > 1: its queries on rank 0 delay that rank's launches
+    and the exchange makes every rank wait for them (0.142 against 0.133 ms per step at 4 GPUs)."""
+
+    def __init__(self, torch_index):
+        import pynvml
+        import torch
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:  # noqa: BLE001
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_index)
+        self.samples = []
+
+    def sample(self, n=4, gap_s=3e-4):
+        nv = self.nv
+        for _ in range(n):
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # noqa: BLE001
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((sm, mx, int(rs)))
+            time.sleep(gap_s)
+
+    def result(self):
+        nv = self.nv
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML sample"]}
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r & bit for _, _, r in self.samples))
+        return {"sm_mhz": statistics.median([x[0] for x in self.samples]), "sm_max_mhz": max(x[1] for x in self.samples),
+                "samples": len(self.samples), "reasons": reasons,
+                "how": "NVML from the main thread while the GPU executes the timed steps (after the last launch, "
+                       "before the wait)"}
+
+
 # ------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------
@@ -438,9 +485,9 @@ def run_ours(args, rank, local_rank, world):
 
     peer = peer_gather_for(N_SETS, dev) if world > 1 else None
 
-    step_events = []
+    step_events, last_steps = [], []
 
-    def timed_steps(step, n, flags=0, kernel_events=True):
+    def timed_steps(step, n, flags=0, kernel_events=True, busy_hook=None):
         """Sum of the per-step device times (CUDA events around every step, the L2 flush between steps outside
         them).  Without the kernel events the n steps are enqueued back to back and the host waits once at the
         end: at N > 1 the ranks then stay in step through the exchange itself instead of drifting apart by the
@@ -449,13 +496,22 @@ def run_ours(args, rank, local_rank, world):
         if not kernel_events:
             while len(step_events) < 2 * n:
                 step_events.append(torch.cuda.Event(enable_timing=True))
+            if world > 1:
+                # one more untimed step in front, enqueued with the timed ones: the ranks leave the host barrier up to
+                # ~0.1 ms apart, and without it the first timed step of the early ranks is a wait for the late ones
+                # (0.27 ms against 0.133 at 4 GPUs); the exchange of this step lines the GPUs up
+                flush_l2()
+                step(flags)
             for i in range(n):
                 flush_l2()
                 step_events[2 * i].record()
                 step(flags)
                 step_events[2 * i + 1].record()
+            if busy_hook is not None:
+                busy_hook()  # (the GPU is executing the steps: clocks under load)
             torch.cuda.synchronize()
-            return sum(step_events[2 * i].elapsed_time(step_events[2 * i + 1]) for i in range(n)), 0.0
+            last_steps[:] = [step_events[2 * i].elapsed_time(step_events[2 * i + 1]) for i in range(n)]
+            return sum(last_steps), 0.0
         for _ in range(n):
             flush_l2()
             lib.jxp_profile_events(ctypes.c_void_p(kev0.cuda_event), ctypes.c_void_p(kev1.cuda_event))
@@ -492,18 +548,23 @@ def run_ours(args, rank, local_rank, world):
     # profile events bracket that launch (a development option that moves the event records, nothing else)
     st_w = prob.stats()
     tables_used = st_w["tab_evals"] > 0.5 * max(st_w["ld"], 1)
-    sampler = ClockSampler(local_rank)
+    sampler, nvml = None, None
     if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+        try:
+            nvml = NvmlSampler(local_rank)
+        except Exception:  # noqa: BLE001 -- no NVML bindings: the nvidia-smi loop
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            time.sleep(0.25)
     barrier()
     t_lo = time.perf_counter()
     # (no event records inside the call during the timed steps -- the pair around the dominant launch costs ~14 us of
     # a 0.28 ms step --: the dominant kernel's own duration is measured in separate steps right after)
-    tot_ms, _ = timed_steps(step, args.steps, kernel_events=False)
+    tot_ms, _ = timed_steps(step, args.steps, kernel_events=False, busy_hook=nvml.sample if nvml else None)
     barrier()
     t_hi = time.perf_counter()
-    clocks = sampler.stop(t_lo, t_hi) if rank == 0 else None
+    per_step_ms = [round(x, 4) for x in last_steps]
+    clocks = (nvml.result() if nvml else sampler.stop(t_lo, t_hi)) if rank == 0 else None
     st = prob.stats()
     walk_used = st["items"] > 0 and st["flags"] == 0
     lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_ITEMS if tables_used else 0)
@@ -543,14 +604,22 @@ def run_ours(args, rank, local_rank, world):
         if peer is not None:
             got = peer.gather(prob.ll, lo).clone()
             torch.cuda.synchronize()
-            timed_steps(step_nccl, 3, kernel_events=False)
-            barrier()
-            n_ms, _ = timed_steps(step_nccl, args.steps, kernel_events=False)
-            barrier()
+            # the step with either exchange, measured alternately under the same conditions
+            ab = {"peer": [], "nccl": []}
+            for _ in range(2):
+                for which, fn in (("peer", step), ("nccl", step_nccl)):
+                    timed_steps(fn, 3, kernel_events=False)
+                    barrier()
+                    x_ms, _ = timed_steps(fn, args.steps, kernel_events=False)
+                    barrier()
+                    ab[which].append(max_over_ranks(x_ms) / args.steps)
             exchange = {"kind": "peer stores over NVLink into CUDA-IPC exchange buffers + epoch flags, one launch per step "
                                 "(jxp_peer_allgather_f64)",
                         "identical_to_nccl_all_gather": bool(torch.equal(got, ll_all)), "status": peer.status(),
-                        "ms_per_step_with_nccl_all_gather": max_over_ranks(n_ms) / args.steps}
+                        "ms_per_step_with_peer_stores": min(ab["peer"]),
+                        "ms_per_step_with_nccl_all_gather": min(ab["nccl"]),
+                        "how": "the timed step with either exchange, 2 x K steps each, alternating, best of the two; "
+                               "measured right after the headline"}
 
     # ---- weak scaling as a second field (N > 1): 4096 sets per GPU, round 1's definition -----------
     weak = None
@@ -768,7 +837,7 @@ def run_ours(args, rank, local_rank, world):
                 "c_abi": {"value": points_per_step / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
                           "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 from one pinned host arena "
                                   "(one H2D copy per step), pinned D2H of the log-likelihoods"}},
-        "weak": weak, "exchange": exchange, "flux_all_gather": flux_gather,
+        "per_step_ms_rank0": per_step_ms, "weak": weak, "exchange": exchange, "flux_all_gather": flux_gather,
         "gpu_launches": len(launches) * args.steps,
         "gpu_launches_per_step": launches,
         "clocks": clocks, "secondary": secondary,
