@@ -542,6 +542,51 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- value: device-resident inputs, the 4096 sets sharded over the ranks ---------------------
     step = make_step(prob, ll_all, peer, lo)
+
+    # The timed step is the C-ABI call (and, at N > 1, the peer-store exchange behind it) captured ONCE into a CUDA
+    # graph and replayed: the launches of a step are fixed -- everything that depends on the data is decided on the
+    # device --, so a step is a launch-bound chain of seven small kernels and two streams, which is what graphs are for
+    # (an XLA program would run the custom call under a command buffer the same way).  The replay writes the same bits
+    # as the stream-ordered call (tests/test_cuda_graph.py; checked below).  Stream-ordered launches are timed beside
+    # it (`ms_per_step_stream_launches`).  Not with the NCCL fallback of the exchange, nor with --no-graph.
+    def capture(step_fn, pg):
+        try:
+            g, cs = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                step_fn()  # (warm-up on the capture stream; at N > 1 every rank runs this exchange)
+            torch.cuda.current_stream().wait_stream(cs)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=cs):
+                step_fn()
+            if pg is not None:
+                torch.cuda.synchronize()
+                pg.sync_epoch()  # (the captured launch was counted on the host but has not run)
+            return g
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench.py: CUDA graph capture failed ({exc!r}); stream-ordered launches", file=sys.stderr)
+            return None
+
+    graph = None
+    if not args.no_graph and (world == 1 or peer is not None):
+        step()
+        torch.cuda.synchronize()
+        ll_eager = prob.ll.clone()
+        graph = capture(step, peer)
+        if graph is not None:
+            prob.ll.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            if not torch.equal(prob.ll, ll_eager):
+                raise AssertionError("graph replay and stream-ordered call disagree")
+    flag = torch.tensor([1 if graph is not None else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # (all ranks or none: the exchange must be launched by everyone)
+    use_graph = bool(int(flag.item()))
+    step_eager = step
+    if use_graph:
+        def step(flags=0):  # noqa: F811
+            graph.replay()
     warm = max(args.warmup, 3)
     timed_steps(step, warm, kernel_events=False)
     # which kernel dominates: with the per-set function tables (the default) k_walk_items, else k_walk_eval; the
@@ -567,6 +612,16 @@ def run_ours(args, rank, local_rank, world):
     clocks = (nvml.result() if nvml else sampler.stop(t_lo, t_hi)) if rank == 0 else None
     st = prob.stats()
     walk_used = st["items"] > 0 and st["flags"] == 0
+    eager_ms = None
+    if use_graph:
+        if peer is not None:
+            peer.sync_epoch()
+        step = step_eager
+        timed_steps(step, 3, kernel_events=False)
+        barrier()
+        e_ms, _ = timed_steps(step, args.steps, kernel_events=False)
+        barrier()
+        eager_ms = max_over_ranks(e_ms) / args.steps
     lib.jxp_set_dev_options(_lib.JXP_DEV_PROFILE_ITEMS if tables_used else 0)
     n_k = min(args.steps, 10)
     _, k_ms = timed_steps(step, n_k)
@@ -627,7 +682,16 @@ def run_ours(args, rank, local_rank, world):
         pw, uw, _, _, _ = c3_inputs(seed=1 + rank)
         probw = Problem(pw, uw, t_h, dev)
         llw_all = torch.empty(world * N_SETS, dtype=torch.float64, device=dev)
-        stepw = make_step(probw, llw_all, peer_gather_for(world * N_SETS, dev), rank * N_SETS)
+        pgw = peer_gather_for(world * N_SETS, dev)
+        stepw = make_step(probw, llw_all, pgw, rank * N_SETS)
+        if use_graph and pgw is not None:  # (the same launch mode as the headline)
+            stepw()
+            gw = capture(stepw, pgw)
+            fw = torch.tensor([1 if gw is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(fw, op=dist.ReduceOp.MIN)
+            if int(fw.item()):
+                def stepw(flags=0):  # noqa: F811
+                    gw.replay()
         timed_steps(stepw, 3, kernel_events=False)
         barrier()
         w_ms, _ = timed_steps(stepw, args.steps, kernel_events=False)
@@ -837,6 +901,9 @@ def run_ours(args, rank, local_rank, world):
                 "c_abi": {"value": points_per_step / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
                           "path": "jxp_orbital_elements_f64 + jxp_system_light_curve_f64 from one pinned host arena "
                                   "(one H2D copy per step), pinned D2H of the log-likelihoods"}},
+        "launch": ("CUDA graph replay of the captured C-ABI call" + (" + peer-store exchange" if world > 1 else "")
+                   if use_graph else "stream-ordered launches through the C ABI"),
+        "ms_per_step_stream_launches": eager_ms,
         "per_step_ms_rank0": per_step_ms, "weak": weak, "exchange": exchange, "flux_all_gather": flux_gather,
         "gpu_launches": len(launches) * args.steps,
         "gpu_launches_per_step": launches,
@@ -1005,6 +1072,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time stream-ordered launches instead of a graph replay")
     args = ap.parse_args()
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))

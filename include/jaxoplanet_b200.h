@@ -399,7 +399,10 @@ int jxp_peak_fma_f32(float* sink, int32_t n_blocks, int32_t n_threads, int64_t i
  *       src[0 .. n_local) -> element offset .. of every rank's buffer; returns (stream-ordered) when the
  *       blocks of all ranks for this epoch have arrived in bufs[rank].  Epochs count up from 1, the same
  *       on every rank; the gathered values of epoch e sit at bufs[rank] + 256 + (e & 1) * n_total * 8.
- *   jxp_peer_status(own_buf, &status, stream)  0, or which peer a wait timed out on (5 s)
+ *       epoch = 0 (on every rank): the kernel counts the epochs itself in its buffer, so the launch carries
+ *       no argument that changes from call to call and can be replayed from a CUDA graph.
+ *   jxp_peer_status(own_buf, status[2], stream)  status[0] = 0, or which peer a wait timed out on (5 s);
+ *       status[1] = the last epoch this rank has started
  * ---------------------------------------------------------------------------------- */
 size_t jxp_peer_buffer_bytes(int64_t n_total);
 int jxp_peer_alloc(size_t bytes, void** ptr, void* handle_out);

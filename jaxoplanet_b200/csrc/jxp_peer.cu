@@ -7,7 +7,10 @@
 //
 // Exchange buffer of a rank (jxp_peer_buffer_bytes):
 //   [0, 128)    u64 flag[16]   flag[r] = the last epoch rank r has delivered into this buffer
-//   [128, 256)  u64 status     != 0: a wait timed out (the peer named in the low bits never delivered)
+//   [128, 136)  u64 status     != 0: a wait timed out (the peer named in the low bits never delivered)
+//   [136, 144)  u64 epoch      the last epoch this rank has started (epoch argument 0: the kernel counts itself,
+//                              so that the launch has no argument that changes from call to call and a CUDA graph
+//                              that holds it can be replayed)
 //   [256, ...)  2 x n_total doubles: the gathered values of even / odd epochs (double-buffered: a rank that is one
 //               step ahead writes the other half, and cannot get two steps ahead without this rank's next flag)
 #include <cstdint>
@@ -38,7 +41,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 __global__ void __launch_bounds__(1024) k_peer_allgather(const __grid_constant__ PeerArgs a) {
-  const size_t slot = PEER_HDR + (size_t)(a.epoch & 1ull) * (size_t)a.n_total * sizeof(double);
+  __shared__ unsigned long long s_epoch;
+  if (threadIdx.x == 0) {
+    unsigned long long* ctr = reinterpret_cast<unsigned long long*>(a.bufs[a.rank]) + 17;
+    const unsigned long long e = a.epoch ? a.epoch : *ctr + 1ull;
+    *ctr = e;
+    s_epoch = e;
+  }
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  const size_t slot = PEER_HDR + (size_t)(epoch & 1ull) * (size_t)a.n_total * sizeof(double);
   for (long long i = threadIdx.x; i < a.n_local; i += blockDim.x) {
     const double v = a.src[i];
     for (int r = 0; r < a.world; ++r)
@@ -50,13 +62,13 @@ __global__ void __launch_bounds__(1024) k_peer_allgather(const __grid_constant__
     const int r = (int)threadIdx.x;
     __threadfence_system();  // (cumulative: orders the stores of the whole CTA, observed through the barrier, before the flag)
     unsigned long long* theirs = reinterpret_cast<unsigned long long*>(a.bufs[r]) + a.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(a.epoch) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(a.bufs[a.rank]) + r;
     const unsigned long long t0 = globaltimer_ns();
     for (;;) {
       unsigned long long f;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(mine) : "memory");
-      if (f >= a.epoch) break;
+      if (f >= epoch) break;
       if (globaltimer_ns() - t0 > a.timeout_ns) {  // never hang the GPU on a peer that died
         reinterpret_cast<unsigned long long*>(a.bufs[a.rank])[16] = 0x100ull | (unsigned long long)r;
         break;
@@ -121,7 +133,7 @@ extern "C" int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_
   if (n_local < 0 || offset < 0 || offset + n_local > n_total)
     return fail(JXP_ERR_BAD_SHAPE, "jxp_peer_allgather: block [%lld, %lld) outside [0, %lld)", (long long)offset,
                 (long long)(offset + n_local), (long long)n_total);
-  if (epoch == 0) return fail(JXP_ERR_BAD_SHAPE, "jxp_peer_allgather: epochs start at 1");
+  // (epoch 0: the kernel counts the epochs itself, in its own buffer -- every rank must then do so)
   PeerArgs a;
   for (int r = 0; r < PEER_MAX_WORLD; ++r) a.bufs[r] = r < world ? bufs[r] : 0ull;
   for (int r = 0; r < world; ++r)
@@ -140,7 +152,8 @@ extern "C" int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_
 
 extern "C" int jxp_peer_status(const void* own_buf, uint64_t* status_host, void* stream) {
   if (!own_buf || !status_host) return fail(JXP_ERR_NULL_POINTER, "jxp_peer_status: null pointer");
-  cudaError_t e = cudaMemcpyAsync(status_host, static_cast<const unsigned char*>(own_buf) + 128, sizeof(uint64_t),
+  // status_host[0] = status word, status_host[1] = the last epoch started (two words)
+  cudaError_t e = cudaMemcpyAsync(status_host, static_cast<const unsigned char*>(own_buf) + 128, 2 * sizeof(uint64_t),
                                   cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   return e == cudaSuccess ? JXP_OK : fail(JXP_ERR_CUDA, "jxp_peer_status: %s", cudaGetErrorString(e));

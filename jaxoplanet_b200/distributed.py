@@ -88,18 +88,32 @@ class PeerGather:
 
         if local.dtype != torch.float64 or local.dim() != 1 or not local.is_contiguous():
             raise ValueError("PeerGather.gather: contiguous 1-D float64 block expected")
+        # (epoch argument 0: the kernel counts the epochs in its buffer -- the launch can be captured into a CUDA
+        # graph and replayed; `self.epoch` mirrors the count for the calls made through here, see sync_epoch)
         self.epoch += 1
         self._lib.call("jxp_peer_allgather_f64", local.data_ptr(), local.numel(), int(offset), self.n_total,
-                       self._C.addressof(self._bufs), self.rank, self.world, self.epoch, A.stream_ptr())
+                       self._C.addressof(self._bufs), self.rank, self.world, 0, A.stream_ptr())
         return self._views[self.epoch & 1]
+
+    def _status2(self):
+        from jaxoplanet_b200 import _array as A
+
+        st = (self._C.c_uint64 * 2)()
+        self._lib.call("jxp_peer_status", self.own, self._C.addressof(st), A.stream_ptr())
+        return int(st[0]), int(st[1])
 
     def status(self) -> int:
         """0, or 0x100 | peer if a wait for that peer's block timed out (the values are then incomplete)."""
-        from jaxoplanet_b200 import _array as A
+        return self._status2()[0]
 
-        st = self._C.c_uint64(0)
-        self._lib.call("jxp_peer_status", self.own, self._C.byref(st), A.stream_ptr())
-        return int(st.value)
+    def sync_epoch(self) -> int:
+        """After replays of a CUDA graph that holds a gather (launches this object did not see): take the epoch
+        count from the device.  Returns it; `latest()` is then the view of the last gather."""
+        self.epoch = self._status2()[1]
+        return self.epoch
+
+    def latest(self) -> torch.Tensor:
+        return self._views[self.epoch & 1]
 
     def close(self):
         """Collective: nobody unmaps or frees while a peer may still be storing."""

@@ -18,7 +18,6 @@ def test_peer_entry_points_check_their_arguments():
                  (src, 1, 0, 2, C.addressof(bufs), 2, 2, 1, None),           # rank outside the world
                  (src, 1, 0, 2, C.addressof(bufs), 0, 17, 1, None),          # more ranks than the flag block holds
                  (src, 3, 0, 2, C.addressof(bufs), 0, 2, 1, None),           # block outside the total
-                 (src, 1, 0, 2, C.addressof(bufs), 0, 2, 0, None),           # epochs start at 1
                  (src, 1, 0, 2, C.addressof(bufs), 0, 2, 1, None)):          # no buffer mapped for rank 0
         with pytest.raises(_lib.JxpError):
             _lib.call("jxp_peer_allgather_f64", *args)
