@@ -550,23 +550,11 @@ def run_ours(args, rank, local_rank, world):
     # as the stream-ordered call (tests/test_cuda_graph.py; checked below).  Stream-ordered launches are timed beside
     # it (`ms_per_step_stream_launches`).  Not with the NCCL fallback of the exchange, nor with --no-graph.
     def capture(step_fn, pg):
-        cs = torch.cuda.Stream()
-        cs.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(cs):
-            step_fn()  # (warm-up on the capture stream; at N > 1 every rank runs this exchange, whatever follows)
-        torch.cuda.current_stream().wait_stream(cs)
-        torch.cuda.synchronize()
-        g = None
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cs):
-                step_fn()
-        except Exception as exc:  # noqa: BLE001
-            print(f"bench.py: CUDA graph capture failed ({exc!r}); stream-ordered launches", file=sys.stderr)
-            g = None
-        if pg is not None:
-            torch.cuda.synchronize()
-            pg.sync_epoch()  # (the captured launch was counted on the host but has not run)
+        from jaxoplanet_b200.graphs import capture as capture_call
+
+        g = capture_call(step_fn, after_capture=pg.sync_epoch if pg is not None else None)
+        if g is None:
+            print("bench.py: CUDA graph capture failed; stream-ordered launches", file=sys.stderr)
         return g
 
     graph = None

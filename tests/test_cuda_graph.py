@@ -9,16 +9,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _capture(fn):
-    import torch
+    from jaxoplanet_b200.graphs import capture
 
-    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        fn()
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    with torch.cuda.graph(g, stream=s):
-        fn()
+    g = capture(fn)
+    assert g is not None
     return g
 
 
