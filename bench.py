@@ -922,15 +922,17 @@ def secondary_configs(dev, lib, ev0, ev1, rank, world, fp64_peak, max_over_ranks
     except Exception:
         pass
 
-    def best_of(fn, n=3):
+    def best_of(fn, n=3, warm=5):
+        # (five untimed runs first: on freshly allocated output buffers the float K5 takes 6.7 ms for its first four
+        # runs and 5.9 ms from the fifth on -- tools/k5_f32_order.py --, whatever ran before)
         best = 1e30
         barrier()
-        for i in range(n + 1):
+        for i in range(warm + n):
             ev0.record()
             fn()
             ev1.record()
             torch.cuda.synchronize()
-            if i:
+            if i >= warm:
                 best = min(best, ev0.elapsed_time(ev1))
         return max_over_ranks(best)
 
