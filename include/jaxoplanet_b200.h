@@ -395,12 +395,13 @@ int jxp_peak_fma_f32(float* sink, int32_t n_blocks, int32_t n_threads, int64_t i
  *   jxp_peer_alloc(bytes, &ptr, handle)  cudaMalloc + zero + 64-byte CUDA IPC handle to pass to the peers
  *   jxp_peer_open(handle, &ptr)          map a peer's buffer (cudaIpcOpenMemHandle, peer access enabled)
  *   jxp_peer_close / jxp_peer_free
- *   jxp_peer_allgather_f64(src, n_local, offset, n_total, bufs[world], rank, world, epoch, stream)
+ *   jxp_peer_allgather_f64(src, n_local, offset, n_total, bufs[world], rank, world, epoch, out, stream)
  *       src[0 .. n_local) -> element offset .. of every rank's buffer; returns (stream-ordered) when the
  *       blocks of all ranks for this epoch have arrived in bufs[rank].  Epochs count up from 1, the same
  *       on every rank; the gathered values of epoch e sit at bufs[rank] + 256 + (e & 1) * n_total * 8.
  *       epoch = 0 (on every rank): the kernel counts the epochs itself in its buffer, so the launch carries
  *       no argument that changes from call to call and can be replayed from a CUDA graph.
+ *       out (optional): the n_total gathered values are also copied there by the same launch.
  *   jxp_peer_status(own_buf, status[2], stream)  status[0] = 0, or which peer a wait timed out on (5 s);
  *       status[1] = the last epoch this rank has started
  * ---------------------------------------------------------------------------------- */
@@ -410,7 +411,8 @@ int jxp_peer_open(const void* handle, void** ptr);
 int jxp_peer_close(void* ptr);
 int jxp_peer_free(void* ptr);
 int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_t offset, int64_t n_total,
-                           const uint64_t* bufs, int32_t rank, int32_t world, uint64_t epoch, void* stream);
+                           const uint64_t* bufs, int32_t rank, int32_t world, uint64_t epoch, double* out,
+                           void* stream);
 int jxp_peer_status(const void* own_buf, uint64_t* status_host, void* stream);
 
 #ifdef __cplusplus

@@ -121,7 +121,7 @@ SIGNATURES = {
     "jxp_peer_open": (C.c_int, [_p, _p]),
     "jxp_peer_close": (C.c_int, [_p]),
     "jxp_peer_free": (C.c_int, [_p]),
-    "jxp_peer_allgather_f64": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, C.c_uint64, _p]),
+    "jxp_peer_allgather_f64": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, C.c_uint64, _p, _p]),
     "jxp_peer_status": (C.c_int, [_p, _p, _p]),
 }
 

@@ -28,6 +28,7 @@ constexpr size_t PEER_HDR = 256;
 struct PeerArgs {
   unsigned long long bufs[PEER_MAX_WORLD];  // every rank's exchange buffer as mapped into THIS process
   const double* src;
+  double* out;  // optional: the gathered values copied out of the exchange buffer (n_total doubles), or nullptr
   long long n_local, offset, n_total;
   int rank, world;
   unsigned long long epoch;
@@ -77,6 +78,10 @@ __global__ void __launch_bounds__(1024) k_peer_allgather(const __grid_constant__
     }
   }
   __syncthreads();
+  if (a.out != nullptr) {  // (the flags were read with acquire semantics; the values bypass L1)
+    const double* got = reinterpret_cast<const double*>(a.bufs[a.rank] + slot);
+    for (long long i = threadIdx.x; i < a.n_total; i += blockDim.x) a.out[i] = __ldcg(got + i);
+  }
 }
 }  // namespace
 
@@ -126,7 +131,7 @@ extern "C" int jxp_peer_free(void* ptr) {
 
 extern "C" int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_t offset, int64_t n_total,
                                       const uint64_t* bufs, int32_t rank, int32_t world, uint64_t epoch,
-                                      void* stream) {
+                                      double* out, void* stream) {
   if (!src || !bufs) return fail(JXP_ERR_NULL_POINTER, "jxp_peer_allgather: null pointer");
   if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world)
     return fail(JXP_ERR_BAD_SHAPE, "jxp_peer_allgather: rank %d of %d (at most %d ranks)", rank, world, PEER_MAX_WORLD);
@@ -139,6 +144,7 @@ extern "C" int jxp_peer_allgather_f64(const double* src, int64_t n_local, int64_
   for (int r = 0; r < world; ++r)
     if (!a.bufs[r]) return fail(JXP_ERR_NULL_POINTER, "jxp_peer_allgather: no buffer for rank %d", r);
   a.src = src;
+  a.out = out;
   a.n_local = n_local;
   a.offset = offset;
   a.n_total = n_total;

@@ -18,6 +18,8 @@
 //                         jax.jvp / jax.grad of the above             orbits/keplerian.py:262-340, core/kepler.py:59-79
 //   JxpOrbitalElementsF64 OrbitalBody.__init__                        src/jaxoplanet/orbits/keplerian.py:262-340
 //   JxpOrbitState*        OrbitalBody.position / velocity families    src/jaxoplanet/orbits/keplerian.py:366-637
+//   JxpPeerAllGatherF64   (no counterpart: the all_gather XLA inserts behind light_curves/limb_dark.py:62 when the
+//                         parameter sets are sharded over devices) -- peer stores over NVLink, csrc/jxp_peer.cu
 //   JxpTransitOrbit*      light_curve(TransitOrbit | TTVOrbit, *u)(t) src/jaxoplanet/orbits/transit.py:93-107, ttv.py:194-225
 //   JxpInterpPeriodic*    transforms.interpolate(...)(t)              src/jaxoplanet/light_curves/transforms.py:163-183
 //
@@ -345,6 +347,23 @@ ffi::Error OrbitalElementsF64(cudaStream_t s, Buf<ffi::F64> elements, Out<ffi::F
 }
 
 // ---------------------------------------------------------------------------------------------
+// The exchange of the set-sharded path: local [n_local] -> gathered [n_total] on every rank.  The exchange buffers
+// (jxp_peer_alloc / jxp_peer_open, one per rank, set up once by the host program) come in as attributes: addresses
+// as mapped into THIS process, up to eight ranks.  The epoch is counted on the device (argument 0), so the call has
+// no state on the host and sits in a command buffer like any other.
+// ---------------------------------------------------------------------------------------------
+ffi::Error PeerAllGatherF64(cudaStream_t s, Buf<ffi::F64> local, Out<ffi::F64> gathered, int64_t offset, int64_t rank,
+                            int64_t world, int64_t buf0, int64_t buf1, int64_t buf2, int64_t buf3, int64_t buf4,
+                            int64_t buf5, int64_t buf6, int64_t buf7) {
+  if (world < 1 || world > 8) return bad("jxp_peer_allgather: 1..8 ranks through this handler");
+  const uint64_t bufs[8] = {(uint64_t)buf0, (uint64_t)buf1, (uint64_t)buf2, (uint64_t)buf3,
+                            (uint64_t)buf4, (uint64_t)buf5, (uint64_t)buf6, (uint64_t)buf7};
+  return status(jxp_peer_allgather_f64(local.typed_data(), static_cast<int64_t>(local.element_count()), offset,
+                                       static_cast<int64_t>(gathered->element_count()), bufs, (int32_t)rank,
+                                       (int32_t)world, 0, gathered->typed_data(), s));
+}
+
+// ---------------------------------------------------------------------------------------------
 // K8  positions and velocities: bodies [n_sets][12], r_scale / k_amp [n_sets] or [1],
 //     asc_node [n_sets][2] (cos, sin; pass has_asc_node = 0 and any [n_sets][2] array when the
 //     ascending node is not given), t [n_times] -> pos, vel [3][n_sets][n_times]
@@ -475,6 +494,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpTransitGradientPolyF64, TransitGradientPolyF64,
                               JXP_STREAM_SCRATCH.A64.A64.A64.A64.A64.R64.R64.Attr<int64_t>("gl_order")
                                   .Attr<int64_t>("flags"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpOrbitalElementsF64, OrbitalElementsF64, JXP_STREAM.A64.R64);
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpPeerAllGatherF64, PeerAllGatherF64,
+                              JXP_STREAM.A64.R64.Attr<int64_t>("offset").Attr<int64_t>("rank").Attr<int64_t>("world")
+                                  .Attr<int64_t>("buf0").Attr<int64_t>("buf1").Attr<int64_t>("buf2").Attr<int64_t>("buf3")
+                                  .Attr<int64_t>("buf4").Attr<int64_t>("buf5").Attr<int64_t>("buf6").Attr<int64_t>("buf7"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpOrbitStateF64, OrbitStateF64,
                               JXP_STREAM.A64.A64.A64.A64.A64.R64.R64.Attr<int64_t>("has_asc_node").Attr<int64_t>("flags"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(JxpOrbitStateF32, OrbitStateF32,

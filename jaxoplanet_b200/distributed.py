@@ -83,7 +83,9 @@ class PeerGather:
         self._views = [torch.as_tensor(_RawCuda(self.own + 256 + k * self.n_total * 8, self.n_total), device=device)
                        for k in range(2)]
 
-    def gather(self, local: torch.Tensor, offset: int) -> torch.Tensor:
+    def gather(self, local: torch.Tensor, offset: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """This rank's block -> every rank.  Returns `out` (contiguous float64, n_total values, written by the same
+        launch) if given, else a view of the exchange buffer that stays valid until the gather after next."""
         from jaxoplanet_b200 import _array as A
 
         if local.dtype != torch.float64 or local.dim() != 1 or not local.is_contiguous():
@@ -92,8 +94,8 @@ class PeerGather:
         # graph and replayed; `self.epoch` mirrors the count for the calls made through here, see sync_epoch)
         self.epoch += 1
         self._lib.call("jxp_peer_allgather_f64", local.data_ptr(), local.numel(), int(offset), self.n_total,
-                       self._C.addressof(self._bufs), self.rank, self.world, 0, A.stream_ptr())
-        return self._views[self.epoch & 1]
+                       self._C.addressof(self._bufs), self.rank, self.world, 0, A.ptr(out), A.stream_ptr())
+        return out if out is not None else self._views[self.epoch & 1]
 
     def _status2(self):
         from jaxoplanet_b200 import _array as A
@@ -157,7 +159,7 @@ def gather_sets(local: torch.Tensor, n_sets: int) -> torch.Tensor:
         pg = peer_gather_for(n_sets, local.device)
         if pg is not None:
             lo, _ = shard_range(n_sets, dist.get_rank(), world)
-            return pg.gather(local.contiguous(), lo).clone()
+            return pg.gather(local.contiguous(), lo, out=torch.empty(n_sets, dtype=torch.float64, device=local.device))
     sizes = [shard_range(n_sets, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

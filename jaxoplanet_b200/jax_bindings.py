@@ -41,6 +41,7 @@ TARGETS = {
     "JxpTransitPartialsPolyF64": "jxp_transit_partials_poly_f64",
     "JxpTransitGradientPolyF64": "jxp_transit_gradient_poly_f64",
     "JxpOrbitalElementsF64": "jxp_orbital_elements_f64",
+    "JxpPeerAllGatherF64": "jxp_peer_allgather_f64",
     "JxpOrbitStateF64": "jxp_orbit_state_f64", "JxpOrbitStateF32": "jxp_orbit_state_f32",
     "JxpTransitOrbitF64": "jxp_transit_orbit_f64", "JxpTransitOrbitF32": "jxp_transit_orbit_f32",
     "JxpInterpPeriodicF64": "jxp_interp_periodic_f64", "JxpInterpPeriodicF32": "jxp_interp_periodic_f32",
@@ -191,6 +192,17 @@ if available():
         elements = jnp.asarray(elements, dtype=jnp.float64)
         out = jax.ShapeDtypeStruct(elements.shape[:-1] + (12,), jnp.float64)
         return jax.ffi.ffi_call("jxp_orbital_elements_f64", out, vmap_method="sequential")(elements)
+
+    def peer_all_gather(local, *, offset, n_total, rank, world, bufs):
+        """The exchange of the set-sharded path (one process per GPU): this rank's block of per-set values -> the
+        (n_total,) vector on every rank, by peer stores over NVLink.  `bufs`: addresses of the ranks' exchange buffers
+        as mapped into this process (jaxoplanet_b200.distributed.PeerGather sets them up; at most eight)."""
+        register()
+        addr = [int(b) for b in bufs] + [0] * (8 - len(bufs))
+        out = jax.ShapeDtypeStruct((int(n_total),), jnp.float64)
+        return jax.ffi.ffi_call("jxp_peer_allgather_f64", out, has_side_effect=True)(
+            jnp.asarray(local, dtype=jnp.float64), offset=np.int64(offset), rank=np.int64(rank), world=np.int64(world),
+            **{f"buf{i}": np.int64(a) for i, a in enumerate(addr)})
 
     def _system(kind, bodies, u, t, extra, out, dtype, exposure_time, exp_order, num_samples, order):
         register()

@@ -13,12 +13,12 @@ def test_peer_entry_points_check_their_arguments():
     assert lib.jxp_peer_buffer_bytes(-1) == 0
     bufs = (C.c_uint64 * 2)(0, 0)
     src = C.c_void_p(8)
-    for args in ((None, 1, 0, 2, C.addressof(bufs), 0, 2, 1, None),          # null source
-                 (src, 1, 0, 2, None, 0, 2, 1, None),                        # null buffer table
-                 (src, 1, 0, 2, C.addressof(bufs), 2, 2, 1, None),           # rank outside the world
-                 (src, 1, 0, 2, C.addressof(bufs), 0, 17, 1, None),          # more ranks than the flag block holds
-                 (src, 3, 0, 2, C.addressof(bufs), 0, 2, 1, None),           # block outside the total
-                 (src, 1, 0, 2, C.addressof(bufs), 0, 2, 1, None)):          # no buffer mapped for rank 0
+    for args in ((None, 1, 0, 2, C.addressof(bufs), 0, 2, 1, None, None),          # null source
+                 (src, 1, 0, 2, None, 0, 2, 1, None, None),                        # null buffer table
+                 (src, 1, 0, 2, C.addressof(bufs), 2, 2, 1, None, None),           # rank outside the world
+                 (src, 1, 0, 2, C.addressof(bufs), 0, 17, 1, None, None),          # more ranks than the flag block holds
+                 (src, 3, 0, 2, C.addressof(bufs), 0, 2, 1, None, None),           # block outside the total
+                 (src, 1, 0, 2, C.addressof(bufs), 0, 2, 1, None, None)):          # no buffer mapped for rank 0
         with pytest.raises(_lib.JxpError):
             _lib.call("jxp_peer_allgather_f64", *args)
     with pytest.raises(_lib.JxpError):

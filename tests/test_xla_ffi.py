@@ -47,7 +47,7 @@ def test_ffi_handlers_type_check_link_and_export_every_target(tmp_path):
                 "jxp_transit_partials_poly_f64", "jxp_transit_poly_workspace_bytes",
                 "jxp_orbital_elements_f64", "jxp_orbit_state_f64", "jxp_orbit_state_f32",
                 "jxp_transit_orbit_light_curve_f64", "jxp_transit_orbit_light_curve_f32",
-                "jxp_interp_periodic_f64", "jxp_interp_periodic_f32", "jxp_last_error"):
+                "jxp_interp_periodic_f64", "jxp_interp_periodic_f32", "jxp_peer_allgather_f64", "jxp_last_error"):
         assert sym in used, sym
 
 
@@ -69,7 +69,7 @@ def test_stub_rejects_a_handler_that_does_not_match_its_binding(tmp_path):
 def test_jax_bindings_module_imports_without_jax_and_names_every_symbol():
     from jaxoplanet_b200 import jax_bindings as jb
 
-    assert len(set(jb.TARGETS.values())) == len(jb.TARGETS) == 23
+    assert len(set(jb.TARGETS.values())) == len(jb.TARGETS) == 24
     if not jb.available():
         assert not hasattr(jb, "kepler")  # nothing pretends to work without JAX
         cmd = jb.ffi_compile_command("/nonexistent/include", "/tmp/x.so")
