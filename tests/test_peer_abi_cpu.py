@@ -24,3 +24,16 @@ def test_peer_entry_points_check_their_arguments():
     with pytest.raises(_lib.JxpError):
         _lib.call("jxp_peer_open", None, None)
     assert lib.jxp_peer_close(None) == 0 and lib.jxp_peer_free(None) == 0
+
+
+def test_graph_helper_and_peer_gather_are_importable_without_a_gpu():
+    """Host-side modules of the multi-GPU / graph paths import on a machine without CUDA; nothing in them falls back
+    to the CPU: peer_gather_for answers None outside an NCCL process group, capture needs a CUDA stream."""
+    import torch
+
+    from jaxoplanet_b200 import distributed, graphs
+
+    assert callable(graphs.capture)
+    assert distributed.peer_gather_for(16, torch.device("cpu")) is None
+    x = torch.arange(5, dtype=torch.float64)
+    assert distributed.gather_sets(x, 5) is x  # (no process group: the block is the whole)
